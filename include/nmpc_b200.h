@@ -1,0 +1,139 @@
+/*
+ * nmpc_b200.h -- C ABI of the B200-native batched NMPC solver (libnmpc_b200.so).
+ *
+ * Drop-in boundary for ONE path of devsonni/MPC-Implementation: the per-step NLP solve
+ *     sol = solver(x0=, lbx=, ubx=, lbg=, ubg=, p=)            Python/NMPC_TT.py:358-365
+ * of the CasADi `Function` built by  ca.nlpsol('solver','ipopt',nlp_prob,opts)  (:250-267), plus
+ * the plant/target/warm-start shift around it (shift_timestep, :13-30) and the FOV-centre
+ * bookkeeping (:399-402).  Everything the reference derives symbolically from its SX graph
+ * (dynamics :139-148, rollout :160-167, cost :193-221, constraint rows :234-244) is compiled into
+ * the kernels; what the scripts edit in source (T, N, obstacles, weights) is the `nmpc_spec`.
+ *
+ * Conventions
+ *   - All vectors use CasADi's layouts: w = vec(U) column-major, w[6k+i] = U[i,k] (:247-248,:294);
+ *     g stage-major, rows [z, theta, X5, X6, X7, obs_1..obs_n] per stage k=0..N (:235-243);
+ *     p = [x(8); x_t; y_t; theta_t] (:350-353).
+ *   - Batches are instance-major: field[b][i].  Each field is its own array (structure of arrays
+ *     at field level); one warp solves one instance and reads its row with coalesced loads.
+ *   - FP64 throughout.  +-inf (or |b| >= 1e19) in lbg/ubg/lbx/ubx means "no bound" (:280-282).
+ *   - Every function returns 0 on success, non-zero on error (message via nmpc_last_error()).
+ *     Per-instance solver outcomes are DATA (status[], iters[]), never error returns -- the
+ *     reference never inspects IPOPT's status either (:358-367).
+ *   - Device pointers unless the name says _host.  Calls are asynchronous on `cuda_stream`
+ *     (a cudaStream_t cast to void*; NULL = default stream); the caller synchronises.
+ *   - One handle per (device, stream); calls on one handle are not re-entrant.
+ *   - There is no CPU fallback: nmpc_create fails if no sm_100 device is present.
+ */
+#ifndef NMPC_B200_H
+#define NMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMPC_NX 8
+#define NMPC_NU 6
+#define NMPC_NP 11
+#define NMPC_MAX_STAGES 32   /* N + 1 <= 32: one horizon stage per warp lane */
+#define NMPC_MAX_OBS 16
+
+/* per-instance return status (mirrors IPOPT's ApplicationReturnStatus names where one exists) */
+enum {
+  NMPC_SOLVE_SUCCEEDED = 0,
+  NMPC_MAXITER_EXCEEDED = 1,
+  NMPC_RESTORATION_NEEDED = 2,   /* line search failed; IPOPT would enter restoration (not implemented) */
+  NMPC_STEP_TOO_SMALL = 3,
+  NMPC_INVALID_NUMBER = 4,
+  NMPC_PERTURBATION_FAILED = 5
+};
+
+/* What the reference scripts hard-code in source.  Replaces the SX dict {'f','x','g','p'} and the
+ * opts dict handed to ca.nlpsol (NMPC_TT.py:250-267). */
+typedef struct nmpc_spec {
+  double T;            /* Euler step                           NMPC_TT.py:57   */
+  int32_t N;           /* horizon, N + 1 <= NMPC_MAX_STAGES    NMPC_TT.py:58   */
+  int32_t n_obs;       /* obstacle rows per stage              NMPC_TT.py:241-243 */
+  double w1, w2;       /* cost weights                         NMPC_TT.py:204-205 */
+  double vfov, hfov;   /* field of view                        NMPC_TT.py:201-202 */
+  /* IPOPT options the scripts set (NMPC_TT.py:257-265) or leave at default */
+  int32_t max_iter;    /* 100 */
+  int32_t scaling;     /* 1 = gradient-based NLP scaling (IPOPT default) */
+  double tol;          /* 1e-8 */
+  int32_t max_batch;   /* largest B any call will pass */
+  int32_t reserved;
+} nmpc_spec;
+
+typedef struct nmpc_handle nmpc_handle;
+
+/* ca.nlpsol(...)  (NMPC_TT.py:267): allocate the per-device workspace. */
+int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out);
+int nmpc_destroy(nmpc_handle* h);
+
+/* flags for nmpc_solve */
+#define NMPC_OBS_PER_INSTANCE 1u   /* obst is [B][n_obs][3] instead of [n_obs][3] */
+
+/* solver(x0,lbx,ubx,lbg,ubg,p)  (NMPC_TT.py:358-365), B instances at once.
+ *   p    [B][11]   x0  [B][6N]                       inputs
+ *   lbx, ubx [6N]; lbg, ubg [n_g]                    shared by the batch (as in every script)
+ *   obst [n_obs][3] = {cx, cy, r_uav + r_obs}        (x_o_j, y_o_j, UAV_r+obs_r of :224-243)
+ *   x [B][6N], f [B], g [B][n_g], lam_x [B][6N], lam_g [B][n_g]   outputs; g/lam_* may be NULL
+ *   status [B], iters [B]                            per-instance outcome (may be NULL)          */
+int nmpc_solve(nmpc_handle* h, int32_t B,
+               const double* p, const double* x0,
+               const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+               const double* obst, uint32_t flags,
+               double* x, double* f, double* g, double* lam_x, double* lam_g,
+               int32_t* status, int32_t* iters, void* cuda_stream);
+
+/* Same call with HOST buffers (what a CasADi-DM caller holds): H2D copies, solve, D2H copies and a
+ * stream synchronise happen inside. */
+int nmpc_solve_host(nmpc_handle* h, int32_t B,
+                    const double* p, const double* x0,
+                    const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                    const double* obst, uint32_t flags,
+                    double* x, double* f, double* g, double* lam_x, double* lam_g,
+                    int32_t* status, int32_t* iters);
+
+/* Function-level evaluation (what CasADi's generated nlp_f / nlp_g / nlp_grad_f / nlp_hess_l
+ * compute for IPOPT): at w [B][6N], p [B][11]
+ *   f [B], g [B][n_g], grad_f [B][6N],
+ *   jtv [B][6N]  = J(w)^T lam          (lam [B][n_g])
+ *   hv  [B][6N]  = Hess_w(sigma f + lam^T g) v          (v [B][6N])
+ * Any output may be NULL. */
+int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const double* obst, uint32_t flags,
+              double sigma, const double* lam, const double* v,
+              double* f, double* g, double* grad_f, double* jtv, double* hv, void* cuda_stream);
+
+/* shift_timestep (NMPC_TT.py:13-30) + FOV centre (:399-402) for B instances, in place:
+ *   state [B][8] <- state + T f_u(state, u[:,0]);  u_warm [B][6N] <- shift(x_sol) (repeat last);
+ *   target [B][3] <- target + T [v cos th, v sin th, om], target_vw [B][2] = (v, om) of this step;
+ *   fov_centre [B][2] (may be NULL) = (X_E, Y_E) of the NEW state. */
+int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* state, double* target,
+              double* u_warm, const double* target_vw, double* fov_centre, void* cuda_stream);
+
+/* statistics of the last nmpc_solve on this handle (device work counters, host copy) */
+typedef struct nmpc_stats {
+  int64_t kernel_launches;     /* kernels launched by the last call */
+  int64_t factorizations;      /* Riccati factorisations summed over the batch */
+  int64_t ls_trials;           /* line-search trial points summed over the batch */
+  int64_t soc_accepted;
+} nmpc_stats;
+int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out);   /* synchronises the handle's last stream */
+
+/* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
+ * dev_buf [B][rows][8] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials}; NULL disables. */
+int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);
+
+/* sizes implied by a spec */
+int32_t nmpc_n_w(const nmpc_spec* spec);   /* 6 N */
+int32_t nmpc_n_g(const nmpc_spec* spec);   /* (5 + n_obs)(N + 1) */
+
+const char* nmpc_last_error(void);   /* thread-local */
+const char* nmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

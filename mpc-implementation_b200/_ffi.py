@@ -1,0 +1,78 @@
+"""ctypes binding of include/nmpc_b200.h (libnmpc_b200.so, built in-tree under csrc/).
+
+There is deliberately no fallback: if the CUDA library is missing or cannot be loaded the import of
+`lib()` raises, and `nmpc_create` itself fails on a machine without an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+_CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = _CSRC / "libnmpc_b200.so"
+
+NMPC_OBS_PER_INSTANCE = 1
+
+STATUS_NAMES = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "Restoration_Needed",
+                3: "Search_Direction_Becomes_Too_Small", 4: "Invalid_Number_Detected", 5: "Perturbation_Failed"}
+
+
+class NmpcSpec(C.Structure):
+    """struct nmpc_spec (include/nmpc_b200.h)."""
+    _fields_ = [("T", C.c_double), ("N", C.c_int32), ("n_obs", C.c_int32),
+                ("w1", C.c_double), ("w2", C.c_double), ("vfov", C.c_double), ("hfov", C.c_double),
+                ("max_iter", C.c_int32), ("scaling", C.c_int32), ("tol", C.c_double),
+                ("max_batch", C.c_int32), ("reserved", C.c_int32)]
+
+
+class NmpcStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("factorizations", C.c_int64),
+                ("ls_trials", C.c_int64), ("soc_accepted", C.c_int64)]
+
+
+EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_eval", "nmpc_step",
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_n_w", "nmpc_n_g", "nmpc_last_error", "nmpc_version"]
+
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    args = ["make", "-C", str(_CSRC), "-s"] + (["-B"] if force else [])
+    subprocess.check_call(args)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+    L.nmpc_create.argtypes = [C.POINTER(NmpcSpec), C.c_int, C.POINTER(vp)]
+    L.nmpc_destroy.argtypes = [vp]
+    # pointers are passed as integers (device or host addresses)
+    L.nmpc_solve.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7 + [vp]
+    L.nmpc_solve_host.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7
+    L.nmpc_eval.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_uint32, C.c_double, vp, vp] + [vp] * 5 + [vp]
+    L.nmpc_step.argtypes = [vp, C.c_int32] + [vp] * 6 + [vp]
+    L.nmpc_get_stats.argtypes = [vp, C.POINTER(NmpcStats)]
+    L.nmpc_set_debug_log.argtypes = [vp, vp, C.c_int32]
+    L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
+    L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]
+    for name in EXPORTS:
+        getattr(L, name).restype = C.c_int
+    L.nmpc_last_error.restype = C.c_char_p
+    L.nmpc_version.restype = C.c_char_p
+    L.nmpc_n_w.restype = C.c_int32
+    L.nmpc_n_g.restype = C.c_int32
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().nmpc_last_error().decode()}")

@@ -1,0 +1,424 @@
+// nmpc_b200.cu -- kernels + C ABI (include/nmpc_b200.h) of the B200-native batched NMPC solver.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+//
+// Kernels
+//   nmpc_ipm_kernel   persistent, one warp per NLP instance, whole IPM loop in-kernel (nmpc_solve.cuh)
+//   nmpc_eval_kernel  function-level f / g / grad f / J^T lam / Hess_L v  (one warp per instance)
+//   nmpc_step_kernel  closed-loop shift (NMPC_TT.py:13-30) + FOV centre (:399-402), one thread per instance
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/nmpc_b200.h"
+#include "nmpc_solve.cuh"
+
+using namespace nmpc;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int WARPS_MAX = 4;
+
+__global__ void __launch_bounds__(WARPS_MAX * 32) nmpc_ipm_kernel(const SolveArgs A) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* ws = smem + (size_t)warp * A.ws_doubles;
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(A.counter, 1);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= A.B) break;
+    solve_instance(A, ws, b, lane);
+  }
+}
+
+struct EvalArgs {
+  Prob pr; int B;
+  const double *w, *p, *obs; int obs_per_instance;
+  double sigma; const double *lam, *v;
+  double *f, *g, *grad, *jtv, *hv;
+};
+
+__global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
+  const Prob& pr = A.pr;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= A.B) return;
+  const int N = pr.N, R = pr.R, S = pr.S, n_obs = pr.n_obs, nw = NU * N, ng = R * S;
+  const bool act = lane <= N, hasu = lane < N;
+  const double T = pr.T;
+  const double* pp = A.p + (size_t)b * NPAR;
+  double X0[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) X0[i] = pp[i];
+  const double xt = pp[8], yt = pp[9];
+  double u[6], vv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { u[i] = hasu ? A.w[(size_t)b * nw + NU * lane + i] : 0.0; vv[i] = (hasu && A.v) ? A.v[(size_t)b * nw + NU * lane + i] : 0.0; }
+  const double* obs = A.obs + (A.obs_per_instance ? (size_t)b * 3 * n_obs : 0);
+  Stage st;
+  rollout(pr, X0, u, lane, st);
+  const double tv = hasu ? T * u[0] : 0.0;
+  const double e03 = -tv * st.cps * st.sth, e13 = -tv * st.sps * st.sth, e23 = tv * st.cth, e04 = -tv * st.sps * st.cth, e14 = tv * st.cps * st.cth;
+  auto adjoint = [&](const double* a, double* lamn) {
+    double lam[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i == 3 || i == 4) continue;
+      lam[i] = rscan_incl(act ? a[i] : 0.0, lane); lamn[i] = shfl_next(lam[i], lane);
+    }
+    lam[3] = rscan_incl((act ? a[3] : 0.0) + e03 * lamn[0] + e13 * lamn[1] + e23 * lamn[2], lane); lamn[3] = shfl_next(lam[3], lane);
+    lam[4] = rscan_incl((act ? a[4] : 0.0) + e04 * lamn[0] + e14 * lamn[1], lane); lamn[4] = shfl_next(lam[4], lane);
+  };
+  auto Bt = [&](const double* lamn, double* out) {
+    out[0] = T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]);
+#pragma unroll
+    for (int r = 1; r < 6; ++r) out[r] = T * lamn[r + 2];
+  };
+  double gl[6], Hl[21];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) gl[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) Hl[i] = 0.0;
+  double l = 0.0;
+  if (hasu) l = stage_cost_d2(pr, st.X, xt, yt, gl, Hl);
+  const double fsum = warp_sum(l);
+  if (lane == 0 && A.f) A.f[b] = fsum;
+  if (act && A.g) {
+    double* go = A.g + (size_t)b * ng + lane * R;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) go[r] = st.X[box_state(r)];
+    for (int jn = 0; jn < n_obs; ++jn) {
+      const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
+      go[5 + jn] = obs[3 * jn + 2] - sqrt(dx_ * dx_ + dy_ * dy_);
+    }
+  }
+  double a[8], lamn[8], out[6];
+  if (A.grad) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
+    adjoint(a, lamn); Bt(lamn, out);
+    if (hasu) for (int i = 0; i < 6; ++i) A.grad[(size_t)b * nw + NU * lane + i] = out[i];
+  }
+  const double* lm = A.lam ? A.lam + (size_t)b * ng + lane * R : nullptr;
+  auto gt_lam = [&](double* acc) {   // acc += G_k^T lam_k
+    if (act && lm) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) acc[box_state(r)] += lm[r];
+      for (int jn = 0; jn < n_obs; ++jn) {
+        const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
+        const double iD = 1.0 / sqrt(dx_ * dx_ + dy_ * dy_);
+        acc[0] += -lm[5 + jn] * dx_ * iD; acc[1] += -lm[5 + jn] * dy_ * iD;
+      }
+    }
+  };
+  if (A.jtv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.0;
+    gt_lam(a);
+    adjoint(a, lamn); Bt(lamn, out);
+    if (hasu) for (int i = 0; i < 6; ++i) A.jtv[(size_t)b * nw + NU * lane + i] = out[i];
+  }
+  if (A.hv) {
+    // adjoint of the Lagrangian sigma f + lam^T g
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) a[cost_state(v)] = A.sigma * gl[v];
+    gt_lam(a);
+    adjoint(a, lamn);
+    // linearised rollout of the direction v
+    double dx[8];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) dx[3 + c] = scan_excl(hasu ? T * vv[c + 1] : 0.0, lane);
+    const double tvv = hasu ? T * vv[0] : 0.0;
+    dx[0] = scan_excl(e03 * dx[3] + e04 * dx[4] + tvv * st.cps * st.cth, lane);
+    dx[1] = scan_excl(e13 * dx[3] + e14 * dx[4] + tvv * st.sps * st.cth, lane);
+    dx[2] = scan_excl(e23 * dx[3] + tvv * st.sth, lane);
+    // w_x = Q dx + S^T v_u,  w_u = S dx
+    double wx[8], wu0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wx[i] = 0.0;
+    if (act) {
+      if (hasu && lane >= 1) {
+#pragma unroll
+        for (int uu = 0; uu < 6; ++uu)
+#pragma unroll
+          for (int v = 0; v < 6; ++v) wx[cost_state(uu)] += A.sigma * Hl[tri(uu, v)] * dx[cost_state(v)];
+      }
+      if (lm) for (int jn = 0; jn < n_obs; ++jn) {
+        const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
+        const double D = sqrt(dx_ * dx_ + dy_ * dy_), iD = 1.0 / D, nx = dx_ * iD, ny = dy_ * iD;
+        const double cur = -lm[5 + jn] * iD;
+        wx[0] += cur * ((1.0 - nx * nx) * dx[0] - nx * ny * dx[1]);
+        wx[1] += cur * (-nx * ny * dx[0] + (1.0 - ny * ny) * dx[1]);
+      }
+      if (hasu) {
+        const double L0 = T * lamn[0], L1 = T * lamn[1], L2 = T * lamn[2], v = u[0];
+        const double cc = st.cps * st.cth, sc = st.sps * st.cth, cs = st.cps * st.sth, ss = st.sps * st.sth;
+        const double q33 = -v * (L0 * cc + L1 * sc + L2 * st.sth), q44 = -v * (L0 * cc + L1 * sc), q34 = v * (L0 * ss - L1 * cs);
+        const double svt = -L0 * cs - L1 * ss + L2 * st.cth, svp = -L0 * sc + L1 * cc;
+        wx[3] += q33 * dx[3] + q34 * dx[4] + svt * vv[0];
+        wx[4] += q34 * dx[3] + q44 * dx[4] + svp * vv[0];
+        wu0 = svt * dx[3] + svp * dx[4];
+      }
+    }
+    adjoint(wx, lamn); Bt(lamn, out);
+    out[0] += wu0;
+    if (hasu) for (int i = 0; i < 6; ++i) A.hv[(size_t)b * nw + NU * lane + i] = out[i];
+  }
+}
+
+struct StepArgs {
+  double T, hv, hh; int N, B;
+  const double* x_sol; double *state, *target, *u_warm; const double* vw; double* fov;
+};
+
+__global__ void nmpc_step_kernel(const StepArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  const int nw = NU * A.N;
+  const double* xs = A.x_sol + (size_t)b * nw;
+  double* st = A.state + (size_t)b * NX;
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = st[i];
+  double sth, cth, sps, cps;
+  sincos(x[3], &sth, &cth); sincos(x[4], &sps, &cps);
+  const double v = xs[0];
+  x[0] += A.T * (v * cps * cth); x[1] += A.T * (v * sps * cth); x[2] += A.T * (v * sth);
+#pragma unroll
+  for (int i = 1; i < 6; ++i) x[i + 2] += A.T * xs[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st[i] = x[i];
+  // warm start: drop the first stage, repeat the last (NMPC_TT.py:20-23).  x_sol may alias u_warm.
+  double* uw = A.u_warm + (size_t)b * nw;
+  for (int k = 0; k < A.N - 1; ++k)
+    for (int i = 0; i < NU; ++i) uw[NU * k + i] = xs[NU * (k + 1) + i];
+  if (A.u_warm != A.x_sol)
+    for (int i = 0; i < NU; ++i) uw[NU * (A.N - 1) + i] = xs[NU * (A.N - 1) + i];
+  double* tg = A.target + (size_t)b * 3;
+  const double tv = A.vw[2 * b], tw = A.vw[2 * b + 1], th = tg[2];
+  tg[0] += A.T * tv * cos(th); tg[1] += A.T * tv * sin(th); tg[2] += A.T * tw;
+  if (A.fov) {
+    const double t6p = tan(x[6] + A.hv), t6m = tan(x[6] - A.hv), t5p = tan(x[5] + A.hh), t5m = tan(x[5] - A.hh);
+    const double a_p = (x[2] * t6p - x[2] * t6m) / 2, b_p = (x[2] * t5p - x[2] * t5m) / 2;
+    A.fov[2 * b] = x[0] + a_p + x[2] * t6m;
+    A.fov[2 * b + 1] = x[1] + b_p + x[2] * t5m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+struct nmpc_handle {
+  nmpc_spec spec; int device; int sm_count;
+  Prob pr; Opt opt;
+  int ws_doubles, warps, blocks_per_sm;
+  int* d_counter; unsigned long long* d_stats;
+  // staging for nmpc_solve_host
+  double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
+  int32_t *d_status, *d_iters; size_t obs_cap;
+  cudaStream_t own_stream, last_stream;
+  int64_t launches;
+  double* dbg; int dbg_rows;
+};
+
+extern "C" {
+
+const char* nmpc_last_error(void) { return g_err.c_str(); }
+const char* nmpc_version(void) { return "nmpc_b200 0.1 (sm_100a)"; }
+int32_t nmpc_n_w(const nmpc_spec* s) { return NU * s->N; }
+int32_t nmpc_n_g(const nmpc_spec* s) { return (5 + s->n_obs) * (s->N + 1); }
+
+int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
+  if (!spec || !out) return fail("nmpc_create: null argument");
+  if (spec->N < 1 || spec->N + 1 > NMPC_MAX_STAGES) return fail("nmpc_create: need 1 <= N <= 31");
+  if (spec->n_obs < 0 || spec->n_obs > NMPC_MAX_OBS) return fail("nmpc_create: need 0 <= n_obs <= 16");
+  if (!(spec->T > 0)) return fail("nmpc_create: T must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("nmpc_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("nmpc_create: bad device index");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("nmpc_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  CK(cudaSetDevice(device));
+  nmpc_handle* h = new (std::nothrow) nmpc_handle();
+  if (!h) return fail("nmpc_create: out of memory");
+  memset(h, 0, sizeof *h);
+  h->spec = *spec; h->device = device; h->sm_count = prop.multiProcessorCount;
+  h->pr.T = spec->T; h->pr.w1 = spec->w1; h->pr.w2 = spec->w2; h->pr.hv = 0.5 * spec->vfov; h->pr.hh = 0.5 * spec->hfov;
+  h->pr.N = spec->N; h->pr.n_obs = spec->n_obs; h->pr.R = 5 + spec->n_obs; h->pr.S = spec->N + 1;
+  h->opt = Opt();
+  h->opt.max_iter = spec->max_iter > 0 ? spec->max_iter : 100;
+  h->opt.scaling = spec->scaling; h->opt.tol = spec->tol > 0 ? spec->tol : 1e-8;
+  h->ws_doubles = ws_size(h->pr.S, h->pr.R, h->pr.n_obs);
+  const size_t per_warp = (size_t)h->ws_doubles * sizeof(double);
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  h->warps = WARPS_MAX;
+  while (h->warps > 1 && per_warp * h->warps > max_smem) --h->warps;
+  if (per_warp * h->warps > max_smem) { delete h; return fail("nmpc_create: horizon / obstacle count needs more shared memory than one SM has"); }
+  CK(cudaFuncSetAttribute(nmpc_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * h->warps)));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, nmpc_ipm_kernel, h->warps * 32, per_warp * h->warps));
+  if (h->blocks_per_sm < 1) { delete h; return fail("nmpc_create: kernel does not fit on an SM"); }
+  CK(cudaMalloc(&h->d_counter, sizeof(int)));
+  CK(cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  const int mb = spec->max_batch > 0 ? spec->max_batch : 0;
+  if (mb > 0) {
+    const size_t nw = NU * spec->N, ng = (size_t)h->pr.R * h->pr.S;
+    CK(cudaMalloc(&h->d_p, sizeof(double) * mb * NPAR)); CK(cudaMalloc(&h->d_x0, sizeof(double) * mb * nw));
+    CK(cudaMalloc(&h->d_lbx, sizeof(double) * nw)); CK(cudaMalloc(&h->d_ubx, sizeof(double) * nw));
+    CK(cudaMalloc(&h->d_lbg, sizeof(double) * ng)); CK(cudaMalloc(&h->d_ubg, sizeof(double) * ng));
+    h->obs_cap = (size_t)mb * 3 * (spec->n_obs > 0 ? spec->n_obs : 1);
+    CK(cudaMalloc(&h->d_obs, sizeof(double) * h->obs_cap));
+    CK(cudaMalloc(&h->d_x, sizeof(double) * mb * nw)); CK(cudaMalloc(&h->d_f, sizeof(double) * mb));
+    CK(cudaMalloc(&h->d_g, sizeof(double) * mb * ng)); CK(cudaMalloc(&h->d_lamx, sizeof(double) * mb * nw));
+    CK(cudaMalloc(&h->d_lamg, sizeof(double) * mb * ng));
+    CK(cudaMalloc(&h->d_status, sizeof(int32_t) * mb)); CK(cudaMalloc(&h->d_iters, sizeof(int32_t) * mb));
+  }
+  *out = h;
+  return 0;
+}
+
+int nmpc_destroy(nmpc_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
+                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
+               const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+               const double* obst, uint32_t flags,
+               double* x, double* f, double* g, double* lam_x, double* lam_g,
+               int32_t* status, int32_t* iters, void* cuda_stream) {
+  if (!h) return fail("nmpc_solve: null handle");
+  if (B <= 0) return 0;
+  if (!p || !x0 || !lbx || !ubx || !lbg || !ubg || !x) return fail("nmpc_solve: null required pointer");
+  if (h->pr.n_obs > 0 && !obst) return fail("nmpc_solve: obstacle table required");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  SolveArgs A;
+  A.pr = h->pr; A.o = h->opt; A.B = B;
+  A.p = p; A.x0 = x0; A.lbx = lbx; A.ubx = ubx; A.lbg = lbg; A.ubg = ubg; A.obs = obst;
+  A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
+  A.x = x; A.f = f; A.g = g; A.lam_x = lam_x; A.lam_g = lam_g; A.status = status; A.iters = iters;
+  A.counter = h->d_counter; A.stats = h->d_stats; A.ws_doubles = h->ws_doubles;
+  A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
+  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
+  const int threads = h->warps * 32;
+  int blocks = (B + h->warps - 1) / h->warps;
+  const int maxb = h->sm_count * h->blocks_per_sm;
+  if (blocks > maxb) blocks = maxb;
+  const size_t smem = (size_t)h->ws_doubles * sizeof(double) * h->warps;
+  nmpc_ipm_kernel<<<blocks, threads, smem, s>>>(A);
+  CK(cudaGetLastError());
+  h->last_stream = s; h->launches = 1;
+  return 0;
+}
+
+int nmpc_solve_host(nmpc_handle* h, int32_t B, const double* p, const double* x0,
+                    const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                    const double* obst, uint32_t flags,
+                    double* x, double* f, double* g, double* lam_x, double* lam_g,
+                    int32_t* status, int32_t* iters) {
+  if (!h) return fail("nmpc_solve_host: null handle");
+  if (B <= 0) return 0;
+  if (B > h->spec.max_batch) return fail("nmpc_solve_host: B exceeds spec.max_batch");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->own_stream;
+  const size_t nw = NU * h->pr.N, ng = (size_t)h->pr.R * h->pr.S;
+  const size_t nobs = (size_t)3 * h->pr.n_obs * ((flags & NMPC_OBS_PER_INSTANCE) ? B : 1);
+  CK(cudaMemcpyAsync(h->d_p, p, sizeof(double) * B * NPAR, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * B * nw, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_lbx, lbx, sizeof(double) * nw, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_ubx, ubx, sizeof(double) * nw, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_lbg, lbg, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_ubg, ubg, sizeof(double) * ng, cudaMemcpyHostToDevice, s));
+  if (nobs) CK(cudaMemcpyAsync(h->d_obs, obst, sizeof(double) * nobs, cudaMemcpyHostToDevice, s));
+  int rc = nmpc_solve(h, B, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs, flags,
+                      h->d_x, h->d_f, g ? h->d_g : nullptr, lam_x ? h->d_lamx : nullptr, lam_g ? h->d_lamg : nullptr,
+                      h->d_status, h->d_iters, (void*)s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(x, h->d_x, sizeof(double) * B * nw, cudaMemcpyDeviceToHost, s));
+  if (f) CK(cudaMemcpyAsync(f, h->d_f, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+  if (g) CK(cudaMemcpyAsync(g, h->d_g, sizeof(double) * B * ng, cudaMemcpyDeviceToHost, s));
+  if (lam_x) CK(cudaMemcpyAsync(lam_x, h->d_lamx, sizeof(double) * B * nw, cudaMemcpyDeviceToHost, s));
+  if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lamg, sizeof(double) * B * ng, cudaMemcpyDeviceToHost, s));
+  if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+  if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const double* obst, uint32_t flags,
+              double sigma, const double* lam, const double* v,
+              double* f, double* g, double* grad_f, double* jtv, double* hv, void* cuda_stream) {
+  if (!h) return fail("nmpc_eval: null handle");
+  if (B <= 0) return 0;
+  if (!w || !p) return fail("nmpc_eval: null required pointer");
+  if (h->pr.n_obs > 0 && !obst) return fail("nmpc_eval: obstacle table required");
+  if (jtv && !lam) return fail("nmpc_eval: jtv needs lam");
+  if (hv && !v) return fail("nmpc_eval: hv needs v");
+  CK(cudaSetDevice(h->device));
+  EvalArgs A;
+  A.pr = h->pr; A.B = B; A.w = w; A.p = p; A.obs = obst; A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
+  A.sigma = sigma; A.lam = lam; A.v = v; A.f = f; A.g = g; A.grad = grad_f; A.jtv = jtv; A.hv = hv;
+  const int warps = 4;
+  nmpc_eval_kernel<<<(B + warps - 1) / warps, warps * 32, 0, (cudaStream_t)cuda_stream>>>(A);
+  CK(cudaGetLastError());
+  h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;
+  return 0;
+}
+
+int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* state, double* target,
+              double* u_warm, const double* target_vw, double* fov_centre, void* cuda_stream) {
+  if (!h) return fail("nmpc_step: null handle");
+  if (B <= 0) return 0;
+  if (!x_sol || !state || !target || !u_warm || !target_vw) return fail("nmpc_step: null required pointer");
+  CK(cudaSetDevice(h->device));
+  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, x_sol, state, target, u_warm, target_vw, fov_centre};
+  nmpc_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(A);
+  CK(cudaGetLastError());
+  h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;
+  return 0;
+}
+
+int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows) {
+  if (!h) return fail("nmpc_set_debug_log: null handle");
+  h->dbg = dev_buf; h->dbg_rows = dev_buf ? rows : 0;
+  return 0;
+}
+
+int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out) {
+  if (!h || !out) return fail("nmpc_get_stats: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->last_stream));
+  unsigned long long st[3];
+  CK(cudaMemcpy(st, h->d_stats, sizeof st, cudaMemcpyDeviceToHost));
+  out->kernel_launches = h->launches; out->factorizations = (int64_t)st[0]; out->ls_trials = (int64_t)st[1]; out->soc_accepted = (int64_t)st[2];
+  return 0;
+}
+
+}  // extern "C"

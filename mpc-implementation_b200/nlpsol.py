@@ -1,0 +1,268 @@
+"""CasADi-shaped facade over the C ABI: the one line a reference script swaps.
+
+Reference (Python/NMPC_TT.py:250-267, :358-367):
+    solver = ca.nlpsol('solver', 'ipopt', nlp_prob, opts)
+    sol = solver(x0=args['x0'], lbx=args['lbx'], ubx=args['ubx'], lbg=args['lbg'], ubg=args['ubg'], p=args['p'])
+    u = ca.reshape(sol['x'], n_controls, N)
+Here:
+    solver = b200nmpc.nlpsol('solver', 'ipm', scenario_or_dict, opts)       # nlp_prob -> problem constants
+    sol = solver(x0=..., lbx=..., ubx=..., lbg=..., ubg=..., p=...)          # same keywords, same layouts
+    u = sol['x'].reshape(N, 6).T
+
+Every argument may be a single instance ((n,), (n,1), list) or a batch (B, n); host containers (numpy, lists)
+go through nmpc_solve_host (copies inside), torch CUDA float64 tensors are used in place on torch's current
+stream.  Like CasADi's nlpsol the call never raises on a non-converged instance: the outcome is in
+solver.stats() ('return_status', 'success', 'iter_count'), which the reference never reads (:358-367).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _ffi
+from .scenarios import NP, NU, Scenario
+
+try:  # torch is plumbing for device memory / streams only
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_cuda_tensor(a) -> bool:
+    return torch is not None and isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def _spec_from(problem, opts: Optional[dict]) -> Dict[str, Any]:
+    if isinstance(problem, Scenario):
+        d = dict(T=problem.T, N=problem.N, obstacles=problem.obstacle_table(), w1=problem.w1, w2=problem.w2,
+                 vfov=problem.vfov, hfov=problem.hfov)
+    else:
+        d = dict(problem)
+        if "obstacles" in d:
+            o = np.asarray(d["obstacles"], dtype=np.float64).reshape(-1, 3).copy()
+            o[:, 2] += float(d.get("uav_r", 5.0))
+            d["obstacles"] = o
+        else:
+            d["obstacles"] = np.zeros((int(d.get("n_obs", 0)), 3))
+    ip = dict((opts or {}).get("ipopt", {}))
+    d["max_iter"] = int(ip.get("max_iter", 100))          # NMPC_TT.py:259
+    d["tol"] = float(ip.get("tol", 1e-8))
+    d["scaling"] = 0 if ip.get("nlp_scaling_method", "gradient-based") == "none" else 1
+    return d
+
+
+class Solver:
+    """Callable returned by nlpsol(); owns one nmpc_handle."""
+
+    def __init__(self, name: str, problem, opts: Optional[dict] = None, device: int = 0, max_batch: int = 1):
+        self.name = name
+        d = _spec_from(problem, opts)
+        self.T, self.N = float(d["T"]), int(d["N"])
+        self.obstacles = np.ascontiguousarray(d["obstacles"], dtype=np.float64)
+        self.n_obs = self.obstacles.shape[0]
+        self.n_w, self.n_g = NU * self.N, (5 + self.n_obs) * (self.N + 1)
+        self.device = device
+        self._d = d
+        self._h = C.c_void_p()
+        self._max_batch = 0
+        self._dev_cache: Dict[str, Any] = {}
+        self._stats: Dict[str, Any] = {}
+        self._create(max_batch)
+
+    # -- handle management ---------------------------------------------------------------------
+    def _create(self, max_batch: int):
+        L = _ffi.lib()
+        if self._h:
+            L.nmpc_destroy(self._h)
+            self._h = C.c_void_p()
+        d = self._d
+        spec = _ffi.NmpcSpec(self.T, self.N, self.n_obs, float(d.get("w1", 1.0)), float(d.get("w2", 2.0)),
+                             float(d.get("vfov", 1.0)), float(d.get("hfov", 1.0)),
+                             d["max_iter"], d["scaling"], d["tol"], int(max_batch), 0)
+        _ffi.check(L.nmpc_create(C.byref(spec), self.device, C.byref(self._h)), "nmpc_create")
+        self._max_batch = max_batch
+        self.spec = spec
+
+    def close(self):
+        if self._h:
+            _ffi.lib().nmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _dev_const(self, key: str, arr) -> "torch.Tensor":
+        """Device copy of a batch-shared vector (bounds, obstacle table), cached by content."""
+        if _is_cuda_tensor(arr):
+            return arr.to(torch.float64).contiguous().view(-1)
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float64).reshape(-1))
+        hit = self._dev_cache.get(key)
+        if hit is not None and hit[0].shape == a.shape and np.array_equal(hit[0], a):
+            return hit[1]
+        t = torch.from_numpy(a.copy()).to(f"cuda:{self.device}")
+        self._dev_cache[key] = (a.copy(), t)
+        return t
+
+    @staticmethod
+    def _host(a, n: int) -> np.ndarray:
+        if torch is not None and isinstance(a, torch.Tensor):
+            a = a.detach().cpu().numpy()
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == 2 and a.shape[1] == 1 and a.shape[0] == n:   # CasADi column vector
+            a = a.reshape(1, n)
+        a = a.reshape(-1, n) if a.ndim != 2 else a
+        return np.ascontiguousarray(a)
+
+    # -- the call --------------------------------------------------------------------------------
+    def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, obstacles=None,
+                 want_g: bool = True, want_lam: bool = True):
+        if p is None:
+            raise ValueError("solver: p is required")
+        if any(v is None for v in (lbx, ubx, lbg, ubg)):
+            raise ValueError("solver: lbx, ubx, lbg, ubg are required (the reference passes all four)")
+        if _is_cuda_tensor(p):
+            return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+        return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+
+    def _obst(self, obstacles, B):
+        if obstacles is None:
+            return self.obstacles, 0
+        o = obstacles.detach().cpu().numpy() if (torch is not None and isinstance(obstacles, torch.Tensor)) else obstacles
+        o = np.ascontiguousarray(np.asarray(o, dtype=np.float64))
+        if o.size == 3 * self.n_obs:
+            return o.reshape(self.n_obs, 3), 0
+        if o.size == 3 * self.n_obs * B:
+            return o.reshape(B, self.n_obs, 3), _ffi.NMPC_OBS_PER_INSTANCE
+        raise ValueError("solver: obstacles must be [n_obs,3] or [B,n_obs,3] of (cx, cy, r_uav + r_obs)")
+
+    def _call_host(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam):
+        L = _ffi.lib()
+        single = np.asarray(p).ndim == 1 or (np.asarray(p).ndim == 2 and np.asarray(p).shape[1] == 1)
+        p = self._host(p, NP)
+        B = p.shape[0]
+        x0 = np.zeros((B, self.n_w)) if x0 is None else self._host(x0, self.n_w)
+        if x0.shape[0] != B:
+            raise ValueError("solver: x0 and p disagree on the batch size")
+        lbx, ubx = self._host(lbx, self.n_w), self._host(ubx, self.n_w)
+        lbg, ubg = self._host(lbg, self.n_g), self._host(ubg, self.n_g)
+        obs, flags = self._obst(obstacles, B)
+        if B > self._max_batch:
+            self._create(max(B, 2 * self._max_batch))
+        x = np.empty((B, self.n_w)); f = np.empty(B)
+        g = np.empty((B, self.n_g)) if want_g else None
+        lam_x = np.empty((B, self.n_w)) if want_lam else None
+        lam_g = np.empty((B, self.n_g)) if want_lam else None
+        status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+        ptr = lambda a: None if a is None else a.ctypes.data
+        _ffi.check(L.nmpc_solve_host(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
+                                     ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters)),
+                   "nmpc_solve_host")
+        self._stats = dict(return_status=status, iter_count=iters, success=status == 0)
+        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
+        if single:
+            out = {k: (v[0] if v is not None else None) for k, v in out.items()}
+        return out
+
+    def _call_device(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam):
+        L = _ffi.lib()
+        dev = p.device
+        single = p.dim() == 1
+        p = p.to(torch.float64).reshape(-1, NP).contiguous()
+        B = p.shape[0]
+        x0 = torch.zeros((B, self.n_w), dtype=torch.float64, device=dev) if x0 is None else x0.to(torch.float64).reshape(B, self.n_w).contiguous()
+        lbx, ubx = self._dev_const("lbx", lbx), self._dev_const("ubx", ubx)
+        lbg, ubg = self._dev_const("lbg", lbg), self._dev_const("ubg", ubg)
+        flags = 0
+        if obstacles is None:
+            obs = self._dev_const("obs", self.obstacles)
+        elif _is_cuda_tensor(obstacles):
+            obs = obstacles.to(torch.float64).contiguous()
+            flags = _ffi.NMPC_OBS_PER_INSTANCE if obs.numel() == 3 * self.n_obs * B and B > 1 else 0
+        else:
+            o, flags = self._obst(obstacles, B)
+            obs = torch.from_numpy(o).to(dev)
+        for t, n in ((lbx, self.n_w), (ubx, self.n_w), (lbg, self.n_g), (ubg, self.n_g)):
+            if t.numel() != n:
+                raise ValueError("solver: bound vector has the wrong length")
+        x = torch.empty((B, self.n_w), dtype=torch.float64, device=dev)
+        f = torch.empty(B, dtype=torch.float64, device=dev)
+        g = torch.empty((B, self.n_g), dtype=torch.float64, device=dev) if want_g else None
+        lam_x = torch.empty((B, self.n_w), dtype=torch.float64, device=dev) if want_lam else None
+        lam_g = torch.empty((B, self.n_g), dtype=torch.float64, device=dev) if want_lam else None
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _ffi.check(L.nmpc_solve(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
+                                ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters), stream),
+                   "nmpc_solve")
+        self._keep = (p, x0, obs)   # keep inputs alive until the stream has consumed them
+        self._stats = dict(return_status=status, iter_count=iters, success=status == 0)
+        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
+        if single:
+            out = {k: (v[0] if v is not None else None) for k, v in out.items()}
+        return out
+
+    def stats(self) -> Dict[str, Any]:
+        """Per-instance outcome of the last call (CasADi: solver.stats())."""
+        return self._stats
+
+    def work_counters(self) -> Dict[str, int]:
+        st = _ffi.NmpcStats()
+        _ffi.check(_ffi.lib().nmpc_get_stats(self._h, C.byref(st)), "nmpc_get_stats")
+        return dict(kernel_launches=st.kernel_launches, factorizations=st.factorizations, ls_trials=st.ls_trials,
+                    soc_accepted=st.soc_accepted)
+
+    # -- function-level evaluation (nlp_f / nlp_g / nlp_grad_f / nlp_hess_l of the reference's nlpsol) ----
+    def evaluate(self, w, p, lam=None, v=None, sigma: float = 1.0, obstacles=None):
+        L = _ffi.lib()
+        dev = f"cuda:{self.device}"
+        to = lambda a, n: torch.as_tensor(np.asarray(a, dtype=np.float64) if not _is_cuda_tensor(a) else a,
+                                          dtype=torch.float64, device=dev).reshape(-1, n).contiguous()
+        w, p = to(w, self.n_w), to(p, NP)
+        B = w.shape[0]
+        lam_t = to(lam, self.n_g) if lam is not None else None
+        v_t = to(v, self.n_w) if v is not None else None
+        flags = 0
+        if obstacles is None:
+            obs = self._dev_const("obs", self.obstacles)
+        else:
+            o, flags = self._obst(obstacles, B)
+            obs = torch.from_numpy(o).to(dev)
+        z = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+        f, g, grad = z(B), z(B, self.n_g), z(B, self.n_w)
+        jtv = z(B, self.n_w) if lam_t is not None else None
+        hv = z(B, self.n_w) if v_t is not None else None
+        ptr = lambda t: None if t is None else t.data_ptr()
+        stream = torch.cuda.current_stream(torch.device(dev)).cuda_stream
+        _ffi.check(L.nmpc_eval(self._h, B, ptr(w), ptr(p), ptr(obs), flags, float(sigma), ptr(lam_t), ptr(v_t),
+                               ptr(f), ptr(g), ptr(grad), ptr(jtv), ptr(hv), stream), "nmpc_eval")
+        torch.cuda.synchronize()
+        return dict(f=f, g=g, grad=grad, jtv=jtv, hv=hv)
+
+    # -- shift_timestep (NMPC_TT.py:13-30) on device --------------------------------------------
+    def step(self, x_sol, state, target, u_warm, target_vw, fov_centre=None):
+        """In-place closed-loop shift of B instances (torch CUDA float64 tensors)."""
+        L = _ffi.lib()
+        B = state.shape[0]
+        stream = torch.cuda.current_stream(state.device).cuda_stream
+        _ffi.check(L.nmpc_step(self._h, B, x_sol.data_ptr(), state.data_ptr(), target.data_ptr(), u_warm.data_ptr(),
+                               target_vw.data_ptr(), None if fov_centre is None else fov_centre.data_ptr(), stream),
+                   "nmpc_step")
+
+
+def nlpsol(name: str, plugin: str, problem, opts: Optional[dict] = None, device: int = 0, max_batch: int = 1) -> Solver:
+    """Mirror of ca.nlpsol(name, 'ipopt', nlp_prob, opts) (NMPC_TT.py:267).
+
+    plugin: 'ipm' (or 'ipopt' for drop-in spelling) -- the in-kernel interior-point method.
+    problem: a scenarios.Scenario or a dict(T=, N=, obstacles=[(cx,cy,r_obs)...], uav_r=5, w1=1, w2=2).
+    opts: {'ipopt': {'max_iter': 100, ...}} as in the reference; unknown keys are ignored like print_level."""
+    if plugin not in ("ipm", "ipopt"):
+        raise ValueError(f"nlpsol: unknown plugin '{plugin}' (only the in-kernel 'ipm' exists)")
+    return Solver(name, problem, opts, device=device, max_batch=max_batch)
