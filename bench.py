@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- converged NMPC solves/s of the batched closed loop (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): Python/NMPC_TT.py's NLP (T=1, N=15, 3 obstacles) batched over 4096
+randomised UAV initial states and target speeds PER GPU, driven by the reference's shift-and-apply-first-input
+closed loop.  A "step" is one closed-loop batch step: one NLP solve per instance + plant/target/warm-start shift.
+Warm-up steps include the atypical cold first solve (all-zero warm start, NMPC_TT.py:329).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference ...                            CPU restatement of the reference path (oracle/)
+Under torchrun every rank drives its own GPU on its own instances (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "converged_nmpc_solves_per_sec"
+UNIT = "solves/s"
+SCENARIO = "nmpc_tt"
+
+
+def host_shift(T, p, x, vw):
+    """Vectorised shift_timestep (NMPC_TT.py:13-30) on host arrays: p [B,11] in place, returns the warm start."""
+    th, ps, v = p[:, 3].copy(), p[:, 4].copy(), x[:, 0]
+    p[:, 0] += T * v * np.cos(ps) * np.cos(th)
+    p[:, 1] += T * v * np.sin(ps) * np.cos(th)
+    p[:, 2] += T * v * np.sin(th)
+    p[:, 3:8] += T * x[:, 1:6]
+    tt = p[:, 10].copy()
+    p[:, 8] += T * vw[:, 0] * np.cos(tt)
+    p[:, 9] += T * vw[:, 0] * np.sin(tt)
+    p[:, 10] += T * vw[:, 1]
+    return np.concatenate([x[:, 6:], x[:, -6:]], axis=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops(N, n_obs, iters, n_fact, n_ls):
+    """SURVEY.md section 8d planning formula (add/mul = 1, FMA = 2): Riccati factorisation N*3379, Riccati solve N*968,
+    derivative evaluation + adjoint + residuals N*(560+30*n_obs), one line-search trial N*(60+8*n_obs)."""
+    return N * (3379.0 * n_fact + 968.0 * iters + (560.0 + 30.0 * n_obs) * iters + (60.0 + 8.0 * n_obs) * n_ls)
+
+
+def bytes_per_solve(N, n_obs, per_instance_obs=False):
+    """Algorithmic HBM bytes per solve: read p + warm start, write x + f, status + iters."""
+    return 8 * (11 + 6 * N) + 8 * (6 * N + 1) + 8 + (24 * n_obs if per_instance_obs else 0)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (CPU restatement of the reference's CasADi/IPOPT path -- the reference itself cannot run
+    here: casadi is not installable) on all host cores, same closed loop, bounded sample."""
+    if rank != 0:
+        return
+    import b200nmpc
+    import oracle
+    oracle.build()
+    sc = b200nmpc.SCENARIOS[SCENARIO]
+    cores = os.cpu_count() or 1
+    B = args.ref_batch or max(64, 16 * cores)
+    p, vw = b200nmpc.random_instances(sc, B, seed=2000)
+    sp = oracle.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    obs = sc.obstacle_table(); lbx, ubx, lbg, ubg = sc.bounds()
+    u = np.zeros((B, sc.n_w))
+    conv, iters_sum, step_ms = 0, 0, []
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = oracle.solve(sp, obs, p, u, lbx, ubx, lbg, ubg, nthreads=cores, want_g=False, want_lam=False)
+        u = host_shift(sc.T, p, r["x"], vw)
+        dt = time.perf_counter() - t0
+        if k >= args.warmup:
+            step_ms.append(dt * 1e3); conv += int((r["status"] == 0).sum()); iters_sum += int(r["iters"].sum())
+    total = sum(step_ms) * 1e-3
+    val = conv / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}) closed loop, randomised states/targets",
+                       "batch": B, "note": "bounded CPU sample of the GPU arm's workload"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{B} instances x {args.steps} closed-loop steps, oracle/nmpc_oracle.cpp on {cores} threads "
+                                       "(CasADi/IPOPT itself is unavailable in this image)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "converged_fraction": conv / (B * args.steps), "mean_iters": iters_sum / (B * args.steps)}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import b200nmpc
+    from mpc_implementation_b200 import sharding
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sc = b200nmpc.SCENARIOS[SCENARIO]
+    B = args.batch
+    p, vw = b200nmpc.random_instances(sc, B, seed=2000 + rank)
+    solver = b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=B)
+    cl = ClosedLoop(solver, sc, p, target_vw=vw)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)    # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cold = None
+    for k in range(args.warmup):
+        cl.step()
+        if k == 0:
+            st = solver.stats()
+            cold = {"converged_fraction": float(st["success"].double().mean()), "mean_iters": float(st["iter_count"].double().mean())}
+    barrier()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    conv_t = torch.zeros((), dtype=torch.int64, device=dev)
+    it_t = torch.zeros((), dtype=torch.int64, device=dev)
+    fact = ls = 0
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                                   # L2 flush between timed iterations (inputs are ~6 MB << L2)
+        cl._schedule_vw()
+        tb = cl.p[:, 8:10].clone()
+        ev[k][0].record()
+        sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False)
+        ev[k][1].record()
+        solver.step(sol["x"], cl.p, cl.u_warm, cl.vw, cl.fov)
+        cl.err_sum += torch.linalg.vector_norm(cl.fov - tb, dim=1)
+        ev[k][2].record()
+        st = solver.stats()
+        conv_t += st["success"].sum(); it_t += st["iter_count"].sum()
+        cl.mpc_iter += 1
+        if args.count_work:
+            c = solver.work_counters(); fact += c["factorizations"]; ls += c["ls_trials"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    step_ms = [ev[k][0].elapsed_time(ev[k][2]) for k in range(K)]
+    solve_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
+    t_rank = sum(step_ms) * 1e-3
+    t_max = sharding.max_over_ranks(t_rank, dev)
+    tot = sharding.sum_counters([int(conv_t.item()), int(it_t.item()), fact, ls], dev).cpu().numpy()
+    conv_all, iters_all = float(tot[0]), float(tot[1])
+    value = conv_all / t_max
+
+    # ---- e2e: the same closed loop through the host-buffer entry point (H2D + solve + D2H every step)
+    Ke = min(K, args.e2e_steps)
+    ph = torch.empty((B, 11), dtype=torch.float64).pin_memory().numpy(); ph[:] = cl.p.cpu().numpy()
+    uh = torch.empty((B, sc.n_w), dtype=torch.float64).pin_memory().numpy(); uh[:] = cl.u_warm.cpu().numpy()
+    lbx, ubx, lbg, ubg = sc.bounds(); vwh = vw.copy()
+    barrier()
+    conv_e = 0; t_e = 0.0
+    for k in range(Ke + 1):
+        t0 = time.perf_counter()
+        s2 = solver(x0=uh, p=ph, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, want_g=False, want_lam=False)
+        uh[:] = host_shift(sc.T, ph, s2["x"], vwh)
+        dt = time.perf_counter() - t0
+        if k > 0:
+            t_e += dt; conv_e += int(solver.stats()["success"].sum())
+    barrier()
+    t_e_max = sharding.max_over_ranks(t_e, dev)
+    conv_e_all = float(sharding.sum_counters([conv_e], dev)[0])
+    e2e_val = conv_e_all / t_e_max if t_e_max > 0 else None
+    h2d = B * (11 + sc.n_w) * 8 + (2 * sc.n_w + 2 * sc.n_g + 3 * sc.n_obs) * 8
+    d2h = B * (sc.n_w + 1) * 8 + B * 8
+
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- work counters for the flop numerator (one extra untimed step on rank 0)
+    sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False)
+    torch.cuda.synchronize()
+    wc = solver.work_counters(); st = solver.stats()
+    it_step = float(st["iter_count"].sum())
+    flops_step = algorithmic_flops(sc.N, sc.n_obs, it_step, wc["factorizations"], wc["ls_trials"])
+    k_ms = float(np.mean(solve_ms))
+    peak64 = ctypes_fp64_peak(b200nmpc, local_rank)
+    lbx, ubx, lbg, ubg = sc.bounds()
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); which = "of measured" if "hbm_gbs" in peaks else "of fallback"
+    ach_gbs = bytes_per_solve(sc.N, sc.n_obs) * B / (k_ms * 1e-3) / 1e9
+    ach_tf = flops_step / (k_ms * 1e-3) / 1e12
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        cores = os.cpu_count() or 1
+        ns = min(B, args.cpu_sample or max(256, 64 * cores))
+        pc = cl.p.cpu().numpy()[:ns].copy(); uc = cl.u_warm.cpu().numpy()[:ns].copy()
+        sp = oracle.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+        t0 = time.perf_counter()
+        r = oracle.solve(sp, sc.obstacle_table(), pc, uc, lbx, ubx, lbg, ubg, nthreads=cores, want_g=False, want_lam=False)
+        dt = time.perf_counter() - t0
+        cpu = {"value": float((r["status"] == 0).sum() / dt), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {ns} instances of the GPU batch at the state after the timed steps (warm starts), one solve each, "
+                         f"oracle/nmpc_oracle.cpp on {cores} threads; CasADi/IPOPT itself cannot run in this image",
+               "seconds": dt, "converged_fraction": float((r["status"] == 0).mean()), "mean_iters": float(r["iters"].mean())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": t_max * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}, n_w={sc.n_w}, n_g={sc.n_g}) closed loop: "
+                               f"{B} randomised UAV states / target speeds per GPU (BASELINE.json configs[1])",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
+                   "l2": "flushed between timed steps (256 MB write)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
+        "p50_step_ms": float(np.median(step_ms)), "p50_solve_kernel_ms": float(np.median(solve_ms)),
+        "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
+        "cold_first_step": cold, "wall_s": wall,
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=) with pinned numpy buffers -> nmpc_solve_host"},
+        "gpu_launches": 2 * K,
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+                     "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "peak_source": which,
+                     "bytes_per_solve": bytes_per_solve(sc.N, sc.n_obs),
+                     "note": "not HBM-bound by design (SURVEY 8d): the limiter is the FP64 dependency chain; see fp64"},
+        "fp64": {"achieved": ach_tf, "peak": peak64, "unit": "TFLOP/s", "frac": (ach_tf / peak64) if peak64 else None,
+                 "flops_per_step": flops_step, "peak_source": "nmpc_measure_fp64_peak (DFMA loop, this GPU, this run)",
+                 "iters": it_step, "factorizations": wc["factorizations"], "ls_trials": wc["ls_trials"]},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def ctypes_fp64_peak(b200nmpc, device):
+    import ctypes as C
+    v = C.c_double(0.0)
+    rc = b200nmpc._ffi.lib().nmpc_measure_fp64_peak(device, C.byref(v))
+    return float(v.value) if rc == 0 else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--ref-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--count-work", action="store_true", help="read device work counters every timed step (adds a sync)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

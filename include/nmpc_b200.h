@@ -106,11 +106,13 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
               double sigma, const double* lam, const double* v,
               double* f, double* g, double* grad_f, double* jtv, double* hv, void* cuda_stream);
 
-/* shift_timestep (NMPC_TT.py:13-30) + FOV centre (:399-402) for B instances, in place:
- *   state [B][8] <- state + T f_u(state, u[:,0]);  u_warm [B][6N] <- shift(x_sol) (repeat last);
- *   target [B][3] <- target + T [v cos th, v sin th, om], target_vw [B][2] = (v, om) of this step;
+/* shift_timestep (NMPC_TT.py:13-30) + FOV centre (:399-402) for B instances, in place on the
+ * parameter block the next solve reads:
+ *   p [B][11]: p[0:8] <- x + T f_u(x, u[:,0]);  p[8:11] <- target + T [v cos th, v sin th, om]
+ *   u_warm [B][6N] <- x_sol shifted by one stage, last stage repeated (may alias x_sol)
+ *   target_vw [B][2] = (v, om) of the target for this step (the scripts' con_t, keyed on mpc_iter)
  *   fov_centre [B][2] (may be NULL) = (X_E, Y_E) of the NEW state. */
-int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* state, double* target,
+int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
               double* u_warm, const double* target_vw, double* fov_centre, void* cuda_stream);
 
 /* statistics of the last nmpc_solve on this handle (device work counters, host copy) */
@@ -125,6 +127,10 @@ int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out);   /* synchronises the handl
 /* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
  * dev_buf [B][rows][8] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials}; NULL disables. */
 int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);
+
+/* Measurement aid: FP64 FMA peak of `device` in TFLOP/s (register-resident DFMA loop on every SM).
+ * MEASURED_PEAKS.json carries HBM and bf16 peaks only; this is the denominator of the FP64 roofline. */
+int nmpc_measure_fp64_peak(int device, double* tflops);
 
 /* sizes implied by a spec */
 int32_t nmpc_n_w(const nmpc_spec* spec);   /* 6 N */

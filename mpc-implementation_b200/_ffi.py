@@ -32,7 +32,8 @@ class NmpcStats(C.Structure):
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_eval", "nmpc_step",
-           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_n_w", "nmpc_n_g", "nmpc_last_error", "nmpc_version"]
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
+           "nmpc_last_error", "nmpc_version"]
 
 _lib = None
 
@@ -58,9 +59,10 @@ def lib():
     L.nmpc_solve.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7 + [vp]
     L.nmpc_solve_host.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7
     L.nmpc_eval.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_uint32, C.c_double, vp, vp] + [vp] * 5 + [vp]
-    L.nmpc_step.argtypes = [vp, C.c_int32] + [vp] * 6 + [vp]
+    L.nmpc_step.argtypes = [vp, C.c_int32] + [vp] * 5 + [vp]
     L.nmpc_get_stats.argtypes = [vp, C.POINTER(NmpcStats)]
     L.nmpc_set_debug_log.argtypes = [vp, vp, C.c_int32]
+    L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
     L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]
     for name in EXPORTS:

@@ -1,0 +1,77 @@
+"""Batched shift-and-apply-first-input closed loop (Python/NMPC_TT.py:346-402) with all state on the GPU.
+
+Per step and per instance the reference does
+    p  = vertcat(x0, xs);  x0_nlp = reshape(u0, 6N, 1)                     :350-356
+    sol = solver(x0=..., lbx, ubx, lbg, ubg, p)                             :358-365
+    u   = reshape(sol['x'], 6, N)                                           :367
+    t0, x0, u0, xs = shift_timestep(T, t0, x0, u, f_u, xs)                  :382  (schedule keyed on mpc_iter)
+    x_e_1, y_e_1 = FOV centre of the new x0                                 :399-402
+Here B such loops advance together: one nmpc_solve launch + one nmpc_step launch per batch step, no host
+round trip.  The final metric of the scripts, sum_i ||FOVcentre_{i+1} - target_i|| (:433-440), is
+accumulated per instance.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from .nlpsol import Solver
+from .scenarios import NP, Scenario
+
+
+class ClosedLoop:
+    def __init__(self, solver: Solver, scenario: Scenario, p0, target_vw=None, device: Optional[str] = None,
+                 phase=None):
+        """p0 [B,11] initial [state; target]; target_vw [B,2] constant per-instance target (v, omega) or None to
+        follow scenario.schedule(mpc_iter + phase[b])."""
+        self.solver, self.sc = solver, scenario
+        dev = device or f"cuda:{solver.device}"
+        self.p = torch.as_tensor(np.asarray(p0, dtype=np.float64), device=dev).reshape(-1, NP).contiguous().clone()
+        self.B = self.p.shape[0]
+        self.u_warm = torch.zeros((self.B, scenario.n_w), dtype=torch.float64, device=dev)     # u0 = 0  (:329)
+        lbx, ubx, lbg, ubg = scenario.bounds()
+        to = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+        self.lbx, self.ubx, self.lbg, self.ubg = to(lbx), to(ubx), to(lbg), to(ubg)
+        self.fov = torch.zeros((self.B, 2), dtype=torch.float64, device=dev)
+        self.err_sum = torch.zeros(self.B, dtype=torch.float64, device=dev)
+        self.mpc_iter = 0
+        self.phase = None if phase is None else np.asarray(phase, dtype=np.int64)
+        if target_vw is not None:
+            self.vw = to(np.asarray(target_vw, dtype=np.float64)).reshape(self.B, 2).contiguous()
+            self._const_vw = True
+        else:
+            self.vw = torch.zeros((self.B, 2), dtype=torch.float64, device=dev)
+            self._const_vw = False
+        self.last = None
+
+    def _schedule_vw(self):
+        if self._const_vw:
+            return
+        if self.phase is None:
+            v, w = self.sc.schedule(self.mpc_iter)
+            self.vw[:, 0] = v; self.vw[:, 1] = w
+        else:
+            vw = np.array([self.sc.schedule(self.mpc_iter + int(ph)) for ph in self.phase], dtype=np.float64)
+            self.vw.copy_(torch.from_numpy(vw))
+
+    def step(self, want_g: bool = False, want_lam: bool = False):
+        """One closed-loop batch step; returns the solver output dict (device tensors)."""
+        self._schedule_vw()
+        target_before = self.p[:, 8:10].clone()
+        sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg,
+                          want_g=want_g, want_lam=want_lam)
+        self.solver.step(sol["x"], self.p, self.u_warm, self.vw, self.fov)
+        # error[i] = || FOVcentre_{i+1} - target_i ||   (NMPC_TT.py:435)
+        self.err_sum += torch.linalg.vector_norm(self.fov - target_before, dim=1)
+        self.mpc_iter += 1
+        self.last = sol
+        return sol
+
+    def run(self, steps: int):
+        conv = 0
+        for _ in range(steps):
+            self.step()
+            conv += int(self.solver.stats()["success"].sum().item())
+        return conv

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
 
 struct StepArgs {
   double T, hv, hh; int N, B;
-  const double* x_sol; double *state, *target, *u_warm; const double* vw; double* fov;
+  const double* x_sol; double *p, *u_warm; const double* vw; double* fov;
 };
 
 __global__ void nmpc_step_kernel(const StepArgs A) {
@@ -185,7 +185,7 @@ __global__ void nmpc_step_kernel(const StepArgs A) {
   if (b >= A.B) return;
   const int nw = NU * A.N;
   const double* xs = A.x_sol + (size_t)b * nw;
-  double* st = A.state + (size_t)b * NX;
+  double* st = A.p + (size_t)b * NPAR;
   double x[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = st[i];
@@ -203,7 +203,7 @@ __global__ void nmpc_step_kernel(const StepArgs A) {
     for (int i = 0; i < NU; ++i) uw[NU * k + i] = xs[NU * (k + 1) + i];
   if (A.u_warm != A.x_sol)
     for (int i = 0; i < NU; ++i) uw[NU * (A.N - 1) + i] = xs[NU * (A.N - 1) + i];
-  double* tg = A.target + (size_t)b * 3;
+  double* tg = st + NX;
   const double tv = A.vw[2 * b], tw = A.vw[2 * b + 1], th = tg[2];
   tg[0] += A.T * tv * cos(th); tg[1] += A.T * tv * sin(th); tg[2] += A.T * tw;
   if (A.fov) {
@@ -392,13 +392,13 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
   return 0;
 }
 
-int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* state, double* target,
+int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
               double* u_warm, const double* target_vw, double* fov_centre, void* cuda_stream) {
   if (!h) return fail("nmpc_step: null handle");
   if (B <= 0) return 0;
-  if (!x_sol || !state || !target || !u_warm || !target_vw) return fail("nmpc_step: null required pointer");
+  if (!x_sol || !p || !u_warm || !target_vw) return fail("nmpc_step: null required pointer");
   CK(cudaSetDevice(h->device));
-  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, x_sol, state, target, u_warm, target_vw, fov_centre};
+  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, x_sol, p, u_warm, target_vw, fov_centre};
   nmpc_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(A);
   CK(cudaGetLastError());
   h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;
@@ -422,3 +422,38 @@ int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// FP64 roofline denominator: register-resident DFMA loop on every SM (MEASURED_PEAKS.json has no FP64 entry)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nmpc_dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;   // never true; keeps the loop alive
+}
+
+extern "C" int nmpc_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail("nmpc_measure_fp64_peak: null argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr; CK(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(e0, 0));
+    nmpc_dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops = best;
+  return 0;
+}

@@ -247,12 +247,12 @@ class Solver:
         return dict(f=f, g=g, grad=grad, jtv=jtv, hv=hv)
 
     # -- shift_timestep (NMPC_TT.py:13-30) on device --------------------------------------------
-    def step(self, x_sol, state, target, u_warm, target_vw, fov_centre=None):
-        """In-place closed-loop shift of B instances (torch CUDA float64 tensors)."""
+    def step(self, x_sol, p, u_warm, target_vw, fov_centre=None):
+        """In-place closed-loop shift of B instances (torch CUDA float64 tensors): p [B,11], u_warm [B,6N]."""
         L = _ffi.lib()
-        B = state.shape[0]
-        stream = torch.cuda.current_stream(state.device).cuda_stream
-        _ffi.check(L.nmpc_step(self._h, B, x_sol.data_ptr(), state.data_ptr(), target.data_ptr(), u_warm.data_ptr(),
+        B = p.shape[0]
+        stream = torch.cuda.current_stream(p.device).cuda_stream
+        _ffi.check(L.nmpc_step(self._h, B, x_sol.data_ptr(), p.data_ptr(), u_warm.data_ptr(),
                                target_vw.data_ptr(), None if fov_centre is None else fov_centre.data_ptr(), stream),
                    "nmpc_step")
 

@@ -139,7 +139,7 @@ def eval_all(spec: RefSpec, w: np.ndarray, p: np.ndarray, lam_g: np.ndarray | No
     g = constraints(spec, wt, pt)
     grad = torch.autograd.grad(f, wt, retain_graph=True)[0]
     J = torch.autograd.functional.jacobian(lambda ww: constraints(spec, ww, pt), wt)
-    out = dict(f=float(f), g=g.detach().numpy(), grad=grad.numpy(), J=J.numpy())
+    out = dict(f=float(f.detach()), g=g.detach().numpy(), grad=grad.numpy(), J=J.numpy())
     if lam_g is not None:
         lt = torch.tensor(np.asarray(lam_g, dtype=np.float64))
         H = torch.autograd.functional.hessian(
