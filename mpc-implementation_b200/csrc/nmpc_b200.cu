@@ -21,18 +21,20 @@ using namespace nmpc;
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-constexpr int WARPS_MAX = 4;
-
-__global__ void __launch_bounds__(WARPS_MAX * 32) nmpc_ipm_kernel(const SolveArgs A) {
+// One warp per block: the per-instance workspace (ws_doubles of shared memory) is the occupancy limiter, and
+// independent 32-thread blocks let the hardware pack as many as fit (9 per SM at N = 15, n_obs = 3).
+__global__ void __launch_bounds__(32) nmpc_ipm_kernel(const SolveArgs A) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* ws = smem + (size_t)warp * A.ws_doubles;
+  const int lane = threadIdx.x;
+  Ws ws = carve(smem, A.pr.S, A.pr.R, A.pr.n_obs);
+  ws.ric = A.ric + (size_t)blockIdx.x * A.ric_stride;
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(A.counter, 1);
     b = __shfl_sync(FULL, b, 0);
     if (b >= A.B) break;
     solve_instance(A, ws, b, lane);
+    __syncwarp();
   }
 }
 
@@ -62,18 +64,9 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
   const double* obs = A.obs + (A.obs_per_instance ? (size_t)b * 3 * n_obs : 0);
   Stage st;
   rollout(pr, X0, u, lane, st);
-  const double tv = hasu ? T * u[0] : 0.0;
-  const double e03 = -tv * st.cps * st.sth, e13 = -tv * st.sps * st.sth, e23 = tv * st.cth, e04 = -tv * st.sps * st.cth, e14 = tv * st.cps * st.cth;
-  auto adjoint = [&](const double* a, double* lamn) {
-    double lam[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i == 3 || i == 4) continue;
-      lam[i] = rscan_incl(act ? a[i] : 0.0, lane); lamn[i] = shfl_next(lam[i], lane);
-    }
-    lam[3] = rscan_incl((act ? a[3] : 0.0) + e03 * lamn[0] + e13 * lamn[1] + e23 * lamn[2], lane); lamn[3] = shfl_next(lam[3], lane);
-    lam[4] = rscan_incl((act ? a[4] : 0.0) + e04 * lamn[0] + e14 * lamn[1], lane); lamn[4] = shfl_next(lam[4], lane);
-  };
+  const Dyn dyn = dyn_entries(st, hasu ? T * u[0] : 0.0);
+  const double e03 = dyn.e03, e13 = dyn.e13, e23 = dyn.e23, e04 = dyn.e04, e14 = dyn.e14;
+  auto adjoint = [&](const double* a, double* lamn) { nmpc::adjoint(a, dyn, act, lane, lamn); };
   auto Bt = [&](const double* lamn, double* out) {
     out[0] = T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]);
 #pragma unroll
@@ -135,12 +128,19 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
     adjoint(a, lamn);
     // linearised rollout of the direction v
     double dx[8];
+    {
+      double a5[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) dx[3 + c] = scan_excl(hasu ? T * vv[c + 1] : 0.0, lane);
-    const double tvv = hasu ? T * vv[0] : 0.0;
-    dx[0] = scan_excl(e03 * dx[3] + e04 * dx[4] + tvv * st.cps * st.cth, lane);
-    dx[1] = scan_excl(e13 * dx[3] + e14 * dx[4] + tvv * st.sps * st.cth, lane);
-    dx[2] = scan_excl(e23 * dx[3] + tvv * st.sth, lane);
+      for (int c = 0; c < 5; ++c) a5[c] = hasu ? T * vv[c + 1] : 0.0;
+      scan_excl<5>(a5, lane);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) dx[3 + c] = a5[c];
+      const double tvv = hasu ? T * vv[0] : 0.0;
+      double a3[3] = {e03 * dx[3] + e04 * dx[4] + tvv * st.cps * st.cth, e13 * dx[3] + e14 * dx[4] + tvv * st.sps * st.cth,
+                      e23 * dx[3] + tvv * st.sth};
+      scan_excl<3>(a3, lane);
+      dx[0] = a3[0]; dx[1] = a3[1]; dx[2] = a3[2];
+    }
     // w_x = Q dx + S^T v_u,  w_u = S dx
     double wx[8], wu0 = 0.0;
 #pragma unroll
@@ -228,7 +228,8 @@ static int fail(const std::string& m) { g_err = m; return 1; }
 struct nmpc_handle {
   nmpc_spec spec; int device; int sm_count;
   Prob pr; Opt opt;
-  int ws_doubles, warps, blocks_per_sm;
+  int ws_doubles, blocks_per_sm, max_blocks;
+  double* d_ric; int ric_stride;
   int* d_counter; unsigned long long* d_stats;
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
@@ -267,14 +268,14 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   h->opt.max_iter = spec->max_iter > 0 ? spec->max_iter : 100;
   h->opt.scaling = spec->scaling; h->opt.tol = spec->tol > 0 ? spec->tol : 1e-8;
   h->ws_doubles = ws_size(h->pr.S, h->pr.R, h->pr.n_obs);
-  const size_t per_warp = (size_t)h->ws_doubles * sizeof(double);
-  const size_t max_smem = prop.sharedMemPerBlockOptin;
-  h->warps = WARPS_MAX;
-  while (h->warps > 1 && per_warp * h->warps > max_smem) --h->warps;
-  if (per_warp * h->warps > max_smem) { delete h; return fail("nmpc_create: horizon / obstacle count needs more shared memory than one SM has"); }
-  CK(cudaFuncSetAttribute(nmpc_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * h->warps)));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, nmpc_ipm_kernel, h->warps * 32, per_warp * h->warps));
+  const size_t smem = (size_t)h->ws_doubles * sizeof(double);
+  if (smem > prop.sharedMemPerBlockOptin) { delete h; return fail("nmpc_create: horizon / obstacle count needs more shared memory than one SM has"); }
+  CK(cudaFuncSetAttribute(nmpc_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, nmpc_ipm_kernel, 32, smem));
   if (h->blocks_per_sm < 1) { delete h; return fail("nmpc_create: kernel does not fit on an SM"); }
+  h->max_blocks = h->sm_count * h->blocks_per_sm;
+  h->ric_stride = RIC_N * h->pr.N;
+  CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks));   // L2-resident Riccati scratch
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));
@@ -299,7 +300,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
 int nmpc_destroy(nmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
+  void* ptrs[] = {h->d_ric, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
                   h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -324,15 +325,12 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
   A.x = x; A.f = f; A.g = g; A.lam_x = lam_x; A.lam_g = lam_g; A.status = status; A.iters = iters;
   A.counter = h->d_counter; A.stats = h->d_stats; A.ws_doubles = h->ws_doubles;
+  A.ric = h->d_ric; A.ric_stride = h->ric_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
-  const int threads = h->warps * 32;
-  int blocks = (B + h->warps - 1) / h->warps;
-  const int maxb = h->sm_count * h->blocks_per_sm;
-  if (blocks > maxb) blocks = maxb;
-  const size_t smem = (size_t)h->ws_doubles * sizeof(double) * h->warps;
-  nmpc_ipm_kernel<<<blocks, threads, smem, s>>>(A);
+  const int blocks = B < h->max_blocks ? B : h->max_blocks;
+  nmpc_ipm_kernel<<<blocks, 32, (size_t)h->ws_doubles * sizeof(double), s>>>(A);
   CK(cudaGetLastError());
   h->last_stream = s; h->launches = 1;
   return 0;

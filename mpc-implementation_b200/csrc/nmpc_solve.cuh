@@ -5,8 +5,12 @@
 // options (NMPC_TT.py:257-265): slack form g(w) - s = 0, relaxed bounds, gradient-based scaling,
 // monotone barrier, fraction-to-boundary, inertia correction, filter line search + second-order
 // correction, scaled optimality-error termination.  The whole iteration loop runs inside the kernel.
+//
+// v2 structure: the iterate lives in shared memory; every phase is a __noinline__ function that loads its
+// operands, works in registers and stores back, so each heavy code sequence exists exactly once.
 #pragma once
 #include "nmpc_device.cuh"
+#include "nmpc_riccati.cuh"
 
 namespace nmpc {
 
@@ -34,22 +38,38 @@ struct SolveArgs {
   int32_t *status, *iters;
   int* counter;                      // work queue
   unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
-  int ws_doubles;                    // per-warp workspace size
+  double* ric; int ric_stride;       // L2-resident Riccati scratch, one slice per resident warp
+  int ws_doubles;                    // per-warp shared-memory workspace
   double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][8] (tests only)
 };
 
+// shared-memory workspace of one warp
+struct Ws { double *lv, *rows, *lq, *soc, *stg, *obs, *filt, *res, *par, *ric; };
+
+__host__ __device__ inline bool soc_aliases_lq(int R) { return 3 * R + 14 <= LQ_DEAD; }
 __host__ __device__ inline int ws_size(int S, int R, int n_obs) {
-  int n = A_NROW * R * S + LQ_N * S + RIC_N * S + 3 * n_obs + 2 * FILT_CAP;
+  int n = LV_N * S + A_NROW * R * S + LQ_N * S + (soc_aliases_lq(R) ? 0 : (3 * R + 14) * S) + STG_N + 3 * n_obs + 2 * FILT_CAP + 24 + 12;
   return (n + 1) & ~1;
+}
+__device__ __forceinline__ Ws carve(double* base, int S, int R, int n_obs) {
+  Ws w; double* q = base;
+  w.lv = q; q += LV_N * S;
+  w.rows = q; q += A_NROW * R * S;
+  w.lq = q; q += LQ_N * S;
+  if (soc_aliases_lq(R)) w.soc = w.lq; else { w.soc = q; q += (3 * R + 14) * S; }
+  w.stg = q; q += STG_N;
+  w.obs = q; q += 3 * n_obs;
+  w.filt = q; q += 2 * FILT_CAP;
+  w.res = q; q += 24;
+  w.par = q;
+  w.ric = nullptr;
+  return w;
 }
 
 constexpr double EPSM = 2.220446049250313e-16;
 __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * EPSM * fabs(bas); }
-__device__ __forceinline__ bool is_lo(double b) { return b > -1e300; }
-__device__ __forceinline__ bool is_hi(double b) { return b < 1e300; }
 
-__device__ __forceinline__ double push_in(double v, double lo, double hi, double k1, double k2) {
-  const bool hl = is_lo(lo), hu = is_hi(hi);
+__device__ __forceinline__ double push_in(double v, double lo, double hi, bool hl, bool hu, double k1, double k2) {
   if (hl && hu) {
     const double pl = fmin(k1 * fmax(1.0, fabs(lo)), k2 * (hi - lo));
     const double pu = fmin(k1 * fmax(1.0, fabs(hi)), k2 * (hi - lo));
@@ -59,455 +79,619 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi, double
   return v;
 }
 
-// ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void solve_instance(const SolveArgs& A, double* __restrict__ ws, int b, int lane) {
-  const Prob& pr = A.pr; const Opt& o = A.o;
-  const int N = pr.N, S = pr.S, R = pr.R, n_obs = pr.n_obs;
-  const bool act = lane <= N, hasu = lane < N;
-  const double T = pr.T;
-  double* rows = ws;
-  double* lq = rows + A_NROW * R * S;
-  double* ric = lq + LQ_N * S;
-  double* obs = ric + RIC_N * S;
-  double* filt = obs + 3 * n_obs;
-#define RW(arr, r) rows[((arr) * R + (r)) * S + lane]
-#define LQ(e) lq[(e) * S + lane]
-  const double NINF = -CUDART_INF, PINF = CUDART_INF;
+struct Bnd { double lo, hi; bool hl, hu; };
+// relaxed bounds of control i of stage k (NMPC_TT.py:294-306) and of the scaled row r of stage k (:275-291)
+__device__ __forceinline__ Bnd ctl_bounds(const SolveArgs& A, int k, int i) {
+  const double lo = __ldg(A.lbx + NU * k + i), hi = __ldg(A.ubx + NU * k + i);
+  Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
+  b.lo = b.hl ? lo - A.o.bound_relax * fmax(1.0, fabs(lo)) : -CUDART_INF;
+  b.hi = b.hu ? hi + A.o.bound_relax * fmax(1.0, fabs(hi)) : CUDART_INF;
+  return b;
+}
+__device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, double dc) {
+  const double lo = __ldg(A.lbg + k * A.pr.R + r), hi = __ldg(A.ubg + k * A.pr.R + r);
+  Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
+  const double l2 = dc * lo, h2 = dc * hi;
+  b.lo = b.hl ? l2 - A.o.bound_relax * fmax(1.0, fabs(l2)) : -CUDART_INF;
+  b.hi = b.hu ? h2 + A.o.bound_relax * fmax(1.0, fabs(h2)) : CUDART_INF;
+  return b;
+}
 
-  // ---------------- load instance ------------------------------------------------------------
-  double X0[8], xt, yt;
-  {
-    const double* pp = A.p + (size_t)b * NPAR;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) X0[i] = pp[i];
-    xt = pp[8]; yt = pp[9];
-  }
-  double u[6], xL[6], xU[6], zL[6], zU[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { u[i] = 0.0; xL[i] = NINF; xU[i] = PINF; zL[i] = 0.0; zU[i] = 0.0; }
-  if (hasu) {
+#define LV(e) ws.lv[(e) * S + lane]
+#define RW(arr, r) ws.rows[((arr) * R + (r)) * S + lane]
+#define LQ(e) ws.lq[(e) * S + lane]
+#define SOC(e) ws.soc[(e) * S + lane]
+#define SOC_DS2 0
+#define SOC_CSOC (R)
+#define SOC_CT (2 * R)
+#define SOC_DUS (3 * R)
+#define SOC_Q2 (3 * R + 6)
+
+// T-scaled non-zeros of the dynamics Jacobian A_k - I of this lane's stage
+struct Dyn { double e03, e13, e23, e04, e14; };
+__device__ __forceinline__ Dyn dyn_entries(const Stage& s, double tv) {
+  Dyn d; d.e03 = -tv * s.cps * s.sth; d.e13 = -tv * s.sps * s.sth; d.e23 = tv * s.cth;
+  d.e04 = -tv * s.sps * s.cth; d.e14 = tv * s.cps * s.cth;
+  return d;
+}
+// adjoint recursion lam_k = a_k + A_k^T lam_{k+1} by suffix scans; returns lam_{k+1} in lamn
+__device__ __forceinline__ void adjoint(const double* a, const Dyn& d, bool act, int lane, double* lamn) {
+  double v[6] = {act ? a[0] : 0.0, act ? a[1] : 0.0, act ? a[2] : 0.0, act ? a[5] : 0.0, act ? a[6] : 0.0, act ? a[7] : 0.0};
+  rscan_incl<6>(v, lane);
+  lamn[0] = shfl_next(v[0], lane); lamn[1] = shfl_next(v[1], lane); lamn[2] = shfl_next(v[2], lane);
+  lamn[5] = shfl_next(v[3], lane); lamn[6] = shfl_next(v[4], lane); lamn[7] = shfl_next(v[5], lane);
+  double w[2] = {(act ? a[3] : 0.0) + d.e03 * lamn[0] + d.e13 * lamn[1] + d.e23 * lamn[2],
+                 (act ? a[4] : 0.0) + d.e04 * lamn[0] + d.e14 * lamn[1]};
+  rscan_incl<2>(w, lane);
+  lamn[3] = shfl_next(w[0], lane); lamn[4] = shfl_next(w[1], lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// load one instance: p -> par, warm start -> LV_U, obstacle table, unit scaling
+__device__ __noinline__ void ph_load(const SolveArgs& A, const Ws& ws, int b, int lane) {
+  const int N = A.pr.N, S = A.pr.S, R = A.pr.R, n_obs = A.pr.n_obs;
+  if (lane < NPAR) ws.par[lane] = A.p[(size_t)b * NPAR + lane];
+  const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * n_obs : 0);
+  for (int i = lane; i < 3 * n_obs; i += 32) ws.obs[i] = ob[i];
+  if (lane <= N) {
     const double* xx = A.x0 + (size_t)b * (NU * N) + NU * lane;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      u[i] = xx[i];
-      const double lo = A.lbx[NU * lane + i], hi = A.ubx[NU * lane + i];
-      xL[i] = lo > -1e19 ? lo - o.bound_relax * fmax(1.0, fabs(lo)) : NINF;
-      xU[i] = hi < 1e19 ? hi + o.bound_relax * fmax(1.0, fabs(hi)) : PINF;
-    }
-  }
-  {
-    const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * n_obs : 0);
-    for (int i = lane; i < 3 * n_obs; i += 32) obs[i] = ob[i];
+    for (int i = 0; i < 6; ++i) { LV(LV_U + i) = lane < N ? xx[i] : 0.0; LV(LV_DU + i) = 0.0; }
+    for (int r = 0; r < R; ++r) { RW(A_DC, r) = 1.0; RW(A_DS, r) = 0.0; }
   }
   __syncwarp();
+}
 
-  Stage st;
-  double df = 1.0;
-  if (act) for (int r = 0; r < R; ++r) RW(A_DC, r) = 1.0;
-
-  // stage-local helpers ------------------------------------------------------------------------
-  // T-scaled dynamics Jacobian entries of this lane's stage
-  double e03, e13, e23, e04, e14;
-  auto dyn_entries = [&](const Stage& s_, const double* u_) {
-    const double tv = hasu ? T * u_[0] : 0.0;
-    e03 = -tv * s_.cps * s_.sth; e13 = -tv * s_.sps * s_.sth; e23 = tv * s_.cth;
-    e04 = -tv * s_.sps * s_.cth; e14 = tv * s_.cps * s_.cth;
-  };
-  // adjoint recursion lam_k = a_k + A_k^T lam_{k+1} by suffix scans
-  auto adjoint = [&](const double* a, double* lam, double* lamn) {
+// gradient-based scaling at the user's starting point (IPOPT nlp_scaling_method = gradient-based): returns df, sets DC
+__device__ __noinline__ double ph_scaling(const SolveArgs& A, const Ws& ws, int lane) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R, n_obs = pr.n_obs; const double T = pr.T;
+  const bool act = lane <= N, hasu = lane < N;
+  double u[6];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i == 3 || i == 4) continue;
-      lam[i] = rscan_incl(act ? a[i] : 0.0, lane); lamn[i] = shfl_next(lam[i], lane);
-    }
-    const double b3 = (act ? a[3] : 0.0) + e03 * lamn[0] + e13 * lamn[1] + e23 * lamn[2];
-    const double b4 = (act ? a[4] : 0.0) + e04 * lamn[0] + e14 * lamn[1];
-    lam[3] = rscan_incl(b3, lane); lamn[3] = shfl_next(lam[3], lane);
-    lam[4] = rscan_incl(b4, lane); lamn[4] = shfl_next(lam[4], lane);
-  };
-  // scaled constraint values of stage `lane` into row array `arr`
-  auto eval_g = [&](const Stage& s_, int arr) {
-    if (act) {
+  for (int i = 0; i < 6; ++i) u[i] = act ? LV(LV_U + i) : 0.0;
+  Stage st; rollout(pr, ws.par, u, lane, st);
+  const Dyn dy = dyn_entries(st, hasu ? T * u[0] : 0.0);
+  double gl[6], Hl[21], a[8], lamn[8];
 #pragma unroll
-      for (int r = 0; r < 5; ++r) RW(arr, r) = RW(A_DC, r) * s_.X[box_state(r)];
+  for (int i = 0; i < 8; ++i) a[i] = 0.0;
+  if (hasu && lane >= 1) {
+    stage_cost_d2(pr, st.X, ws.par[8], ws.par[9], gl, Hl);
+#pragma unroll
+    for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
+  }
+  adjoint(a, dy, act, lane, lamn);
+  double gmax = 0.0;
+  if (hasu) {
+    gmax = fabs(T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]));
+#pragma unroll
+    for (int r = 1; r < 6; ++r) gmax = fmax(gmax, fabs(T * lamn[r + 2]));
+  }
+  gmax = warp_max(gmax);
+  // row maxima of the Jacobian: |d g_{k,i} / d u_j| for j < k
+  const double d0 = st.cps * st.cth, d1 = st.sps * st.cth, d2 = st.sth;
+  double c3[3] = {dy.e03, dy.e13, dy.e23}, c4[2] = {dy.e04, dy.e14};
+  scan_excl<3>(c3, lane); scan_excl<2>(c4, lane);
+  double zmax = 0.0;
+  // scratch in row arrays that are not live yet: A_G = row max, A_IL / A_IU = obstacle normal
+  if (act) for (int jn = 0; jn < n_obs; ++jn) {
+    const double dx_ = st.X[0] - ws.obs[3 * jn], dy_ = st.X[1] - ws.obs[3 * jn + 1];
+    const double iD = rsqrt(dx_ * dx_ + dy_ * dy_);
+    RW(A_G, 5 + jn) = 0.0; RW(A_IL, 5 + jn) = dx_ * iD; RW(A_IU, 5 + jn) = dy_ * iD;
+  }
+  for (int jj = 0; jj < N; ++jj) {
+    const double dj0 = __shfl_sync(FULL, d0, jj), dj1 = __shfl_sync(FULL, d1, jj), dj2 = __shfl_sync(FULL, d2, jj);
+    const double a30 = __shfl_sync(FULL, c3[0], jj + 1), a31 = __shfl_sync(FULL, c3[1], jj + 1), a32 = __shfl_sync(FULL, c3[2], jj + 1);
+    const double a40 = __shfl_sync(FULL, c4[0], jj + 1), a41 = __shfl_sync(FULL, c4[1], jj + 1);
+    if (act && jj < lane) {
+      const double pv0 = T * dj0, pv1 = T * dj1, pv2 = T * dj2;
+      const double pt0 = T * (c3[0] - a30), pt1 = T * (c3[1] - a31), pt2 = T * (c3[2] - a32);
+      const double pp0 = T * (c4[0] - a40), pp1 = T * (c4[1] - a41);
+      zmax = fmax(zmax, fmax(fabs(pv2), fabs(pt2)));
       for (int jn = 0; jn < n_obs; ++jn) {
-        const double dx_ = s_.X[0] - obs[3 * jn], dy_ = s_.X[1] - obs[3 * jn + 1];
-        RW(arr, 5 + jn) = RW(A_DC, 5 + jn) * (obs[3 * jn + 2] - sqrt(dx_ * dx_ + dy_ * dy_));
+        const double nx = RW(A_IL, 5 + jn), ny = RW(A_IU, 5 + jn);
+        const double m1 = fabs(nx * pv0 + ny * pv1), m2 = fabs(nx * pt0 + ny * pt1), m3 = fabs(nx * pp0 + ny * pp1);
+        RW(A_G, 5 + jn) = fmax(RW(A_G, 5 + jn), fmax(m1, fmax(m2, m3)));
       }
     }
-  };
-  auto cost_sum = [&](const Stage& s_) -> double {
-    const double l = hasu ? stage_cost(pr, s_.X, xt, yt) : 0.0;
-    return df * warp_sum(l);
-  };
-
-  // ---------------- gradient-based scaling at the user's starting point ----------------------
-  if (o.scaling) {
-    rollout(pr, X0, u, lane, st);
-    dyn_entries(st, u);
-    double gl[6], Hl[21], a[8], lam[8], lamn[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.0;
-    if (hasu && lane >= 1) {
-      stage_cost_d2(pr, st.X, xt, yt, gl, Hl);
-#pragma unroll
-      for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
-    }
-    adjoint(a, lam, lamn);
-    double gmax = 0.0;
-    if (hasu) {
-      gmax = fabs(T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]));
-#pragma unroll
-      for (int r = 1; r < 6; ++r) gmax = fmax(gmax, fabs(T * lamn[r + 2]));
-    }
-    gmax = warp_max(gmax);
-    // row maxima of the Jacobian: |d g_{k,i} / d u_j| for j < k
-    const double d0 = st.cps * st.cth, d1 = st.sps * st.cth, d2 = st.sth;
-    const double c30 = scan_excl(e03, lane), c31 = scan_excl(e13, lane), c32 = scan_excl(e23, lane);
-    const double c40 = scan_excl(e04, lane), c41 = scan_excl(e14, lane);
-    double zmax = 0.0;
-    // scratch in row arrays that are not live yet: A_GT = row max, A_DS / A_DS2 = obstacle normal
-    if (act) for (int jn = 0; jn < n_obs; ++jn) {
-      const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
-      const double iD = 1.0 / sqrt(dx_ * dx_ + dy_ * dy_);
-      RW(A_GT, 5 + jn) = 0.0; RW(A_DS, 5 + jn) = dx_ * iD; RW(A_DS2, 5 + jn) = dy_ * iD;
-    }
-    for (int jj = 0; jj < N; ++jj) {
-      const double dj0 = __shfl_sync(FULL, d0, jj), dj1 = __shfl_sync(FULL, d1, jj), dj2 = __shfl_sync(FULL, d2, jj);
-      const double a30 = __shfl_sync(FULL, c30, jj + 1), a31 = __shfl_sync(FULL, c31, jj + 1), a32 = __shfl_sync(FULL, c32, jj + 1);
-      const double a40 = __shfl_sync(FULL, c40, jj + 1), a41 = __shfl_sync(FULL, c41, jj + 1);
-      if (act && jj < lane) {
-        const double pv0 = T * dj0, pv1 = T * dj1, pv2 = T * dj2;
-        const double pt0 = T * (c30 - a30), pt1 = T * (c31 - a31), pt2 = T * (c32 - a32);
-        const double pp0 = T * (c40 - a40), pp1 = T * (c41 - a41);
-        zmax = fmax(zmax, fmax(fabs(pv2), fabs(pt2)));
-        for (int jn = 0; jn < n_obs; ++jn) {
-          const double nx = RW(A_DS, 5 + jn), ny = RW(A_DS2, 5 + jn);
-          const double m1 = fabs(nx * pv0 + ny * pv1), m2 = fabs(nx * pt0 + ny * pt1), m3 = fabs(nx * pp0 + ny * pp1);
-          RW(A_GT, 5 + jn) = fmax(RW(A_GT, 5 + jn), fmax(m1, fmax(m2, m3)));
-        }
-      }
-    }
-    if (act) {
-      auto sc = [&](double m) { return m > o.max_grad ? fmax(o.scal_min, o.max_grad / m) : 1.0; };
-      RW(A_DC, 0) = sc(zmax);
-      const double lin = lane >= 1 ? T : 0.0;
-#pragma unroll
-      for (int r = 1; r < 5; ++r) RW(A_DC, r) = sc(lin);
-      for (int jn = 0; jn < n_obs; ++jn) RW(A_DC, 5 + jn) = sc(RW(A_GT, 5 + jn));
-    }
-    df = gmax > o.max_grad ? fmax(o.scal_min, o.max_grad / gmax) : 1.0;
   }
-  // ---------------- scaled + relaxed constraint bounds ---------------------------------------
   if (act) {
-    for (int r = 0; r < R; ++r) {
-      const double lo = A.lbg[lane * R + r], hi = A.ubg[lane * R + r], dc = RW(A_DC, r);
-      double l2 = NINF, h2 = PINF;
-      if (lo > -1e19) { l2 = dc * lo; l2 -= o.bound_relax * fmax(1.0, fabs(l2)); }
-      if (hi < 1e19) { h2 = dc * hi; h2 += o.bound_relax * fmax(1.0, fabs(h2)); }
-      RW(A_DL, r) = l2; RW(A_DU, r) = h2;
-    }
+    const double mg = A.o.max_grad, smin = A.o.scal_min;
+    RW(A_DC, 0) = zmax > mg ? fmax(smin, mg / zmax) : 1.0;
+    const double lin = lane >= 1 ? T : 0.0, sl = lin > mg ? fmax(smin, mg / lin) : 1.0;
+#pragma unroll
+    for (int r = 1; r < 5; ++r) RW(A_DC, r) = sl;
+    for (int jn = 0; jn < n_obs; ++jn) { const double m = RW(A_G, 5 + jn); RW(A_DC, 5 + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
   }
-  // ---------------- starting point -------------------------------------------------------------
+  __syncwarp();
+  return gmax > A.o.max_grad ? fmax(A.o.scal_min, A.o.max_grad / gmax) : 1.0;
+}
+
+// constraint value of row r of this lane's stage (unscaled) and, for obstacle rows, the unit normal
+__device__ __forceinline__ double row_value(const Ws& ws, const double* X, int r, double& nx, double& ny, double& iD) {
+  if (r < 5) { nx = 0.0; ny = 0.0; iD = 0.0; return X[box_state(r)]; }
+  const int jn = r - 5;
+  const double dx_ = X[0] - ws.obs[3 * jn], dy_ = X[1] - ws.obs[3 * jn + 1];
+  const double d2 = dx_ * dx_ + dy_ * dy_;
+  const double D = sqrt(d2);
+  iD = rcp(D); nx = dx_ * iD; ny = dy_ * iD;
+  return ws.obs[3 * jn + 2] - D;
+}
+
+// starting point: push controls and slacks inside their bounds, unit bound multipliers; returns #finite bounds
+__device__ __noinline__ int ph_start(const SolveArgs& A, const Ws& ws, int lane) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  const bool act = lane <= N, hasu = lane < N;
+  double u[6]; int nz = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
-    if (hasu) { u[i] = push_in(u[i], xL[i], xU[i], o.bound_push, o.bound_frac); zL[i] = is_lo(xL[i]) ? 1.0 : 0.0; zU[i] = is_hi(xU[i]) ? 1.0 : 0.0; }
+    u[i] = act ? LV(LV_U + i) : 0.0;
+    if (hasu) {
+      const Bnd b = ctl_bounds(A, lane, i);
+      u[i] = push_in(u[i], b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
+      LV(LV_U + i) = u[i]; LV(LV_ZL + i) = b.hl ? 1.0 : 0.0; LV(LV_ZU + i) = b.hu ? 1.0 : 0.0;
+      nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
+    } else if (act) { LV(LV_ZL + i) = 0.0; LV(LV_ZU + i) = 0.0; }
   }
-  rollout(pr, X0, u, lane, st);
-  double f = cost_sum(st);
-  eval_g(st, A_G);
+  Stage st; rollout(pr, ws.par, u, lane, st);
+  if (act) for (int r = 0; r < R; ++r) {
+    double nx, ny, iD; const double dc = RW(A_DC, r);
+    const double g = dc * row_value(ws, st.X, r, nx, ny, iD);
+    const Bnd b = row_bounds(A, lane, r, dc);
+    const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
+    RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = 0.0;
+    RW(A_VL, r) = b.hl ? 1.0 : 0.0; RW(A_VU, r) = b.hu ? 1.0 : 0.0;
+    RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
+    nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
+  }
+  __syncwarp();
+  return __reduce_add_sync(FULL, nz);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// derivatives at the current point: stage Hessian blocks / gradients of the LQ sub-problem into LQ, optimality
+// error ingredients into res.  ls = least-squares multiplier system (W = 0, Sigma = I, rhs = gradient of L).
+__device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lane, bool ls, double df) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R; const double T = pr.T;
+  const bool act = lane <= N, hasu = lane < N;
+  double u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = act ? LV(LV_U + i) : 0.0;
+  Stage st; rollout(pr, ws.par, u, lane, st);
+  const Dyn dy = dyn_entries(st, hasu ? T * u[0] : 0.0);
+  double gl[6], Hl[21];
+#pragma unroll
+  for (int v = 0; v < 6; ++v) gl[v] = 0.0;
+#pragma unroll
+  for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
+  double l = 0.0;
+  if (hasu) {
+    l = stage_cost_d2(pr, st.X, ws.par[8], ws.par[9], gl, Hl);
+    if (lane == 0) {   // stage 0 is constant in w
+#pragma unroll
+      for (int v = 0; v < 6; ++v) gl[v] = 0.0;
+#pragma unroll
+      for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
+    }
+  }
+  const double fsum = df * warp_sum(l);
+  double a[8], qa[8], qb[8], qd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.0; qa[i] = 0.0; qb[i] = 0.0; qd[i] = 0.0; }
+  double du_l = 0.0, pr_l = 0.0, sumy = 0.0, sumz = 0.0, viol = 0.0, pmax = 0.0, pmin = CUDART_INF;
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) LV(LV_X + i) = st.X[i];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) { gl[v] *= df; LV(LV_GL + v) = gl[v]; a[cost_state(v)] = gl[v]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qa[i] = a[i];
+    double q66[21], q22 = 0.0, nn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 21; ++e) q66[e] = ls ? 0.0 : df * Hl[e];
+    for (int r = 0; r < R; ++r) {
+      double nx, ny, iD; const double dc = RW(A_DC, r);
+      const double gu = row_value(ws, st.X, r, nx, ny, iD), g = dc * gu;
+      const double s = RW(A_S, r), y = RW(A_Y, r), vl = RW(A_VL, r), vu = RW(A_VU, r), il = RW(A_IL, r), iu = RW(A_IU, r);
+      const bool hl = il > 0.0, hu = iu > 0.0;
+      RW(A_G, r) = g;
+      const double c = g - s;
+      const double sig = ls ? 1.0 : vl * il + vu * iu;
+      double beta = iu - il;                              // barrier gradient per unit mu (with damping)
+      if (hl && !hu) beta += A.o.kappa_d;
+      if (hu && !hl) beta -= A.o.kappa_d;
+      const double ya = ls ? (vu - vl) : sig * c;         // delta_w- and mu-free part of y-hat
+      const double w = dc * dc * sig;
+      if (r < 5) {
+        const int i = box_state(r);
+        a[i] += dc * y; qa[i] += dc * ya; qb[i] += dc * beta; qd[i] += dc * c;
+        if (r == 0) q66[tri(2, 2)] += w; else if (r == 1) q22 += w; else if (r == 2) q66[tri(3, 3)] += w;
+        else if (r == 3) q66[tri(4, 4)] += w; else q66[tri(5, 5)] += w;
+      } else {
+        const double cur = ls ? 0.0 : -y * dc * iD;        // y * d2h,  d2h = -(I - n n^T)/D
+        q66[tri(0, 0)] += w * nx * nx + cur * (1.0 - nx * nx);
+        q66[tri(1, 0)] += w * nx * ny - cur * nx * ny;
+        q66[tri(1, 1)] += w * ny * ny + cur * (1.0 - ny * ny);
+        nn[0] += dc * dc * nx * nx; nn[1] += dc * dc * nx * ny; nn[2] += dc * dc * ny * ny;
+        const double gy = -dc * y, ga = -dc * ya, gb = -dc * beta, gd = -dc * c;
+        a[0] += gy * nx; a[1] += gy * ny; qa[0] += ga * nx; qa[1] += ga * ny;
+        qb[0] += gb * nx; qb[1] += gb * ny; qd[0] += gd * nx; qd[1] += gd * ny;
+      }
+      // optimality-error ingredients
+      du_l = fmax(du_l, fabs(-y - vl + vu)); pr_l = fmax(pr_l, fabs(c)); sumy += fabs(y); sumz += vl + vu;
+      const Bnd b = row_bounds(A, lane, r, dc);
+      if (b.hl) { const double pz = (s - b.lo) * vl; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
+      if (b.hu) { const double pz = (b.hi - s) * vu; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
+      const double lo_o = __ldg(A.lbg + lane * R + r), hi_o = __ldg(A.ubg + lane * R + r);
+      if (lo_o > -1e19) viol = fmax(viol, lo_o - gu);
+      if (hi_o < 1e19) viol = fmax(viol, gu - hi_o);
+    }
+#pragma unroll
+    for (int e = 0; e < 21; ++e) LQ(LQ_Q + e) = q66[e];
+    LQ(LQ_Q + 21) = q22; LQ(LQ_Q + 22) = 0.0; LQ(LQ_Q + 23) = 0.0;
+    LQ(LQ_NN + 0) = nn[0]; LQ(LQ_NN + 1) = nn[1]; LQ(LQ_NN + 2) = nn[2];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) { const double dc = RW(A_DC, r); LQ(LQ_DG + r) = dc * dc; }
+    LQ(LQ_ZERO) = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { LQ(LQ_QA + i) = qa[i]; LQ(LQ_QB + i) = ls ? 0.0 : qb[i]; LQ(LQ_QD + i) = ls ? 0.0 : qd[i]; }
+    LQ(LQ_DD + 0) = st.cps * st.cth; LQ(LQ_DD + 1) = st.sps * st.cth; LQ(LQ_DD + 2) = st.sth;
+    LQ(LQ_EE + 0) = dy.e03; LQ(LQ_EE + 1) = dy.e13; LQ(LQ_EE + 2) = dy.e23; LQ(LQ_EE + 3) = dy.e04; LQ(LQ_EE + 4) = dy.e14;
+  }
+  double lamn[8];
+  adjoint(a, dy, act, lane, lamn);
+  if (act) {
+    double svt = 0.0, svp = 0.0;
+    if (hasu && !ls) {
+      // curvature of T*v*d(theta,psi) weighted by the next-stage adjoint
+      const double L0 = T * lamn[0], L1 = T * lamn[1], L2 = T * lamn[2], v = u[0];
+      const double cc = st.cps * st.cth, sc = st.sps * st.cth, cs = st.cps * st.sth, ss = st.sps * st.sth;
+      LQ(LQ_Q + 21) += -v * (L0 * cc + L1 * sc + L2 * st.sth);
+      LQ(LQ_Q + 23) = -v * (L0 * cc + L1 * sc);
+      LQ(LQ_Q + 22) = v * (L0 * ss - L1 * cs);
+      svt = -L0 * cs - L1 * ss + L2 * st.cth;
+      svp = -L0 * sc + L1 * cc;
+    }
+    LQ(LQ_SV + 0) = svt; LQ(LQ_SV + 1) = svp;
+    // controls: Sigma_x, gradient per unit mu, dual infeasibility, complementarity products
+    double glx[6];
+    glx[0] = T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]);
+#pragma unroll
+    for (int r = 1; r < 6; ++r) glx[r] = T * lamn[r + 2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double sig = 1.0, rb = 0.0;
+      if (hasu) {
+        const Bnd b = ctl_bounds(A, lane, i);
+        const double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
+        const double sl = u[i] - b.lo, su = b.hi - u[i];
+        if (ls) rb = zu - zl;
+        else {
+          const double il = b.hl ? rcp(sl) : 0.0, iu = b.hu ? rcp(su) : 0.0;
+          sig = zl * il + zu * iu; rb = iu - il;
+          if (b.hl && !b.hu) rb += A.o.kappa_d;
+          if (b.hu && !b.hl) rb -= A.o.kappa_d;
+        }
+        du_l = fmax(du_l, fabs(glx[i] - zl + zu)); sumz += zl + zu;
+        if (b.hl) { const double pz = sl * zl; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
+        if (b.hu) { const double pz = su * zu; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
+      }
+      LQ(LQ_RD + i) = sig; LQ(LQ_RB + i) = rb;
+    }
+  }
+  du_l = warp_max(du_l); pr_l = warp_max(pr_l); sumy = warp_sum(sumy); sumz = warp_sum(sumz);
+  viol = warp_max(viol); pmax = warp_max(pmax); pmin = warp_min(pmin);
+  if (lane == 0) {
+    ws.res[R_F] = fsum; ws.res[R_DU] = du_l; ws.res[R_PR] = pr_l; ws.res[R_SUMY] = sumy; ws.res[R_SUMZ] = sumz;
+    ws.res[R_VIOL] = viol; ws.res[R_PMAX] = pmax; ws.res[R_PMIN] = pmin;
+  }
+  __syncwarp();
+}
+
+// least-squares multipliers from the solved LS system: y = G dx + (v_U - v_L); zero if too large
+__device__ __noinline__ void ph_lsy(const SolveArgs& A, const Ws& ws, int lane, bool ok) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  const bool act = lane <= N;
+  double ymax = 0.0;
+  if (act && ok) {
+    double X[8], dx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); dx[i] = LV(LV_DX + i); }
+    for (int r = 0; r < R; ++r) {
+      double nx, ny, iD; row_value(ws, X, r, nx, ny, iD);
+      const double dc = RW(A_DC, r);
+      const double gd = r < 5 ? dc * dx[box_state(r)] : -dc * (nx * dx[0] + ny * dx[1]);
+      const double yv = gd + (RW(A_VU, r) - RW(A_VL, r));
+      RW(A_Y, r) = yv; ymax = fmax(ymax, fabs(yv));
+    }
+  }
+  ymax = warp_max(ymax);
+  if (!ok || !(ymax <= A.o.constr_mult_init_max)) { if (act) for (int r = 0; r < R; ++r) RW(A_Y, r) = 0.0; }
+  __syncwarp();
+}
+
+// step in the slacks, fraction-to-the-boundary limits, directional derivative of the barrier function.
+// soc: second-order-correction direction (residual CSOC, controls DUS, output DS2).
+__device__ __noinline__ void ph_dir(const SolveArgs& A, const Ws& ws, int lane, double mu, double tau, bool soc) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  const bool act = lane <= N, hasu = lane < N;
+  double tp = 0.0, dnum = 0.0, dden = 1.0, gbd = 0.0, theta = 0.0; bool nottiny = false;
+  const double tt = A.o.tiny_step_tol, kd = A.o.kappa_d;
+  auto dual_frac = [&](double z, double dz) {   // track max of -dz/z over dz < 0 as a fraction
+    if (dz < 0.0 && -dz * dden > dnum * z) { dnum = -dz; dden = z; }
+  };
+  if (act) {
+    double X[8], dx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); dx[i] = LV(LV_DX + i); }
+    for (int r = 0; r < R; ++r) {
+      double nx, ny, iD; row_value(ws, X, r, nx, ny, iD);
+      const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), vl = RW(A_VL, r), vu = RW(A_VU, r);
+      const bool hl = il > 0.0, hu = iu > 0.0;
+      const double c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) - s;
+      const double gd = r < 5 ? dc * dx[box_state(r)] : -dc * (nx * dx[0] + ny * dx[1]);
+      const double ds = gd + c;
+      if (soc) SOC(SOC_DS2 + r) = ds; else RW(A_DS, r) = ds;
+      tp = fmax(tp, fmax(-ds * il, ds * iu));
+      if (hl) dual_frac(vl, (mu - vl * ds) * il - vl);
+      if (hu) dual_frac(vu, (mu + vu * ds) * iu - vu);
+      double beta = iu - il;
+      if (hl && !hu) beta += kd;
+      if (hu && !hl) beta -= kd;
+      gbd += mu * beta * ds; theta += fabs(c);
+      nottiny = nottiny || (fabs(ds) > tt * (1.0 + fabs(s)));
+    }
+    if (hasu) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const Bnd b = ctl_bounds(A, lane, i);
+        const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
+        const double il = b.hl ? rcp(u - b.lo) : 0.0, iu = b.hu ? rcp(b.hi - u) : 0.0;
+        tp = fmax(tp, fmax(-du * il, du * iu));
+        if (b.hl) dual_frac(zl, (mu - zl * du) * il - zl);
+        if (b.hu) dual_frac(zu, (mu + zu * du) * iu - zu);
+        double beta = iu - il;
+        if (b.hl && !b.hu) beta += kd;
+        if (b.hu && !b.hl) beta -= kd;
+        gbd += mu * beta * du;
+        nottiny = nottiny || (fabs(du) > tt * (1.0 + fabs(u)));
+      }
+#pragma unroll
+      for (int v = 0; v < 6; ++v) gbd += LV(LV_GL + v) * dx[cost_state(v)];
+    }
+  }
+  tp = warp_max(tp);
+  const double td = warp_max(dnum / dden);
+  gbd = warp_sum(gbd); theta = warp_sum(theta);
+  const bool any_nt = __any_sync(FULL, nottiny);
+  if (lane == 0) {
+    ws.res[R_APR] = tp > tau ? tau / tp : 1.0;             // alpha = min(1, tau / max ratio)
+    ws.res[R_ADU] = td > tau ? tau / td : 1.0;
+    if (!soc) { ws.res[R_GBD] = gbd; ws.res[R_THETA] = theta; ws.res[R_TINY] = any_nt ? 0.0 : 1.0; }
+  }
+  __syncwarp();
+}
+
+// trial point u + alpha*du, s + alpha*ds: objective, constraint violation, barrier pieces; residual into CT
+__device__ __noinline__ void ph_trial(const SolveArgs& A, const Ws& ws, int lane, double alpha, bool soc, double df) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  const bool act = lane <= N, hasu = lane < N;
+  double ut[6], lb = 0.0, dt = 0.0;
+  double prod = 1.0; int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    ut[i] = 0.0;
+    if (hasu) {
+      ut[i] = fma(alpha, soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), LV(LV_U + i));   // same expression as ph_accept
+      const Bnd b = ctl_bounds(A, lane, i);
+      if (b.hl) prod *= ut[i] - b.lo;
+      if (b.hu) prod *= b.hi - ut[i];
+      if (b.hl && !b.hu) dt += ut[i] - b.lo;
+      if (b.hu && !b.hl) dt += b.hi - ut[i];
+      if (i == 2 || i == 5) { lb += n_log(prod); prod = 1.0; }
+    }
+  }
+  Stage st; rollout(pr, ws.par, ut, lane, st);
+  const double l = hasu ? stage_cost(pr, st.X, ws.par[8], ws.par[9]) : 0.0;
+  double th = 0.0;
   if (act) {
     for (int r = 0; r < R; ++r) {
-      const double lo = RW(A_DL, r), hi = RW(A_DU, r);
-      RW(A_S, r) = push_in(RW(A_G, r), lo, hi, o.bound_push, o.bound_frac);
-      RW(A_VL, r) = is_lo(lo) ? 1.0 : 0.0; RW(A_VU, r) = is_hi(hi) ? 1.0 : 0.0;
-      RW(A_Y, r) = 0.0;
+      double nx, ny, iD; const double dc = RW(A_DC, r);
+      const double g = dc * row_value(ws, st.X, r, nx, ny, iD);
+      const double sv = fma(alpha, soc ? SOC(SOC_DS2 + r) : RW(A_DS, r), RW(A_S, r));
+      const double ct = g - sv;
+      SOC(SOC_CT + r) = ct; th += fabs(ct);
+      const Bnd b = row_bounds(A, lane, r, dc);
+      if (b.hl) { prod *= sv - b.lo; ++cnt; }
+      if (b.hu) { prod *= b.hi - sv; ++cnt; }
+      if (b.hl && !b.hu) dt += sv - b.lo;
+      if (b.hu && !b.hl) dt += b.hi - sv;
+      if (cnt >= 4) { lb += n_log(prod); prod = 1.0; cnt = 0; }
+    }
+    if (cnt) lb += n_log(prod);
+  }
+  const double fs = df * warp_sum(l);
+  th = warp_sum(th); lb = warp_sum(lb); dt = warp_sum(dt);
+  if (lane == 0) { ws.res[R_FT] = fs; ws.res[R_THT] = th; ws.res[R_LBT] = lb; ws.res[R_DTT] = dt; }
+  __syncwarp();
+}
+
+// SOC right-hand side: c_soc <- a_soc * c_soc + c(trial);  q' = grad l + G^T((Sigma_s + dw) c_soc + mu beta)
+__device__ __noinline__ void ph_socrhs(const SolveArgs& A, const Ws& ws, int lane, double a_soc, double mu, double dw, bool first) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  if (lane <= N) {
+    double X[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); q[i] = 0.0; }
+#pragma unroll
+    for (int v = 0; v < 6; ++v) q[cost_state(v)] = LV(LV_GL + v);
+    for (int r = 0; r < R; ++r) {
+      double nx, ny, iD; row_value(ws, X, r, nx, ny, iD);
+      const double dc = RW(A_DC, r), il = RW(A_IL, r), iu = RW(A_IU, r);
+      const bool hl = il > 0.0, hu = iu > 0.0;
+      const double cprev = first ? RW(A_G, r) - RW(A_S, r) : SOC(SOC_CSOC + r);
+      const double cs = a_soc * cprev + SOC(SOC_CT + r);
+      SOC(SOC_CSOC + r) = cs;
+      double beta = iu - il;
+      if (hl && !hu) beta += A.o.kappa_d;
+      if (hu && !hl) beta -= A.o.kappa_d;
+      const double yh = (RW(A_VL, r) * il + RW(A_VU, r) * iu + dw) * cs + mu * beta;
+      if (r < 5) q[box_state(r)] += dc * yh; else { q[0] -= dc * yh * nx; q[1] -= dc * yh * ny; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) SOC(SOC_Q2 + i) = q[i];
+  }
+  __syncwarp();
+}
+
+// accept the trial point: primal step alpha, dual step a_du, kappa_Sigma reset, new reciprocal slacks
+__device__ __noinline__ void ph_accept(const SolveArgs& A, const Ws& ws, int lane, double alpha, double a_du, double mu, double dw, bool soc) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  const bool act = lane <= N, hasu = lane < N;
+  const double ks = A.o.kappa_sigma, kd = A.o.kappa_d, iks = 1.0 / A.o.kappa_sigma;
+  if (hasu) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const Bnd b = ctl_bounds(A, lane, i);
+      const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i);
+      double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
+      if (b.hl) zl += a_du * ((mu - zl * du) * rcp(u - b.lo) - zl);
+      if (b.hu) zu += a_du * ((mu + zu * du) * rcp(b.hi - u) - zu);
+      const double un = fma(alpha, du, u);
+      if (b.hl) { const double i2 = rcp(un - b.lo); zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
+      if (b.hu) { const double i2 = rcp(b.hi - un); zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
+      LV(LV_U + i) = un; LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu;
     }
   }
-  double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
-  const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
-  double theta_max, theta_min;
-  {
-    double th = 0.0;
-    if (act) for (int r = 0; r < R; ++r) th += fabs(RW(A_G, r) - RW(A_S, r));
-    th = warp_sum(th);
-    theta_max = o.theta_max_fact * fmax(1.0, th); theta_min = o.theta_min_fact * fmax(1.0, th);
+  if (act) for (int r = 0; r < R; ++r) {
+    const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
+    const double ds = soc ? SOC(SOC_DS2 + r) : RW(A_DS, r);
+    const bool hl = il > 0.0, hu = iu > 0.0;
+    double vl = RW(A_VL, r), vu = RW(A_VU, r);
+    double beta = iu - il;
+    if (hl && !hu) beta += kd;
+    if (hu && !hl) beta -= kd;
+    const double dy = (vl * il + vu * iu + dw) * ds + (mu * beta - y);
+    RW(A_Y, r) = y + alpha * dy;
+    if (hl) vl += a_du * ((mu - vl * ds) * il - vl);
+    if (hu) vu += a_du * ((mu + vu * ds) * iu - vu);
+    const double sn = fma(alpha, ds, s);
+    const Bnd b = row_bounds(A, lane, r, dc);
+    double il2 = 0.0, iu2 = 0.0;
+    if (hl) { il2 = rcp(sn - b.lo); vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
+    if (hu) { iu2 = rcp(b.hi - sn); vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
+    RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
   }
-  int nfilt = 0;
-  double dw_last = 0.0;
+  __syncwarp();
+}
+
+// outputs: honour the original bounds, unscale multipliers, f and g at the returned point
+__device__ __noinline__ void ph_output(const SolveArgs& A, const Ws& ws, int b, int lane, double df, int status, int iter) {
+  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+  const bool act = lane <= N, hasu = lane < N;
+  const int nw = NU * N, ng = R * S;
+  double u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = 0.0;
+  if (hasu) {
+    double* xo = A.x + (size_t)b * nw + NU * lane;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      u[i] = fmin(fmax(LV(LV_U + i), __ldg(A.lbx + NU * lane + i)), __ldg(A.ubx + NU * lane + i));
+      xo[i] = u[i];
+    }
+    if (A.lam_x) {
+      double* lo = A.lam_x + (size_t)b * nw + NU * lane;
+      const double idf = 1.0 / df;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) lo[i] = (LV(LV_ZU + i) - LV(LV_ZL + i)) * idf;
+    }
+  }
+  Stage st; rollout(pr, ws.par, u, lane, st);
+  const double l = hasu ? stage_cost(pr, st.X, ws.par[8], ws.par[9]) : 0.0;
+  const double fu = warp_sum(l);
+  if (lane == 0) {
+    if (A.f) A.f[b] = fu;
+    if (A.status) A.status[b] = status;
+    if (A.iters) A.iters[b] = iter;
+  }
+  if (act) {
+    if (A.g) {
+      double* go = A.g + (size_t)b * ng + lane * R;
+      for (int r = 0; r < R; ++r) { double nx, ny, iD; go[r] = row_value(ws, st.X, r, nx, ny, iD); }
+    }
+    if (A.lam_g) {
+      double* lo = A.lam_g + (size_t)b * ng + lane * R;
+      const double idf = 1.0 / df;
+      for (int r = 0; r < R; ++r) lo[r] = RW(A_Y, r) * RW(A_DC, r) * idf;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, int b, int lane) {
+  const Prob& pr = A.pr; const Opt& o = A.o;
+  const int S = pr.S, R = pr.R;
+  double* res = ws.res; double* filt = ws.filt;
   unsigned long long n_fact = 0, n_ls = 0, n_soc = 0;
 
-  // barrier pieces of the current point: LB = sum log(slack), DT = sum of one-sided slacks
-  auto barrier_parts = [&](const double* u_, int sarr_is_trial, double alpha, int dsarr, double& LB, double& DT) {
-    // slack values: s (current) or s + alpha*ds (trial)
-    double lb = 0.0, dt = 0.0;
-    if (hasu) {
-      double prod = 1.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const bool hl = is_lo(xL[i]), hu = is_hi(xU[i]);
-        if (hl) prod *= (u_[i] - xL[i]);
-        if (hu) prod *= (xU[i] - u_[i]);
-        if (hl && !hu) dt += u_[i] - xL[i];
-        if (hu && !hl) dt += xU[i] - u_[i];
-        if (i == 2 || i == 5) { lb += log(prod); prod = 1.0; }
-      }
-    }
-    if (act) {
-      double prod = 1.0; int cnt = 0;
-      for (int r = 0; r < R; ++r) {
-        const double sv = sarr_is_trial ? RW(A_S, r) + alpha * RW(dsarr, r) : RW(A_S, r);
-        const double lo = RW(A_DL, r), hi = RW(A_DU, r);
-        const bool hl = is_lo(lo), hu = is_hi(hi);
-        if (hl) { prod *= (sv - lo); ++cnt; }
-        if (hu) { prod *= (hi - sv); ++cnt; }
-        if (hl && !hu) dt += sv - lo;
-        if (hu && !hl) dt += hi - sv;
-        if (cnt >= 4) { lb += log(prod); prod = 1.0; cnt = 0; }
-      }
-      if (cnt) lb += log(prod);
-    }
-    LB = warp_sum(lb); DT = warp_sum(dt);
-  };
-  double LB, DT;
-  barrier_parts(u, 0, 0.0, A_DS, LB, DT);
-
-  // ---- derivative evaluation at the current point: fills Q (Hessian of the Lagrangian in stage form),
-  //      dynamics data, and returns the cost gradient gl (scaled by df) and the adjoint of the Lagrangian.
-  double gl[6], lam[8], lamn[8];
-  auto eval_derivs = [&](bool ls_mode) {
-    // ls_mode: least-squares multiplier system (W = 0, Sigma = I)
-    dyn_entries(st, u);
-    double Hl[21];
-#pragma unroll
-    for (int v = 0; v < 6; ++v) gl[v] = 0.0;
-#pragma unroll
-    for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
-    if (hasu && lane >= 1) {
-      stage_cost_d2(pr, st.X, xt, yt, gl, Hl);
-#pragma unroll
-      for (int v = 0; v < 6; ++v) gl[v] *= df;
-    }
-    double a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.0;
-    if (act) {
-#pragma unroll
-      for (int e = 0; e < 36; ++e) LQ(LQ_Q + e) = 0.0;
-      if (!ls_mode) {
-#pragma unroll
-        for (int uu = 0; uu < 6; ++uu)
-#pragma unroll
-          for (int v = 0; v <= uu; ++v) LQ(LQ_Q + tri(cost_state(uu), cost_state(v))) = df * Hl[tri(uu, v)];
-      }
-#pragma unroll
-      for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
-      // box rows
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const int i = box_state(r);
-        const double dc = RW(A_DC, r), sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r);
-        double sig = 1.0;
-        if (!ls_mode) sig = (is_lo(lo) ? RW(A_VL, r) / (sv - lo) : 0.0) + (is_hi(hi) ? RW(A_VU, r) / (hi - sv) : 0.0);
-        LQ(LQ_Q + tri(i, i)) += dc * dc * sig;
-        LQ(LQ_DG + r) = dc * dc;
-        a[i] += dc * RW(A_Y, r);
-      }
-      // obstacle rows
-      double nn0 = 0.0, nn1 = 0.0, nn2 = 0.0, q00 = 0.0, q01 = 0.0, q11 = 0.0;
-      for (int jn = 0; jn < n_obs; ++jn) {
-        const int r = 5 + jn;
-        const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
-        const double D = sqrt(dx_ * dx_ + dy_ * dy_), iD = 1.0 / D, nx = dx_ * iD, ny = dy_ * iD;
-        const double dc = RW(A_DC, r), sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r), yv = RW(A_Y, r);
-        double sig = 1.0;
-        if (!ls_mode) sig = (is_lo(lo) ? RW(A_VL, r) / (sv - lo) : 0.0) + (is_hi(hi) ? RW(A_VU, r) / (hi - sv) : 0.0);
-        const double w = dc * dc;
-        nn0 += w * nx * nx; nn1 += w * nx * ny; nn2 += w * ny * ny;
-        const double cur = ls_mode ? 0.0 : -yv * dc * iD;   // y * d2h,  d2h = -(I - n n^T)/D
-        q00 += w * sig * nx * nx + cur * (1.0 - nx * nx);
-        q01 += w * sig * nx * ny + cur * (-nx * ny);
-        q11 += w * sig * ny * ny + cur * (1.0 - ny * ny);
-        a[0] += -dc * yv * nx; a[1] += -dc * yv * ny;
-      }
-      LQ(LQ_Q + tri(0, 0)) += q00; LQ(LQ_Q + tri(1, 0)) += q01; LQ(LQ_Q + tri(1, 1)) += q11;
-      LQ(LQ_NN + 0) = nn0; LQ(LQ_NN + 1) = nn1; LQ(LQ_NN + 2) = nn2;
-      LQ(LQ_DD + 0) = st.cps * st.cth; LQ(LQ_DD + 1) = st.sps * st.cth; LQ(LQ_DD + 2) = st.sth;
-      LQ(LQ_EE + 0) = e03; LQ(LQ_EE + 1) = e13; LQ(LQ_EE + 2) = e23; LQ(LQ_EE + 3) = e04; LQ(LQ_EE + 4) = e14;
-    }
-    adjoint(a, lam, lamn);
-    if (act) {
-      double svt = 0.0, svp = 0.0;
-      if (hasu && !ls_mode) {
-        // curvature of T*v*d(theta,psi) weighted by the next-stage adjoint
-        const double L0 = T * lamn[0], L1 = T * lamn[1], L2 = T * lamn[2], v = u[0];
-        const double cc = st.cps * st.cth, sc = st.sps * st.cth, cs = st.cps * st.sth, ss = st.sps * st.sth;
-        LQ(LQ_Q + tri(3, 3)) += -v * (L0 * cc + L1 * sc + L2 * st.sth);
-        LQ(LQ_Q + tri(4, 4)) += -v * (L0 * cc + L1 * sc);
-        LQ(LQ_Q + tri(4, 3)) += v * (L0 * ss - L1 * cs);
-        svt = -L0 * cs - L1 * ss + L2 * st.cth;
-        svp = -L0 * sc + L1 * cc;
-      }
-      LQ(LQ_SV + 0) = svt; LQ(LQ_SV + 1) = svp;
-    }
-  };
-
-  // Newton right-hand side (q, r, Sigma_x) for barrier parameter mu into the LQ arrays.
-  auto build_rhs = [&](bool ls_mode) {
-    if (act) {
-      double q[8], qd[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { q[i] = 0.0; qd[i] = 0.0; }
-#pragma unroll
-      for (int v = 0; v < 6; ++v) q[cost_state(v)] = gl[v];
-      for (int r = 0; r < R; ++r) {
-        const double dc = RW(A_DC, r), sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r);
-        const bool hl = is_lo(lo), hu = is_hi(hi);
-        double yh, cd;   // yh = y + Sigma_s c + rs (delta_w-free part), cd = c
-        if (ls_mode) { yh = -RW(A_VL, r) + RW(A_VU, r); cd = 0.0; }
-        else {
-          const double sig = (hl ? RW(A_VL, r) / (sv - lo) : 0.0) + (hu ? RW(A_VU, r) / (hi - sv) : 0.0);
-          const double c = RW(A_G, r) - sv;
-          double bg = (hl ? -mu / (sv - lo) : 0.0) + (hu ? mu / (hi - sv) : 0.0);
-          if (hl && !hu) bg += o.kappa_d * mu; if (hu && !hl) bg -= o.kappa_d * mu;
-          yh = sig * c + bg; cd = c;
-        }
-        if (r < 5) { const int i = box_state(r); q[i] += dc * yh; qd[i] += dc * cd; }
-        else {
-          const int jn = r - 5;
-          const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
-          const double iD = 1.0 / sqrt(dx_ * dx_ + dy_ * dy_), nx = dx_ * iD, ny = dy_ * iD;
-          q[0] += -dc * yh * nx; q[1] += -dc * yh * ny; qd[0] += -dc * cd * nx; qd[1] += -dc * cd * ny;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { LQ(LQ_QV + i) = q[i]; LQ(LQ_QD + i) = qd[i]; }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        double sig = 1.0, rr = 0.0;
-        if (hasu) {
-          const bool hl = is_lo(xL[i]), hu = is_hi(xU[i]);
-          if (ls_mode) rr = -zL[i] + zU[i];
-          else {
-            sig = (hl ? zL[i] / (u[i] - xL[i]) : 0.0) + (hu ? zU[i] / (xU[i] - u[i]) : 0.0);
-            rr = (hl ? -mu / (u[i] - xL[i]) : 0.0) + (hu ? mu / (xU[i] - u[i]) : 0.0);
-            if (hl && !hu) rr += o.kappa_d * mu; if (hu && !hl) rr -= o.kappa_d * mu;
-          }
-        }
-        LQ(LQ_RD + i) = sig; LQ(LQ_RV + i) = rr;
-      }
-    }
-    __syncwarp();
-  };
-
-  // ---------------- least-squares multiplier start -------------------------------------------
-  double mydx[8], mydu[6];
-  {
-    eval_derivs(true);
-    build_rhs(true);
-    ++n_fact;
-    const bool ok = riccati_factor(pr, lq, ric, 0.0, lane);
-    double ymax = 0.0;
-    if (ok) {
-      riccati_forward(pr, lq, ric, false, lane, mydx, mydu);
-      if (act) {
-        for (int r = 0; r < R; ++r) {
-          const double dc = RW(A_DC, r);
-          double gd;
-          if (r < 5) gd = dc * mydx[box_state(r)];
-          else {
-            const int jn = r - 5;
-            const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
-            const double iD = 1.0 / sqrt(dx_ * dx_ + dy_ * dy_);
-            gd = -dc * (dx_ * iD * mydx[0] + dy_ * iD * mydx[1]);
-          }
-          const double yv = gd + (-RW(A_VL, r) + RW(A_VU, r));
-          RW(A_Y, r) = yv; ymax = fmax(ymax, fabs(yv));
-        }
-      }
-      ymax = warp_max(ymax);
-    }
-    if (!ok || !(ymax <= o.constr_mult_init_max)) { if (act) for (int r = 0; r < R; ++r) RW(A_Y, r) = 0.0; }
+  ph_load(A, ws, b, lane);
+  double df = 1.0;
+  if (o.scaling) {
+    df = ph_scaling(A, ws, lane);
+    if (o.scaling == 3) df = 1.0;                                  // debug: constraint scaling only
+    if (o.scaling == 2 && lane <= pr.N) { for (int r = 0; r < R; ++r) ws.rows[(A_DC * R + r) * S + lane] = 1.0; }   // debug: objective only
     __syncwarp();
   }
+  const int nzt = ph_start(A, ws, lane);
+  ph_trial(A, ws, lane, 0.0, false, df);          // barrier pieces and constraint violation of the start
+  double f = res[R_FT], LB = res[R_LBT], DT = res[R_DTT];
+  const double th0 = res[R_THT];
+  const double theta_max = o.theta_max_fact * fmax(1.0, th0), theta_min = o.theta_min_fact * fmax(1.0, th0);
+  double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
+  const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
+  int nfilt = 0; double dw_last = 0.0;
+  int iter = 0, status = NMPC_MAXITER_EXCEEDED, tiny_count = 0; bool tiny_flag = false, ls = true;
+  const int mtot = R * S;
 
-  // ---------------- main loop ------------------------------------------------------------------
-  int iter = 0, status = NMPC_MAXITER_EXCEEDED, tiny_count = 0; bool tiny_flag = false;
   for (;;) {
-    eval_derivs(false);
-    // ---- optimality error
-    double du_l = 0.0, pr_l = 0.0, sumy = 0.0, sumz = 0.0, viol = 0.0; int nz = 0;
-    double glx[6];
-    if (hasu) {
-      glx[0] = T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]);
-#pragma unroll
-      for (int r = 1; r < 6; ++r) glx[r] = T * lamn[r + 2];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        du_l = fmax(du_l, fabs(glx[i] - zL[i] + zU[i]));
-        if (is_lo(xL[i])) { sumz += fabs(zL[i]); ++nz; }
-        if (is_hi(xU[i])) { sumz += fabs(zU[i]); ++nz; }
-      }
+    ph_derivs(A, ws, lane, ls, df);
+    if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
+      ++n_fact;
+      const bool ok = riccati_factor(pr, ws.lq, ws.ric, ws.stg, 1.0, 0.0, lane);
+      if (ok) riccati_forward(pr, ws.lq, ws.ric, false, lane, ws.lv + LV_DX * S, ws.lv + LV_DU * S);
+      ph_lsy(A, ws, lane, ok);
+      ls = false;
+      continue;
     }
-    if (act) {
-      for (int r = 0; r < R; ++r) {
-        const double yv = RW(A_Y, r), gv = RW(A_G, r), sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r), dc = RW(A_DC, r);
-        du_l = fmax(du_l, fabs(-yv - RW(A_VL, r) + RW(A_VU, r)));
-        pr_l = fmax(pr_l, fabs(gv - sv));
-        sumy += fabs(yv);
-        if (is_lo(lo)) { sumz += fabs(RW(A_VL, r)); ++nz; }
-        if (is_hi(hi)) { sumz += fabs(RW(A_VU, r)); ++nz; }
-        const double gu = gv / dc, lo_o = A.lbg[lane * R + r], hi_o = A.ubg[lane * R + r];
-        if (lo_o > -1e19) viol = fmax(viol, lo_o - gu);
-        if (hi_o < 1e19) viol = fmax(viol, gu - hi_o);
-      }
-    }
-    const double du_inf = warp_max(du_l), pr_inf = warp_max(pr_l);
-    sumy = warp_sum(sumy); sumz = warp_sum(sumz); viol = warp_max(viol);
-    const int nzt = __reduce_add_sync(FULL, nz);
-    const int mtot = R * S;
+    // ---- optimality error (scaled) and termination
+    const double du_inf = res[R_DU], pr_inf = res[R_PR], sumy = res[R_SUMY], sumz = res[R_SUMZ], viol = res[R_VIOL];
+    const double pmax = res[R_PMAX], pmin = res[R_PMIN];
     const double sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nzt)) / o.s_max;
     const double sc = fmax(o.s_max, sumz / (double)max(1, nzt)) / o.s_max;
-    auto compl_err = [&](double mu_) {
-      double co = 0.0;
-      if (hasu) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          if (is_lo(xL[i])) co = fmax(co, fabs((u[i] - xL[i]) * zL[i] - mu_));
-          if (is_hi(xU[i])) co = fmax(co, fabs((xU[i] - u[i]) * zU[i] - mu_));
-        }
-      }
-      if (act) for (int r = 0; r < R; ++r) {
-        const double sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r);
-        if (is_lo(lo)) co = fmax(co, fabs((sv - lo) * RW(A_VL, r) - mu_));
-        if (is_hi(hi)) co = fmax(co, fabs((hi - sv) * RW(A_VU, r) - mu_));
-      }
-      return warp_max(co);
-    };
-    const double co0 = compl_err(0.0);
-    const double E0 = fmax(du_inf / sd, fmax(pr_inf, co0 / sc));
+    const double E0 = fmax(du_inf / sd, fmax(pr_inf, pmax / sc));
     if (!isfinite(E0) || !isfinite(f)) { status = NMPC_INVALID_NUMBER; break; }
-    if (E0 <= o.tol && du_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol && co0 / df <= o.compl_inf_tol) {
+    if (E0 <= o.tol && du_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
       status = NMPC_SOLVE_SUCCEEDED; break;
     }
     if (iter >= o.max_iter) { status = NMPC_MAXITER_EXCEEDED; break; }
-    // ---- barrier parameter
+    // ---- barrier parameter (monotone, with fast decrease)
     {
-      double Emu = fmax(du_inf / sd, fmax(pr_inf, compl_err(mu) / sc));
+      auto emu = [&](double m) { return fmax(du_inf / sd, fmax(pr_inf, fmax(pmax - m, m - pmin) / sc)); };
+      double Emu = emu(mu);
       while ((Emu <= o.kappa_eps * mu || tiny_flag) && mu > mu_floor) {
-        mu = fmax(mu_floor, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+        mu = fmax(mu_floor, fmin(o.kappa_mu * mu, n_pow(mu, o.theta_mu)));
         tau = fmax(o.tau_min, 1.0 - mu); nfilt = 0; tiny_flag = false;
-        Emu = fmax(du_inf / sd, fmax(pr_inf, compl_err(mu) / sc));
+        Emu = emu(mu);
       }
       if (tiny_flag && mu <= mu_floor) { status = NMPC_STEP_TOO_SMALL; break; }
     }
     // ---- search direction with inertia correction
     const unsigned long long ls_before = n_ls;
-    build_rhs(false);
     double dw = 0.0; bool ok = false;
     for (;;) {
       ++n_fact;
-      ok = riccati_factor(pr, lq, ric, dw, lane);
+      ok = riccati_factor(pr, ws.lq, ws.ric, ws.stg, mu, dw, lane);
       if (ok) break;
       if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, dw_last * o.dw_dec);
       else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
@@ -515,102 +699,15 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* __restri
     }
     if (!ok) { status = NMPC_PERTURBATION_FAILED; break; }
     if (dw > 0.0) dw_last = dw;
-    riccati_forward(pr, lq, ric, false, lane, mydx, mydu);
-
-    // per-row step ds = G dx + c into array `dsarr` for residual array c = (carr ? csoc : g - s)
-    auto row_steps = [&](const double* dx_, int dsarr, bool soc) {
-      if (act) for (int r = 0; r < R; ++r) {
-        const double dc = RW(A_DC, r);
-        double gd;
-        if (r < 5) gd = dc * dx_[box_state(r)];
-        else {
-          const int jn = r - 5;
-          const double ddx = st.X[0] - obs[3 * jn], ddy = st.X[1] - obs[3 * jn + 1];
-          const double iD = 1.0 / sqrt(ddx * ddx + ddy * ddy);
-          gd = -dc * (ddx * iD * dx_[0] + ddy * iD * dx_[1]);
-        }
-        const double c = soc ? RW(A_CSOC, r) : RW(A_G, r) - RW(A_S, r);
-        RW(dsarr, r) = gd + c;
-      }
-    };
-    auto ftb_primal = [&](const double* du_, int dsarr) {
-      double a = 1.0;
-      if (hasu) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          if (is_lo(xL[i]) && du_[i] < 0.0) a = fmin(a, -tau * (u[i] - xL[i]) / du_[i]);
-          if (is_hi(xU[i]) && du_[i] > 0.0) a = fmin(a, tau * (xU[i] - u[i]) / du_[i]);
-        }
-      }
-      if (act) for (int r = 0; r < R; ++r) {
-        const double sv = RW(A_S, r), dsv = RW(dsarr, r), lo = RW(A_DL, r), hi = RW(A_DU, r);
-        if (is_lo(lo) && dsv < 0.0) a = fmin(a, -tau * (sv - lo) / dsv);
-        if (is_hi(hi) && dsv > 0.0) a = fmin(a, tau * (hi - sv) / dsv);
-      }
-      return warp_min(a);
-    };
-    // dual steps are recomputed from (du, ds) where needed:  dz = (mu -+ z*d)/slack - z
-    auto ftb_dual = [&](const double* du_, int dsarr) {
-      double a = 1.0;
-      if (hasu) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          if (is_lo(xL[i])) { const double dz = (mu - zL[i] * du_[i]) / (u[i] - xL[i]) - zL[i]; if (dz < 0.0) a = fmin(a, -tau * zL[i] / dz); }
-          if (is_hi(xU[i])) { const double dz = (mu + zU[i] * du_[i]) / (xU[i] - u[i]) - zU[i]; if (dz < 0.0) a = fmin(a, -tau * zU[i] / dz); }
-        }
-      }
-      if (act) for (int r = 0; r < R; ++r) {
-        const double sv = RW(A_S, r), dsv = RW(dsarr, r), lo = RW(A_DL, r), hi = RW(A_DU, r);
-        if (is_lo(lo)) { const double v = RW(A_VL, r), dz = (mu - v * dsv) / (sv - lo) - v; if (dz < 0.0) a = fmin(a, -tau * v / dz); }
-        if (is_hi(hi)) { const double v = RW(A_VU, r), dz = (mu + v * dsv) / (hi - sv) - v; if (dz < 0.0) a = fmin(a, -tau * v / dz); }
-      }
-      return warp_min(a);
-    };
-    row_steps(mydx, A_DS, false);
-    const double a_pr_max = ftb_primal(mydu, A_DS);
-    double a_du = ftb_dual(mydu, A_DS);
-    // ---- line-search reference quantities
-    double theta = 0.0, gbd = 0.0, tiny_l = 0.0;
-    if (hasu) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const bool hl = is_lo(xL[i]), hu = is_hi(xU[i]);
-        double bgv = (hl ? -mu / (u[i] - xL[i]) : 0.0) + (hu ? mu / (xU[i] - u[i]) : 0.0);
-        if (hl && !hu) bgv += o.kappa_d * mu; if (hu && !hl) bgv -= o.kappa_d * mu;
-        gbd += bgv * mydu[i];
-        tiny_l = fmax(tiny_l, fabs(mydu[i]) / (1.0 + fabs(u[i])));
-      }
-#pragma unroll
-      for (int v = 0; v < 6; ++v) gbd += gl[v] * mydx[cost_state(v)];
-    }
-    if (act) for (int r = 0; r < R; ++r) {
-      const double sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r), dsv = RW(A_DS, r);
-      const bool hl = is_lo(lo), hu = is_hi(hi);
-      double bgv = (hl ? -mu / (sv - lo) : 0.0) + (hu ? mu / (hi - sv) : 0.0);
-      if (hl && !hu) bgv += o.kappa_d * mu; if (hu && !hl) bgv -= o.kappa_d * mu;
-      gbd += bgv * dsv;
-      theta += fabs(RW(A_G, r) - sv);
-      tiny_l = fmax(tiny_l, fabs(dsv) / (1.0 + fabs(sv)));
-    }
-    theta = warp_sum(theta); gbd = warp_sum(gbd); tiny_l = warp_max(tiny_l);
+    riccati_forward(pr, ws.lq, ws.ric, false, lane, ws.lv + LV_DX * S, ws.lv + LV_DU * S);
+    ph_dir(A, ws, lane, mu, tau, false);
+    const double a_pr_max = res[R_APR]; double a_du = res[R_ADU];
+    const double gbd = res[R_GBD], theta = res[R_THETA];
+    const bool tiny = res[R_TINY] != 0.0 && theta <= 1e-4;
     const double phi = f - mu * LB + o.kappa_d * mu * DT;
-    bool tiny = tiny_l <= o.tiny_step_tol && theta <= 1e-4;
-
-    // trial point evaluation: u + alpha*du_, s + alpha*ds[dsarr]
-    Stage stt; double ut[6], f_t, th_t, LB_t, DT_t;
-    auto eval_trial = [&](double alpha, const double* du_, int dsarr) {
-      ++n_ls;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) ut[i] = u[i] + alpha * du_[i];
-      rollout(pr, X0, ut, lane, stt);
-      f_t = cost_sum(stt);
-      eval_g(stt, A_GT);
-      double th = 0.0;
-      if (act) for (int r = 0; r < R; ++r) th += fabs(RW(A_GT, r) - (RW(A_S, r) + alpha * RW(dsarr, r)));
-      th_t = warp_sum(th);
-      barrier_parts(ut, 1, alpha, dsarr, LB_t, DT_t);
-    };
-    auto is_ftype = [&](double a) { return gbd < 0.0 && a * pow(-gbd, o.s_phi) > o.delta * pow(theta, o.s_theta); };
+    // ---- filter line search
+    const double pw_gbd = gbd < 0.0 ? n_pow(-gbd, o.s_phi) : 0.0, pw_th = n_pow(theta, o.s_theta);
+    auto is_ftype = [&](double a) { return gbd < 0.0 && a * pw_gbd > o.delta * pw_th; };
     auto armijo = [&](double a, double ph_t) { return cmp_le(ph_t - phi, o.eta_phi * a * gbd, phi); };
     auto acceptable = [&](double a_test, double th_, double ph_) {
       if (!isfinite(th_) || !isfinite(ph_)) return false;
@@ -622,78 +719,53 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* __restri
       for (int e = 0; e < nfilt; ++e) if (!(th_ < filt[2 * e] || ph_ < filt[2 * e + 1])) return false;
       return true;
     };
-    double alpha = a_pr_max, alpha_test = a_pr_max; bool accepted = false, used_soc = false;
-    double phi_t = 0.0;
-    double dxs[8], dus[6];   // SOC direction
-    if (tiny) {
-      eval_trial(alpha, mydu, A_DS); accepted = true; ++tiny_count; tiny_flag = true;
-      phi_t = f_t - mu * LB_t + o.kappa_d * mu * DT_t;
-      if (tiny_count >= 2 && mu <= mu_floor) { status = NMPC_STEP_TOO_SMALL; break; }
-    } else {
-      tiny_count = 0;
-      double amin = o.gamma_theta;
-      if (gbd < 0.0) {
-        amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gbd));
-        if (theta <= theta_min) amin = fmin(amin, o.delta * pow(theta, o.s_theta) / pow(-gbd, o.s_phi));
-      }
-      amin *= o.alpha_min_frac;
-      bool first = true;
-      while (alpha > amin || first) {
-        eval_trial(alpha, mydu, A_DS);
-        phi_t = f_t - mu * LB_t + o.kappa_d * mu * DT_t;
-        alpha_test = alpha;
-        if (acceptable(alpha, th_t, phi_t)) { accepted = true; break; }
-        if (first && o.max_soc > 0 && th_t >= theta && isfinite(th_t)) {
-          // ---- second-order correction
-          double a_soc = alpha, th_prev = th_t;
-          if (act) for (int r = 0; r < R; ++r) RW(A_CSOC, r) = RW(A_G, r) - RW(A_S, r);
-          int dsprev = A_DS;
-          for (int kk = 0; kk < o.max_soc; ++kk) {
-            // c_soc = a_soc * c_soc + c(trial); q' = grad l + G^T (D_s c_soc + barrier gradient)
-            if (act) {
-              double q[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) q[i] = 0.0;
-#pragma unroll
-              for (int v = 0; v < 6; ++v) q[cost_state(v)] = gl[v];
-              for (int r = 0; r < R; ++r) {
-                const double sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r), dc = RW(A_DC, r);
-                const bool hl = is_lo(lo), hu = is_hi(hi);
-                const double cs = a_soc * RW(A_CSOC, r) + (RW(A_GT, r) - (sv + a_soc * RW(dsprev, r)));
-                RW(A_CSOC, r) = cs;
-                const double sig = (hl ? RW(A_VL, r) / (sv - lo) : 0.0) + (hu ? RW(A_VU, r) / (hi - sv) : 0.0) + dw;
-                double bg = (hl ? -mu / (sv - lo) : 0.0) + (hu ? mu / (hi - sv) : 0.0);
-                if (hl && !hu) bg += o.kappa_d * mu; if (hu && !hl) bg -= o.kappa_d * mu;
-                const double yh = sig * cs + bg;
-                if (r < 5) q[box_state(r)] += dc * yh;
-                else {
-                  const int jn = r - 5;
-                  const double ddx = st.X[0] - obs[3 * jn], ddy = st.X[1] - obs[3 * jn + 1];
-                  const double iD = 1.0 / sqrt(ddx * ddx + ddy * ddy);
-                  q[0] += -dc * yh * ddx * iD; q[1] += -dc * yh * ddy * iD;
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) LQ(LQ_Q2 + i) = q[i];
-            }
-            __syncwarp();
-            riccati_resolve(pr, lq, ric, lane);
-            riccati_forward(pr, lq, ric, true, lane, dxs, dus);
-            row_steps(dxs, A_DS2, true);
-            a_soc = ftb_primal(dus, A_DS2);
-            eval_trial(a_soc, dus, A_DS2);
-            dsprev = A_DS2;
-            const double ph_s = f_t - mu * LB_t + o.kappa_d * mu * DT_t;
-            if (acceptable(alpha, th_t, ph_s)) { accepted = true; used_soc = true; phi_t = ph_s; alpha = a_soc; ++n_soc; break; }
-            if (!(th_t <= o.kappa_soc * th_prev)) break;
-            th_prev = th_t;
-          }
-          if (accepted) break;
-        }
-        first = false;
-        alpha *= o.alpha_red;
-      }
+    double amin = o.gamma_theta;
+    if (gbd < 0.0) {
+      amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gbd));
+      if (theta <= theta_min) amin = fmin(amin, o.delta * pw_th / pw_gbd);
     }
+    amin *= o.alpha_min_frac;
+    double alpha = a_pr_max, alpha_test = a_pr_max, phi_t = 0.0, a_soc = 0.0, th_prev = 0.0;
+    bool accepted = false, used_soc = false, first = true;
+    int soc_left = 0;      // > 0: the next trial is a second-order-correction trial
+    if (tiny) { ++tiny_count; tiny_flag = true; } else tiny_count = 0;
+    for (;;) {
+      const bool soc_trial = soc_left > 0;
+      const double a_try = soc_trial ? a_soc : alpha;
+      ph_trial(A, ws, lane, a_try, soc_trial, df);
+      ++n_ls;
+      const double th_t = res[R_THT];
+      phi_t = res[R_FT] - mu * res[R_LBT] + o.kappa_d * mu * res[R_DTT];
+      if (tiny) { accepted = true; break; }
+      if (!soc_trial) alpha_test = alpha;
+      if (acceptable(alpha, th_t, phi_t)) {
+        accepted = true;
+        if (soc_trial) { used_soc = true; alpha = a_soc; ++n_soc; }
+        break;
+      }
+      bool next_soc = false;
+      if (soc_trial) {
+        --soc_left;
+        next_soc = soc_left > 0 && th_t <= o.kappa_soc * th_prev;
+        if (!next_soc) soc_left = 0;
+      } else if (first && o.max_soc > 0 && th_t >= theta && isfinite(th_t)) {
+        soc_left = o.max_soc; next_soc = true;
+      }
+      if (next_soc) {
+        const bool first_soc = !soc_trial;
+        th_prev = th_t;
+        ph_socrhs(A, ws, lane, first_soc ? alpha : a_soc, mu, dw, first_soc);
+        riccati_resolve(pr, ws.lq, ws.soc + SOC_Q2 * S, ws.ric, mu, lane);
+        riccati_forward(pr, ws.lq, ws.ric, true, lane, ws.lv + LV_DX * S, ws.soc + SOC_DUS * S);
+        ph_dir(A, ws, lane, mu, tau, true);
+        a_soc = res[R_APR];
+        continue;
+      }
+      first = false;
+      alpha *= o.alpha_red;
+      if (!(alpha > amin)) break;
+    }
+    if (tiny && tiny_count >= 2 && mu <= mu_floor) { status = NMPC_STEP_TOO_SMALL; break; }
     if (!accepted) { status = NMPC_RESTORATION_NEEDED; break; }
     // ---- filter augmentation
     if (!tiny && !(is_ftype(alpha_test) && armijo(alpha_test, phi_t))) {
@@ -705,93 +777,22 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* __restri
       if (nfilt < FILT_CAP) ++nfilt;
       __syncwarp();
     }
+    if (used_soc) a_du = res[R_ADU];
     if (A.dbg && lane == 0 && iter < A.dbg_rows) {
       double* L = A.dbg + ((size_t)b * A.dbg_rows + iter) * 8;
       L[0] = mu; L[1] = f / df; L[2] = pr_inf; L[3] = du_inf; L[4] = dw; L[5] = alpha; L[6] = a_du; L[7] = (double)(n_ls - ls_before);
     }
-    // ---- accept the trial point
-    const double* du_acc = used_soc ? dus : mydu;
-    const int ds_acc = used_soc ? A_DS2 : A_DS;
-    if (used_soc) a_du = ftb_dual(dus, A_DS2);
-    if (hasu) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const bool hl = is_lo(xL[i]), hu = is_hi(xU[i]);
-        const double sl = u[i] - xL[i], su = xU[i] - u[i];
-        double zl = zL[i], zu = zU[i];
-        if (hl) zl += a_du * ((mu - zl * du_acc[i]) / sl - zl);
-        if (hu) zu += a_du * ((mu + zu * du_acc[i]) / su - zu);
-        u[i] = ut[i];
-        if (hl) { const double s2 = u[i] - xL[i]; zl = fmax(fmin(zl, o.kappa_sigma * mu / s2), mu / (o.kappa_sigma * s2)); }
-        if (hu) { const double s2 = xU[i] - u[i]; zu = fmax(fmin(zu, o.kappa_sigma * mu / s2), mu / (o.kappa_sigma * s2)); }
-        zL[i] = zl; zU[i] = zu;
-      }
-    }
-    if (act) for (int r = 0; r < R; ++r) {
-      const double sv = RW(A_S, r), lo = RW(A_DL, r), hi = RW(A_DU, r), dsv = RW(ds_acc, r);
-      const bool hl = is_lo(lo), hu = is_hi(hi);
-      double vl = RW(A_VL, r), vu = RW(A_VU, r);
-      const double sig = (hl ? vl / (sv - lo) : 0.0) + (hu ? vu / (hi - sv) : 0.0) + dw;
-      double bg = (hl ? -mu / (sv - lo) : 0.0) + (hu ? mu / (hi - sv) : 0.0);
-      if (hl && !hu) bg += o.kappa_d * mu; if (hu && !hl) bg -= o.kappa_d * mu;
-      const double yv = RW(A_Y, r);
-      const double dy = sig * dsv + (-yv + bg);
-      RW(A_Y, r) = yv + alpha * dy;
-      if (hl) vl += a_du * ((mu - vl * dsv) / (sv - lo) - vl);
-      if (hu) vu += a_du * ((mu + vu * dsv) / (hi - sv) - vu);
-      const double sn = sv + alpha * dsv;
-      if (hl) { const double s2 = sn - lo; vl = fmax(fmin(vl, o.kappa_sigma * mu / s2), mu / (o.kappa_sigma * s2)); }
-      if (hu) { const double s2 = hi - sn; vu = fmax(fmin(vu, o.kappa_sigma * mu / s2), mu / (o.kappa_sigma * s2)); }
-      RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_G, r) = RW(A_GT, r);
-    }
-    st = stt; f = f_t; LB = LB_t; DT = DT_t;
+    ph_accept(A, ws, lane, alpha, a_du, mu, dw, used_soc);
+    f = res[R_FT]; LB = res[R_LBT]; DT = res[R_DTT];
     ++iter;
-    __syncwarp();
   }
+  ph_output(A, ws, b, lane, df, status, iter);
+  if (lane == 0 && A.stats) { atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); }
+}
 
-  // ---------------- outputs: honour original bounds, unscale ----------------------------------
-  const int nw = NU * N, ng = R * S;
-  if (hasu) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) u[i] = fmin(fmax(u[i], A.lbx[NU * lane + i]), A.ubx[NU * lane + i]);
-    double* xo = A.x + (size_t)b * nw + NU * lane;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) xo[i] = u[i];
-    if (A.lam_x) {
-      double* lo = A.lam_x + (size_t)b * nw + NU * lane;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) lo[i] = (zU[i] - zL[i]) / df;
-    }
-  }
-  rollout(pr, X0, u, lane, st);
-  {
-    const double l = hasu ? stage_cost(pr, st.X, xt, yt) : 0.0;
-    const double fu = warp_sum(l);
-    if (lane == 0) {
-      if (A.f) A.f[b] = fu;
-      if (A.status) A.status[b] = status;
-      if (A.iters) A.iters[b] = iter;
-      if (A.stats) { atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); }
-    }
-  }
-  if (act) {
-    if (A.g) {
-      double* go = A.g + (size_t)b * ng + lane * R;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) go[r] = st.X[box_state(r)];
-      for (int jn = 0; jn < n_obs; ++jn) {
-        const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
-        go[5 + jn] = obs[3 * jn + 2] - sqrt(dx_ * dx_ + dy_ * dy_);
-      }
-    }
-    if (A.lam_g) {
-      double* lo = A.lam_g + (size_t)b * ng + lane * R;
-      for (int r = 0; r < R; ++r) lo[r] = RW(A_Y, r) * RW(A_DC, r) / df;
-    }
-  }
-  __syncwarp();
+#undef LV
 #undef RW
 #undef LQ
-}
+#undef SOC
 
 }  // namespace nmpc

@@ -49,7 +49,7 @@ def _spec_from(problem, opts: Optional[dict]) -> Dict[str, Any]:
     ip = dict((opts or {}).get("ipopt", {}))
     d["max_iter"] = int(ip.get("max_iter", 100))          # NMPC_TT.py:259
     d["tol"] = float(ip.get("tol", 1e-8))
-    d["scaling"] = 0 if ip.get("nlp_scaling_method", "gradient-based") == "none" else 1
+    d["scaling"] = 0 if ip.get("nlp_scaling_method", "gradient-based") == "none" else int(ip.get("_scaling_debug_mode", 1))
     return d
 
 

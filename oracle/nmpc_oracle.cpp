@@ -529,6 +529,8 @@ struct Ipm {
         dc[r] = rm > o.max_grad ? std::max(o.scal_min, o.max_grad / rm) : 1.0;
       }
       df = dfn;
+      if (o.scaling == 2) std::fill(dc.begin(), dc.end(), 1.0);   // debug: objective scaling only
+      if (o.scaling == 3) df = 1.0;                                // debug: constraint scaling only
     }
     // ---- bounds (scaled, relaxed)
     xL.resize(n); xU.resize(n); dL.resize(m); dU.resize(m);
