@@ -81,19 +81,23 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi, bool h
 
 struct Bnd { double lo, hi; bool hl, hu; };
 // relaxed bounds of control i of stage k (NMPC_TT.py:294-306) and of the scaled row r of stage k (:275-291)
+// NOTE: these are inlined into several phase functions; the explicit round-to-nearest intrinsics keep the compiler
+// from contracting the expressions into FMAs differently per copy.  A bound that differs by one ulp between the
+// function that builds the Newton system and the one that updates the multipliers is a 1e-6 RELATIVE error of a
+// 1e-10 slack, i.e. a 1e-5 error in a multiplier -- enough to stall the end game (seen with v2).
 __device__ __forceinline__ Bnd ctl_bounds(const SolveArgs& A, int k, int i) {
   const double lo = __ldg(A.lbx + NU * k + i), hi = __ldg(A.ubx + NU * k + i);
   Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
-  b.lo = b.hl ? lo - A.o.bound_relax * fmax(1.0, fabs(lo)) : -CUDART_INF;
-  b.hi = b.hu ? hi + A.o.bound_relax * fmax(1.0, fabs(hi)) : CUDART_INF;
+  b.lo = b.hl ? __dsub_rn(lo, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(lo)))) : -CUDART_INF;
+  b.hi = b.hu ? __dadd_rn(hi, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(hi)))) : CUDART_INF;
   return b;
 }
 __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, double dc) {
   const double lo = __ldg(A.lbg + k * A.pr.R + r), hi = __ldg(A.ubg + k * A.pr.R + r);
   Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
-  const double l2 = dc * lo, h2 = dc * hi;
-  b.lo = b.hl ? l2 - A.o.bound_relax * fmax(1.0, fabs(l2)) : -CUDART_INF;
-  b.hi = b.hu ? h2 + A.o.bound_relax * fmax(1.0, fabs(h2)) : CUDART_INF;
+  const double l2 = __dmul_rn(dc, lo), h2 = __dmul_rn(dc, hi);
+  b.lo = b.hl ? __dsub_rn(l2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(l2)))) : -CUDART_INF;
+  b.hi = b.hu ? __dadd_rn(h2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(h2)))) : CUDART_INF;
   return b;
 }
 
@@ -211,7 +215,7 @@ __device__ __forceinline__ double row_value(const Ws& ws, const double* X, int r
   if (r < 5) { nx = 0.0; ny = 0.0; iD = 0.0; return X[box_state(r)]; }
   const int jn = r - 5;
   const double dx_ = X[0] - ws.obs[3 * jn], dy_ = X[1] - ws.obs[3 * jn + 1];
-  const double d2 = dx_ * dx_ + dy_ * dy_;
+  const double d2 = __fma_rn(dx_, dx_, __dmul_rn(dy_, dy_));
   const double D = sqrt(d2);
   iD = rcp(D); nx = dx_ * iD; ny = dy_ * iD;
   return ws.obs[3 * jn + 2] - D;
@@ -235,7 +239,7 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, const Ws& ws, int lane)
   Stage st; rollout(pr, ws.par, u, lane, st);
   if (act) for (int r = 0; r < R; ++r) {
     double nx, ny, iD; const double dc = RW(A_DC, r);
-    const double g = dc * row_value(ws, st.X, r, nx, ny, iD);
+    const double g = __dmul_rn(dc, row_value(ws, st.X, r, nx, ny, iD));
     const Bnd b = row_bounds(A, lane, r, dc);
     const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
     RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = 0.0;
@@ -290,7 +294,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lan
     for (int e = 0; e < 21; ++e) q66[e] = ls ? 0.0 : df * Hl[e];
     for (int r = 0; r < R; ++r) {
       double nx, ny, iD; const double dc = RW(A_DC, r);
-      const double gu = row_value(ws, st.X, r, nx, ny, iD), g = dc * gu;
+      const double gu = row_value(ws, st.X, r, nx, ny, iD), g = __dmul_rn(dc, gu);
       const double s = RW(A_S, r), y = RW(A_Y, r), vl = RW(A_VL, r), vu = RW(A_VU, r), il = RW(A_IL, r), iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       RW(A_G, r) = g;
@@ -496,7 +500,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, const Ws& ws, int lane
   if (act) {
     for (int r = 0; r < R; ++r) {
       double nx, ny, iD; const double dc = RW(A_DC, r);
-      const double g = dc * row_value(ws, st.X, r, nx, ny, iD);
+      const double g = __dmul_rn(dc, row_value(ws, st.X, r, nx, ny, iD));
       const double sv = fma(alpha, soc ? SOC(SOC_DS2 + r) : RW(A_DS, r), RW(A_S, r));
       const double ct = g - sv;
       SOC(SOC_CT + r) = ct; th += fabs(ct);

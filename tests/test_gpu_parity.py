@@ -215,9 +215,11 @@ def test_full_size_properties(pkg):
     ev = s.evaluate(sol["x"], p, lam=sol["lam_g"])
     r = ev["grad"].cpu().numpy() + ev["jtv"].cpu().numpy() + sol["lam_x"]
     mult = np.maximum(1.0, np.maximum(np.abs(sol["lam_g"]).max(axis=1), np.abs(sol["lam_x"]).max(axis=1)))
-    # x is clipped to the original bounds on return (honor_original_bounds): up to 1e-8 |b| off the internal iterate,
-    # times the curvature of the T = 1 problem ~ 1e-4 in the gradient
-    assert np.all(np.abs(r[ok]).max(axis=1) <= 2e-4 + 1e-7 * mult[ok])
+    # x is clipped to the original bounds on return (honor_original_bounds): up to 1e-8 |b| off the internal iterate
+    # (1.4e-7 on an active v = 14 bound), times the curvature of the T = 1 problem -> scale the tolerance with the
+    # size of the terms that cancel
+    gscale = np.maximum(np.abs(ev["grad"].cpu().numpy()).max(axis=1), mult)
+    assert np.all(np.abs(r[ok]).max(axis=1) <= 1e-6 + 2e-6 * gscale[ok])
     # idempotence: re-solving from the solution converges to the same point
     sol2 = s(x0=sol["x"][ok][:256], p=p[ok][:256], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
     ok2 = s.stats()["success"]
