@@ -124,6 +124,11 @@ typedef struct nmpc_stats {
 } nmpc_stats;
 int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out);   /* synchronises the handle's last stream */
 
+/* Scheduling hint for the NEXT nmpc_solve on this handle: dev_order [B] is a permutation of 0..B-1 giving the order
+ * in which the persistent kernel fetches instances (e.g. previous-step iteration counts, longest first).  Results
+ * do not depend on it (instances are independent); only the tail of the batch step does.  NULL = natural order. */
+int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order);
+
 /* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
  * dev_buf [B][rows][8] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials}; NULL disables. */
 int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);

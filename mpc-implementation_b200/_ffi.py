@@ -32,7 +32,7 @@ class NmpcStats(C.Structure):
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_eval", "nmpc_step",
-           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
            "nmpc_last_error", "nmpc_version"]
 
 _lib = None
@@ -40,7 +40,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
-    args = ["make", "-C", str(_CSRC), "-s"] + (["-B"] if force else [])
+    args = ["make", "-C", str(_CSRC), "-s"] + (["-B"] if force else [])   # the Makefile runs itself with -j8
     subprocess.check_call(args)
     return LIB_PATH
 
@@ -62,6 +62,7 @@ def lib():
     L.nmpc_step.argtypes = [vp, C.c_int32] + [vp] * 5 + [vp]
     L.nmpc_get_stats.argtypes = [vp, C.POINTER(NmpcStats)]
     L.nmpc_set_debug_log.argtypes = [vp, vp, C.c_int32]
+    L.nmpc_set_order.argtypes = [vp, vp]
     L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
     L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]

@@ -21,22 +21,16 @@ using namespace nmpc;
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-// One warp per block: the per-instance workspace (ws_doubles of shared memory) is the occupancy limiter, and
-// independent 32-thread blocks let the hardware pack as many as fit (9 per SM at N = 15, n_obs = 3).
-__global__ void __launch_bounds__(32) nmpc_ipm_kernel(const SolveArgs A) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x;
-  Ws ws = carve(smem, A.pr.S, A.pr.R, A.pr.n_obs);
-  ws.ric = A.ric + (size_t)blockIdx.x * A.ric_stride;
-  for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(A.counter, 1);
-    b = __shfl_sync(FULL, b, 0);
-    if (b >= A.B) break;
-    solve_instance(A, ws, b, lane);
-    __syncwarp();
-  }
-}
+// The IPM kernel (nmpc_solve.cuh) is a template on (N, n_obs); its instantiations live in nmpc_inst.cu objects.
+namespace nmpc {
+#define NMPC_DECL_INST(N, O)                      \
+  int ipm_prepare_##N##_##O(int*, size_t*);        \
+  int ipm_launch_##N##_##O(const SolveArgs&, int, size_t, cudaStream_t);
+NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3)
+}  // namespace nmpc
+struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
+#define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_launch_##N##_##O}
+static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3)};
 
 struct EvalArgs {
   Prob pr; int B;
@@ -228,8 +222,9 @@ static int fail(const std::string& m) { g_err = m; return 1; }
 struct nmpc_handle {
   nmpc_spec spec; int device; int sm_count;
   Prob pr; Opt opt;
-  int ws_doubles, blocks_per_sm, max_blocks;
+  const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks;
   double* d_ric; int ric_stride;
+  int32_t* d_order; const int32_t* order_next;
   int* d_counter; unsigned long long* d_stats;
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
@@ -267,11 +262,18 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   h->opt = Opt();
   h->opt.max_iter = spec->max_iter > 0 ? spec->max_iter : 100;
   h->opt.scaling = spec->scaling; h->opt.tol = spec->tol > 0 ? spec->tol : 1e-8;
-  h->ws_doubles = ws_size(h->pr.S, h->pr.R, h->pr.n_obs);
-  const size_t smem = (size_t)h->ws_doubles * sizeof(double);
-  if (smem > prop.sharedMemPerBlockOptin) { delete h; return fail("nmpc_create: horizon / obstacle count needs more shared memory than one SM has"); }
-  CK(cudaFuncSetAttribute(nmpc_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, nmpc_ipm_kernel, 32, smem));
+  h->inst = nullptr;
+  for (const IpmInst& in : IPM_INSTS) if (in.N == spec->N && in.n_obs == spec->n_obs) h->inst = &in;
+  if (!h->inst) {
+    std::string have;
+    for (const IpmInst& in : IPM_INSTS) have += " (" + std::to_string(in.N) + "," + std::to_string(in.n_obs) + ")";
+    delete h;
+    return fail("nmpc_create: no kernel instantiation for this (N, n_obs); built:" + have + " -- add the pair to csrc/Makefile INSTS and the table in nmpc_b200.cu");
+  }
+  {
+    const int rc = h->inst->prepare(&h->blocks_per_sm, &h->smem_bytes);
+    if (rc != 0) { delete h; return fail(std::string("nmpc_create: kernel setup failed: ") + cudaGetErrorString((cudaError_t)rc)); }
+  }
   if (h->blocks_per_sm < 1) { delete h; return fail("nmpc_create: kernel does not fit on an SM"); }
   h->max_blocks = h->sm_count * h->blocks_per_sm;
   h->ric_stride = RIC_N * h->pr.N;
@@ -324,14 +326,17 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.p = p; A.x0 = x0; A.lbx = lbx; A.ubx = ubx; A.lbg = lbg; A.ubg = ubg; A.obs = obst;
   A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
   A.x = x; A.f = f; A.g = g; A.lam_x = lam_x; A.lam_g = lam_g; A.status = status; A.iters = iters;
-  A.counter = h->d_counter; A.stats = h->d_stats; A.ws_doubles = h->ws_doubles;
+  A.counter = h->d_counter; A.stats = h->d_stats;
   A.ric = h->d_ric; A.ric_stride = h->ric_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
+  A.order = h->order_next; h->order_next = nullptr;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
   const int blocks = B < h->max_blocks ? B : h->max_blocks;
-  nmpc_ipm_kernel<<<blocks, 32, (size_t)h->ws_doubles * sizeof(double), s>>>(A);
-  CK(cudaGetLastError());
+  {
+    const int rc = h->inst->launch(A, blocks, h->smem_bytes, s);
+    if (rc != 0) return fail(std::string("nmpc_solve: launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+  }
   h->last_stream = s; h->launches = 1;
   return 0;
 }
@@ -400,6 +405,12 @@ int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
   nmpc_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(A);
   CK(cudaGetLastError());
   h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;
+  return 0;
+}
+
+int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order) {
+  if (!h) return fail("nmpc_set_order: null handle");
+  h->order_next = dev_order;
   return 0;
 }
 

@@ -51,7 +51,7 @@ constexpr int RIC_L = 54;     // 21: Cholesky factor of Lambda (packed lower) + 
 constexpr int RIC_K2 = 81;    // 6 : kappa of the SOC right-hand side
 constexpr int RIC_N = 88;
 constexpr int FILT_CAP = 24;
-constexpr int STG_N = 432;    // Riccati staging area (nmpc_riccati.cuh)
+constexpr int STG_N = 460;    // Riccati staging area (nmpc_riccati.cuh)
 
 // scalar results returned by the phases through shared memory
 enum Res { R_F = 0, R_DU, R_PR, R_SUMY, R_SUMZ, R_VIOL, R_PMAX, R_PMIN, R_APR, R_ADU, R_GBD, R_THETA, R_TINY,
@@ -72,24 +72,24 @@ __device__ __forceinline__ int q_index(int i, int j) {
 }
 
 // ---- no-inline math: one copy of each slow sequence ---------------------------------------------
-__device__ __noinline__ double n_tan(double x) { return tan(x); }
-__device__ __noinline__ double n_log(double x) { return log(x); }
-__device__ __noinline__ double n_pow(double x, double y) { return pow(x, y); }
-__device__ __noinline__ double2 n_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
+static __device__ __noinline__ double n_tan(double x) { return tan(x); }
+static __device__ __noinline__ double n_log(double x) { return log(x); }
+static __device__ __noinline__ double n_pow(double x, double y) { return pow(x, y); }
+static __device__ __noinline__ double2 n_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
 
 // ---- warp collectives ---------------------------------------------------------------------------
-__device__ __noinline__ double warp_sum(double v) {
+static __device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-__device__ __noinline__ double warp_max(double v) {
+static __device__ __noinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
-__device__ __noinline__ double warp_min(double v) {
+static __device__ __noinline__ double warp_min(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
   return v;
@@ -133,6 +133,25 @@ __device__ __forceinline__ double shfl_next(double v, int lane) {   // value of 
 struct Prob {
   double T, w1, w2, hv, hh;   // hv = VFOV/2, hh = HFOV/2
   int N, n_obs, R, S;         // R = 5 + n_obs rows per stage, S = N + 1 stages
+};
+
+// ---- compile-time shared-memory layout of one warp's workspace (one warp per block => offsets from smem[0]).
+//      With N and n_obs as template parameters every workspace access is an LDS/STS with an immediate offset.
+__host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
+template <int N_, int NOBS_>
+struct Lay {
+  static constexpr int N = N_, S = N_ + 1, R = 5 + NOBS_, NOBS = NOBS_;
+  static constexpr int LV0 = 0;
+  static constexpr int RW0 = even_up(LV0 + LV_N * S);
+  static constexpr int LQ0 = even_up(RW0 + A_NROW * R * S);
+  static constexpr bool SOC_ALIAS = (3 * R + 14 <= LQ_DEAD);      // SOC scratch fits in the LQ entries that are dead after the factorisation
+  static constexpr int SOC0 = SOC_ALIAS ? LQ0 : even_up(LQ0 + LQ_N * S);
+  static constexpr int STG0 = SOC_ALIAS ? even_up(LQ0 + LQ_N * S) : even_up(SOC0 + (3 * R + 14) * S);
+  static constexpr int OBS0 = STG0 + STG_N;
+  static constexpr int FILT0 = even_up(OBS0 + 3 * NOBS_ + 1);
+  static constexpr int RES0 = FILT0 + 2 * FILT_CAP;
+  static constexpr int PAR0 = RES0 + 24;
+  static constexpr int TOTAL = PAR0 + 12;
 };
 
 // ---- stage state of one lane -----------------------------------------------------------------------
@@ -182,7 +201,7 @@ __device__ __forceinline__ double stage_cost(const Prob& pr, const double* X, do
 }
 
 // stage cost with gradient gl[6] and packed Hessian Hl[21] over (x, y, z, X5, X6, X7)
-__device__ __noinline__ double stage_cost_d2(const Prob& pr, const double* X, double xt, double yt, double* gl, double* Hl) {
+__device__ __forceinline__ double stage_cost_d2(const Prob& pr, const double* X, double xt, double yt, double* gl, double* Hl) {
   Fov f; fov_trig(pr, X, f);
   const double z = X[2];
   const double d6p = 1.0 + f.t6p * f.t6p, d6m = 1.0 + f.t6m * f.t6m, d5p = 1.0 + f.t5p * f.t5p, d5m = 1.0 + f.t5m * f.t5m;

@@ -1,0 +1,30 @@
+// nmpc_inst.cu -- one translation unit per (N, n_obs) instantiation of the IPM kernel (compiled in parallel):
+//   nvcc -DINST_N=15 -DINST_NOBS=3 -c nmpc_inst.cu -o inst_15_3.o
+#include <cuda_runtime.h>
+#include "../../include/nmpc_b200.h"
+#include "nmpc_solve.cuh"
+
+#if !defined(INST_N) || !defined(INST_NOBS)
+#error "compile with -DINST_N=<horizon> -DINST_NOBS=<obstacle rows>"
+#endif
+#define NMPC_CAT_(a, b, c) a##_##b##_##c
+#define NMPC_CAT(a, b, c) NMPC_CAT_(a, b, c)
+
+namespace nmpc {
+
+int NMPC_CAT(ipm_prepare, INST_N, INST_NOBS)(int* blocks_per_sm, size_t* smem_bytes) {
+  using L = Lay<INST_N, INST_NOBS>;
+  const size_t smem = (size_t)L::TOTAL * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(nmpc_ipm_kernel<INST_N, INST_NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nmpc_ipm_kernel<INST_N, INST_NOBS>, 32, smem);
+  *smem_bytes = smem;
+  return (int)e;
+}
+
+int NMPC_CAT(ipm_launch, INST_N, INST_NOBS)(const SolveArgs& A, int blocks, size_t smem, cudaStream_t s) {
+  nmpc_ipm_kernel<INST_N, INST_NOBS><<<blocks, 32, smem, s>>>(A);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace nmpc

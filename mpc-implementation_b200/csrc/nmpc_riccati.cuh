@@ -4,36 +4,44 @@
 //     H = Z^T P+ Z + [R S; S^T Q],   h = Z^T p+ + [r; q],          Z = [B_k | A_k]  (8 x 14),
 // and eliminating the six control pivots by a right-looking Cholesky leaves P_k (8 x 8) and p_k in the trailing
 // block, L (6 x 6), L^-1 Psi (6 x 8) and L^-1 psi in the pivot columns.  All 32 lanes work: every lane OWNS up
-// to four entries of the packed lower triangle (registers), operands are exchanged through a 3.4 KB shared-memory
-// staging area, and every loop is rolled so the whole stage body stays resident in the L0 instruction cache
-// (the first version was 1900 unrolled instructions with 9 of 32 lanes active and stalled on instruction fetch).
+// to four entries of the packed lower triangle (registers), operands are exchanged through a shared-memory
+// staging area, loops are rolled so the stage body is small (the first version was 1900 unrolled instructions with
+// 9 of 32 lanes active and stalled on instruction fetch).
 // "Inertia correct" (IPOPT)  <=>  all six pivots of every stage positive.
+//
+// All workspace accesses go through the `extern __shared__` array with compile-time offsets (Lay<N, NOBS>), so
+// they compile to LDS/STS with immediates (passing shared pointers across __noinline__ calls made them generic
+// LD/ST + R2UR: 41 % of this function's instructions in v2).
 #pragma once
 #include "nmpc_device.cuh"
 
 namespace nmpc {
 
-// staging area layout (doubles)
-constexpr int SG_PP = 0;      // [9][8]  rows 0..7 = P+ (symmetric), row 8 = p+
-constexpr int SG_Z = 72;      // [8][16] Z[s][j], j < 14
-constexpr int SG_Y = 200;     // [15][8] Y_j = P+ z_j (j < 14), Y_14 = p+
-constexpr int SG_COL = 320;   // [16]    published pivot column
-constexpr int SG_FAC = 336;   // [6][16] factor columns l[a], a = 0..14, and 1/l[j][j] at [15]
-constexpr int SG_N = 432;
+extern __shared__ double smem[];
 
-// state-Hessian entry Q_k[i][j] (+ delta_w part) / gradient entry, used for the terminal stage only
-__device__ __forceinline__ double q_entry(const double* lq, int S, int k, int i, int j, double dw) {
+// staging area layout (doubles, relative to Lay::STG0); row strides of 9 keep column accesses conflict-free
+constexpr int SG_PP = 0;      // [9][9]  rows 0..7 = P+ (symmetric), row 8 = p+
+constexpr int SG_Z = 82;      // [8][16] Z[s][j], j < 14
+constexpr int SG_Y = 210;     // [15][9] Y_j = P+ z_j (j < 14), Y_14 = p+
+constexpr int SG_COL = 346;   // [16]    published pivot column
+constexpr int SG_FAC = 362;   // [6][16] factor columns l[a], a = 0..14, and 1/l[j][j] at [15]
+static_assert(SG_FAC + 96 <= STG_N, "staging area too small");
+
+// state-Hessian entry Q_k[i][j] (+ delta_w part), used for the terminal stage only
+template <class L>
+__device__ __forceinline__ double q_entry(int k, int i, int j, double dw) {
   const int qi = q_index(i, j);
-  double v = qi >= 0 ? lq[(LQ_Q + qi) * S + k] : 0.0;
-  if (i < 2 && j < 2) v += dw * lq[(LQ_NN + i + j) * S + k];
-  else if (i == j && i != 4) v += dw * lq[(LQ_DG + ((i == 2) ? 0 : (i == 3 ? 1 : i - 3))) * S + k];
+  double v = qi >= 0 ? smem[L::LQ0 + (LQ_Q + qi) * L::S + k] : 0.0;
+  if (i < 2 && j < 2) v += dw * smem[L::LQ0 + (LQ_NN + i + j) * L::S + k];
+  else if (i == j && i != 4) v += dw * smem[L::LQ0 + (LQ_DG + ((i == 2) ? 0 : (i == 3 ? 1 : i - 3))) * L::S + k];
   return v;
 }
 
-__device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, double* ric, double* stg, double mu, double dw, int lane) {
-  const int S = pr.S, N = pr.N;
-  const double T = pr.T;
-  double* PP = stg + SG_PP; double* ZS = stg + SG_Z; double* YS = stg + SG_Y; double* COL = stg + SG_COL; double* FAC = stg + SG_FAC;
+template <class L>
+__device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, double mu, double dw, int lane) {
+  constexpr int S = L::S, N = L::N;
+  constexpr int PP = L::STG0 + SG_PP, ZS = L::STG0 + SG_Z, YS = L::STG0 + SG_Y, COL = L::STG0 + SG_COL, FAC = L::STG0 + SG_FAC;
+  constexpr int LQ0 = L::LQ0;
   // ---- ownership map: entry e = lane + 32 m of the packed lower triangle of the 15 x 15 matrix, and the
   //      LQ entries that are added to it:  ent += lq[o0] + mu * lq[o1] + dw * (lq[o2] + c3)
   int ia[4], ib[4], o0[4], o1[4], o2[4]; double c3[4];
@@ -62,29 +70,32 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
         else { p0 = LQ_QA + (b - 6); p1 = LQ_QB + (b - 6); p2 = LQ_QD + (b - 6); }
       }
     }
-    o0[m] = p0 * S; o1[m] = p1 * S; o2[m] = p2 * S; c3[m] = cc;
+    o0[m] = LQ0 + p0 * S; o1[m] = LQ0 + p1 * S; o2[m] = LQ0 + p2 * S; c3[m] = cc;
   }
   // ---- static part of Z = [B | A]:  B = T [d e_v ; I_5 on the angle rows],  A = I + E
+#pragma unroll 1
   for (int o = lane; o < 128; o += 32) {
     const int s = o >> 4, j = o & 15;
     double v = 0.0;
     if (j >= 1 && j < 6 && s == j + 2) v = T;
     if (j >= 6 && j < 14 && s == j - 6) v = 1.0;
-    ZS[o] = v;
+    smem[ZS + o] = v;
   }
   // ---- terminal stage: P_N = Q_N, p_N = q_N
+#pragma unroll 1
   for (int o = lane; o < 72; o += 32) {
     const int i = o >> 3, j = o & 7;
-    PP[o] = i < 8 ? q_entry(lq, S, N, i, j, dw)
-                  : lq[(LQ_QA + j) * S + N] + mu * lq[(LQ_QB + j) * S + N] + dw * lq[(LQ_QD + j) * S + N];
+    smem[PP + i * 9 + j] = i < 8 ? q_entry<L>(N, i, j, dw)
+                                 : smem[LQ0 + (LQ_QA + j) * S + N] + mu * smem[LQ0 + (LQ_QB + j) * S + N] + dw * smem[LQ0 + (LQ_QD + j) * S + N];
   }
   __syncwarp();
+#pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
     // stage-dependent entries of Z
     if (lane < 8) {
       const int t = lane;
       const int dst = t < 3 ? t * 16 : (t < 6 ? (t - 3) * 16 + 9 : (t - 6) * 16 + 10);
-      ZS[dst] = t < 3 ? T * lq[(LQ_DD + t) * S + k] : lq[(LQ_EE + (t - 3)) * S + k];
+      smem[ZS + dst] = t < 3 ? T * smem[LQ0 + (LQ_DD + t) * S + k] : smem[LQ0 + (LQ_EE + (t - 3)) * S + k];
     }
     __syncwarp();
     // Y_j = P+ z_j  (j < 14),  Y_14 = p+
@@ -94,9 +105,9 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
       if (j < 14) {
         double acc = 0.0;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) acc += ZS[s * 16 + j] * PP[i * 8 + s];
-        YS[o] = acc;
-      } else if (j == 14) YS[o] = PP[64 + i];
+        for (int s = 0; s < 8; ++s) acc += smem[ZS + s * 16 + j] * smem[PP + i * 9 + s];
+        smem[YS + j * 9 + i] = acc;
+      } else if (j == 14) smem[YS + 14 * 9 + i] = smem[PP + 8 * 9 + i];
     }
     __syncwarp();
     // owned entries of [H | h]
@@ -107,8 +118,8 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
       if (ia[m] >= 0) {
         const int zc = ia[m] == 14 ? ib[m] : ia[m], yr = ia[m] == 14 ? 14 : ib[m];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) acc += ZS[s * 16 + zc] * YS[yr * 8 + s];
-        acc += lq[o0[m] + k] + mu * lq[o1[m] + k] + dw * (lq[o2[m] + k] + c3[m]);
+        for (int s = 0; s < 8; ++s) acc += smem[ZS + s * 16 + zc] * smem[YS + yr * 9 + s];
+        acc += smem[o0[m] + k] + mu * smem[o1[m] + k] + dw * (smem[o2[m] + k] + c3[m]);
       }
       ent[m] = acc;
     }
@@ -116,16 +127,16 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
 #pragma unroll 1
     for (int j = 0; j < 6; ++j) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) if (ib[m] == j) COL[ia[m]] = ent[m];
+      for (int m = 0; m < 4; ++m) if (ib[m] == j) smem[COL + ia[m]] = ent[m];
       __syncwarp();
-      const double d = COL[j];
+      const double d = smem[COL + j];
       if (!(d > 0.0)) return false;                 // uniform: every lane reads the same pivot
       const double id = rsqrt(d);
 #pragma unroll
       for (int m = 0; m < 4; ++m)
-        if (ib[m] > j && ib[m] < 99) ent[m] -= (COL[ia[m]] * id) * (COL[ib[m]] * id);
-      if (lane >= j && lane < 15) FAC[j * 16 + lane] = COL[lane] * id;
-      if (lane == 15) FAC[j * 16 + 15] = id;
+        if (ib[m] > j && ib[m] < 99) ent[m] -= (smem[COL + ia[m]] * id) * (smem[COL + ib[m]] * id);
+      if (lane >= j && lane < 15) smem[FAC + j * 16 + lane] = smem[COL + lane] * id;
+      if (lane == 15) smem[FAC + j * 16 + 15] = id;
       __syncwarp();
     }
     // trailing block -> P_k, p_k for the next stage
@@ -133,8 +144,8 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
     for (int m = 0; m < 4; ++m) {
       if (ib[m] >= 6 && ib[m] < 99) {
         const int a = ia[m] - 6, b = ib[m] - 6;
-        if (ia[m] == 14) PP[64 + b] = ent[m];
-        else { PP[a * 8 + b] = ent[m]; PP[b * 8 + a] = ent[m]; }
+        if (ia[m] == 14) smem[PP + 8 * 9 + b] = ent[m];
+        else { smem[PP + a * 9 + b] = ent[m]; smem[PP + b * 9 + a] = ent[m]; }
       }
     }
     // K = L^-T [L^-1 Psi | L^-1 psi]: lane c < 9 back-substitutes column c
@@ -143,19 +154,19 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
       double x[6];
 #pragma unroll
       for (int i = 5; i >= 0; --i) {
-        double s = FAC[i * 16 + 6 + lane];
+        double s = smem[FAC + i * 16 + 6 + lane];
 #pragma unroll
-        for (int m = i + 1; m < 6; ++m) s -= FAC[i * 16 + m] * x[m];
-        x[i] = s * FAC[i * 16 + 15];
+        for (int m = i + 1; m < 6; ++m) s -= smem[FAC + i * 16 + m] * x[m];
+        x[i] = s * smem[FAC + i * 16 + 15];
       }
 #pragma unroll
       for (int r = 0; r < 6; ++r) rk[RIC_K + r * 9 + lane] = x[r];
     } else if (lane < 30) {            // L (packed lower) for the SOC re-solves: entry e = tri(r, c) = FAC[c][r]
       const int e = lane - 9;
       const int r = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15), c = e - r * (r + 1) / 2;
-      rk[RIC_L + e] = FAC[c * 16 + r];
+      rk[RIC_L + e] = smem[FAC + c * 16 + r];
     }
-    if (lane < 6) rk[RIC_L + 21 + lane] = FAC[lane * 16 + 15];
+    if (lane < 6) rk[RIC_L + 21 + lane] = smem[FAC + lane * 16 + 15];
     __syncwarp();
   }
   return true;
@@ -163,10 +174,10 @@ __device__ __noinline__ bool riccati_factor(const Prob& pr, const double* lq, do
 
 // Forward sweep: du_k = -K_k dx_k - kappa_k, dx_{k+1} = A_k dx_k + B_k du_k.  Lane r < 6 computes row r of du
 // from its row of [K | kappa] (prefetched one stage ahead from the L2-resident scratch); dx is replicated.
-// Lane k keeps its own stage's dx, du and writes them to dxo[8][S], duo[6][S].
-__device__ __noinline__ void riccati_forward(const Prob& pr, const double* lq, const double* ric,
-                                             bool soc, int lane, double* dxo, double* duo) {
-  const int S = pr.S, N = pr.N; const double T = pr.T;
+// Lane k keeps its own stage's dx, du and writes them to the shared-memory entries dx0 / du0 (offsets, [.][S]).
+template <class L>
+__device__ __noinline__ void riccati_forward(double T, const double* ric, bool soc, int lane, int dx0, int du0) {
+  constexpr int S = L::S, N = L::N, LQ0 = L::LQ0;
   const int r = lane < 6 ? lane : 5;
   double dx[8], mydx[8], mydu[6];
 #pragma unroll
@@ -196,9 +207,9 @@ __device__ __noinline__ void riccati_forward(const Prob& pr, const double* lq, c
 #pragma unroll
       for (int i = 0; i < 6; ++i) mydu[i] = du[i];
     }
-    const double d0 = lq[(LQ_DD + 0) * S + k], d1 = lq[(LQ_DD + 1) * S + k], d2 = lq[(LQ_DD + 2) * S + k];
-    const double e03 = lq[(LQ_EE + 0) * S + k], e13 = lq[(LQ_EE + 1) * S + k], e23 = lq[(LQ_EE + 2) * S + k];
-    const double e04 = lq[(LQ_EE + 3) * S + k], e14 = lq[(LQ_EE + 4) * S + k];
+    const double d0 = smem[LQ0 + (LQ_DD + 0) * S + k], d1 = smem[LQ0 + (LQ_DD + 1) * S + k], d2 = smem[LQ0 + (LQ_DD + 2) * S + k];
+    const double e03 = smem[LQ0 + (LQ_EE + 0) * S + k], e13 = smem[LQ0 + (LQ_EE + 1) * S + k], e23 = smem[LQ0 + (LQ_EE + 2) * S + k];
+    const double e04 = smem[LQ0 + (LQ_EE + 3) * S + k], e14 = smem[LQ0 + (LQ_EE + 4) * S + k];
     const double tv = T * du[0];
     dx[0] += e03 * dx[3] + e04 * dx[4] + tv * d0;
     dx[1] += e13 * dx[3] + e14 * dx[4] + tv * d1;
@@ -212,38 +223,40 @@ __device__ __noinline__ void riccati_forward(const Prob& pr, const double* lq, c
   }
   if (lane <= N) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dxo[i * S + lane] = mydx[i];
+    for (int i = 0; i < 8; ++i) smem[dx0 + i * S + lane] = mydx[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) duo[i * S + lane] = mydu[i];
+    for (int i = 0; i < 6; ++i) smem[du0 + i * S + lane] = mydu[i];
   }
   __syncwarp();
 }
 
-// Backward sweep for a new state gradient q' (q2[8][S]) with the stored factors (SOC right-hand sides).
-__device__ __noinline__ void riccati_resolve(const Prob& pr, const double* lq, const double* q2, double* ric, double mu, int lane) {
-  const int S = pr.S, N = pr.N; const double T = pr.T;
+// Backward sweep for a new state gradient q' (shared-memory entries q20, [8][S]) with the stored factors
+// (second-order-correction right-hand sides).
+template <class L>
+__device__ __noinline__ void riccati_resolve(double T, int q20, double* ric, double mu, int lane) {
+  constexpr int S = L::S, N = L::N, LQ0 = L::LQ0;
   double p[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) p[i] = q2[i * S + N];
+  for (int i = 0; i < 8; ++i) p[i] = smem[q20 + i * S + N];
 #pragma unroll 1
   for (int k = N - 1; k >= 0; --k) {
     double* rk = ric + k * RIC_N;
-    const double d0 = lq[(LQ_DD + 0) * S + k], d1 = lq[(LQ_DD + 1) * S + k], d2 = lq[(LQ_DD + 2) * S + k];
-    const double e03 = lq[(LQ_EE + 0) * S + k], e13 = lq[(LQ_EE + 1) * S + k], e23 = lq[(LQ_EE + 2) * S + k];
-    const double e04 = lq[(LQ_EE + 3) * S + k], e14 = lq[(LQ_EE + 4) * S + k];
+    const double d0 = smem[LQ0 + (LQ_DD + 0) * S + k], d1 = smem[LQ0 + (LQ_DD + 1) * S + k], d2 = smem[LQ0 + (LQ_DD + 2) * S + k];
+    const double e03 = smem[LQ0 + (LQ_EE + 0) * S + k], e13 = smem[LQ0 + (LQ_EE + 1) * S + k], e23 = smem[LQ0 + (LQ_EE + 2) * S + k];
+    const double e04 = smem[LQ0 + (LQ_EE + 3) * S + k], e14 = smem[LQ0 + (LQ_EE + 4) * S + k];
     double psi[6], kap[6];
-    psi[0] = mu * lq[(LQ_RB + 0) * S + k] + T * (d0 * p[0] + d1 * p[1] + d2 * p[2]);
+    psi[0] = mu * smem[LQ0 + (LQ_RB + 0) * S + k] + T * (d0 * p[0] + d1 * p[1] + d2 * p[2]);
 #pragma unroll
-    for (int r = 1; r < 6; ++r) psi[r] = mu * lq[(LQ_RB + r) * S + k] + T * p[r + 2];
-    double L[21], idg[6];
+    for (int r = 1; r < 6; ++r) psi[r] = mu * smem[LQ0 + (LQ_RB + r) * S + k] + T * p[r + 2];
+    double Lf[21], idg[6];
 #pragma unroll
-    for (int e = 0; e < 21; ++e) L[e] = __ldcg(rk + RIC_L + e);
+    for (int e = 0; e < 21; ++e) Lf[e] = __ldcg(rk + RIC_L + e);
 #pragma unroll
     for (int r = 0; r < 6; ++r) { idg[r] = __ldcg(rk + RIC_L + 21 + r); kap[r] = psi[r]; }
-    chol6_solve(L, idg, kap);
+    chol6_solve(Lf, idg, kap);
     double pn[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pn[i] = q2[i * S + k] + p[i];
+    for (int i = 0; i < 8; ++i) pn[i] = smem[q20 + i * S + k] + p[i];
     pn[3] += e03 * p[0] + e13 * p[1] + e23 * p[2];
     pn[4] += e04 * p[0] + e14 * p[1];
 #pragma unroll

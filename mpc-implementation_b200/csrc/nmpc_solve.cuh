@@ -6,8 +6,9 @@
 // monotone barrier, fraction-to-boundary, inertia correction, filter line search + second-order
 // correction, scaled optimality-error termination.  The whole iteration loop runs inside the kernel.
 //
-// v2 structure: the iterate lives in shared memory; every phase is a __noinline__ function that loads its
-// operands, works in registers and stores back, so each heavy code sequence exists exactly once.
+// Structure (v3): the iterate lives in shared memory at compile-time offsets (Lay<N, NOBS>); every phase is a
+// __noinline__ function template that loads its operands, works in registers and stores back, so each heavy
+// code sequence exists exactly once and every workspace access is an LDS/STS with an immediate offset.
 #pragma once
 #include "nmpc_device.cuh"
 #include "nmpc_riccati.cuh"
@@ -36,35 +37,12 @@ struct SolveArgs {
   int obs_per_instance;
   double *x, *f, *g, *lam_x, *lam_g;
   int32_t *status, *iters;
+  const int32_t* order;              // optional processing order (longest-first scheduling); NULL = 0..B-1
   int* counter;                      // work queue
   unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
   double* ric; int ric_stride;       // L2-resident Riccati scratch, one slice per resident warp
-  int ws_doubles;                    // per-warp shared-memory workspace
   double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][8] (tests only)
 };
-
-// shared-memory workspace of one warp
-struct Ws { double *lv, *rows, *lq, *soc, *stg, *obs, *filt, *res, *par, *ric; };
-
-__host__ __device__ inline bool soc_aliases_lq(int R) { return 3 * R + 14 <= LQ_DEAD; }
-__host__ __device__ inline int ws_size(int S, int R, int n_obs) {
-  int n = LV_N * S + A_NROW * R * S + LQ_N * S + (soc_aliases_lq(R) ? 0 : (3 * R + 14) * S) + STG_N + 3 * n_obs + 2 * FILT_CAP + 24 + 12;
-  return (n + 1) & ~1;
-}
-__device__ __forceinline__ Ws carve(double* base, int S, int R, int n_obs) {
-  Ws w; double* q = base;
-  w.lv = q; q += LV_N * S;
-  w.rows = q; q += A_NROW * R * S;
-  w.lq = q; q += LQ_N * S;
-  if (soc_aliases_lq(R)) w.soc = w.lq; else { w.soc = q; q += (3 * R + 14) * S; }
-  w.stg = q; q += STG_N;
-  w.obs = q; q += 3 * n_obs;
-  w.filt = q; q += 2 * FILT_CAP;
-  w.res = q; q += 24;
-  w.par = q;
-  w.ric = nullptr;
-  return w;
-}
 
 constexpr double EPSM = 2.220446049250313e-16;
 __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * EPSM * fabs(bas); }
@@ -80,7 +58,7 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi, bool h
 }
 
 struct Bnd { double lo, hi; bool hl, hu; };
-// relaxed bounds of control i of stage k (NMPC_TT.py:294-306) and of the scaled row r of stage k (:275-291)
+// Relaxed bounds of control i of stage k (NMPC_TT.py:294-306) and of the scaled row r of stage k (:275-291).
 // NOTE: these are inlined into several phase functions; the explicit round-to-nearest intrinsics keep the compiler
 // from contracting the expressions into FMAs differently per copy.  A bound that differs by one ulp between the
 // function that builds the Newton system and the one that updates the multipliers is a 1e-6 RELATIVE error of a
@@ -92,8 +70,9 @@ __device__ __forceinline__ Bnd ctl_bounds(const SolveArgs& A, int k, int i) {
   b.hi = b.hu ? __dadd_rn(hi, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(hi)))) : CUDART_INF;
   return b;
 }
+template <class L>
 __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, double dc) {
-  const double lo = __ldg(A.lbg + k * A.pr.R + r), hi = __ldg(A.ubg + k * A.pr.R + r);
+  const double lo = __ldg(A.lbg + k * L::R + r), hi = __ldg(A.ubg + k * L::R + r);
   Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
   const double l2 = __dmul_rn(dc, lo), h2 = __dmul_rn(dc, hi);
   b.lo = b.hl ? __dsub_rn(l2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(l2)))) : -CUDART_INF;
@@ -101,15 +80,17 @@ __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, doub
   return b;
 }
 
-#define LV(e) ws.lv[(e) * S + lane]
-#define RW(arr, r) ws.rows[((arr) * R + (r)) * S + lane]
-#define LQ(e) ws.lq[(e) * S + lane]
-#define SOC(e) ws.soc[(e) * S + lane]
+#define LV(e) smem[L::LV0 + (e) * L::S + lane]
+#define RW(arr, r) smem[L::RW0 + ((arr) * L::R + (r)) * L::S + lane]
+#define LQ(e) smem[L::LQ0 + (e) * L::S + lane]
+#define SOC(e) smem[L::SOC0 + (e) * L::S + lane]
+#define RES(i) smem[L::RES0 + (i)]
+#define PAR(i) smem[L::PAR0 + (i)]
 #define SOC_DS2 0
-#define SOC_CSOC (R)
-#define SOC_CT (2 * R)
-#define SOC_DUS (3 * R)
-#define SOC_Q2 (3 * R + 6)
+#define SOC_CSOC (L::R)
+#define SOC_CT (2 * L::R)
+#define SOC_DUS (3 * L::R)
+#define SOC_Q2 (3 * L::R + 6)
 
 // T-scaled non-zeros of the dynamics Jacobian A_k - I of this lane's stage
 struct Dyn { double e03, e13, e23, e04, e14; };
@@ -130,36 +111,62 @@ __device__ __forceinline__ void adjoint(const double* a, const Dyn& d, bool act,
   lamn[3] = shfl_next(w[0], lane); lamn[4] = shfl_next(w[1], lane);
 }
 
+// obstacle row jn of this lane's stage: value (r_u + r_o) - ||(x,y) - c_j||, unit normal, 1/distance   NMPC_TT.py:241-243
+template <class L>
+__device__ __forceinline__ double obs_value(const double* X, int jn, double& nx, double& ny, double& iD) {
+  const double dx_ = X[0] - smem[L::OBS0 + 3 * jn], dy_ = X[1] - smem[L::OBS0 + 3 * jn + 1];
+  const double d2 = __fma_rn(dx_, dx_, __dmul_rn(dy_, dy_));
+  const double D = sqrt(d2);
+  iD = rcp(D); nx = dx_ * iD; ny = dy_ * iD;
+  return smem[L::OBS0 + 3 * jn + 2] - D;
+}
+// Visit the rows of this lane's stage: the five box rows fully unrolled (static state index si), the obstacle
+// rows in a rolled loop.  body(r, box, si, gu, nx, ny, iD) with gu the unscaled row value.
+#define FOR_ROWS(X, body)                                                                           \
+  do {                                                                                              \
+    _Pragma("unroll") for (int r_ = 0; r_ < 5; ++r_) {                                              \
+      const int si_ = r_ == 0 ? 2 : (r_ == 1 ? 3 : r_ + 3);                                         \
+      body(r_, true, si_, (X)[si_], 0.0, 0.0, 0.0);                                                 \
+    }                                                                                               \
+    _Pragma("unroll 1") for (int jn_ = 0; jn_ < L::NOBS; ++jn_) {                                   \
+      double nx_, ny_, iD_;                                                                         \
+      const double gu_ = obs_value<L>((X), jn_, nx_, ny_, iD_);                                     \
+      body(5 + jn_, false, 0, gu_, nx_, ny_, iD_);                                                  \
+    }                                                                                               \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------
-// load one instance: p -> par, warm start -> LV_U, obstacle table, unit scaling
-__device__ __noinline__ void ph_load(const SolveArgs& A, const Ws& ws, int b, int lane) {
-  const int N = A.pr.N, S = A.pr.S, R = A.pr.R, n_obs = A.pr.n_obs;
-  if (lane < NPAR) ws.par[lane] = A.p[(size_t)b * NPAR + lane];
-  const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * n_obs : 0);
-  for (int i = lane; i < 3 * n_obs; i += 32) ws.obs[i] = ob[i];
-  if (lane <= N) {
-    const double* xx = A.x0 + (size_t)b * (NU * N) + NU * lane;
+// load one instance: p -> PAR, warm start -> LV_U, obstacle table, unit scaling
+template <class L>
+__device__ __noinline__ void ph_load(const SolveArgs& A, int b, int lane) {
+  if (lane < NPAR) PAR(lane) = A.p[(size_t)b * NPAR + lane];
+  const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * L::NOBS : 0);
+  for (int i = lane; i < 3 * L::NOBS; i += 32) smem[L::OBS0 + i] = ob[i];
+  if (lane <= L::N) {
+    const double* xx = A.x0 + (size_t)b * (NU * L::N) + NU * lane;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { LV(LV_U + i) = lane < N ? xx[i] : 0.0; LV(LV_DU + i) = 0.0; }
-    for (int r = 0; r < R; ++r) { RW(A_DC, r) = 1.0; RW(A_DS, r) = 0.0; }
+    for (int i = 0; i < 6; ++i) { LV(LV_U + i) = lane < L::N ? xx[i] : 0.0; LV(LV_DU + i) = 0.0; }
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) { RW(A_DC, r) = 1.0; RW(A_DS, r) = 0.0; }
   }
   __syncwarp();
 }
 
 // gradient-based scaling at the user's starting point (IPOPT nlp_scaling_method = gradient-based): returns df, sets DC
-__device__ __noinline__ double ph_scaling(const SolveArgs& A, const Ws& ws, int lane) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R, n_obs = pr.n_obs; const double T = pr.T;
+template <class L>
+__device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
+  const Prob& pr = A.pr; constexpr int N = L::N; const double T = pr.T;
   const bool act = lane <= N, hasu = lane < N;
   double u[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = act ? LV(LV_U + i) : 0.0;
-  Stage st; rollout(pr, ws.par, u, lane, st);
+  Stage st; rollout(pr, &PAR(0), u, lane, st);
   const Dyn dy = dyn_entries(st, hasu ? T * u[0] : 0.0);
   double gl[6], Hl[21], a[8], lamn[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.0;
   if (hasu && lane >= 1) {
-    stage_cost_d2(pr, st.X, ws.par[8], ws.par[9], gl, Hl);
+    stage_cost_d2(pr, st.X, PAR(8), PAR(9), gl, Hl);
 #pragma unroll
     for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
   }
@@ -177,11 +184,14 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, const Ws& ws, int 
   scan_excl<3>(c3, lane); scan_excl<2>(c4, lane);
   double zmax = 0.0;
   // scratch in row arrays that are not live yet: A_G = row max, A_IL / A_IU = obstacle normal
-  if (act) for (int jn = 0; jn < n_obs; ++jn) {
-    const double dx_ = st.X[0] - ws.obs[3 * jn], dy_ = st.X[1] - ws.obs[3 * jn + 1];
-    const double iD = rsqrt(dx_ * dx_ + dy_ * dy_);
-    RW(A_G, 5 + jn) = 0.0; RW(A_IL, 5 + jn) = dx_ * iD; RW(A_IU, 5 + jn) = dy_ * iD;
+  if (act) {
+#pragma unroll 1
+    for (int jn = 0; jn < L::NOBS; ++jn) {
+      double nx, ny, iD; obs_value<L>(st.X, jn, nx, ny, iD);
+      RW(A_G, 5 + jn) = 0.0; RW(A_IL, 5 + jn) = nx; RW(A_IU, 5 + jn) = ny;
+    }
   }
+#pragma unroll 1
   for (int jj = 0; jj < N; ++jj) {
     const double dj0 = __shfl_sync(FULL, d0, jj), dj1 = __shfl_sync(FULL, d1, jj), dj2 = __shfl_sync(FULL, d2, jj);
     const double a30 = __shfl_sync(FULL, c3[0], jj + 1), a31 = __shfl_sync(FULL, c3[1], jj + 1), a32 = __shfl_sync(FULL, c3[2], jj + 1);
@@ -191,7 +201,8 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, const Ws& ws, int 
       const double pt0 = T * (c3[0] - a30), pt1 = T * (c3[1] - a31), pt2 = T * (c3[2] - a32);
       const double pp0 = T * (c4[0] - a40), pp1 = T * (c4[1] - a41);
       zmax = fmax(zmax, fmax(fabs(pv2), fabs(pt2)));
-      for (int jn = 0; jn < n_obs; ++jn) {
+#pragma unroll 1
+      for (int jn = 0; jn < L::NOBS; ++jn) {
         const double nx = RW(A_IL, 5 + jn), ny = RW(A_IU, 5 + jn);
         const double m1 = fabs(nx * pv0 + ny * pv1), m2 = fabs(nx * pt0 + ny * pt1), m3 = fabs(nx * pp0 + ny * pp1);
         RW(A_G, 5 + jn) = fmax(RW(A_G, 5 + jn), fmax(m1, fmax(m2, m3)));
@@ -204,26 +215,17 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, const Ws& ws, int 
     const double lin = lane >= 1 ? T : 0.0, sl = lin > mg ? fmax(smin, mg / lin) : 1.0;
 #pragma unroll
     for (int r = 1; r < 5; ++r) RW(A_DC, r) = sl;
-    for (int jn = 0; jn < n_obs; ++jn) { const double m = RW(A_G, 5 + jn); RW(A_DC, 5 + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
+#pragma unroll 1
+    for (int jn = 0; jn < L::NOBS; ++jn) { const double m = RW(A_G, 5 + jn); RW(A_DC, 5 + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
   }
   __syncwarp();
   return gmax > A.o.max_grad ? fmax(A.o.scal_min, A.o.max_grad / gmax) : 1.0;
 }
 
-// constraint value of row r of this lane's stage (unscaled) and, for obstacle rows, the unit normal
-__device__ __forceinline__ double row_value(const Ws& ws, const double* X, int r, double& nx, double& ny, double& iD) {
-  if (r < 5) { nx = 0.0; ny = 0.0; iD = 0.0; return X[box_state(r)]; }
-  const int jn = r - 5;
-  const double dx_ = X[0] - ws.obs[3 * jn], dy_ = X[1] - ws.obs[3 * jn + 1];
-  const double d2 = __fma_rn(dx_, dx_, __dmul_rn(dy_, dy_));
-  const double D = sqrt(d2);
-  iD = rcp(D); nx = dx_ * iD; ny = dy_ * iD;
-  return ws.obs[3 * jn + 2] - D;
-}
-
 // starting point: push controls and slacks inside their bounds, unit bound multipliers; returns #finite bounds
-__device__ __noinline__ int ph_start(const SolveArgs& A, const Ws& ws, int lane) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+template <class L>
+__device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
+  const Prob& pr = A.pr; constexpr int N = L::N;
   const bool act = lane <= N, hasu = lane < N;
   double u[6]; int nz = 0;
 #pragma unroll
@@ -236,16 +238,19 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, const Ws& ws, int lane)
       nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
     } else if (act) { LV(LV_ZL + i) = 0.0; LV(LV_ZU + i) = 0.0; }
   }
-  Stage st; rollout(pr, ws.par, u, lane, st);
-  if (act) for (int r = 0; r < R; ++r) {
-    double nx, ny, iD; const double dc = RW(A_DC, r);
-    const double g = __dmul_rn(dc, row_value(ws, st.X, r, nx, ny, iD));
-    const Bnd b = row_bounds(A, lane, r, dc);
-    const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
-    RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = 0.0;
-    RW(A_VL, r) = b.hl ? 1.0 : 0.0; RW(A_VU, r) = b.hu ? 1.0 : 0.0;
-    RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
-    nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
+  Stage st; rollout(pr, &PAR(0), u, lane, st);
+  if (act) {
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
+      const double dc = RW(A_DC, r);
+      const double g = __dmul_rn(dc, gu);
+      const Bnd b = row_bounds<L>(A, lane, r, dc);
+      const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
+      RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = 0.0;
+      RW(A_VL, r) = b.hl ? 1.0 : 0.0; RW(A_VU, r) = b.hu ? 1.0 : 0.0;
+      RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
+      nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
+    };
+    FOR_ROWS(st.X, body);
   }
   __syncwarp();
   return __reduce_add_sync(FULL, nz);
@@ -253,14 +258,15 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, const Ws& ws, int lane)
 
 // ---------------------------------------------------------------------------------------------------
 // derivatives at the current point: stage Hessian blocks / gradients of the LQ sub-problem into LQ, optimality
-// error ingredients into res.  ls = least-squares multiplier system (W = 0, Sigma = I, rhs = gradient of L).
-__device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lane, bool ls, double df) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R; const double T = pr.T;
+// error ingredients into RES.  ls = least-squares multiplier system (W = 0, Sigma = I, rhs = gradient of L).
+template <class L>
+__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df) {
+  const Prob& pr = A.pr; constexpr int N = L::N; const double T = pr.T;
   const bool act = lane <= N, hasu = lane < N;
   double u[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = act ? LV(LV_U + i) : 0.0;
-  Stage st; rollout(pr, ws.par, u, lane, st);
+  Stage st; rollout(pr, &PAR(0), u, lane, st);
   const Dyn dy = dyn_entries(st, hasu ? T * u[0] : 0.0);
   double gl[6], Hl[21];
 #pragma unroll
@@ -268,14 +274,12 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lan
 #pragma unroll
   for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
   double l = 0.0;
-  if (hasu) {
-    l = stage_cost_d2(pr, st.X, ws.par[8], ws.par[9], gl, Hl);
-    if (lane == 0) {   // stage 0 is constant in w
+  if (hasu) l = stage_cost_d2(pr, st.X, PAR(8), PAR(9), gl, Hl);
+  if (lane == 0) {   // stage 0 is constant in w
 #pragma unroll
-      for (int v = 0; v < 6; ++v) gl[v] = 0.0;
+    for (int v = 0; v < 6; ++v) gl[v] = 0.0;
 #pragma unroll
-      for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
-    }
+    for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
   }
   const double fsum = df * warp_sum(l);
   double a[8], qa[8], qb[8], qd[8];
@@ -286,35 +290,33 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lan
 #pragma unroll
     for (int i = 0; i < 8; ++i) LV(LV_X + i) = st.X[i];
 #pragma unroll
-    for (int v = 0; v < 6; ++v) { gl[v] *= df; LV(LV_GL + v) = gl[v]; a[cost_state(v)] = gl[v]; }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qa[i] = a[i];
+    for (int v = 0; v < 6; ++v) { gl[v] *= df; LV(LV_GL + v) = gl[v]; a[cost_state(v)] = gl[v]; qa[cost_state(v)] = gl[v]; }
     double q66[21], q22 = 0.0, nn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int e = 0; e < 21; ++e) q66[e] = ls ? 0.0 : df * Hl[e];
-    for (int r = 0; r < R; ++r) {
-      double nx, ny, iD; const double dc = RW(A_DC, r);
-      const double gu = row_value(ws, st.X, r, nx, ny, iD), g = __dmul_rn(dc, gu);
+    const double kd = A.o.kappa_d;
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
+      const double dc = RW(A_DC, r);
+      const double g = __dmul_rn(dc, gu);
       const double s = RW(A_S, r), y = RW(A_Y, r), vl = RW(A_VL, r), vu = RW(A_VU, r), il = RW(A_IL, r), iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       RW(A_G, r) = g;
       const double c = g - s;
       const double sig = ls ? 1.0 : vl * il + vu * iu;
       double beta = iu - il;                              // barrier gradient per unit mu (with damping)
-      if (hl && !hu) beta += A.o.kappa_d;
-      if (hu && !hl) beta -= A.o.kappa_d;
+      if (hl && !hu) beta += kd;
+      if (hu && !hl) beta -= kd;
       const double ya = ls ? (vu - vl) : sig * c;         // delta_w- and mu-free part of y-hat
       const double w = dc * dc * sig;
-      if (r < 5) {
-        const int i = box_state(r);
-        a[i] += dc * y; qa[i] += dc * ya; qb[i] += dc * beta; qd[i] += dc * c;
-        if (r == 0) q66[tri(2, 2)] += w; else if (r == 1) q22 += w; else if (r == 2) q66[tri(3, 3)] += w;
-        else if (r == 3) q66[tri(4, 4)] += w; else q66[tri(5, 5)] += w;
+      if (box) {
+        a[si] += dc * y; qa[si] += dc * ya; qb[si] += dc * beta; qd[si] += dc * c;
+        if (si == 3) q22 += w; else q66[tri(si < 3 ? si : si - 2, si < 3 ? si : si - 2)] += w;
+        LQ(LQ_DG + r) = dc * dc;
       } else {
         const double cur = ls ? 0.0 : -y * dc * iD;        // y * d2h,  d2h = -(I - n n^T)/D
-        q66[tri(0, 0)] += w * nx * nx + cur * (1.0 - nx * nx);
-        q66[tri(1, 0)] += w * nx * ny - cur * nx * ny;
-        q66[tri(1, 1)] += w * ny * ny + cur * (1.0 - ny * ny);
+        q66[0] += w * nx * nx + cur * (1.0 - nx * nx);
+        q66[1] += w * nx * ny - cur * nx * ny;
+        q66[2] += w * ny * ny + cur * (1.0 - ny * ny);
         nn[0] += dc * dc * nx * nx; nn[1] += dc * dc * nx * ny; nn[2] += dc * dc * ny * ny;
         const double gy = -dc * y, ga = -dc * ya, gb = -dc * beta, gd = -dc * c;
         a[0] += gy * nx; a[1] += gy * ny; qa[0] += ga * nx; qa[1] += ga * ny;
@@ -322,39 +324,39 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lan
       }
       // optimality-error ingredients
       du_l = fmax(du_l, fabs(-y - vl + vu)); pr_l = fmax(pr_l, fabs(c)); sumy += fabs(y); sumz += vl + vu;
-      const Bnd b = row_bounds(A, lane, r, dc);
+      const Bnd b = row_bounds<L>(A, lane, r, dc);
       if (b.hl) { const double pz = (s - b.lo) * vl; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
       if (b.hu) { const double pz = (b.hi - s) * vu; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
-      const double lo_o = __ldg(A.lbg + lane * R + r), hi_o = __ldg(A.ubg + lane * R + r);
+      const double lo_o = __ldg(A.lbg + lane * L::R + r), hi_o = __ldg(A.ubg + lane * L::R + r);
       if (lo_o > -1e19) viol = fmax(viol, lo_o - gu);
       if (hi_o < 1e19) viol = fmax(viol, gu - hi_o);
-    }
+    };
+    FOR_ROWS(st.X, body);
 #pragma unroll
     for (int e = 0; e < 21; ++e) LQ(LQ_Q + e) = q66[e];
-    LQ(LQ_Q + 21) = q22; LQ(LQ_Q + 22) = 0.0; LQ(LQ_Q + 23) = 0.0;
     LQ(LQ_NN + 0) = nn[0]; LQ(LQ_NN + 1) = nn[1]; LQ(LQ_NN + 2) = nn[2];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) { const double dc = RW(A_DC, r); LQ(LQ_DG + r) = dc * dc; }
     LQ(LQ_ZERO) = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { LQ(LQ_QA + i) = qa[i]; LQ(LQ_QB + i) = ls ? 0.0 : qb[i]; LQ(LQ_QD + i) = ls ? 0.0 : qd[i]; }
     LQ(LQ_DD + 0) = st.cps * st.cth; LQ(LQ_DD + 1) = st.sps * st.cth; LQ(LQ_DD + 2) = st.sth;
     LQ(LQ_EE + 0) = dy.e03; LQ(LQ_EE + 1) = dy.e13; LQ(LQ_EE + 2) = dy.e23; LQ(LQ_EE + 3) = dy.e04; LQ(LQ_EE + 4) = dy.e14;
+    LQ(LQ_Q + 21) = q22;
   }
   double lamn[8];
   adjoint(a, dy, act, lane, lamn);
   if (act) {
-    double svt = 0.0, svp = 0.0;
+    double svt = 0.0, svp = 0.0, q33 = 0.0, q34 = 0.0, q44 = 0.0;
     if (hasu && !ls) {
       // curvature of T*v*d(theta,psi) weighted by the next-stage adjoint
       const double L0 = T * lamn[0], L1 = T * lamn[1], L2 = T * lamn[2], v = u[0];
       const double cc = st.cps * st.cth, sc = st.sps * st.cth, cs = st.cps * st.sth, ss = st.sps * st.sth;
-      LQ(LQ_Q + 21) += -v * (L0 * cc + L1 * sc + L2 * st.sth);
-      LQ(LQ_Q + 23) = -v * (L0 * cc + L1 * sc);
-      LQ(LQ_Q + 22) = v * (L0 * ss - L1 * cs);
+      q33 = -v * (L0 * cc + L1 * sc + L2 * st.sth);
+      q44 = -v * (L0 * cc + L1 * sc);
+      q34 = v * (L0 * ss - L1 * cs);
       svt = -L0 * cs - L1 * ss + L2 * st.cth;
       svp = -L0 * sc + L1 * cc;
     }
+    LQ(LQ_Q + 21) += q33; LQ(LQ_Q + 22) = q34; LQ(LQ_Q + 23) = q44;
     LQ(LQ_SV + 0) = svt; LQ(LQ_SV + 1) = svp;
     // controls: Sigma_x, gradient per unit mu, dual infeasibility, complementarity products
     double glx[6];
@@ -385,39 +387,44 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, const Ws& ws, int lan
   du_l = warp_max(du_l); pr_l = warp_max(pr_l); sumy = warp_sum(sumy); sumz = warp_sum(sumz);
   viol = warp_max(viol); pmax = warp_max(pmax); pmin = warp_min(pmin);
   if (lane == 0) {
-    ws.res[R_F] = fsum; ws.res[R_DU] = du_l; ws.res[R_PR] = pr_l; ws.res[R_SUMY] = sumy; ws.res[R_SUMZ] = sumz;
-    ws.res[R_VIOL] = viol; ws.res[R_PMAX] = pmax; ws.res[R_PMIN] = pmin;
+    RES(R_F) = fsum; RES(R_DU) = du_l; RES(R_PR) = pr_l; RES(R_SUMY) = sumy; RES(R_SUMZ) = sumz;
+    RES(R_VIOL) = viol; RES(R_PMAX) = pmax; RES(R_PMIN) = pmin;
   }
   __syncwarp();
 }
 
 // least-squares multipliers from the solved LS system: y = G dx + (v_U - v_L); zero if too large
-__device__ __noinline__ void ph_lsy(const SolveArgs& A, const Ws& ws, int lane, bool ok) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
-  const bool act = lane <= N;
+template <class L>
+__device__ __noinline__ void ph_lsy(const SolveArgs& A, int lane, bool ok) {
+  const bool act = lane <= L::N;
   double ymax = 0.0;
   if (act && ok) {
     double X[8], dx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); dx[i] = LV(LV_DX + i); }
-    for (int r = 0; r < R; ++r) {
-      double nx, ny, iD; row_value(ws, X, r, nx, ny, iD);
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r);
-      const double gd = r < 5 ? dc * dx[box_state(r)] : -dc * (nx * dx[0] + ny * dx[1]);
+      const double gd = box ? dc * dx[si] : -dc * (nx * dx[0] + ny * dx[1]);
       const double yv = gd + (RW(A_VU, r) - RW(A_VL, r));
       RW(A_Y, r) = yv; ymax = fmax(ymax, fabs(yv));
-    }
+    };
+    FOR_ROWS(X, body);
   }
   ymax = warp_max(ymax);
-  if (!ok || !(ymax <= A.o.constr_mult_init_max)) { if (act) for (int r = 0; r < R; ++r) RW(A_Y, r) = 0.0; }
+  if (!ok || !(ymax <= A.o.constr_mult_init_max)) {
+    if (act) {
+#pragma unroll 1
+      for (int r = 0; r < L::R; ++r) RW(A_Y, r) = 0.0;
+    }
+  }
   __syncwarp();
 }
 
 // step in the slacks, fraction-to-the-boundary limits, directional derivative of the barrier function.
 // soc: second-order-correction direction (residual CSOC, controls DUS, output DS2).
-__device__ __noinline__ void ph_dir(const SolveArgs& A, const Ws& ws, int lane, double mu, double tau, bool soc) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
-  const bool act = lane <= N, hasu = lane < N;
+template <class L>
+__device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, double tau, bool soc) {
+  const bool act = lane <= L::N, hasu = lane < L::N;
   double tp = 0.0, dnum = 0.0, dden = 1.0, gbd = 0.0, theta = 0.0; bool nottiny = false;
   const double tt = A.o.tiny_step_tol, kd = A.o.kappa_d;
   auto dual_frac = [&](double z, double dz) {   // track max of -dz/z over dz < 0 as a fraction
@@ -427,12 +434,11 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, const Ws& ws, int lane, 
     double X[8], dx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); dx[i] = LV(LV_DX + i); }
-    for (int r = 0; r < R; ++r) {
-      double nx, ny, iD; row_value(ws, X, r, nx, ny, iD);
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), vl = RW(A_VL, r), vu = RW(A_VU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       const double c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) - s;
-      const double gd = r < 5 ? dc * dx[box_state(r)] : -dc * (nx * dx[0] + ny * dx[1]);
+      const double gd = box ? dc * dx[si] : -dc * (nx * dx[0] + ny * dx[1]);
       const double ds = gd + c;
       if (soc) SOC(SOC_DS2 + r) = ds; else RW(A_DS, r) = ds;
       tp = fmax(tp, fmax(-ds * il, ds * iu));
@@ -443,7 +449,8 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, const Ws& ws, int lane, 
       if (hu && !hl) beta -= kd;
       gbd += mu * beta * ds; theta += fabs(c);
       nottiny = nottiny || (fabs(ds) > tt * (1.0 + fabs(s)));
-    }
+    };
+    FOR_ROWS(X, body);
     if (hasu) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
@@ -468,17 +475,18 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, const Ws& ws, int lane, 
   gbd = warp_sum(gbd); theta = warp_sum(theta);
   const bool any_nt = __any_sync(FULL, nottiny);
   if (lane == 0) {
-    ws.res[R_APR] = tp > tau ? tau / tp : 1.0;             // alpha = min(1, tau / max ratio)
-    ws.res[R_ADU] = td > tau ? tau / td : 1.0;
-    if (!soc) { ws.res[R_GBD] = gbd; ws.res[R_THETA] = theta; ws.res[R_TINY] = any_nt ? 0.0 : 1.0; }
+    RES(R_APR) = tp > tau ? tau / tp : 1.0;             // alpha = min(1, tau / max ratio)
+    RES(R_ADU) = td > tau ? tau / td : 1.0;
+    if (!soc) { RES(R_GBD) = gbd; RES(R_THETA) = theta; RES(R_TINY) = any_nt ? 0.0 : 1.0; }
   }
   __syncwarp();
 }
 
 // trial point u + alpha*du, s + alpha*ds: objective, constraint violation, barrier pieces; residual into CT
-__device__ __noinline__ void ph_trial(const SolveArgs& A, const Ws& ws, int lane, double alpha, bool soc, double df) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
-  const bool act = lane <= N, hasu = lane < N;
+template <class L>
+__device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha, bool soc, double df) {
+  const Prob& pr = A.pr;
+  const bool act = lane <= L::N, hasu = lane < L::N;
   double ut[6], lb = 0.0, dt = 0.0;
   double prod = 1.0; int cnt = 0;
 #pragma unroll
@@ -494,53 +502,55 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, const Ws& ws, int lane
       if (i == 2 || i == 5) { lb += n_log(prod); prod = 1.0; }
     }
   }
-  Stage st; rollout(pr, ws.par, ut, lane, st);
-  const double l = hasu ? stage_cost(pr, st.X, ws.par[8], ws.par[9]) : 0.0;
+  Stage st; rollout(pr, &PAR(0), ut, lane, st);
+  const double l = hasu ? stage_cost(pr, st.X, PAR(8), PAR(9)) : 0.0;
   double th = 0.0;
   if (act) {
-    for (int r = 0; r < R; ++r) {
-      double nx, ny, iD; const double dc = RW(A_DC, r);
-      const double g = __dmul_rn(dc, row_value(ws, st.X, r, nx, ny, iD));
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
+      const double dc = RW(A_DC, r);
+      const double g = __dmul_rn(dc, gu);
       const double sv = fma(alpha, soc ? SOC(SOC_DS2 + r) : RW(A_DS, r), RW(A_S, r));
       const double ct = g - sv;
       SOC(SOC_CT + r) = ct; th += fabs(ct);
-      const Bnd b = row_bounds(A, lane, r, dc);
+      const Bnd b = row_bounds<L>(A, lane, r, dc);
       if (b.hl) { prod *= sv - b.lo; ++cnt; }
       if (b.hu) { prod *= b.hi - sv; ++cnt; }
       if (b.hl && !b.hu) dt += sv - b.lo;
       if (b.hu && !b.hl) dt += b.hi - sv;
       if (cnt >= 4) { lb += n_log(prod); prod = 1.0; cnt = 0; }
-    }
+    };
+    FOR_ROWS(st.X, body);
     if (cnt) lb += n_log(prod);
   }
   const double fs = df * warp_sum(l);
   th = warp_sum(th); lb = warp_sum(lb); dt = warp_sum(dt);
-  if (lane == 0) { ws.res[R_FT] = fs; ws.res[R_THT] = th; ws.res[R_LBT] = lb; ws.res[R_DTT] = dt; }
+  if (lane == 0) { RES(R_FT) = fs; RES(R_THT) = th; RES(R_LBT) = lb; RES(R_DTT) = dt; }
   __syncwarp();
 }
 
 // SOC right-hand side: c_soc <- a_soc * c_soc + c(trial);  q' = grad l + G^T((Sigma_s + dw) c_soc + mu beta)
-__device__ __noinline__ void ph_socrhs(const SolveArgs& A, const Ws& ws, int lane, double a_soc, double mu, double dw, bool first) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
-  if (lane <= N) {
+template <class L>
+__device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_soc, double mu, double dw, bool first) {
+  if (lane <= L::N) {
     double X[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); q[i] = 0.0; }
 #pragma unroll
     for (int v = 0; v < 6; ++v) q[cost_state(v)] = LV(LV_GL + v);
-    for (int r = 0; r < R; ++r) {
-      double nx, ny, iD; row_value(ws, X, r, nx, ny, iD);
+    const double kd = A.o.kappa_d;
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r), il = RW(A_IL, r), iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       const double cprev = first ? RW(A_G, r) - RW(A_S, r) : SOC(SOC_CSOC + r);
       const double cs = a_soc * cprev + SOC(SOC_CT + r);
       SOC(SOC_CSOC + r) = cs;
       double beta = iu - il;
-      if (hl && !hu) beta += A.o.kappa_d;
-      if (hu && !hl) beta -= A.o.kappa_d;
+      if (hl && !hu) beta += kd;
+      if (hu && !hl) beta -= kd;
       const double yh = (RW(A_VL, r) * il + RW(A_VU, r) * iu + dw) * cs + mu * beta;
-      if (r < 5) q[box_state(r)] += dc * yh; else { q[0] -= dc * yh * nx; q[1] -= dc * yh * ny; }
-    }
+      if (box) q[si] += dc * yh; else { q[0] -= dc * yh * nx; q[1] -= dc * yh * ny; }
+    };
+    FOR_ROWS(X, body);
 #pragma unroll
     for (int i = 0; i < 8; ++i) SOC(SOC_Q2 + i) = q[i];
   }
@@ -548,9 +558,9 @@ __device__ __noinline__ void ph_socrhs(const SolveArgs& A, const Ws& ws, int lan
 }
 
 // accept the trial point: primal step alpha, dual step a_du, kappa_Sigma reset, new reciprocal slacks
-__device__ __noinline__ void ph_accept(const SolveArgs& A, const Ws& ws, int lane, double alpha, double a_du, double mu, double dw, bool soc) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
-  const bool act = lane <= N, hasu = lane < N;
+template <class L>
+__device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alpha, double a_du, double mu, double dw, bool soc) {
+  const bool act = lane <= L::N, hasu = lane < L::N;
   const double ks = A.o.kappa_sigma, kd = A.o.kappa_d, iks = 1.0 / A.o.kappa_sigma;
   if (hasu) {
 #pragma unroll
@@ -566,33 +576,37 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, const Ws& ws, int lan
       LV(LV_U + i) = un; LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu;
     }
   }
-  if (act) for (int r = 0; r < R; ++r) {
-    const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
-    const double ds = soc ? SOC(SOC_DS2 + r) : RW(A_DS, r);
-    const bool hl = il > 0.0, hu = iu > 0.0;
-    double vl = RW(A_VL, r), vu = RW(A_VU, r);
-    double beta = iu - il;
-    if (hl && !hu) beta += kd;
-    if (hu && !hl) beta -= kd;
-    const double dy = (vl * il + vu * iu + dw) * ds + (mu * beta - y);
-    RW(A_Y, r) = y + alpha * dy;
-    if (hl) vl += a_du * ((mu - vl * ds) * il - vl);
-    if (hu) vu += a_du * ((mu + vu * ds) * iu - vu);
-    const double sn = fma(alpha, ds, s);
-    const Bnd b = row_bounds(A, lane, r, dc);
-    double il2 = 0.0, iu2 = 0.0;
-    if (hl) { il2 = rcp(sn - b.lo); vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
-    if (hu) { iu2 = rcp(b.hi - sn); vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
-    RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
+  if (act) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) {
+      const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
+      const double ds = soc ? SOC(SOC_DS2 + r) : RW(A_DS, r);
+      const bool hl = il > 0.0, hu = iu > 0.0;
+      double vl = RW(A_VL, r), vu = RW(A_VU, r);
+      double beta = iu - il;
+      if (hl && !hu) beta += kd;
+      if (hu && !hl) beta -= kd;
+      const double dy = (vl * il + vu * iu + dw) * ds + (mu * beta - y);
+      RW(A_Y, r) = y + alpha * dy;
+      if (hl) vl += a_du * ((mu - vl * ds) * il - vl);
+      if (hu) vu += a_du * ((mu + vu * ds) * iu - vu);
+      const double sn = fma(alpha, ds, s);
+      const Bnd b = row_bounds<L>(A, lane, r, dc);
+      double il2 = 0.0, iu2 = 0.0;
+      if (hl) { il2 = rcp(sn - b.lo); vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
+      if (hu) { iu2 = rcp(b.hi - sn); vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
+      RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
+    }
   }
   __syncwarp();
 }
 
 // outputs: honour the original bounds, unscale multipliers, f and g at the returned point
-__device__ __noinline__ void ph_output(const SolveArgs& A, const Ws& ws, int b, int lane, double df, int status, int iter) {
-  const Prob& pr = A.pr; const int N = pr.N, S = pr.S, R = pr.R;
+template <class L>
+__device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, double df, int status, int iter) {
+  const Prob& pr = A.pr; constexpr int N = L::N, R = L::R, S = L::S;
   const bool act = lane <= N, hasu = lane < N;
-  const int nw = NU * N, ng = R * S;
+  constexpr int nw = NU * N, ng = R * S;
   double u[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = 0.0;
@@ -610,8 +624,8 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, const Ws& ws, int b, 
       for (int i = 0; i < 6; ++i) lo[i] = (LV(LV_ZU + i) - LV(LV_ZL + i)) * idf;
     }
   }
-  Stage st; rollout(pr, ws.par, u, lane, st);
-  const double l = hasu ? stage_cost(pr, st.X, ws.par[8], ws.par[9]) : 0.0;
+  Stage st; rollout(pr, &PAR(0), u, lane, st);
+  const double l = hasu ? stage_cost(pr, st.X, PAR(8), PAR(9)) : 0.0;
   const double fu = warp_sum(l);
   if (lane == 0) {
     if (A.f) A.f[b] = fu;
@@ -621,11 +635,13 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, const Ws& ws, int b, 
   if (act) {
     if (A.g) {
       double* go = A.g + (size_t)b * ng + lane * R;
-      for (int r = 0; r < R; ++r) { double nx, ny, iD; go[r] = row_value(ws, st.X, r, nx, ny, iD); }
+      auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) { go[r] = gu; };
+      FOR_ROWS(st.X, body);
     }
     if (A.lam_g) {
       double* lo = A.lam_g + (size_t)b * ng + lane * R;
       const double idf = 1.0 / df;
+#pragma unroll 1
       for (int r = 0; r < R; ++r) lo[r] = RW(A_Y, r) * RW(A_DC, r) * idf;
     }
   }
@@ -633,44 +649,46 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, const Ws& ws, int b, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-__device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, int b, int lane) {
+template <class L>
+__device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int b, int lane) {
   const Prob& pr = A.pr; const Opt& o = A.o;
-  const int S = pr.S, R = pr.R;
-  double* res = ws.res; double* filt = ws.filt;
+  constexpr int S = L::S, R = L::R;
+  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::SOC0 + (3 * R) * S, Q20 = L::SOC0 + (3 * R + 6) * S;
+  const double T = pr.T;
   unsigned long long n_fact = 0, n_ls = 0, n_soc = 0;
 
-  ph_load(A, ws, b, lane);
+  ph_load<L>(A, b, lane);
   double df = 1.0;
   if (o.scaling) {
-    df = ph_scaling(A, ws, lane);
+    df = ph_scaling<L>(A, lane);
     if (o.scaling == 3) df = 1.0;                                  // debug: constraint scaling only
-    if (o.scaling == 2 && lane <= pr.N) { for (int r = 0; r < R; ++r) ws.rows[(A_DC * R + r) * S + lane] = 1.0; }   // debug: objective only
+    if (o.scaling == 2 && lane <= L::N) { for (int r = 0; r < R; ++r) RW(A_DC, r) = 1.0; }   // debug: objective only
     __syncwarp();
   }
-  const int nzt = ph_start(A, ws, lane);
-  ph_trial(A, ws, lane, 0.0, false, df);          // barrier pieces and constraint violation of the start
-  double f = res[R_FT], LB = res[R_LBT], DT = res[R_DTT];
-  const double th0 = res[R_THT];
+  const int nzt = ph_start<L>(A, lane);
+  ph_trial<L>(A, lane, 0.0, false, df);          // barrier pieces and constraint violation of the start
+  double f = RES(R_FT), LB = RES(R_LBT), DT = RES(R_DTT);
+  const double th0 = RES(R_THT);
   const double theta_max = o.theta_max_fact * fmax(1.0, th0), theta_min = o.theta_min_fact * fmax(1.0, th0);
   double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
   const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
   int nfilt = 0; double dw_last = 0.0;
   int iter = 0, status = NMPC_MAXITER_EXCEEDED, tiny_count = 0; bool tiny_flag = false, ls = true;
-  const int mtot = R * S;
+  constexpr int mtot = R * S;
 
   for (;;) {
-    ph_derivs(A, ws, lane, ls, df);
+    ph_derivs<L>(A, lane, ls, df);
     if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
       ++n_fact;
-      const bool ok = riccati_factor(pr, ws.lq, ws.ric, ws.stg, 1.0, 0.0, lane);
-      if (ok) riccati_forward(pr, ws.lq, ws.ric, false, lane, ws.lv + LV_DX * S, ws.lv + LV_DU * S);
-      ph_lsy(A, ws, lane, ok);
+      const bool ok = riccati_factor<L>(T, ric, 1.0, 0.0, lane);
+      if (ok) riccati_forward<L>(T, ric, false, lane, DX0, DU0);
+      ph_lsy<L>(A, lane, ok);
       ls = false;
       continue;
     }
     // ---- optimality error (scaled) and termination
-    const double du_inf = res[R_DU], pr_inf = res[R_PR], sumy = res[R_SUMY], sumz = res[R_SUMZ], viol = res[R_VIOL];
-    const double pmax = res[R_PMAX], pmin = res[R_PMIN];
+    const double du_inf = RES(R_DU), pr_inf = RES(R_PR), sumy = RES(R_SUMY), sumz = RES(R_SUMZ), viol = RES(R_VIOL);
+    const double pmax = RES(R_PMAX), pmin = RES(R_PMIN);
     const double sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nzt)) / o.s_max;
     const double sc = fmax(o.s_max, sumz / (double)max(1, nzt)) / o.s_max;
     const double E0 = fmax(du_inf / sd, fmax(pr_inf, pmax / sc));
@@ -695,7 +713,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, in
     double dw = 0.0; bool ok = false;
     for (;;) {
       ++n_fact;
-      ok = riccati_factor(pr, ws.lq, ws.ric, ws.stg, mu, dw, lane);
+      ok = riccati_factor<L>(T, ric, mu, dw, lane);
       if (ok) break;
       if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, dw_last * o.dw_dec);
       else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
@@ -703,11 +721,11 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, in
     }
     if (!ok) { status = NMPC_PERTURBATION_FAILED; break; }
     if (dw > 0.0) dw_last = dw;
-    riccati_forward(pr, ws.lq, ws.ric, false, lane, ws.lv + LV_DX * S, ws.lv + LV_DU * S);
-    ph_dir(A, ws, lane, mu, tau, false);
-    const double a_pr_max = res[R_APR]; double a_du = res[R_ADU];
-    const double gbd = res[R_GBD], theta = res[R_THETA];
-    const bool tiny = res[R_TINY] != 0.0 && theta <= 1e-4;
+    riccati_forward<L>(T, ric, false, lane, DX0, DU0);
+    ph_dir<L>(A, lane, mu, tau, false);
+    const double a_pr_max = RES(R_APR); double a_du = RES(R_ADU);
+    const double gbd = RES(R_GBD), theta = RES(R_THETA);
+    const bool tiny = RES(R_TINY) != 0.0 && theta <= 1e-4;
     const double phi = f - mu * LB + o.kappa_d * mu * DT;
     // ---- filter line search
     const double pw_gbd = gbd < 0.0 ? n_pow(-gbd, o.s_phi) : 0.0, pw_th = n_pow(theta, o.s_theta);
@@ -720,7 +738,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, in
       if (a_test > 0.0 && is_ftype(a_test) && theta <= theta_min) acc = armijo(a_test, ph_);
       else acc = cmp_le(th_, (1.0 - o.gamma_theta) * theta, theta) || cmp_le(ph_ - phi, -o.gamma_phi * theta, phi);
       if (!acc) return false;
-      for (int e = 0; e < nfilt; ++e) if (!(th_ < filt[2 * e] || ph_ < filt[2 * e + 1])) return false;
+      for (int e = 0; e < nfilt; ++e) if (!(th_ < smem[L::FILT0 + 2 * e] || ph_ < smem[L::FILT0 + 2 * e + 1])) return false;
       return true;
     };
     double amin = o.gamma_theta;
@@ -736,10 +754,10 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, in
     for (;;) {
       const bool soc_trial = soc_left > 0;
       const double a_try = soc_trial ? a_soc : alpha;
-      ph_trial(A, ws, lane, a_try, soc_trial, df);
+      ph_trial<L>(A, lane, a_try, soc_trial, df);
       ++n_ls;
-      const double th_t = res[R_THT];
-      phi_t = res[R_FT] - mu * res[R_LBT] + o.kappa_d * mu * res[R_DTT];
+      const double th_t = RES(R_THT);
+      phi_t = RES(R_FT) - mu * RES(R_LBT) + o.kappa_d * mu * RES(R_DTT);
       if (tiny) { accepted = true; break; }
       if (!soc_trial) alpha_test = alpha;
       if (acceptable(alpha, th_t, phi_t)) {
@@ -758,11 +776,11 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, in
       if (next_soc) {
         const bool first_soc = !soc_trial;
         th_prev = th_t;
-        ph_socrhs(A, ws, lane, first_soc ? alpha : a_soc, mu, dw, first_soc);
-        riccati_resolve(pr, ws.lq, ws.soc + SOC_Q2 * S, ws.ric, mu, lane);
-        riccati_forward(pr, ws.lq, ws.ric, true, lane, ws.lv + LV_DX * S, ws.soc + SOC_DUS * S);
-        ph_dir(A, ws, lane, mu, tau, true);
-        a_soc = res[R_APR];
+        ph_socrhs<L>(A, lane, first_soc ? alpha : a_soc, mu, dw, first_soc);
+        riccati_resolve<L>(T, Q20, ric, mu, lane);
+        riccati_forward<L>(T, ric, true, lane, DX0, DUS0);
+        ph_dir<L>(A, lane, mu, tau, true);
+        a_soc = RES(R_APR);
         continue;
       }
       first = false;
@@ -774,29 +792,48 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, const Ws& ws, in
     // ---- filter augmentation
     if (!tiny && !(is_ftype(alpha_test) && armijo(alpha_test, phi_t))) {
       if (lane == 0) {
-        if (nfilt == FILT_CAP) for (int e = 0; e < 2 * (FILT_CAP - 1); ++e) filt[e] = filt[e + 2];   // drop the oldest entry
+        if (nfilt == FILT_CAP) for (int e = 0; e < 2 * (FILT_CAP - 1); ++e) smem[L::FILT0 + e] = smem[L::FILT0 + e + 2];   // drop the oldest
         const int at = nfilt == FILT_CAP ? FILT_CAP - 1 : nfilt;
-        filt[2 * at] = (1.0 - o.gamma_theta) * theta; filt[2 * at + 1] = phi - o.gamma_phi * theta;
+        smem[L::FILT0 + 2 * at] = (1.0 - o.gamma_theta) * theta; smem[L::FILT0 + 2 * at + 1] = phi - o.gamma_phi * theta;
       }
       if (nfilt < FILT_CAP) ++nfilt;
       __syncwarp();
     }
-    if (used_soc) a_du = res[R_ADU];
+    if (used_soc) a_du = RES(R_ADU);
     if (A.dbg && lane == 0 && iter < A.dbg_rows) {
-      double* L = A.dbg + ((size_t)b * A.dbg_rows + iter) * 8;
-      L[0] = mu; L[1] = f / df; L[2] = pr_inf; L[3] = du_inf; L[4] = dw; L[5] = alpha; L[6] = a_du; L[7] = (double)(n_ls - ls_before);
+      double* Lg = A.dbg + ((size_t)b * A.dbg_rows + iter) * 8;
+      Lg[0] = mu; Lg[1] = f / df; Lg[2] = pr_inf; Lg[3] = du_inf; Lg[4] = dw; Lg[5] = alpha; Lg[6] = a_du; Lg[7] = (double)(n_ls - ls_before);
     }
-    ph_accept(A, ws, lane, alpha, a_du, mu, dw, used_soc);
-    f = res[R_FT]; LB = res[R_LBT]; DT = res[R_DTT];
+    ph_accept<L>(A, lane, alpha, a_du, mu, dw, used_soc);
+    f = RES(R_FT); LB = RES(R_LBT); DT = RES(R_DTT);
     ++iter;
   }
-  ph_output(A, ws, b, lane, df, status, iter);
+  ph_output<L>(A, b, lane, df, status, iter);
   if (lane == 0 && A.stats) { atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); }
+}
+
+// persistent kernel: one warp per block, instances from an atomic work queue (optionally in a caller-given order)
+template <int N_, int NOBS_>
+__global__ void __launch_bounds__(32) nmpc_ipm_kernel(const SolveArgs A) {
+  using L = Lay<N_, NOBS_>;
+  const int lane = threadIdx.x;
+  double* ric = A.ric + (size_t)blockIdx.x * A.ric_stride;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(A.counter, 1);
+    q = __shfl_sync(FULL, q, 0);
+    if (q >= A.B) break;
+    const int b = A.order ? A.order[q] : q;
+    solve_instance<L>(A, ric, b, lane);
+    __syncwarp();
+  }
 }
 
 #undef LV
 #undef RW
 #undef LQ
 #undef SOC
+#undef RES
+#undef PAR
 
 }  // namespace nmpc
