@@ -181,7 +181,8 @@ def run_b200(args, rank, world, local_rank):
         cl._schedule_vw()
         tb = cl.p[:, 8:10].clone()
         ev[k][0].record()
-        sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False)
+        sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False,
+                     order=None if args.no_lpt else cl.next_order())
         ev[k][1].record()
         solver.step(sol["x"], cl.p, cl.u_warm, cl.vw, cl.fov)
         cl.err_sum += torch.linalg.vector_norm(cl.fov - tb, dim=1)
@@ -271,7 +272,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}, n_w={sc.n_w}, n_g={sc.n_g}) closed loop: "
                                f"{B} randomised UAV states / target speeds per GPU (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
-                   "l2": "flushed between timed steps (256 MB write)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
+                   "l2": "flushed between timed steps (256 MB write)", "scheduling": "natural order" if args.no_lpt else "longest-first by previous-step iteration count (argsort inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
         "p50_step_ms": float(np.median(step_ms)), "p50_solve_kernel_ms": float(np.median(solve_ms)),
         "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
         "cold_first_step": cold, "wall_s": wall,
@@ -311,6 +312,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lpt", action="store_true", help="disable longest-first scheduling by previous iteration counts")
     ap.add_argument("--count-work", action="store_true", help="read device work counters every timed step (adds a sync)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -56,12 +56,21 @@ class ClosedLoop:
             vw = np.array([self.sc.schedule(self.mpc_iter + int(ph)) for ph in self.phase], dtype=np.float64)
             self.vw.copy_(torch.from_numpy(vw))
 
+    def next_order(self):
+        """Longest-first fetch order for the persistent kernel: instances that needed many iterations last step are
+        started first, so the batch step does not end with a few 100-iteration stragglers running alone."""
+        st = self.solver.stats()
+        it = st.get("iter_count") if st else None
+        if it is None or not torch.is_tensor(it) or it.numel() != self.B:
+            return None
+        return torch.argsort(it, descending=True)
+
     def step(self, want_g: bool = False, want_lam: bool = False):
         """One closed-loop batch step; returns the solver output dict (device tensors)."""
         self._schedule_vw()
         target_before = self.p[:, 8:10].clone()
         sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg,
-                          want_g=want_g, want_lam=want_lam)
+                          want_g=want_g, want_lam=want_lam, order=self.next_order())
         self.solver.step(sol["x"], self.p, self.u_warm, self.vw, self.fov)
         # error[i] = || FOVcentre_{i+1} - target_i ||   (NMPC_TT.py:435)
         self.err_sum += torch.linalg.vector_norm(self.fov - target_before, dim=1)

@@ -44,7 +44,7 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
   constexpr int LQ0 = L::LQ0;
   // ---- ownership map: entry e = lane + 32 m of the packed lower triangle of the 15 x 15 matrix, and the
   //      LQ entries that are added to it:  ent += lq[o0] + mu * lq[o1] + dw * (lq[o2] + c3)
-  int ia[4], ib[4], o0[4], o1[4], o2[4]; double c3[4];
+  int ia[4], ib[4], o0[4], o1[4], o2[4], ymain[4], zsp[4], ybase[4]; double c3[4], cmain[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const int e = lane + 32 * m;
@@ -71,16 +71,18 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
       }
     }
     o0[m] = LQ0 + p0 * S; o1[m] = LQ0 + p1 * S; o2[m] = LQ0 + p2 * S; c3[m] = cc;
+    // H[a][b] = z_a^T Y_b (rhs row a = 14: z_b^T p+).  Column z_c of Z = [B | A] is T e_{c+2} (c = 1..5) or
+    // e_{c-6} (c >= 6), plus stage-dependent entries in rows 0..2 for the "special" columns c = 0 (v), 9 (theta), 10 (psi).
+    const int zc = a == 14 ? b : a, yr = a == 14 ? 14 : b;
+    const int smain = zc >= 6 ? zc - 6 : zc + 2;
+    ymain[m] = YS + yr * 9 + (zc >= 1 ? smain : 0);
+    cmain[m] = !valid || zc == 0 ? 0.0 : (zc < 6 ? T : 1.0);
+    zsp[m] = valid && (zc == 0 || zc == 9 || zc == 10) ? ZS + zc : -1;
+    ybase[m] = YS + yr * 9;
   }
-  // ---- static part of Z = [B | A]:  B = T [d e_v ; I_5 on the angle rows],  A = I + E
+  // ---- Z entries that are not units: rows 0..2 of columns 0, 9, 10 ([3][16], the rest stays zero)
 #pragma unroll 1
-  for (int o = lane; o < 128; o += 32) {
-    const int s = o >> 4, j = o & 15;
-    double v = 0.0;
-    if (j >= 1 && j < 6 && s == j + 2) v = T;
-    if (j >= 6 && j < 14 && s == j - 6) v = 1.0;
-    smem[ZS + o] = v;
-  }
+  for (int o = lane; o < 48; o += 32) smem[ZS + o] = 0.0;
   // ---- terminal stage: P_N = Q_N, p_N = q_N
 #pragma unroll 1
   for (int o = lane; o < 72; o += 32) {
@@ -94,18 +96,19 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
     // stage-dependent entries of Z
     if (lane < 8) {
       const int t = lane;
-      const int dst = t < 3 ? t * 16 : (t < 6 ? (t - 3) * 16 + 9 : (t - 6) * 16 + 10);
+      const int dst = t < 3 ? t * 16 : (t < 6 ? (t - 3) * 16 + 9 : (t - 6) * 16 + 10);   // [row 0..2][16 columns]
       smem[ZS + dst] = t < 3 ? T * smem[LQ0 + (LQ_DD + t) * S + k] : smem[LQ0 + (LQ_EE + (t - 3)) * S + k];
     }
     __syncwarp();
-    // Y_j = P+ z_j  (j < 14),  Y_14 = p+
+    // Y_j = P+ z_j  (j < 14),  Y_14 = p+ : one unit/T column of P+ plus, for the special columns, three more terms
 #pragma unroll 1
     for (int m = 0; m < 4; ++m) {
       const int o = lane + 32 * m, j = o >> 3, i = o & 7;
       if (j < 14) {
         double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) acc += smem[ZS + s * 16 + j] * smem[PP + i * 9 + s];
+        if (j >= 1) acc = (j < 6 ? T : 1.0) * smem[PP + i * 9 + (j < 6 ? j + 2 : j - 6)];
+        if (j == 0 || j == 9 || j == 10)
+          acc += smem[ZS + j] * smem[PP + i * 9] + smem[ZS + 16 + j] * smem[PP + i * 9 + 1] + smem[ZS + 32 + j] * smem[PP + i * 9 + 2];
         smem[YS + j * 9 + i] = acc;
       } else if (j == 14) smem[YS + 14 * 9 + i] = smem[PP + 8 * 9 + i];
     }
@@ -114,13 +117,10 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
     double ent[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      double acc = 0.0;
-      if (ia[m] >= 0) {
-        const int zc = ia[m] == 14 ? ib[m] : ia[m], yr = ia[m] == 14 ? 14 : ib[m];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) acc += smem[ZS + s * 16 + zc] * smem[YS + yr * 9 + s];
-        acc += smem[o0[m] + k] + mu * smem[o1[m] + k] + dw * (smem[o2[m] + k] + c3[m]);
-      }
+      double acc = cmain[m] * smem[ymain[m]];
+      if (zsp[m] >= 0)
+        acc += smem[zsp[m]] * smem[ybase[m]] + smem[zsp[m] + 16] * smem[ybase[m] + 1] + smem[zsp[m] + 32] * smem[ybase[m] + 2];
+      if (ia[m] >= 0) acc += smem[o0[m] + k] + mu * smem[o1[m] + k] + dw * (smem[o2[m] + k] + c3[m]);
       ent[m] = acc;
     }
     // partial Cholesky: eliminate the six control pivots
@@ -131,10 +131,10 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
       __syncwarp();
       const double d = smem[COL + j];
       if (!(d > 0.0)) return false;                 // uniform: every lane reads the same pivot
-      const double id = rsqrt(d);
+      const double id = rsqrt(d), inv_d = id * id;
 #pragma unroll
       for (int m = 0; m < 4; ++m)
-        if (ib[m] > j && ib[m] < 99) ent[m] -= (smem[COL + ia[m]] * id) * (smem[COL + ib[m]] * id);
+        if (ib[m] > j && ib[m] < 99) ent[m] = fma(-(smem[COL + ia[m]] * inv_d), smem[COL + ib[m]], ent[m]);
       if (lane >= j && lane < 15) smem[FAC + j * 16 + lane] = smem[COL + lane] * id;
       if (lane == 15) smem[FAC + j * 16 + 15] = id;
       __syncwarp();

@@ -121,13 +121,13 @@ class Solver:
 
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, obstacles=None,
-                 want_g: bool = True, want_lam: bool = True):
+                 want_g: bool = True, want_lam: bool = True, order=None):
         if p is None:
             raise ValueError("solver: p is required")
         if any(v is None for v in (lbx, ubx, lbg, ubg)):
             raise ValueError("solver: lbx, ubx, lbg, ubg are required (the reference passes all four)")
         if _is_cuda_tensor(p):
-            return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+            return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order)
         return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
 
     def _obst(self, obstacles, B):
@@ -169,7 +169,7 @@ class Solver:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
         return out
 
-    def _call_device(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam):
+    def _call_device(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order=None):
         L = _ffi.lib()
         dev = p.device
         single = p.dim() == 1
@@ -199,10 +199,15 @@ class Solver:
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         ptr = lambda t: None if t is None else t.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if order is not None:      # scheduling hint only: longest-first fetch order of the persistent kernel
+            order = order.to(torch.int32).contiguous()
+            if order.numel() != B:
+                raise ValueError("solver: order must be a permutation of range(B)")
+            _ffi.check(L.nmpc_set_order(self._h, order.data_ptr()), "nmpc_set_order")
         _ffi.check(L.nmpc_solve(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
                                 ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters), stream),
                    "nmpc_solve")
-        self._keep = (p, x0, obs)   # keep inputs alive until the stream has consumed them
+        self._keep = (p, x0, obs, order)   # keep inputs alive until the stream has consumed them
         self._stats = dict(return_status=status, iter_count=iters, success=status == 0)
         out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
         if single:
