@@ -24,11 +24,11 @@ using namespace nmpc;
 // The IPM kernel (nmpc_solve.cuh) is a template on (N, n_obs); its instantiations live in nmpc_inst.cu objects.
 namespace nmpc {
 #define NMPC_DECL_INST(N, O)                      \
-  int ipm_prepare_##N##_##O(int*, size_t*);        \
+  int ipm_prepare_##N##_##O(int*, size_t*, int*);        \
   int ipm_launch_##N##_##O(const SolveArgs&, int, size_t, cudaStream_t);
 NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3)
 }  // namespace nmpc
-struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
+struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
 #define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_launch_##N##_##O}
 static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3)};
 
@@ -222,7 +222,7 @@ static int fail(const std::string& m) { g_err = m; return 1; }
 struct nmpc_handle {
   nmpc_spec spec; int device; int sm_count;
   Prob pr; Opt opt;
-  const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks;
+  const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
   double* d_ric; int ric_stride;
   int32_t* d_order; const int32_t* order_next;
   int* d_counter; unsigned long long* d_stats;
@@ -271,13 +271,13 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     return fail("nmpc_create: no kernel instantiation for this (N, n_obs); built:" + have + " -- add the pair to csrc/Makefile INSTS and the table in nmpc_b200.cu");
   }
   {
-    const int rc = h->inst->prepare(&h->blocks_per_sm, &h->smem_bytes);
+    const int rc = h->inst->prepare(&h->blocks_per_sm, &h->smem_bytes, &h->warps_per_block);
     if (rc != 0) { delete h; return fail(std::string("nmpc_create: kernel setup failed: ") + cudaGetErrorString((cudaError_t)rc)); }
   }
   if (h->blocks_per_sm < 1) { delete h; return fail("nmpc_create: kernel does not fit on an SM"); }
   h->max_blocks = h->sm_count * h->blocks_per_sm;
   h->ric_stride = RIC_N * h->pr.N;
-  CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks));   // L2-resident Riccati scratch
+  CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));

@@ -135,8 +135,11 @@ struct Prob {
   int N, n_obs, R, S;         // R = 5 + n_obs rows per stage, S = N + 1 stages
 };
 
-// ---- compile-time shared-memory layout of one warp's workspace (one warp per block => offsets from smem[0]).
+// ---- compile-time shared-memory layout of one warp's workspace (offsets from the warp's slice base).
 //      With N and n_obs as template parameters every workspace access is an LDS/STS with an immediate offset.
+#ifndef NMPC_WPB_MAX
+#define NMPC_WPB_MAX 8     // 8 warps x 255 registers is the whole register file of an SM
+#endif
 __host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
 template <int N_, int NOBS_>
 struct Lay {
@@ -151,7 +154,10 @@ struct Lay {
   static constexpr int FILT0 = even_up(OBS0 + 3 * NOBS_ + 1);
   static constexpr int RES0 = FILT0 + 2 * FILT_CAP;
   static constexpr int PAR0 = RES0 + 24;
-  static constexpr int TOTAL = PAR0 + 12;
+  static constexpr int TOTAL = even_up(PAR0 + 12);
+  // warps (= concurrent instances) per block: as many slices as fit in the 227 KB a block may use, at most NMPC_WPB_MAX
+  static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);
+  static constexpr int WPB = WPB_FIT < 1 ? 1 : (WPB_FIT > NMPC_WPB_MAX ? NMPC_WPB_MAX : WPB_FIT);
 };
 
 // ---- stage state of one lane -----------------------------------------------------------------------

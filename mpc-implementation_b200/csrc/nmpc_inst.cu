@@ -12,18 +12,20 @@
 
 namespace nmpc {
 
-int NMPC_CAT(ipm_prepare, INST_N, INST_NOBS)(int* blocks_per_sm, size_t* smem_bytes) {
+int NMPC_CAT(ipm_prepare, INST_N, INST_NOBS)(int* blocks_per_sm, size_t* smem_bytes, int* warps_per_block) {
   using L = Lay<INST_N, INST_NOBS>;
-  const size_t smem = (size_t)L::TOTAL * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(nmpc_ipm_kernel<INST_N, INST_NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t bytes = (size_t)L::TOTAL * sizeof(double) * L::WPB;
+  *warps_per_block = L::WPB;
+  cudaError_t e = cudaFuncSetAttribute(nmpc_ipm_kernel<INST_N, INST_NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nmpc_ipm_kernel<INST_N, INST_NOBS>, 32, smem);
-  *smem_bytes = smem;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nmpc_ipm_kernel<INST_N, INST_NOBS>, 32 * L::WPB, bytes);
+  *smem_bytes = bytes;
   return (int)e;
 }
 
-int NMPC_CAT(ipm_launch, INST_N, INST_NOBS)(const SolveArgs& A, int blocks, size_t smem, cudaStream_t s) {
-  nmpc_ipm_kernel<INST_N, INST_NOBS><<<blocks, 32, smem, s>>>(A);
+int NMPC_CAT(ipm_launch, INST_N, INST_NOBS)(const SolveArgs& A, int blocks, size_t bytes, cudaStream_t s) {
+  using L = Lay<INST_N, INST_NOBS>;
+  nmpc_ipm_kernel<INST_N, INST_NOBS><<<blocks, 32 * L::WPB, bytes, s>>>(A);
   return (int)cudaGetLastError();
 }
 

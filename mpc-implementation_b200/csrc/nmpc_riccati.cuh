@@ -17,7 +17,10 @@
 
 namespace nmpc {
 
-extern __shared__ double smem[];
+// The block holds Lay::WPB warps, each solving its own instance in its own Lay::TOTAL slice of dynamic shared
+// memory; `smem` is the executing warp's slice (every function that uses it has the layout type L in scope).
+extern __shared__ double smem_all[];
+#define smem (smem_all + (threadIdx.x >> 5) * L::TOTAL)
 
 // staging area layout (doubles, relative to Lay::STG0); row strides of 9 keep column accesses conflict-free
 constexpr int SG_PP = 0;      // [9][9]  rows 0..7 = P+ (symmetric), row 8 = p+

@@ -677,6 +677,10 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
   constexpr int mtot = R * S;
 
   for (;;) {
+    // Alignment point: the warps of a block start every IPM iteration together, so that they walk through the
+    // same ~200 KB of phase code at the same time and share instruction-cache lines (unaligned warps thrash it:
+    // `no_instruction` was 56 % of all stall cycles in v3).  Pure scheduling; results cannot depend on it.
+    __syncthreads_or(1);
     ph_derivs<L>(A, lane, ls, df);
     if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
       ++n_fact;
@@ -812,12 +816,13 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
   if (lane == 0 && A.stats) { atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); }
 }
 
-// persistent kernel: one warp per block, instances from an atomic work queue (optionally in a caller-given order)
+// persistent kernel: Lay::WPB warps per block (one block per SM), one instance per warp at a time, instances from
+// an atomic work queue (optionally in a caller-given order)
 template <int N_, int NOBS_>
-__global__ void __launch_bounds__(32) nmpc_ipm_kernel(const SolveArgs A) {
+__global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(const SolveArgs A) {
   using L = Lay<N_, NOBS_>;
-  const int lane = threadIdx.x;
-  double* ric = A.ric + (size_t)blockIdx.x * A.ric_stride;
+  const int lane = threadIdx.x & 31;
+  double* ric = A.ric + (size_t)(blockIdx.x * L::WPB + (threadIdx.x >> 5)) * A.ric_stride;
   for (;;) {
     int q = 0;
     if (lane == 0) q = atomicAdd(A.counter, 1);
@@ -827,6 +832,7 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const SolveArgs A) {
     solve_instance<L>(A, ric, b, lane);
     __syncwarp();
   }
+  while (__syncthreads_or(0)) {}   // out of work: keep matching the alignment barrier until every warp is done
 }
 
 #undef LV
@@ -835,5 +841,6 @@ __global__ void __launch_bounds__(32) nmpc_ipm_kernel(const SolveArgs A) {
 #undef SOC
 #undef RES
 #undef PAR
+#undef smem
 
 }  // namespace nmpc
