@@ -24,10 +24,10 @@ extern __shared__ double smem_all[];
 
 // staging area layout (doubles, relative to Lay::STG0); row strides of 9 keep column accesses conflict-free
 constexpr int SG_PP = 0;      // [9][9]  rows 0..7 = P+ (symmetric), row 8 = p+
-constexpr int SG_Z = 82;      // [8][16] Z[s][j], j < 14
-constexpr int SG_Y = 210;     // [15][9] Y_j = P+ z_j (j < 14), Y_14 = p+
-constexpr int SG_COL = 346;   // [16]    published pivot column
-constexpr int SG_FAC = 362;   // [6][16] factor columns l[a], a = 0..14, and 1/l[j][j] at [15]
+constexpr int SG_Z = 82;      // [3][16] the non-trivial rows 0..2 of Z = [B | A] (columns 0, 9, 10); the rest is 0 / T / identity
+constexpr int SG_Y = 130;     // [15][9] Y_j = P+ z_j (j < 14), Y_14 = p+
+constexpr int SG_COL = 266;   // [16]    published pivot column
+constexpr int SG_FAC = 282;   // [6][16] factor columns l[a], a = 0..14, and 1/l[j][j] at [15]
 static_assert(SG_FAC + 96 <= STG_N, "staging area too small");
 
 // state-Hessian entry Q_k[i][j] (+ delta_w part), used for the terminal stage only
