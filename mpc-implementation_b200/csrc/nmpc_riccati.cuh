@@ -22,13 +22,14 @@ namespace nmpc {
 extern __shared__ double smem_all[];
 #define smem (smem_all + (threadIdx.x >> 5) * L::TOTAL)
 
-// staging area layout (doubles, relative to Lay::STG0); row strides of 9 keep column accesses conflict-free
+// staging area layout (doubles, relative to Lay::STG0); every base is even (16-byte aligned)
 constexpr int SG_PP = 0;      // [9][9]  rows 0..7 = P+ (symmetric), row 8 = p+
 constexpr int SG_Z = 82;      // [3][16] the non-trivial rows 0..2 of Z = [B | A] (columns 0, 9, 10); the rest is 0 / T / identity
-constexpr int SG_Y = 130;     // [15][9] Y_j = P+ z_j (j < 14), Y_14 = p+
-constexpr int SG_COL = 266;   // [16]    published pivot column
-constexpr int SG_FAC = 282;   // [6][16] factor columns l[a], a = 0..14, and 1/l[j][j] at [15]
-static_assert(SG_FAC + 96 <= STG_N, "staging area too small");
+constexpr int SG_Y = 130;     // [3][8]  Y_c = P+ z_c of the three special columns c = 0, 9, 10
+constexpr int SG_H = 154;     // [120]   packed lower triangle of the 15 x 15 stage matrix [H | h]
+constexpr int SG_W = 274;     // [9][6]  W = [Psi | psi]^T L^-T  (rows: 8 states + rhs)
+constexpr int SG_L = 328;     // [28]    L (21, packed lower) and the six 1/L[j][j]
+static_assert(SG_L + 28 <= STG_N, "staging area too small");
 
 // state-Hessian entry Q_k[i][j] (+ delta_w part), used for the terminal stage only
 template <class L>
@@ -43,11 +44,16 @@ __device__ __forceinline__ double q_entry(int k, int i, int j, double dw) {
 template <class L>
 __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, double mu, double dw, int lane) {
   constexpr int S = L::S, N = L::N;
-  constexpr int PP = L::STG0 + SG_PP, ZS = L::STG0 + SG_Z, YS = L::STG0 + SG_Y, COL = L::STG0 + SG_COL, FAC = L::STG0 + SG_FAC;
+  constexpr int PP = L::STG0 + SG_PP, ZS = L::STG0 + SG_Z, YS = L::STG0 + SG_Y, HS = L::STG0 + SG_H, WS = L::STG0 + SG_W, LS = L::STG0 + SG_L;
   constexpr int LQ0 = L::LQ0;
-  // ---- ownership map: entry e = lane + 32 m of the packed lower triangle of the 15 x 15 matrix, and the
-  //      LQ entries that are added to it:  ent += lq[o0] + mu * lq[o1] + dw * (lq[o2] + c3)
-  int ia[4], ib[4], o0[4], o1[4], o2[4], ymain[4], zsp[4], ybase[4]; double c3[4], cmain[4];
+  // Column c of Z = [B | A] is T e_{c+2} (c = 1..5) or e_{c-6} (c >= 6), plus stage-dependent entries in rows 0..2
+  // for the "special" columns c = 0 (v: no unit part), 9 (theta), 10 (psi).
+  auto spec = [](int c) { return c == 0 || c == 9 || c == 10; };
+  auto sid = [](int c) { return c >= 6 ? c - 6 : c + 2; };                 // row of the unit entry (c >= 1)
+  auto spj = [](int c) { return c == 0 ? 0 : c - 8; };                     // special column -> 0, 1, 2
+  // ---- ownership map for BUILDING the stage matrix: entry e = lane + 32 m of the packed lower triangle,
+  //      ent = cmain * smem[ymain] + lq[o0] + mu * lq[o1] + dw * (lq[o2] + c3)
+  int o0[4], o1[4], o2[4], ymain[4]; double c3[4], cmain[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const int e = lane + 32 * m;
@@ -56,8 +62,8 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
     while ((a + 1) * (a + 2) / 2 <= e) ++a;
     const int b = e - a * (a + 1) / 2;
     const bool valid = e < 119;                       // e == 119 is (14,14): not needed
-    ia[m] = valid ? a : -1; ib[m] = valid ? b : 99;
     int p0 = LQ_ZERO, p1 = LQ_ZERO, p2 = LQ_ZERO; double cc = 0.0;
+    int ym = PP; double cm = 0.0;
     if (valid) {
       if (a < 6) { if (a == b) { p0 = LQ_RD + a; cc = 1.0; } }
       else if (a < 14) {
@@ -72,18 +78,44 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
         if (b < 6) p1 = LQ_RB + b;
         else { p0 = LQ_QA + (b - 6); p1 = LQ_QB + (b - 6); p2 = LQ_QD + (b - 6); }
       }
+      // H[a][b] = z_a^T P+ z_b,  h[b] = z_b^T p+ : the part that is ONE scaled entry of P+ / p+ / Y_special
+      const double ca = (a >= 1 && a < 6) ? T : 1.0, cb = (b >= 1 && b < 6) ? T : 1.0;
+      if (a == 14) {
+        if (b != 0) { ym = PP + 72 + sid(b); cm = cb; }                      // b == 0: correction only
+      } else if (!spec(a) && !spec(b)) { ym = PP + sid(a) * 9 + sid(b); cm = ca * cb; }
+      else if (spec(b) && !spec(a)) { ym = YS + spj(b) * 8 + sid(a); cm = ca; }
+      else if (spec(a) && !spec(b)) { ym = YS + spj(a) * 8 + sid(b); cm = cb; }
+      else if (a != 0) { ym = YS + spj(b) * 8 + sid(a); cm = 1.0; }          // both special: unit part of z_a (none for a == 0)
     }
     o0[m] = LQ0 + p0 * S; o1[m] = LQ0 + p1 * S; o2[m] = LQ0 + p2 * S; c3[m] = cc;
-    // H[a][b] = z_a^T Y_b (rhs row a = 14: z_b^T p+).  Column z_c of Z = [B | A] is T e_{c+2} (c = 1..5) or
-    // e_{c-6} (c >= 6), plus stage-dependent entries in rows 0..2 for the "special" columns c = 0 (v), 9 (theta), 10 (psi).
-    const int zc = a == 14 ? b : a, yr = a == 14 ? 14 : b;
-    const int smain = zc >= 6 ? zc - 6 : zc + 2;
-    ymain[m] = YS + yr * 9 + (zc >= 1 ? smain : 0);
-    cmain[m] = !valid || zc == 0 ? 0.0 : (zc < 6 ? T : 1.0);
-    zsp[m] = valid && (zc == 0 || zc == 9 || zc == 10) ? ZS + zc : -1;
-    ybase[m] = YS + yr * 9;
+    ymain[m] = ym; cmain[m] = cm;
   }
-  // ---- Z entries that are not units: rows 0..2 of columns 0, 9, 10 ([3][16], the rest stays zero)
+  // ---- the nine entries whose z_a AND z_b (or p+) are special get  sum_s Z[s][za] * Yv[s]  on top (lanes 0..8)
+  int cz = ZS, cy = PP, ch = HS;
+  {
+    const int ca_[9] = {0, 9, 10, 9, 10, 10, 14, 14, 14}, cb_[9] = {0, 0, 0, 9, 9, 10, 0, 9, 10};
+    int a = 0, b = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) if (lane == t) { a = ca_[t]; b = cb_[t]; }
+    cz = ZS + (a == 14 ? b : a);
+    cy = a == 14 ? PP + 72 : YS + spj(b) * 8;
+    ch = HS + a * (a + 1) / 2 + b;
+  }
+  // ---- ownership map for the TRAILING update: t = lane + 32 r over the packed lower triangle of the 9 x 9 block
+  int th[2], twa[2], twb[2], tp0[2], tp1[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = lane + 32 * r;
+    int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (a * (a + 1) / 2 > t) --a;
+    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+    const int b = t - a * (a + 1) / 2;
+    const bool valid = t < 44;                        // t == 44 is (rhs, rhs)
+    th[r] = valid ? HS + (a + 6) * (a + 7) / 2 + (b + 6) : -1;
+    twa[r] = WS + (valid ? a : 0) * 6; twb[r] = WS + (valid ? b : 0) * 6;
+    tp0[r] = a == 8 ? PP + 72 + b : PP + a * 9 + b;
+    tp1[r] = a == 8 ? PP + 72 + b : PP + b * 9 + a;
+  }
 #pragma unroll 1
   for (int o = lane; o < 48; o += 32) smem[ZS + o] = 0.0;
   // ---- terminal stage: P_N = Q_N, p_N = q_N
@@ -103,73 +135,69 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
       smem[ZS + dst] = t < 3 ? T * smem[LQ0 + (LQ_DD + t) * S + k] : smem[LQ0 + (LQ_EE + (t - 3)) * S + k];
     }
     __syncwarp();
-    // Y_j = P+ z_j  (j < 14),  Y_14 = p+ : one unit/T column of P+ plus, for the special columns, three more terms
-#pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
-      const int o = lane + 32 * m, j = o >> 3, i = o & 7;
-      if (j < 14) {
-        double acc = 0.0;
-        if (j >= 1) acc = (j < 6 ? T : 1.0) * smem[PP + i * 9 + (j < 6 ? j + 2 : j - 6)];
-        if (j == 0 || j == 9 || j == 10)
-          acc += smem[ZS + j] * smem[PP + i * 9] + smem[ZS + 16 + j] * smem[PP + i * 9 + 1] + smem[ZS + 32 + j] * smem[PP + i * 9 + 2];
-        smem[YS + j * 9 + i] = acc;
-      } else if (j == 14) smem[YS + 14 * 9 + i] = smem[PP + 8 * 9 + i];
+    // Y_c = P+ z_c for the special columns c = 0, 9, 10 (lanes 0..23)
+    if (lane < 24) {
+      const int j = lane >> 3, i = lane & 7, c = j == 0 ? 0 : 8 + j;
+      double acc = smem[ZS + c] * smem[PP + i * 9] + smem[ZS + 16 + c] * smem[PP + i * 9 + 1] + smem[ZS + 32 + c] * smem[PP + i * 9 + 2];
+      if (j > 0) acc += smem[PP + i * 9 + 2 + j];
+      smem[YS + lane] = acc;
     }
     __syncwarp();
-    // owned entries of [H | h]
-    double ent[4];
+    // [H | h] -> staging
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      double acc = cmain[m] * smem[ymain[m]];
-      if (zsp[m] >= 0)
-        acc += smem[zsp[m]] * smem[ybase[m]] + smem[zsp[m] + 16] * smem[ybase[m] + 1] + smem[zsp[m] + 32] * smem[ybase[m] + 2];
-      if (ia[m] >= 0) acc += smem[o0[m] + k] + mu * smem[o1[m] + k] + dw * (smem[o2[m] + k] + c3[m]);
-      ent[m] = acc;
+      const double v = cmain[m] * smem[ymain[m]] + smem[o0[m] + k] + mu * smem[o1[m] + k] + dw * (smem[o2[m] + k] + c3[m]);
+      if (m < 3 || lane < 24) smem[HS + lane + 32 * m] = v;
     }
-    // partial Cholesky: eliminate the six control pivots
-#pragma unroll 1
-    for (int j = 0; j < 6; ++j) {
+    __syncwarp();
+    if (lane < 9) smem[ch] += smem[cz] * smem[cy] + smem[cz + 16] * smem[cy + 1] + smem[cz + 32] * smem[cy + 2];
+    __syncwarp();
+    // Cholesky of the 6 x 6 control block, redundantly in every lane's registers (uniform inertia verdict)
+    double Lf[21], idg[6];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) if (ib[m] == j) smem[COL + ia[m]] = ent[m];
-      __syncwarp();
-      const double d = smem[COL + j];
-      if (!(d > 0.0)) return false;                 // uniform: every lane reads the same pivot
-      const double id = rsqrt(d), inv_d = id * id;
+    for (int e = 0; e < 21; ++e) Lf[e] = smem[HS + e];
+    if (!chol6(Lf, idg)) return false;
+    if (lane == 0) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-        if (ib[m] > j && ib[m] < 99) ent[m] = fma(-(smem[COL + ia[m]] * inv_d), smem[COL + ib[m]], ent[m]);
-      if (lane >= j && lane < 15) smem[FAC + j * 16 + lane] = smem[COL + lane] * id;
-      if (lane == 15) smem[FAC + j * 16 + 15] = id;
-      __syncwarp();
+      for (int e = 0; e < 21; ++e) smem[LS + e] = Lf[e];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) smem[LS + 21 + e] = idg[e];
     }
-    // trailing block -> P_k, p_k for the next stage
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (ib[m] >= 6 && ib[m] < 99) {
-        const int a = ia[m] - 6, b = ib[m] - 6;
-        if (ia[m] == 14) smem[PP + 8 * 9 + b] = ent[m];
-        else { smem[PP + a * 9 + b] = ent[m]; smem[PP + b * 9 + a] = ent[m]; }
-      }
-    }
-    // K = L^-T [L^-1 Psi | L^-1 psi]: lane c < 9 back-substitutes column c
+    // lane c < 9: row c of W = [Psi | psi]^T L^-T, then column c of K = L^-T W^T
     double* rk = ric + k * RIC_N;
     if (lane < 9) {
-      double x[6];
+      double w[6];
+      const int row = HS + (lane + 6) * (lane + 7) / 2;
 #pragma unroll
-      for (int i = 5; i >= 0; --i) {
-        double s = smem[FAC + i * 16 + 6 + lane];
+      for (int j = 0; j < 6; ++j) {
+        double s_ = smem[row + j];
 #pragma unroll
-        for (int m = i + 1; m < 6; ++m) s -= smem[FAC + i * 16 + m] * x[m];
-        x[i] = s * smem[FAC + i * 16 + 15];
+        for (int m = 0; m < j; ++m) s_ -= w[m] * Lf[tri(j, m)];
+        w[j] = s_ * idg[j];
+        smem[WS + lane * 6 + j] = w[j];
       }
 #pragma unroll
-      for (int r = 0; r < 6; ++r) rk[RIC_K + r * 9 + lane] = x[r];
-    } else if (lane < 30) {            // L (packed lower) for the SOC re-solves: entry e = tri(r, c) = FAC[c][r]
-      const int e = lane - 9;
-      const int r = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15), c = e - r * (r + 1) / 2;
-      rk[RIC_L + e] = smem[FAC + c * 16 + r];
+      for (int i = 5; i >= 0; --i) {
+        double s_ = w[i];
+#pragma unroll
+        for (int m = i + 1; m < 6; ++m) s_ -= Lf[tri(m, i)] * w[m];
+        w[i] = s_ * idg[i];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) rk[RIC_K + r * 9 + lane] = w[r];
     }
-    if (lane < 6) rk[RIC_L + 21 + lane] = smem[FAC + lane * 16 + 15];
+    __syncwarp();
+    if (lane < 27) rk[RIC_L + lane] = smem[LS + lane];   // L and 1/diag for the SOC re-solves
+    // trailing block -> P_k, p_k for the next stage
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (th[r] >= 0) {
+        double acc = smem[th[r]];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc -= smem[twa[r] + j] * smem[twb[r] + j];
+        smem[tp0[r]] = acc; smem[tp1[r]] = acc;
+      }
+    }
     __syncwarp();
   }
   return true;
