@@ -6,6 +6,7 @@
 //   nmpc_eval_kernel  function-level f / g / grad f / J^T lam / Hess_L v  (one warp per instance)
 //   nmpc_step_kernel  closed-loop shift (NMPC_TT.py:13-30) + FOV centre (:399-402), one thread per instance
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -232,6 +233,7 @@ struct nmpc_handle {
   cudaStream_t own_stream, last_stream;
   int64_t launches;
   double* dbg; int dbg_rows;
+  int align_group;
 };
 
 extern "C" {
@@ -276,6 +278,11 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   }
   if (h->blocks_per_sm < 1) { delete h; return fail("nmpc_create: kernel does not fit on an SM"); }
   h->max_blocks = h->sm_count * h->blocks_per_sm;
+  h->align_group = h->warps_per_block;
+  if (const char* e = getenv("NMPC_B200_ALIGN_GROUP")) {     // tuning knob: 0 = off, else a divisor of the warps per block
+    const int g = atoi(e);
+    if (g == 0 || (g > 0 && h->warps_per_block % g == 0)) h->align_group = g;
+  }
   h->ric_stride = RIC_N * h->pr.N;
   CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
@@ -330,6 +337,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.ric = h->d_ric; A.ric_stride = h->ric_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
   A.order = h->order_next; h->order_next = nullptr;
+  A.align_group = h->align_group;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
   const int blocks = B < h->max_blocks ? B : h->max_blocks;

@@ -42,6 +42,7 @@ struct SolveArgs {
   unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
   double* ric; int ric_stride;       // L2-resident Riccati scratch, one slice per resident warp
   double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][8] (tests only)
+  int align_group;                   // warps that start each IPM iteration together (0 = no alignment, else divides WPB)
 };
 
 constexpr double EPSM = 2.220446049250313e-16;
@@ -78,6 +79,17 @@ __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, doub
   b.lo = b.hl ? __dsub_rn(l2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(l2)))) : -CUDART_INF;
   b.hi = b.hu ? __dadd_rn(h2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(h2)))) : CUDART_INF;
   return b;
+}
+
+// Barrier over the group of `g` consecutive warps this warp belongs to (named barrier 1 + group index), OR-reducing
+// `working`.  g == 0: no alignment.
+__device__ __forceinline__ int align_warps(int g, int working) {
+  if (g == 0) return 0;
+  unsigned out;
+  const unsigned id = 1 + (threadIdx.x >> 5) / g, nt = 32 * g;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(out) : "r"((unsigned)working), "r"(id), "r"(nt) : "memory");
+  return (int)out;
 }
 
 #define LV(e) smem[L::LV0 + (e) * L::S + lane]
@@ -680,7 +692,9 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
     // Alignment point: the warps of a block start every IPM iteration together, so that they walk through the
     // same ~200 KB of phase code at the same time and share instruction-cache lines (unaligned warps thrash it:
     // `no_instruction` was 56 % of all stall cycles in v3).  Pure scheduling; results cannot depend on it.
-    __syncthreads_or(1);
+    // (Aligning at more points per iteration -- before the factorisation, direction, line search, accept -- was
+    // measured and is slower: each phase then lasts as long as its slowest warp; 43 -> 65 ms at B = 16384.)
+    align_warps(A.align_group, 1);
     ph_derivs<L>(A, lane, ls, df);
     if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
       ++n_fact;
@@ -832,7 +846,7 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
     solve_instance<L>(A, ric, b, lane);
     __syncwarp();
   }
-  while (__syncthreads_or(0)) {}   // out of work: keep matching the alignment barrier until every warp is done
+  while (align_warps(A.align_group, 0)) {}   // out of work: keep matching the alignment barrier until the group is done
 }
 
 #undef LV
