@@ -209,14 +209,14 @@ def run_b200(args, rank, world, local_rank):
     uh = torch.empty((B, sc.n_w), dtype=torch.float64).pin_memory().numpy(); uh[:] = cl.u_warm.cpu().numpy()
     lbx, ubx, lbg, ubg = sc.bounds(); vwh = vw.copy()
     barrier()
-    conv_e = 0; t_e = 0.0
+    conv_e = 0; t_e = 0.0; e2e_ms = []
     for k in range(Ke + 1):
         t0 = time.perf_counter()
         s2 = solver(x0=uh, p=ph, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, want_g=False, want_lam=False)
         uh[:] = host_shift(sc.T, ph, s2["x"], vwh)
         dt = time.perf_counter() - t0
         if k > 0:
-            t_e += dt; conv_e += int(solver.stats()["success"].sum())
+            t_e += dt; conv_e += int(solver.stats()["success"].sum()); e2e_ms.append(round(dt * 1e3, 3))
     barrier()
     t_e_max = sharding.max_over_ranks(t_e, dev)
     conv_e_all = float(sharding.sum_counters([conv_e], dev)[0])
@@ -277,7 +277,7 @@ def run_b200(args, rank, world, local_rank):
         "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
         "cold_first_step": cold, "wall_s": wall,
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=) with pinned numpy buffers -> nmpc_solve_host"},
         "gpu_launches": 2 * K,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,

@@ -229,6 +229,63 @@ def test_full_size_properties(pkg):
     assert same.mean() >= 0.8
 
 
+@pytest.mark.parametrize("name,N,B,jitter", [("t_trajectory", 15, 65536, 0),          # BASELINE config 3 (one GPU's batch)
+                                              ("plus_trajectory", 15, 65536, 0),
+                                              ("10_obstacles", 15, 32768, 3),         # config 4: 262144 / 8 GPUs, 3 real obstacles jittered
+                                              ("race_track_2", 30, 131072, 10)])      # config 5: 2x horizon, 1M / 8 GPUs, 10 obstacles jittered
+def test_full_size_other_configs(pkg, name, N, B, jitter):
+    """BASELINE configs 3-5 at the per-GPU batch size, all on the device: size-independent properties."""
+    sc = pkg.SCENARIOS[name]
+    if N != sc.N:
+        sc = sc.with_horizon(N)
+    dev = "cuda:0"
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, _ = pkg.random_instances(sc, B, seed=1000 * 3 + N + jitter)
+    obs = None
+    if jitter:
+        rng = np.random.default_rng(77)
+        obs = np.tile(sc.obstacle_table(), (B, 1, 1))
+        obs[:, :jitter, :2] += rng.uniform(-100, 100, (B, jitter, 2))
+        # SURVEY 8d: reject layouts that put an obstacle within r + 20 of the start (move it away instead)
+        d = np.linalg.norm(obs[:, :, :2] - p[:, None, :2], axis=2)
+        close = d < obs[:, :, 2] + 20.0
+        obs[:, :, 0] += np.where(close, 400.0, 0.0)
+    T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    x0 = T(np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (B, sc.N)))
+    pt = T(p); obt = None if obs is None else T(obs)
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    sol = s(x0=x0, p=pt, lbx=T(lbx), ubx=T(ubx), lbg=T(lbg), ubg=T(ubg), obstacles=obt)
+    st = s.stats()
+    ok = st["success"]
+    assert float(ok.double().mean()) > 0.9
+    assert int(st["iter_count"].max()) <= 100 and int(st["iter_count"][ok].min()) > 0
+    x, g = sol["x"][ok], sol["g"][ok]
+    assert bool((x >= T(lbx) - 1e-12).all()) and bool((x <= T(ubx) + 1e-12).all())
+    assert bool((g <= T(ubg) + 1e-4).all()) and bool((g >= T(lbg) - 1e-4).all())
+    ev = s.evaluate(sol["x"], pt, lam=sol["lam_g"], obstacles=obs)
+    assert torch.allclose(ev["f"], sol["f"], rtol=1e-13, atol=0)
+    assert torch.allclose(ev["g"], sol["g"], rtol=0, atol=1e-9)
+    r = (ev["grad"] + ev["jtv"] + sol["lam_x"]).abs().amax(dim=1)
+    mult = torch.maximum(sol["lam_g"].abs().amax(dim=1), sol["lam_x"].abs().amax(dim=1)).clamp(min=1.0)
+    gscale = torch.maximum(ev["grad"].abs().amax(dim=1), mult)
+    # The returned x is clipped to the original bounds (IPOPT's honor_original_bounds): up to 1e-8 off the internal
+    # iterate.  Where the UAV passes almost exactly over the target the sqrt term has curvature 1/distance ~ 1e4
+    # (SURVEY 7.3-5), so on a fraction of a percent of the instances that clip shows up as 1e-4 in the gradient of
+    # an active control (tools/stat_probe.py).  Bound the bulk tightly and the outliers loosely.
+    ratio = r[ok] / (1e-6 + 2e-6 * gscale[ok])
+    assert float((ratio <= 1.0).double().mean()) >= 0.995, float((ratio <= 1.0).double().mean())
+    assert float((r[ok] / (1.0 + gscale[ok])).max()) <= 1e-3
+    # complementarity and sign of the bound multipliers (CasADi convention: lam > 0 at an upper bound)
+    lam_g = sol["lam_g"][ok]
+    ub, lb = T(ubg), T(lbg)
+    fu, fl = torch.isfinite(ub), torch.isfinite(lb)
+    zero = torch.zeros((), dtype=torch.float64, device=dev)
+    up, lo = lam_g.clamp(min=0), (-lam_g).clamp(min=0)
+    # IPOPT's unscaled complementarity tolerance compl_inf_tol = 1e-4
+    assert float((up * torch.where(fu, ub - g, zero)).amax()) <= 1e-4 and float((lo * torch.where(fl, g - lb, zero)).amax()) <= 1e-4
+    assert float(up[:, ~fu].amax() if (~fu).any() else 0.0) <= 1e-8 and float(lo[:, ~fl].amax() if (~fl).any() else 0.0) <= 1e-8
+
+
 def test_edge_cases(pkg):
     sc = pkg.SCENARIOS["t_trajectory"]
     lbx, ubx, lbg, ubg = sc.bounds()
