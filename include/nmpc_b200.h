@@ -129,6 +129,11 @@ int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out);   /* synchronises the handl
  * do not depend on it (instances are independent); only the tail of the batch step does.  NULL = natural order. */
 int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order);
 
+/* Per-instance cost weights (w1, w2) for the weight sweeps of the reference's outer loops (MATLAB/Race Track 1/MPC.m:1,:90;
+ * the dead tables at NMPC_TT.py:178-188): dev_weights [B][2] is read by every subsequent nmpc_solve / nmpc_solve_host /
+ * nmpc_eval on this handle (it must stay allocated and hold at least B rows); NULL restores spec.w1 / spec.w2. */
+int nmpc_set_weights(nmpc_handle* h, const double* dev_weights);
+
 /* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
  * dev_buf [B][rows][8] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials}; NULL disables. */
 int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);

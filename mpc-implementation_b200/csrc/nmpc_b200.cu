@@ -36,6 +36,7 @@ static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_IN
 struct EvalArgs {
   Prob pr; int B;
   const double *w, *p, *obs; int obs_per_instance;
+  const double* weights;
   double sigma; const double *lam, *v;
   double *f, *g, *grad, *jtv, *hv;
 };
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
 #pragma unroll
   for (int i = 0; i < 21; ++i) Hl[i] = 0.0;
   double l = 0.0;
-  if (hasu) l = stage_cost_d2(pr, st.X, xt, yt, gl, Hl);
+  if (hasu) l = stage_cost_d2(A.weights ? with_weights(pr, A.weights[2 * (size_t)b], A.weights[2 * (size_t)b + 1]) : pr, st.X, xt, yt, gl, Hl);
   const double fsum = warp_sum(l);
   if (lane == 0 && A.f) A.f[b] = fsum;
   if (act && A.g) {
@@ -226,6 +227,7 @@ struct nmpc_handle {
   const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
   double* d_ric; int ric_stride;
   int32_t* d_order; const int32_t* order_next;
+  const double* weights;
   int* d_counter; unsigned long long* d_stats;
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
@@ -337,6 +339,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.ric = h->d_ric; A.ric_stride = h->ric_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
   A.order = h->order_next; h->order_next = nullptr;
+  A.weights = h->weights;
   A.align_group = h->align_group;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
@@ -395,6 +398,7 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
   CK(cudaSetDevice(h->device));
   EvalArgs A;
   A.pr = h->pr; A.B = B; A.w = w; A.p = p; A.obs = obst; A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
+  A.weights = h->weights;
   A.sigma = sigma; A.lam = lam; A.v = v; A.f = f; A.g = g; A.grad = grad_f; A.jtv = jtv; A.hv = hv;
   const int warps = 4;
   nmpc_eval_kernel<<<(B + warps - 1) / warps, warps * 32, 0, (cudaStream_t)cuda_stream>>>(A);
@@ -419,6 +423,12 @@ int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
 int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order) {
   if (!h) return fail("nmpc_set_order: null handle");
   h->order_next = dev_order;
+  return 0;
+}
+
+int nmpc_set_weights(nmpc_handle* h, const double* dev_weights) {
+  if (!h) return fail("nmpc_set_weights: null handle");
+  h->weights = dev_weights;
   return 0;
 }
 

@@ -154,7 +154,7 @@ struct Lay {
   static constexpr int FILT0 = even_up(OBS0 + 3 * NOBS_ + 1);
   static constexpr int RES0 = FILT0 + 2 * FILT_CAP;
   static constexpr int PAR0 = RES0 + 24;
-  static constexpr int TOTAL = even_up(PAR0 + 12);
+  static constexpr int TOTAL = even_up(PAR0 + 14);   // p (11), w1, w2 of this instance
   // warps (= concurrent instances) per block: as many slices as fit in the 227 KB a block may use, at most NMPC_WPB_MAX
   static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);
   static constexpr int WPB = WPB_FIT < 1 ? 1 : (WPB_FIT > NMPC_WPB_MAX ? NMPC_WPB_MAX : WPB_FIT);
@@ -193,6 +193,9 @@ __device__ __forceinline__ void fov_trig(const Prob& pr, const double* X, Fov& f
   f.t5p = n_tan(X[5] + pr.hh); f.t5m = n_tan(X[5] - pr.hh);
   const double2 sc = n_sincos(X[7]); f.s7 = sc.x; f.c7 = sc.y;
 }
+
+// problem constants with this instance's cost weights (NMPC_TT.py:204-205; per instance for weight sweeps)
+__device__ __forceinline__ Prob with_weights(const Prob& pr, double w1, double w2) { Prob q = pr; q.w1 = w1; q.w2 = w2; return q; }
 
 // stage cost value (compact form of NMPC_TT.py:209-220)
 __device__ __forceinline__ double stage_cost(const Prob& pr, const double* X, double xt, double yt) {

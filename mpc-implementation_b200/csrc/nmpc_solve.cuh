@@ -37,6 +37,7 @@ struct SolveArgs {
   int obs_per_instance;
   double *x, *f, *g, *lam_x, *lam_g;
   int32_t *status, *iters;
+  const double* weights;             // optional per-instance cost weights [B][2] = (w1, w2); NULL = spec weights
   const int32_t* order;              // optional processing order (longest-first scheduling); NULL = 0..B-1
   int* counter;                      // work queue
   unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
@@ -152,6 +153,8 @@ __device__ __forceinline__ double obs_value(const double* X, int jn, double& nx,
 template <class L>
 __device__ __noinline__ void ph_load(const SolveArgs& A, int b, int lane) {
   if (lane < NPAR) PAR(lane) = A.p[(size_t)b * NPAR + lane];
+  if (lane == NPAR) PAR(NPAR) = A.weights ? A.weights[2 * (size_t)b] : A.pr.w1;
+  if (lane == NPAR + 1) PAR(NPAR + 1) = A.weights ? A.weights[2 * (size_t)b + 1] : A.pr.w2;
   const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * L::NOBS : 0);
   for (int i = lane; i < 3 * L::NOBS; i += 32) smem[L::OBS0 + i] = ob[i];
   if (lane <= L::N) {
@@ -178,7 +181,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.0;
   if (hasu && lane >= 1) {
-    stage_cost_d2(pr, st.X, PAR(8), PAR(9), gl, Hl);
+    stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9), gl, Hl);
 #pragma unroll
     for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
   }
@@ -286,7 +289,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
 #pragma unroll
   for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
   double l = 0.0;
-  if (hasu) l = stage_cost_d2(pr, st.X, PAR(8), PAR(9), gl, Hl);
+  if (hasu) l = stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9), gl, Hl);
   if (lane == 0) {   // stage 0 is constant in w
 #pragma unroll
     for (int v = 0; v < 6; ++v) gl[v] = 0.0;
@@ -515,7 +518,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     }
   }
   Stage st; rollout(pr, &PAR(0), ut, lane, st);
-  const double l = hasu ? stage_cost(pr, st.X, PAR(8), PAR(9)) : 0.0;
+  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9)) : 0.0;
   double th = 0.0;
   if (act) {
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
@@ -637,7 +640,7 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
     }
   }
   Stage st; rollout(pr, &PAR(0), u, lane, st);
-  const double l = hasu ? stage_cost(pr, st.X, PAR(8), PAR(9)) : 0.0;
+  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9)) : 0.0;
   const double fu = warp_sum(l);
   if (lane == 0) {
     if (A.f) A.f[b] = fu;

@@ -121,14 +121,42 @@ class Solver:
 
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, obstacles=None,
-                 want_g: bool = True, want_lam: bool = True, order=None):
+                 want_g: bool = True, want_lam: bool = True, order=None, weights=None):
+        """weights: optional [B, 2] per-instance cost weights (w1, w2) for this call (numpy or CUDA tensor); the
+        reference edits them in source (NMPC_TT.py:204-205) and its MATLAB outer loop sweeps them (MPC.m:90)."""
         if p is None:
             raise ValueError("solver: p is required")
         if any(v is None for v in (lbx, ubx, lbg, ubg)):
             raise ValueError("solver: lbx, ubx, lbg, ubg are required (the reference passes all four)")
-        if _is_cuda_tensor(p):
-            return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order)
-        return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+        with self._weights(weights, p):
+            if _is_cuda_tensor(p):
+                return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order)
+            return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+
+    def _weights(self, weights, p):
+        """Context manager: nmpc_set_weights for the duration of one call."""
+        import contextlib
+        if weights is None:
+            return contextlib.nullcontext()
+        B = int(p.shape[0]) if (hasattr(p, "shape") and len(p.shape) == 2 and p.shape[1] == NP) else 1
+        w = torch.as_tensor(weights if _is_cuda_tensor(weights) else np.asarray(weights, dtype=np.float64),
+                            dtype=torch.float64, device=f"cuda:{self.device}").reshape(-1, 2).contiguous()
+        if w.shape[0] != B:
+            raise ValueError("solver: weights must be [B, 2]")
+        L = _ffi.lib()
+
+        @contextlib.contextmanager
+        def cm():
+            if B > self._max_batch:          # grow first: the weights belong to the handle that runs the call
+                self._create(max(B, 2 * self._max_batch))
+            _ffi.check(L.nmpc_set_weights(self._h, w.data_ptr()), "nmpc_set_weights")
+            try:
+                yield
+            finally:
+                if _is_cuda_tensor(p):      # asynchronous call: the kernel reads w later on the stream
+                    self._keep_w = w
+                L.nmpc_set_weights(self._h, None)
+        return cm()
 
     def _obst(self, obstacles, B):
         if obstacles is None:
@@ -225,7 +253,10 @@ class Solver:
                     soc_accepted=st.soc_accepted)
 
     # -- function-level evaluation (nlp_f / nlp_g / nlp_grad_f / nlp_hess_l of the reference's nlpsol) ----
-    def evaluate(self, w, p, lam=None, v=None, sigma: float = 1.0, obstacles=None):
+    def evaluate(self, w, p, lam=None, v=None, sigma: float = 1.0, obstacles=None, weights=None):
+        if weights is not None:
+            with self._weights(weights, np.asarray(p) if not _is_cuda_tensor(p) else p):
+                return self.evaluate(w, p, lam=lam, v=v, sigma=sigma, obstacles=obstacles)
         L = _ffi.lib()
         dev = f"cuda:{self.device}"
         to = lambda a, n: torch.as_tensor(np.asarray(a, dtype=np.float64) if not _is_cuda_tensor(a) else a,

@@ -120,6 +120,42 @@ def test_per_instance_obstacles(pkg, oracle_mod):
     _compare(r2, sel(sol), st["return_status"][both], st["iter_count"][both], (lbx, ubx, lbg, ubg))
 
 
+def test_per_instance_weights(pkg, oracle_mod):
+    """cost weights (w1, w2) as per-instance inputs (the reference's RL-style weight sweeps)."""
+    sc = pkg.SCENARIOS["t_trajectory"]
+    B = 36
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, _ = pkg.random_instances(sc, B, seed=31)
+    x0 = np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (B, sc.N))
+    pairs = [(1.0, 2.0), (0.5, 4.0), (3.0, 0.5)]
+    wts = np.array([pairs[i % 3] for i in range(B)])
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    sol = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, weights=wts)
+    st = s.stats()
+    for k, (w1, w2) in enumerate(pairs):
+        sel = np.arange(B) % 3 == k
+        sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, w1, w2, sc.vfov, sc.hfov)
+        ref = oracle_mod.solve(sp, sc.obstacle_table(), p[sel], x0[sel], lbx, ubx, lbg, ubg)
+        got = {q: sol[q][sel] for q in ("x", "f", "g")}
+        assert (ref["status"] == st["return_status"][sel]).mean() >= 0.9
+        both = (ref["status"] == 0) & (st["return_status"][sel] == 0)
+        assert both.sum() >= 8
+        r2 = {q: ref[q][both] for q in ("x", "f", "g")}; r2["status"] = ref["status"][both]
+        _compare(r2, {q: got[q][both] for q in got}, st["return_status"][sel][both], st["iter_count"][sel][both], (lbx, ubx, lbg, ubg))
+        # function level with the same weights
+        ev = s.evaluate(sol["x"][sel], p[sel], weights=wts[sel])
+        for j in range(3):
+            fo = oracle_mod.evaluate(sp, sc.obstacle_table(), sol["x"][sel][j], p[sel][j])
+            assert abs(float(ev["f"][j]) - fo["f"]) <= 1e-12 * abs(fo["f"])
+            assert np.allclose(ev["grad"][j].cpu().numpy(), fo["grad"], rtol=1e-8, atol=1e-9 * np.abs(fo["grad"]).max())
+    # the weights applied to that call only: the next call uses the spec's (1, 2) again
+    sol2 = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    k0 = np.arange(B) % 3 == 0
+    ok = (st["return_status"] == 0) & (s.stats()["return_status"] == 0) & k0
+    assert np.allclose(sol2["f"][ok], sol["f"][ok], rtol=1e-9)
+    assert not np.allclose(sol2["f"][~k0], sol["f"][~k0], rtol=1e-3)
+
+
 def test_function_level(pkg, oracle_mod):
     """nmpc_eval (f, g, grad f, J^T lam, Hess_L v) vs the oracle's dense derivatives."""
     for name in ("nmpc_tt", "race_track_2"):
