@@ -151,6 +151,8 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     sc = b200nmpc.SCENARIOS[SCENARIO]
     B = args.batch
+    if args.no_lpt:
+        os.environ["NMPC_B200_AUTO_ORDER"] = "0"
     p, vw = b200nmpc.random_instances(sc, B, seed=2000 + rank)
     solver = b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=B)
     cl = ClosedLoop(solver, sc, p, target_vw=vw)
@@ -181,8 +183,7 @@ def run_b200(args, rank, world, local_rank):
         cl._schedule_vw()
         tb = cl.p[:, 8:10].clone()
         ev[k][0].record()
-        sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False,
-                     order=None if args.no_lpt else cl.next_order())
+        sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False)
         ev[k][1].record()
         solver.step(sol["x"], cl.p, cl.u_warm, cl.vw, cl.fov)
         cl.err_sum += torch.linalg.vector_norm(cl.fov - tb, dim=1)
@@ -203,19 +204,23 @@ def run_b200(args, rank, world, local_rank):
     conv_all, iters_all = float(tot[0]), float(tot[1])
     value = conv_all / t_max
 
-    # ---- e2e: the same closed loop through the host-buffer entry point (H2D + solve + D2H every step)
-    Ke = min(K, args.e2e_steps)
-    ph = torch.empty((B, 11), dtype=torch.float64).pin_memory().numpy(); ph[:] = cl.p.cpu().numpy()
-    uh = torch.empty((B, sc.n_w), dtype=torch.float64).pin_memory().numpy(); uh[:] = cl.u_warm.cpu().numpy()
+    # ---- e2e: the SAME closed loop (same instances, same warm-up, same timed steps) driven through the host-buffer
+    #      entry point: every step copies p and the warm start H2D from pinned memory, solves, copies x, f, status,
+    #      iters D2H, and does the shift on the host like the reference script does (NMPC_TT.py:382)
+    Ke = min(K, args.e2e_steps) if args.e2e_steps > 0 else K
+    ph = torch.empty((B, 11), dtype=torch.float64).pin_memory().numpy(); ph[:] = p
+    uh = torch.empty((B, sc.n_w), dtype=torch.float64).pin_memory().numpy(); uh[:] = 0.0
     lbx, ubx, lbg, ubg = sc.bounds(); vwh = vw.copy()
     barrier()
     conv_e = 0; t_e = 0.0; e2e_ms = []
-    for k in range(Ke + 1):
+    for k in range(args.warmup + Ke):
+        if k == args.warmup:
+            barrier()
         t0 = time.perf_counter()
         s2 = solver(x0=uh, p=ph, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, want_g=False, want_lam=False)
         uh[:] = host_shift(sc.T, ph, s2["x"], vwh)
         dt = time.perf_counter() - t0
-        if k > 0:
+        if k >= args.warmup:
             t_e += dt; conv_e += int(solver.stats()["success"].sum()); e2e_ms.append(round(dt * 1e3, 3))
     barrier()
     t_e_max = sharding.max_over_ranks(t_e, dev)
@@ -272,14 +277,14 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}, n_w={sc.n_w}, n_g={sc.n_g}) closed loop: "
                                f"{B} randomised UAV states / target speeds per GPU (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
-                   "l2": "flushed between timed steps (256 MB write)", "scheduling": "natural order" if args.no_lpt else "longest-first by previous-step iteration count (argsort inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
+                   "l2": "flushed between timed steps (256 MB write)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (nmpc_order_kernel inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
         "p50_step_ms": float(np.median(step_ms)), "p50_solve_kernel_ms": float(np.median(solve_ms)),
         "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
         "cold_first_step": cold, "wall_s": wall,
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=) with pinned numpy buffers -> nmpc_solve_host"},
-        "gpu_launches": 2 * K,
+        "gpu_launches": (2 if args.no_lpt else 3) * K,     # [nmpc_order_kernel,] nmpc_ipm_kernel, nmpc_step_kernel per step
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
                      "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "peak_source": which,
                      "bytes_per_solve": bytes_per_solve(sc.N, sc.n_obs),
@@ -308,11 +313,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed steps of the host-buffer arm (0 = as many as --steps)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-lpt", action="store_true", help="disable longest-first scheduling by previous iteration counts")
+    ap.add_argument("--no-lpt", action="store_true", help="disable the library's longest-first scheduling (NMPC_B200_AUTO_ORDER=0)")
     ap.add_argument("--count-work", action="store_true", help="read device work counters every timed step (adds a sync)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -57,8 +57,9 @@ class ClosedLoop:
             self.vw.copy_(torch.from_numpy(vw))
 
     def next_order(self):
-        """Longest-first fetch order for the persistent kernel: instances that needed many iterations last step are
-        started first, so the batch step does not end with a few 100-iteration stragglers running alone."""
+        """Explicit longest-first fetch order (previous iteration counts, descending) for `solver(order=)`.  The
+        library does the same by itself for consecutive calls with equal B (include/nmpc_b200.h, "Scheduling"), so
+        the loop below does not pass one; kept for callers that permute their instances between steps."""
         st = self.solver.stats()
         it = st.get("iter_count") if st else None
         if it is None or not torch.is_tensor(it) or it.numel() != self.B:
@@ -70,7 +71,7 @@ class ClosedLoop:
         self._schedule_vw()
         target_before = self.p[:, 8:10].clone()
         sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg,
-                          want_g=want_g, want_lam=want_lam, order=self.next_order())
+                          want_g=want_g, want_lam=want_lam)
         self.solver.step(sol["x"], self.p, self.u_warm, self.vw, self.fov)
         # error[i] = || FOVcentre_{i+1} - target_i ||   (NMPC_TT.py:435)
         self.err_sum += torch.linalg.vector_norm(self.fov - target_before, dim=1)

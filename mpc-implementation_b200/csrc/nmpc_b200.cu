@@ -176,6 +176,22 @@ struct StepArgs {
   const double* x_sol; double *p, *u_warm; const double* vw; double* fov;
 };
 
+// Longest-first fetch order for the persistent kernel from the previous call's iteration counts: counting sort,
+// descending, one block (B = 4096: ~10 us; the order inside a bin is arbitrary -- results do not depend on it).
+__global__ void __launch_bounds__(1024) nmpc_order_kernel(const int32_t* __restrict__ iters, int B, int32_t* __restrict__ order) {
+  __shared__ int bin[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) bin[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&bin[min(max(iters[i], 0), 255)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int v = 255; v >= 0; --v) { const int c = bin[v]; bin[v] = acc; acc += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) order[atomicAdd(&bin[min(max(iters[i], 0), 255)], 1)] = i;
+}
+
 __global__ void nmpc_step_kernel(const StepArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
@@ -226,7 +242,7 @@ struct nmpc_handle {
   Prob pr; Opt opt;
   const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
   double* d_ric; int ric_stride;
-  int32_t* d_order; const int32_t* order_next;
+  int32_t *d_order, *d_keep_iters; int order_cap, prev_B, auto_order; const int32_t* order_next;
   const double* weights;
   int* d_counter; unsigned long long* d_stats;
   // staging for nmpc_solve_host
@@ -235,7 +251,7 @@ struct nmpc_handle {
   cudaStream_t own_stream, last_stream;
   int64_t launches;
   double* dbg; int dbg_rows;
-  int align_group;
+  int align_group, align_quorum;
 };
 
 extern "C" {
@@ -285,6 +301,13 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     const int g = atoi(e);
     if (g == 0 || (g > 0 && h->warps_per_block % g == 0)) h->align_group = g;
   }
+  h->align_quorum = h->align_group;
+  if (const char* e = getenv("NMPC_B200_ALIGN_QUORUM")) {    // tuning knob: arrivals that release the barrier
+    const int q = atoi(e);
+    if (q >= 1 && q <= h->align_group) h->align_quorum = q;
+  }
+  h->auto_order = 1;
+  if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
   h->ric_stride = RIC_N * h->pr.N;
   CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
@@ -312,7 +335,7 @@ int nmpc_destroy(nmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_ric, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
-                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters};
+                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order, h->d_keep_iters};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -338,9 +361,23 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.counter = h->d_counter; A.stats = h->d_stats;
   A.ric = h->d_ric; A.ric_stride = h->ric_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
+  if (B > h->order_cap) {     // (re)allocate the scheduling buffers; the previous counts are dropped
+    if (h->d_order) cudaFree(h->d_order);
+    if (h->d_keep_iters) cudaFree(h->d_keep_iters);
+    h->d_order = nullptr; h->d_keep_iters = nullptr; h->order_cap = 0; h->prev_B = 0;
+    CK(cudaMalloc(&h->d_order, sizeof(int32_t) * B)); CK(cudaMalloc(&h->d_keep_iters, sizeof(int32_t) * B));
+    h->order_cap = B;
+  }
+  A.iters_keep = h->d_keep_iters;
   A.order = h->order_next; h->order_next = nullptr;
+  h->launches = 1;
+  if (!A.order && h->auto_order && h->prev_B == B) {   // same batch as last time: start last time's longest solves first
+    nmpc_order_kernel<<<1, 1024, 0, s>>>(h->d_keep_iters, B, h->d_order);
+    A.order = h->d_order; h->launches = 2;
+  }
+  h->prev_B = B;
   A.weights = h->weights;
-  A.align_group = h->align_group;
+  A.align_group = h->align_group; A.align_quorum = h->align_quorum;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
   const int blocks = B < h->max_blocks ? B : h->max_blocks;
@@ -348,7 +385,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
     const int rc = h->inst->launch(A, blocks, h->smem_bytes, s);
     if (rc != 0) return fail(std::string("nmpc_solve: launch failed: ") + cudaGetErrorString((cudaError_t)rc));
   }
-  h->last_stream = s; h->launches = 1;
+  h->last_stream = s;
   return 0;
 }
 
