@@ -26,11 +26,12 @@ using namespace nmpc;
 namespace nmpc {
 #define NMPC_DECL_INST(N, O)                      \
   int ipm_prepare_##N##_##O(int*, size_t*, int*);        \
+  int ipm_ricmap_##N##_##O(unsigned*, cudaStream_t);     \
   int ipm_launch_##N##_##O(const SolveArgs&, int, size_t, cudaStream_t);
 NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3)
 }  // namespace nmpc
-struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
-#define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_launch_##N##_##O}
+struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*); int (*ricmap)(unsigned*, cudaStream_t); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
+#define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_ricmap_##N##_##O, nmpc::ipm_launch_##N##_##O}
 static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3)};
 
 struct EvalArgs {
@@ -241,7 +242,7 @@ struct nmpc_handle {
   nmpc_spec spec; int device; int sm_count;
   Prob pr; Opt opt;
   const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
-  double* d_ric; int ric_stride;
+  double* d_ric; int ric_stride; unsigned* d_ricmap;
   int32_t *d_order, *d_keep_iters; int order_cap, prev_B, auto_order; const int32_t* order_next;
   const double* weights;
   int* d_counter; unsigned long long* d_stats;
@@ -310,6 +311,12 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
   h->ric_stride = RIC_N * h->pr.N;
   CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
+  CK(cudaMalloc(&h->d_ricmap, sizeof(unsigned) * 32 * 16));
+  {
+    const int rc = h->inst->ricmap(h->d_ricmap, 0);
+    if (rc != 0) { return fail(std::string("nmpc_create: map kernel failed: ") + cudaGetErrorString((cudaError_t)rc)); }
+    CK(cudaDeviceSynchronize());
+  }
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));
@@ -335,7 +342,7 @@ int nmpc_destroy(nmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_ric, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
-                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order, h->d_keep_iters};
+                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order, h->d_keep_iters, h->d_ricmap};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -359,7 +366,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
   A.x = x; A.f = f; A.g = g; A.lam_x = lam_x; A.lam_g = lam_g; A.status = status; A.iters = iters;
   A.counter = h->d_counter; A.stats = h->d_stats;
-  A.ric = h->d_ric; A.ric_stride = h->ric_stride;
+  A.ric = h->d_ric; A.ric_stride = h->ric_stride; A.ricmap = h->d_ricmap;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
   if (B > h->order_cap) {     // (re)allocate the scheduling buffers; the previous counts are dropped
     if (h->d_order) cudaFree(h->d_order);

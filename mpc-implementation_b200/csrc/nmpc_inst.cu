@@ -23,6 +23,12 @@ int NMPC_CAT(ipm_prepare, INST_N, INST_NOBS)(int* blocks_per_sm, size_t* smem_by
   return (int)e;
 }
 
+// fills the [RIC_MAP_WORDS][32] table the factorisation loads its ownership maps from (once, at nmpc_create)
+int NMPC_CAT(ipm_ricmap, INST_N, INST_NOBS)(unsigned* dev_table, cudaStream_t s) {
+  ric_map_kernel<Lay<INST_N, INST_NOBS>><<<1, 32, 0, s>>>(dev_table);
+  return (int)cudaGetLastError();
+}
+
 int NMPC_CAT(ipm_launch, INST_N, INST_NOBS)(const SolveArgs& A, int blocks, size_t bytes, cudaStream_t s) {
   using L = Lay<INST_N, INST_NOBS>;
   nmpc_ipm_kernel<INST_N, INST_NOBS><<<blocks, 32 * L::WPB, bytes, s>>>(A);

@@ -41,31 +41,37 @@ __device__ __forceinline__ double q_entry(int k, int i, int j, double dw) {
   return v;
 }
 
+// ---- per-lane ownership maps of the factorisation -------------------------------------------------------------
+// They depend on the lane and the layout only, so they are computed once per (N, n_obs) instantiation by
+// ric_map_kernel (at nmpc_create) into a global table of RIC_MAP_WORDS x 32 words, [word][lane], and loaded by
+// riccati_factor (15 coalesced L1-resident loads instead of ~800 instructions of index arithmetic per call).
+// All entries are shared-memory indices relative to the warp's slice, packed two per word:
+//   w0..1 o0[4]   w2..3 o1[4]   w4..5 o2[4]   w6..7 ymain[4]   w8 cz|cy   w9 ch|th0   w10 th1|twa0   w11 twb0|twa1
+//   w12 twb1|tp0[0]   w13 tp1[0]|tp0[1]   w14 tp1[1]|codes,  codes = cmain code (2 bits: 0, 1, T, T^2) x 4 | c3 flag x 4 << 8
+constexpr int RIC_MAP_WORDS = 15;
+
 template <class L>
-__device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, double mu, double dw, int lane) {
-  constexpr int S = L::S, N = L::N;
-  constexpr int PP = L::STG0 + SG_PP, ZS = L::STG0 + SG_Z, YS = L::STG0 + SG_Y, HS = L::STG0 + SG_H, WS = L::STG0 + SG_W, LS = L::STG0 + SG_L;
+__device__ void ric_map_build(int lane, unsigned* __restrict__ out /* [RIC_MAP_WORDS][32] */) {
+  constexpr int S = L::S;
+  constexpr int PP = L::STG0 + SG_PP, ZS = L::STG0 + SG_Z, YS = L::STG0 + SG_Y, HS = L::STG0 + SG_H, WS = L::STG0 + SG_W;
   constexpr int LQ0 = L::LQ0;
   // Column c of Z = [B | A] is T e_{c+2} (c = 1..5) or e_{c-6} (c >= 6), plus stage-dependent entries in rows 0..2
   // for the "special" columns c = 0 (v: no unit part), 9 (theta), 10 (psi).
   auto spec = [](int c) { return c == 0 || c == 9 || c == 10; };
   auto sid = [](int c) { return c >= 6 ? c - 6 : c + 2; };                 // row of the unit entry (c >= 1)
   auto spj = [](int c) { return c == 0 ? 0 : c - 8; };                     // special column -> 0, 1, 2
-  // ---- ownership map for BUILDING the stage matrix: entry e = lane + 32 m of the packed lower triangle,
+  auto row_of = [](int e) { int a = 0; while ((a + 1) * (a + 2) / 2 <= e) ++a; return a; };
+  // ---- BUILDING the stage matrix: entry e = lane + 32 m of the packed lower triangle,
   //      ent = cmain * smem[ymain] + lq[o0] + mu * lq[o1] + dw * (lq[o2] + c3)
-  int o0[4], o1[4], o2[4], ymain[4]; double c3[4], cmain[4];
-#pragma unroll
+  int o0[4], o1[4], o2[4], ymain[4]; unsigned codes = 0;
   for (int m = 0; m < 4; ++m) {
     const int e = lane + 32 * m;
-    int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-    while (a * (a + 1) / 2 > e) --a;
-    while ((a + 1) * (a + 2) / 2 <= e) ++a;
-    const int b = e - a * (a + 1) / 2;
+    const int a = row_of(e), b = e - a * (a + 1) / 2;
     const bool valid = e < 119;                       // e == 119 is (14,14): not needed
-    int p0 = LQ_ZERO, p1 = LQ_ZERO, p2 = LQ_ZERO; double cc = 0.0;
-    int ym = PP; double cm = 0.0;
+    int p0 = LQ_ZERO, p1 = LQ_ZERO, p2 = LQ_ZERO, cc = 0;
+    int ym = PP, cm = 0;                              // cm: 0 -> 0.0, 1 -> 1.0, 2 -> T, 3 -> T*T
     if (valid) {
-      if (a < 6) { if (a == b) { p0 = LQ_RD + a; cc = 1.0; } }
+      if (a < 6) { if (a == b) { p0 = LQ_RD + a; cc = 1; } }
       else if (a < 14) {
         if (b < 6) { if (b == 0 && a == 9) p0 = LQ_SV + 0; else if (b == 0 && a == 10) p0 = LQ_SV + 1; }
         else {
@@ -79,42 +85,69 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
         else { p0 = LQ_QA + (b - 6); p1 = LQ_QB + (b - 6); p2 = LQ_QD + (b - 6); }
       }
       // H[a][b] = z_a^T P+ z_b,  h[b] = z_b^T p+ : the part that is ONE scaled entry of P+ / p+ / Y_special
-      const double ca = (a >= 1 && a < 6) ? T : 1.0, cb = (b >= 1 && b < 6) ? T : 1.0;
+      const int ca = (a >= 1 && a < 6) ? 1 : 0, cb = (b >= 1 && b < 6) ? 1 : 0;    // powers of T
       if (a == 14) {
-        if (b != 0) { ym = PP + 72 + sid(b); cm = cb; }                      // b == 0: correction only
-      } else if (!spec(a) && !spec(b)) { ym = PP + sid(a) * 9 + sid(b); cm = ca * cb; }
-      else if (spec(b) && !spec(a)) { ym = YS + spj(b) * 8 + sid(a); cm = ca; }
-      else if (spec(a) && !spec(b)) { ym = YS + spj(a) * 8 + sid(b); cm = cb; }
-      else if (a != 0) { ym = YS + spj(b) * 8 + sid(a); cm = 1.0; }          // both special: unit part of z_a (none for a == 0)
+        if (b != 0) { ym = PP + 72 + sid(b); cm = 1 + cb; }                  // b == 0: correction only
+      } else if (!spec(a) && !spec(b)) { ym = PP + sid(a) * 9 + sid(b); cm = 1 + ca + cb; }
+      else if (spec(b) && !spec(a)) { ym = YS + spj(b) * 8 + sid(a); cm = 1 + ca; }
+      else if (spec(a) && !spec(b)) { ym = YS + spj(a) * 8 + sid(b); cm = 1 + cb; }
+      else if (a != 0) { ym = YS + spj(b) * 8 + sid(a); cm = 1; }            // both special: unit part of z_a (none for a == 0)
     }
-    o0[m] = LQ0 + p0 * S; o1[m] = LQ0 + p1 * S; o2[m] = LQ0 + p2 * S; c3[m] = cc;
-    ymain[m] = ym; cmain[m] = cm;
+    o0[m] = LQ0 + p0 * S; o1[m] = LQ0 + p1 * S; o2[m] = LQ0 + p2 * S;
+    ymain[m] = ym; codes |= (unsigned)cm << (2 * m); codes |= (unsigned)cc << (8 + m);
   }
   // ---- the nine entries whose z_a AND z_b (or p+) are special get  sum_s Z[s][za] * Yv[s]  on top (lanes 0..8)
   int cz = ZS, cy = PP, ch = HS;
-  {
+  if (lane < 9) {
     const int ca_[9] = {0, 9, 10, 9, 10, 10, 14, 14, 14}, cb_[9] = {0, 0, 0, 9, 9, 10, 0, 9, 10};
-    int a = 0, b = 0;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) if (lane == t) { a = ca_[t]; b = cb_[t]; }
+    const int a = ca_[lane], b = cb_[lane];
     cz = ZS + (a == 14 ? b : a);
     cy = a == 14 ? PP + 72 : YS + spj(b) * 8;
     ch = HS + a * (a + 1) / 2 + b;
   }
-  // ---- ownership map for the TRAILING update: t = lane + 32 r over the packed lower triangle of the 9 x 9 block
+  // ---- TRAILING update: t = lane + 32 r over the packed lower triangle of the 9 x 9 block (0xffff: no entry)
   int th[2], twa[2], twb[2], tp0[2], tp1[2];
-#pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = lane + 32 * r;
-    int a = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while (a * (a + 1) / 2 > t) --a;
-    while ((a + 1) * (a + 2) / 2 <= t) ++a;
-    const int b = t - a * (a + 1) / 2;
+    const int a = row_of(t), b = t - a * (a + 1) / 2;
     const bool valid = t < 44;                        // t == 44 is (rhs, rhs)
-    th[r] = valid ? HS + (a + 6) * (a + 7) / 2 + (b + 6) : -1;
+    th[r] = valid ? HS + (a + 6) * (a + 7) / 2 + (b + 6) : 0xffff;
     twa[r] = WS + (valid ? a : 0) * 6; twb[r] = WS + (valid ? b : 0) * 6;
-    tp0[r] = a == 8 ? PP + 72 + b : PP + a * 9 + b;
-    tp1[r] = a == 8 ? PP + 72 + b : PP + b * 9 + a;
+    tp0[r] = !valid ? PP : (a == 8 ? PP + 72 + b : PP + a * 9 + b);
+    tp1[r] = !valid ? PP : (a == 8 ? PP + 72 + b : PP + b * 9 + a);
+  }
+  auto pk = [](int lo, int hi) { return (unsigned)lo | ((unsigned)hi << 16); };
+  unsigned w[RIC_MAP_WORDS] = {pk(o0[0], o0[1]), pk(o0[2], o0[3]), pk(o1[0], o1[1]), pk(o1[2], o1[3]), pk(o2[0], o2[1]), pk(o2[2], o2[3]),
+                               pk(ymain[0], ymain[1]), pk(ymain[2], ymain[3]), pk(cz, cy), pk(ch, th[0]), pk(th[1], twa[0]),
+                               pk(twb[0], twa[1]), pk(twb[1], tp0[0]), pk(tp1[0], tp0[1]), pk(tp1[1], (int)codes)};
+  for (int i = 0; i < RIC_MAP_WORDS; ++i) out[i * 32 + lane] = w[i];
+}
+template <class L>
+__global__ void ric_map_kernel(unsigned* out) { ric_map_build<L>(threadIdx.x & 31, out); }
+
+template <class L>
+__device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, const unsigned* __restrict__ map, double mu, double dw, int lane) {
+  constexpr int S = L::S, N = L::N;
+  constexpr int PP = L::STG0 + SG_PP, ZS = L::STG0 + SG_Z, YS = L::STG0 + SG_Y, HS = L::STG0 + SG_H, WS = L::STG0 + SG_W, LS = L::STG0 + SG_L;
+  constexpr int LQ0 = L::LQ0;
+  unsigned w[RIC_MAP_WORDS];
+#pragma unroll
+  for (int i = 0; i < RIC_MAP_WORDS; ++i) w[i] = __ldg(map + i * 32 + lane);
+  auto lo16 = [](unsigned v) { return (int)(v & 0xffffu); };
+  auto hi16 = [](unsigned v) { return (int)(v >> 16); };
+  const int o0[4] = {lo16(w[0]), hi16(w[0]), lo16(w[1]), hi16(w[1])}, o1[4] = {lo16(w[2]), hi16(w[2]), lo16(w[3]), hi16(w[3])};
+  const int o2[4] = {lo16(w[4]), hi16(w[4]), lo16(w[5]), hi16(w[5])}, ymain[4] = {lo16(w[6]), hi16(w[6]), lo16(w[7]), hi16(w[7])};
+  const int cz = lo16(w[8]), cy = hi16(w[8]), ch = lo16(w[9]);
+  const int th[2] = {hi16(w[9]) == 0xffff ? -1 : hi16(w[9]), lo16(w[10]) == 0xffff ? -1 : lo16(w[10])};
+  const int twa[2] = {hi16(w[10]), hi16(w[11])}, twb[2] = {lo16(w[11]), lo16(w[12])};
+  const int tp0[2] = {hi16(w[12]), hi16(w[13])}, tp1[2] = {lo16(w[13]), lo16(w[14])};
+  const unsigned codes = w[14] >> 16;
+  double c3[4], cmain[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const unsigned cm = (codes >> (2 * m)) & 3u;
+    cmain[m] = cm == 0 ? 0.0 : (cm == 1 ? 1.0 : (cm == 2 ? T : T * T));
+    c3[m] = ((codes >> (8 + m)) & 1u) ? 1.0 : 0.0;
   }
 #pragma unroll 1
   for (int o = lane; o < 48; o += 32) smem[ZS + o] = 0.0;

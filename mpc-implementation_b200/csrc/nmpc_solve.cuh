@@ -43,6 +43,7 @@ struct SolveArgs {
   int* counter;                      // work queue
   unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
   double* ric; int ric_stride;       // L2-resident Riccati scratch, one slice per resident warp
+  const unsigned* ricmap;            // per-lane ownership maps of the factorisation (nmpc_riccati.cuh: ric_map_build)
   double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][8] (tests only)
   int align_group;                   // warps that start each IPM iteration together (0 = no alignment, else divides WPB)
   int align_quorum;                  // arrivals that release the alignment barrier (<= align_group)
@@ -710,7 +711,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
     ph_derivs<L>(A, lane, ls, df);
     if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
       ++n_fact;
-      const bool ok = riccati_factor<L>(T, ric, 1.0, 0.0, lane);
+      const bool ok = riccati_factor<L>(T, ric, A.ricmap, 1.0, 0.0, lane);
       if (ok) riccati_forward<L>(T, ric, false, lane, DX0, DU0);
       ph_lsy<L>(A, lane, ok);
       ls = false;
@@ -743,7 +744,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
     double dw = 0.0; bool ok = false;
     for (;;) {
       ++n_fact;
-      ok = riccati_factor<L>(T, ric, mu, dw, lane);
+      ok = riccati_factor<L>(T, ric, A.ricmap, mu, dw, lane);
       if (ok) break;
       if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, dw_last * o.dw_dec);
       else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
