@@ -314,7 +314,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   CK(cudaMalloc(&h->d_ricmap, sizeof(unsigned) * 32 * 16));
   {
     const int rc = h->inst->ricmap(h->d_ricmap, 0);
-    if (rc != 0) { return fail(std::string("nmpc_create: map kernel failed: ") + cudaGetErrorString((cudaError_t)rc)); }
+    if (rc != 0) { nmpc_destroy(h); return fail(std::string("nmpc_create: map kernel failed: ") + cudaGetErrorString((cudaError_t)rc)); }
     CK(cudaDeviceSynchronize());
   }
   CK(cudaMalloc(&h->d_counter, sizeof(int)));

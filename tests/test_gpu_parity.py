@@ -322,6 +322,28 @@ def test_full_size_other_configs(pkg, name, N, B, jitter):
     assert float(up[:, ~fu].amax() if (~fu).any() else 0.0) <= 1e-8 and float(lo[:, ~fl].amax() if (~fl).any() else 0.0) <= 1e-8
 
 
+def test_schedule_independence(pkg):
+    """The fetch order of the persistent kernel (nmpc_set_order / the library's longest-first order) and the lockstep
+    alignment of the warps of a block are pure scheduling: results are bit-identical whatever the order."""
+    sc = pkg.SCENARIOS["nmpc_tt"]
+    B = 1500                                           # more instances than resident warps -> the queue is used
+    dev = "cuda:0"
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, _ = pkg.random_instances(sc, B, seed=77)
+    T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    x0 = T(np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (B, sc.N))); pt = T(p)
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    args = dict(x0=x0, p=pt, lbx=T(lbx), ubx=T(ubx), lbg=T(lbg), ubg=T(ubg))
+    a = s(**args); sa = {k: v.clone() for k, v in s.stats().items()}                 # first call: natural order
+    b = s(**args); sb = {k: v.clone() for k, v in s.stats().items()}                 # second call: longest-first (auto)
+    perm = torch.randperm(B, device=dev)
+    c = s(order=perm, **args); sc_ = {k: v.clone() for k, v in s.stats().items()}     # explicit random order
+    for other, so in ((b, sb), (c, sc_)):
+        assert torch.equal(sa["return_status"], so["return_status"]) and torch.equal(sa["iter_count"], so["iter_count"])
+        for k in ("x", "f", "g", "lam_x", "lam_g"):
+            assert torch.equal(a[k], other[k]), k
+
+
 def test_edge_cases(pkg):
     sc = pkg.SCENARIOS["t_trajectory"]
     lbx, ubx, lbg, ubg = sc.bounds()
