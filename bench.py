@@ -284,7 +284,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=) with pinned numpy buffers -> nmpc_solve_host"},
-        "gpu_launches": (2 if args.no_lpt else 3) * K,     # [nmpc_order_kernel,] nmpc_ipm_kernel, nmpc_step_kernel per step
+        "gpu_launches": (3 if args.no_lpt else 4) * K,     # nmpc_relax_bounds_kernel, [nmpc_order_kernel,] nmpc_ipm_kernel, nmpc_step_kernel per step
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
                      "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "peak_source": which,
                      "bytes_per_solve": bytes_per_solve(sc.N, sc.n_obs),

@@ -177,6 +177,17 @@ struct StepArgs {
   const double* x_sol; double *p, *u_warm; const double* vw; double* fov;
 };
 
+// Relaxed bounds (IPOPT bound_relax_factor) of the batch-shared bound vectors, once per nmpc_solve call: the IPM
+// phases then load them instead of redoing the arithmetic per row and phase (nmpc_solve.cuh: ctl_bounds / row_bounds;
+// same intrinsics, so the values are bit-identical to the in-kernel formula used for scaled rows).
+__global__ void nmpc_relax_bounds_kernel(const double* __restrict__ lbx, const double* __restrict__ ubx,
+                                         const double* __restrict__ lbg, const double* __restrict__ ubg,
+                                         int nw, int ng, double relax, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) { out[i] = relaxed_lo(lbx[i], relax); out[nw + i] = relaxed_hi(ubx[i], relax); }
+  if (i < ng) { out[2 * nw + i] = relaxed_lo(lbg[i], relax); out[2 * nw + ng + i] = relaxed_hi(ubg[i], relax); }
+}
+
 // Longest-first fetch order for the persistent kernel from the previous call's iteration counts: counting sort,
 // descending, one block (B = 4096: ~10 us; the order inside a bin is arbitrary -- results do not depend on it).
 __global__ void __launch_bounds__(1024) nmpc_order_kernel(const int32_t* __restrict__ iters, int B, int32_t* __restrict__ order) {
@@ -243,6 +254,7 @@ struct nmpc_handle {
   Prob pr; Opt opt;
   const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
   double* d_ric; int ric_stride; unsigned* d_ricmap;
+  double* d_bnd;      // relaxed lbx | ubx | lbg | ubg of the current call
   int32_t *d_order, *d_keep_iters; int order_cap, prev_B, auto_order; const int32_t* order_next;
   const double* weights;
   int* d_counter; unsigned long long* d_stats;
@@ -317,6 +329,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     if (rc != 0) { nmpc_destroy(h); return fail(std::string("nmpc_create: map kernel failed: ") + cudaGetErrorString((cudaError_t)rc)); }
     CK(cudaDeviceSynchronize());
   }
+  CK(cudaMalloc(&h->d_bnd, sizeof(double) * 2 * (NU * h->pr.N + (size_t)h->pr.R * h->pr.S)));
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
   CK(cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));
@@ -342,7 +355,7 @@ int nmpc_destroy(nmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_ric, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
-                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order, h->d_keep_iters, h->d_ricmap};
+                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order, h->d_keep_iters, h->d_ricmap, h->d_bnd};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -375,12 +388,17 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
     CK(cudaMalloc(&h->d_order, sizeof(int32_t) * B)); CK(cudaMalloc(&h->d_keep_iters, sizeof(int32_t) * B));
     h->order_cap = B;
   }
+  {
+    const int nw = NU * h->pr.N, ng = h->pr.R * h->pr.S, n = nw > ng ? nw : ng;
+    nmpc_relax_bounds_kernel<<<(n + 127) / 128, 128, 0, s>>>(lbx, ubx, lbg, ubg, nw, ng, h->opt.bound_relax, h->d_bnd);
+    A.xlo_r = h->d_bnd; A.xhi_r = h->d_bnd + nw; A.glo_r = h->d_bnd + 2 * nw; A.ghi_r = h->d_bnd + 2 * nw + ng;
+  }
   A.iters_keep = h->d_keep_iters;
   A.order = h->order_next; h->order_next = nullptr;
-  h->launches = 1;
+  h->launches = 2;     // nmpc_relax_bounds_kernel + nmpc_ipm_kernel
   if (!A.order && h->auto_order && h->prev_B == B) {   // same batch as last time: start last time's longest solves first
     nmpc_order_kernel<<<1, 1024, 0, s>>>(h->d_keep_iters, B, h->d_order);
-    A.order = h->d_order; h->launches = 2;
+    A.order = h->d_order; h->launches = 3;
   }
   h->prev_B = B;
   A.weights = h->weights;

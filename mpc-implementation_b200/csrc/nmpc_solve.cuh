@@ -34,6 +34,8 @@ struct SolveArgs {
   Prob pr; Opt o;
   int B;
   const double *p, *x0, *lbx, *ubx, *lbg, *ubg, *obs;
+  const double *xlo_r, *xhi_r, *glo_r, *ghi_r;   // relaxed bounds (-inf / +inf = none), computed once per call by
+                                                 // nmpc_relax_bounds_kernel with relaxed_lo / relaxed_hi below; g: for d_c = 1
   int obs_per_instance;
   double *x, *f, *g, *lam_x, *lam_g;
   int32_t *status, *iters;
@@ -68,20 +70,24 @@ struct Bnd { double lo, hi; bool hl, hu; };
 // from contracting the expressions into FMAs differently per copy.  A bound that differs by one ulp between the
 // function that builds the Newton system and the one that updates the multipliers is a 1e-6 RELATIVE error of a
 // 1e-10 slack, i.e. a 1e-5 error in a multiplier -- enough to stall the end game (seen with v2).
+__device__ __forceinline__ double relaxed_lo(double lo, double relax) { return lo > -1e19 ? __dsub_rn(lo, __dmul_rn(relax, fmax(1.0, fabs(lo)))) : -CUDART_INF; }
+__device__ __forceinline__ double relaxed_hi(double hi, double relax) { return hi < 1e19 ? __dadd_rn(hi, __dmul_rn(relax, fmax(1.0, fabs(hi)))) : CUDART_INF; }
 __device__ __forceinline__ Bnd ctl_bounds(const SolveArgs& A, int k, int i) {
-  const double lo = __ldg(A.lbx + NU * k + i), hi = __ldg(A.ubx + NU * k + i);
-  Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
-  b.lo = b.hl ? __dsub_rn(lo, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(lo)))) : -CUDART_INF;
-  b.hi = b.hu ? __dadd_rn(hi, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(hi)))) : CUDART_INF;
+  Bnd b; b.lo = __ldg(A.xlo_r + NU * k + i); b.hi = __ldg(A.xhi_r + NU * k + i);
+  b.hl = b.lo > -CUDART_INF; b.hu = b.hi < CUDART_INF;
   return b;
 }
 template <class L>
 __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, double dc) {
-  const double lo = __ldg(A.lbg + k * L::R + r), hi = __ldg(A.ubg + k * L::R + r);
-  Bnd b; b.hl = lo > -1e19; b.hu = hi < 1e19;
-  const double l2 = __dmul_rn(dc, lo), h2 = __dmul_rn(dc, hi);
-  b.lo = b.hl ? __dsub_rn(l2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(l2)))) : -CUDART_INF;
-  b.hi = b.hu ? __dadd_rn(h2, __dmul_rn(A.o.bound_relax, fmax(1.0, fabs(h2)))) : CUDART_INF;
+  Bnd b;
+  if (dc == 1.0) {          // the usual case: the scaled row is the row, its relaxed bounds are batch-shared
+    b.lo = __ldg(A.glo_r + k * L::R + r); b.hi = __ldg(A.ghi_r + k * L::R + r);
+  } else {
+    const double lo = __ldg(A.lbg + k * L::R + r), hi = __ldg(A.ubg + k * L::R + r);
+    b.lo = relaxed_lo(lo > -1e19 ? __dmul_rn(dc, lo) : lo, A.o.bound_relax);
+    b.hi = relaxed_hi(hi < 1e19 ? __dmul_rn(dc, hi) : hi, A.o.bound_relax);
+  }
+  b.hl = b.lo > -CUDART_INF; b.hu = b.hi < CUDART_INF;
   return b;
 }
 
