@@ -137,6 +137,12 @@ int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order);
  * nmpc_eval on this handle (it must stay allocated and hold at least B rows); NULL restores spec.w1 / spec.w2. */
 int nmpc_set_weights(nmpc_handle* h, const double* dev_weights);
 
+/* Predicted target trajectory (north star: "p = [UAV state; predicted target trajectory]").  The reference
+ * holds the target at p[8:10] over the whole horizon (NMPC_TT.py:219-220); with dev_targets [B][N][2] = (x_t, y_t) of
+ * stage k = 0..N-1 every stage cost uses its own prediction instead.  Read by every subsequent nmpc_solve /
+ * nmpc_solve_host / nmpc_eval on this handle (must stay allocated, at least B rows); NULL restores p[8:10]. */
+int nmpc_set_target_trajectory(nmpc_handle* h, const double* dev_targets);
+
 /* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
  * dev_buf [B][rows][8] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials}; NULL disables. */
 int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);

@@ -32,7 +32,7 @@ class NmpcStats(C.Structure):
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_eval", "nmpc_step",
-           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
            "nmpc_last_error", "nmpc_version"]
 
 _lib = None
@@ -64,6 +64,7 @@ def lib():
     L.nmpc_set_debug_log.argtypes = [vp, vp, C.c_int32]
     L.nmpc_set_order.argtypes = [vp, vp]
     L.nmpc_set_weights.argtypes = [vp, vp]
+    L.nmpc_set_target_trajectory.argtypes = [vp, vp]
     L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
     L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]

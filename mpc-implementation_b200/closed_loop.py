@@ -23,9 +23,12 @@ from .scenarios import NP, Scenario
 
 class ClosedLoop:
     def __init__(self, solver: Solver, scenario: Scenario, p0, target_vw=None, device: Optional[str] = None,
-                 phase=None):
+                 phase=None, predict_target: bool = False):
         """p0 [B,11] initial [state; target]; target_vw [B,2] constant per-instance target (v, omega) or None to
-        follow scenario.schedule(mpc_iter + phase[b])."""
+        follow scenario.schedule(mpc_iter + phase[b]).  predict_target: hand the solver the target's own Euler
+        prediction over the horizon (same model as the target step of shift_timestep, NMPC_TT.py:24-27) instead of
+        the frozen target the reference uses."""
+        self.predict_target = predict_target
         self.solver, self.sc = solver, scenario
         dev = device or f"cuda:{solver.device}"
         self.p = torch.as_tensor(np.asarray(p0, dtype=np.float64), device=dev).reshape(-1, NP).contiguous().clone()
@@ -56,6 +59,15 @@ class ClosedLoop:
             vw = np.array([self.sc.schedule(self.mpc_iter + int(ph)) for ph in self.phase], dtype=np.float64)
             self.vw.copy_(torch.from_numpy(vw))
 
+    def target_prediction(self):
+        """[B, N, 2]: x_t, y_t of stages 0..N-1 under theta_{k+1} = theta_k + T w, (x, y)_{k+1} = (x, y)_k + T v (cos, sin)(theta_k)."""
+        N, T = self.sc.N, self.sc.T
+        k = torch.arange(N, dtype=torch.float64, device=self.p.device)
+        th = self.p[:, 10:11] + T * self.vw[:, 1:2] * k[None, :]                        # theta at stage k
+        step = T * self.vw[:, 0:1, None] * torch.stack([torch.cos(th), torch.sin(th)], dim=2)
+        pos = self.p[:, None, 8:10] + torch.cumsum(step, dim=1) - step                   # exclusive prefix sum
+        return pos.contiguous()
+
     def next_order(self):
         """Explicit longest-first fetch order (previous iteration counts, descending) for `solver(order=)`.  The
         library does the same by itself for consecutive calls with equal B (include/nmpc_b200.h, "Scheduling"), so
@@ -71,7 +83,8 @@ class ClosedLoop:
         self._schedule_vw()
         target_before = self.p[:, 8:10].clone()
         sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg,
-                          want_g=want_g, want_lam=want_lam)
+                          want_g=want_g, want_lam=want_lam,
+                          target_traj=self.target_prediction() if self.predict_target else None)
         self.solver.step(sol["x"], self.p, self.u_warm, self.vw, self.fov)
         # error[i] = || FOVcentre_{i+1} - target_i ||   (NMPC_TT.py:435)
         self.err_sum += torch.linalg.vector_norm(self.fov - target_before, dim=1)

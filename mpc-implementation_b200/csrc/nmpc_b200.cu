@@ -37,7 +37,7 @@ static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_IN
 struct EvalArgs {
   Prob pr; int B;
   const double *w, *p, *obs; int obs_per_instance;
-  const double* weights;
+  const double *weights, *tgt;
   double sigma; const double *lam, *v;
   double *f, *g, *grad, *jtv, *hv;
 };
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
   double X0[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) X0[i] = pp[i];
-  const double xt = pp[8], yt = pp[9];
+  const double xt = (A.tgt && hasu) ? A.tgt[((size_t)b * N + lane) * 2] : pp[8];
+  const double yt = (A.tgt && hasu) ? A.tgt[((size_t)b * N + lane) * 2 + 1] : pp[9];
   double u[6], vv[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) { u[i] = hasu ? A.w[(size_t)b * nw + NU * lane + i] : 0.0; vv[i] = (hasu && A.v) ? A.v[(size_t)b * nw + NU * lane + i] : 0.0; }
@@ -256,7 +257,7 @@ struct nmpc_handle {
   double* d_ric; int ric_stride; unsigned* d_ricmap;
   double* d_bnd;      // relaxed lbx | ubx | lbg | ubg of the current call
   int32_t *d_order, *d_keep_iters; int order_cap, prev_B, auto_order; const int32_t* order_next;
-  const double* weights;
+  const double *weights, *tgt;
   int* d_counter; unsigned long long* d_stats;
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
@@ -394,6 +395,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
     A.xlo_r = h->d_bnd; A.xhi_r = h->d_bnd + nw; A.glo_r = h->d_bnd + 2 * nw; A.ghi_r = h->d_bnd + 2 * nw + ng;
   }
   A.iters_keep = h->d_keep_iters;
+  A.tgt = h->tgt;
   A.order = h->order_next; h->order_next = nullptr;
   h->launches = 2;     // nmpc_relax_bounds_kernel + nmpc_ipm_kernel
   if (!A.order && h->auto_order && h->prev_B == B) {   // same batch as last time: start last time's longest solves first
@@ -460,7 +462,7 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
   CK(cudaSetDevice(h->device));
   EvalArgs A;
   A.pr = h->pr; A.B = B; A.w = w; A.p = p; A.obs = obst; A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
-  A.weights = h->weights;
+  A.weights = h->weights; A.tgt = h->tgt;
   A.sigma = sigma; A.lam = lam; A.v = v; A.f = f; A.g = g; A.grad = grad_f; A.jtv = jtv; A.hv = hv;
   const int warps = 4;
   nmpc_eval_kernel<<<(B + warps - 1) / warps, warps * 32, 0, (cudaStream_t)cuda_stream>>>(A);
@@ -491,6 +493,12 @@ int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order) {
 int nmpc_set_weights(nmpc_handle* h, const double* dev_weights) {
   if (!h) return fail("nmpc_set_weights: null handle");
   h->weights = dev_weights;
+  return 0;
+}
+
+int nmpc_set_target_trajectory(nmpc_handle* h, const double* dev_targets) {
+  if (!h) return fail("nmpc_set_target_trajectory: null handle");
+  h->tgt = dev_targets;
   return 0;
 }
 

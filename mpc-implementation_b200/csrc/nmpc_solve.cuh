@@ -40,6 +40,7 @@ struct SolveArgs {
   double *x, *f, *g, *lam_x, *lam_g;
   int32_t *status, *iters;
   const double* weights;             // optional per-instance cost weights [B][2] = (w1, w2); NULL = spec weights
+  const double* tgt;                 // optional per-instance, per-stage predicted target [B][N][2]; NULL = p[8:10]
   int32_t* iters_keep;               // handle-owned copy of iters[] (drives the next call's fetch order)
   const int32_t* order;              // optional processing order (longest-first scheduling); NULL = 0..B-1
   int* counter;                      // work queue
@@ -161,6 +162,15 @@ __device__ __forceinline__ double obs_value(const double* X, int jn, double& nx,
     }                                                                                               \
   } while (0)
 
+// target position seen by this lane's stage: the reference keeps (x_t, y_t) = p[8:10] over the horizon
+// (NMPC_TT.py:219-220); with a predicted trajectory (nmpc_set_target_trajectory) stage k has its own
+template <class L>
+__device__ __forceinline__ double2 stage_target(const SolveArgs& A, int lane) {
+  if (!A.tgt || lane >= L::N) return make_double2(PAR(8), PAR(9));
+  const double* t = A.tgt + ((size_t)PAR(NPAR + 2) * L::N + lane) * 2;
+  return make_double2(__ldg(t), __ldg(t + 1));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // load one instance: p -> PAR, warm start -> LV_U, obstacle table, unit scaling
 template <class L>
@@ -168,6 +178,7 @@ __device__ __noinline__ void ph_load(const SolveArgs& A, int b, int lane) {
   if (lane < NPAR) PAR(lane) = A.p[(size_t)b * NPAR + lane];
   if (lane == NPAR) PAR(NPAR) = A.weights ? A.weights[2 * (size_t)b] : A.pr.w1;
   if (lane == NPAR + 1) PAR(NPAR + 1) = A.weights ? A.weights[2 * (size_t)b + 1] : A.pr.w2;
+  if (lane == NPAR + 2) PAR(NPAR + 2) = (double)b;      // instance index, for the per-stage target lookup
   const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * L::NOBS : 0);
   for (int i = lane; i < 3 * L::NOBS; i += 32) smem[L::OBS0 + i] = ob[i];
   if (lane <= L::N) {
@@ -194,7 +205,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.0;
   if (hasu && lane >= 1) {
-    stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9), gl, Hl);
+    stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y, gl, Hl);
 #pragma unroll
     for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
   }
@@ -302,7 +313,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
 #pragma unroll
   for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
   double l = 0.0;
-  if (hasu) l = stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9), gl, Hl);
+  if (hasu) l = stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y, gl, Hl);
   if (lane == 0) {   // stage 0 is constant in w
 #pragma unroll
     for (int v = 0; v < 6; ++v) gl[v] = 0.0;
@@ -531,7 +542,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     }
   }
   Stage st; rollout(pr, &PAR(0), ut, lane, st);
-  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9)) : 0.0;
+  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y) : 0.0;
   double th = 0.0;
   if (act) {
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
@@ -653,7 +664,7 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
     }
   }
   Stage st; rollout(pr, &PAR(0), u, lane, st);
-  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, PAR(8), PAR(9)) : 0.0;
+  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y) : 0.0;
   const double fu = warp_sum(l);
   if (lane == 0) {
     if (A.f) A.f[b] = fu;

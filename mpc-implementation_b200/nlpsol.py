@@ -121,17 +121,44 @@ class Solver:
 
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, obstacles=None,
-                 want_g: bool = True, want_lam: bool = True, order=None, weights=None):
+                 want_g: bool = True, want_lam: bool = True, order=None, weights=None, target_traj=None):
         """weights: optional [B, 2] per-instance cost weights (w1, w2) for this call (numpy or CUDA tensor); the
-        reference edits them in source (NMPC_TT.py:204-205) and its MATLAB outer loop sweeps them (MPC.m:90)."""
+        reference edits them in source (NMPC_TT.py:204-205) and its MATLAB outer loop sweeps them (MPC.m:90).
+        target_traj: optional [B, N, 2] predicted target positions per stage (default: p[8:10] for every stage, as
+        in the reference)."""
         if p is None:
             raise ValueError("solver: p is required")
         if any(v is None for v in (lbx, ubx, lbg, ubg)):
             raise ValueError("solver: lbx, ubx, lbg, ubg are required (the reference passes all four)")
-        with self._weights(weights, p):
+        with self._weights(weights, p), self._traj(target_traj, p):
             if _is_cuda_tensor(p):
                 return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order)
             return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+
+    def _traj(self, traj, p):
+        """Context manager: nmpc_set_target_trajectory for the duration of one call."""
+        import contextlib
+        if traj is None:
+            return contextlib.nullcontext()
+        B = int(p.shape[0]) if (hasattr(p, "shape") and len(p.shape) == 2 and p.shape[1] == NP) else 1
+        t = torch.as_tensor(traj if _is_cuda_tensor(traj) else np.asarray(traj, dtype=np.float64),
+                            dtype=torch.float64, device=f"cuda:{self.device}").reshape(-1, self.N, 2).contiguous()
+        if t.shape[0] != B:
+            raise ValueError("solver: target_traj must be [B, N, 2]")
+        L = _ffi.lib()
+
+        @contextlib.contextmanager
+        def cm():
+            if B > self._max_batch:
+                self._create(max(B, 2 * self._max_batch))
+            _ffi.check(L.nmpc_set_target_trajectory(self._h, t.data_ptr()), "nmpc_set_target_trajectory")
+            try:
+                yield
+            finally:
+                if _is_cuda_tensor(p):
+                    self._keep_t = t
+                L.nmpc_set_target_trajectory(self._h, None)
+        return cm()
 
     def _weights(self, weights, p):
         """Context manager: nmpc_set_weights for the duration of one call."""
@@ -253,9 +280,10 @@ class Solver:
                     soc_accepted=st.soc_accepted)
 
     # -- function-level evaluation (nlp_f / nlp_g / nlp_grad_f / nlp_hess_l of the reference's nlpsol) ----
-    def evaluate(self, w, p, lam=None, v=None, sigma: float = 1.0, obstacles=None, weights=None):
-        if weights is not None:
-            with self._weights(weights, np.asarray(p) if not _is_cuda_tensor(p) else p):
+    def evaluate(self, w, p, lam=None, v=None, sigma: float = 1.0, obstacles=None, weights=None, target_traj=None):
+        if weights is not None or target_traj is not None:
+            pp = np.asarray(p) if not _is_cuda_tensor(p) else p
+            with self._weights(weights, pp), self._traj(target_traj, pp):
                 return self.evaluate(w, p, lam=lam, v=v, sigma=sigma, obstacles=obstacles)
         L = _ffi.lib()
         dev = f"cuda:{self.device}"

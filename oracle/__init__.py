@@ -45,6 +45,8 @@ def lib():
         _lib.oracle_eval.restype = C.c_int
         _lib.oracle_solve.restype = C.c_int
         _lib.oracle_solve_log.restype = C.c_int
+        _lib.oracle_eval_traj.restype = C.c_int
+        _lib.oracle_solve_traj.restype = C.c_int
     return _lib
 
 
@@ -71,7 +73,7 @@ def obstacle_table(obstacles, uav_r=5.0) -> np.ndarray:
     return o
 
 
-def evaluate(spec: OracleSpec, obs: np.ndarray, w, p, lam_g=None, sigma=1.0, hessian=False):
+def evaluate(spec: OracleSpec, obs: np.ndarray, w, p, lam_g=None, sigma=1.0, hessian=False, target_traj=None):
     N, n_obs = spec.N, spec.n_obs
     nw, ng = 6 * N, (5 + n_obs) * (N + 1)
     w, p, obs = _c(w), _c(p), _c(obs)
@@ -79,13 +81,14 @@ def evaluate(spec: OracleSpec, obs: np.ndarray, w, p, lam_g=None, sigma=1.0, hes
     g = np.zeros(ng); grad = np.zeros(nw); J = np.zeros((ng, nw)); X = np.zeros((N + 1, 8))
     H = np.zeros((nw, nw)) if hessian else None
     lam = _c(lam_g) if lam_g is not None else np.zeros(ng)
-    lib().oracle_eval(C.byref(spec), _dp(obs), _dp(w), _dp(p), C.c_double(sigma), _dp(lam),
-                      C.byref(f), _dp(g), _dp(grad), _dp(J), _dp(H), _dp(X))
+    tg = None if target_traj is None else _c(target_traj).reshape(N, 2)     # per-stage predicted target
+    lib().oracle_eval_traj(C.byref(spec), _dp(obs), _dp(w), _dp(p), _dp(tg), C.c_double(sigma), _dp(lam),
+                           C.byref(f), _dp(g), _dp(grad), _dp(J), _dp(H), _dp(X))
     return dict(f=f.value, g=g, grad=grad, J=J, H=H, X=X)
 
 
 def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=False, scaling=True,
-          max_iter=0, tol=0.0, nthreads=None, want_g=True, want_lam=True):
+          max_iter=0, tol=0.0, nthreads=None, want_g=True, want_lam=True, target_traj=None):
     """Batch solve: p (B,11), x0 (B,6N) -> dict(x,f,g,lam_x,lam_g,status,iters,stats)."""
     N, n_obs = spec.N, spec.n_obs
     nw, ng = 6 * N, (5 + n_obs) * (N + 1)
@@ -101,7 +104,8 @@ def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=
     status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32); stats = np.zeros((B, 4), dtype=np.int32)
     if nthreads is None:
         nthreads = min(B, os.cpu_count() or 1)
-    lib().oracle_solve(C.byref(spec), C.c_int(B), _dp(p), _dp(x0), _dp(lbx), _dp(ubx), _dp(lbg), _dp(ubg),
+    tg = None if target_traj is None else _c(target_traj).reshape(B, N, 2)
+    lib().oracle_solve_traj(C.byref(spec), C.c_int(B), _dp(p), _dp(x0), _dp(tg), _dp(lbx), _dp(ubx), _dp(lbg), _dp(ubg),
                        _dp(obs), C.c_int(int(obs_per_instance)), C.c_int(int(scaling)), C.c_int(int(max_iter)),
                        C.c_double(float(tol)),
                        _dp(x), _dp(f), _dp(g), _dp(lam_x), _dp(lam_g), _ip(status), _ip(iters), _ip(stats),

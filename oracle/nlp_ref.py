@@ -76,8 +76,9 @@ def rollout(spec: RefSpec, w: torch.Tensor, p: torch.Tensor) -> List[torch.Tenso
     return X
 
 
-def objective(spec: RefSpec, w: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
-    """Literal transcription of NMPC_TT.py:193-221."""
+def objective(spec: RefSpec, w: torch.Tensor, p: torch.Tensor, target_traj: torch.Tensor | None = None) -> torch.Tensor:
+    """Literal transcription of NMPC_TT.py:193-221.  target_traj [N, 2] (optional) replaces the constant
+    target (p[8], p[9]) by a per-stage prediction; the reference itself keeps the target fixed over the horizon."""
     X = rollout(spec, w, p)
     obj = torch.zeros((), dtype=w.dtype)
     VFOV, HFOV = spec.vfov, spec.hfov
@@ -90,8 +91,9 @@ def objective(spec: RefSpec, w: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
         C = (torch.sin(st[7])) ** 2 / a ** 2 + (torch.cos(st[7])) ** 2 / b ** 2
         X_E = st[0] + a + st[2] * torch.tan(st[6] - VFOV / 2)
         Y_E = st[1] + b + st[2] * torch.tan(st[5] - HFOV / 2)
-        obj = obj + spec.w1 * torch.sqrt((st[0] - p[8]) ** 2 + (st[1] - p[9]) ** 2) + \
-            spec.w2 * ((A * (p[8] - X_E) ** 2 + B * (p[9] - Y_E) * (p[8] - X_E) + C * (p[9] - Y_E) ** 2) - 1)
+        xt, yt = (p[8], p[9]) if target_traj is None else (target_traj[k, 0], target_traj[k, 1])
+        obj = obj + spec.w1 * torch.sqrt((st[0] - xt) ** 2 + (st[1] - yt) ** 2) + \
+            spec.w2 * ((A * (xt - X_E) ** 2 + B * (yt - Y_E) * (xt - X_E) + C * (yt - Y_E) ** 2) - 1)
     return obj
 
 
@@ -131,11 +133,13 @@ def bounds(spec: RefSpec):
     return lbx, ubx, lbg, ubg
 
 
-def eval_all(spec: RefSpec, w: np.ndarray, p: np.ndarray, lam_g: np.ndarray | None = None, sigma: float = 1.0):
+def eval_all(spec: RefSpec, w: np.ndarray, p: np.ndarray, lam_g: np.ndarray | None = None, sigma: float = 1.0,
+             target_traj: np.ndarray | None = None):
     """f, g, grad f, J, and (if lam_g given) Hessian of sigma*f + lam_g^T g -- all by autograd."""
     wt = torch.tensor(np.asarray(w, dtype=np.float64), requires_grad=True)
     pt = torch.tensor(np.asarray(p, dtype=np.float64))
-    f = objective(spec, wt, pt)
+    tt = None if target_traj is None else torch.tensor(np.asarray(target_traj, dtype=np.float64)).reshape(spec.N, 2)
+    f = objective(spec, wt, pt, tt)
     g = constraints(spec, wt, pt)
     grad = torch.autograd.grad(f, wt, retain_graph=True)[0]
     J = torch.autograd.functional.jacobian(lambda ww: constraints(spec, ww, pt), wt)
@@ -143,7 +147,7 @@ def eval_all(spec: RefSpec, w: np.ndarray, p: np.ndarray, lam_g: np.ndarray | No
     if lam_g is not None:
         lt = torch.tensor(np.asarray(lam_g, dtype=np.float64))
         H = torch.autograd.functional.hessian(
-            lambda ww: sigma * objective(spec, ww, pt) + (lt * constraints(spec, ww, pt)).sum(), wt)
+            lambda ww: sigma * objective(spec, ww, pt, tt) + (lt * constraints(spec, ww, pt)).sum(), wt)
         out["H"] = H.numpy()
     return out
 

@@ -164,6 +164,11 @@ struct Instance {
   std::vector<Jet<2>> obsj;     // (N+1) x n_obs
   std::vector<Jet<3>> dyn;      // N x 3   (theta, psi, v) -> T*rhs rows 0..2
 
+  // optional per-stage predicted target [N][2] (the reference keeps (x_t, y_t) = p[8:10] over the horizon)
+  const double* tgt = nullptr;
+  double xt(int k) const { return tgt ? tgt[2 * k] : p[8]; }
+  double yt(int k) const { return tgt ? tgt[2 * k + 1] : p[9]; }
+
   Instance(const Spec& s, const double* p_, const double* obs_) : sp(s), p(p_), obs(obs_) {
     nw = sp.nw(); ng = sp.ng(); rows = sp.rows();
     X.resize((sp.N + 1) * NX);
@@ -190,7 +195,7 @@ struct Instance {
     double f = 0;
     for (int k = 0; k < sp.N; ++k) {
       const double* st = &X[k * NX];
-      f += stage_cost_literal<D>(sp, st[0], st[1], st[2], st[5], st[6], st[7], p[8], p[9], dtan, dsin, dcos, dsqrt, dsq).v;
+      f += stage_cost_literal<D>(sp, st[0], st[1], st[2], st[5], st[6], st[7], xt(k), yt(k), dtan, dsin, dcos, dsqrt, dsq).v;
     }
     for (int k = 0; k <= sp.N; ++k) {
       const double* st = &X[k * NX]; double* gk = g + k * rows;
@@ -211,7 +216,7 @@ struct Instance {
       const double* st = &X[k * NX];
       J6 v[6];
       for (int i = 0; i < 6; ++i) v[i] = J6::var(st[COST_IDX[i]], i);
-      cost[k] = stage_cost_literal<J6>(sp, v[0], v[1], v[2], v[3], v[4], v[5], p[8], p[9], j6tan, j6sin, j6cos, j6sqrt, j6sq);
+      cost[k] = stage_cost_literal<J6>(sp, v[0], v[1], v[2], v[3], v[4], v[5], xt(k), yt(k), j6tan, j6sin, j6cos, j6sqrt, j6sq);
       Jet<3> th = Jet<3>::var(st[3], 0), ps = Jet<3>::var(st[4], 1), vv = Jet<3>::var(w[NU * k], 2);
       dyn[k * 3 + 0] = sp.T * (vv * jcos(ps) * jcos(th));
       dyn[k * 3 + 1] = sp.T * (vv * jsin(ps) * jcos(th));
@@ -766,10 +771,19 @@ struct oracle_spec { double T; int32_t N; int32_t n_obs; double w1, w2, vfov, hf
 static Spec to_spec(const oracle_spec* s) { return Spec{s->T, s->N, s->n_obs, s->w1, s->w2, s->vfov, s->hfov}; }
 
 // function-level evaluation at (w, p): any output pointer may be NULL
+int oracle_eval_traj(const oracle_spec* spec, const double* obs, const double* w, const double* p, const double* tgt,
+                     double sigma, const double* lam_g,
+                     double* f, double* g, double* grad, double* J, double* H, double* X);
 int oracle_eval(const oracle_spec* spec, const double* obs, const double* w, const double* p,
                 double sigma, const double* lam_g,
                 double* f, double* g, double* grad, double* J, double* H, double* X) {
-  Spec sp = to_spec(spec); Instance I(sp, p, obs);
+  return oracle_eval_traj(spec, obs, w, p, nullptr, sigma, lam_g, f, g, grad, J, H, X);
+}
+// same with a per-stage target trajectory tgt [N][2] (NULL = p[8:10] for every stage)
+int oracle_eval_traj(const oracle_spec* spec, const double* obs, const double* w, const double* p, const double* tgt,
+                     double sigma, const double* lam_g,
+                     double* f, double* g, double* grad, double* J, double* H, double* X) {
+  Spec sp = to_spec(spec); Instance I(sp, p, obs); I.tgt = tgt;
   std::vector<double> gg(I.ng);
   double fv = I.eval_fg(w, gg.data());
   if (f) *f = fv;
@@ -787,11 +801,25 @@ int oracle_eval(const oracle_spec* spec, const double* obs, const double* w, con
 // batch solve.  Instance-major arrays: p [B][11], x0 [B][nw], outputs x [B][nw], f [B], g [B][ng], ...
 // bounds shared ([nw], [ng]).  obs: [n_obs][3] shared (obs_per_instance=0) or [B][n_obs][3].
 // stats (optional) [B][4] : n_fact, n_soc_accepted, 0, 0
+int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const double* x0, const double* tgt,
+                      const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                      const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
+                      double* x, double* f, double* g, double* lam_x, double* lam_g,
+                      int32_t* status, int32_t* iters, int32_t* stats, int nthreads);
 int oracle_solve(const oracle_spec* spec, int B, const double* p, const double* x0,
                  const double* lbx, const double* ubx, const double* lbg, const double* ubg,
                  const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
                  double* x, double* f, double* g, double* lam_x, double* lam_g,
                  int32_t* status, int32_t* iters, int32_t* stats, int nthreads) {
+  return oracle_solve_traj(spec, B, p, x0, nullptr, lbx, ubx, lbg, ubg, obs, obs_per_instance, scaling, max_iter, tol,
+                           x, f, g, lam_x, lam_g, status, iters, stats, nthreads);
+}
+// same with per-instance, per-stage target trajectories tgt [B][N][2] (NULL = p[8:10] for every stage)
+int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const double* x0, const double* tgt,
+                      const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                      const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
+                      double* x, double* f, double* g, double* lam_x, double* lam_g,
+                      int32_t* status, int32_t* iters, int32_t* stats, int nthreads) {
   Spec sp = to_spec(spec); const int nw = sp.nw(), ng = sp.ng();
   if (nthreads < 1) nthreads = 1;
   std::atomic<int> next(0);
@@ -800,6 +828,7 @@ int oracle_solve(const oracle_spec* spec, int B, const double* p, const double* 
       int b = next.fetch_add(1); if (b >= B) break;
       const double* ob = obs + (obs_per_instance ? (size_t)b * sp.n_obs * 3 : 0);
       Instance I(sp, p + (size_t)b * NPAR, ob);
+      if (tgt) I.tgt = tgt + (size_t)b * 2 * sp.N;
       Options o; o.scaling = scaling; if (max_iter > 0) o.max_iter = max_iter; if (tol > 0) o.tol = tol;
       Ipm ipm(I, o);
       std::vector<double> xo(nw);

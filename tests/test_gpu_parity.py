@@ -156,6 +156,49 @@ def test_per_instance_weights(pkg, oracle_mod):
     assert not np.allclose(sol2["f"][~k0], sol["f"][~k0], rtol=1e-3)
 
 
+def test_predicted_target_trajectory(pkg, oracle_mod):
+    """SURVEY 8f-2 / north star "p = [UAV state; predicted target trajectory]": per-stage target positions."""
+    sc = pkg.SCENARIOS["t_trajectory"]
+    B = 24
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, vw = pkg.random_instances(sc, B, seed=41)
+    x0 = np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (B, sc.N))
+    k = np.arange(sc.N)[None, :, None]
+    head = np.stack([np.cos(p[:, 10] + 0.0), np.sin(p[:, 10])], axis=1)[:, None, :]
+    traj = p[:, None, 8:10] + sc.T * k * vw[:, None, 0:1] * head            # constant-velocity prediction [B, N, 2]
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    ref = oracle_mod.solve(sp, sc.obstacle_table(), p, x0, lbx, ubx, lbg, ubg, target_traj=traj)
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    sol = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, target_traj=traj)
+    st = s.stats()
+    assert (ref["status"] == st["return_status"]).mean() >= 0.9
+    both = (ref["status"] == 0) & (st["return_status"] == 0)
+    assert both.sum() >= 18
+    r2 = {q: ref[q][both] for q in ("x", "f", "g")}; r2["status"] = ref["status"][both]
+    _compare(r2, {q: sol[q][both] for q in ("x", "f", "g")}, st["return_status"][both], st["iter_count"][both], (lbx, ubx, lbg, ubg))
+    ev = s.evaluate(sol["x"], p, target_traj=traj)
+    for j in range(3):
+        fo = oracle_mod.evaluate(sp, sc.obstacle_table(), sol["x"][j], p[j], target_traj=traj[j])
+        assert abs(float(ev["f"][j]) - fo["f"]) <= 1e-12 * abs(fo["f"])
+        assert np.allclose(ev["grad"][j].cpu().numpy(), fo["grad"], rtol=1e-8, atol=1e-9 * np.abs(fo["grad"]).max())
+    # the prediction changes the problem (a moving target is not the frozen one) and applies to that call only
+    base = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    assert not np.allclose(base["f"], sol["f"], rtol=1e-3)
+    frozen = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, target_traj=np.tile(p[:, None, 8:10], (1, sc.N, 1)))
+    assert np.array_equal(frozen["x"], base["x"]) and np.array_equal(frozen["f"], base["f"])
+    # closed loop with the target's own prediction: tracks at least as well as the frozen-target loop of the reference
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    errs = []
+    for pred in (False, True):
+        cl = ClosedLoop(pkg.nlpsol("solver", "ipm", sc, max_batch=B), sc, p, target_vw=vw, predict_target=pred)
+        if pred:      # stage 0 of the prediction is the current target
+            assert torch.equal(cl.target_prediction()[:, 0, :], cl.p[:, 8:10])
+        for _ in range(25):
+            cl.step()
+        errs.append(float(cl.err_sum.mean()))
+    assert errs[1] <= 1.05 * errs[0], errs
+
+
 def test_function_level(pkg, oracle_mod):
     """nmpc_eval (f, g, grad f, J^T lam, Hess_L v) vs the oracle's dense derivatives."""
     for name in ("nmpc_tt", "race_track_2"):

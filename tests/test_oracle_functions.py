@@ -38,6 +38,26 @@ def test_oracle_matches_autograd(oracle_mod, name):
         assert np.abs(a - b).max() <= tol * max(1.0, np.abs(a).max()), key
 
 
+@pytest.mark.parametrize("name", ["nmpc_tt", "short"])
+def test_oracle_matches_autograd_with_target_trajectory(oracle_mod, name):
+    """per-stage predicted target instead of the constant (p[8], p[9])."""
+    rs = SPECS[name]
+    sp = oracle_mod.make_spec(rs.T, rs.N, rs.n_obs, rs.w1, rs.w2, rs.vfov, rs.hfov)
+    obs = oracle_mod.obstacle_table(rs.obstacles, rs.uav_r)
+    w, p, lam = _point(rs, 19)
+    k = np.arange(rs.N)[:, None]
+    traj = np.array([p[8], p[9]]) + rs.T * k * np.array([[9.0, -4.0]]) + 0.3 * np.sin(k)        # a curved prediction
+    ref = nlp_ref.eval_all(rs, w, p, lam, 0.6, target_traj=traj)
+    got = oracle_mod.evaluate(sp, obs, w, p, lam, 0.6, hessian=True, target_traj=traj)
+    for key, tol in [("f", 1e-13), ("g", 1e-13), ("grad", 1e-12), ("J", 1e-12), ("H", 1e-11)]:
+        a, b = np.asarray(ref[key]), np.asarray(got[key])
+        assert np.abs(a - b).max() <= tol * max(1.0, np.abs(a).max()), key
+    # a trajectory that repeats p[8:10] is the reference problem
+    same = oracle_mod.evaluate(sp, obs, w, p, lam, 0.6, hessian=True, target_traj=np.tile(p[8:10], (rs.N, 1)))
+    base = oracle_mod.evaluate(sp, obs, w, p, lam, 0.6, hessian=True)
+    assert same["f"] == base["f"] and np.array_equal(same["H"], base["H"])
+
+
 def test_gradient_against_central_differences(oracle_mod):
     rs = SPECS["t02"]
     sp = oracle_mod.make_spec(rs.T, rs.N, rs.n_obs)
