@@ -250,6 +250,14 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); which = "of measured" if "hbm_gbs" in peaks else "of fallback"
+    traffic_src = None
+    traffic = None       # measured DRAM bytes of one launch of this configuration, from the committed ncu capture
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"{sc.N}_{sc.n_obs}_{B}")
+        if t:
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]; traffic_src = t["source"]
+    except Exception:
+        pass
     ach_gbs = bytes_per_solve(sc.N, sc.n_obs) * B / (k_ms * 1e-3) / 1e9
     ach_tf = flops_step / (k_ms * 1e-3) / 1e12
 
@@ -285,7 +293,8 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=) with pinned numpy buffers -> nmpc_solve_host"},
         "gpu_launches": (3 if args.no_lpt else 4) * K,     # nmpc_relax_bounds_kernel, [nmpc_order_kernel,] nmpc_ipm_kernel, nmpc_step_kernel per step
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": bytes_per_solve(sc.N, sc.n_obs) * B,
                      "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "peak_source": which,
                      "bytes_per_solve": bytes_per_solve(sc.N, sc.n_obs),
                      "note": "not HBM-bound by design (SURVEY 8d): the limiter is the FP64 dependency chain; see fp64"},
