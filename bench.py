@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
                                        "(CasADi/IPOPT itself is unavailable in this image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "converged_fraction": conv / (B * args.steps), "mean_iters": iters_sum / (B * args.steps)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -303,7 +303,7 @@ def run_b200(args, rank, world, local_rank):
                  "iters": it_step, "factorizations": wc["factorizations"], "ls_trials": wc["ls_trials"]},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
@@ -315,7 +315,25 @@ def ctypes_fp64_peak(b200nmpc, device):
     return float(v.value) if rc == 0 else None
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to stdout (NCCL's "NCCL version ..." banner at init): send fd 1 to stderr for the duration of the
+    # run and keep the real stdout for the JSON line, so that stdout carries exactly one line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
