@@ -65,7 +65,8 @@ class ClosedLoop:
         k = torch.arange(N, dtype=torch.float64, device=self.p.device)
         th = self.p[:, 10:11] + T * self.vw[:, 1:2] * k[None, :]                        # theta at stage k
         step = T * self.vw[:, 0:1, None] * torch.stack([torch.cos(th), torch.sin(th)], dim=2)
-        pos = self.p[:, None, 8:10] + torch.cumsum(step, dim=1) - step                   # exclusive prefix sum
+        excl = torch.cat([torch.zeros_like(step[:, :1]), torch.cumsum(step[:, :-1], dim=1)], dim=1)   # exclusive prefix sum
+        pos = self.p[:, None, 8:10] + excl
         return pos.contiguous()
 
     def next_order(self):

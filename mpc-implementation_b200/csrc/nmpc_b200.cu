@@ -265,7 +265,7 @@ struct nmpc_handle {
   cudaStream_t own_stream, last_stream;
   int64_t launches;
   double* dbg; int dbg_rows;
-  int align_group, align_quorum;
+  int align_group;
 };
 
 extern "C" {
@@ -314,11 +314,6 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   if (const char* e = getenv("NMPC_B200_ALIGN_GROUP")) {     // tuning knob: 0 = off, else a divisor of the warps per block
     const int g = atoi(e);
     if (g == 0 || (g > 0 && h->warps_per_block % g == 0)) h->align_group = g;
-  }
-  h->align_quorum = h->align_group;
-  if (const char* e = getenv("NMPC_B200_ALIGN_QUORUM")) {    // tuning knob: arrivals that release the barrier
-    const int q = atoi(e);
-    if (q >= 1 && q <= h->align_group) h->align_quorum = q;
   }
   h->auto_order = 1;
   if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
@@ -404,7 +399,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   }
   h->prev_B = B;
   A.weights = h->weights;
-  A.align_group = h->align_group; A.align_quorum = h->align_quorum;
+  A.align_group = h->align_group;
   CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
   const int blocks = B < h->max_blocks ? B : h->max_blocks;

@@ -156,7 +156,7 @@ struct Lay {
   static constexpr int PAR0 = RES0 + 24;
   static constexpr int TOTAL = even_up(PAR0 + 14);   // p (11), w1, w2 of this instance
   // warps (= concurrent instances) per block: as many slices as fit in the 227 KB a block may use, at most NMPC_WPB_MAX
-  static constexpr int WPB_FIT = (227 * 1024 - 16) / (TOTAL * 8);
+  static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);
   static constexpr int WPB = WPB_FIT < 1 ? 1 : (WPB_FIT > NMPC_WPB_MAX ? NMPC_WPB_MAX : WPB_FIT);
 };
 

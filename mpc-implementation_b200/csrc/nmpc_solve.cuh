@@ -49,7 +49,6 @@ struct SolveArgs {
   const unsigned* ricmap;            // per-lane ownership maps of the factorisation (nmpc_riccati.cuh: ric_map_build)
   double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][8] (tests only)
   int align_group;                   // warps that start each IPM iteration together (0 = no alignment, else divides WPB)
-  int align_quorum;                  // arrivals that release the alignment barrier (<= align_group)
 };
 
 constexpr double EPSM = 2.220446049250313e-16;
@@ -92,19 +91,17 @@ __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, doub
   return b;
 }
 
-// Alignment barrier of the group of `g` consecutive warps this warp belongs to (named barrier 1 + group index).
-// It completes when `q` <= g warps have arrived (a quorum): the slowest warps of a group do not hold the others up,
-// they join the next completion.  Warps that ran out of work keep arriving (blocking, once per completion) until the
-// whole block is done, then release whoever is still blocked with non-blocking arrivals.  g == 0: no alignment.
-__device__ __forceinline__ void align_warps(int g, int q) {
-  if (g == 0) return;
-  const unsigned id = 1 + (threadIdx.x >> 5) / g, nt = 32 * q;
-  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nt) : "memory");
-}
-__device__ __forceinline__ void align_idle(int g, int q) {
-  if (g == 0) return;
-  const unsigned id = 1 + (threadIdx.x >> 5) / g, nt = 32 * q;
-  asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nt) : "memory");
+// Alignment barrier over the group of `g` consecutive warps this warp belongs to (named barrier 1 + group index),
+// OR-reducing `working` over the group.  Every warp of the group calls it the same number of times: working warps
+// once per IPM iteration, warps that ran out of work in a loop until the reduction says nobody is working -- the
+// exit decision comes out of the barrier itself, so no warp can leave while another still waits.  g == 0: no alignment.
+__device__ __forceinline__ int align_warps(int g, int working) {
+  if (g == 0) return 0;
+  unsigned out;
+  const unsigned id = 1 + (threadIdx.x >> 5) / g, nt = 32 * g;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(out) : "r"((unsigned)working), "r"(id), "r"(nt) : "memory");
+  return (int)out;
 }
 
 #define LV(e) smem[L::LV0 + (e) * L::S + lane]
@@ -724,7 +721,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
     // measured and is slower: each phase then lasts as long as its slowest warp; 43 -> 65 ms at B = 16384.)
     // (Measured and rejected: releasing the barrier with a quorum of 5-7 of 8 warps, and letting warps with long line
     // searches pay their arrival in advance and run out of phase -- both slower; strict lockstep wins.)
-    align_warps(A.align_group, A.align_quorum);
+    align_warps(A.align_group, 1);
     ph_derivs<L>(A, lane, ls, df);
     if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
       ++n_fact;
@@ -866,8 +863,6 @@ template <int N_, int NOBS_>
 __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(const SolveArgs A) {
   using L = Lay<N_, NOBS_>;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) *reinterpret_cast<int*>(smem_all + (size_t)L::WPB * L::TOTAL) = 0;   // warps-done counter
-  __syncthreads();
   double* ric = A.ric + (size_t)(blockIdx.x * L::WPB + (threadIdx.x >> 5)) * A.ric_stride;
   for (;;) {
     int q = 0;
@@ -878,13 +873,7 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
     solve_instance<L>(A, ric, b, lane);
     __syncwarp();
   }
-  // out of work: keep feeding the alignment barrier until every warp of the block is done
-  volatile int* done = reinterpret_cast<volatile int*>(smem_all + (size_t)L::WPB * L::TOTAL);
-  __syncwarp();
-  if (lane == 0) { atomicAdd(const_cast<int*>(done), 1); __threadfence_block(); }
-  __syncwarp();
-  while (*done < L::WPB) align_warps(A.align_group, A.align_quorum);      // one arrival per completion, like a working warp
-  for (int i = 0; i < A.align_quorum; ++i) align_idle(A.align_group, A.align_quorum);   // release warps still blocked
+  while (align_warps(A.align_group, 0)) {}   // out of work: keep matching the alignment barrier until the group is done
 }
 
 #undef LV
