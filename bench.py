@@ -54,6 +54,8 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):      # (debug knob)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -143,7 +145,7 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     import b200nmpc
     from mpc_implementation_b200 import sharding
-    from mpc_implementation_b200.closed_loop import ClosedLoop
+    from mpc_implementation_b200.closed_loop import ClosedLoop, PipelinedClosedLoop
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -153,9 +155,14 @@ def run_b200(args, rank, world, local_rank):
     B = args.batch
     if args.no_lpt:
         os.environ["NMPC_B200_AUTO_ORDER"] = "0"
+    # sub-batches: measured best 8 at B = 4096, 2 at B = 16384 (tools/pipeline_probe.py): about 32768 / B, at most 8
+    S = max(1, min(args.pipelines, B)) if args.pipelines > 0 else max(1, min(8, 32768 // max(B, 1)))
     p, vw = b200nmpc.random_instances(sc, B, seed=2000 + rank)
-    solver = b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=B)
-    cl = ClosedLoop(solver, sc, p, target_vw=vw)
+    mk = lambda n: b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=n)
+    # the batch advances as S independently pipelined sub-batches (own handle + stream each): one sub-batch's stragglers
+    # overlap with the next one's bulk; per-instance results are those of the single-batch loop (tests/test_gpu_parity.py)
+    cl = PipelinedClosedLoop(mk, sc, p, target_vw=vw, pipelines=S)
+    solver = cl.loops[0].solver
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)    # > 126 MB L2
 
     def barrier():
@@ -167,81 +174,105 @@ def run_b200(args, rank, world, local_rank):
     for k in range(args.warmup):
         cl.step()
         if k == 0:
-            st = solver.stats()
+            st = cl.stats()
             cold = {"converged_fraction": float(st["success"].double().mean()), "mean_iters": float(st["iter_count"].double().mean())}
     barrier()
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    conv_t = torch.zeros((), dtype=torch.int64, device=dev)
-    it_t = torch.zeros((), dtype=torch.int64, device=dev)
-    fact = ls = 0
+    ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(S)] for _ in range(K)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    keep = []
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     wall0 = time.perf_counter()
+    cur = torch.cuda.current_stream(dev)
+    e_start.record(cur)
+    for st_ in cl.streams:
+        st_.wait_event(e_start)
     for k in range(K):
-        flush.zero_()                                   # L2 flush between timed iterations (inputs are ~6 MB << L2)
-        cl._schedule_vw()
-        tb = cl.p[:, 8:10].clone()
-        ev[k][0].record()
-        sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False)
-        ev[k][1].record()
-        solver.step(sol["x"], cl.p, cl.u_warm, cl.vw, cl.fov)
-        cl.err_sum += torch.linalg.vector_norm(cl.fov - tb, dim=1)
-        ev[k][2].record()
-        st = solver.stats()
-        conv_t += st["success"].sum(); it_t += st["iter_count"].sum()
-        cl.mpc_iter += 1
-        if args.count_work:
-            c = solver.work_counters(); fact += c["factorizations"]; ls += c["ls_trials"]
+        for i, (lp, st_) in enumerate(zip(cl.loops, cl.streams)):
+            with torch.cuda.stream(st_):
+                if not os.environ.get("BENCH_NO_FLUSH"):    # (debug knob; reported numbers always flush)
+                    flush.zero_()                       # L2 flush before every sub-batch step (inputs are ~6 MB << L2)
+                lp._schedule_vw()
+                ev[k][i][0].record()
+                sol = lp.solver(x0=lp.u_warm, p=lp.p, lbx=lp.lbx, ubx=lp.ubx, lbg=lp.lbg, ubg=lp.ubg, want_g=False, want_lam=False)
+                ev[k][i][1].record()
+                lp.solver.step(sol["x"], lp.p, lp.u_warm, lp.vw, lp.fov, lp.err_sum)
+                ev[k][i][2].record()
+                sst = lp.solver._stats               # status / iteration arrays of this step: counted after the timed region
+                keep.append((sst["return_status"], sst["iter_count"]))
+                lp.mpc_iter += 1
+    cl.join(cur)
+    e_end.record(cur)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    step_ms = [ev[k][0].elapsed_time(ev[k][2]) for k in range(K)]
-    solve_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
-    t_rank = sum(step_ms) * 1e-3
+    step_ms = [ev[k][i][0].elapsed_time(ev[k][i][2]) for k in range(K) for i in range(S)]     # per sub-batch step
+    solve_ms = [ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(K) for i in range(S)]
+    fact = ls = 0
+    t_rank = e_start.elapsed_time(e_end) * 1e-3
     t_max = sharding.max_over_ranks(t_rank, dev)
-    tot = sharding.sum_counters([int(conv_t.item()), int(it_t.item()), fact, ls], dev).cpu().numpy()
+    conv_loc = sum(int((a == 0).sum().item()) for a, _ in keep); it_loc = sum(int(b_.sum().item()) for _, b_ in keep)
+    tot = sharding.sum_counters([conv_loc, it_loc, fact, ls], dev).cpu().numpy()
     conv_all, iters_all = float(tot[0]), float(tot[1])
     value = conv_all / t_max
 
-    # ---- e2e: the SAME closed loop (same instances, same warm-up, same timed steps) driven through the host-buffer
-    #      entry point: every step copies p and the warm start H2D from pinned memory, solves, copies x, f, status,
-    #      iters D2H, and does the shift on the host like the reference script does (NMPC_TT.py:382)
+    # ---- e2e: the SAME closed loop (same instances, same warm-up, same timed steps, same sub-batches) driven through the
+    #      host-buffer entry point: every step copies p and the warm start H2D from pinned memory, solves, copies x, f,
+    #      status, iters D2H, and does the shift on the host like the reference script does (NMPC_TT.py:382).  The
+    #      sub-batches are issued with nmpc_solve_host_async and completed in turn, so that the host-side shift of one
+    #      overlaps the device work of the others.
     Ke = min(K, args.e2e_steps) if args.e2e_steps > 0 else K
-    ph = torch.empty((B, 11), dtype=torch.float64).pin_memory().numpy(); ph[:] = p
-    uh = torch.empty((B, sc.n_w), dtype=torch.float64).pin_memory().numpy(); uh[:] = 0.0
-    lbx, ubx, lbg, ubg = sc.bounds(); vwh = vw.copy()
+    lbx, ubx, lbg, ubg = sc.bounds()
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    hs = []
+    for idx in cl.index:
+        ph = pin((len(idx), 11)); ph[:] = p[idx]
+        uh = pin((len(idx), sc.n_w)); uh[:] = 0.0
+        hs.append(dict(p=ph, u=uh, vw=vw[idx].copy(), solver=mk(len(idx))))
+    issue = lambda h: h["solver"](x0=h["u"], p=h["p"], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, want_g=False, want_lam=False, blocking=False)
     barrier()
     conv_e = 0; t_e = 0.0; e2e_ms = []
+    pend = [issue(h) for h in hs]
+    t_mark = time.perf_counter()
     for k in range(args.warmup + Ke):
+        last = k == args.warmup + Ke - 1
         if k == args.warmup:
-            barrier()
-        t0 = time.perf_counter()
-        s2 = solver(x0=uh, p=ph, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, want_g=False, want_lam=False)
-        uh[:] = host_shift(sc.T, ph, s2["x"], vwh)
-        dt = time.perf_counter() - t0
+            t_mark = time.perf_counter()
+        for i, h in enumerate(hs):
+            h["solver"].wait()
+            if k >= args.warmup:
+                conv_e += int(h["solver"].stats()["success"].sum())
+            h["u"][:] = host_shift(sc.T, h["p"], pend[i]["x"], h["vw"])
+            if not last:
+                pend[i] = issue(h)
         if k >= args.warmup:
-            t_e += dt; conv_e += int(solver.stats()["success"].sum()); e2e_ms.append(round(dt * 1e3, 3))
+            now = time.perf_counter(); e2e_ms.append(round((now - t_mark) * 1e3, 3)); t_e += now - t_mark; t_mark = now
     barrier()
     t_e_max = sharding.max_over_ranks(t_e, dev)
     conv_e_all = float(sharding.sum_counters([conv_e], dev)[0])
     e2e_val = conv_e_all / t_e_max if t_e_max > 0 else None
-    h2d = B * (11 + sc.n_w) * 8 + (2 * sc.n_w + 2 * sc.n_g + 3 * sc.n_obs) * 8
+    h2d = B * (11 + sc.n_w) * 8 + S * (2 * sc.n_w + 2 * sc.n_g + 3 * sc.n_obs) * 8
     d2h = B * (sc.n_w + 1) * 8 + B * 8
-
 
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return
 
-    # ---- work counters for the flop numerator (one extra untimed step on rank 0)
-    sol = solver(x0=cl.u_warm, p=cl.p, lbx=cl.lbx, ubx=cl.ubx, lbg=cl.lbg, ubg=cl.ubg, want_g=False, want_lam=False)
+    # ---- work counters for the flop numerator (one extra untimed step on rank 0, all sub-batches)
+    it_step = 0.0; wc = {"factorizations": 0, "ls_trials": 0}
+    for lp, st_ in zip(cl.loops, cl.streams):
+        with torch.cuda.stream(st_):
+            lp.solver(x0=lp.u_warm, p=lp.p, lbx=lp.lbx, ubx=lp.ubx, lbg=lp.lbg, ubg=lp.ubg, want_g=False, want_lam=False)
     torch.cuda.synchronize()
-    wc = solver.work_counters(); st = solver.stats()
-    it_step = float(st["iter_count"].sum())
+    for lp in cl.loops:
+        c = lp.solver.work_counters(); wc["factorizations"] += c["factorizations"]; wc["ls_trials"] += c["ls_trials"]
+        it_step += float(lp.solver.stats()["iter_count"].sum())
     flops_step = algorithmic_flops(sc.N, sc.n_obs, it_step, wc["factorizations"], wc["ls_trials"])
-    k_ms = float(np.mean(solve_ms))
+    # time of one whole-batch step; with S > 1 the S launches of a step overlap each other and the neighbouring steps,
+    # so the per-launch event times (p50_solve_kernel_ms) are not additive
+    k_ms = t_rank * 1e3 / K
     peak64 = ctypes_fp64_peak(b200nmpc, local_rank)
     lbx, ubx, lbg, ubg = sc.bounds()
     peaks = {}
@@ -285,17 +316,18 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}, n_w={sc.n_w}, n_g={sc.n_g}) closed loop: "
                                f"{B} randomised UAV states / target speeds per GPU (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
-                   "l2": "flushed between timed steps (256 MB write)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (nmpc_order_kernel inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
+                   "pipelines": S, "l2": "flushed before every sub-batch step (256 MB write)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (nmpc_order_kernel inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
         "p50_step_ms": float(np.median(step_ms)), "p50_solve_kernel_ms": float(np.median(solve_ms)),
+        "p50_note": "per sub-batch: stream time from the start of its solve to the end of its shift / of its solve kernel",
         "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
         "cold_first_step": cold, "wall_s": wall,
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
-                "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=) with pinned numpy buffers -> nmpc_solve_host"},
-        "gpu_launches": (3 if args.no_lpt else 4) * K,     # nmpc_relax_bounds_kernel, [nmpc_order_kernel,] nmpc_ipm_kernel, nmpc_step_kernel per step
+                "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=, blocking=False) with pinned numpy buffers -> nmpc_solve_host_async / nmpc_synchronize, one solver per sub-batch"},
+        "gpu_launches": 3 * K * S,     # nmpc_prologue_kernel, nmpc_ipm_kernel, nmpc_step_kernel per sub-batch step
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bytes_per_solve(sc.N, sc.n_obs) * B,
-                     "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "peak_source": which,
+                     "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "launches_per_step": S, "peak_source": which,
                      "bytes_per_solve": bytes_per_solve(sc.N, sc.n_obs),
                      "note": "not HBM-bound by design (SURVEY 8d): the limiter is the FP64 dependency chain; see fp64"},
         "fp64": {"achieved": ach_tf, "peak": peak64, "unit": "TFLOP/s", "frac": (ach_tf / peak64) if peak64 else None,
@@ -344,6 +376,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipelines", type=int, default=0, help="independently pipelined sub-batches per GPU (0 = choose from the batch size, 1 = one batch on one stream)")
     ap.add_argument("--no-lpt", action="store_true", help="disable the library's longest-first scheduling (NMPC_B200_AUTO_ORDER=0)")
     ap.add_argument("--count-work", action="store_true", help="read device work counters every timed step (adds a sync)")
     args = ap.parse_args()

@@ -96,6 +96,18 @@ int nmpc_solve_host(nmpc_handle* h, int32_t B,
                     double* x, double* f, double* g, double* lam_x, double* lam_g,
                     int32_t* status, int32_t* iters);
 
+/* The same, asynchronous: the copies and the solve are enqueued on the handle's own stream and the call returns.
+ * The host buffers should be page-locked (cudaHostAlloc, torch pin_memory) -- pageable memory makes the copies
+ * synchronous -- and must not be read or written until nmpc_synchronize(h) has returned.  Several handles driven this
+ * way overlap: while one sub-batch waits for its stragglers, the next one's copies and solve proceed. */
+int nmpc_solve_host_async(nmpc_handle* h, int32_t B,
+                          const double* p, const double* x0,
+                          const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                          const double* obst, uint32_t flags,
+                          double* x, double* f, double* g, double* lam_x, double* lam_g,
+                          int32_t* status, int32_t* iters);
+int nmpc_synchronize(nmpc_handle* h);   /* waits for the handle's own stream */
+
 /* Function-level evaluation (what CasADi's generated nlp_f / nlp_g / nlp_grad_f / nlp_hess_l
  * compute for IPOPT): at w [B][6N], p [B][11]
  *   f [B], g [B][n_g], grad_f [B][6N],
@@ -111,9 +123,11 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
  *   p [B][11]: p[0:8] <- x + T f_u(x, u[:,0]);  p[8:11] <- target + T [v cos th, v sin th, om]
  *   u_warm [B][6N] <- x_sol shifted by one stage, last stage repeated (may alias x_sol)
  *   target_vw [B][2] = (v, om) of the target for this step (the scripts' con_t, keyed on mpc_iter)
- *   fov_centre [B][2] (may be NULL) = (X_E, Y_E) of the NEW state. */
+ *   fov_centre [B][2] (may be NULL) = (X_E, Y_E) of the NEW state
+ *   err_accum [B] (may be NULL; needs fov_centre) += || FOV centre of the NEW state - target of THIS step ||, the
+ *   per-step term of the scripts' final metric (NMPC_TT.py:433-440). */
 int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
-              double* u_warm, const double* target_vw, double* fov_centre, void* cuda_stream);
+              double* u_warm, const double* target_vw, double* fov_centre, double* err_accum, void* cuda_stream);
 
 /* statistics of the last nmpc_solve on this handle (device work counters, host copy) */
 typedef struct nmpc_stats {

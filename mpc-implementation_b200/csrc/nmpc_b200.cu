@@ -175,23 +175,30 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
 
 struct StepArgs {
   double T, hv, hh; int N, B;
-  const double* x_sol; double *p, *u_warm; const double* vw; double* fov;
+  const double* x_sol; double *p, *u_warm; const double* vw; double *fov, *err;
 };
 
-// Relaxed bounds (IPOPT bound_relax_factor) of the batch-shared bound vectors, once per nmpc_solve call: the IPM
-// phases then load them instead of redoing the arithmetic per row and phase (nmpc_solve.cuh: ctl_bounds / row_bounds;
-// same intrinsics, so the values are bit-identical to the in-kernel formula used for scaled rows).
-__global__ void nmpc_relax_bounds_kernel(const double* __restrict__ lbx, const double* __restrict__ ubx,
-                                         const double* __restrict__ lbg, const double* __restrict__ ubg,
-                                         int nw, int ng, double relax, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nw) { out[i] = relaxed_lo(lbx[i], relax); out[nw + i] = relaxed_hi(ubx[i], relax); }
-  if (i < ng) { out[2 * nw + i] = relaxed_lo(lbg[i], relax); out[2 * nw + ng + i] = relaxed_hi(ubg[i], relax); }
-}
-
-// Longest-first fetch order for the persistent kernel from the previous call's iteration counts: counting sort,
-// descending, one block (B = 4096: ~10 us; the order inside a bin is arbitrary -- results do not depend on it).
-__global__ void __launch_bounds__(1024) nmpc_order_kernel(const int32_t* __restrict__ iters, int B, int32_t* __restrict__ order) {
+// Prologue of a solve, ONE launch (every extra small kernel of a call has to wait for a free SM slot next to the
+// persistent blocks of whatever other handles are running on the device):
+//   block 0      resets the work queue and the work counters and, if asked, writes the longest-first fetch order from
+//                the previous call's iteration counts (counting sort, descending; the order inside a bin is arbitrary
+//                -- results do not depend on it);
+//   blocks 1..   relaxed bounds (IPOPT bound_relax_factor) of the batch-shared bound vectors, which the IPM phases then
+//                load instead of redoing the arithmetic per row and phase (nmpc_solve.cuh: ctl_bounds / row_bounds;
+//                same intrinsics, so bit-identical to the in-kernel formula used for scaled rows).
+__global__ void __launch_bounds__(1024) nmpc_prologue_kernel(const double* __restrict__ lbx, const double* __restrict__ ubx,
+                                                             const double* __restrict__ lbg, const double* __restrict__ ubg,
+                                                             int nw, int ng, double relax, double* __restrict__ out,
+                                                             const int32_t* __restrict__ iters, int B, int32_t* __restrict__ order,
+                                                             int* counter, unsigned long long* stats) {
+  if (blockIdx.x > 0) {
+    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+    if (i < nw) { out[i] = relaxed_lo(lbx[i], relax); out[nw + i] = relaxed_hi(ubx[i], relax); }
+    if (i < ng) { out[2 * nw + i] = relaxed_lo(lbg[i], relax); out[2 * nw + ng + i] = relaxed_hi(ubg[i], relax); }
+    return;
+  }
+  if (threadIdx.x == 0) { *counter = 0; stats[0] = 0; stats[1] = 0; stats[2] = 0; }
+  if (!order) return;
   __shared__ int bin[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) bin[i] = 0;
   __syncthreads();
@@ -229,13 +236,15 @@ __global__ void nmpc_step_kernel(const StepArgs A) {
   if (A.u_warm != A.x_sol)
     for (int i = 0; i < NU; ++i) uw[NU * (A.N - 1) + i] = xs[NU * (A.N - 1) + i];
   double* tg = st + NX;
+  const double tx0 = tg[0], ty0 = tg[1];          // target of THIS step: the error pairs it with the NEXT FOV centre
   const double tv = A.vw[2 * b], tw = A.vw[2 * b + 1], th = tg[2];
   tg[0] += A.T * tv * cos(th); tg[1] += A.T * tv * sin(th); tg[2] += A.T * tw;
   if (A.fov) {
     const double t6p = tan(x[6] + A.hv), t6m = tan(x[6] - A.hv), t5p = tan(x[5] + A.hh), t5m = tan(x[5] - A.hh);
     const double a_p = (x[2] * t6p - x[2] * t6m) / 2, b_p = (x[2] * t5p - x[2] * t5m) / 2;
-    A.fov[2 * b] = x[0] + a_p + x[2] * t6m;
-    A.fov[2 * b + 1] = x[1] + b_p + x[2] * t5m;
+    const double xe = x[0] + a_p + x[2] * t6m, ye = x[1] + b_p + x[2] * t5m;
+    A.fov[2 * b] = xe; A.fov[2 * b + 1] = ye;
+    if (A.err) A.err[b] += sqrt((xe - tx0) * (xe - tx0) + (ye - ty0) * (ye - ty0));     // NMPC_TT.py:435
   }
 }
 
@@ -384,24 +393,23 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
     CK(cudaMalloc(&h->d_order, sizeof(int32_t) * B)); CK(cudaMalloc(&h->d_keep_iters, sizeof(int32_t) * B));
     h->order_cap = B;
   }
-  {
-    const int nw = NU * h->pr.N, ng = h->pr.R * h->pr.S, n = nw > ng ? nw : ng;
-    nmpc_relax_bounds_kernel<<<(n + 127) / 128, 128, 0, s>>>(lbx, ubx, lbg, ubg, nw, ng, h->opt.bound_relax, h->d_bnd);
-    A.xlo_r = h->d_bnd; A.xhi_r = h->d_bnd + nw; A.glo_r = h->d_bnd + 2 * nw; A.ghi_r = h->d_bnd + 2 * nw + ng;
-  }
   A.iters_keep = h->d_keep_iters;
   A.tgt = h->tgt;
-  A.order = h->order_next; h->order_next = nullptr;
-  h->launches = 2;     // nmpc_relax_bounds_kernel + nmpc_ipm_kernel
-  if (!A.order && h->auto_order && h->prev_B == B) {   // same batch as last time: start last time's longest solves first
-    nmpc_order_kernel<<<1, 1024, 0, s>>>(h->d_keep_iters, B, h->d_order);
-    A.order = h->d_order; h->launches = 3;
-  }
-  h->prev_B = B;
   A.weights = h->weights;
   A.align_group = h->align_group;
-  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
-  CK(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(unsigned long long), s));
+  A.order = h->order_next; h->order_next = nullptr;
+  {
+    const int nw = NU * h->pr.N, ng = h->pr.R * h->pr.S, n = nw > ng ? nw : ng;
+    int32_t* make_order = nullptr;
+    if (!A.order && h->auto_order && h->prev_B == B) {   // same batch as last time: start last time's longest solves first
+      make_order = h->d_order; A.order = h->d_order;
+    }
+    nmpc_prologue_kernel<<<1 + (n + 1023) / 1024, 1024, 0, s>>>(lbx, ubx, lbg, ubg, nw, ng, h->opt.bound_relax, h->d_bnd,
+                                                                   h->d_keep_iters, B, make_order, h->d_counter, h->d_stats);
+    A.xlo_r = h->d_bnd; A.xhi_r = h->d_bnd + nw; A.glo_r = h->d_bnd + 2 * nw; A.ghi_r = h->d_bnd + 2 * nw + ng;
+  }
+  h->launches = 2;     // nmpc_prologue_kernel + nmpc_ipm_kernel
+  h->prev_B = B;
   const int blocks = B < h->max_blocks ? B : h->max_blocks;
   {
     const int rc = h->inst->launch(A, blocks, h->smem_bytes, s);
@@ -416,6 +424,22 @@ int nmpc_solve_host(nmpc_handle* h, int32_t B, const double* p, const double* x0
                     const double* obst, uint32_t flags,
                     double* x, double* f, double* g, double* lam_x, double* lam_g,
                     int32_t* status, int32_t* iters) {
+  const int rc = nmpc_solve_host_async(h, B, p, x0, lbx, ubx, lbg, ubg, obst, flags, x, f, g, lam_x, lam_g, status, iters);
+  return rc ? rc : nmpc_synchronize(h);
+}
+
+int nmpc_synchronize(nmpc_handle* h) {
+  if (!h) return fail("nmpc_synchronize: null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->own_stream));
+  return 0;
+}
+
+int nmpc_solve_host_async(nmpc_handle* h, int32_t B, const double* p, const double* x0,
+                          const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                          const double* obst, uint32_t flags,
+                          double* x, double* f, double* g, double* lam_x, double* lam_g,
+                          int32_t* status, int32_t* iters) {
   if (!h) return fail("nmpc_solve_host: null handle");
   if (B <= 0) return 0;
   if (B > h->spec.max_batch) return fail("nmpc_solve_host: B exceeds spec.max_batch");
@@ -441,7 +465,6 @@ int nmpc_solve_host(nmpc_handle* h, int32_t B, const double* p, const double* x0
   if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lamg, sizeof(double) * B * ng, cudaMemcpyDeviceToHost, s));
   if (status) CK(cudaMemcpyAsync(status, h->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
   if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
   return 0;
 }
 
@@ -467,12 +490,13 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
 }
 
 int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
-              double* u_warm, const double* target_vw, double* fov_centre, void* cuda_stream) {
+              double* u_warm, const double* target_vw, double* fov_centre, double* err_accum, void* cuda_stream) {
   if (!h) return fail("nmpc_step: null handle");
   if (B <= 0) return 0;
   if (!x_sol || !p || !u_warm || !target_vw) return fail("nmpc_step: null required pointer");
   CK(cudaSetDevice(h->device));
-  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, x_sol, p, u_warm, target_vw, fov_centre};
+  if (err_accum && !fov_centre) return fail("nmpc_step: err_accum needs fov_centre");
+  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, x_sol, p, u_warm, target_vw, fov_centre, err_accum};
   nmpc_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(A);
   CK(cudaGetLastError());
   h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;

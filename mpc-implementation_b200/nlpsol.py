@@ -121,11 +121,15 @@ class Solver:
 
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, obstacles=None,
-                 want_g: bool = True, want_lam: bool = True, order=None, weights=None, target_traj=None):
+                 want_g: bool = True, want_lam: bool = True, order=None, weights=None, target_traj=None,
+                 blocking: bool = True):
         """weights: optional [B, 2] per-instance cost weights (w1, w2) for this call (numpy or CUDA tensor); the
         reference edits them in source (NMPC_TT.py:204-205) and its MATLAB outer loop sweeps them (MPC.m:90).
         target_traj: optional [B, N, 2] predicted target positions per stage (default: p[8:10] for every stage, as
-        in the reference)."""
+        in the reference).
+        blocking=False (host buffers only): enqueue the copies and the solve and return at once; the outputs are
+        page-locked arrays owned by this solver that become valid after `solver.wait()` and are reused by the next
+        call.  Pass page-locked inputs (torch pin_memory) for the copies to overlap."""
         if p is None:
             raise ValueError("solver: p is required")
         if any(v is None for v in (lbx, ubx, lbg, ubg)):
@@ -133,7 +137,21 @@ class Solver:
         with self._weights(weights, p), self._traj(target_traj, p):
             if _is_cuda_tensor(p):
                 return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order)
-            return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam)
+            return self._call_host(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, blocking)
+
+    def wait(self):
+        """Complete a blocking=False call (nmpc_synchronize)."""
+        _ffi.check(_ffi.lib().nmpc_synchronize(self._h), "nmpc_synchronize")
+
+    def _pinned(self, key: str, shape, dtype=np.float64):
+        """Page-locked output buffer, cached per (name, shape)."""
+        k = ("pin", key, tuple(shape), np.dtype(dtype).str)
+        buf = self._dev_cache.get(k)
+        if buf is None:
+            t = torch.empty(tuple(shape), dtype=torch.float64 if dtype == np.float64 else torch.int32).pin_memory()
+            buf = (t, t.numpy())
+            self._dev_cache[k] = buf
+        return buf[1]
 
     def _traj(self, traj, p):
         """Context manager: nmpc_set_target_trajectory for the duration of one call."""
@@ -196,7 +214,7 @@ class Solver:
             return o.reshape(B, self.n_obs, 3), _ffi.NMPC_OBS_PER_INSTANCE
         raise ValueError("solver: obstacles must be [n_obs,3] or [B,n_obs,3] of (cx, cy, r_uav + r_obs)")
 
-    def _call_host(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam):
+    def _call_host(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, blocking=True):
         L = _ffi.lib()
         single = np.asarray(p).ndim == 1 or (np.asarray(p).ndim == 2 and np.asarray(p).shape[1] == 1)
         p = self._host(p, NP)
@@ -209,16 +227,20 @@ class Solver:
         obs, flags = self._obst(obstacles, B)
         if B > self._max_batch:
             self._create(max(B, 2 * self._max_batch))
-        x = np.empty((B, self.n_w)); f = np.empty(B)
-        g = np.empty((B, self.n_g)) if want_g else None
-        lam_x = np.empty((B, self.n_w)) if want_lam else None
-        lam_g = np.empty((B, self.n_g)) if want_lam else None
-        status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+        new = (lambda k, shape, dt=np.float64: np.empty(shape, dtype=dt)) if blocking else self._pinned
+        x = new("x", (B, self.n_w)); f = new("f", (B,))
+        g = new("g", (B, self.n_g)) if want_g else None
+        lam_x = new("lam_x", (B, self.n_w)) if want_lam else None
+        lam_g = new("lam_g", (B, self.n_g)) if want_lam else None
+        status = new("status", (B,), np.int32); iters = new("iters", (B,), np.int32)
         ptr = lambda a: None if a is None else a.ctypes.data
-        _ffi.check(L.nmpc_solve_host(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
-                                     ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters)),
+        fn = L.nmpc_solve_host if blocking else L.nmpc_solve_host_async
+        if not blocking:
+            self._keep = (p, x0, lbx, ubx, lbg, ubg, obs)      # inputs stay alive until wait()
+        _ffi.check(fn(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
+                      ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters)),
                    "nmpc_solve_host")
-        self._stats = dict(return_status=status, iter_count=iters, success=status == 0)
+        self._stats = dict(return_status=status, iter_count=iters)      # success is derived in stats(): valid after wait()
         out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
         if single:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
@@ -263,15 +285,19 @@ class Solver:
                                 ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters), stream),
                    "nmpc_solve")
         self._keep = (p, x0, obs, order)   # keep inputs alive until the stream has consumed them
-        self._stats = dict(return_status=status, iter_count=iters, success=status == 0)
+        self._stats = dict(return_status=status, iter_count=iters)      # success is derived lazily in stats()
         out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
         if single:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
         return out
 
     def stats(self) -> Dict[str, Any]:
-        """Per-instance outcome of the last call (CasADi: solver.stats())."""
-        return self._stats
+        """Per-instance outcome of the last call (CasADi: solver.stats()); after a blocking=False call, valid once
+        wait() has returned."""
+        d = dict(self._stats)
+        if d and "success" not in d:
+            d["success"] = d["return_status"] == 0
+        return d
 
     def work_counters(self) -> Dict[str, int]:
         st = _ffi.NmpcStats()
@@ -311,13 +337,15 @@ class Solver:
         return dict(f=f, g=g, grad=grad, jtv=jtv, hv=hv)
 
     # -- shift_timestep (NMPC_TT.py:13-30) on device --------------------------------------------
-    def step(self, x_sol, p, u_warm, target_vw, fov_centre=None):
-        """In-place closed-loop shift of B instances (torch CUDA float64 tensors): p [B,11], u_warm [B,6N]."""
+    def step(self, x_sol, p, u_warm, target_vw, fov_centre=None, err_accum=None):
+        """In-place closed-loop shift of B instances (torch CUDA float64 tensors): p [B,11], u_warm [B,6N];
+        err_accum [B] += ||new FOV centre - this step's target|| (NMPC_TT.py:435)."""
         L = _ffi.lib()
         B = p.shape[0]
         stream = torch.cuda.current_stream(p.device).cuda_stream
         _ffi.check(L.nmpc_step(self._h, B, x_sol.data_ptr(), p.data_ptr(), u_warm.data_ptr(),
-                               target_vw.data_ptr(), None if fov_centre is None else fov_centre.data_ptr(), stream),
+                               target_vw.data_ptr(), None if fov_centre is None else fov_centre.data_ptr(),
+                               None if err_accum is None else err_accum.data_ptr(), stream),
                    "nmpc_step")
 
 

@@ -387,6 +387,24 @@ def test_schedule_independence(pkg):
             assert torch.equal(a[k], other[k]), k
 
 
+def test_pipelined_closed_loop_is_the_same_loop(pkg):
+    """PipelinedClosedLoop (sub-batches on their own handles and streams) advances every instance exactly like the
+    single-batch ClosedLoop: bit-identical states, warm starts, error sums and solver stats after several steps."""
+    from mpc_implementation_b200.closed_loop import ClosedLoop, PipelinedClosedLoop
+    sc = pkg.SCENARIOS["nmpc_tt"]
+    B = 700
+    p, vw = pkg.random_instances(sc, B, seed=123)
+    mk = lambda n: pkg.nlpsol("solver", "ipm", sc, max_batch=n)
+    one = ClosedLoop(mk(B), sc, p, target_vw=vw)
+    many = PipelinedClosedLoop(mk, sc, p, target_vw=vw, pipelines=3)
+    for _ in range(4):
+        one.step(); many.step()
+    torch.cuda.synchronize()
+    assert torch.equal(one.p, many.p) and torch.equal(one.u_warm, many.u_warm) and torch.equal(one.err_sum, many.err_sum)
+    so, sm = one.solver.stats(), many.stats()
+    assert torch.equal(so["return_status"], sm["return_status"]) and torch.equal(so["iter_count"], sm["iter_count"])
+
+
 def test_edge_cases(pkg):
     sc = pkg.SCENARIOS["t_trajectory"]
     lbx, ubx, lbg, ubg = sc.bounds()
