@@ -231,23 +231,27 @@ def run_b200(args, rank, world, local_rank):
         uh = pin((len(idx), sc.n_w)); uh[:] = 0.0
         hs.append(dict(p=ph, u=uh, vw=vw[idx].copy(), solver=mk(len(idx))))
     issue = lambda h: h["solver"](x0=h["u"], p=h["p"], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, want_g=False, want_lam=False, blocking=False)
+    def host_steps(n, count):
+        """n closed-loop steps of every sub-batch, software-pipelined: returns (converged solves, per-step wall times)."""
+        conv, times = 0, []
+        pend = [issue(h) for h in hs]
+        t_mark = time.perf_counter()
+        for k in range(n):
+            for i, h in enumerate(hs):
+                h["solver"].wait()
+                if count:
+                    conv += int(h["solver"].stats()["success"].sum())
+                h["u"][:] = host_shift(sc.T, h["p"], pend[i]["x"], h["vw"])
+                if k < n - 1:
+                    pend[i] = issue(h)
+            now = time.perf_counter(); times.append(now - t_mark); t_mark = now
+        return conv, times
+
     barrier()
-    conv_e = 0; t_e = 0.0; e2e_ms = []
-    pend = [issue(h) for h in hs]
-    t_mark = time.perf_counter()
-    for k in range(args.warmup + Ke):
-        last = k == args.warmup + Ke - 1
-        if k == args.warmup:
-            t_mark = time.perf_counter()
-        for i, h in enumerate(hs):
-            h["solver"].wait()
-            if k >= args.warmup:
-                conv_e += int(h["solver"].stats()["success"].sum())
-            h["u"][:] = host_shift(sc.T, h["p"], pend[i]["x"], h["vw"])
-            if not last:
-                pend[i] = issue(h)
-        if k >= args.warmup:
-            now = time.perf_counter(); e2e_ms.append(round((now - t_mark) * 1e3, 3)); t_e += now - t_mark; t_mark = now
+    host_steps(args.warmup, False)          # untimed; the pipeline is drained when it returns
+    barrier()
+    conv_e, times = host_steps(Ke, True)
+    t_e = sum(times); e2e_ms = [round(t * 1e3, 3) for t in times]
     barrier()
     t_e_max = sharding.max_over_ranks(t_e, dev)
     conv_e_all = float(sharding.sum_counters([conv_e], dev)[0])
@@ -284,7 +288,7 @@ def run_b200(args, rank, world, local_rank):
     traffic_src = None
     traffic = None       # measured DRAM bytes of one launch of this configuration, from the committed ncu capture
     try:
-        t = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"{sc.N}_{sc.n_obs}_{B}")
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"{sc.N}_{sc.n_obs}_{len(cl.index[0])}")
         if t:
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]; traffic_src = t["source"]
     except Exception:
@@ -326,7 +330,7 @@ def run_b200(args, rank, world, local_rank):
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=, blocking=False) with pinned numpy buffers -> nmpc_solve_host_async / nmpc_synchronize, one solver per sub-batch"},
         "gpu_launches": 3 * K * S,     # nmpc_prologue_kernel, nmpc_ipm_kernel, nmpc_step_kernel per sub-batch step
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": bytes_per_solve(sc.N, sc.n_obs) * B,
+                     "algorithmic_bytes_per_launch": bytes_per_solve(sc.N, sc.n_obs) * len(cl.index[0]),
                      "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "launches_per_step": S, "peak_source": which,
                      "bytes_per_solve": bytes_per_solve(sc.N, sc.n_obs),
                      "note": "not HBM-bound by design (SURVEY 8d): the limiter is the FP64 dependency chain; see fp64"},
