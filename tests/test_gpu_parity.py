@@ -405,6 +405,29 @@ def test_pipelined_closed_loop_is_the_same_loop(pkg):
     assert torch.equal(so["return_status"], sm["return_status"]) and torch.equal(so["iter_count"], sm["iter_count"])
 
 
+def test_async_host_entry_point(pkg):
+    """nmpc_solve_host_async + nmpc_synchronize (solver(..., blocking=False); solver.wait()) returns what the blocking
+    host call returns; two handles driven this way can be in flight together."""
+    sc = pkg.SCENARIOS["t_trajectory"]
+    B = 64
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, _ = pkg.random_instances(sc, 2 * B, seed=3)
+    pin = lambda a: (lambda t: (t.copy_(torch.from_numpy(np.ascontiguousarray(a))), t.numpy())[1])(torch.empty(a.shape, dtype=torch.float64).pin_memory())
+    x0 = np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (2 * B, sc.N))
+    s1, s2 = pkg.nlpsol("a", "ipm", sc, max_batch=B), pkg.nlpsol("b", "ipm", sc, max_batch=B)
+    ref1 = s1(x0=x0[:B], p=p[:B], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    ref2 = s2(x0=x0[B:], p=p[B:], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    st1 = {k: v.copy() for k, v in s1.stats().items()}
+    pa, pb, xa, xb = pin(p[:B]), pin(p[B:]), pin(x0[:B]), pin(x0[B:])
+    o1 = s1(x0=xa, p=pa, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, blocking=False)       # both enqueued before either is waited for
+    o2 = s2(x0=xb, p=pb, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, blocking=False)
+    s1.wait(); s2.wait()
+    for k in ("x", "f", "g", "lam_x", "lam_g"):
+        assert np.array_equal(o1[k], ref1[k]) and np.array_equal(o2[k], ref2[k]), k
+    assert np.array_equal(s1.stats()["return_status"], st1["return_status"]) and np.array_equal(s1.stats()["iter_count"], st1["iter_count"])
+    assert s1.stats()["success"].dtype == bool
+
+
 def test_edge_cases(pkg):
     sc = pkg.SCENARIOS["t_trajectory"]
     lbx, ubx, lbg, ubg = sc.bounds()
