@@ -195,9 +195,13 @@ def run_b200(args, rank, world, local_rank):
                     flush.zero_()                       # L2 flush before every sub-batch step (inputs are ~6 MB << L2)
                 lp._schedule_vw()
                 ev[k][i][0].record()
-                sol = lp.solver(x0=lp.u_warm, p=lp.p, lbx=lp.lbx, ubx=lp.ubx, lbg=lp.lbg, ubg=lp.ubg, want_g=False, want_lam=False)
-                ev[k][i][1].record()
-                lp.solver.step(sol["x"], lp.p, lp.u_warm, lp.vw, lp.fov, lp.err_sum)
+                if args.unfused_step:
+                    sol = lp.solver(x0=lp.u_warm, p=lp.p, lbx=lp.lbx, ubx=lp.ubx, lbg=lp.lbg, ubg=lp.ubg, want_g=False, want_lam=False)
+                    ev[k][i][1].record()
+                    lp.solver.step(sol["x"], lp.p, lp.u_warm, lp.vw, lp.fov, lp.err_sum)
+                else:       # solve + shift_timestep + FOV error in one launch
+                    lp.solver.solve_and_step(lp.p, lp.u_warm, lp.lbx, lp.ubx, lp.lbg, lp.ubg, lp.vw, lp.fov, lp.err_sum)
+                    ev[k][i][1].record()
                 ev[k][i][2].record()
                 sst = lp.solver._stats               # status / iteration arrays of this step: counted after the timed region
                 keep.append((sst["return_status"], sst["iter_count"]))
@@ -328,7 +332,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=, blocking=False) with pinned numpy buffers -> nmpc_solve_host_async / nmpc_synchronize, one solver per sub-batch"},
-        "gpu_launches": 3 * K * S,     # nmpc_prologue_kernel, nmpc_ipm_kernel, nmpc_step_kernel per sub-batch step
+        "gpu_launches": (3 if args.unfused_step else 2) * K * S,     # nmpc_prologue_kernel, nmpc_ipm_kernel (with the shift in its epilogue) [, nmpc_step_kernel] per sub-batch step
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bytes_per_solve(sc.N, sc.n_obs) * len(cl.index[0]),
                      "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "launches_per_step": S, "peak_source": which,
@@ -380,6 +384,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-step", action="store_true", help="nmpc_solve + nmpc_step as two launches instead of nmpc_solve_and_step")
     ap.add_argument("--pipelines", type=int, default=0, help="independently pipelined sub-batches per GPU (0 = choose from the batch size, 1 = one batch on one stream)")
     ap.add_argument("--no-lpt", action="store_true", help="disable the library's longest-first scheduling (NMPC_B200_AUTO_ORDER=0)")
     ap.add_argument("--count-work", action="store_true", help="read device work counters every timed step (adds a sync)")

@@ -129,6 +129,16 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
 int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
               double* u_warm, const double* target_vw, double* fov_centre, double* err_accum, void* cuda_stream);
 
+/* nmpc_solve and nmpc_step in ONE launch ("fused into the solve kernel's epilogue"): the warp that solved
+ * instance b applies the shift to it right away -- p[b] and u_warm[b] (which is also the warm start x0 of the solve)
+ * are updated in place, fov_centre / err_accum as in nmpc_step.  x (may be NULL) receives the un-shifted solution and
+ * must not alias u_warm.  g / lam_* are not produced by this entry point. */
+int nmpc_solve_and_step(nmpc_handle* h, int32_t B, double* p, double* u_warm,
+                        const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                        const double* obst, uint32_t flags, const double* target_vw,
+                        double* x, double* f, double* fov_centre, double* err_accum,
+                        int32_t* status, int32_t* iters, void* cuda_stream);
+
 /* statistics of the last nmpc_solve on this handle (device work counters, host copy) */
 typedef struct nmpc_stats {
   int64_t kernel_launches;     /* kernels launched by the last call */

@@ -79,9 +79,16 @@ class ClosedLoop:
             return None
         return torch.argsort(it, descending=True)
 
-    def step(self, want_g: bool = False, want_lam: bool = False):
-        """One closed-loop batch step; returns the solver output dict (device tensors)."""
+    def step(self, want_g: bool = False, want_lam: bool = False, want_x: bool = True):
+        """One closed-loop batch step; returns the solver output dict (device tensors).  Without g / multipliers /
+        target prediction the solve and the shift are one launch (nmpc_solve_and_step)."""
         self._schedule_vw()
+        if not (want_g or want_lam or self.predict_target):
+            sol = self.solver.solve_and_step(self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg, self.vw, self.fov,
+                                             self.err_sum, want_x=want_x)
+            self.mpc_iter += 1
+            self.last = sol
+            return sol
         sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg,
                           want_g=want_g, want_lam=want_lam,
                           target_traj=self.target_prediction() if self.predict_target else None)

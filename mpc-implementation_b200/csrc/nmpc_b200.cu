@@ -217,35 +217,16 @@ __global__ void nmpc_step_kernel(const StepArgs A) {
   if (b >= A.B) return;
   const int nw = NU * A.N;
   const double* xs = A.x_sol + (size_t)b * nw;
-  double* st = A.p + (size_t)b * NPAR;
-  double x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = st[i];
-  double sth, cth, sps, cps;
-  sincos(x[3], &sth, &cth); sincos(x[4], &sps, &cps);
-  const double v = xs[0];
-  x[0] += A.T * (v * cps * cth); x[1] += A.T * (v * sps * cth); x[2] += A.T * (v * sth);
-#pragma unroll
-  for (int i = 1; i < 6; ++i) x[i + 2] += A.T * xs[i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) st[i] = x[i];
+  double u0[NU];
+  for (int i = 0; i < NU; ++i) u0[i] = xs[i];
   // warm start: drop the first stage, repeat the last (NMPC_TT.py:20-23).  x_sol may alias u_warm.
   double* uw = A.u_warm + (size_t)b * nw;
   for (int k = 0; k < A.N - 1; ++k)
     for (int i = 0; i < NU; ++i) uw[NU * k + i] = xs[NU * (k + 1) + i];
   if (A.u_warm != A.x_sol)
     for (int i = 0; i < NU; ++i) uw[NU * (A.N - 1) + i] = xs[NU * (A.N - 1) + i];
-  double* tg = st + NX;
-  const double tx0 = tg[0], ty0 = tg[1];          // target of THIS step: the error pairs it with the NEXT FOV centre
-  const double tv = A.vw[2 * b], tw = A.vw[2 * b + 1], th = tg[2];
-  tg[0] += A.T * tv * cos(th); tg[1] += A.T * tv * sin(th); tg[2] += A.T * tw;
-  if (A.fov) {
-    const double t6p = tan(x[6] + A.hv), t6m = tan(x[6] - A.hv), t5p = tan(x[5] + A.hh), t5m = tan(x[5] - A.hh);
-    const double a_p = (x[2] * t6p - x[2] * t6m) / 2, b_p = (x[2] * t5p - x[2] * t5m) / 2;
-    const double xe = x[0] + a_p + x[2] * t6m, ye = x[1] + b_p + x[2] * t5m;
-    A.fov[2 * b] = xe; A.fov[2 * b + 1] = ye;
-    if (A.err) A.err[b] += sqrt((xe - tx0) * (xe - tx0) + (ye - ty0) * (ye - ty0));     // NMPC_TT.py:435
-  }
+  closed_loop_shift(A.T, A.hv, A.hh, A.p + (size_t)b * NPAR, u0, A.vw[2 * b], A.vw[2 * b + 1],
+                    A.fov ? A.fov + 2 * (size_t)b : nullptr, A.err ? A.err + b : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,6 +248,7 @@ struct nmpc_handle {
   double* d_bnd;      // relaxed lbx | ubx | lbg | ubg of the current call
   int32_t *d_order, *d_keep_iters; int order_cap, prev_B, auto_order; const int32_t* order_next;
   const double *weights, *tgt;
+  double *fuse_p, *fuse_u, *fuse_fov, *fuse_err; const double* fuse_vw;   // set for the duration of nmpc_solve_and_step
   int* d_counter; unsigned long long* d_stats;
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
@@ -274,7 +256,7 @@ struct nmpc_handle {
   cudaStream_t own_stream, last_stream;
   int64_t launches;
   double* dbg; int dbg_rows;
-  int align_group;
+  int align_group, fill;
 };
 
 extern "C" {
@@ -324,6 +306,8 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     const int g = atoi(e);
     if (g == 0 || (g > 0 && h->warps_per_block % g == 0)) h->align_group = g;
   }
+  h->fill = 1;
+  if (const char* e = getenv("NMPC_B200_FILL")) { const int f = atoi(e); if (f >= 1) h->fill = f; }
   h->auto_order = 1;
   if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
   h->ric_stride = RIC_N * h->pr.N;
@@ -374,7 +358,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
                int32_t* status, int32_t* iters, void* cuda_stream) {
   if (!h) return fail("nmpc_solve: null handle");
   if (B <= 0) return 0;
-  if (!p || !x0 || !lbx || !ubx || !lbg || !ubg || !x) return fail("nmpc_solve: null required pointer");
+  if (!p || !x0 || !lbx || !ubx || !lbg || !ubg || (!x && !h->fuse_p)) return fail("nmpc_solve: null required pointer");
   if (h->pr.n_obs > 0 && !obst) return fail("nmpc_solve: obstacle table required");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)cuda_stream;
@@ -394,6 +378,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
     h->order_cap = B;
   }
   A.iters_keep = h->d_keep_iters;
+  A.step_p = h->fuse_p; A.step_u = h->fuse_u; A.step_vw = h->fuse_vw; A.step_fov = h->fuse_fov; A.step_err = h->fuse_err;
   A.tgt = h->tgt;
   A.weights = h->weights;
   A.align_group = h->align_group;
@@ -410,13 +395,35 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   }
   h->launches = 2;     // nmpc_prologue_kernel + nmpc_ipm_kernel
   h->prev_B = B;
-  const int blocks = B < h->max_blocks ? B : h->max_blocks;
+  // Grid: one block per SM at most; with `fill` > 1 a small batch is packed onto fewer SMs (fill instances per warp,
+  // refilled from the queue) so that concurrent solves of other handles find free SMs instead of SMs held by blocks
+  // whose eight warps wait for one straggler.
+  int blocks = B < h->max_blocks ? B : h->max_blocks;
+  if (h->fill > 1) {
+    const int packed = (B + h->warps_per_block * h->fill - 1) / (h->warps_per_block * h->fill);
+    if (packed < blocks) blocks = packed < 1 ? 1 : packed;
+  }
   {
     const int rc = h->inst->launch(A, blocks, h->smem_bytes, s);
     if (rc != 0) return fail(std::string("nmpc_solve: launch failed: ") + cudaGetErrorString((cudaError_t)rc));
   }
   h->last_stream = s;
   return 0;
+}
+
+int nmpc_solve_and_step(nmpc_handle* h, int32_t B, double* p, double* u_warm,
+                        const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                        const double* obst, uint32_t flags, const double* target_vw,
+                        double* x, double* f, double* fov_centre, double* err_accum,
+                        int32_t* status, int32_t* iters, void* cuda_stream) {
+  if (!h) return fail("nmpc_solve_and_step: null handle");
+  if (!p || !u_warm || !target_vw) return fail("nmpc_solve_and_step: null required pointer");
+  if (err_accum && !fov_centre) return fail("nmpc_solve_and_step: err_accum needs fov_centre");
+  if (x == u_warm) return fail("nmpc_solve_and_step: x must not alias u_warm (pass NULL if the solution itself is not needed)");
+  h->fuse_p = p; h->fuse_u = u_warm; h->fuse_vw = target_vw; h->fuse_fov = fov_centre; h->fuse_err = err_accum;
+  const int rc = nmpc_solve(h, B, p, u_warm, lbx, ubx, lbg, ubg, obst, flags, x, f, nullptr, nullptr, nullptr, status, iters, cuda_stream);
+  h->fuse_p = nullptr; h->fuse_u = nullptr; h->fuse_vw = nullptr; h->fuse_fov = nullptr; h->fuse_err = nullptr;
+  return rc;
 }
 
 int nmpc_solve_host(nmpc_handle* h, int32_t B, const double* p, const double* x0,

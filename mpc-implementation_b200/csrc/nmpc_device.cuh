@@ -290,6 +290,35 @@ __device__ __forceinline__ double stage_cost_d2(const Prob& pr, const double* X,
   return w1 * D + w2 * (U * U + V * V - 1.0);
 }
 
+// Closed-loop shift of ONE instance (NMPC_TT.py:13-30, :399-402, :435): plant Euler step with the first input u0, target
+// Euler step with (tv, tw), FOV centre of the new state and the tracking-error term.  st = [x(8); x_t, y_t, theta_t] in
+// place.  Used by nmpc_step_kernel (one thread per instance) and by the fused epilogue of the IPM kernel (lane 0).
+__device__ __forceinline__ void closed_loop_shift(double T, double hv, double hh, double* st, const double* u0, double tv, double tw,
+                                                  double* fov, double* err) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = st[i];
+  double sth, cth, sps, cps;
+  sincos(x[3], &sth, &cth); sincos(x[4], &sps, &cps);
+  const double v = u0[0];
+  x[0] += T * (v * cps * cth); x[1] += T * (v * sps * cth); x[2] += T * (v * sth);
+#pragma unroll
+  for (int i = 1; i < 6; ++i) x[i + 2] += T * u0[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st[i] = x[i];
+  double* tg = st + NX;
+  const double tx0 = tg[0], ty0 = tg[1];          // target of THIS step: the error pairs it with the NEXT FOV centre
+  const double th = tg[2];
+  tg[0] += T * tv * cos(th); tg[1] += T * tv * sin(th); tg[2] += T * tw;
+  if (fov) {
+    const double t6p = tan(x[6] + hv), t6m = tan(x[6] - hv), t5p = tan(x[5] + hh), t5m = tan(x[5] - hh);
+    const double a_p = (x[2] * t6p - x[2] * t6m) / 2, b_p = (x[2] * t5p - x[2] * t5m) / 2;
+    const double xe = x[0] + a_p + x[2] * t6m, ye = x[1] + b_p + x[2] * t5m;
+    fov[0] = xe; fov[1] = ye;
+    if (err) *err += sqrt((xe - tx0) * (xe - tx0) + (ye - ty0) * (ye - ty0));     // NMPC_TT.py:435
+  }
+}
+
 // 6x6 Cholesky on a packed lower triangle (in place).  Returns false when a pivot is not positive.
 __device__ __forceinline__ bool chol6(double* L, double* inv_diag) {
   bool ok = true;

@@ -41,6 +41,9 @@ struct SolveArgs {
   int32_t *status, *iters;
   const double* weights;             // optional per-instance cost weights [B][2] = (w1, w2); NULL = spec weights
   const double* tgt;                 // optional per-instance, per-stage predicted target [B][N][2]; NULL = p[8:10]
+  // fused closed-loop shift (nmpc_solve_and_step): when step_p != NULL the warp that solved instance b also applies
+  // shift_timestep to it -- p[b] and u_warm[b] in place, FOV centre, error term -- and no nmpc_step launch is needed
+  double *step_p, *step_u; const double* step_vw; double *step_fov, *step_err;
   int32_t* iters_keep;               // handle-owned copy of iters[] (drives the next call's fetch order)
   const int32_t* order;              // optional processing order (longest-first scheduling); NULL = 0..B-1
   int* counter;                      // work queue
@@ -647,11 +650,12 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = 0.0;
   if (hasu) {
-    double* xo = A.x + (size_t)b * nw + NU * lane;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      u[i] = fmin(fmax(LV(LV_U + i), __ldg(A.lbx + NU * lane + i)), __ldg(A.ubx + NU * lane + i));
-      xo[i] = u[i];
+    for (int i = 0; i < 6; ++i) u[i] = fmin(fmax(LV(LV_U + i), __ldg(A.lbx + NU * lane + i)), __ldg(A.ubx + NU * lane + i));
+    if (A.x) {
+      double* xo = A.x + (size_t)b * nw + NU * lane;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xo[i] = u[i];
     }
     if (A.lam_x) {
       double* lo = A.lam_x + (size_t)b * nw + NU * lane;
@@ -681,6 +685,18 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
 #pragma unroll 1
       for (int r = 0; r < R; ++r) lo[r] = RW(A_Y, r) * RW(A_DC, r) * idf;
     }
+  }
+  if (A.step_p) {     // fused closed-loop shift of this instance (NMPC_TT.py:13-30): warm start, plant, target, FOV error
+    double* uw = A.step_u + (size_t)b * nw;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double un = __shfl_down_sync(FULL, u[i], 1);          // control of the next stage
+      if (lane < N - 1) uw[NU * lane + i] = un;                   // drop the first stage ...
+      else if (lane == N - 1) uw[NU * lane + i] = u[i];           // ... and repeat the last (:20-23)
+    }
+    if (lane == 0)
+      closed_loop_shift(pr.T, pr.hv, pr.hh, A.step_p + (size_t)b * NPAR, u, __ldg(A.step_vw + 2 * (size_t)b), __ldg(A.step_vw + 2 * (size_t)b + 1),
+                        A.step_fov ? A.step_fov + 2 * (size_t)b : nullptr, A.step_err ? A.step_err + b : nullptr);
   }
   __syncwarp();
 }

@@ -337,6 +337,35 @@ class Solver:
         return dict(f=f, g=g, grad=grad, jtv=jtv, hv=hv)
 
     # -- shift_timestep (NMPC_TT.py:13-30) on device --------------------------------------------
+    def solve_and_step(self, p, u_warm, lbx, ubx, lbg, ubg, target_vw, fov_centre=None, err_accum=None, obstacles=None,
+                       want_x: bool = False):
+        """One closed-loop step of B instances in ONE kernel launch (nmpc_solve_and_step): solves from the warm start
+        u_warm with parameters p, then shifts p / u_warm in place (torch CUDA float64 tensors).  Returns dict(x, f)
+        with x None unless want_x; status / iterations through stats()."""
+        L = _ffi.lib()
+        dev = p.device
+        B = p.shape[0]
+        lbx, ubx = self._dev_const("lbx", lbx), self._dev_const("ubx", ubx)
+        lbg, ubg = self._dev_const("lbg", lbg), self._dev_const("ubg", ubg)
+        flags = 0
+        if obstacles is None:
+            obs = self._dev_const("obs", self.obstacles)
+        else:
+            obs = obstacles.to(torch.float64).contiguous()
+            flags = _ffi.NMPC_OBS_PER_INSTANCE if obs.numel() == 3 * self.n_obs * B and B > 1 else 0
+        x = torch.empty((B, self.n_w), dtype=torch.float64, device=dev) if want_x else None
+        f = torch.empty(B, dtype=torch.float64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _ffi.check(L.nmpc_solve_and_step(self._h, B, ptr(p), ptr(u_warm), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
+                                         ptr(target_vw), ptr(x), ptr(f), ptr(fov_centre), ptr(err_accum), ptr(status), ptr(iters),
+                                         stream), "nmpc_solve_and_step")
+        self._keep = (obs,)
+        self._stats = dict(return_status=status, iter_count=iters)
+        return dict(x=x, f=f, g=None, lam_x=None, lam_g=None)
+
     def step(self, x_sol, p, u_warm, target_vw, fov_centre=None, err_accum=None):
         """In-place closed-loop shift of B instances (torch CUDA float64 tensors): p [B,11], u_warm [B,6N];
         err_accum [B] += ||new FOV centre - this step's target|| (NMPC_TT.py:435)."""
