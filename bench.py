@@ -163,7 +163,7 @@ def run_b200(args, rank, world, local_rank):
     # overlap with the next one's bulk; per-instance results are those of the single-batch loop (tests/test_gpu_parity.py)
     cl = PipelinedClosedLoop(mk, sc, p, target_vw=vw, pipelines=S)
     solver = cl.loops[0].solver
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)    # > 126 MB L2
+    flush = torch.empty(144 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)    # 151 MB > 126 MB L2
 
     def barrier():
         if world > 1:
@@ -324,7 +324,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}, n_w={sc.n_w}, n_g={sc.n_g}) closed loop: "
                                f"{B} randomised UAV states / target speeds per GPU (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
-                   "pipelines": S, "l2": "flushed before every sub-batch step (256 MB write)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (nmpc_order_kernel inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
+                   "pipelines": S, "l2": "flushed before every sub-batch step (151 MB write > 126 MB L2)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (nmpc_order_kernel inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
         "p50_step_ms": float(np.median(step_ms)), "p50_solve_kernel_ms": float(np.median(solve_ms)),
         "p50_note": "per sub-batch: stream time from the start of its solve to the end of its shift / of its solve kernel",
         "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
