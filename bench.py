@@ -324,7 +324,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{sc.script} NLP (T={sc.T}, N={sc.N}, n_obs={sc.n_obs}, n_w={sc.n_w}, n_g={sc.n_g}) closed loop: "
                                f"{B} randomised UAV states / target speeds per GPU (BASELINE.json configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instances sharded over {world} GPU(s), no collective on the solve path",
-                   "pipelines": S, "l2": "flushed before every sub-batch step (151 MB write > 126 MB L2)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (nmpc_order_kernel inside the timed region)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
+                   "pipelines": S, "l2": "flushed before every sub-batch step (151 MB write > 126 MB L2)", "scheduling": "natural order" if args.no_lpt else "longest-first by the previous step's iteration counts (written by the previous launch's last warp)", "ipopt_options": "max_iter=100 tol=1e-8 (NMPC_TT.py:257-265)"},
         "p50_step_ms": float(np.median(step_ms)), "p50_solve_kernel_ms": float(np.median(solve_ms)),
         "p50_note": "per sub-batch: stream time from the start of its solve to the end of its shift / of its solve kernel",
         "converged_fraction": conv_all / (B * world * K), "mean_iters": iters_all / (B * world * K),
@@ -332,7 +332,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms,
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=, blocking=False) with pinned numpy buffers -> nmpc_solve_host_async / nmpc_synchronize, one solver per sub-batch"},
-        "gpu_launches": (3 if args.unfused_step else 2) * K * S,     # nmpc_prologue_kernel, nmpc_ipm_kernel (with the shift in its epilogue) [, nmpc_step_kernel] per sub-batch step
+        "gpu_launches": (2 if args.unfused_step else 1) * K * S,     # nmpc_ipm_kernel (solve + shift + next call's fetch order) [, nmpc_step_kernel] per sub-batch step
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": bytes_per_solve(sc.N, sc.n_obs) * len(cl.index[0]),
                      "kernel": "nmpc_ipm_kernel", "kernel_ms": k_ms, "launches_per_step": S, "peak_source": which,

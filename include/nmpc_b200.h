@@ -151,7 +151,8 @@ int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out);   /* synchronises the handl
 /* Scheduling.  The persistent kernel fetches instances from a queue; the step ends when the last straggler does, so
  * long solves should start first.  By default the library orders the queue itself: when a call has the same B as
  * the previous call on this handle (a closed loop), instances are fetched by the previous call's iteration counts,
- * longest first (a small counting-sort kernel; NMPC_B200_AUTO_ORDER=0 in the environment disables it).
+ * longest first (a counting sort done by the previous launch's last warp; NMPC_B200_AUTO_ORDER=0 in the environment
+ * disables it).
  * nmpc_set_order overrides this for the NEXT nmpc_solve only: dev_order [B] is a permutation of 0..B-1.
  * Results never depend on the order (instances are independent); only the tail of the batch step does. */
 int nmpc_set_order(nmpc_handle* h, const int32_t* dev_order);

@@ -178,40 +178,6 @@ struct StepArgs {
   const double* x_sol; double *p, *u_warm; const double* vw; double *fov, *err;
 };
 
-// Prologue of a solve, ONE launch (every extra small kernel of a call has to wait for a free SM slot next to the
-// persistent blocks of whatever other handles are running on the device):
-//   block 0      resets the work queue and the work counters and, if asked, writes the longest-first fetch order from
-//                the previous call's iteration counts (counting sort, descending; the order inside a bin is arbitrary
-//                -- results do not depend on it);
-//   blocks 1..   relaxed bounds (IPOPT bound_relax_factor) of the batch-shared bound vectors, which the IPM phases then
-//                load instead of redoing the arithmetic per row and phase (nmpc_solve.cuh: ctl_bounds / row_bounds;
-//                same intrinsics, so bit-identical to the in-kernel formula used for scaled rows).
-__global__ void __launch_bounds__(1024) nmpc_prologue_kernel(const double* __restrict__ lbx, const double* __restrict__ ubx,
-                                                             const double* __restrict__ lbg, const double* __restrict__ ubg,
-                                                             int nw, int ng, double relax, double* __restrict__ out,
-                                                             const int32_t* __restrict__ iters, int B, int32_t* __restrict__ order,
-                                                             int* counter, unsigned long long* stats) {
-  if (blockIdx.x > 0) {
-    const int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
-    if (i < nw) { out[i] = relaxed_lo(lbx[i], relax); out[nw + i] = relaxed_hi(ubx[i], relax); }
-    if (i < ng) { out[2 * nw + i] = relaxed_lo(lbg[i], relax); out[2 * nw + ng + i] = relaxed_hi(ubg[i], relax); }
-    return;
-  }
-  if (threadIdx.x == 0) { *counter = 0; stats[0] = 0; stats[1] = 0; stats[2] = 0; }
-  if (!order) return;
-  __shared__ int bin[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) bin[i] = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&bin[min(max(iters[i], 0), 255)], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int v = 255; v >= 0; --v) { const int c = bin[v]; bin[v] = acc; acc += c; }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x) order[atomicAdd(&bin[min(max(iters[i], 0), 255)], 1)] = i;
-}
-
 __global__ void nmpc_step_kernel(const StepArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
@@ -245,11 +211,13 @@ struct nmpc_handle {
   Prob pr; Opt opt;
   const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
   double* d_ric; int ric_stride; unsigned* d_ricmap;
-  double* d_bnd;      // relaxed lbx | ubx | lbg | ubg of the current call
-  int32_t *d_order, *d_keep_iters; int order_cap, prev_B, auto_order; const int32_t* order_next;
+  // per-call bookkeeping, double-buffered by call parity: the launch of call n resets / produces the buffers of call n+1
+  int32_t *d_order[2], *d_keep_iters; int order_cap, prev_B, auto_order, parity, have_order; const int32_t* order_next;
   const double *weights, *tgt;
   double *fuse_p, *fuse_u, *fuse_fov, *fuse_err; const double* fuse_vw;   // set for the duration of nmpc_solve_and_step
-  int* d_counter; unsigned long long* d_stats;
+  int* d_counter;                  // [4]: queue counter x2, done counter x2
+  unsigned long long* d_stats;     // [2][3]
+  unsigned long long* stats_last;  // the half written by the last call
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
   int32_t *d_status, *d_iters; size_t obs_cap;
@@ -318,10 +286,10 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     if (rc != 0) { nmpc_destroy(h); return fail(std::string("nmpc_create: map kernel failed: ") + cudaGetErrorString((cudaError_t)rc)); }
     CK(cudaDeviceSynchronize());
   }
-  CK(cudaMalloc(&h->d_bnd, sizeof(double) * 2 * (NU * h->pr.N + (size_t)h->pr.R * h->pr.S)));
-  CK(cudaMalloc(&h->d_counter, sizeof(int)));
-  CK(cudaMalloc(&h->d_stats, 3 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->d_stats, 0, 3 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));
+  CK(cudaMemset(h->d_counter, 0, 4 * sizeof(int)));
+  CK(cudaMalloc(&h->d_stats, 6 * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_stats, 0, 6 * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   const int mb = spec->max_batch > 0 ? spec->max_batch : 0;
   if (mb > 0) {
@@ -344,7 +312,7 @@ int nmpc_destroy(nmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_ric, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
-                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order, h->d_keep_iters, h->d_ricmap, h->d_bnd};
+                  h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order[0], h->d_order[1], h->d_keep_iters, h->d_ricmap};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -367,14 +335,20 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.p = p; A.x0 = x0; A.lbx = lbx; A.ubx = ubx; A.lbg = lbg; A.ubg = ubg; A.obs = obst;
   A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
   A.x = x; A.f = f; A.g = g; A.lam_x = lam_x; A.lam_g = lam_g; A.status = status; A.iters = iters;
-  A.counter = h->d_counter; A.stats = h->d_stats;
+  const int par = h->parity; h->parity ^= 1;
+  A.counter = h->d_counter + par; A.counter_next = h->d_counter + (par ^ 1);
+  A.done = h->d_counter + 2 + par; A.done_next = h->d_counter + 2 + (par ^ 1);
+  A.stats = h->d_stats + 3 * par; A.stats_next = h->d_stats + 3 * (par ^ 1);
+  h->stats_last = h->d_stats + 3 * par;
   A.ric = h->d_ric; A.ric_stride = h->ric_stride; A.ricmap = h->d_ricmap;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
   if (B > h->order_cap) {     // (re)allocate the scheduling buffers; the previous counts are dropped
-    if (h->d_order) cudaFree(h->d_order);
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < 2; ++i) { if (h->d_order[i]) cudaFree(h->d_order[i]); h->d_order[i] = nullptr; }
     if (h->d_keep_iters) cudaFree(h->d_keep_iters);
-    h->d_order = nullptr; h->d_keep_iters = nullptr; h->order_cap = 0; h->prev_B = 0;
-    CK(cudaMalloc(&h->d_order, sizeof(int32_t) * B)); CK(cudaMalloc(&h->d_keep_iters, sizeof(int32_t) * B));
+    h->d_keep_iters = nullptr; h->order_cap = 0; h->prev_B = 0; h->have_order = 0;
+    CK(cudaMalloc(&h->d_order[0], sizeof(int32_t) * B)); CK(cudaMalloc(&h->d_order[1], sizeof(int32_t) * B));
+    CK(cudaMalloc(&h->d_keep_iters, sizeof(int32_t) * B));
     h->order_cap = B;
   }
   A.iters_keep = h->d_keep_iters;
@@ -382,18 +356,12 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.tgt = h->tgt;
   A.weights = h->weights;
   A.align_group = h->align_group;
+  // fetch order: explicit (nmpc_set_order) > the order the previous call on this handle prepared for the same B > natural
   A.order = h->order_next; h->order_next = nullptr;
-  {
-    const int nw = NU * h->pr.N, ng = h->pr.R * h->pr.S, n = nw > ng ? nw : ng;
-    int32_t* make_order = nullptr;
-    if (!A.order && h->auto_order && h->prev_B == B) {   // same batch as last time: start last time's longest solves first
-      make_order = h->d_order; A.order = h->d_order;
-    }
-    nmpc_prologue_kernel<<<1 + (n + 1023) / 1024, 1024, 0, s>>>(lbx, ubx, lbg, ubg, nw, ng, h->opt.bound_relax, h->d_bnd,
-                                                                   h->d_keep_iters, B, make_order, h->d_counter, h->d_stats);
-    A.xlo_r = h->d_bnd; A.xhi_r = h->d_bnd + nw; A.glo_r = h->d_bnd + 2 * nw; A.ghi_r = h->d_bnd + 2 * nw + ng;
-  }
-  h->launches = 2;     // nmpc_prologue_kernel + nmpc_ipm_kernel
+  if (!A.order && h->auto_order && h->have_order && h->prev_B == B) A.order = h->d_order[par];
+  A.order_out = h->auto_order ? h->d_order[par ^ 1] : nullptr;       // ... and this call prepares the next one's
+  h->have_order = h->auto_order;
+  h->launches = 1;
   h->prev_B = B;
   // Grid: one block per SM at most; with `fill` > 1 a small batch is packed onto fewer SMs (fill instances per warp,
   // refilled from the queue) so that concurrent solves of other handles find free SMs instead of SMs held by blocks
@@ -539,7 +507,7 @@ int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->last_stream));
   unsigned long long st[3];
-  CK(cudaMemcpy(st, h->d_stats, sizeof st, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(st, h->stats_last ? h->stats_last : h->d_stats, sizeof st, cudaMemcpyDeviceToHost));
   out->kernel_launches = h->launches; out->factorizations = (int64_t)st[0]; out->ls_trials = (int64_t)st[1]; out->soc_accepted = (int64_t)st[2];
   return 0;
 }

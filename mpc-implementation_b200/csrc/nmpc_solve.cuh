@@ -34,8 +34,6 @@ struct SolveArgs {
   Prob pr; Opt o;
   int B;
   const double *p, *x0, *lbx, *ubx, *lbg, *ubg, *obs;
-  const double *xlo_r, *xhi_r, *glo_r, *ghi_r;   // relaxed bounds (-inf / +inf = none), computed once per call by
-                                                 // nmpc_relax_bounds_kernel with relaxed_lo / relaxed_hi below; g: for d_c = 1
   int obs_per_instance;
   double *x, *f, *g, *lam_x, *lam_g;
   int32_t *status, *iters;
@@ -46,7 +44,13 @@ struct SolveArgs {
   double *step_p, *step_u; const double* step_vw; double *step_fov, *step_err;
   int32_t* iters_keep;               // handle-owned copy of iters[] (drives the next call's fetch order)
   const int32_t* order;              // optional processing order (longest-first scheduling); NULL = 0..B-1
-  int* counter;                      // work queue
+  int* counter;                      // work queue of THIS call
+  // Bookkeeping for the NEXT call on the same handle is done by this launch, so that a solve is ONE launch: the first
+  // thread resets the next call's queue / done / work counters (calls on a handle are stream-ordered), and the warp that
+  // finishes the last instance writes the next call's longest-first fetch order from this call's iteration counts.
+  int *counter_next, *done, *done_next;
+  unsigned long long* stats_next;
+  int32_t* order_out;                // may be NULL (no automatic ordering)
   unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
   double* ric; int ric_stride;       // L2-resident Riccati scratch, one slice per resident warp
   const unsigned* ricmap;            // per-lane ownership maps of the factorisation (nmpc_riccati.cuh: ric_map_build)
@@ -76,20 +80,16 @@ struct Bnd { double lo, hi; bool hl, hu; };
 __device__ __forceinline__ double relaxed_lo(double lo, double relax) { return lo > -1e19 ? __dsub_rn(lo, __dmul_rn(relax, fmax(1.0, fabs(lo)))) : -CUDART_INF; }
 __device__ __forceinline__ double relaxed_hi(double hi, double relax) { return hi < 1e19 ? __dadd_rn(hi, __dmul_rn(relax, fmax(1.0, fabs(hi)))) : CUDART_INF; }
 __device__ __forceinline__ Bnd ctl_bounds(const SolveArgs& A, int k, int i) {
-  Bnd b; b.lo = __ldg(A.xlo_r + NU * k + i); b.hi = __ldg(A.xhi_r + NU * k + i);
+  Bnd b; b.lo = relaxed_lo(__ldg(A.lbx + NU * k + i), A.o.bound_relax); b.hi = relaxed_hi(__ldg(A.ubx + NU * k + i), A.o.bound_relax);
   b.hl = b.lo > -CUDART_INF; b.hu = b.hi < CUDART_INF;
   return b;
 }
 template <class L>
 __device__ __forceinline__ Bnd row_bounds(const SolveArgs& A, int k, int r, double dc) {
+  const double lo = __ldg(A.lbg + k * L::R + r), hi = __ldg(A.ubg + k * L::R + r);
   Bnd b;
-  if (dc == 1.0) {          // the usual case: the scaled row is the row, its relaxed bounds are batch-shared
-    b.lo = __ldg(A.glo_r + k * L::R + r); b.hi = __ldg(A.ghi_r + k * L::R + r);
-  } else {
-    const double lo = __ldg(A.lbg + k * L::R + r), hi = __ldg(A.ubg + k * L::R + r);
-    b.lo = relaxed_lo(lo > -1e19 ? __dmul_rn(dc, lo) : lo, A.o.bound_relax);
-    b.hi = relaxed_hi(hi < 1e19 ? __dmul_rn(dc, hi) : hi, A.o.bound_relax);
-  }
+  b.lo = relaxed_lo(lo > -1e19 ? __dmul_rn(dc, lo) : lo, A.o.bound_relax);
+  b.hi = relaxed_hi(hi < 1e19 ? __dmul_rn(dc, hi) : hi, A.o.bound_relax);
   b.hl = b.lo > -CUDART_INF; b.hu = b.hi < CUDART_INF;
   return b;
 }
@@ -873,12 +873,34 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
   if (lane == 0 && A.stats) { atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); }
 }
 
+// Longest-first fetch order for the NEXT call on this handle from this call's iteration counts: counting sort,
+// descending, by the warp that finished the call's last instance (its shared-memory slice is free; the order inside a
+// bin is arbitrary -- results do not depend on it).
+template <class L>
+__device__ __noinline__ void next_order(const SolveArgs& A, int lane) {
+  int* bin = reinterpret_cast<int*>(&smem[0]);          // 256 ints
+  for (int i = lane; i < 256; i += 32) bin[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < A.B; i += 32) atomicAdd(&bin[min(max(__ldcg(A.iters_keep + i), 0), 255)], 1);
+  __syncwarp();
+  if (lane == 0) {
+    int acc = 0;
+    for (int v = 255; v >= 0; --v) { const int c = bin[v]; bin[v] = acc; acc += c; }
+  }
+  __syncwarp();
+  for (int i = lane; i < A.B; i += 32) A.order_out[atomicAdd(&bin[min(max(__ldcg(A.iters_keep + i), 0), 255)], 1)] = i;
+  __syncwarp();
+}
+
 // persistent kernel: Lay::WPB warps per block (one block per SM), one instance per warp at a time, instances from
 // an atomic work queue (optionally in a caller-given order)
 template <int N_, int NOBS_>
 __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(const SolveArgs A) {
   using L = Lay<N_, NOBS_>;
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next call on this handle starts from clean counters
+    *A.counter_next = 0; *A.done_next = 0; A.stats_next[0] = 0; A.stats_next[1] = 0; A.stats_next[2] = 0;
+  }
   double* ric = A.ric + (size_t)(blockIdx.x * L::WPB + (threadIdx.x >> 5)) * A.ric_stride;
   for (;;) {
     int q = 0;
@@ -888,6 +910,10 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
     const int b = A.order ? A.order[q] : q;
     solve_instance<L>(A, ric, b, lane);
     __syncwarp();
+    int fin = 0;
+    if (lane == 0) { __threadfence(); fin = atomicAdd(A.done, 1); }      // this instance's outputs are visible before the count
+    fin = __shfl_sync(FULL, fin, 0);
+    if (fin == A.B - 1 && A.order_out) next_order<L>(A, lane);           // last instance of the call
   }
   while (align_warps(A.align_group, 0)) {}   // out of work: keep matching the alignment barrier until the group is done
 }
