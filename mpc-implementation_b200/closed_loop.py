@@ -80,12 +80,13 @@ class ClosedLoop:
         return torch.argsort(it, descending=True)
 
     def step(self, want_g: bool = False, want_lam: bool = False, want_x: bool = True):
-        """One closed-loop batch step; returns the solver output dict (device tensors).  Without g / multipliers /
-        target prediction the solve and the shift are one launch (nmpc_solve_and_step)."""
+        """One closed-loop batch step; returns the solver output dict (device tensors).  Without g / multipliers
+        the solve and the shift are one launch (nmpc_solve_and_step)."""
         self._schedule_vw()
-        if not (want_g or want_lam or self.predict_target):
+        if not (want_g or want_lam):
             sol = self.solver.solve_and_step(self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg, self.vw, self.fov,
-                                             self.err_sum, want_x=want_x)
+                                             self.err_sum, want_x=want_x,
+                                             target_traj=self.target_prediction() if self.predict_target else None)
             self.mpc_iter += 1
             self.last = sol
             return sol

@@ -338,7 +338,13 @@ class Solver:
 
     # -- shift_timestep (NMPC_TT.py:13-30) on device --------------------------------------------
     def solve_and_step(self, p, u_warm, lbx, ubx, lbg, ubg, target_vw, fov_centre=None, err_accum=None, obstacles=None,
-                       want_x: bool = False):
+                       want_x: bool = False, weights=None, target_traj=None):
+        if weights is not None or target_traj is not None:
+            with self._weights(weights, p), self._traj(target_traj, p):
+                return self.solve_and_step(p, u_warm, lbx, ubx, lbg, ubg, target_vw, fov_centre, err_accum, obstacles, want_x)
+        return self._solve_and_step(p, u_warm, lbx, ubx, lbg, ubg, target_vw, fov_centre, err_accum, obstacles, want_x)
+
+    def _solve_and_step(self, p, u_warm, lbx, ubx, lbg, ubg, target_vw, fov_centre, err_accum, obstacles, want_x):
         """One closed-loop step of B instances in ONE kernel launch (nmpc_solve_and_step): solves from the warm start
         u_warm with parameters p, then shifts p / u_warm in place (torch CUDA float64 tensors).  Returns dict(x, f)
         with x None unless want_x; status / iterations through stats()."""
