@@ -158,7 +158,9 @@ def run_b200(args, rank, world, local_rank):
     # sub-batches: measured best 8 at B = 4096, 2 at B = 16384 (tools/pipeline_probe.py): about 32768 / B, at most 8
     S = max(1, min(args.pipelines, B)) if args.pipelines > 0 else max(1, min(8, 32768 // max(B, 1)))
     p, vw = b200nmpc.random_instances(sc, B, seed=2000 + rank)
-    mk = lambda n: b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=n)
+    # fill = 2: a sub-batch occupies half as many SMs as it has warps' worth of instances, leaving SMs to the other sub-batches
+    mk = lambda n: b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=n,
+                                   fill=2 if S > 1 else 1)
     # the batch advances as S independently pipelined sub-batches (own handle + stream each): one sub-batch's stragglers
     # overlap with the next one's bulk; per-instance results are those of the single-batch loop (tests/test_gpu_parity.py)
     cl = PipelinedClosedLoop(mk, sc, p, target_vw=vw, pipelines=S)

@@ -62,7 +62,9 @@ typedef struct nmpc_spec {
   int32_t scaling;     /* 1 = gradient-based NLP scaling (IPOPT default) */
   double tol;          /* 1e-8 */
   int32_t max_batch;   /* largest B any call will pass */
-  int32_t reserved;
+  int32_t fill;        /* scheduling hint, 0 or 1 = default: a batch smaller than the machine is spread over as many SMs as it
+                          has instances; k > 1 packs it onto fewer SMs, k instances per resident warp (refilled from the
+                          queue), which leaves SMs to the concurrent solves of other handles (pipelined sub-batches) */
 } nmpc_spec;
 
 typedef struct nmpc_handle nmpc_handle;

@@ -23,7 +23,7 @@ class NmpcSpec(C.Structure):
     _fields_ = [("T", C.c_double), ("N", C.c_int32), ("n_obs", C.c_int32),
                 ("w1", C.c_double), ("w2", C.c_double), ("vfov", C.c_double), ("hfov", C.c_double),
                 ("max_iter", C.c_int32), ("scaling", C.c_int32), ("tol", C.c_double),
-                ("max_batch", C.c_int32), ("reserved", C.c_int32)]
+                ("max_batch", C.c_int32), ("fill", C.c_int32)]
 
 
 class NmpcStats(C.Structure):

@@ -274,8 +274,8 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     const int g = atoi(e);
     if (g == 0 || (g > 0 && h->warps_per_block % g == 0)) h->align_group = g;
   }
-  h->fill = 1;
-  if (const char* e = getenv("NMPC_B200_FILL")) { const int f = atoi(e); if (f >= 1) h->fill = f; }
+  h->fill = spec->fill > 1 ? spec->fill : 1;
+  if (const char* e = getenv("NMPC_B200_FILL")) { const int f = atoi(e); if (f >= 1) h->fill = f; }   // tuning override
   h->auto_order = 1;
   if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
   h->ric_stride = RIC_N * h->pr.N;

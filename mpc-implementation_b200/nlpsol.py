@@ -56,8 +56,9 @@ def _spec_from(problem, opts: Optional[dict]) -> Dict[str, Any]:
 class Solver:
     """Callable returned by nlpsol(); owns one nmpc_handle."""
 
-    def __init__(self, name: str, problem, opts: Optional[dict] = None, device: int = 0, max_batch: int = 1):
+    def __init__(self, name: str, problem, opts: Optional[dict] = None, device: int = 0, max_batch: int = 1, fill: int = 1):
         self.name = name
+        self.fill = int(fill)
         d = _spec_from(problem, opts)
         self.T, self.N = float(d["T"]), int(d["N"])
         self.obstacles = np.ascontiguousarray(d["obstacles"], dtype=np.float64)
@@ -80,7 +81,7 @@ class Solver:
         d = self._d
         spec = _ffi.NmpcSpec(self.T, self.N, self.n_obs, float(d.get("w1", 1.0)), float(d.get("w2", 2.0)),
                              float(d.get("vfov", 1.0)), float(d.get("hfov", 1.0)),
-                             d["max_iter"], d["scaling"], d["tol"], int(max_batch), 0)
+                             d["max_iter"], d["scaling"], d["tol"], int(max_batch), self.fill)
         _ffi.check(L.nmpc_create(C.byref(spec), self.device, C.byref(self._h)), "nmpc_create")
         self._max_batch = max_batch
         self.spec = spec
@@ -384,12 +385,14 @@ class Solver:
                    "nmpc_step")
 
 
-def nlpsol(name: str, plugin: str, problem, opts: Optional[dict] = None, device: int = 0, max_batch: int = 1) -> Solver:
+def nlpsol(name: str, plugin: str, problem, opts: Optional[dict] = None, device: int = 0, max_batch: int = 1,
+           fill: int = 1) -> Solver:
     """Mirror of ca.nlpsol(name, 'ipopt', nlp_prob, opts) (NMPC_TT.py:267).
 
     plugin: 'ipm' (or 'ipopt' for drop-in spelling) -- the in-kernel interior-point method.
     problem: a scenarios.Scenario or a dict(T=, N=, obstacles=[(cx,cy,r_obs)...], uav_r=5, w1=1, w2=2).
-    opts: {'ipopt': {'max_iter': 100, ...}} as in the reference; unknown keys are ignored like print_level."""
+    opts: {'ipopt': {'max_iter': 100, ...}} as in the reference; unknown keys are ignored like print_level.
+    fill: scheduling hint for solvers that run next to others (PipelinedClosedLoop): instances per resident warp."""
     if plugin not in ("ipm", "ipopt"):
         raise ValueError(f"nlpsol: unknown plugin '{plugin}' (only the in-kernel 'ipm' exists)")
-    return Solver(name, problem, opts, device=device, max_batch=max_batch)
+    return Solver(name, problem, opts, device=device, max_batch=max_batch, fill=fill)

@@ -65,7 +65,7 @@ def test_no_cpu_fallback(pkg):
 def test_spec_struct_layout_matches_header(pkg):
     """ctypes mirror of struct nmpc_spec has the field order / size the C header implies."""
     f = [n for n, _ in pkg._ffi.NmpcSpec._fields_]
-    assert f == ["T", "N", "n_obs", "w1", "w2", "vfov", "hfov", "max_iter", "scaling", "tol", "max_batch", "reserved"]
+    assert f == ["T", "N", "n_obs", "w1", "w2", "vfov", "hfov", "max_iter", "scaling", "tol", "max_batch", "fill"]
     assert ctypes.sizeof(pkg._ffi.NmpcSpec) == 72
 
 
