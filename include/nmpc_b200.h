@@ -109,6 +109,7 @@ int nmpc_solve_host_async(nmpc_handle* h, int32_t B,
                           double* x, double* f, double* g, double* lam_x, double* lam_g,
                           int32_t* status, int32_t* iters);
 int nmpc_synchronize(nmpc_handle* h);   /* waits for the handle's own stream */
+int nmpc_query(nmpc_handle* h, int32_t* busy);   /* *busy = 1 while an asynchronous host call is still in flight; never blocks */
 
 /* Function-level evaluation (what CasADi's generated nlp_f / nlp_g / nlp_grad_f / nlp_hess_l
  * compute for IPOPT): at w [B][6N], p [B][11]

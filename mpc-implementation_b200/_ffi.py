@@ -31,7 +31,7 @@ class NmpcStats(C.Structure):
                 ("ls_trials", C.c_int64), ("soc_accepted", C.c_int64)]
 
 
-EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_solve_and_step", "nmpc_eval", "nmpc_step",
+EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_eval", "nmpc_step",
            "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
            "nmpc_last_error", "nmpc_version"]
 
@@ -60,6 +60,7 @@ def lib():
     L.nmpc_solve_host.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7
     L.nmpc_solve_host_async.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7
     L.nmpc_synchronize.argtypes = [vp]
+    L.nmpc_query.argtypes = [vp, C.POINTER(C.c_int32)]
     L.nmpc_solve_and_step.argtypes = [vp, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 7 + [vp]
     L.nmpc_eval.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_uint32, C.c_double, vp, vp] + [vp] * 5 + [vp]
     L.nmpc_step.argtypes = [vp, C.c_int32] + [vp] * 6 + [vp]

@@ -410,6 +410,15 @@ int nmpc_synchronize(nmpc_handle* h) {
   return 0;
 }
 
+int nmpc_query(nmpc_handle* h, int32_t* busy) {
+  if (!h || !busy) return fail("nmpc_query: null argument");
+  CK(cudaSetDevice(h->device));
+  const cudaError_t e = cudaStreamQuery(h->own_stream);
+  if (e != cudaSuccess && e != cudaErrorNotReady) return fail(std::string("nmpc_query: ") + cudaGetErrorString(e));
+  *busy = e == cudaErrorNotReady ? 1 : 0;
+  return 0;
+}
+
 int nmpc_solve_host_async(nmpc_handle* h, int32_t B, const double* p, const double* x0,
                           const double* lbx, const double* ubx, const double* lbg, const double* ubg,
                           const double* obst, uint32_t flags,

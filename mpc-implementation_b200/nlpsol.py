@@ -144,6 +144,12 @@ class Solver:
         """Complete a blocking=False call (nmpc_synchronize)."""
         _ffi.check(_ffi.lib().nmpc_synchronize(self._h), "nmpc_synchronize")
 
+    def done(self) -> bool:
+        """True when no blocking=False call is in flight any more (nmpc_query; never blocks)."""
+        busy = C.c_int32(0)
+        _ffi.check(_ffi.lib().nmpc_query(self._h, C.byref(busy)), "nmpc_query")
+        return busy.value == 0
+
     def _pinned(self, key: str, shape, dtype=np.float64):
         """Page-locked output buffer, cached per (name, shape)."""
         k = ("pin", key, tuple(shape), np.dtype(dtype).str)
