@@ -22,3 +22,6 @@ SCENARIOS = _pkg.SCENARIOS
 scenarios = _pkg.scenarios
 random_instances = _pkg.random_instances
 _ffi = _pkg._ffi
+
+# closed-loop drivers (need torch + a GPU at call time, not at import time)
+from mpc_implementation_b200.closed_loop import ClosedLoop, PipelinedClosedLoop  # noqa: E402

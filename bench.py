@@ -156,7 +156,7 @@ def run_b200(args, rank, world, local_rank):
     if args.no_lpt:
         os.environ["NMPC_B200_AUTO_ORDER"] = "0"
     # sub-batches: measured best 8 at B = 4096, 2 at B = 16384 (tools/pipeline_probe.py): about 32768 / B, at most 8
-    S = max(1, min(args.pipelines, B)) if args.pipelines > 0 else max(1, min(8, 32768 // max(B, 1)))
+    S = max(1, min(args.pipelines, B)) if args.pipelines > 0 else max(1, min(8, 32768 // max(B, 1)))     # PipelinedClosedLoop default
     p, vw = b200nmpc.random_instances(sc, B, seed=2000 + rank)
     # fill = 2: a sub-batch occupies half as many SMs as it has warps' worth of instances, leaving SMs to the other sub-batches
     mk = lambda n: b200nmpc.nlpsol("solver", "ipm", sc, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=n,
