@@ -2,7 +2,8 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 //
 // Kernels
-//   nmpc_ipm_kernel   persistent, one warp per NLP instance, whole IPM loop in-kernel (nmpc_solve.cuh)
+//   nmpc_ipm_kernel   persistent, one warp per NLP instance, whole IPM loop in-kernel (nmpc_solve.cuh / nmpc_inst.cu);
+//                     optionally the closed-loop shift in its epilogue (nmpc_solve_and_step)
 //   nmpc_eval_kernel  function-level f / g / grad f / J^T lam / Hess_L v  (one warp per instance)
 //   nmpc_step_kernel  closed-loop shift (NMPC_TT.py:13-30) + FOV centre (:399-402), one thread per instance
 #include <cuda_runtime.h>

@@ -6,8 +6,8 @@
 //   * stage cost (NMPC_TT.py:193-221) in its compact form  w1*dist + w2*((P/a)^2 + (Q/b)^2 - 1)
 //     with hand-derived gradient and Hessian (chain rule through the intermediates (Dx, Dy, a, b, X7)).
 //   * Newton step of the reduced (single-shooting) primal-dual system = stage-structured LQ problem,
-//     solved by a Riccati recursion whose 8x8 / 6x8 / 6x6 blocks are spread over lanes 0..8
-//     (lane j = column j of [P | p]); cross-column operands are staged through shared memory.
+//     solved by a Riccati recursion (nmpc_riccati.cuh): per stage a 15 x 15 matrix built by all 32 lanes, a 6 x 6
+//     Cholesky in registers, 9 forward/back substitutions and a 44-entry trailing update.
 // Code-size discipline: transcendental functions and the big phases are __noinline__ so that every
 // heavy instruction sequence exists once (v1 was 785 KB of SASS and stalled on instruction fetch).
 #pragma once

@@ -6,9 +6,12 @@
 // monotone barrier, fraction-to-boundary, inertia correction, filter line search + second-order
 // correction, scaled optimality-error termination.  The whole iteration loop runs inside the kernel.
 //
-// Structure (v3): the iterate lives in shared memory at compile-time offsets (Lay<N, NOBS>); every phase is a
-// __noinline__ function template that loads its operands, works in registers and stores back, so each heavy
-// code sequence exists exactly once and every workspace access is an LDS/STS with an immediate offset.
+// Structure: the iterate lives in the warp's slice of shared memory at compile-time offsets (Lay<N, NOBS>); every
+// phase is a __noinline__ function template that loads its operands, works in registers and stores back, so each
+// heavy code sequence exists exactly once and every workspace access is an LDS/STS with an immediate offset.  A block
+// holds Lay::WPB warps (8 at N = 15, n_obs = 3) that start every IPM iteration together (align_warps) so that they
+// share instruction-cache lines.  One launch is one whole closed-loop step when asked (nmpc_solve_and_step: the shift
+// runs in ph_output) and also prepares the next call on the handle (queue / counters, longest-first fetch order).
 #pragma once
 #include "nmpc_device.cuh"
 #include "nmpc_riccati.cuh"
