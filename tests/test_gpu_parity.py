@@ -405,6 +405,29 @@ def test_pipelined_closed_loop_is_the_same_loop(pkg):
     assert torch.equal(so["return_status"], sm["return_status"]) and torch.equal(so["iter_count"], sm["iter_count"])
 
 
+def test_handle_reuse_across_batch_sizes(pkg):
+    """One handle, calls of changing batch size (the launch of call n prepares the queue, counters and fetch order of
+    call n+1): every call returns what a fresh solver returns for the same inputs."""
+    sc = pkg.SCENARIOS["nmpc_tt"]
+    dev = "cuda:0"
+    lbx, ubx, lbg, ubg = sc.bounds()
+    T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    p, _ = pkg.random_instances(sc, 1300, seed=5)
+    x0 = np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (1300, sc.N))
+    bt = (T(lbx), T(ubx), T(lbg), T(ubg))
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=64)
+    for B in (64, 1300, 1300, 200, 1300, 1, 200, 200):
+        got = s(x0=T(x0[:B]), p=T(p[:B]), lbx=bt[0], ubx=bt[1], lbg=bt[2], ubg=bt[3], want_g=False, want_lam=False)
+        gst = {k: v.clone() for k, v in s.stats().items()}
+        f = pkg.nlpsol("fresh", "ipm", sc, max_batch=B)
+        ref = f(x0=T(x0[:B]), p=T(p[:B]), lbx=bt[0], ubx=bt[1], lbg=bt[2], ubg=bt[3], want_g=False, want_lam=False)
+        rst = f.stats()
+        assert torch.equal(got["x"], ref["x"]) and torch.equal(got["f"], ref["f"]), B
+        assert torch.equal(gst["return_status"], rst["return_status"]) and torch.equal(gst["iter_count"], rst["iter_count"]), B
+        wc = s.work_counters(); wf = f.work_counters()
+        assert wc["factorizations"] == wf["factorizations"] and wc["ls_trials"] == wf["ls_trials"], B
+
+
 def test_async_host_entry_point(pkg):
     """nmpc_solve_host_async + nmpc_synchronize (solver(..., blocking=False); solver.wait()) returns what the blocking
     host call returns; two handles driven this way can be in flight together."""
