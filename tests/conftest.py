@@ -22,4 +22,6 @@ def oracle_mod():
 @pytest.fixture(scope="session")
 def pkg():
     import b200nmpc
+    if not b200nmpc._ffi.LIB_PATH.exists():      # a tree that was never built: compile (nvcc cross-compiles without a GPU)
+        b200nmpc._ffi.build()
     return b200nmpc
