@@ -23,12 +23,18 @@ from .scenarios import NP, Scenario
 
 class ClosedLoop:
     def __init__(self, solver: Solver, scenario: Scenario, p0, target_vw=None, device: Optional[str] = None,
-                 phase=None, predict_target: bool = False):
+                 phase=None, predict_target: bool = False, obstacles=None, obstacle_vel=None):
         """p0 [B,11] initial [state; target]; target_vw [B,2] constant per-instance target (v, omega) or None to
         follow scenario.schedule(mpc_iter + phase[b]).  predict_target: hand the solver the target's own Euler
         prediction over the horizon (same model as the target step of shift_timestep, NMPC_TT.py:24-27) instead of
-        the frozen target the reference uses."""
+        the frozen target the reference uses.  obstacles [B, n_obs, 3] = (cx, cy, r_uav + r_obs) per instance and
+        obstacle_vel [B, n_obs, 2]: obstacle fields as data, moved by T * velocity after every step (the moving
+        obstacles of MATLAB/Dynamic Obstacles/Dynamic Obstacle avoidance.m:128-133, whose positions are parameters)."""
         self.predict_target = predict_target
+        dev0 = device or f"cuda:{solver.device}"
+        t64 = lambda a: None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float64) if not torch.is_tensor(a) else a,
+                                                               dtype=torch.float64, device=dev0).contiguous().clone()
+        self.obstacles, self.obstacle_vel = t64(obstacles), t64(obstacle_vel)
         self.solver, self.sc = solver, scenario
         dev = device or f"cuda:{solver.device}"
         self.p = torch.as_tensor(np.asarray(p0, dtype=np.float64), device=dev).reshape(-1, NP).contiguous().clone()
@@ -59,6 +65,10 @@ class ClosedLoop:
             vw = np.array([self.sc.schedule(self.mpc_iter + int(ph)) for ph in self.phase], dtype=np.float64)
             self.vw.copy_(torch.from_numpy(vw))
 
+    def _move_obstacles(self):
+        if self.obstacles is not None and self.obstacle_vel is not None:
+            self.obstacles[:, :, :2] += self.sc.T * self.obstacle_vel
+
     def target_prediction(self):
         """[B, N, 2]: x_t, y_t of stages 0..N-1 under theta_{k+1} = theta_k + T w, (x, y)_{k+1} = (x, y)_k + T v (cos, sin)(theta_k)."""
         N, T = self.sc.N, self.sc.T
@@ -85,16 +95,18 @@ class ClosedLoop:
         self._schedule_vw()
         if not (want_g or want_lam):
             sol = self.solver.solve_and_step(self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg, self.vw, self.fov,
-                                             self.err_sum, want_x=want_x,
+                                             self.err_sum, obstacles=self.obstacles, want_x=want_x,
                                              target_traj=self.target_prediction() if self.predict_target else None)
+            self._move_obstacles()
             self.mpc_iter += 1
             self.last = sol
             return sol
-        sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg,
+        sol = self.solver(x0=self.u_warm, p=self.p, lbx=self.lbx, ubx=self.ubx, lbg=self.lbg, ubg=self.ubg, obstacles=self.obstacles,
                           want_g=want_g, want_lam=want_lam,
                           target_traj=self.target_prediction() if self.predict_target else None)
         # shift + error[i] = || FOVcentre_{i+1} - target_i ||   (NMPC_TT.py:435), one kernel
         self.solver.step(sol["x"], self.p, self.u_warm, self.vw, self.fov, self.err_sum)
+        self._move_obstacles()
         self.mpc_iter += 1
         self.last = sol
         return sol

@@ -199,6 +199,40 @@ def test_predicted_target_trajectory(pkg, oracle_mod):
     assert errs[1] <= 1.05 * errs[0], errs
 
 
+def test_moving_obstacles_closed_loop(pkg):
+    """Obstacle fields as data that move between steps (MATLAB/Dynamic Obstacles/Dynamic Obstacle avoidance.m:128-133):
+    a slowly moving disc is placed so that it overlaps the path the unobstructed loop flies; the loop keeps its distance."""
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    sc = pkg.SCENARIOS["t_trajectory"]
+    B, K, K0 = 6, 90, 45
+    p0 = np.tile(np.array(list(sc.x_init) + list(sc.target_init)), (B, 1))
+    p0[:, 1] += np.linspace(-6, 6, B); p0[:, 9] = p0[:, 1]                      # parallel lanes
+    vw = np.tile(np.array([12.0, 0.0]), (B, 1))                                   # target straight along +x
+    v_obs = np.array([-2.0, 0.0])
+
+    def fly(obs, vel):
+        s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+        cl = ClosedLoop(s, sc, p0, target_vw=vw, obstacles=obs, obstacle_vel=vel)
+        path, conv = [], 0
+        for k in range(K):
+            cl.step(); conv += int(s.stats()["success"].sum())
+            path.append(cl.p[:, :2].cpu().numpy().copy())
+        return np.array(path), conv, cl
+
+    free, _, _ = fly(None, None)                                                  # [K, B, 2]
+    # disc of radius 35 whose centre passes 27 m beside the free path at step K0 (the track cuts 8 m into it)
+    c_at = lambda k: free[K0] + np.array([0.0, 27.0]) + v_obs * sc.T * (k - K0)
+    obs = np.tile(sc.obstacle_table(), (B, 1, 1)); obs[:, 0, :2] = c_at(-1); obs[:, 0, 2] = 35.0
+    vel = np.zeros((B, sc.n_obs, 2)); vel[:, 0, :] = v_obs
+    path, conv, cl = fly(obs, vel)
+    assert torch.allclose(cl.obstacles[:, 0, :2], torch.as_tensor(c_at(K - 1), device=cl.obstacles.device), atol=1e-9)
+    assert conv >= 0.6 * K * B, conv
+    d_with = np.array([np.linalg.norm(path[k] - c_at(k), axis=1) for k in range(K)]).min(axis=0)
+    d_free = np.array([np.linalg.norm(free[k] - c_at(k), axis=1) for k in range(K)]).min(axis=0)
+    assert (d_free < 30.0).all(), d_free                          # it was in the way ...
+    assert (d_with >= 35.0 - 1e-2).all(), d_with                  # ... and is avoided (r_uav + r_obs = 35)
+
+
 def test_function_level(pkg, oracle_mod):
     """nmpc_eval (f, g, grad f, J^T lam, Hess_L v) vs the oracle's dense derivatives."""
     for name in ("nmpc_tt", "race_track_2"):
