@@ -130,7 +130,8 @@ class PipelinedClosedLoop:
     solves/s at 4096 instances per GPU)."""
 
     def __init__(self, make_solver: Callable[[int], Solver], scenario: Scenario, p0, target_vw=None,
-                 pipelines: Optional[int] = None, device: Optional[str] = None, phase=None, predict_target: bool = False):
+                 pipelines: Optional[int] = None, device: Optional[str] = None, phase=None, predict_target: bool = False,
+                 obstacles=None, obstacle_vel=None):
         """make_solver(n) -> Solver for a sub-batch of n instances (give it `fill=2`: a sub-batch then leaves SMs to
         the others).  pipelines: number of sub-batches; None = about 32768 / B, at most 8 (measured best: 8 at
         B = 4096, 2 at B = 16384 on a B200)."""
@@ -147,8 +148,10 @@ class PipelinedClosedLoop:
             dev = device or f"cuda:{sol.device}"
             st = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(st):
+                sub = lambda a: None if a is None else (a[torch.as_tensor(idx, device=a.device)] if torch.is_tensor(a) else np.asarray(a)[idx])
                 lp = ClosedLoop(sol, scenario, p0[idx], None if target_vw is None else np.asarray(target_vw)[idx], device=dev,
-                                phase=None if phase is None else np.asarray(phase)[idx], predict_target=predict_target)
+                                phase=None if phase is None else np.asarray(phase)[idx], predict_target=predict_target,
+                                obstacles=sub(obstacles), obstacle_vel=sub(obstacle_vel))
             self.loops.append(lp); self.streams.append(st)
         self.synchronize()
 
