@@ -19,7 +19,24 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import b200nmpc                      # noqa: E402
-from oracle import nlp_ref           # noqa: E402   (only the restated shift_timestep / fov_centre helpers of :13-30, :399-402)
+
+
+def shift_timestep(T, x0, u, xs, con_t):
+    """NMPC_TT.py:13-30 with numpy: plant Euler step with the first input, warm start shifted by one stage (last
+    repeated), target Euler step with (v, omega) = con_t."""
+    v, th, ps = u[0, 0], x0[3], x0[4]
+    f = np.array([v * np.cos(ps) * np.cos(th), v * np.sin(ps) * np.cos(th), v * np.sin(th), *u[1:, 0]])
+    x0 = x0 + T * f
+    u0 = np.concatenate([u[:, 1:], u[:, -1:]], axis=1)
+    xs = xs + T * np.array([con_t[0] * np.cos(xs[2]), con_t[0] * np.sin(xs[2]), con_t[1]])
+    return x0, u0, xs
+
+
+def fov_centre(x0, vfov, hfov):
+    """NMPC_TT.py:399-402."""
+    a_p = (x0[2] * np.tan(x0[6] + vfov / 2) - x0[2] * np.tan(x0[6] - vfov / 2)) / 2
+    b_p = (x0[2] * np.tan(x0[5] + hfov / 2) - x0[2] * np.tan(x0[5] - hfov / 2)) / 2
+    return x0[0] + a_p + x0[2] * np.tan(x0[6] - vfov / 2), x0[1] + b_p + x0[2] * np.tan(x0[5] - hfov / 2)
 
 
 def main():
@@ -41,8 +58,8 @@ def main():
         sol = solver(x0=w0, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, p=p)                 # :358-365
         u = sol["x"].reshape(sc.N, 6).T                                              # ca.reshape(sol['x'], 6, N) (:367)
         st = solver.stats(); conv += int(st["success"][0]); iters += int(st["iter_count"][0])
-        x0, u0, xs = nlp_ref.shift_timestep(sc.T, x0, u, xs, sc.schedule(mpc_iter))  # :382
-        x_e[mpc_iter + 1], y_e[mpc_iter + 1] = nlp_ref.fov_centre(x0, sc.vfov, sc.hfov)   # :399-402
+        x0, u0, xs = shift_timestep(sc.T, x0, u, xs, sc.schedule(mpc_iter))  # :382
+        x_e[mpc_iter + 1], y_e[mpc_iter + 1] = fov_centre(x0, sc.vfov, sc.hfov)   # :399-402
         ss[:, mpc_iter + 1] = xs
     total = time.perf_counter() - t_start
     error = np.hypot(x_e[1:loop_run + 1] - ss[0, :loop_run], y_e[1:loop_run + 1] - ss[1, :loop_run])   # :433-436

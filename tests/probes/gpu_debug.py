@@ -1,7 +1,7 @@
 """GPU-side debugging aid (not a test): function-level and solve-level comparison with the CPU oracle."""
 import sys, time
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import numpy as np, torch
 import b200nmpc, oracle
 np.set_printoptions(linewidth=220, precision=5)

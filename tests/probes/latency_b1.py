@@ -1,7 +1,7 @@
 """single-instance latency (BASELINE config 1: batch 1) through the host-buffer call and on the device"""
 import sys, time
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import numpy as np, torch
 import b200nmpc, oracle
 for name in ("t_trajectory", "nmpc_tt"):

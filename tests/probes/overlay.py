@@ -4,7 +4,7 @@ target schedules.  Writes profiles/overlay_<script>.csv (step, UAV x y z, FOV ce
 the largest deviation -- the "closed-loop trajectories overlaid" of the north star, as numbers (no matplotlib here)."""
 import sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np, torch
 import b200nmpc, oracle
