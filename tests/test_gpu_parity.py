@@ -233,6 +233,24 @@ def test_moving_obstacles_closed_loop(pkg):
     assert (d_with >= 35.0 - 1e-2).all(), d_with                  # ... and is avoided (r_uav + r_obs = 35)
 
 
+def test_schedule_phases(pkg):
+    """BASELINE config 3: instances of one batch start at different phases of the script's target schedule
+    (T_Trajectory.py's con_t keyed on mpc_iter); phase 0 is the script's own loop."""
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    sc = pkg.SCENARIOS["t_trajectory"]
+    p0 = np.array(list(sc.x_init) + list(sc.target_init))
+    one = ClosedLoop(pkg.nlpsol("a", "ipm", sc), sc, p0)
+    many = ClosedLoop(pkg.nlpsol("b", "ipm", sc, max_batch=3), sc, np.tile(p0, (3, 1)), phase=[0, 40, 400])
+    for _ in range(30):
+        one.step(); many.step()
+    torch.cuda.synchronize()
+    assert torch.equal(one.p[0], many.p[0]) and torch.equal(one.err_sum[0], many.err_sum[0])
+    v0, w0 = sc.schedule(29); v2, w2 = sc.schedule(429)
+    assert float(many.vw[0, 0]) == v0 and float(many.vw[0, 1]) == w0 and float(many.vw[2, 0]) == v2 and float(many.vw[2, 1]) == w2
+    if (v0, w0) != (v2, w2):
+        assert not torch.equal(many.p[0, 8:], many.p[2, 8:])
+
+
 def test_function_level(pkg, oracle_mod):
     """nmpc_eval (f, g, grad f, J^T lam, Hess_L v) vs the oracle's dense derivatives."""
     for name in ("nmpc_tt", "race_track_2"):
