@@ -65,7 +65,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """Wall-clock marker: call at the start and at the end of the timed region."""
+        self.marks = getattr(self, "marks", []) + [time.time()]
 
     def stop(self):
         if self.proc is None:
@@ -75,8 +79,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        marks = getattr(self, "marks", [])
+        rows, window = [r for _, r in self.rows], "whole run (the device is busy from the first warm-up step on)"
+        if len(marks) >= 2:     # samples taken during the timed region; nvidia-smi's period is 100 ms, so keep a margin
+            inside = [r for t, r in self.rows if marks[0] - 0.05 <= t <= marks[-1] + 0.05]
+            if inside:
+                rows, window = inside, "timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -86,7 +96,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def algorithmic_flops(N, n_obs, iters, n_fact, n_ls):
@@ -172,6 +183,7 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank); sampler.start()     # started early: nvidia-smi needs ~0.3 s to deliver its first line
     cold = None
     for k in range(args.warmup):
         cl.step()
@@ -183,8 +195,8 @@ def run_b200(args, rank, world, local_rank):
     ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(S)] for _ in range(K)]
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     keep = []
-    sampler = ClockSampler(local_rank); sampler.start()
     barrier()
+    sampler.mark()
     wall0 = time.perf_counter()
     cur = torch.cuda.current_stream(dev)
     e_start.record(cur)
@@ -212,6 +224,7 @@ def run_b200(args, rank, world, local_rank):
     e_end.record(cur)
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark()
     clocks = sampler.stop()
     step_ms = [ev[k][i][0].elapsed_time(ev[k][i][2]) for k in range(K) for i in range(S)]     # per sub-batch step
     solve_ms = [ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(K) for i in range(S)]
