@@ -338,16 +338,20 @@ def run_b200(args, rank, world, local_rank):
         import oracle
         oracle.build()
         cores = os.cpu_count() or 1
-        ns = min(B, args.cpu_sample or max(256, 64 * cores))
-        pc = cl.p.cpu().numpy()[:ns].copy(); uc = cl.u_warm.cpu().numpy()[:ns].copy()
+        ns = min(B, args.cpu_sample or 4096)
+        pc = cl.p.cpu().numpy()[:ns].copy(); uc = cl.u_warm.cpu().numpy()[:ns].copy(); vc = vw[:ns].copy()
         sp = oracle.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+        nsteps, conv_c, it_c = 4, 0, 0
         t0 = time.perf_counter()
-        r = oracle.solve(sp, sc.obstacle_table(), pc, uc, lbx, ubx, lbg, ubg, nthreads=cores, want_g=False, want_lam=False)
+        for _ in range(nsteps):       # a few consecutive closed-loop steps of the same instances, ~10 s of CPU work
+            r = oracle.solve(sp, sc.obstacle_table(), pc, uc, lbx, ubx, lbg, ubg, nthreads=cores, want_g=False, want_lam=False)
+            conv_c += int((r["status"] == 0).sum()); it_c += int(r["iters"].sum())
+            uc = host_shift(sc.T, pc, r["x"], vc)
         dt = time.perf_counter() - t0
-        cpu = {"value": float((r["status"] == 0).sum() / dt), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {ns} instances of the GPU batch at the state after the timed steps (warm starts), one solve each, "
-                         f"oracle/nmpc_oracle.cpp on {cores} threads; CasADi/IPOPT itself cannot run in this image",
-               "seconds": dt, "converged_fraction": float((r["status"] == 0).mean()), "mean_iters": float(r["iters"].mean())}
+        cpu = {"value": float(conv_c / dt), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{ns} instances of the GPU batch, {nsteps} consecutive closed-loop steps from the state after the timed steps "
+                         f"(warm starts), oracle/nmpc_oracle.cpp on {cores} threads; CasADi/IPOPT itself cannot run in this image",
+               "seconds": dt, "converged_fraction": conv_c / (ns * nsteps), "mean_iters": it_c / (ns * nsteps)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
