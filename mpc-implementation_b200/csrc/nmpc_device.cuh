@@ -147,9 +147,15 @@ struct Lay {
   static constexpr int LV0 = 0;
   static constexpr int RW0 = even_up(LV0 + LV_N * S);
   static constexpr int LQ0 = even_up(RW0 + A_NROW * R * S);
-  static constexpr bool SOC_ALIAS = (3 * R + 14 <= LQ_DEAD);      // SOC scratch fits in the LQ entries that are dead after the factorisation
-  static constexpr int SOC0 = SOC_ALIAS ? LQ0 : even_up(LQ0 + LQ_N * S);
-  static constexpr int STG0 = SOC_ALIAS ? even_up(LQ0 + LQ_N * S) : even_up(SOC0 + (3 * R + 14) * S);
+  // Second-order-correction scratch, 3R + 14 entries: as many as fit live in the LQ entries that are dead after the
+  // factorisation ([0, LQ_DEAD)), the rest in an extra region.  The last 14 entries (du_soc, q') are addressed as
+  // blocks by the Riccati sweeps, so they are never split: SOC_LO <= 3R unless everything fits.
+  static constexpr int SOC_N = 3 * R + 14;
+  static constexpr bool SOC_ALIAS = SOC_N <= LQ_DEAD;
+  static constexpr int SOC_LO = SOC_ALIAS ? SOC_N : (3 * R < LQ_DEAD ? 3 * R : LQ_DEAD);
+  static constexpr int SOCX0 = even_up(LQ0 + LQ_N * S);
+  static constexpr int STG0 = even_up(SOCX0 + (SOC_N - SOC_LO) * S);
+  __host__ __device__ static constexpr int soc(int e) { return e < SOC_LO ? LQ0 + e * S : SOCX0 + (e - SOC_LO) * S; }
   static constexpr int OBS0 = STG0 + STG_N;
   static constexpr int FILT0 = even_up(OBS0 + 3 * NOBS_ + 1);
   static constexpr int RES0 = FILT0 + 2 * FILT_CAP;

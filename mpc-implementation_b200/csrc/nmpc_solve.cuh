@@ -113,7 +113,7 @@ __device__ __forceinline__ int align_warps(int g, int working) {
 #define LV(e) smem[L::LV0 + (e) * L::S + lane]
 #define RW(arr, r) smem[L::RW0 + ((arr) * L::R + (r)) * L::S + lane]
 #define LQ(e) smem[L::LQ0 + (e) * L::S + lane]
-#define SOC(e) smem[L::SOC0 + (e) * L::S + lane]
+#define SOC(e) smem[L::soc(e) + lane]
 #define RES(i) smem[L::RES0 + (i)]
 #define PAR(i) smem[L::PAR0 + (i)]
 #define SOC_DS2 0
@@ -709,7 +709,7 @@ template <class L>
 __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int b, int lane) {
   const Prob& pr = A.pr; const Opt& o = A.o;
   constexpr int S = L::S, R = L::R;
-  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::SOC0 + (3 * R) * S, Q20 = L::SOC0 + (3 * R + 6) * S;
+  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(3 * R), Q20 = L::soc(3 * R + 6);
   const double T = pr.T;
   unsigned long long n_fact = 0, n_ls = 0, n_soc = 0;
 
