@@ -20,8 +20,11 @@ _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_build" / "libnmpc_oracle.so"
 _lib = None
 
-STATUS_NAMES = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "Restoration_Needed",
-                3: "Search_Direction_Becomes_Too_Small", 4: "Invalid_Number_Detected", 5: "Perturbation_Failed"}
+STATUS_NAMES = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "Restoration_Failed",
+                3: "Search_Direction_Becomes_Too_Small", 4: "Invalid_Number_Detected", 5: "Error_In_Step_Computation",
+                6: "Infeasible_Problem_Detected"}
+STAT_COLUMNS = ("factorizations", "soc_accepted", "resto_calls", "resto_iters", "watchdog_starts", "soft_resto_steps",
+                "filter_resets", "slack_safeguards")
 
 
 class OracleSpec(C.Structure):
@@ -47,7 +50,18 @@ def lib():
         _lib.oracle_solve_log.restype = C.c_int
         _lib.oracle_eval_traj.restype = C.c_int
         _lib.oracle_solve_traj.restype = C.c_int
+        _lib.oracle_set_option.restype = C.c_int
+        _lib.oracle_set_option.argtypes = [C.c_char_p, C.c_double]
     return _lib
+
+
+def set_option(name: str, value: float):
+    """Override one algorithmic option of the oracle (Options in nmpc_oracle.cpp), e.g. set_option("resto", 0)."""
+    lib().oracle_set_option(name.encode(), float(value))
+
+
+def clear_options():
+    lib().oracle_clear_options()
 
 
 def _dp(a):
@@ -101,7 +115,7 @@ def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=
     g = np.zeros((B, ng)) if want_g else None
     lam_x = np.zeros((B, nw)) if want_lam else None
     lam_g = np.zeros((B, ng)) if want_lam else None
-    status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32); stats = np.zeros((B, 4), dtype=np.int32)
+    status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32); stats = np.zeros((B, 8), dtype=np.int32)
     if nthreads is None:
         nthreads = min(B, os.cpu_count() or 1)
     tg = None if target_traj is None else _c(target_traj).reshape(B, N, 2)
@@ -116,7 +130,7 @@ def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=
 def solve_log(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, scaling=True, max_log=128):
     N = spec.N; nw = 6 * N
     x = np.zeros(nw); f = C.c_double(); st = C.c_int32(); it = C.c_int32()
-    log = np.zeros((max_log, 8))
+    log = np.zeros((max_log, 9))
     n = lib().oracle_solve_log(C.byref(spec), _dp(_c(p)), _dp(_c(x0)), _dp(_c(lbx)), _dp(_c(ubx)), _dp(_c(lbg)),
                                _dp(_c(ubg)), _dp(_c(obs)), C.c_int(int(scaling)), _dp(x), C.byref(f), C.byref(st),
                                C.byref(it), _dp(log), C.c_int(max_log))

@@ -35,7 +35,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -348,12 +351,29 @@ void chol_solve(const double* L, int n, double* b) {
   for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < n; ++k) s -= L[(size_t)k * n + i] * b[k]; b[i] = s / L[(size_t)i * n + i]; }
 }
 
+
 // ------------------------------------------------------------------------------------------
 // IPOPT-algorithm interior point method
+//
+// [3P] Everything below restates IPOPT (3.12 line; the version CasADi 3.5.5 bundles) from its paper and
+// documented defaults -- the class names in the comments say which IPOPT component a block stands for:
+//   Algo::optimize ................. IpoptAlgorithm::Optimize
+//   Algo::check_convergence ........ OptimalityErrorConvergenceCheck / RestoFilterConvergenceCheck
+//   Algo::update_mu ................ MonotoneMuUpdate
+//   Algo::compute_direction ........ PDSearchDirCalculator + PDFullSpaceSolver + PDPerturbationHandler
+//                                    (+ AugRestoSystemSolver: elimination of the n/p variables)
+//   Algo::line_search .............. BacktrackingLineSearch::FindAcceptableTrialPoint (watchdog, soft
+//                                    restoration phase, tiny steps) + FilterLSAcceptor (filter, switching /
+//                                    Armijo conditions, second-order correction, filter resets, obj_max_inc)
+//   Algo::perform_restoration ...... MinC_1NrmRestorationPhase (outer) / RestoRestorationPhase (inner)
+//   RestoNlp ....................... RestoIpoptNLP,  Algo::init_resto = RestoIterateInitializer
+// The restoration problem is handed to the SAME algorithm object type, as IPOPT does.
 // ------------------------------------------------------------------------------------------
 enum Status : int32_t {
-  SOLVE_SUCCEEDED = 0, MAXITER_EXCEEDED = 1, RESTORATION_NEEDED = 2, STEP_TOO_SMALL = 3, INVALID_NUMBER = 4,
-  PERTURBATION_FAILED = 5
+  SOLVE_SUCCEEDED = 0, MAXITER_EXCEEDED = 1, RESTORATION_FAILED = 2, STEP_TOO_SMALL = 3, INVALID_NUMBER = 4,
+  ERROR_IN_STEP_COMPUTATION = 5, INFEASIBLE_PROBLEM_DETECTED = 6,
+  // results of the restoration sub-algorithm (never returned to the caller)
+  RESTO_SUCCESS = 100, RESTO_CONVERGED_TO_FEASIBLE = 101, CONTINUE = 200
 };
 
 struct Options {
@@ -368,399 +388,935 @@ struct Options {
   double gamma_theta = 1e-5, gamma_phi = 1e-8, eta_phi = 1e-8, s_theta = 1.1, s_phi = 2.3, delta = 1.0;
   double alpha_min_frac = 0.05, alpha_red = 0.5; int max_soc = 4; double kappa_soc = 0.99;
   double theta_max_fact = 1e4, theta_min_fact = 1e-4;
-  double tiny_step_tol = 10 * EPS;
+  double tiny_step_tol = 10 * EPS, tiny_step_y_tol = 1e-2;
+  double obj_max_inc = 5.0; int max_filter_resets = 5, filter_reset_trigger = 5;
+  int filter_cap = 24;      // IPOPT's filter is unbounded; entries dominated by a new one are removed, so it stays short
+  int watchdog_trigger = 10, watchdog_trial_max = 3;                 // watchdog_shortened_iter_trigger, watchdog_trial_iter_max
+  int max_soft_resto = 10; double soft_resto_red = 1.0 - 1e-4;      // max_soft_resto_iters, soft_resto_pderror_reduction_factor
+  double slack_move = 1.8189894035458565e-12;                        // eps^(3/4)
+  // restoration phase
+  int resto = 1;                                                     // 0: report RESTORATION_FAILED instead of entering it (round-1 behaviour)
+  double resto_rho = 1000.0, resto_eta_factor = 1.0, kappa_resto = 0.9;   // resto_penalty_parameter, resto_proximity_weight, required_infeasibility_reduction
+  double bound_mult_reset_threshold = 1e3, constr_mult_reset_threshold = 0.0;
+  double resto_theta_max_fact = 1e8;
+  int resto_explicit = 0;      // 1: factor the restoration KKT system with the n/p variables explicit (validation of the elimination)
 };
 
-struct IterLog { double mu, f, inf_pr, inf_du, dw, alpha_pr, alpha_du; int ls; };
+struct Counters {
+  int n_fact = 0, n_soc_acc = 0, n_resto = 0, n_resto_iter = 0, n_watchdog = 0, n_soft = 0, n_filter_reset = 0, n_slack_adj = 0;
+};
 
-struct Result { int32_t status; int32_t iters; double f; int n_fact; int n_soc_acc; };
+struct IterLog { double mu, f, inf_pr, inf_du, dw, alpha_pr, alpha_du; int ls; int tag; };
 
 inline bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * EPS * std::fabs(bas); }
 
-struct Ipm {
-  Instance& P; Options o; int n, m;
-  std::vector<double> xL, xU, dL, dU;            // relaxed (scaled for d) bounds; +-INF when absent
-  std::vector<double> dc; double df = 1.0;       // scaling
-  std::vector<double> x, s, y, zL, zU, vL, vU;
-  std::vector<double> g, grad, J, W, M, rhs, c;
-  std::vector<double> dx, ds, dy, dzL, dzU, dvL, dvU;
-  std::vector<std::pair<double, double>> filter;   // (theta, phi) margins
-  double mu, tau, dw_last = 0.0, theta_max = 0, theta_min = 0;
-  std::vector<IterLog>* log = nullptr;
-  int n_fact = 0, n_soc_acc = 0;
+// The problem as the algorithm sees it (IpoptNLP): scaled functions, relaxed bounds.  Variables are the n0
+// "structural" ones followed by `ne` pairs (n_r, p_r) of elastic variables that enter row r as + n_r - p_r and
+// nowhere else (ne = 0 for the original problem, ne = m for the restoration problem).
+struct Nlp {
+  int n0 = 0, ne = 0, m = 0;
+  int n() const { return n0 + 2 * ne; }
+  std::vector<double> xL, xU, dL, dU;
+  double df = 1.0;                      // objective scaling of the original problem (unscaled tolerances)
+  std::vector<double> dc;               // row scaling
+  virtual double eval_fg(const double* x, double mu, double* g0) = 0;
+  virtual void eval_derivs(const double* x, double mu, double* grad, double* J0) = 0;     // grad [n], J0 [m][n0]
+  virtual void eval_hess(double sigma, const double* y, double mu, double* W0) = 0;        // [n0][n0], at the point of eval_derivs
+  virtual ~Nlp() {}
+};
 
-  Ipm(Instance& P_, const Options& o_) : P(P_), o(o_), n(P_.nw), m(P_.ng) {}
-
-  double feval(const double* xx, double* gg) {   // scaled f, g
-    double f = P.eval_fg(xx, gg);
-    for (int i = 0; i < m; ++i) gg[i] *= dc[i];
+struct OrigNlp : Nlp {
+  Instance& I; std::vector<double> ytmp;
+  explicit OrigNlp(Instance& I_) : I(I_) { n0 = I.nw; ne = 0; m = I.ng; dc.assign(m, 1.0); ytmp.resize(m); }
+  double eval_fg(const double* x, double, double* g0) override {
+    double f = I.eval_fg(x, g0);
+    for (int r = 0; r < m; ++r) g0[r] *= dc[r];
     return df * f;
   }
-  void deriv(const double* xx) {   // scaled grad, J at xx
-    P.eval_derivs(xx); P.grad_f(grad.data()); P.jac_g(J.data());
-    for (int i = 0; i < n; ++i) grad[i] *= df;
-    for (int r = 0; r < m; ++r) if (dc[r] != 1.0) for (int cidx = 0; cidx < n; ++cidx) J[(size_t)r * n + cidx] *= dc[r];
+  void jac(double* J0) {
+    I.jac_g(J0);
+    for (int r = 0; r < m; ++r) if (dc[r] != 1.0) for (int c = 0; c < n0; ++c) J0[(size_t)r * n0 + c] *= dc[r];
   }
-  static void push(double& v, double lo, double hi, double k1, double k2) {
-    bool hl = lo > -INF, hu = hi < INF;
-    if (hl && hu) {
-      double pl = std::min(k1 * std::max(1.0, std::fabs(lo)), k2 * (hi - lo));
-      double pu = std::min(k1 * std::max(1.0, std::fabs(hi)), k2 * (hi - lo));
-      v = std::max(v, lo + pl); v = std::min(v, hi - pu);
-    } else if (hl) v = std::max(v, lo + k1 * std::max(1.0, std::fabs(lo)));
-    else if (hu) v = std::min(v, hi - k1 * std::max(1.0, std::fabs(hi)));
+  void eval_derivs(const double* x, double, double* grad, double* J0) override {
+    I.eval_derivs(x); I.grad_f(grad); jac(J0);
+    for (int i = 0; i < n0; ++i) grad[i] *= df;
   }
-  // error measure E_mu (scaled)
-  double error(double mu_, double* o_du = nullptr, double* o_pr = nullptr, double* o_co = nullptr) {
-    double du = 0, pr = 0, co = 0, sumy = 0, sumz = 0; int nz = 0;
-    for (int i = 0; i < n; ++i) {
-      double gl = grad[i];
-      for (int r = 0; r < m; ++r) gl += J[(size_t)r * n + i] * y[r];
-      gl += -zL[i] + zU[i];
-      du = std::max(du, std::fabs(gl));
-      if (xL[i] > -INF) { co = std::max(co, std::fabs((x[i] - xL[i]) * zL[i] - mu_)); sumz += std::fabs(zL[i]); ++nz; }
-      if (xU[i] < INF) { co = std::max(co, std::fabs((xU[i] - x[i]) * zU[i] - mu_)); sumz += std::fabs(zU[i]); ++nz; }
-    }
-    for (int r = 0; r < m; ++r) {
-      du = std::max(du, std::fabs(-y[r] - vL[r] + vU[r]));
-      pr = std::max(pr, std::fabs(g[r] - s[r]));
-      sumy += std::fabs(y[r]);
-      if (dL[r] > -INF) { co = std::max(co, std::fabs((s[r] - dL[r]) * vL[r] - mu_)); sumz += std::fabs(vL[r]); ++nz; }
-      if (dU[r] < INF) { co = std::max(co, std::fabs((dU[r] - s[r]) * vU[r] - mu_)); sumz += std::fabs(vU[r]); ++nz; }
-    }
-    double sd = std::max(o.s_max, (sumy + sumz) / std::max(1, m + nz)) / o.s_max;
-    double sc = std::max(o.s_max, sumz / std::max(1, nz)) / o.s_max;
-    if (o_du) *o_du = du; if (o_pr) *o_pr = pr; if (o_co) *o_co = co;
-    return std::max(du / sd, std::max(pr, co / sc));
-  }
-  double barrier(const double* xx, const double* ss, double f) const {
-    double phi = f;
-    for (int i = 0; i < n; ++i) {
-      bool hl = xL[i] > -INF, hu = xU[i] < INF;
-      if (hl) phi -= mu * std::log(xx[i] - xL[i]);
-      if (hu) phi -= mu * std::log(xU[i] - xx[i]);
-      if (hl && !hu) phi += o.kappa_d * mu * (xx[i] - xL[i]);
-      if (hu && !hl) phi += o.kappa_d * mu * (xU[i] - xx[i]);
-    }
-    for (int r = 0; r < m; ++r) {
-      bool hl = dL[r] > -INF, hu = dU[r] < INF;
-      if (hl) phi -= mu * std::log(ss[r] - dL[r]);
-      if (hu) phi -= mu * std::log(dU[r] - ss[r]);
-      if (hl && !hu) phi += o.kappa_d * mu * (ss[r] - dL[r]);
-      if (hu && !hl) phi += o.kappa_d * mu * (dU[r] - ss[r]);
-    }
-    return phi;
-  }
-  // build condensed matrix for given (use_W, Dx, Ds) into M and factor.  returns false if not PD
-  bool factor(bool use_W, const std::vector<double>& Dx, const std::vector<double>& Ds) {
-    ++n_fact;
-    if (use_W) M = W; else std::fill(M.begin(), M.end(), 0.0);
-    for (int i = 0; i < n; ++i) M[(size_t)i * n + i] += Dx[i];
-    for (int r = 0; r < m; ++r) {
-      const double* Jr = &J[(size_t)r * n]; double d = Ds[r];
-      int last = -1; for (int cidx = n - 1; cidx >= 0; --cidx) if (Jr[cidx] != 0.0) { last = cidx; break; }
-      for (int a = 0; a <= last; ++a) { double ja = d * Jr[a]; if (ja == 0.0) continue; double* Mr = &M[(size_t)a * n];
-        for (int b = 0; b <= a; ++b) Mr[b] += ja * Jr[b]; }
-    }
-    return cholesky(M.data(), n);   // only the lower triangle is referenced
-  }
-  // solve the reduced primal-dual system for constraint residual cc (c or c_soc); M must be factored with (Dx, Ds)
-  void solve_dir(const std::vector<double>& Ds, const std::vector<double>& rx, const std::vector<double>& rs,
-                 const double* cc, double* ddx, double* dds, double* ddy) {
-    std::vector<double> t(m);
-    for (int r = 0; r < m; ++r) t[r] = Ds[r] * cc[r] + rs[r];
-    for (int i = 0; i < n; ++i) { double v = rx[i]; for (int r = 0; r < m; ++r) v += J[(size_t)r * n + i] * t[r]; ddx[i] = -v; }
-    chol_solve(M.data(), n, ddx);
-    for (int r = 0; r < m; ++r) {
-      double jd = 0; for (int i = 0; i < n; ++i) jd += J[(size_t)r * n + i] * ddx[i];
-      dds[r] = jd + cc[r]; ddy[r] = Ds[r] * dds[r] + rs[r];
-    }
-  }
-  void dual_dirs(const double* ddx, const double* dds) {
-    for (int i = 0; i < n; ++i) {
-      dzL[i] = dzU[i] = 0;
-      if (xL[i] > -INF) { double sl = x[i] - xL[i]; dzL[i] = (mu - zL[i] * ddx[i]) / sl - zL[i]; }
-      if (xU[i] < INF) { double sl = xU[i] - x[i]; dzU[i] = (mu + zU[i] * ddx[i]) / sl - zU[i]; }
-    }
-    for (int r = 0; r < m; ++r) {
-      dvL[r] = dvU[r] = 0;
-      if (dL[r] > -INF) { double sl = s[r] - dL[r]; dvL[r] = (mu - vL[r] * dds[r]) / sl - vL[r]; }
-      if (dU[r] < INF) { double sl = dU[r] - s[r]; dvU[r] = (mu + vU[r] * dds[r]) / sl - vU[r]; }
-    }
-  }
-  double ftb_primal(const double* ddx, const double* dds) const {
-    double a = 1.0;
-    for (int i = 0; i < n; ++i) {
-      if (xL[i] > -INF && ddx[i] < 0) a = std::min(a, -tau * (x[i] - xL[i]) / ddx[i]);
-      if (xU[i] < INF && ddx[i] > 0) a = std::min(a, tau * (xU[i] - x[i]) / ddx[i]);
-    }
-    for (int r = 0; r < m; ++r) {
-      if (dL[r] > -INF && dds[r] < 0) a = std::min(a, -tau * (s[r] - dL[r]) / dds[r]);
-      if (dU[r] < INF && dds[r] > 0) a = std::min(a, tau * (dU[r] - s[r]) / dds[r]);
-    }
-    return a;
-  }
-  double ftb_dual() const {
-    double a = 1.0;
-    for (int i = 0; i < n; ++i) {
-      if (dzL[i] < 0 && xL[i] > -INF) a = std::min(a, -tau * zL[i] / dzL[i]);
-      if (dzU[i] < 0 && xU[i] < INF) a = std::min(a, -tau * zU[i] / dzU[i]);
-    }
-    for (int r = 0; r < m; ++r) {
-      if (dvL[r] < 0 && dL[r] > -INF) a = std::min(a, -tau * vL[r] / dvL[r]);
-      if (dvU[r] < 0 && dU[r] < INF) a = std::min(a, -tau * vU[r] / dvU[r]);
-    }
-    return a;
-  }
-  bool filter_ok(double th, double ph) const {
-    for (auto& e : filter) if (!(th < e.first || ph < e.second)) return false;
-    return true;
-  }
-
-  Result solve(const double* x0, const double* lbx, const double* ubx, const double* lbg, const double* ubg,
-               double* x_out, double* g_out, double* lamx_out, double* lamg_out) {
-    Result res{};
-    x.assign(x0, x0 + n); s.assign(m, 0); y.assign(m, 0);
-    g.resize(m); grad.resize(n); J.resize((size_t)m * n); W.resize((size_t)n * n); M.resize((size_t)n * n);
-    c.resize(m); dx.resize(n); ds.resize(m); dy.resize(m); dzL.resize(n); dzU.resize(n); dvL.resize(m); dvU.resize(m);
-    dc.assign(m, 1.0); df = 1.0;
-    // ---- gradient-based scaling at the user's starting point
-    if (o.scaling) {
-      deriv(x.data());
-      double gmax = 0; for (int i = 0; i < n; ++i) gmax = std::max(gmax, std::fabs(grad[i]));
-      double dfn = gmax > o.max_grad ? std::max(o.scal_min, o.max_grad / gmax) : 1.0;
-      for (int r = 0; r < m; ++r) {
-        double rm = 0; for (int i = 0; i < n; ++i) rm = std::max(rm, std::fabs(J[(size_t)r * n + i]));
-        dc[r] = rm > o.max_grad ? std::max(o.scal_min, o.max_grad / rm) : 1.0;
-      }
-      df = dfn;
-      if (o.scaling == 2) std::fill(dc.begin(), dc.end(), 1.0);   // debug: objective scaling only
-      if (o.scaling == 3) df = 1.0;                                // debug: constraint scaling only
-    }
-    // ---- bounds (scaled, relaxed)
-    xL.resize(n); xU.resize(n); dL.resize(m); dU.resize(m);
-    auto relax_lo = [&](double b) { return b > -1e19 ? b - o.bound_relax * std::max(1.0, std::fabs(b)) : -INF; };
-    auto relax_hi = [&](double b) { return b < 1e19 ? b + o.bound_relax * std::max(1.0, std::fabs(b)) : INF; };
-    for (int i = 0; i < n; ++i) { xL[i] = relax_lo(lbx[i]); xU[i] = relax_hi(ubx[i]); }
-    for (int r = 0; r < m; ++r) {
-      dL[r] = lbg[r] > -1e19 ? relax_lo(dc[r] * lbg[r]) : -INF;
-      dU[r] = ubg[r] < 1e19 ? relax_hi(dc[r] * ubg[r]) : INF;
-    }
-    // ---- starting point
-    for (int i = 0; i < n; ++i) push(x[i], xL[i], xU[i], o.bound_push, o.bound_frac);
-    double f = feval(x.data(), g.data());
-    for (int r = 0; r < m; ++r) { s[r] = g[r]; push(s[r], dL[r], dU[r], o.bound_push, o.bound_frac); }
-    zL.assign(n, 0); zU.assign(n, 0); vL.assign(m, 0); vU.assign(m, 0);
-    for (int i = 0; i < n; ++i) { if (xL[i] > -INF) zL[i] = 1; if (xU[i] < INF) zU[i] = 1; }
-    for (int r = 0; r < m; ++r) { if (dL[r] > -INF) vL[r] = 1; if (dU[r] < INF) vU[r] = 1; }
-    deriv(x.data());
-    {   // least-squares multipliers
-      std::vector<double> one_n(n, 1.0), one_m(m, 1.0), rx(n), rs(m), zero(m, 0.0), tx(n), ts(m);
-      for (int i = 0; i < n; ++i) rx[i] = grad[i] - zL[i] + zU[i];
-      for (int r = 0; r < m; ++r) rs[r] = -vL[r] + vU[r];
-      bool ok = factor(false, one_n, one_m);
-      if (ok) {
-        solve_dir(one_m, rx, rs, zero.data(), tx.data(), ts.data(), y.data());
-        double ym = 0; for (int r = 0; r < m; ++r) ym = std::max(ym, std::fabs(y[r]));
-        if (!(ym <= o.constr_mult_init_max)) std::fill(y.begin(), y.end(), 0.0);
-      } else std::fill(y.begin(), y.end(), 0.0);
-    }
-    mu = o.mu_init; tau = std::max(o.tau_min, 1 - mu);
-    double mu_floor = std::min(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
-    {
-      double th0 = 0; for (int r = 0; r < m; ++r) th0 += std::fabs(g[r] - s[r]);
-      theta_max = o.theta_max_fact * std::max(1.0, th0); theta_min = o.theta_min_fact * std::max(1.0, th0);
-    }
-    filter.clear();
-    std::vector<double> Dx(n), Ds(m), rx(n), rs(m), xt(n), st(m), gt(m), csoc(m), dx2(n), ds2(m), dy2(m);
-    int iter = 0; int tiny_count = 0; bool tiny_flag = false;
-    Status status = MAXITER_EXCEEDED;
-    for (;;) {
-      // -------- convergence check
-      double du, pr, co;
-      double E0 = error(0.0, &du, &pr, &co);
-      if (!std::isfinite(E0) || !std::isfinite(f)) { status = INVALID_NUMBER; break; }
-      {
-        // unscaled quantities for the absolute tolerances
-        double viol = 0;
-        for (int r = 0; r < m; ++r) {
-          double gu = g[r] / dc[r];
-          if (lbg[r] > -1e19) viol = std::max(viol, lbg[r] - gu);
-          if (ubg[r] < 1e19) viol = std::max(viol, gu - ubg[r]);
-        }
-        if (E0 <= o.tol && du / df <= o.dual_inf_tol && viol <= o.constr_viol_tol && co / df <= o.compl_inf_tol) {
-          status = SOLVE_SUCCEEDED; break;
-        }
-      }
-      if (iter >= o.max_iter) { status = MAXITER_EXCEEDED; break; }
-      // -------- barrier parameter update
-      {
-        double Emu = error(mu);
-        while ((Emu <= o.kappa_eps * mu || tiny_flag) && mu > mu_floor) {
-          double nm = std::max(mu_floor, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
-          mu = nm; tau = std::max(o.tau_min, 1 - mu); filter.clear(); tiny_flag = false;
-          Emu = error(mu);
-        }
-        if (tiny_flag && mu <= mu_floor) { status = STEP_TOO_SMALL; break; }
-      }
-      // -------- search direction
-      P.hess_l(df, [&] { for (int r = 0; r < m; ++r) c[r] = y[r] * dc[r]; return c.data(); }(), W.data());
-      for (int r = 0; r < m; ++r) c[r] = g[r] - s[r];
-      double theta = 0; for (int r = 0; r < m; ++r) theta += std::fabs(c[r]);
-      std::vector<double> Sx_(n), Ss_(m);
-      for (int i = 0; i < n; ++i) {
-        double sig = 0, r_ = grad[i];
-        for (int r = 0; r < m; ++r) r_ += J[(size_t)r * n + i] * y[r];
-        bool hl = xL[i] > -INF, hu = xU[i] < INF;
-        if (hl) { sig += zL[i] / (x[i] - xL[i]); r_ -= mu / (x[i] - xL[i]); }
-        if (hu) { sig += zU[i] / (xU[i] - x[i]); r_ += mu / (xU[i] - x[i]); }
-        if (hl && !hu) r_ += o.kappa_d * mu; if (hu && !hl) r_ -= o.kappa_d * mu;
-        Sx_[i] = sig; rx[i] = r_;
-      }
-      for (int r = 0; r < m; ++r) {
-        double sig = 0, r_ = -y[r];
-        bool hl = dL[r] > -INF, hu = dU[r] < INF;
-        if (hl) { sig += vL[r] / (s[r] - dL[r]); r_ -= mu / (s[r] - dL[r]); }
-        if (hu) { sig += vU[r] / (dU[r] - s[r]); r_ += mu / (dU[r] - s[r]); }
-        if (hl && !hu) r_ += o.kappa_d * mu; if (hu && !hl) r_ -= o.kappa_d * mu;
-        Ss_[r] = sig; rs[r] = r_;
-      }
-      double dw = 0.0; bool ok = false;
-      for (;;) {
-        for (int i = 0; i < n; ++i) Dx[i] = Sx_[i] + dw;
-        for (int r = 0; r < m; ++r) Ds[r] = Ss_[r] + dw;
-        ok = factor(true, Dx, Ds);
-        if (ok) break;
-        if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : std::max(o.dw_min, dw_last * o.dw_dec);
-        else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
-        if (dw > o.dw_max) break;
-      }
-      if (!ok) { status = PERTURBATION_FAILED; break; }
-      if (dw > 0) dw_last = dw;
-      solve_dir(Ds, rx, rs, c.data(), dx.data(), ds.data(), dy.data());
-      dual_dirs(dx.data(), ds.data());
-      double a_pr_max = ftb_primal(dx.data(), ds.data());
-      double a_du = ftb_dual();
-      // -------- line search
-      double phi = barrier(x.data(), s.data(), f);
-      double gbd = 0;   // directional derivative of the barrier function
-      for (int i = 0; i < n; ++i) {
-        double gi = grad[i]; bool hl = xL[i] > -INF, hu = xU[i] < INF;
-        if (hl) gi -= mu / (x[i] - xL[i]); if (hu) gi += mu / (xU[i] - x[i]);
-        if (hl && !hu) gi += o.kappa_d * mu; if (hu && !hl) gi -= o.kappa_d * mu;
-        gbd += gi * dx[i];
-      }
-      for (int r = 0; r < m; ++r) {
-        double gi = 0; bool hl = dL[r] > -INF, hu = dU[r] < INF;
-        if (hl) gi -= mu / (s[r] - dL[r]); if (hu) gi += mu / (dU[r] - s[r]);
-        if (hl && !hu) gi += o.kappa_d * mu; if (hu && !hl) gi -= o.kappa_d * mu;
-        gbd += gi * ds[r];
-      }
-      // tiny step?
-      bool tiny = true;
-      for (int i = 0; i < n && tiny; ++i) if (std::fabs(dx[i]) / (1 + std::fabs(x[i])) > o.tiny_step_tol) tiny = false;
-      for (int r = 0; r < m && tiny; ++r) if (std::fabs(ds[r]) / (1 + std::fabs(s[r])) > o.tiny_step_tol) tiny = false;
-      if (tiny && theta > 1e-4) tiny = false;
-      double alpha = a_pr_max; bool accepted = false; int ls = 0; double f_t = f;
-      const double* use_dx = dx.data(); const double* use_ds = ds.data(); const double* use_dy = dy.data();
-      double alpha_test = alpha;   // alpha used in the Armijo / switching tests
-      auto is_ftype = [&](double a) { return gbd < 0 && a * std::pow(-gbd, o.s_phi) > o.delta * std::pow(theta, o.s_theta); };
-      auto armijo = [&](double a, double ph_t) { return cmp_le(ph_t - phi, o.eta_phi * a * gbd, phi); };
-      auto acceptable = [&](double a_test, double th_t, double ph_t) {
-        if (!std::isfinite(th_t) || !std::isfinite(ph_t)) return false;
-        if (th_t > theta_max) return false;
-        bool acc;
-        if (a_test > 0 && is_ftype(a_test) && theta <= theta_min) acc = armijo(a_test, ph_t);
-        else acc = cmp_le(th_t, (1 - o.gamma_theta) * theta, theta) || cmp_le(ph_t - phi, -o.gamma_phi * theta, phi);
-        if (!acc) return false;
-        return filter_ok(th_t, ph_t);
-      };
-      if (tiny) {
-        for (int i = 0; i < n; ++i) xt[i] = x[i] + alpha * dx[i];
-        for (int r = 0; r < m; ++r) st[r] = s[r] + alpha * ds[r];
-        f_t = feval(xt.data(), gt.data()); accepted = true; ++tiny_count; tiny_flag = true;
-        if (tiny_count >= 2 && mu <= mu_floor) { status = STEP_TOO_SMALL; }
-      } else {
-        tiny_count = 0;
-        double amin = o.gamma_theta;
-        if (gbd < 0) {
-          amin = std::min(o.gamma_theta, o.gamma_phi * theta / (-gbd));
-          if (theta <= theta_min) amin = std::min(amin, o.delta * std::pow(theta, o.s_theta) / std::pow(-gbd, o.s_phi));
-        }
-        amin *= o.alpha_min_frac;
-        bool first = true;
-        while (alpha > amin || first) {
-          ++ls;
-          for (int i = 0; i < n; ++i) xt[i] = x[i] + alpha * dx[i];
-          for (int r = 0; r < m; ++r) st[r] = s[r] + alpha * ds[r];
-          f_t = feval(xt.data(), gt.data());
-          double th_t = 0; for (int r = 0; r < m; ++r) th_t += std::fabs(gt[r] - st[r]);
-          double ph_t = barrier(xt.data(), st.data(), f_t);
-          alpha_test = alpha;
-          if (acceptable(alpha, th_t, ph_t)) { accepted = true; break; }
-          if (first && o.max_soc > 0 && th_t >= theta && std::isfinite(th_t)) {
-            // ---- second-order correction
-            double a_soc = alpha; double th_prev = th_t;
-            for (int r = 0; r < m; ++r) csoc[r] = c[r];
-            std::vector<double> gs = gt, ss = st;
-            for (int k = 0; k < o.max_soc; ++k) {
-              for (int r = 0; r < m; ++r) csoc[r] = a_soc * csoc[r] + (gs[r] - ss[r]);
-              solve_dir(Ds, rx, rs, csoc.data(), dx2.data(), ds2.data(), dy2.data());
-              a_soc = ftb_primal(dx2.data(), ds2.data());
-              for (int i = 0; i < n; ++i) xt[i] = x[i] + a_soc * dx2[i];
-              for (int r = 0; r < m; ++r) ss[r] = s[r] + a_soc * ds2[r];
-              double f_s = feval(xt.data(), gs.data());
-              double th_s = 0; for (int r = 0; r < m; ++r) th_s += std::fabs(gs[r] - ss[r]);
-              double ph_s = barrier(xt.data(), ss.data(), f_s);
-              ++ls;
-              if (acceptable(alpha, th_s, ph_s)) {
-                accepted = true; f_t = f_s; gt = gs; st = ss; alpha = a_soc;
-                use_dx = dx2.data(); use_ds = ds2.data(); use_dy = dy2.data(); ++n_soc_acc;
-                break;
-              }
-              if (!(th_s <= o.kappa_soc * th_prev)) break;
-              th_prev = th_s;
-            }
-            if (accepted) break;
-          }
-          first = false;
-          alpha *= o.alpha_red;
-        }
-      }
-      if (status == STEP_TOO_SMALL) break;
-      if (!accepted) { status = RESTORATION_NEEDED; break; }
-      // -------- filter augmentation (uses the reference point and the original direction)
-      if (!tiny && !(is_ftype(alpha_test) && [&] {
-            double ph_t = barrier(xt.data(), st.data(), f_t); return armijo(alpha_test, ph_t); }())) {
-        filter.emplace_back((1 - o.gamma_theta) * theta, phi - o.gamma_phi * theta);
-      }
-      // -------- accept
-      if (use_dx != dx.data()) { dual_dirs(use_dx, use_ds); a_du = ftb_dual(); }
-      if (log) log->push_back({mu, f / df, pr, du, dw, alpha, a_du, ls});
-      x = xt; s = st; g = gt; f = f_t;
-      for (int r = 0; r < m; ++r) y[r] += alpha * use_dy[r];
-      for (int i = 0; i < n; ++i) { zL[i] += a_du * dzL[i]; zU[i] += a_du * dzU[i]; }
-      for (int r = 0; r < m; ++r) { vL[r] += a_du * dvL[r]; vU[r] += a_du * dvU[r]; }
-      auto reset = [&](double& z, double sl) { z = std::max(std::min(z, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl)); };
-      for (int i = 0; i < n; ++i) { if (xL[i] > -INF) reset(zL[i], x[i] - xL[i]); if (xU[i] < INF) reset(zU[i], xU[i] - x[i]); }
-      for (int r = 0; r < m; ++r) { if (dL[r] > -INF) reset(vL[r], s[r] - dL[r]); if (dU[r] < INF) reset(vU[r], dU[r] - s[r]); }
-      deriv(x.data());
-      ++iter;
-    }
-    // ---- finalize: honour original bounds, unscale
-    for (int i = 0; i < n; ++i) x_out[i] = std::min(std::max(x[i], lbx[i]), ubx[i]);
-    std::vector<double> gu(m);
-    double fu = P.eval_fg(x_out, gu.data());   // unscaled f, g at the returned point
-    if (g_out) std::memcpy(g_out, gu.data(), sizeof(double) * m);
-    if (lamx_out) for (int i = 0; i < n; ++i) lamx_out[i] = (zU[i] - zL[i]) / df;
-    if (lamg_out) for (int r = 0; r < m; ++r) lamg_out[r] = y[r] * dc[r] / df;
-    res.status = status; res.iters = iter; res.f = fu; res.n_fact = n_fact; res.n_soc_acc = n_soc_acc;
-    return res;
+  void eval_hess(double sigma, const double* y, double, double* W0) override {
+    for (int r = 0; r < m; ++r) ytmp[r] = y[r] * dc[r];
+    I.hess_l(sigma * df, ytmp.data(), W0);
   }
 };
 
-}  // namespace
+// RestoIpoptNLP:  min rho * sum(n + p) + eta(mu)/2 ||D_R (x - x_R)||^2   s.t.  d_L <= d(x) + n - p <= d_U,  x_L <= x <= x_U,  n, p >= 0
+struct RestoNlp : Nlp {
+  OrigNlp& O; std::vector<double> xR, dR2; double rho, eta_factor;
+  RestoNlp(OrigNlp& O_, const double* x_ref, double rho_, double eta_f) : O(O_), rho(rho_), eta_factor(eta_f) {
+    n0 = O.n0; ne = O.m; m = O.m; df = O.df; dc = O.dc;
+    xL = O.xL; xU = O.xU; xL.resize(n(), 0.0); xU.resize(n(), INF);
+    dL = O.dL; dU = O.dU;
+    xR.assign(x_ref, x_ref + n0); dR2.resize(n0);
+    for (int i = 0; i < n0; ++i) { double d = 1.0 / std::max(1.0, std::fabs(xR[i])); dR2[i] = d * d; }
+  }
+  double eta(double mu) const { return eta_factor * std::sqrt(mu); }
+  double eval_fg(const double* x, double mu, double* g0) override {
+    O.eval_fg(x, mu, g0);
+    double q = 0, l1 = 0;
+    for (int i = 0; i < n0; ++i) { double d = x[i] - xR[i]; q += dR2[i] * d * d; }
+    for (int j = n0; j < n(); ++j) l1 += x[j];
+    return rho * l1 + 0.5 * eta(mu) * q;
+  }
+  void eval_derivs(const double* x, double mu, double* grad, double* J0) override {
+    O.I.eval_derivs(x); O.jac(J0);
+    for (int i = 0; i < n0; ++i) grad[i] = eta(mu) * dR2[i] * (x[i] - xR[i]);
+    for (int j = n0; j < n(); ++j) grad[j] = rho;
+  }
+  void eval_hess(double sigma, const double* y, double mu, double* W0) override {
+    O.eval_hess(0.0, y, mu, W0);
+    for (int i = 0; i < n0; ++i) W0[(size_t)i * n0 + i] += sigma * eta(mu) * dR2[i];
+  }
+};
 
+struct Iter { std::vector<double> x, s, y, zL, zU, vL, vU; };
+
+struct Exit { Status st; };
+
+struct Algo {
+  Nlp& P; Options o; const bool is_resto; Algo* const outer; Counters& C;
+  const int n, n0, ne, m;
+  Iter cur, del, dsoc, tr;
+  double f = 0, f_t = 0; std::vector<double> g, g_t, grad, J0, W0, M;
+  double mu = 0.1, tau = 0.99; int iter = 0;
+  double resto_tol;                        // RestoConvergenceCheck may tighten the restoration problem's tolerance once
+  // linear system state
+  std::vector<double> Dx, Ds, Om, Sgx, Sgs, rX, rS, cvec;
+  double dw_last = 0.0, dw_cur = 0.0;
+  // FilterLSAcceptor
+  struct FEntry { double barr, theta; };
+  std::vector<FEntry> filter;
+  double theta_max = -1, theta_min = -1, ref_theta = 0, ref_barr = 0, ref_gbd = 0;
+  bool last_rej_filter = false; int succ_filter_rej = 0, n_filter_resets = 0;
+  // BacktrackingLineSearch
+  bool in_watchdog = false; int wd_short = 0, wd_trial = 0; double wd_theta = 0, wd_barr = 0, wd_gbd = 0, wd_alpha_test = 0, wd_dw = 0;
+  Iter wd_iter, wd_del;
+  bool in_soft = false; int soft_cnt = 0;
+  bool tiny_last = false, tiny_flag = false;
+  bool first_resto_iter = true;
+  std::vector<IterLog>* log = nullptr;
+  // info of the last iteration (log)
+  double info_alpha_pr = 0, info_alpha_du = 0; int info_ls = 0, info_tag = 0;
+
+  Algo(Nlp& P_, const Options& o_, bool resto_, Algo* outer_, Counters& C_)
+      : P(P_), o(o_), is_resto(resto_), outer(outer_), C(C_), n(P_.n()), n0(P_.n0), ne(P_.ne), m(P_.m) {
+    g.resize(m); g_t.resize(m); grad.resize(n); J0.resize((size_t)m * n0); W0.resize((size_t)n0 * n0);
+    const int nm = (ne && o.resto_explicit) ? n : n0;
+    M.resize((size_t)nm * nm);
+    Dx.resize(n); Ds.resize(m); Om.resize(m); Sgx.resize(n); Sgs.resize(m); rX.resize(n); rS.resize(m); cvec.resize(m);
+    resto_tol = o.tol;
+  }
+  static void resize(Iter& it, int n, int m) {
+    it.x.assign(n, 0); it.s.assign(m, 0); it.y.assign(m, 0); it.zL.assign(n, 0); it.zU.assign(n, 0); it.vL.assign(m, 0); it.vU.assign(m, 0);
+  }
+  bool hasxL(int i) const { return P.xL[i] > -INF; } bool hasxU(int i) const { return P.xU[i] < INF; }
+  bool hasdL(int r) const { return P.dL[r] > -INF; } bool hasdU(int r) const { return P.dU[r] < INF; }
+
+  // ---- small helpers -----------------------------------------------------------------------
+  double crow(const std::vector<double>& gg, const Iter& it, int r) const {     // residual of row r: d(x) + n - p - s
+    double c = gg[r] - it.s[r];
+    if (ne) c += it.x[n0 + r] - it.x[n0 + m + r];
+    return c;
+  }
+  double theta_of(const std::vector<double>& gg, const Iter& it) const { double t = 0; for (int r = 0; r < m; ++r) t += std::fabs(crow(gg, it, r)); return t; }
+  double infpr_of(const std::vector<double>& gg, const Iter& it) const { double t = 0; for (int r = 0; r < m; ++r) t = std::max(t, std::fabs(crow(gg, it, r))); return t; }
+  void JtY(const double* y, double* out) const {            // J_X^T y
+    for (int i = 0; i < n0; ++i) { double v = 0; for (int r = 0; r < m; ++r) v += J0[(size_t)r * n0 + i] * y[r]; out[i] = v; }
+    for (int r = 0; r < ne; ++r) { out[n0 + r] = y[r]; out[n0 + m + r] = -y[r]; }
+  }
+  void JX(const double* dX, double* out) const {            // J_X dX
+    for (int r = 0; r < m; ++r) {
+      double v = 0; const double* Jr = &J0[(size_t)r * n0];
+      for (int i = 0; i < n0; ++i) v += Jr[i] * dX[i];
+      if (ne) v += dX[n0 + r] - dX[n0 + m + r];
+      out[r] = v;
+    }
+  }
+  // CalculateSafeSlack: a slack that rounding has pushed to (or below) zero is replaced by a tiny positive value
+  double safe_slack(double sl, double z, double bnd, bool* adj = nullptr) const {
+    const double s_min = EPS * std::min(1.0, mu);
+    if (sl < s_min) {
+      if (adj) *adj = true;
+      const double t = std::max(mu / z, s_min);
+      return std::min(t, std::max(sl, 0.0) + o.slack_move * std::max(1.0, std::fabs(bnd)));
+    }
+    return sl;
+  }
+  double slxL(const Iter& it, int i) const { return safe_slack(it.x[i] - P.xL[i], cur.zL[i], P.xL[i]); }
+  double slxU(const Iter& it, int i) const { return safe_slack(P.xU[i] - it.x[i], cur.zU[i], P.xU[i]); }
+  double sldL(const Iter& it, int r) const { return safe_slack(it.s[r] - P.dL[r], cur.vL[r], P.dL[r]); }
+  double sldU(const Iter& it, int r) const { return safe_slack(P.dU[r] - it.s[r], cur.vU[r], P.dU[r]); }
+
+  double barrier_of(const Iter& it, double fv, double mu_) const {
+    double phi = fv;
+    for (int i = 0; i < n; ++i) {
+      const bool hl = hasxL(i), hu = hasxU(i);
+      if (hl) { double sl = slxL(it, i); phi -= mu_ * std::log(sl); if (!hu) phi += o.kappa_d * mu_ * sl; }
+      if (hu) { double sl = slxU(it, i); phi -= mu_ * std::log(sl); if (!hl) phi += o.kappa_d * mu_ * sl; }
+    }
+    for (int r = 0; r < m; ++r) {
+      const bool hl = hasdL(r), hu = hasdU(r);
+      if (hl) { double sl = sldL(it, r); phi -= mu_ * std::log(sl); if (!hu) phi += o.kappa_d * mu_ * sl; }
+      if (hu) { double sl = sldU(it, r); phi -= mu_ * std::log(sl); if (!hl) phi += o.kappa_d * mu_ * sl; }
+    }
+    return phi;
+  }
+  void eval_point() {      // f, g, grad, J at cur.x
+    f = P.eval_fg(cur.x.data(), mu, g.data());
+    P.eval_derivs(cur.x.data(), mu, grad.data(), J0.data());
+  }
+
+  // ---- optimality error (IpoptCalculatedQuantities::curr_nlp_error / curr_barrier_error) --------
+  struct Err { double du, pr, co, sd, sc, E; };
+  Err error_at(const Iter& it, const std::vector<double>& gg, const std::vector<double>& gradv, double mu_) const {
+    Err e{0, 0, 0, 1, 1, 0}; double sumy = 0, sumz = 0; int nz = 0;
+    std::vector<double> jty(n); JtY(it.y.data(), jty.data());
+    for (int i = 0; i < n; ++i) {
+      e.du = std::max(e.du, std::fabs(gradv[i] + jty[i] - it.zL[i] + it.zU[i]));
+      if (hasxL(i)) { e.co = std::max(e.co, std::fabs(slxL(it, i) * it.zL[i] - mu_)); sumz += std::fabs(it.zL[i]); ++nz; }
+      if (hasxU(i)) { e.co = std::max(e.co, std::fabs(slxU(it, i) * it.zU[i] - mu_)); sumz += std::fabs(it.zU[i]); ++nz; }
+    }
+    for (int r = 0; r < m; ++r) {
+      e.du = std::max(e.du, std::fabs(-it.y[r] - it.vL[r] + it.vU[r]));
+      e.pr = std::max(e.pr, std::fabs(crow(gg, it, r)));
+      sumy += std::fabs(it.y[r]);
+      if (hasdL(r)) { e.co = std::max(e.co, std::fabs(sldL(it, r) * it.vL[r] - mu_)); sumz += std::fabs(it.vL[r]); ++nz; }
+      if (hasdU(r)) { e.co = std::max(e.co, std::fabs(sldU(it, r) * it.vU[r] - mu_)); sumz += std::fabs(it.vU[r]); ++nz; }
+    }
+    e.sd = std::max(o.s_max, (sumy + sumz) / std::max(1, m + nz)) / o.s_max;
+    e.sc = std::max(o.s_max, sumz / std::max(1, nz)) / o.s_max;
+    e.E = std::max(e.du / e.sd, std::max(e.pr, e.co / e.sc));
+    return e;
+  }
+  Err error(double mu_) const { return error_at(cur, g, grad, mu_); }
+  // curr/trial_primal_dual_system_error (soft restoration phase): averaged 1-norms
+  double pd_error(const Iter& it, const std::vector<double>& gg, const std::vector<double>& gradv, const std::vector<double>& jty) const {
+    double du = 0, pr = 0, co = 0; int nb = 0;
+    for (int i = 0; i < n; ++i) {
+      du += std::fabs(gradv[i] + jty[i] - it.zL[i] + it.zU[i]);
+      if (hasxL(i)) { co += std::fabs(slxL(it, i) * it.zL[i] - mu); ++nb; }
+      if (hasxU(i)) { co += std::fabs(slxU(it, i) * it.zU[i] - mu); ++nb; }
+    }
+    for (int r = 0; r < m; ++r) {
+      du += std::fabs(-it.y[r] - it.vL[r] + it.vU[r]); pr += std::fabs(crow(gg, it, r));
+      if (hasdL(r)) { co += std::fabs(sldL(it, r) * it.vL[r] - mu); ++nb; }
+      if (hasdU(r)) { co += std::fabs(sldU(it, r) * it.vU[r] - mu); ++nb; }
+    }
+    return du / (n + m) + (m > 0 ? pr / m : 0.0) + (nb > 0 ? co / nb : 0.0);
+  }
+
+  // ---- linear algebra: condensed primal-dual system -------------------------------------------------
+  // (W + D_x + J^T D_s J) dX = -(r_X + J^T (D_s c + r_s));  ds = J dX + c;  dy = D_s ds + r_s.
+  // Restoration problem: the n/p variables are eliminated row by row (AugRestoSystemSolver), which turns D_s into
+  // Omega = 1 / (1/D_s + 1/D_n + 1/D_p) and leaves a system in the structural variables only.
+  bool factor(bool use_W, const std::vector<double>& Dx_, const std::vector<double>& Ds_) {
+    ++C.n_fact;
+    if (&Dx_ != &Dx) Dx = Dx_;
+    if (&Ds_ != &Ds) Ds = Ds_;
+    const bool expl = ne && o.resto_explicit;
+    const int nm = expl ? n : n0;
+    std::fill(M.begin(), M.end(), 0.0);
+    if (use_W) for (int a = 0; a < n0; ++a) for (int b = 0; b <= a; ++b) M[(size_t)a * nm + b] = W0[(size_t)a * n0 + b];
+    for (int i = 0; i < nm; ++i) M[(size_t)i * nm + i] += Dx[i];
+    for (int r = 0; r < m; ++r) {
+      Om[r] = (ne && !expl) ? 1.0 / (1.0 / Ds[r] + 1.0 / Dx[n0 + r] + 1.0 / Dx[n0 + m + r]) : Ds[r];
+      const double* Jr = &J0[(size_t)r * n0]; const double d = Om[r];
+      int last = -1; for (int c = n0 - 1; c >= 0; --c) if (Jr[c] != 0.0) { last = c; break; }
+      for (int a = 0; a <= last; ++a) { double ja = d * Jr[a]; if (ja == 0.0) continue; double* Mr = &M[(size_t)a * nm];
+        for (int b = 0; b <= a; ++b) Mr[b] += ja * Jr[b]; }
+      if (expl) {
+        double* Mn = &M[(size_t)(n0 + r) * nm]; double* Mp = &M[(size_t)(n0 + m + r) * nm];
+        for (int b = 0; b <= last; ++b) { Mn[b] += d * Jr[b]; Mp[b] -= d * Jr[b]; }
+        Mn[n0 + r] += d; Mp[n0 + m + r] += d; Mp[n0 + r] -= d;
+      }
+    }
+    return cholesky(M.data(), nm);
+  }
+  void solve_dir(const std::vector<double>& rx, const std::vector<double>& rs, const double* cc, Iter& d) {
+    const bool expl = ne && o.resto_explicit;
+    std::vector<double> t(m), tt(m), q(m);
+    for (int r = 0; r < m; ++r) t[r] = Ds[r] * cc[r] + rs[r];
+    if (ne && !expl) {
+      for (int r = 0; r < m; ++r) {
+        const double Dn = Dx[n0 + r], Dp = Dx[n0 + m + r], det = Dn * Dp + Ds[r] * (Dn + Dp);
+        const double bn = rx[n0 + r] + t[r], bp = rx[n0 + m + r] - t[r];
+        tt[r] = t[r] + Ds[r] * (-Dp * bn + Dn * bp) / det;
+      }
+    } else tt = t;
+    const int nm = expl ? n : n0;
+    std::vector<double> rhs(nm);
+    for (int i = 0; i < n0; ++i) { double v = rx[i]; for (int r = 0; r < m; ++r) v += J0[(size_t)r * n0 + i] * tt[r]; rhs[i] = -v; }
+    if (expl) for (int r = 0; r < m; ++r) { rhs[n0 + r] = -(rx[n0 + r] + t[r]); rhs[n0 + m + r] = -(rx[n0 + m + r] - t[r]); }
+    chol_solve(M.data(), nm, rhs.data());
+    for (int i = 0; i < nm; ++i) d.x[i] = rhs[i];
+    for (int r = 0; r < m; ++r) { double v = 0; const double* Jr = &J0[(size_t)r * n0]; for (int i = 0; i < n0; ++i) v += Jr[i] * d.x[i]; q[r] = v; }
+    if (ne && !expl) {
+      for (int r = 0; r < m; ++r) {
+        const double Dn = Dx[n0 + r], Dp = Dx[n0 + m + r], det = Dn * Dp + Ds[r] * (Dn + Dp);
+        const double bn = rx[n0 + r] + t[r], bp = rx[n0 + m + r] - t[r];
+        d.x[n0 + r] = (-(Dp + Ds[r]) * bn - Ds[r] * bp - Ds[r] * Dp * q[r]) / det;
+        d.x[n0 + m + r] = (-Ds[r] * bn - (Dn + Ds[r]) * bp + Ds[r] * Dn * q[r]) / det;
+      }
+    }
+    for (int r = 0; r < m; ++r) {
+      double jd = q[r]; if (ne) jd += d.x[n0 + r] - d.x[n0 + m + r];
+      d.s[r] = jd + cc[r]; d.y[r] = Ds[r] * d.s[r] + rs[r];
+    }
+  }
+  void dual_dirs(Iter& d) const {
+    for (int i = 0; i < n; ++i) {
+      d.zL[i] = d.zU[i] = 0;
+      if (hasxL(i)) { double sl = slxL(cur, i); d.zL[i] = (mu - cur.zL[i] * d.x[i]) / sl - cur.zL[i]; }
+      if (hasxU(i)) { double sl = slxU(cur, i); d.zU[i] = (mu + cur.zU[i] * d.x[i]) / sl - cur.zU[i]; }
+    }
+    for (int r = 0; r < m; ++r) {
+      d.vL[r] = d.vU[r] = 0;
+      if (hasdL(r)) { double sl = sldL(cur, r); d.vL[r] = (mu - cur.vL[r] * d.s[r]) / sl - cur.vL[r]; }
+      if (hasdU(r)) { double sl = sldU(cur, r); d.vU[r] = (mu + cur.vU[r] * d.s[r]) / sl - cur.vU[r]; }
+    }
+  }
+  double ftb_primal(const Iter& d) const {
+    double a = 1.0;
+    for (int i = 0; i < n; ++i) {
+      if (hasxL(i) && d.x[i] < 0) a = std::min(a, -tau * slxL(cur, i) / d.x[i]);
+      if (hasxU(i) && d.x[i] > 0) a = std::min(a, tau * slxU(cur, i) / d.x[i]);
+    }
+    for (int r = 0; r < m; ++r) {
+      if (hasdL(r) && d.s[r] < 0) a = std::min(a, -tau * sldL(cur, r) / d.s[r]);
+      if (hasdU(r) && d.s[r] > 0) a = std::min(a, tau * sldU(cur, r) / d.s[r]);
+    }
+    return a;
+  }
+  static double ftb_dual_of(const Iter& z, const Iter& d, double tau_, const Algo& A) {
+    double a = 1.0;
+    for (int i = 0; i < A.n; ++i) {
+      if (d.zL[i] < 0 && A.hasxL(i)) a = std::min(a, -tau_ * z.zL[i] / d.zL[i]);
+      if (d.zU[i] < 0 && A.hasxU(i)) a = std::min(a, -tau_ * z.zU[i] / d.zU[i]);
+    }
+    for (int r = 0; r < A.m; ++r) {
+      if (d.vL[r] < 0 && A.hasdL(r)) a = std::min(a, -tau_ * z.vL[r] / d.vL[r]);
+      if (d.vU[r] < 0 && A.hasdU(r)) a = std::min(a, -tau_ * z.vU[r] / d.vU[r]);
+    }
+    return a;
+  }
+  double ftb_dual(const Iter& d) const { return ftb_dual_of(cur, d, tau, *this); }
+  // gradient of the barrier function (with damping) times the step
+  double grad_barr_t_delta(const Iter& d) const {
+    double gbd = 0;
+    for (int i = 0; i < n; ++i) {
+      double gi = grad[i]; const bool hl = hasxL(i), hu = hasxU(i);
+      if (hl) gi -= mu / slxL(cur, i);
+      if (hu) gi += mu / slxU(cur, i);
+      if (hl && !hu) gi += o.kappa_d * mu;
+      if (hu && !hl) gi -= o.kappa_d * mu;
+      gbd += gi * d.x[i];
+    }
+    for (int r = 0; r < m; ++r) {
+      double gi = 0; const bool hl = hasdL(r), hu = hasdU(r);
+      if (hl) gi -= mu / sldL(cur, r);
+      if (hu) gi += mu / sldU(cur, r);
+      if (hl && !hu) gi += o.kappa_d * mu;
+      if (hu && !hl) gi -= o.kappa_d * mu;
+      gbd += gi * d.s[r];
+    }
+    return gbd;
+  }
+
+  // ---- search direction (with inertia correction) ---------------------------------------------------
+  bool compute_direction() {
+    P.eval_hess(1.0, cur.y.data(), mu, W0.data());
+    std::vector<double> jty(n); JtY(cur.y.data(), jty.data());
+    for (int i = 0; i < n; ++i) {
+      double sig = 0, r_ = grad[i] + jty[i]; const bool hl = hasxL(i), hu = hasxU(i);
+      if (hl) { double sl = slxL(cur, i); sig += cur.zL[i] / sl; r_ -= mu / sl; }
+      if (hu) { double sl = slxU(cur, i); sig += cur.zU[i] / sl; r_ += mu / sl; }
+      if (hl && !hu) r_ += o.kappa_d * mu;
+      if (hu && !hl) r_ -= o.kappa_d * mu;
+      Sgx[i] = sig; rX[i] = r_;
+    }
+    for (int r = 0; r < m; ++r) {
+      double sig = 0, r_ = -cur.y[r]; const bool hl = hasdL(r), hu = hasdU(r);
+      if (hl) { double sl = sldL(cur, r); sig += cur.vL[r] / sl; r_ -= mu / sl; }
+      if (hu) { double sl = sldU(cur, r); sig += cur.vU[r] / sl; r_ += mu / sl; }
+      if (hl && !hu) r_ += o.kappa_d * mu;
+      if (hu && !hl) r_ -= o.kappa_d * mu;
+      Sgs[r] = sig; rS[r] = r_;
+      cvec[r] = crow(g, cur, r);
+    }
+    double dw = 0.0; bool ok = false;
+    for (;;) {       // PDPerturbationHandler: delta_x = delta_s = dw, delta_c = delta_d = 0
+      for (int i = 0; i < n; ++i) Dx[i] = Sgx[i] + dw;
+      for (int r = 0; r < m; ++r) Ds[r] = Sgs[r] + dw;
+      ok = factor(true, Dx, Ds);
+      if (ok) break;
+      if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : std::max(o.dw_min, dw_last * o.dw_dec);
+      else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
+      if (dw > o.dw_max) break;
+    }
+    if (!ok) return false;
+    if (dw > 0) dw_last = dw;
+    dw_cur = dw;
+    solve_dir(rX, rS, cvec.data(), del);
+    dual_dirs(del);
+    return true;
+  }
+
+  // ---- FilterLSAcceptor ---------------------------------------------------------------------------------
+  bool filter_acceptable(double barr, double theta) const {
+    for (auto& e : filter) if (!(cmp_le(barr, e.barr, e.barr) || cmp_le(theta, e.theta, e.theta))) return false;
+    return true;
+  }
+  void augment_filter() {
+    const FEntry ne_{ref_barr - o.gamma_phi * ref_theta, (1 - o.gamma_theta) * ref_theta};
+    std::vector<FEntry> keep;
+    for (auto& e : filter) if (!(e.barr >= ne_.barr && e.theta >= ne_.theta)) keep.push_back(e);    // drop dominated entries
+    if ((int)keep.size() >= o.filter_cap) keep.erase(keep.begin());       // bounded filter (the kernel's FILT_CAP): drop the oldest
+    keep.push_back(ne_); filter.swap(keep);
+  }
+  void acceptor_reset() { filter.clear(); last_rej_filter = false; succ_filter_rej = 0; }
+  bool is_ftype(double a_test) const {
+    if (ref_theta == 0.0 && ref_gbd > 0.0 && ref_gbd < 100.0 * EPS) return true;
+    return ref_gbd < 0.0 && a_test * std::pow(-ref_gbd, o.s_phi) > o.delta * std::pow(ref_theta, o.s_theta);
+  }
+  bool armijo(double a_test, double trial_barr) const { return cmp_le(trial_barr - ref_barr, o.eta_phi * a_test * ref_gbd, ref_barr); }
+  bool acceptable_to_current_iterate(double trial_barr, double trial_theta, bool from_resto = false) const {
+    if (!from_resto && trial_barr > ref_barr) {
+      double basval = 1.0; if (std::fabs(ref_barr) > 10.0) basval = std::log10(std::fabs(ref_barr));
+      if (std::log10(trial_barr - ref_barr) > o.obj_max_inc + basval) return false;
+    }
+    return cmp_le(trial_theta, (1 - o.gamma_theta) * ref_theta, ref_theta) || cmp_le(trial_barr - ref_barr, -o.gamma_phi * ref_theta, ref_barr);
+  }
+  bool check_acceptability(double a_test, double trial_barr, double trial_theta) {
+    if (!std::isfinite(trial_barr) || !std::isfinite(trial_theta)) return false;
+    if (theta_max < 0) theta_max = o.theta_max_fact * std::max(1.0, ref_theta);
+    if (theta_min < 0) theta_min = o.theta_min_fact * std::max(1.0, ref_theta);
+    if (theta_max > 0 && trial_theta > theta_max) return false;
+    bool acc;
+    if (a_test > 0.0 && is_ftype(a_test) && ref_theta <= theta_min) acc = armijo(a_test, trial_barr);
+    else acc = acceptable_to_current_iterate(trial_barr, trial_theta);
+    if (!acc) { last_rej_filter = false; return false; }
+    acc = filter_acceptable(trial_barr, trial_theta);
+    if (!acc) last_rej_filter = true;
+    return acc;
+  }
+  double alpha_min() const {
+    const double gbd = grad_barr_t_delta(del), th = theta_of(g, cur);
+    double amin = o.gamma_theta;
+    if (gbd < 0) {
+      amin = std::min(o.gamma_theta, o.gamma_phi * th / (-gbd));
+      if (th <= theta_min) amin = std::min(amin, o.delta * std::pow(th, o.s_theta) / std::pow(-gbd, o.s_phi));
+    }
+    return o.alpha_min_frac * amin;
+  }
+  void init_this_line_search() {
+    if (!in_watchdog) {
+      // filter reset heuristic: the last rejection was due to the filter in filter_reset_trigger successive iterations
+      if (o.max_filter_resets > 0) {
+        if (n_filter_resets < o.max_filter_resets) {
+          if (last_rej_filter) {
+            if (++succ_filter_rej >= o.filter_reset_trigger) { acceptor_reset(); ++n_filter_resets; ++C.n_filter_reset; }
+          } else succ_filter_rej = 0;
+        }
+      }
+      last_rej_filter = false;
+      ref_theta = theta_of(g, cur); ref_barr = barrier_of(cur, f, mu); ref_gbd = grad_barr_t_delta(del);
+    } else { ref_theta = wd_theta; ref_barr = wd_barr; ref_gbd = wd_gbd; }
+  }
+
+  // ---- trial points -----------------------------------------------------------------------------------------
+  double theta_t = 0, barr_t = 0;
+  bool eval_trial(double alpha, const Iter& d) {        // primal trial point; false on evaluation error (NaN / Inf)
+    for (int i = 0; i < n; ++i) tr.x[i] = cur.x[i] + alpha * d.x[i];
+    for (int r = 0; r < m; ++r) tr.s[r] = cur.s[r] + alpha * d.s[r];
+    f_t = P.eval_fg(tr.x.data(), mu, g_t.data());
+    theta_t = theta_of(g_t, tr); barr_t = barrier_of(tr, f_t, mu);
+    return std::isfinite(theta_t) && std::isfinite(barr_t);
+  }
+  void dual_step(double a_pr, double a_du, const Iter& d) {
+    for (int r = 0; r < m; ++r) { tr.y[r] = cur.y[r] + a_pr * d.y[r]; tr.vL[r] = cur.vL[r] + a_du * d.vL[r]; tr.vU[r] = cur.vU[r] + a_du * d.vU[r]; }
+    for (int i = 0; i < n; ++i) { tr.zL[i] = cur.zL[i] + a_du * d.zL[i]; tr.zU[i] = cur.zU[i] + a_du * d.zU[i]; }
+  }
+  bool detect_tiny_step() const {
+    for (int i = 0; i < n; ++i) if (std::fabs(del.x[i]) / (1 + std::fabs(cur.x[i])) > o.tiny_step_tol) return false;
+    for (int r = 0; r < m; ++r) if (std::fabs(del.s[r]) / (1 + std::fabs(cur.s[r])) > o.tiny_step_tol) return false;
+    return theta_of(g, cur) <= 1e-4;
+  }
+  void start_watchdog() {
+    ++C.n_watchdog;
+    in_watchdog = true; wd_iter = cur; wd_del = del; wd_trial = 0; wd_alpha_test = ftb_primal(del); wd_dw = dw_cur;
+    wd_theta = ref_theta; wd_barr = ref_barr; wd_gbd = ref_gbd;
+  }
+  void stop_watchdog() {
+    in_watchdog = false; cur = wd_iter; del = wd_del; wd_short = 0; dw_cur = wd_dw;
+    eval_point();
+    // The primal step (dx, ds) is the stored one; its dual parts are recomputed at the restored point with the CURRENT
+    // barrier parameter (identical to the stored ones unless mu changed while the watchdog was active; the CUDA kernel
+    // never stores dual steps, it derives them from (dx, ds) when it needs them).
+    for (int r = 0; r < m; ++r) {
+      double sig = 0, r_ = -cur.y[r]; const bool hl = hasdL(r), hu = hasdU(r);
+      if (hl) { double sl = sldL(cur, r); sig += cur.vL[r] / sl; r_ -= mu / sl; }
+      if (hu) { double sl = sldU(cur, r); sig += cur.vU[r] / sl; r_ += mu / sl; }
+      if (hl && !hu) r_ += o.kappa_d * mu;
+      if (hu && !hl) r_ -= o.kappa_d * mu;
+      del.y[r] = (sig + wd_dw) * del.s[r] + r_;
+    }
+    dual_dirs(del);
+    ref_theta = wd_theta; ref_barr = wd_barr; ref_gbd = wd_gbd;
+  }
+  // second-order correction (FilterLSAcceptor::TrySecondOrderCorrection)
+  bool try_soc(double a_test, double& alpha_primal, Iter*& actual) {
+    if (o.max_soc == 0) return false;
+    bool accept = false; int count = 0; double theta_old = 0, theta_trial = theta_t, a_soc = alpha_primal;
+    std::vector<double> csoc(cvec);
+    while (count < o.max_soc && !accept && (count == 0 || theta_trial <= o.kappa_soc * theta_old)) {
+      theta_old = theta_trial;
+      for (int r = 0; r < m; ++r) csoc[r] = a_soc * csoc[r] + crow(g_t, tr, r);
+      solve_dir(rX, rS, csoc.data(), dsoc);
+      dual_dirs(dsoc);
+      a_soc = ftb_primal(dsoc);
+      const bool okv = eval_trial(a_soc, dsoc);
+      ++info_ls;
+      if (!okv) break;
+      accept = check_acceptability(a_test, barr_t, theta_t);
+      if (accept) { alpha_primal = a_soc; actual = &dsoc; ++C.n_soc_acc; }
+      else { ++count; theta_trial = theta_t; }
+    }
+    return accept;
+  }
+  // BacktrackingLineSearch::DoBacktrackingLineSearch
+  bool do_backtracking(bool skip_first, double& alpha_primal, bool& soc_taken, int& n_steps, bool& eval_err, Iter*& actual) {
+    eval_err = false; bool accept = false;
+    const double a_max = ftb_primal(*actual);
+    double amin = a_max;
+    if (!in_watchdog) amin = alpha_min();
+    alpha_primal = a_max;
+    double a_test = alpha_primal;
+    if (in_watchdog) a_test = wd_alpha_test;
+    if (skip_first) alpha_primal *= o.alpha_red;
+    while (alpha_primal > amin || n_steps == 0) {
+      const bool okv = eval_trial(alpha_primal, *actual);
+      ++info_ls;
+      if (!in_watchdog) a_test = alpha_primal;      // IPOPT sets alpha_primal_test = alpha_primal inside the loop ...
+      else a_test = wd_alpha_test;                  // ... except that the watchdog keeps testing against its reference step
+      if (okv) accept = check_acceptability(a_test, barr_t, theta_t); else { accept = false; eval_err = true; }
+      if (accept) break;
+      if (in_watchdog) break;
+      if (okv && alpha_primal == a_max && ref_theta <= theta_t) {
+        accept = try_soc(a_test, alpha_primal, actual);
+        if (accept) { soc_taken = true; break; }
+      }
+      alpha_primal *= o.alpha_red; ++n_steps;
+    }
+    if (accept) {     // UpdateForNextIteration: augment the filter unless the step was an Armijo-accepted f-type step
+      if (!is_ftype(a_test) || !armijo(a_test, barr_t)) { augment_filter(); info_tag = soc_taken ? 'H' : 'h'; }
+      else info_tag = soc_taken ? 'F' : 'f';
+    } else if (in_watchdog) info_tag = 'w';
+    return accept;
+  }
+  // BacktrackingLineSearch::TrySoftRestoStep
+  bool try_soft_resto_step(const Iter& d, bool& satisfies_original) {
+    satisfies_original = false;
+    if (o.soft_resto_red == 0.0) return false;
+    const double alpha = std::min(ftb_primal(d), ftb_dual(d));
+    if (!eval_trial(alpha, d)) return false;
+    dual_step(alpha, alpha, d);
+    info_alpha_pr = alpha; info_alpha_du = alpha;
+    if (check_acceptability(0.0, barr_t, theta_t)) { satisfies_original = true; return true; }
+    std::vector<double> jty(n), grad_t(n), Jsave(J0);
+    JtY(cur.y.data(), jty.data());
+    const double curr_err = pd_error(cur, g, grad, jty);
+    P.eval_derivs(tr.x.data(), mu, grad_t.data(), J0.data());
+    JtY(tr.y.data(), jty.data());
+    const double trial_err = pd_error(tr, g_t, grad_t, jty);
+    J0.swap(Jsave);
+    if (trial_err <= o.soft_resto_red * curr_err) { ++C.n_soft; return true; }
+    P.eval_derivs(cur.x.data(), mu, grad_t.data(), Jsave.data());      // leave the model's derivative state at the current point
+    return false;
+  }
+
+  // BacktrackingLineSearch::FindAcceptableTrialPoint.  On return `tr` (primal and dual) is the next iterate.
+  void line_search(bool fallback) {
+    info_ls = 0; info_tag = '?'; info_alpha_du = 0;
+    bool goto_resto = fallback;
+    init_this_line_search();
+    Iter* actual = &del;
+    bool accept = false, soc_taken = false; int n_steps = 0; double alpha_primal = 0.0;
+    bool tiny = !goto_resto && detect_tiny_step();
+    if (in_watchdog && (goto_resto || tiny)) { stop_watchdog(); goto_resto = false; tiny = false; actual = &del; }
+    if (o.watchdog_trigger > 0 && !in_watchdog && !goto_resto && !tiny && !in_soft && wd_short >= o.watchdog_trigger) start_watchdog();
+    if (tiny) {
+      alpha_primal = ftb_primal(del);
+      if (!eval_trial(alpha_primal, del)) throw Exit{INVALID_NUMBER};
+      if (tiny_last) { tiny_flag = true; info_tag = 'T'; } else info_tag = 't';
+      double dyn = 0; for (int r = 0; r < m; ++r) dyn = std::max(dyn, std::fabs(del.y[r]));
+      tiny_last = dyn < o.tiny_step_y_tol;
+      accept = true;
+    } else tiny_last = false;
+    if (!goto_resto && !tiny) {
+      if (in_soft) {
+        if (++soft_cnt > o.max_soft_resto) accept = false;
+        else {
+          bool sat = false;
+          accept = try_soft_resto_step(*actual, sat);
+          if (accept) { info_tag = 's'; if (sat) { in_soft = false; soft_cnt = 0; info_tag = 'S'; } }
+        }
+      } else {
+        bool done = false, skip_first = false, eval_err = false;
+        while (!done) {
+          accept = do_backtracking(skip_first, alpha_primal, soc_taken, n_steps, eval_err, actual);
+          if (in_watchdog) {
+            if (accept) { in_watchdog = false; done = true; }
+            else if (eval_err || ++wd_trial > o.watchdog_trial_max) { stop_watchdog(); actual = &del; skip_first = true; }
+            else { done = true; accept = true; }
+          } else done = true;
+        }
+      }
+    }
+    if (!accept) {
+      if (!in_soft && !goto_resto) {      // try the current direction as a soft restoration step
+        augment_filter();                 // PrepareRestoPhaseStart
+        bool sat = false;
+        accept = try_soft_resto_step(*actual, sat);
+        if (accept) { if (sat) info_tag = 'S'; else { in_soft = true; info_tag = 's'; } }
+      }
+      if (!accept) {
+        if (!in_soft) augment_filter();
+        if (theta_of(g, cur) <= 1e-2 * o.tol) throw Exit{RESTORATION_FAILED};     // "Restoration phase called, but point is almost feasible"
+        if (!o.resto) throw Exit{RESTORATION_FAILED};
+        info_alpha_pr = alpha_primal; info_tag = 'R';
+        perform_restoration();            // throws on failure; on success tr holds the new iterate
+        in_soft = false; soft_cnt = 0; wd_short = 0;
+      }
+    } else if (!in_soft || tiny) {
+      const double a_du = ftb_dual(*actual);
+      dual_step(alpha_primal, a_du, *actual);
+      info_alpha_pr = alpha_primal; info_alpha_du = a_du;
+      if (n_steps == 0) wd_short = 0; else ++wd_short;
+    }
+  }
+
+  // IpoptAlgorithm::AcceptTrialPoint: slack safeguard (bounds move), kappa_sigma correction, new current point
+  void accept_trial_point() {
+    // IPOPT moves a bound whose slack had to be safeguarded (AdjustVariableBounds) and then recomputes the slack as
+    // x - x_L, which rounds back to zero and is safeguarded again; here the bound stays and EVERY slack evaluation goes
+    // through safe_slack() instead (same values up to slack_move * |bound| ~ 1e-12; the CUDA kernel does the same).
+    {
+      bool a = false;
+      for (int i = 0; i < n; ++i) {
+        if (hasxL(i)) { a = false; safe_slack(tr.x[i] - P.xL[i], cur.zL[i], P.xL[i], &a); C.n_slack_adj += a; }
+        if (hasxU(i)) { a = false; safe_slack(P.xU[i] - tr.x[i], cur.zU[i], P.xU[i], &a); C.n_slack_adj += a; }
+      }
+      for (int r = 0; r < m; ++r) {
+        if (hasdL(r)) { a = false; safe_slack(tr.s[r] - P.dL[r], cur.vL[r], P.dL[r], &a); C.n_slack_adj += a; }
+        if (hasdU(r)) { a = false; safe_slack(P.dU[r] - tr.s[r], cur.vU[r], P.dU[r], &a); C.n_slack_adj += a; }
+      }
+    }
+    // (every slack goes through the safeguard, also after a bound has moved: x - (x - 1e-17) rounds to zero)
+    auto reset = [&](double& z, double sl) { z = std::max(std::min(z, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl)); };
+    for (int i = 0; i < n; ++i) { if (hasxL(i)) reset(tr.zL[i], slxL(tr, i)); if (hasxU(i)) reset(tr.zU[i], slxU(tr, i)); }
+    for (int r = 0; r < m; ++r) { if (hasdL(r)) reset(tr.vL[r], sldL(tr, r)); if (hasdU(r)) reset(tr.vU[r], sldU(tr, r)); }
+    cur = tr; f = f_t; g = g_t;
+    P.eval_derivs(cur.x.data(), mu, grad.data(), J0.data());
+  }
+
+  // ---- MonotoneMuUpdate ---------------------------------------------------------------------------------
+  bool mu_initialized = false;
+  void update_mu() {
+    const double mu_floor = std::min(o.tol, P.df * o.compl_inf_tol) / (o.kappa_eps + 1.0);
+    bool tf = tiny_flag; tiny_flag = false;
+    if (is_resto && !mu_initialized) { mu_initialized = true; return; }     // first restoration iteration: mu comes from the initializer
+    mu_initialized = true;
+    double Emu = error(mu).E;
+    bool done = false;
+    while ((Emu <= o.kappa_eps * mu || tf) && !done) {
+      const double nm = std::max(mu_floor, std::min(o.kappa_mu * mu, std::pow(mu, o.theta_mu)));
+      const bool changed = nm != mu;
+      if (!changed && tf) throw Exit{STEP_TOO_SMALL};        // TINY_STEP_DETECTED: "solved to best possible numerical accuracy"
+      if (!changed) break;
+      mu = nm; tau = std::max(o.tau_min, 1 - mu);
+      if (is_resto) { f = P.eval_fg(cur.x.data(), mu, g.data()); P.eval_derivs(cur.x.data(), mu, grad.data(), J0.data()); }   // objective depends on mu
+      if (tf) { done = true; tf = false; }
+      else { Emu = error(mu).E; done = !(Emu <= o.kappa_eps * mu); }
+      in_soft = false; soft_cnt = 0; acceptor_reset();        // linesearch_->Reset()
+    }
+  }
+
+  // ---- convergence checks -------------------------------------------------------------------------------
+  Status check_convergence_orig(const double* lbg, const double* ubg) {
+    const Err e = error(0.0);
+    if (!std::isfinite(e.E) || !std::isfinite(f)) { if (getenv("ORACLE_DEBUG")) fprintf(stderr, "orig invalid: E %g du %g pr %g co %g f %g mu %g iter %d\n", e.E, e.du, e.pr, e.co, f, mu, iter); return INVALID_NUMBER; }
+    double viol = 0;
+    for (int r = 0; r < m; ++r) {
+      const double gu = g[r] / P.dc[r];
+      if (lbg[r] > -1e19) viol = std::max(viol, lbg[r] - gu);
+      if (ubg[r] < 1e19) viol = std::max(viol, gu - ubg[r]);
+    }
+    if (e.E <= o.tol && e.du / P.df <= o.dual_inf_tol && viol <= o.constr_viol_tol && e.co / P.df <= o.compl_inf_tol) return SOLVE_SUCCEEDED;
+    // (acceptable-level termination: the scripts set acceptable_tol = tol = 1e-8, NMPC_TT.py:260, so an "acceptable" point
+    //  already satisfies the regular test and the acceptable_iter counter can never fire first)
+    if (iter >= o.max_iter) return MAXITER_EXCEEDED;
+    return CONTINUE;
+  }
+  // RestoFilterConvergenceCheck: is the restoration iterate good enough for the ORIGINAL problem's filter?
+  Status check_convergence_resto() {
+    Algo& A = *outer; OrigNlp& O = static_cast<RestoNlp&>(P).O;
+    if (iter >= o.max_iter) return MAXITER_EXCEEDED;
+    Iter ot; ot.x.assign(cur.x.begin(), cur.x.begin() + n0); ot.s = cur.s;
+    std::vector<double> og(m);
+    const double of = O.eval_fg(ot.x.data(), A.mu, og.data());
+    const double trial_theta = A.theta_of(og, ot), trial_infpr = A.infpr_of(og, ot);
+    const double curr_infpr = A.infpr_of(A.g, A.cur);
+    double infpr_max = std::max(o.kappa_resto * curr_infpr, std::min(A.o.tol, A.o.constr_viol_tol));
+    if (o.kappa_resto == 0.0) infpr_max = 0.0;
+    Status st = CONTINUE;
+    if (first_resto_iter) st = CONTINUE;                                  // always take at least one step
+    else if (trial_infpr > infpr_max) st = CONTINUE;                      // not enough reduction of the original infeasibility
+    else {
+      // barrier function of the original problem at the restoration iterate (original mu, original bounds)
+      Iter full = A.cur; full.x = ot.x; full.s = ot.s;
+      const double trial_barr = A.barrier_of(full, of, A.mu);
+      if (!A.filter_acceptable(trial_barr, trial_theta)) st = CONTINUE;
+      else if (!A.acceptable_to_current_iterate(trial_barr, trial_theta, true)) st = CONTINUE;
+      else st = RESTO_SUCCESS;
+    }
+    if (st == CONTINUE) {      // is the restoration problem itself solved?  then the original one is locally infeasible
+      const Err e = error(0.0);
+      if (!std::isfinite(e.E) || !std::isfinite(f)) { if (getenv("ORACLE_DEBUG")) fprintf(stderr, "resto invalid: E %g du %g pr %g co %g f %g mu %g iter %d\n", e.E, e.du, e.pr, e.co, f, mu, iter); return INVALID_NUMBER; }
+      const double viol = infpr_of(g, cur);
+      if (e.E <= resto_tol && e.du / P.df <= o.dual_inf_tol && viol <= o.constr_viol_tol && e.co / P.df <= o.compl_inf_tol) {
+        if (trial_infpr <= 1e2 * resto_tol) {
+          if (resto_tol > 1e-1 * A.o.tol) { resto_tol *= 1e-2; st = CONTINUE; }     // tighten once: problem only slightly infeasible
+          else st = RESTO_CONVERGED_TO_FEASIBLE;
+        } else st = INFEASIBLE_PROBLEM_DETECTED;
+      }
+    }
+    first_resto_iter = false;
+    return st;
+  }
+
+  // ---- restoration phase -------------------------------------------------------------------------------------
+  void perform_restoration() {
+    if (is_resto) {       // RestoRestorationPhase: recompute n, p for the current x, s (closed form); duals unchanged
+      RestoNlp& R = static_cast<RestoNlp&>(P);
+      tr = cur;
+      std::vector<double> g0(m);
+      R.O.eval_fg(cur.x.data(), mu, g0.data());
+      for (int r = 0; r < m; ++r) {
+        const double c = g0[r] - cur.s[r];
+        const double a = mu / (2 * R.rho) - 0.5 * c, b = c * mu / (2 * R.rho);
+        const double nv = a + std::sqrt(a * a + b);
+        tr.x[n0 + r] = nv; tr.x[n0 + m + r] = c + nv;
+      }
+      f_t = P.eval_fg(tr.x.data(), mu, g_t.data());
+      return;
+    }
+    ++C.n_resto;
+    OrigNlp& O = static_cast<OrigNlp&>(P);
+    RestoNlp R(O, cur.x.data(), o.resto_rho, o.resto_eta_factor);
+    Options ro = o; ro.theta_max_fact = o.resto_theta_max_fact; ro.constr_mult_init_max = 0.0;
+    Algo A(R, ro, true, this, C);
+    A.log = log;
+    A.iter = iter + 1;
+    const Status rs = A.optimize_resto();
+    C.n_resto_iter += A.iter - (iter + 1);
+    // primal variables of the restoration iterate (also copied back on failure: they are what the caller gets)
+    tr = cur;
+    for (int i = 0; i < n0; ++i) tr.x[i] = A.cur.x[i];
+    tr.s = A.cur.s;
+    f_t = P.eval_fg(tr.x.data(), mu, g_t.data());
+    if (rs != RESTO_SUCCESS) {
+      const double orig_infpr = infpr_of(g_t, tr);
+      cur.x = tr.x; cur.s = tr.s; f = f_t; g = g_t; iter = A.iter;
+      Status out;
+      switch (rs) {
+        case STEP_TOO_SMALL: out = orig_infpr <= 1e2 * o.tol ? RESTORATION_FAILED : INFEASIBLE_PROBLEM_DETECTED; break;
+        case MAXITER_EXCEEDED: out = MAXITER_EXCEEDED; break;
+        case INFEASIBLE_PROBLEM_DETECTED: out = INFEASIBLE_PROBLEM_DETECTED; break;
+        case RESTO_CONVERGED_TO_FEASIBLE: case RESTORATION_FAILED: out = RESTORATION_FAILED; break;
+        case INVALID_NUMBER: out = INVALID_NUMBER; break;
+        default: out = ERROR_IN_STEP_COMPUTATION; break;
+      }
+      throw Exit{out};
+    }
+    // bound multipliers: pretend the whole restoration phase was one primal-dual step
+    Iter dz; resize(dz, n, m);
+    auto bstep = [&](double z, double sl_cur, double sl_tr) { return (mu + z * (sl_cur - sl_tr)) / sl_cur - z; };
+    for (int i = 0; i < n; ++i) {
+      if (hasxL(i)) dz.zL[i] = bstep(cur.zL[i], slxL(cur, i), slxL(tr, i));
+      if (hasxU(i)) dz.zU[i] = bstep(cur.zU[i], slxU(cur, i), slxU(tr, i));
+    }
+    for (int r = 0; r < m; ++r) {
+      if (hasdL(r)) dz.vL[r] = bstep(cur.vL[r], sldL(cur, r), sldL(tr, r));
+      if (hasdU(r)) dz.vU[r] = bstep(cur.vU[r], sldU(cur, r), sldU(tr, r));
+    }
+    const double a_du = ftb_dual(dz);
+    double zmax = 0;
+    for (int i = 0; i < n; ++i) { tr.zL[i] = cur.zL[i] + a_du * dz.zL[i]; tr.zU[i] = cur.zU[i] + a_du * dz.zU[i]; zmax = std::max(zmax, std::max(tr.zL[i], tr.zU[i])); }
+    for (int r = 0; r < m; ++r) { tr.vL[r] = cur.vL[r] + a_du * dz.vL[r]; tr.vU[r] = cur.vU[r] + a_du * dz.vU[r]; zmax = std::max(zmax, std::max(tr.vL[r], tr.vU[r])); }
+    if (zmax > o.bound_mult_reset_threshold) {
+      for (int i = 0; i < n; ++i) { tr.zL[i] = hasxL(i) ? 1.0 : 0.0; tr.zU[i] = hasxU(i) ? 1.0 : 0.0; }
+      for (int r = 0; r < m; ++r) { tr.vL[r] = hasdL(r) ? 1.0 : 0.0; tr.vU[r] = hasdU(r) ? 1.0 : 0.0; }
+    }
+    // constraint multipliers: constr_mult_reset_threshold = 0  =>  no least-squares estimate, y = 0
+    std::fill(tr.y.begin(), tr.y.end(), 0.0);
+    info_alpha_du = a_du;
+    iter = A.iter - 1;
+  }
+  // RestoIterateInitializer
+  void init_resto() {
+    Algo& A = *outer; RestoNlp& R = static_cast<RestoNlp&>(P);
+    resize(cur, n, m); resize(del, n, m); resize(dsoc, n, m); resize(tr, n, m);
+    mu = std::max(A.mu, A.infpr_of(A.g, A.cur)); tau = std::max(o.tau_min, 1 - mu);
+    for (int i = 0; i < n0; ++i) cur.x[i] = A.cur.x[i];
+    cur.s = A.cur.s;
+    for (int r = 0; r < m; ++r) {
+      const double c = A.g[r] - A.cur.s[r];
+      const double a = mu / (2 * R.rho) - 0.5 * c, b = c * mu / (2 * R.rho);
+      const double nv = a + std::sqrt(a * a + b);
+      cur.x[n0 + r] = nv; cur.x[n0 + m + r] = c + nv;
+      cur.zL[n0 + r] = mu / nv; cur.zL[n0 + m + r] = mu / (c + nv);
+    }
+    for (int i = 0; i < n0; ++i) { cur.zL[i] = hasxL(i) ? std::min(R.rho, A.cur.zL[i]) : 0.0; cur.zU[i] = hasxU(i) ? std::min(R.rho, A.cur.zU[i]) : 0.0; }
+    for (int r = 0; r < m; ++r) { cur.vL[r] = hasdL(r) ? std::min(R.rho, A.cur.vL[r]) : 0.0; cur.vU[r] = hasdU(r) ? std::min(R.rho, A.cur.vU[r]) : 0.0; }
+    std::fill(cur.y.begin(), cur.y.end(), 0.0);        // resto.constr_mult_init_max = 0
+    eval_point();
+  }
+  void log_iter(const Err& e) {
+    if (log) log->push_back({mu, (is_resto ? f : f / P.df), e.pr, e.du, dw_cur, info_alpha_pr, info_alpha_du, info_ls, info_tag + (is_resto ? 1000 : 0)});
+  }
+  Status optimize_resto() {
+    try {
+      init_resto();
+      Status st = check_convergence_resto();
+      while (st == CONTINUE) {
+        update_mu();
+        const Err e = error(0.0);
+        const bool ok = compute_direction();
+        line_search(!ok);
+        log_iter(e);
+        accept_trial_point();
+        ++iter;
+        st = check_convergence_resto();
+      }
+      return st;
+    } catch (Exit& e) { return e.st; }
+  }
+};
+
+struct Result { int32_t status; int32_t iters; double f; Counters c; };
+
+// Original problem: scaling, bounds, starting point (DefaultIterateInitializer), main loop, finalisation.
+Result solve_instance(Instance& I, const Options& o, const double* x0, const double* lbx, const double* ubx, const double* lbg,
+                      const double* ubg, double* x_out, double* g_out, double* lamx_out, double* lamg_out, std::vector<IterLog>* log) {
+  Result res{}; Counters C;
+  OrigNlp P(I);
+  const int n = P.n0, m = P.m;
+  Algo A(P, o, false, nullptr, C);
+  A.log = log;
+  Algo::resize(A.cur, n, m); Algo::resize(A.del, n, m); Algo::resize(A.dsoc, n, m); Algo::resize(A.tr, n, m);
+  A.cur.x.assign(x0, x0 + n);
+  // ---- gradient-based scaling at the user's starting point
+  if (o.scaling) {
+    P.eval_derivs(A.cur.x.data(), 0.0, A.grad.data(), A.J0.data());
+    double gmax = 0; for (int i = 0; i < n; ++i) gmax = std::max(gmax, std::fabs(A.grad[i]));
+    const double dfn = gmax > o.max_grad ? std::max(o.scal_min, o.max_grad / gmax) : 1.0;
+    for (int r = 0; r < m; ++r) {
+      double rm = 0; for (int i = 0; i < n; ++i) rm = std::max(rm, std::fabs(A.J0[(size_t)r * n + i]));
+      P.dc[r] = rm > o.max_grad ? std::max(o.scal_min, o.max_grad / rm) : 1.0;
+    }
+    P.df = dfn;
+    if (o.scaling == 2) std::fill(P.dc.begin(), P.dc.end(), 1.0);   // debug: objective scaling only
+    if (o.scaling == 3) P.df = 1.0;                                  // debug: constraint scaling only
+  }
+  // ---- bounds (scaled, relaxed)
+  P.xL.resize(n); P.xU.resize(n); P.dL.resize(m); P.dU.resize(m);
+  auto relax_lo = [&](double b) { return b > -1e19 ? b - o.bound_relax * std::max(1.0, std::fabs(b)) : -INF; };
+  auto relax_hi = [&](double b) { return b < 1e19 ? b + o.bound_relax * std::max(1.0, std::fabs(b)) : INF; };
+  for (int i = 0; i < n; ++i) { P.xL[i] = relax_lo(lbx[i]); P.xU[i] = relax_hi(ubx[i]); }
+  for (int r = 0; r < m; ++r) {
+    P.dL[r] = lbg[r] > -1e19 ? relax_lo(P.dc[r] * lbg[r]) : -INF;
+    P.dU[r] = ubg[r] < 1e19 ? relax_hi(P.dc[r] * ubg[r]) : INF;
+  }
+  auto push = [&](double& v, double lo, double hi) {
+    const bool hl = lo > -INF, hu = hi < INF; const double k1 = o.bound_push, k2 = o.bound_frac;
+    if (hl && hu) {
+      const double pl = std::min(k1 * std::max(1.0, std::fabs(lo)), k2 * (hi - lo));
+      const double pu = std::min(k1 * std::max(1.0, std::fabs(hi)), k2 * (hi - lo));
+      v = std::max(v, lo + pl); v = std::min(v, hi - pu);
+    } else if (hl) v = std::max(v, lo + k1 * std::max(1.0, std::fabs(lo)));
+    else if (hu) v = std::min(v, hi - k1 * std::max(1.0, std::fabs(hi)));
+  };
+  Status status = MAXITER_EXCEEDED;
+  try {
+    // ---- starting point
+    for (int i = 0; i < n; ++i) push(A.cur.x[i], P.xL[i], P.xU[i]);
+    A.mu = o.mu_init; A.tau = std::max(o.tau_min, 1 - A.mu);
+    A.f = P.eval_fg(A.cur.x.data(), A.mu, A.g.data());
+    for (int r = 0; r < m; ++r) { A.cur.s[r] = A.g[r]; push(A.cur.s[r], P.dL[r], P.dU[r]); }
+    for (int i = 0; i < n; ++i) { A.cur.zL[i] = A.hasxL(i) ? 1.0 : 0.0; A.cur.zU[i] = A.hasxU(i) ? 1.0 : 0.0; }
+    for (int r = 0; r < m; ++r) { A.cur.vL[r] = A.hasdL(r) ? 1.0 : 0.0; A.cur.vU[r] = A.hasdU(r) ? 1.0 : 0.0; }
+    P.eval_derivs(A.cur.x.data(), A.mu, A.grad.data(), A.J0.data());
+    {   // least-squares multipliers (LeastSquareMultipliers: W = 0, D_x = D_s = I)
+      std::vector<double> one_n(n, 1.0), one_m(m, 1.0), rx(n), rs(m), zero(m, 0.0);
+      for (int i = 0; i < n; ++i) rx[i] = A.grad[i] - A.cur.zL[i] + A.cur.zU[i];
+      for (int r = 0; r < m; ++r) rs[r] = -A.cur.vL[r] + A.cur.vU[r];
+      bool ok = o.constr_mult_init_max > 0 && A.factor(false, one_n, one_m);
+      if (ok) {
+        Iter t; Algo::resize(t, n, m);
+        A.solve_dir(rx, rs, zero.data(), t);
+        A.cur.y = t.y;
+        double ym = 0; for (int r = 0; r < m; ++r) ym = std::max(ym, std::fabs(A.cur.y[r]));
+        if (!(ym <= o.constr_mult_init_max)) std::fill(A.cur.y.begin(), A.cur.y.end(), 0.0);
+      } else std::fill(A.cur.y.begin(), A.cur.y.end(), 0.0);
+    }
+    // ---- main loop (IpoptAlgorithm::Optimize)
+    Status st = A.check_convergence_orig(lbg, ubg);
+    while (st == CONTINUE) {
+      A.update_mu();
+      const Algo::Err e = A.error(0.0);
+      const bool ok = A.compute_direction();
+      A.line_search(!ok);
+      A.log_iter(e);
+      A.accept_trial_point();
+      ++A.iter;
+      st = A.check_convergence_orig(lbg, ubg);
+    }
+    status = st;
+  } catch (Exit& e) { status = e.st; }
+  // ---- finalize: honour original bounds, unscale
+  for (int i = 0; i < n; ++i) x_out[i] = std::min(std::max(A.cur.x[i], lbx[i]), ubx[i]);
+  std::vector<double> gu(m);
+  const double fu = I.eval_fg(x_out, gu.data());   // unscaled f, g at the returned point
+  if (g_out) std::memcpy(g_out, gu.data(), sizeof(double) * m);
+  if (lamx_out) for (int i = 0; i < n; ++i) lamx_out[i] = (A.cur.zU[i] - A.cur.zL[i]) / P.df;
+  if (lamg_out) for (int r = 0; r < m; ++r) lamg_out[r] = A.cur.y[r] * P.dc[r] / P.df;
+  res.status = status; res.iters = A.iter; res.f = fu; res.c = C;
+  return res;
+}
+
+// option overrides for experiments / tests (not thread safe: set before solving)
+struct Override { char name[48]; double value; };
+std::vector<Override> g_overrides;
+void apply_overrides(Options& o) {
+  for (auto& ov : g_overrides) {
+    const std::string k(ov.name); const double v = ov.value;
+    if (k == "resto") o.resto = (int)v; else if (k == "watchdog_trigger") o.watchdog_trigger = (int)v;
+    else if (k == "max_soft_resto") o.max_soft_resto = (int)v; else if (k == "soft_resto_red") o.soft_resto_red = v;
+    else if (k == "max_filter_resets") o.max_filter_resets = (int)v; else if (k == "resto_explicit") o.resto_explicit = (int)v;
+    else if (k == "max_soc") o.max_soc = (int)v; else if (k == "resto_rho") o.resto_rho = v;
+    else if (k == "obj_max_inc") o.obj_max_inc = v; else if (k == "mu_init") o.mu_init = v;
+    else if (k == "bound_mult_reset_threshold") o.bound_mult_reset_threshold = v;
+  }
+}
+
+}  // namespace
 // ------------------------------------------------------------------------------------------
 // C interface for ctypes (tests / bench only)
 // ------------------------------------------------------------------------------------------
@@ -800,7 +1356,8 @@ int oracle_eval_traj(const oracle_spec* spec, const double* obs, const double* w
 
 // batch solve.  Instance-major arrays: p [B][11], x0 [B][nw], outputs x [B][nw], f [B], g [B][ng], ...
 // bounds shared ([nw], [ng]).  obs: [n_obs][3] shared (obs_per_instance=0) or [B][n_obs][3].
-// stats (optional) [B][4] : n_fact, n_soc_accepted, 0, 0
+// stats (optional) [B][8] : factorisations, SOC steps accepted, restoration calls, restoration iterations,
+//                          watchdog starts, soft-restoration steps, filter resets, slack safeguards
 int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const double* x0, const double* tgt,
                       const double* lbx, const double* ubx, const double* lbg, const double* ubg,
                       const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
@@ -830,16 +1387,20 @@ int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const dou
       Instance I(sp, p + (size_t)b * NPAR, ob);
       if (tgt) I.tgt = tgt + (size_t)b * 2 * sp.N;
       Options o; o.scaling = scaling; if (max_iter > 0) o.max_iter = max_iter; if (tol > 0) o.tol = tol;
-      Ipm ipm(I, o);
+      apply_overrides(o);
       std::vector<double> xo(nw);
-      Result r = ipm.solve(x0 + (size_t)b * nw, lbx, ubx, lbg, ubg, xo.data(),
-                           g ? g + (size_t)b * ng : nullptr, lam_x ? lam_x + (size_t)b * nw : nullptr,
-                           lam_g ? lam_g + (size_t)b * ng : nullptr);
+      Result r = solve_instance(I, o, x0 + (size_t)b * nw, lbx, ubx, lbg, ubg, xo.data(),
+                                g ? g + (size_t)b * ng : nullptr, lam_x ? lam_x + (size_t)b * nw : nullptr,
+                                lam_g ? lam_g + (size_t)b * ng : nullptr, nullptr);
       std::memcpy(x + (size_t)b * nw, xo.data(), sizeof(double) * nw);
       if (f) f[b] = r.f;
       if (status) status[b] = r.status;
       if (iters) iters[b] = r.iters;
-      if (stats) { stats[4 * b] = r.n_fact; stats[4 * b + 1] = r.n_soc_acc; stats[4 * b + 2] = 0; stats[4 * b + 3] = 0; }
+      if (stats) {
+        int32_t* s8 = stats + 8 * (size_t)b;
+        s8[0] = r.c.n_fact; s8[1] = r.c.n_soc_acc; s8[2] = r.c.n_resto; s8[3] = r.c.n_resto_iter;
+        s8[4] = r.c.n_watchdog; s8[5] = r.c.n_soft; s8[6] = r.c.n_filter_reset; s8[7] = r.c.n_slack_adj;
+      }
     }
   };
   if (nthreads == 1) work();
@@ -847,22 +1408,31 @@ int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const dou
   return 0;
 }
 
-// single solve with per-iteration log [max_log][8]: mu, f, inf_pr, inf_du, dw, alpha_pr, alpha_du, ls
+// single solve with per-iteration log [max_log][9]: mu, f, inf_pr, inf_du, dw, alpha_pr, alpha_du, ls, tag (+1000 inside the restoration phase)
 int oracle_solve_log(const oracle_spec* spec, const double* p, const double* x0,
                      const double* lbx, const double* ubx, const double* lbg, const double* ubg,
                      const double* obs, int scaling, double* x, double* f, int32_t* status, int32_t* iters,
                      double* logbuf, int max_log) {
   Spec sp = to_spec(spec); Instance I(sp, p, obs);
-  Options o; o.scaling = scaling; Ipm ipm(I, o);
-  std::vector<IterLog> lg; ipm.log = &lg;
-  Result r = ipm.solve(x0, lbx, ubx, lbg, ubg, x, nullptr, nullptr, nullptr);
+  Options o; o.scaling = scaling; apply_overrides(o);
+  std::vector<IterLog> lg;
+  Result r = solve_instance(I, o, x0, lbx, ubx, lbg, ubg, x, nullptr, nullptr, nullptr, &lg);
   *f = r.f; *status = r.status; *iters = r.iters;
   for (int i = 0; i < (int)lg.size() && i < max_log; ++i) {
-    double* L = logbuf + 8 * i;
+    double* L = logbuf + 9 * i;
     L[0] = lg[i].mu; L[1] = lg[i].f; L[2] = lg[i].inf_pr; L[3] = lg[i].inf_du; L[4] = lg[i].dw;
-    L[5] = lg[i].alpha_pr; L[6] = lg[i].alpha_du; L[7] = lg[i].ls;
+    L[5] = lg[i].alpha_pr; L[6] = lg[i].alpha_du; L[7] = lg[i].ls; L[8] = lg[i].tag;
   }
   return (int)lg.size();
 }
+
+// option overrides for experiments and tests (name as in Options; not thread safe).  oracle_clear_options() removes them.
+int oracle_set_option(const char* name, double value) {
+  Override ov{}; std::strncpy(ov.name, name, sizeof(ov.name) - 1); ov.value = value;
+  for (auto& e : g_overrides) if (std::strcmp(e.name, ov.name) == 0) { e.value = value; return 0; }
+  g_overrides.push_back(ov);
+  return 0;
+}
+int oracle_clear_options(void) { g_overrides.clear(); return 0; }
 
 }  // extern "C"
