@@ -43,10 +43,12 @@ extern "C" {
 enum {
   NMPC_SOLVE_SUCCEEDED = 0,
   NMPC_MAXITER_EXCEEDED = 1,
-  NMPC_RESTORATION_NEEDED = 2,   /* line search failed; IPOPT would enter restoration (not implemented) */
-  NMPC_STEP_TOO_SMALL = 3,
+  NMPC_RESTORATION_FAILED = 2,   /* IPOPT "Restoration_Failed": the restoration phase was called at an (almost) feasible point,
+                                    or converged to a feasible point that the original filter does not accept */
+  NMPC_STEP_TOO_SMALL = 3,       /* "Search_Direction_Becomes_Too_Small" */
   NMPC_INVALID_NUMBER = 4,
-  NMPC_PERTURBATION_FAILED = 5
+  NMPC_ERROR_IN_STEP_COMPUTATION = 5,
+  NMPC_INFEASIBLE_PROBLEM = 6    /* "Infeasible_Problem_Detected": the restoration phase converged to a point of local infeasibility */
 };
 
 /* What the reference scripts hard-code in source.  Replaces the SX dict {'f','x','g','p'} and the
@@ -148,6 +150,11 @@ typedef struct nmpc_stats {
   int64_t factorizations;      /* Riccati factorisations summed over the batch */
   int64_t ls_trials;           /* line-search trial points summed over the batch */
   int64_t soc_accepted;
+  int64_t resto_calls;         /* restoration phases entered */
+  int64_t resto_iters;         /* iterations spent inside restoration phases */
+  int64_t watchdog_starts;
+  int64_t soft_resto_steps;    /* steps accepted by the soft restoration phase's primal-dual error test */
+  int64_t filter_resets;
 } nmpc_stats;
 int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out);   /* synchronises the handle's last stream */
 
@@ -172,7 +179,8 @@ int nmpc_set_weights(nmpc_handle* h, const double* dev_weights);
 int nmpc_set_target_trajectory(nmpc_handle* h, const double* dev_targets);
 
 /* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
- * dev_buf [B][rows][8] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials}; NULL disables. */
+ * dev_buf [B][rows][10] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials, step tag (IPOPT's alpha_primal_char),
+ * 1 inside the restoration phase}; NULL disables. */
 int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);
 
 /* Measurement aid: FP64 FMA peak of `device` in TFLOP/s (register-resident DFMA loop on every SM).

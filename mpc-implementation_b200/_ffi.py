@@ -14,8 +14,10 @@ LIB_PATH = _CSRC / "libnmpc_b200.so"
 
 NMPC_OBS_PER_INSTANCE = 1
 
-STATUS_NAMES = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "Restoration_Needed",
-                3: "Search_Direction_Becomes_Too_Small", 4: "Invalid_Number_Detected", 5: "Perturbation_Failed"}
+# CasADi's stats()['return_status'] strings of the IPOPT plugin
+STATUS_NAMES = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "Restoration_Failed",
+                3: "Search_Direction_Becomes_Too_Small", 4: "Invalid_Number_Detected", 5: "Error_In_Step_Computation",
+                6: "Infeasible_Problem_Detected"}
 
 
 class NmpcSpec(C.Structure):
@@ -28,7 +30,8 @@ class NmpcSpec(C.Structure):
 
 class NmpcStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("factorizations", C.c_int64),
-                ("ls_trials", C.c_int64), ("soc_accepted", C.c_int64)]
+                ("ls_trials", C.c_int64), ("soc_accepted", C.c_int64), ("resto_calls", C.c_int64), ("resto_iters", C.c_int64),
+                ("watchdog_starts", C.c_int64), ("soft_resto_steps", C.c_int64), ("filter_resets", C.c_int64)]
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_eval", "nmpc_step",

@@ -26,12 +26,12 @@ using namespace nmpc;
 // The IPM kernel (nmpc_solve.cuh) is a template on (N, n_obs); its instantiations live in nmpc_inst.cu objects.
 namespace nmpc {
 #define NMPC_DECL_INST(N, O)                      \
-  int ipm_prepare_##N##_##O(int*, size_t*, int*);        \
+  int ipm_prepare_##N##_##O(int*, size_t*, int*, int*);  \
   int ipm_ricmap_##N##_##O(unsigned*, cudaStream_t);     \
   int ipm_launch_##N##_##O(const SolveArgs&, int, size_t, cudaStream_t);
 NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3)
 }  // namespace nmpc
-struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*); int (*ricmap)(unsigned*, cudaStream_t); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
+struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*, int*); int (*ricmap)(unsigned*, cudaStream_t); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
 #define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_ricmap_##N##_##O, nmpc::ipm_launch_##N##_##O}
 static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3)};
 
@@ -211,13 +211,13 @@ struct nmpc_handle {
   nmpc_spec spec; int device; int sm_count;
   Prob pr; Opt opt;
   const IpmInst* inst; size_t smem_bytes; int blocks_per_sm, max_blocks, warps_per_block;
-  double* d_ric; int ric_stride; unsigned* d_ricmap;
+  double* d_ric; int ric_stride; unsigned* d_ricmap; double* d_cold; int cold_stride;
   // per-call bookkeeping, double-buffered by call parity: the launch of call n resets / produces the buffers of call n+1
   int32_t *d_order[2], *d_keep_iters; int order_cap, prev_B, auto_order, parity, have_order; const int32_t* order_next;
   const double *weights, *tgt;
   double *fuse_p, *fuse_u, *fuse_fov, *fuse_err; const double* fuse_vw;   // set for the duration of nmpc_solve_and_step
   int* d_counter;                  // [4]: queue counter x2, done counter x2
-  unsigned long long* d_stats;     // [2][3]
+  unsigned long long* d_stats;     // [2][NSTAT]
   unsigned long long* stats_last;  // the half written by the last call
   // staging for nmpc_solve_host
   double *d_p, *d_x0, *d_lbx, *d_ubx, *d_lbg, *d_ubg, *d_obs, *d_x, *d_f, *d_g, *d_lamx, *d_lamg;
@@ -265,7 +265,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     return fail("nmpc_create: no kernel instantiation for this (N, n_obs); built:" + have + " -- add the pair to csrc/Makefile INSTS and the table in nmpc_b200.cu");
   }
   {
-    const int rc = h->inst->prepare(&h->blocks_per_sm, &h->smem_bytes, &h->warps_per_block);
+    const int rc = h->inst->prepare(&h->blocks_per_sm, &h->smem_bytes, &h->warps_per_block, &h->cold_stride);
     if (rc != 0) { delete h; return fail(std::string("nmpc_create: kernel setup failed: ") + cudaGetErrorString((cudaError_t)rc)); }
   }
   if (h->blocks_per_sm < 1) { delete h; return fail("nmpc_create: kernel does not fit on an SM"); }
@@ -281,6 +281,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
   h->ric_stride = RIC_N * h->pr.N;
   CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
+  CK(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->cold_stride * h->max_blocks * h->warps_per_block));   // rare paths: restoration, watchdog
   CK(cudaMalloc(&h->d_ricmap, sizeof(unsigned) * 32 * 16));
   {
     const int rc = h->inst->ricmap(h->d_ricmap, 0);
@@ -289,8 +290,8 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   }
   CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));
   CK(cudaMemset(h->d_counter, 0, 4 * sizeof(int)));
-  CK(cudaMalloc(&h->d_stats, 6 * sizeof(unsigned long long)));
-  CK(cudaMemset(h->d_stats, 0, 6 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&h->d_stats, 2 * NSTAT * sizeof(unsigned long long)));
+  CK(cudaMemset(h->d_stats, 0, 2 * NSTAT * sizeof(unsigned long long)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   const int mb = spec->max_batch > 0 ? spec->max_batch : 0;
   if (mb > 0) {
@@ -312,7 +313,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
 int nmpc_destroy(nmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->d_ric, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
+  void* ptrs[] = {h->d_ric, h->d_cold, h->d_counter, h->d_stats, h->d_p, h->d_x0, h->d_lbx, h->d_ubx, h->d_lbg, h->d_ubg, h->d_obs,
                   h->d_x, h->d_f, h->d_g, h->d_lamx, h->d_lamg, h->d_status, h->d_iters, h->d_order[0], h->d_order[1], h->d_keep_iters, h->d_ricmap};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -339,9 +340,10 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   const int par = h->parity; h->parity ^= 1;
   A.counter = h->d_counter + par; A.counter_next = h->d_counter + (par ^ 1);
   A.done = h->d_counter + 2 + par; A.done_next = h->d_counter + 2 + (par ^ 1);
-  A.stats = h->d_stats + 3 * par; A.stats_next = h->d_stats + 3 * (par ^ 1);
-  h->stats_last = h->d_stats + 3 * par;
+  A.stats = h->d_stats + NSTAT * par; A.stats_next = h->d_stats + NSTAT * (par ^ 1);
+  h->stats_last = h->d_stats + NSTAT * par;
   A.ric = h->d_ric; A.ric_stride = h->ric_stride; A.ricmap = h->d_ricmap;
+  A.cold = h->d_cold; A.cold_stride = h->cold_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
   if (B > h->order_cap) {     // (re)allocate the scheduling buffers; the previous counts are dropped
     CK(cudaStreamSynchronize(s));
@@ -516,9 +518,11 @@ int nmpc_get_stats(nmpc_handle* h, nmpc_stats* out) {
   if (!h || !out) return fail("nmpc_get_stats: null argument");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->last_stream));
-  unsigned long long st[3];
+  unsigned long long st[NSTAT];
   CK(cudaMemcpy(st, h->stats_last ? h->stats_last : h->d_stats, sizeof st, cudaMemcpyDeviceToHost));
   out->kernel_launches = h->launches; out->factorizations = (int64_t)st[0]; out->ls_trials = (int64_t)st[1]; out->soc_accepted = (int64_t)st[2];
+  out->resto_calls = (int64_t)st[3]; out->resto_iters = (int64_t)st[4]; out->watchdog_starts = (int64_t)st[5];
+  out->soft_resto_steps = (int64_t)st[6]; out->filter_resets = (int64_t)st[7];
   return 0;
 }
 

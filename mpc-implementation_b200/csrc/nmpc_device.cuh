@@ -55,7 +55,13 @@ constexpr int STG_N = 356;    // Riccati staging area (nmpc_riccati.cuh)
 
 // scalar results returned by the phases through shared memory
 enum Res { R_F = 0, R_DU, R_PR, R_SUMY, R_SUMZ, R_VIOL, R_PMAX, R_PMIN, R_APR, R_ADU, R_GBD, R_THETA, R_TINY,
-           R_FT, R_THT, R_LBT, R_DTT, R_YMAX, R_N };
+           R_FT, R_THT, R_LBT, R_DTT, R_YMAX,
+           R_DU1, R_CO1,          // 1-norms of the dual infeasibility and of (slack * multiplier - mu): soft restoration test
+           R_OTH, R_OINF,         // restoration mode: 1-norm / max-norm of the ORIGINAL problem's residual g - s
+           R_DYMAX,               // max |dy| of the step (tiny-step logic)
+           R_NFILT,               // filter length after an augmentation (written by lane 0)
+           R_N };
+static_assert(R_N <= 24, "RES region is 24 doubles");
 
 __host__ __device__ inline int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 // state index of the five linear ("box") rows [z, theta, X5, X6, X7]   NMPC_TT.py:236-240
@@ -77,6 +83,13 @@ static __device__ __noinline__ double n_log(double x) { return log(x); }
 static __device__ __noinline__ double n_pow(double x, double y) { return pow(x, y); }
 static __device__ __noinline__ double2 n_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
+// IPOPT's CalculateSafeSlack: a slack that rounding has pushed to (or below) zero is replaced by a tiny positive value
+// (slack_move = eps^(3/4)).  z = multiplier of that bound at the current iterate, bnd = the bound itself.
+__device__ __forceinline__ double safe_slack(double sl, double z, double bnd, double mu) {
+  const double s_min = 2.220446049250313e-16 * fmin(1.0, mu);
+  if (sl < s_min) sl = fmin(fmax(mu / z, s_min), fmax(sl, 0.0) + 1.8189894035458565e-12 * fmax(1.0, fabs(bnd)));
+  return sl;
+}
 
 // ---- warp collectives ---------------------------------------------------------------------------
 static __device__ __noinline__ double warp_sum(double v) {
@@ -162,6 +175,16 @@ struct Lay {
   static constexpr int PAR0 = RES0 + 24;
   static constexpr int TOTAL = even_up(PAR0 + 14);   // p (11), w1, w2 of this instance
   // warps (= concurrent instances) per block: as many slices as fit in the 227 KB a block may use, at most NMPC_WPB_MAX
+  // ---- cold per-warp scratch in global memory (touched only by the watchdog, the soft restoration phase and the
+  //      restoration phase): restoration row arrays, reference controls, the restoration problem's own filter, and three
+  //      slots that hold a saved iterate + step
+  static constexpr int RSZ = R * S;
+  static constexpr int CG_ROWS = 0;                     // 8 arrays [R][S]: n, p, z_n, z_p, dn, dp, dn_soc, dp_soc
+  static constexpr int CG_UR = 8 * RSZ;                 // [6][S] reference controls x_R of the restoration problem
+  static constexpr int CG_FILT = CG_UR + 6 * S;         // [FILT_CAP][2]
+  static constexpr int CG_SLOT = CG_FILT + 2 * FILT_CAP;
+  static constexpr int SLOT_N = 32 * S + 10 * RSZ;      // U ZL ZU (18 S) | DX DU (14 S) | S Y VL VU (4 RS) | IL IU (2 RS) | n p z_n z_p (4 RS)
+  static constexpr int COLD_TOTAL = even_up(CG_SLOT + 3 * SLOT_N);
   static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);
   static constexpr int WPB = WPB_FIT < 1 ? 1 : (WPB_FIT > NMPC_WPB_MAX ? NMPC_WPB_MAX : WPB_FIT);
 };

@@ -12,10 +12,11 @@
 
 namespace nmpc {
 
-int NMPC_CAT(ipm_prepare, INST_N, INST_NOBS)(int* blocks_per_sm, size_t* smem_bytes, int* warps_per_block) {
+int NMPC_CAT(ipm_prepare, INST_N, INST_NOBS)(int* blocks_per_sm, size_t* smem_bytes, int* warps_per_block, int* cold_doubles) {
   using L = Lay<INST_N, INST_NOBS>;
   const size_t bytes = (size_t)L::TOTAL * sizeof(double) * L::WPB;
   *warps_per_block = L::WPB;
+  *cold_doubles = L::COLD_TOTAL;
   cudaError_t e = cudaFuncSetAttribute(nmpc_ipm_kernel<INST_N, INST_NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, nmpc_ipm_kernel<INST_N, INST_NOBS>, 32 * L::WPB, bytes);

@@ -3,8 +3,10 @@
 // Replaces  sol = solver(x0,lbx,ubx,lbg,ubg,p)  (Python/NMPC_TT.py:358-365; CasADi -> IPOPT -> MUMPS) for the
 // reference's UAV target-tracking NLP.  Algorithm = IPOPT's (Waechter & Biegler 2006) with the scripts'
 // options (NMPC_TT.py:257-265): slack form g(w) - s = 0, relaxed bounds, gradient-based scaling,
-// monotone barrier, fraction-to-boundary, inertia correction, filter line search + second-order
-// correction, scaled optimality-error termination.  The whole iteration loop runs inside the kernel.
+// monotone barrier, fraction-to-boundary, inertia correction, filter line search with second-order
+// correction, watchdog, soft restoration phase and the restoration phase proper (min ||c||_1 with a proximity
+// term, solved by the same algorithm -- `RS = true` instantiations of the phases), scaled optimality-error
+// termination.  The whole iteration loop runs inside the kernel.
 //
 // Structure: the iterate lives in the warp's slice of shared memory at compile-time offsets (Lay<N, NOBS>); every
 // phase is a __noinline__ function template that loads its operands, works in registers and stores back, so each
@@ -12,6 +14,7 @@
 // holds Lay::WPB warps (8 at N = 15, n_obs = 3) that start every IPM iteration together (align_warps) so that they
 // share instruction-cache lines.  One launch is one whole closed-loop step when asked (nmpc_solve_and_step: the shift
 // runs in ph_output) and also prepares the next call on the handle (queue / counters, longest-first fetch order).
+// Rare events (watchdog, soft restoration, restoration) keep their extra state in a per-warp global scratch (`cold`).
 #pragma once
 #include "nmpc_device.cuh"
 #include "nmpc_riccati.cuh"
@@ -30,7 +33,14 @@ struct Opt {
   double gamma_theta = 1e-5, gamma_phi = 1e-8, eta_phi = 1e-8, s_theta = 1.1, s_phi = 2.3, delta = 1.0;
   double alpha_min_frac = 0.05, alpha_red = 0.5; int max_soc = 4; double kappa_soc = 0.99;
   double theta_max_fact = 1e4, theta_min_fact = 1e-4;
-  double tiny_step_tol = 10.0 * 2.220446049250313e-16;
+  double tiny_step_tol = 10.0 * 2.220446049250313e-16, tiny_step_y_tol = 1e-2;
+  double obj_max_inc = 5.0; int max_filter_resets = 5, filter_reset_trigger = 5;
+  int watchdog_trigger = 10, watchdog_trial_max = 3;
+  int max_soft_resto = 10; double soft_resto_red = 1.0 - 1e-4;
+  int resto = 1;                       // 0: a failed line search ends the solve with NMPC_RESTORATION_FAILED (round-1 behaviour)
+  double resto_rho = 1000.0, resto_eta_factor = 1.0, kappa_resto = 0.9;
+  double bound_mult_reset_threshold = 1e3;
+  double resto_theta_max_fact = 1e8;
 };
 
 struct SolveArgs {
@@ -54,12 +64,16 @@ struct SolveArgs {
   int *counter_next, *done, *done_next;
   unsigned long long* stats_next;
   int32_t* order_out;                // may be NULL (no automatic ordering)
-  unsigned long long* stats;         // [3]: factorizations, ls trials, soc accepted
+  unsigned long long* stats;         // [8]: factorizations, ls trials, soc accepted, restoration calls, restoration iterations,
+                                     //      watchdog starts, soft restoration steps, filter resets
   double* ric; int ric_stride;       // L2-resident Riccati scratch, one slice per resident warp
+  double* cold; int cold_stride;     // per-warp scratch of the rare paths (Lay::COLD_TOTAL)
   const unsigned* ricmap;            // per-lane ownership maps of the factorisation (nmpc_riccati.cuh: ric_map_build)
-  double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][8] (tests only)
+  double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][10] (tests only)
   int align_group;                   // warps that start each IPM iteration together (0 = no alignment, else divides WPB)
 };
+constexpr int NSTAT = 8;
+constexpr int DBG_COLS = 10;
 
 constexpr double EPSM = 2.220446049250313e-16;
 __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * EPSM * fabs(bas); }
@@ -121,6 +135,10 @@ __device__ __forceinline__ int align_warps(int g, int working) {
 #define SOC_CT (2 * L::R)
 #define SOC_DUS (3 * L::R)
 #define SOC_Q2 (3 * L::R + 6)
+// restoration row arrays in the cold scratch: (arr * R + r) * S + lane
+#define RG(arr, r) cold[((arr) * L::R + (r)) * L::S + lane]
+#define UREF(i) cold[L::CG_UR + (i) * L::S + lane]
+enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DN2, G_DP2 };
 
 // T-scaled non-zeros of the dynamics Jacobian A_k - I of this lane's stage
 struct Dyn { double e03, e13, e23, e04, e14; };
@@ -172,6 +190,26 @@ __device__ __forceinline__ double2 stage_target(const SolveArgs& A, int lane) {
   if (!A.tgt || lane >= L::N) return make_double2(PAR(8), PAR(9));
   const double* t = A.tgt + ((size_t)PAR(NPAR + 2) * L::N + lane) * 2;
   return make_double2(__ldg(t), __ldg(t + 1));
+}
+
+// Row quantities of the restoration problem's condensed Newton system (AugRestoSystemSolver).  With the slack s and the
+// elastic variables n, p of row  d(x) + n - p - s = 0  eliminated,
+//     dy = Om (G dx + chat),   Om = 1 / (1/D + 1/Dn + 1/Dp),   chat = c + rs/D + rp/Dp - rn/Dn,
+//     ds = (dy - rs)/D,   dn = -(dy + rn)/Dn,   dp = (dy - rp)/Dp.
+struct RestoRow { double D, Dn, Dp, Om, rs, rn, rp, n, p, zn, zp; };
+template <class L>
+__device__ __forceinline__ RestoRow resto_row(const SolveArgs& A, const double* cold, int lane, int r, double sig_s, double beta, double y,
+                                              double mu, double dw) {
+  RestoRow q;
+  q.zn = RG(G_ZN, r); q.zp = RG(G_ZP, r);
+  q.n = safe_slack(RG(G_N, r), q.zn, 0.0, mu); q.p = safe_slack(RG(G_P, r), q.zp, 0.0, mu);
+  const double in_ = rcp(q.n), ip_ = rcp(q.p), kdm = A.o.kappa_d * mu;
+  q.D = sig_s + dw; q.Dn = q.zn * in_ + dw; q.Dp = q.zp * ip_ + dw;
+  q.rs = mu * beta - y;
+  q.rn = A.o.resto_rho + y - mu * in_ + kdm;
+  q.rp = A.o.resto_rho - y - mu * ip_ + kdm;
+  q.Om = rcp(rcp(q.D) + rcp(q.Dn) + rcp(q.Dp));
+  return q;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -301,8 +339,11 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
 // ---------------------------------------------------------------------------------------------------
 // derivatives at the current point: stage Hessian blocks / gradients of the LQ sub-problem into LQ, optimality
 // error ingredients into RES.  ls = least-squares multiplier system (W = 0, Sigma = I, rhs = gradient of L).
-template <class L>
-__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df) {
+// RS (restoration problem): no tracking cost; the objective rho*sum(n+p) + eta/2 ||D_R (u - u_R)||^2 adds eta*D_R^2
+// to the control diagonal and its gradient to the control right-hand side; rows enter with the weight Om(dw) instead
+// of Sigma_s + dw, so this phase is re-run for every inertia-correction value dw.
+template <class L, bool RS>
+__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df, double mu, double dw, double* cold) {
   const Prob& pr = A.pr; constexpr int N = L::N; const double T = pr.T;
   const bool act = lane <= N, hasu = lane < N;
   double u[6];
@@ -316,18 +357,22 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
 #pragma unroll
   for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
   double l = 0.0;
-  if (hasu) l = stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y, gl, Hl);
-  if (lane == 0) {   // stage 0 is constant in w
+  if (!RS) {
+    if (hasu) l = stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y, gl, Hl);
+    if (lane == 0) {   // stage 0 is constant in w
 #pragma unroll
-    for (int v = 0; v < 6; ++v) gl[v] = 0.0;
+      for (int v = 0; v < 6; ++v) gl[v] = 0.0;
 #pragma unroll
-    for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
+      for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
+    }
   }
-  const double fsum = df * warp_sum(l);
+  const double fsum = RS ? 0.0 : df * warp_sum(l);
   double a[8], qa[8], qb[8], qd[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = 0.0; qa[i] = 0.0; qb[i] = 0.0; qd[i] = 0.0; }
   double du_l = 0.0, pr_l = 0.0, sumy = 0.0, sumz = 0.0, viol = 0.0, pmax = 0.0, pmin = CUDART_INF;
+  double du1 = 0.0, pr1 = 0.0, co1 = 0.0, oth = 0.0, oinf = 0.0;
+  auto compl_ = [&](double pz) { pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); co1 += fabs(pz - mu); };
   if (act) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) LV(LV_X + i) = st.X[i];
@@ -343,32 +388,49 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
       const double s = RW(A_S, r), y = RW(A_Y, r), vl = RW(A_VL, r), vu = RW(A_VU, r), il = RW(A_IL, r), iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       RW(A_G, r) = g;
-      const double c = g - s;
+      double c = g - s;
       const double sig = ls ? 1.0 : vl * il + vu * iu;
       double beta = iu - il;                              // barrier gradient per unit mu (with damping)
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
-      const double ya = ls ? (vu - vl) : sig * c;         // delta_w- and mu-free part of y-hat
-      const double w = dc * dc * sig;
+      double ya, w, yad;                                  // ya: delta_w- and mu-free part of y-hat; yad: seed of the adjoint
+      if (RS) {
+        oth += fabs(c); oinf = fmax(oinf, fabs(c));
+        const RestoRow q = resto_row<L>(A, cold, lane, r, sig, beta, y, mu, dw);
+        c += RG(G_N, r) - RG(G_P, r);
+        const double chat = c + q.rs * rcp(q.D) + q.rp * rcp(q.Dp) - q.rn * rcp(q.Dn);
+        ya = y + q.Om * chat; w = dc * dc * q.Om; yad = y;
+        // n / p parts of the optimality error
+        const double gn = A.o.resto_rho + y - q.zn, gp = A.o.resto_rho - y - q.zp;
+        du_l = fmax(du_l, fmax(fabs(gn), fabs(gp))); du1 += fabs(gn) + fabs(gp); sumz += q.zn + q.zp;
+        compl_(q.n * q.zn); compl_(q.p * q.zp);
+      } else {
+        ya = ls ? (vu - vl) : sig * c; w = dc * dc * sig; yad = y;
+      }
       if (box) {
-        a[si] += dc * y; qa[si] += dc * ya; qb[si] += dc * beta; qd[si] += dc * c;
+        a[si] += dc * yad; qa[si] += dc * ya;
+        if (!RS) { qb[si] += dc * beta; qd[si] += dc * c; }
         if (si == 3) q22 += w; else q66[tri(si < 3 ? si : si - 2, si < 3 ? si : si - 2)] += w;
-        LQ(LQ_DG + r) = dc * dc;
+        LQ(LQ_DG + r) = RS ? 0.0 : dc * dc;
       } else {
         const double cur = ls ? 0.0 : -y * dc * iD;        // y * d2h,  d2h = -(I - n n^T)/D
         q66[0] += w * nx * nx + cur * (1.0 - nx * nx);
         q66[1] += w * nx * ny - cur * nx * ny;
         q66[2] += w * ny * ny + cur * (1.0 - ny * ny);
-        nn[0] += dc * dc * nx * nx; nn[1] += dc * dc * nx * ny; nn[2] += dc * dc * ny * ny;
-        const double gy = -dc * y, ga = -dc * ya, gb = -dc * beta, gd = -dc * c;
+        if (!RS) { nn[0] += dc * dc * nx * nx; nn[1] += dc * dc * nx * ny; nn[2] += dc * dc * ny * ny; }
+        const double gy = -dc * yad, ga = -dc * ya;
         a[0] += gy * nx; a[1] += gy * ny; qa[0] += ga * nx; qa[1] += ga * ny;
-        qb[0] += gb * nx; qb[1] += gb * ny; qd[0] += gd * nx; qd[1] += gd * ny;
+        if (!RS) {
+          const double gb = -dc * beta, gd = -dc * c;
+          qb[0] += gb * nx; qb[1] += gb * ny; qd[0] += gd * nx; qd[1] += gd * ny;
+        }
       }
       // optimality-error ingredients
-      du_l = fmax(du_l, fabs(-y - vl + vu)); pr_l = fmax(pr_l, fabs(c)); sumy += fabs(y); sumz += vl + vu;
+      const double gs = fabs(-y - vl + vu);
+      du_l = fmax(du_l, gs); du1 += gs; pr_l = fmax(pr_l, fabs(c)); pr1 += fabs(c); sumy += fabs(y); sumz += vl + vu;
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      if (b.hl) { const double pz = (s - b.lo) * vl; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
-      if (b.hu) { const double pz = (b.hi - s) * vu; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
+      if (b.hl) compl_(safe_slack(s - b.lo, vl, b.lo, mu) * vl);
+      if (b.hu) compl_(safe_slack(b.hi - s, vu, b.hi, mu) * vu);
       const double lo_o = __ldg(A.lbg + lane * L::R + r), hi_o = __ldg(A.ubg + lane * L::R + r);
       if (lo_o > -1e19) viol = fmax(viol, lo_o - gu);
       if (hi_o < 1e19) viol = fmax(viol, gu - hi_o);
@@ -405,32 +467,41 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
     glx[0] = T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]);
 #pragma unroll
     for (int r = 1; r < 6; ++r) glx[r] = T * lamn[r + 2];
+    const double eta = RS ? A.o.resto_eta_factor * sqrt(mu) : 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       double sig = 1.0, rb = 0.0;
       if (hasu) {
         const Bnd b = ctl_bounds(A, lane, i);
         const double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
-        const double sl = u[i] - b.lo, su = b.hi - u[i];
+        const double sl = safe_slack(u[i] - b.lo, zl, b.lo, mu), su = safe_slack(b.hi - u[i], zu, b.hi, mu);
+        double gR = 0.0;
+        if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))); gR = eta * d * d * (u[i] - ur); glx[i] += gR; }
         if (ls) rb = zu - zl;
         else {
           const double il = b.hl ? rcp(sl) : 0.0, iu = b.hu ? rcp(su) : 0.0;
           sig = zl * il + zu * iu; rb = iu - il;
           if (b.hl && !b.hu) rb += A.o.kappa_d;
           if (b.hu && !b.hl) rb -= A.o.kappa_d;
+          if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))); sig += eta * d * d; rb += gR / mu; }
         }
-        du_l = fmax(du_l, fabs(glx[i] - zl + zu)); sumz += zl + zu;
-        if (b.hl) { const double pz = sl * zl; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
-        if (b.hu) { const double pz = su * zu; pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); }
+        const double gx = fabs(glx[i] - zl + zu);
+        du_l = fmax(du_l, gx); du1 += gx; sumz += zl + zu;
+        if (b.hl) compl_(sl * zl);
+        if (b.hu) compl_(su * zu);
       }
       LQ(LQ_RD + i) = sig; LQ(LQ_RB + i) = rb;
     }
   }
   du_l = warp_max(du_l); pr_l = warp_max(pr_l); sumy = warp_sum(sumy); sumz = warp_sum(sumz);
   viol = warp_max(viol); pmax = warp_max(pmax); pmin = warp_min(pmin);
+  du1 = warp_sum(du1); pr1 = warp_sum(pr1); co1 = warp_sum(co1);
+  if (RS) { oth = warp_sum(oth); oinf = warp_max(oinf); }
   if (lane == 0) {
     RES(R_F) = fsum; RES(R_DU) = du_l; RES(R_PR) = pr_l; RES(R_SUMY) = sumy; RES(R_SUMZ) = sumz;
     RES(R_VIOL) = viol; RES(R_PMAX) = pmax; RES(R_PMIN) = pmin;
+    RES(R_DU1) = du1; RES(R_THETA) = pr1; RES(R_CO1) = co1;
+    if (RS) { RES(R_OTH) = oth; RES(R_OINF) = oinf; }
   }
   __syncwarp();
 }
@@ -462,12 +533,12 @@ __device__ __noinline__ void ph_lsy(const SolveArgs& A, int lane, bool ok) {
   __syncwarp();
 }
 
-// step in the slacks, fraction-to-the-boundary limits, directional derivative of the barrier function.
-// soc: second-order-correction direction (residual CSOC, controls DUS, output DS2).
-template <class L>
-__device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, double tau, bool soc) {
+// step in the slacks (and in n, p for RS), fraction-to-the-boundary limits, directional derivative of the barrier
+// function, max |dy|.  soc: second-order-correction direction (residual CSOC, controls DUS, output DS2).
+template <class L, bool RS>
+__device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, double tau, bool soc, double dw, double* cold) {
   const bool act = lane <= L::N, hasu = lane < L::N;
-  double tp = 0.0, dnum = 0.0, dden = 1.0, gbd = 0.0, theta = 0.0; bool nottiny = false;
+  double tp = 0.0, dnum = 0.0, dden = 1.0, gbd = 0.0, theta = 0.0, dymax = 0.0; bool nottiny = false;
   const double tt = A.o.tiny_step_tol, kd = A.o.kappa_d;
   auto dual_frac = [&](double z, double dz) {   // track max of -dz/z over dz < 0 as a fraction
     if (dz < 0.0 && -dz * dden > dnum * z) { dnum = -dz; dden = z; }
@@ -479,26 +550,47 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), vl = RW(A_VL, r), vu = RW(A_VU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      const double c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) - s;
+      double beta = iu - il;
+      if (hl && !hu) beta += kd;
+      if (hu && !hl) beta -= kd;
       const double gd = box ? dc * dx[si] : -dc * (nx * dx[0] + ny * dx[1]);
-      const double ds = gd + c;
+      double c, ds;
+      if (RS) {
+        const double y = RW(A_Y, r);
+        const RestoRow q = resto_row<L>(A, cold, lane, r, vl * il + vu * iu, beta, y, mu, dw);
+        c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) + RG(G_N, r) - RG(G_P, r) - s;
+        const double chat = c + q.rs * rcp(q.D) + q.rp * rcp(q.Dp) - q.rn * rcp(q.Dn);
+        const double dyv = q.Om * (gd + chat);
+        const double dn = -(dyv + q.rn) * rcp(q.Dn), dp = (dyv - q.rp) * rcp(q.Dp);
+        ds = gd + dn - dp + c;
+        if (soc) { RG(G_DN2, r) = dn; RG(G_DP2, r) = dp; } else { RG(G_DN, r) = dn; RG(G_DP, r) = dp; }
+        const double in_ = rcp(q.n), ip_ = rcp(q.p);
+        tp = fmax(tp, fmax(-dn * in_, -dp * ip_));
+        dual_frac(q.zn, (mu - q.zn * dn) * in_ - q.zn);
+        dual_frac(q.zp, (mu - q.zp * dp) * ip_ - q.zp);
+        gbd += (A.o.resto_rho - mu * in_ + kd * mu) * dn + (A.o.resto_rho - mu * ip_ + kd * mu) * dp;
+        nottiny = nottiny || (fabs(dn) > tt * (1.0 + fabs(q.n))) || (fabs(dp) > tt * (1.0 + fabs(q.p)));
+        dymax = fmax(dymax, fabs(q.D * ds + q.rs));
+      } else {
+        c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) - s;
+        ds = gd + c;
+        dymax = fmax(dymax, fabs((vl * il + vu * iu + dw) * ds + (mu * beta - RW(A_Y, r))));
+      }
       if (soc) SOC(SOC_DS2 + r) = ds; else RW(A_DS, r) = ds;
       tp = fmax(tp, fmax(-ds * il, ds * iu));
       if (hl) dual_frac(vl, (mu - vl * ds) * il - vl);
       if (hu) dual_frac(vu, (mu + vu * ds) * iu - vu);
-      double beta = iu - il;
-      if (hl && !hu) beta += kd;
-      if (hu && !hl) beta -= kd;
       gbd += mu * beta * ds; theta += fabs(c);
       nottiny = nottiny || (fabs(ds) > tt * (1.0 + fabs(s)));
     };
     FOR_ROWS(X, body);
     if (hasu) {
+      const double eta = RS ? A.o.resto_eta_factor * sqrt(mu) : 0.0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const Bnd b = ctl_bounds(A, lane, i);
         const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
-        const double il = b.hl ? rcp(u - b.lo) : 0.0, iu = b.hu ? rcp(b.hi - u) : 0.0;
+        const double il = b.hl ? rcp(safe_slack(u - b.lo, zl, b.lo, mu)) : 0.0, iu = b.hu ? rcp(safe_slack(b.hi - u, zu, b.hi, mu)) : 0.0;
         tp = fmax(tp, fmax(-du * il, du * iu));
         if (b.hl) dual_frac(zl, (mu - zl * du) * il - zl);
         if (b.hu) dual_frac(zu, (mu + zu * du) * iu - zu);
@@ -506,30 +598,33 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
         if (b.hl && !b.hu) beta += kd;
         if (b.hu && !b.hl) beta -= kd;
         gbd += mu * beta * du;
+        if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))); gbd += eta * d * d * (u - ur) * du; }
         nottiny = nottiny || (fabs(du) > tt * (1.0 + fabs(u)));
       }
+      if (!RS) {
 #pragma unroll
-      for (int v = 0; v < 6; ++v) gbd += LV(LV_GL + v) * dx[cost_state(v)];
+        for (int v = 0; v < 6; ++v) gbd += LV(LV_GL + v) * dx[cost_state(v)];
+      }
     }
   }
   tp = warp_max(tp);
   const double td = warp_max(dnum / dden);
-  gbd = warp_sum(gbd); theta = warp_sum(theta);
+  gbd = warp_sum(gbd); theta = warp_sum(theta); dymax = warp_max(dymax);
   const bool any_nt = __any_sync(FULL, nottiny);
   if (lane == 0) {
     RES(R_APR) = tp > tau ? tau / tp : 1.0;             // alpha = min(1, tau / max ratio)
     RES(R_ADU) = td > tau ? tau / td : 1.0;
-    if (!soc) { RES(R_GBD) = gbd; RES(R_THETA) = theta; RES(R_TINY) = any_nt ? 0.0 : 1.0; }
+    if (!soc) { RES(R_GBD) = gbd; RES(R_THETA) = theta; RES(R_TINY) = any_nt ? 0.0 : 1.0; RES(R_DYMAX) = dymax; }
   }
   __syncwarp();
 }
 
-// trial point u + alpha*du, s + alpha*ds: objective, constraint violation, barrier pieces; residual into CT
-template <class L>
-__device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha, bool soc, double df) {
+// trial point u + alpha*du, s + alpha*ds (n, p for RS): objective, constraint violation, barrier pieces; residual into CT
+template <class L, bool RS>
+__device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha, bool soc, double df, double mu, double* cold) {
   const Prob& pr = A.pr;
   const bool act = lane <= L::N, hasu = lane < L::N;
-  double ut[6], lb = 0.0, dt = 0.0;
+  double ut[6], lb = 0.0, dt = 0.0, fr = 0.0;
   double prod = 1.0; int cnt = 0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -537,26 +632,36 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     if (hasu) {
       ut[i] = fma(alpha, soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), LV(LV_U + i));   // same expression as ph_accept
       const Bnd b = ctl_bounds(A, lane, i);
-      if (b.hl) prod *= ut[i] - b.lo;
-      if (b.hu) prod *= b.hi - ut[i];
+      if (b.hl) prod *= safe_slack(ut[i] - b.lo, LV(LV_ZL + i), b.lo, mu);
+      if (b.hu) prod *= safe_slack(b.hi - ut[i], LV(LV_ZU + i), b.hi, mu);
       if (b.hl && !b.hu) dt += ut[i] - b.lo;
       if (b.hu && !b.hl) dt += b.hi - ut[i];
       if (i == 2 || i == 5) { lb += n_log(prod); prod = 1.0; }
+      if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))), e = d * (ut[i] - ur); fr += e * e; }
     }
   }
   Stage st; rollout(pr, &PAR(0), ut, lane, st);
-  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y) : 0.0;
+  double l = 0.0;
+  if (!RS) l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y) : 0.0;
+  else l = 0.5 * A.o.resto_eta_factor * sqrt(mu) * fr;
   double th = 0.0;
   if (act) {
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r);
       const double g = __dmul_rn(dc, gu);
       const double sv = fma(alpha, soc ? SOC(SOC_DS2 + r) : RW(A_DS, r), RW(A_S, r));
-      const double ct = g - sv;
+      double ct = g - sv;
+      if (RS) {
+        const double nt = fma(alpha, soc ? RG(G_DN2, r) : RG(G_DN, r), RG(G_N, r));
+        const double pt = fma(alpha, soc ? RG(G_DP2, r) : RG(G_DP, r), RG(G_P, r));
+        ct += nt - pt;
+        const double ns = safe_slack(nt, RG(G_ZN, r), 0.0, mu), ps = safe_slack(pt, RG(G_ZP, r), 0.0, mu);
+        prod *= ns * ps; cnt += 2; dt += ns + ps; l += A.o.resto_rho * (nt + pt);
+      }
       SOC(SOC_CT + r) = ct; th += fabs(ct);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      if (b.hl) { prod *= sv - b.lo; ++cnt; }
-      if (b.hu) { prod *= b.hi - sv; ++cnt; }
+      if (b.hl) { prod *= safe_slack(sv - b.lo, RW(A_VL, r), b.lo, mu); ++cnt; }
+      if (b.hu) { prod *= safe_slack(b.hi - sv, RW(A_VU, r), b.hi, mu); ++cnt; }
       if (b.hl && !b.hu) dt += sv - b.lo;
       if (b.hu && !b.hl) dt += b.hi - sv;
       if (cnt >= 4) { lb += n_log(prod); prod = 1.0; cnt = 0; }
@@ -564,32 +669,43 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     FOR_ROWS(st.X, body);
     if (cnt) lb += n_log(prod);
   }
-  const double fs = df * warp_sum(l);
+  const double fs = (RS ? 1.0 : df) * warp_sum(l);
   th = warp_sum(th); lb = warp_sum(lb); dt = warp_sum(dt);
   if (lane == 0) { RES(R_FT) = fs; RES(R_THT) = th; RES(R_LBT) = lb; RES(R_DTT) = dt; }
   __syncwarp();
 }
 
 // SOC right-hand side: c_soc <- a_soc * c_soc + c(trial);  q' = grad l + G^T((Sigma_s + dw) c_soc + mu beta)
-template <class L>
-__device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_soc, double mu, double dw, bool first) {
+// (RS: q' = G^T (y + Om chat(c_soc)))
+template <class L, bool RS>
+__device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_soc, double mu, double dw, bool first, double* cold) {
   if (lane <= L::N) {
     double X[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); q[i] = 0.0; }
+    if (!RS) {
 #pragma unroll
-    for (int v = 0; v < 6; ++v) q[cost_state(v)] = LV(LV_GL + v);
+      for (int v = 0; v < 6; ++v) q[cost_state(v)] = LV(LV_GL + v);
+    }
     const double kd = A.o.kappa_d;
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r), il = RW(A_IL, r), iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      const double cprev = first ? RW(A_G, r) - RW(A_S, r) : SOC(SOC_CSOC + r);
+      double c0 = RW(A_G, r) - RW(A_S, r);
+      if (RS) c0 += RG(G_N, r) - RG(G_P, r);
+      const double cprev = first ? c0 : SOC(SOC_CSOC + r);
       const double cs = a_soc * cprev + SOC(SOC_CT + r);
       SOC(SOC_CSOC + r) = cs;
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
-      const double yh = (RW(A_VL, r) * il + RW(A_VU, r) * iu + dw) * cs + mu * beta;
+      const double sig = RW(A_VL, r) * il + RW(A_VU, r) * iu;
+      double yh;
+      if (RS) {
+        const double y = RW(A_Y, r);
+        const RestoRow w = resto_row<L>(A, cold, lane, r, sig, beta, y, mu, dw);
+        yh = y + w.Om * (cs + w.rs * rcp(w.D) + w.rp * rcp(w.Dp) - w.rn * rcp(w.Dn));
+      } else yh = (sig + dw) * cs + mu * beta;
       if (box) q[si] += dc * yh; else { q[0] -= dc * yh * nx; q[1] -= dc * yh * ny; }
     };
     FOR_ROWS(X, body);
@@ -599,9 +715,10 @@ __device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_so
   __syncwarp();
 }
 
-// accept the trial point: primal step alpha, dual step a_du, kappa_Sigma reset, new reciprocal slacks
-template <class L>
-__device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alpha, double a_du, double mu, double dw, bool soc) {
+// accept the trial point: primal step alpha, dual step a_du, kappa_Sigma reset (reset), new reciprocal slacks
+template <class L, bool RS>
+__device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alpha, double a_du, double mu, double dw, bool soc, bool reset,
+                                       double* cold) {
   const bool act = lane <= L::N, hasu = lane < L::N;
   const double ks = A.o.kappa_sigma, kd = A.o.kappa_d, iks = 1.0 / A.o.kappa_sigma;
   if (hasu) {
@@ -609,12 +726,15 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
     for (int i = 0; i < 6; ++i) {
       const Bnd b = ctl_bounds(A, lane, i);
       const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i);
-      double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
-      if (b.hl) zl += a_du * ((mu - zl * du) * rcp(u - b.lo) - zl);
-      if (b.hu) zu += a_du * ((mu + zu * du) * rcp(b.hi - u) - zu);
+      const double zl0 = LV(LV_ZL + i), zu0 = LV(LV_ZU + i);
+      double zl = zl0, zu = zu0;
+      if (b.hl) zl += a_du * ((mu - zl * du) * rcp(safe_slack(u - b.lo, zl0, b.lo, mu)) - zl);
+      if (b.hu) zu += a_du * ((mu + zu * du) * rcp(safe_slack(b.hi - u, zu0, b.hi, mu)) - zu);
       const double un = fma(alpha, du, u);
-      if (b.hl) { const double i2 = rcp(un - b.lo); zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
-      if (b.hu) { const double i2 = rcp(b.hi - un); zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
+      if (reset) {
+        if (b.hl) { const double i2 = rcp(safe_slack(un - b.lo, zl0, b.lo, mu)); zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
+        if (b.hu) { const double i2 = rcp(safe_slack(b.hi - un, zu0, b.hi, mu)); zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
+      }
       LV(LV_U + i) = un; LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu;
     }
   }
@@ -624,7 +744,8 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
       const double ds = soc ? SOC(SOC_DS2 + r) : RW(A_DS, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      double vl = RW(A_VL, r), vu = RW(A_VU, r);
+      const double vl0 = RW(A_VL, r), vu0 = RW(A_VU, r);
+      double vl = vl0, vu = vu0;
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
@@ -635,10 +756,129 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       const double sn = fma(alpha, ds, s);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
       double il2 = 0.0, iu2 = 0.0;
-      if (hl) { il2 = rcp(sn - b.lo); vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
-      if (hu) { iu2 = rcp(b.hi - sn); vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
+      if (hl) { il2 = rcp(safe_slack(sn - b.lo, vl0, b.lo, mu)); if (reset) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
+      if (hu) { iu2 = rcp(safe_slack(b.hi - sn, vu0, b.hi, mu)); if (reset) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
       RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
+      if (RS) {
+        const double n0 = RG(G_N, r), p0 = RG(G_P, r), zn0 = RG(G_ZN, r), zp0 = RG(G_ZP, r);
+        const double dn = soc ? RG(G_DN2, r) : RG(G_DN, r), dp = soc ? RG(G_DP2, r) : RG(G_DP, r);
+        double zn = zn0 + a_du * ((mu - zn0 * dn) * rcp(safe_slack(n0, zn0, 0.0, mu)) - zn0);
+        double zp = zp0 + a_du * ((mu - zp0 * dp) * rcp(safe_slack(p0, zp0, 0.0, mu)) - zp0);
+        const double nn_ = fma(alpha, dn, n0), pn_ = fma(alpha, dp, p0);
+        if (reset) {
+          const double i1 = rcp(safe_slack(nn_, zn0, 0.0, mu)), i2 = rcp(safe_slack(pn_, zp0, 0.0, mu));
+          zn = fmax(fmin(zn, ks * mu * i1), mu * i1 * iks); zp = fmax(fmin(zp, ks * mu * i2), mu * i2 * iks);
+        }
+        RG(G_N, r) = nn_; RG(G_P, r) = pn_; RG(G_ZN, r) = zn; RG(G_ZP, r) = zp;
+      }
     }
+  }
+  __syncwarp();
+}
+
+// ---- rare paths --------------------------------------------------------------------------------------------------
+// save / restore the iterate (and the primal step) in a slot of the cold scratch
+template <class L>
+__device__ __noinline__ void ph_slot(double* cold, int slot, bool save, bool with_resto, int lane) {
+  constexpr int S = L::S, RSZ = L::RSZ;
+  double* sl = cold + L::CG_SLOT + slot * L::SLOT_N;
+  auto cp = [&](int sm0, int off, int n) {
+    for (int i = lane; i < n; i += 32) { if (save) sl[off + i] = smem[sm0 + i]; else smem[sm0 + i] = sl[off + i]; }
+  };
+  cp(L::LV0, 0, 18 * S);                                   // U, ZL, ZU
+  cp(L::LV0 + LV_DX * S, 18 * S, 14 * S);                  // DX, DU
+  cp(L::RW0, 32 * S, 4 * RSZ);                             // S, Y, VL, VU
+  cp(L::RW0 + A_IL * RSZ, 32 * S + 4 * RSZ, 2 * RSZ);      // IL, IU
+  if (with_resto)
+    for (int i = lane; i < 4 * RSZ; i += 32) { if (save) sl[32 * S + 6 * RSZ + i] = cold[i]; else cold[i] = sl[32 * S + 6 * RSZ + i]; }
+  __syncwarp();
+}
+
+// RestoIterateInitializer: elastic variables from the closed-form minimiser, their multipliers mu / value, bound
+// multipliers min(rho, .), y = 0, reference point x_R = current controls.  A_G holds g of the current point.
+template <class L>
+__device__ __noinline__ void ph_resto_init(const SolveArgs& A, int lane, double mu, double* cold) {
+  const double rho = A.o.resto_rho, h = mu / (2.0 * rho);
+  if (lane <= L::N) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) {
+      const double c = RW(A_G, r) - RW(A_S, r);
+      const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h), pv = c + nv;
+      RG(G_N, r) = nv; RG(G_P, r) = pv; RG(G_ZN, r) = mu / nv; RG(G_ZP, r) = mu / pv;
+      RW(A_VL, r) = fmin(rho, RW(A_VL, r)); RW(A_VU, r) = fmin(rho, RW(A_VU, r)); RW(A_Y, r) = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { UREF(i) = LV(LV_U + i); LV(LV_ZL + i) = fmin(rho, LV(LV_ZL + i)); LV(LV_ZU + i) = fmin(rho, LV(LV_ZU + i)); }
+  }
+  __syncwarp();
+}
+// RestoRestorationPhase (restoration inside the restoration phase): recompute n, p for the current x, s
+template <class L>
+__device__ __noinline__ void ph_resto_np(const SolveArgs& A, int lane, double mu, double* cold) {
+  const double rho = A.o.resto_rho, h = mu / (2.0 * rho);
+  if (lane <= L::N) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) {
+      const double c = RW(A_G, r) - RW(A_S, r);
+      const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h);
+      RG(G_N, r) = nv; RG(G_P, r) = c + nv; RG(G_DN, r) = 0.0; RG(G_DP, r) = 0.0;
+    }
+  }
+  __syncwarp();
+}
+// MinC_1NrmRestorationPhase, after a successful restoration: bound multipliers of the original problem as if the
+// whole phase had been one primal-dual step from the iterate saved in slot `slot`; y = 0.  Two passes: pass 0 returns
+// the largest -dz/z over decreasing multipliers (RES(R_ADU) <- step), pass 1 applies the step and returns max z.
+template <class L>
+__device__ __noinline__ double ph_resto_finish(const SolveArgs& A, int lane, double mu, double tau, double a_du, int pass, double* cold, int slot) {
+  constexpr int S = L::S;
+  const double* sl = cold + L::CG_SLOT + slot * L::SLOT_N;
+  double dnum = 0.0, dden = 1.0, zmax = 0.0;
+  auto upd = [&](double z0, double sl0, double sl1, double& znew) {
+    const double dz = (mu + z0 * (sl0 - sl1)) * rcp(sl0) - z0;
+    if (pass == 0) { if (dz < 0.0 && -dz * dden > dnum * z0) { dnum = -dz; dden = z0; } }
+    else { znew = z0 + a_du * dz; zmax = fmax(zmax, znew); }
+  };
+  if (lane < L::N) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const Bnd b = ctl_bounds(A, lane, i);
+      const double u0 = sl[(LV_U + i) * S + lane], zl0 = sl[(LV_ZL + i) * S + lane], zu0 = sl[(LV_ZU + i) * S + lane], u1 = LV(LV_U + i);
+      double zl = 0.0, zu = 0.0;
+      if (b.hl) upd(zl0, safe_slack(u0 - b.lo, zl0, b.lo, mu), safe_slack(u1 - b.lo, zl0, b.lo, mu), zl);
+      if (b.hu) upd(zu0, safe_slack(b.hi - u0, zu0, b.hi, mu), safe_slack(b.hi - u1, zu0, b.hi, mu), zu);
+      if (pass == 1) { LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu; }
+    }
+  }
+  if (lane <= L::N) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) {
+      const double dc = RW(A_DC, r);
+      const Bnd b = row_bounds<L>(A, lane, r, dc);
+      const double s0 = sl[32 * S + (A_S * L::R + r) * S + lane], vl0 = sl[32 * S + (A_VL * L::R + r) * S + lane], vu0 = sl[32 * S + (A_VU * L::R + r) * S + lane];
+      const double s1 = RW(A_S, r);
+      double vl = 0.0, vu = 0.0;
+      if (b.hl) upd(vl0, safe_slack(s0 - b.lo, vl0, b.lo, mu), safe_slack(s1 - b.lo, vl0, b.lo, mu), vl);
+      if (b.hu) upd(vu0, safe_slack(b.hi - s0, vu0, b.hi, mu), safe_slack(b.hi - s1, vu0, b.hi, mu), vu);
+      if (pass == 1) { RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_Y, r) = 0.0; RW(A_DS, r) = 0.0; }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) if (pass == 1) LV(LV_DU + i) = 0.0;
+  }
+  __syncwarp();
+  if (pass == 0) { const double td = warp_max(dnum / dden); return td > tau ? tau / td : 1.0; }
+  return warp_max(zmax);
+}
+// all bound multipliers <- 1 (bound_mult_reset_threshold exceeded after the restoration phase)
+template <class L>
+__device__ __noinline__ void ph_unit_mults(const SolveArgs& A, int lane) {
+  if (lane < L::N) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const Bnd b = ctl_bounds(A, lane, i); LV(LV_ZL + i) = b.hl ? 1.0 : 0.0; LV(LV_ZU + i) = b.hu ? 1.0 : 0.0; }
+  }
+  if (lane <= L::N) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) { RW(A_VL, r) = RW(A_IL, r) > 0.0 ? 1.0 : 0.0; RW(A_VU, r) = RW(A_IU, r) > 0.0 ? 1.0 : 0.0; }
   }
   __syncwarp();
 }
@@ -705,13 +945,57 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
 }
 
 // ---------------------------------------------------------------------------------------------------
+// State of one run of the algorithm (IpoptAlgorithm + BacktrackingLineSearch + FilterLSAcceptor members).  The
+// restoration phase is a second run of the same algorithm on the restoration problem; the original run's state is
+// parked in `Ao` meanwhile.
+struct Alg {
+  double mu, tau, dw_last, tol;
+  double theta_max, theta_min, ref_theta, ref_barr, ref_gbd;
+  double f, LB, DT;                      // objective and barrier pieces (sum of logs, damping sum) of the current point
+  double wd_theta, wd_barr, wd_gbd, wd_alpha_test, wd_dw;
+  double infpr;                          // max-norm of g - s where the restoration phase was called
+  int nfilt, succ_rej, n_resets, wd_short, wd_trial, soft_cnt;
+  bool last_rej_filter, in_wd, in_soft, tiny_last, tiny_flag, first_iter, mu_started;
+};
+__device__ __forceinline__ void alg_init(Alg& a, double mu, double tau_min, double tol) {
+  a.mu = mu; a.tau = fmax(tau_min, 1.0 - mu); a.dw_last = 0.0; a.tol = tol;
+  a.theta_max = -1.0; a.theta_min = -1.0; a.ref_theta = 0.0; a.ref_barr = 0.0; a.ref_gbd = 0.0;
+  a.f = 0.0; a.LB = 0.0; a.DT = 0.0; a.wd_theta = a.wd_barr = a.wd_gbd = a.wd_alpha_test = a.wd_dw = 0.0; a.infpr = 0.0;
+  a.nfilt = 0; a.succ_rej = 0; a.n_resets = 0; a.wd_short = 0; a.wd_trial = 0; a.soft_cnt = 0;
+  a.last_rej_filter = false; a.in_wd = false; a.in_soft = false; a.tiny_last = false; a.tiny_flag = false; a.first_iter = true; a.mu_started = false;
+}
+// filter [FILT_CAP][2] = (barrier, theta) margins; the original problem's lives in shared memory, the restoration
+// problem's in the cold scratch
+__device__ __forceinline__ bool filter_ok(const double* filt, int nfilt, double barr, double theta) {
+  for (int e = 0; e < nfilt; ++e) {
+    const double fb = filt[2 * e], ft = filt[2 * e + 1];
+    if (!(cmp_le(barr, fb, fb) || cmp_le(theta, ft, ft))) return false;
+  }
+  return true;
+}
+// add (barr, theta), dropping the entries it dominates (and the oldest one if the filter is full); returns the new length
+static __device__ __noinline__ int filter_add(double* filt, int nfilt, double barr, double theta, int lane) {
+  int n = 0;
+  if (lane == 0) {
+    for (int e = 0; e < nfilt; ++e) {
+      const double fb = filt[2 * e], ft = filt[2 * e + 1];
+      if (!(fb >= barr && ft >= theta)) { filt[2 * n] = fb; filt[2 * n + 1] = ft; ++n; }
+    }
+    if (n >= FILT_CAP) { for (int e = 0; e < 2 * (n - 1); ++e) filt[e] = filt[e + 2]; --n; }
+    filt[2 * n] = barr; filt[2 * n + 1] = theta; ++n;
+  }
+  n = __shfl_sync(FULL, n, 0);
+  __syncwarp();
+  return n;
+}
+
 template <class L>
-__device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int b, int lane) {
+__device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, double* cold, int b, int lane) {
   const Prob& pr = A.pr; const Opt& o = A.o;
   constexpr int S = L::S, R = L::R;
   constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(3 * R), Q20 = L::soc(3 * R + 6);
   const double T = pr.T;
-  unsigned long long n_fact = 0, n_ls = 0, n_soc = 0;
+  unsigned long long n_fact = 0, n_ls = 0, n_soc = 0, n_resto = 0, n_resto_it = 0, n_wd = 0, n_soft = 0, n_freset = 0;
 
   ph_load<L>(A, b, lane);
   double df = 1.0;
@@ -722,27 +1006,60 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
     __syncwarp();
   }
   const int nzt = ph_start<L>(A, lane);
-  ph_trial<L>(A, lane, 0.0, false, df);          // barrier pieces and constraint violation of the start
-  double f = RES(R_FT), LB = RES(R_LBT), DT = RES(R_DTT);
-  const double th0 = RES(R_THT);
-  const double theta_max = o.theta_max_fact * fmax(1.0, th0), theta_min = o.theta_min_fact * fmax(1.0, th0);
-  double mu = o.mu_init, tau = fmax(o.tau_min, 1.0 - mu);
-  const double mu_floor = fmin(o.tol, o.compl_inf_tol) / (o.kappa_eps + 1.0);
-  int nfilt = 0; double dw_last = 0.0;
-  int iter = 0, status = NMPC_MAXITER_EXCEEDED, tiny_count = 0; bool tiny_flag = false, ls = true;
-  constexpr int mtot = R * S;
+  Alg a, ao;                                       // running algorithm; parked original algorithm during restoration
+  alg_init(a, o.mu_init, o.tau_min, o.tol); alg_init(ao, o.mu_init, o.tau_min, o.tol);
+  ph_trial<L, false>(A, lane, 0.0, false, df, a.mu, cold);          // barrier pieces and constraint violation of the start
+  a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+  const double mu_floor = fmin(o.tol, df * o.compl_inf_tol) / (o.kappa_eps + 1.0);
+  int iter = 0, status = NMPC_MAXITER_EXCEEDED, mode = 0; bool ls = true;
+  constexpr int mtot = R * S, nx_ = NU * L::N;
+  double* filt1 = cold + L::CG_FILT;
+
+  // mode-dispatched phases
+  auto derivs = [&](double dw_) { if (mode) ph_derivs<L, true>(A, lane, false, df, a.mu, dw_, cold); else ph_derivs<L, false>(A, lane, false, df, a.mu, dw_, cold); };
+  auto dirs = [&](bool soc_, double dw_) { if (mode) ph_dir<L, true>(A, lane, a.mu, a.tau, soc_, dw_, cold); else ph_dir<L, false>(A, lane, a.mu, a.tau, soc_, dw_, cold); };
+  auto trial = [&](double al, bool soc_) { if (mode) ph_trial<L, true>(A, lane, al, soc_, df, a.mu, cold); else ph_trial<L, false>(A, lane, al, soc_, df, a.mu, cold); ++n_ls; };
+  auto accept_ = [&](double al, double adu, double dw_, bool soc_, bool reset) {
+    if (mode) ph_accept<L, true>(A, lane, al, adu, a.mu, dw_, soc_, reset, cold); else ph_accept<L, false>(A, lane, al, adu, a.mu, dw_, soc_, reset, cold);
+  };
+  auto filt = [&]() -> double* { return mode ? filt1 : &smem[L::FILT0]; };
+  auto barr_of = [&]() { return RES(R_FT) - a.mu * RES(R_LBT) + o.kappa_d * a.mu * RES(R_DTT); };
+  // FilterLSAcceptor
+  auto is_ftype = [&](double at) {
+    if (a.ref_theta == 0.0 && a.ref_gbd > 0.0 && a.ref_gbd < 100.0 * EPSM) return true;
+    return a.ref_gbd < 0.0 && at * n_pow(-a.ref_gbd, o.s_phi) > o.delta * n_pow(a.ref_theta, o.s_theta);
+  };
+  auto armijo = [&](double at, double tb) { return cmp_le(tb - a.ref_barr, o.eta_phi * at * a.ref_gbd, a.ref_barr); };
+  auto ok_to_current = [&](const Alg& q, double tb, double tt_, bool from_resto) {
+    if (!from_resto && tb > q.ref_barr) {
+      const double basval = fabs(q.ref_barr) > 10.0 ? log10(fabs(q.ref_barr)) : 1.0;
+      if (log10(tb - q.ref_barr) > o.obj_max_inc + basval) return false;
+    }
+    return cmp_le(tt_, (1.0 - o.gamma_theta) * q.ref_theta, q.ref_theta) || cmp_le(tb - q.ref_barr, -o.gamma_phi * q.ref_theta, q.ref_barr);
+  };
+  auto check_accept = [&](double at, double tb, double tt_) {
+    if (!isfinite(tb) || !isfinite(tt_)) return false;
+    if (a.theta_max < 0.0) a.theta_max = (mode ? o.resto_theta_max_fact : o.theta_max_fact) * fmax(1.0, a.ref_theta);
+    if (a.theta_min < 0.0) a.theta_min = o.theta_min_fact * fmax(1.0, a.ref_theta);
+    if (a.theta_max > 0.0 && tt_ > a.theta_max) return false;
+    bool acc;
+    if (at > 0.0 && is_ftype(at) && a.ref_theta <= a.theta_min) acc = armijo(at, tb);
+    else acc = ok_to_current(a, tb, tt_, false);
+    if (!acc) { a.last_rej_filter = false; return false; }
+    acc = filter_ok(filt(), a.nfilt, tb, tt_);
+    if (!acc) a.last_rej_filter = true;
+    return acc;
+  };
+  auto augment = [&]() { a.nfilt = filter_add(filt(), a.nfilt, a.ref_barr - o.gamma_phi * a.ref_theta, (1.0 - o.gamma_theta) * a.ref_theta, lane); };
+  auto acceptor_reset = [&]() { a.nfilt = 0; a.last_rej_filter = false; a.succ_rej = 0; };
 
   for (;;) {
     // Alignment point: the warps of a block start every IPM iteration together, so that they walk through the
     // same ~200 KB of phase code at the same time and share instruction-cache lines (unaligned warps thrash it:
     // `no_instruction` was 56 % of all stall cycles in v3).  Pure scheduling; results cannot depend on it.
-    // (Aligning at more points per iteration -- before the factorisation, direction, line search, accept -- was
-    // measured and is slower: each phase then lasts as long as its slowest warp; 43 -> 65 ms at B = 16384.)
-    // (Measured and rejected: releasing the barrier with a quorum of 5-7 of 8 warps, and letting warps with long line
-    // searches pay their arrival in advance and run out of phase -- both slower; strict lockstep wins.)
     align_warps(A.align_group, 1);
-    ph_derivs<L>(A, lane, ls, df);
     if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
+      ph_derivs<L, false>(A, lane, true, df, a.mu, 0.0, cold);
       ++n_fact;
       const bool ok = riccati_factor<L>(T, ric, A.ricmap, 1.0, 0.0, lane);
       if (ok) riccati_forward<L>(T, ric, false, lane, DX0, DU0);
@@ -750,130 +1067,300 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, int
       ls = false;
       continue;
     }
+    derivs(0.0);
     // ---- optimality error (scaled) and termination
-    const double du_inf = RES(R_DU), pr_inf = RES(R_PR), sumy = RES(R_SUMY), sumz = RES(R_SUMZ), viol = RES(R_VIOL);
-    const double pmax = RES(R_PMAX), pmin = RES(R_PMIN);
-    const double sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nzt)) / o.s_max;
-    const double sc = fmax(o.s_max, sumz / (double)max(1, nzt)) / o.s_max;
+    double du_inf = RES(R_DU), pr_inf = RES(R_PR), sumy = RES(R_SUMY), sumz = RES(R_SUMZ), viol = RES(R_VIOL);
+    double pmax = RES(R_PMAX), pmin = RES(R_PMIN);
+    const int nz = mode ? nzt + 2 * mtot : nzt;
+    double sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nz)) / o.s_max;
+    double sc = fmax(o.s_max, sumz / (double)max(1, nz)) / o.s_max;
     const double E0 = fmax(du_inf / sd, fmax(pr_inf, pmax / sc));
-    if (!isfinite(E0) || !isfinite(f)) { status = NMPC_INVALID_NUMBER; break; }
-    if (E0 <= o.tol && du_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
-      status = NMPC_SOLVE_SUCCEEDED; break;
-    }
-    if (iter >= o.max_iter) { status = NMPC_MAXITER_EXCEEDED; break; }
-    // ---- barrier parameter (monotone, with fast decrease)
-    {
-      auto emu = [&](double m) { return fmax(du_inf / sd, fmax(pr_inf, fmax(pmax - m, m - pmin) / sc)); };
-      double Emu = emu(mu);
-      while ((Emu <= o.kappa_eps * mu || tiny_flag) && mu > mu_floor) {
-        mu = fmax(mu_floor, fmin(o.kappa_mu * mu, n_pow(mu, o.theta_mu)));
-        tau = fmax(o.tau_min, 1.0 - mu); nfilt = 0; tiny_flag = false;
-        Emu = emu(mu);
+    if (mode == 0) {
+      if (!isfinite(E0) || !isfinite(a.f)) { status = NMPC_INVALID_NUMBER; break; }
+      if (E0 <= o.tol && du_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
+        status = NMPC_SOLVE_SUCCEEDED; break;
       }
-      if (tiny_flag && mu <= mu_floor) { status = NMPC_STEP_TOO_SMALL; break; }
+      if (iter >= o.max_iter) { status = NMPC_MAXITER_EXCEEDED; break; }
+    } else {
+      // RestoFilterConvergenceCheck: is the current restoration iterate acceptable to the ORIGINAL problem's filter?
+      int st = -1;                                  // -1 continue, -2 success, >= 0 failure status
+      if (iter >= o.max_iter) st = NMPC_MAXITER_EXCEEDED;
+      else {
+        const double oth = RES(R_OTH), oinf = RES(R_OINF);
+        double infpr_max = fmax(o.kappa_resto * ao.infpr, fmin(o.tol, o.constr_viol_tol));
+        if (o.kappa_resto == 0.0) infpr_max = 0.0;
+        if (!a.first_iter && !(oinf > infpr_max)) {
+          ph_trial<L, false>(A, lane, 0.0, false, df, ao.mu, cold);       // original objective and barrier terms at the restoration iterate
+          const double tb = RES(R_FT) - ao.mu * RES(R_LBT) + o.kappa_d * ao.mu * RES(R_DTT);
+          if (filter_ok(&smem[L::FILT0], ao.nfilt, tb, oth) && ok_to_current(ao, tb, oth, true)) st = -2;
+        }
+        if (st == -1) {       // is the restoration problem itself solved?  then the original one is (locally) infeasible
+          if (!isfinite(E0)) st = NMPC_INVALID_NUMBER;
+          else if (E0 <= a.tol && du_inf / df <= o.dual_inf_tol && pr_inf <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
+            if (oinf <= 1e2 * a.tol) {
+              if (a.tol > 1e-1 * o.tol) a.tol *= 1e-2;       // tighten once: the problem is only very slightly infeasible
+              else st = NMPC_RESTORATION_FAILED;              // converged to a feasible point the original filter does not accept
+            } else st = NMPC_INFEASIBLE_PROBLEM;
+          }
+        }
+        a.first_iter = false;
+      }
+      if (st == -2) {        // back to the original problem: x, s from the restoration phase, new bound multipliers, y = 0
+        a = ao; mode = 0;
+        const double adu = ph_resto_finish<L>(A, lane, a.mu, a.tau, 0.0, 0, cold, 1);
+        const double zmax = ph_resto_finish<L>(A, lane, a.mu, a.tau, adu, 1, cold, 1);
+        if (zmax > o.bound_mult_reset_threshold) ph_unit_mults<L>(A, lane);
+        ph_accept<L, false>(A, lane, 0.0, 0.0, a.mu, 0.0, false, true, cold);      // kappa_Sigma reset (AcceptTrialPoint)
+        ph_trial<L, false>(A, lane, 0.0, false, df, a.mu, cold);
+        a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+        a.in_soft = false; a.soft_cnt = 0; a.wd_short = 0;
+        continue;
+      }
+      if (st >= 0) { status = st; break; }
+    }
+    // ---- barrier parameter (MonotoneMuUpdate, with fast decrease)
+    {
+      bool tf = a.tiny_flag, tiny_exit = false; a.tiny_flag = false;
+      auto emu = [&](double m) { return fmax(du_inf / sd, fmax(pr_inf, fmax(pmax - m, m - pmin) / sc)); };
+      if (mode && !a.mu_started) a.mu_started = true;        // first restoration iteration: mu comes from the initializer
+      else {
+        a.mu_started = true;
+        double Emu = emu(a.mu);
+        bool done = false;
+        while ((Emu <= o.kappa_eps * a.mu || tf) && !done) {
+          const double nm = fmax(mu_floor, fmin(o.kappa_mu * a.mu, n_pow(a.mu, o.theta_mu)));
+          const bool changed = nm != a.mu;
+          if (!changed && tf) { tiny_exit = true; break; }     // TINY_STEP_DETECTED: solved to best possible accuracy
+          if (!changed) break;
+          a.mu = nm; a.tau = fmax(o.tau_min, 1.0 - a.mu);
+          if (mode) {     // the restoration objective depends on mu (eta = sqrt(mu)): refresh gradient and error ingredients
+            derivs(0.0);
+            du_inf = RES(R_DU); pr_inf = RES(R_PR); sumy = RES(R_SUMY); sumz = RES(R_SUMZ); pmax = RES(R_PMAX); pmin = RES(R_PMIN);
+            sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nz)) / o.s_max;
+            sc = fmax(o.s_max, sumz / (double)max(1, nz)) / o.s_max;
+            ph_trial<L, true>(A, lane, 0.0, false, df, a.mu, cold); a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+          }
+          if (tf) { done = true; tf = false; }
+          else { Emu = emu(a.mu); done = !(Emu <= o.kappa_eps * a.mu); }
+          a.in_soft = false; a.soft_cnt = 0; acceptor_reset();        // linesearch->Reset()
+        }
+      }
+      if (tiny_exit) {
+        if (mode == 0) status = NMPC_STEP_TOO_SMALL;
+        else status = RES(R_OINF) <= 1e2 * o.tol ? NMPC_RESTORATION_FAILED : NMPC_INFEASIBLE_PROBLEM;
+        break;
+      }
     }
     // ---- search direction with inertia correction
     const unsigned long long ls_before = n_ls;
     double dw = 0.0; bool ok = false;
     for (;;) {
       ++n_fact;
-      ok = riccati_factor<L>(T, ric, A.ricmap, mu, dw, lane);
+      ok = riccati_factor<L>(T, ric, A.ricmap, a.mu, dw, lane);
       if (ok) break;
-      if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, dw_last * o.dw_dec);
-      else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
+      if (dw == 0.0) dw = (a.dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, a.dw_last * o.dw_dec);
+      else dw = (a.dw_last == 0.0 || 1e5 * a.dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
       if (dw > o.dw_max) break;
+      if (mode) derivs(dw);                 // restoration rows enter with Om(dw)
     }
-    if (!ok) { status = NMPC_PERTURBATION_FAILED; break; }
-    if (dw > 0.0) dw_last = dw;
-    riccati_forward<L>(T, ric, false, lane, DX0, DU0);
-    ph_dir<L>(A, lane, mu, tau, false);
-    const double a_pr_max = RES(R_APR); double a_du = RES(R_ADU);
-    const double gbd = RES(R_GBD), theta = RES(R_THETA);
-    const bool tiny = RES(R_TINY) != 0.0 && theta <= 1e-4;
-    const double phi = f - mu * LB + o.kappa_d * mu * DT;
-    // ---- filter line search
-    const double pw_gbd = gbd < 0.0 ? n_pow(-gbd, o.s_phi) : 0.0, pw_th = n_pow(theta, o.s_theta);
-    auto is_ftype = [&](double a) { return gbd < 0.0 && a * pw_gbd > o.delta * pw_th; };
-    auto armijo = [&](double a, double ph_t) { return cmp_le(ph_t - phi, o.eta_phi * a * gbd, phi); };
-    auto acceptable = [&](double a_test, double th_, double ph_) {
-      if (!isfinite(th_) || !isfinite(ph_)) return false;
-      if (th_ > theta_max) return false;
-      bool acc;
-      if (a_test > 0.0 && is_ftype(a_test) && theta <= theta_min) acc = armijo(a_test, ph_);
-      else acc = cmp_le(th_, (1.0 - o.gamma_theta) * theta, theta) || cmp_le(ph_ - phi, -o.gamma_phi * theta, phi);
-      if (!acc) return false;
-      for (int e = 0; e < nfilt; ++e) if (!(th_ < smem[L::FILT0 + 2 * e] || ph_ < smem[L::FILT0 + 2 * e + 1])) return false;
-      return true;
+    bool goto_resto = !ok;                  // step computation failed: fall back to the restoration phase
+    if (ok) {
+      if (dw > 0.0) a.dw_last = dw;
+      riccati_forward<L>(T, ric, false, lane, DX0, DU0);
+      dirs(false, dw);
+    }
+    double a_pr_max = RES(R_APR), a_du = RES(R_ADU), gbd = RES(R_GBD), theta = RES(R_THETA);
+    double phi = a.f - a.mu * a.LB + o.kappa_d * a.mu * a.DT;
+    // ---- BacktrackingLineSearch::FindAcceptableTrialPoint
+    // InitThisLineSearch (+ the filter reset heuristic)
+    if (!a.in_wd) {
+      if (o.max_filter_resets > 0 && a.n_resets < o.max_filter_resets) {
+        if (a.last_rej_filter) { if (++a.succ_rej >= o.filter_reset_trigger) { acceptor_reset(); ++a.n_resets; ++n_freset; } }
+        else a.succ_rej = 0;
+      }
+      a.last_rej_filter = false;
+      a.ref_theta = theta; a.ref_barr = phi; a.ref_gbd = gbd;
+    } else { a.ref_theta = a.wd_theta; a.ref_barr = a.wd_barr; a.ref_gbd = a.wd_gbd; }
+    bool tiny = !goto_resto && RES(R_TINY) != 0.0 && theta <= 1e-4;
+    // restore the watchdog's reference iterate and its step; everything that belongs to the current point is recomputed
+    auto stop_watchdog = [&]() {
+      a.in_wd = false; a.wd_short = 0; dw = a.wd_dw;
+      ph_slot<L>(cold, 0, false, mode != 0, lane);
+      derivs(dw); dirs(false, dw);
+      a_pr_max = RES(R_APR); a_du = RES(R_ADU); gbd = RES(R_GBD); theta = RES(R_THETA);
+      trial(0.0, false); a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+      phi = a.f - a.mu * a.LB + o.kappa_d * a.mu * a.DT;
+      a.ref_theta = a.wd_theta; a.ref_barr = a.wd_barr; a.ref_gbd = a.wd_gbd;
     };
-    double amin = o.gamma_theta;
-    if (gbd < 0.0) {
-      amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gbd));
-      if (theta <= theta_min) amin = fmin(amin, o.delta * pw_th / pw_gbd);
+    if (a.in_wd && (goto_resto || tiny)) { stop_watchdog(); goto_resto = false; tiny = false; }
+    if (o.watchdog_trigger > 0 && !a.in_wd && !goto_resto && !tiny && !a.in_soft && a.wd_short >= o.watchdog_trigger) {
+      ++n_wd;                                  // StartWatchDog
+      a.in_wd = true; a.wd_trial = 0; a.wd_alpha_test = a_pr_max; a.wd_dw = dw;
+      a.wd_theta = a.ref_theta; a.wd_barr = a.ref_barr; a.wd_gbd = a.ref_gbd;
+      ph_slot<L>(cold, 0, true, mode != 0, lane);
     }
-    amin *= o.alpha_min_frac;
-    double alpha = a_pr_max, alpha_test = a_pr_max, phi_t = 0.0, a_soc = 0.0, th_prev = 0.0;
-    bool accepted = false, used_soc = false, first = true;
-    int soc_left = 0;      // > 0: the next trial is a second-order-correction trial
-    if (tiny) { ++tiny_count; tiny_flag = true; } else tiny_count = 0;
-    for (;;) {
-      const bool soc_trial = soc_left > 0;
-      const double a_try = soc_trial ? a_soc : alpha;
-      ph_trial<L>(A, lane, a_try, soc_trial, df);
-      ++n_ls;
-      const double th_t = RES(R_THT);
-      phi_t = RES(R_FT) - mu * RES(R_LBT) + o.kappa_d * mu * RES(R_DTT);
-      if (tiny) { accepted = true; break; }
-      if (!soc_trial) alpha_test = alpha;
-      if (acceptable(alpha, th_t, phi_t)) {
-        accepted = true;
-        if (soc_trial) { used_soc = true; alpha = a_soc; ++n_soc; }
-        break;
-      }
-      bool next_soc = false;
-      if (soc_trial) {
-        --soc_left;
-        next_soc = soc_left > 0 && th_t <= o.kappa_soc * th_prev;
-        if (!next_soc) soc_left = 0;
-      } else if (first && o.max_soc > 0 && th_t >= theta && isfinite(th_t)) {
-        soc_left = o.max_soc; next_soc = true;
-      }
-      if (next_soc) {
-        const bool first_soc = !soc_trial;
-        th_prev = th_t;
-        ph_socrhs<L>(A, lane, first_soc ? alpha : a_soc, mu, dw, first_soc);
-        riccati_resolve<L>(T, Q20, ric, mu, lane);
-        riccati_forward<L>(T, ric, true, lane, DX0, DUS0);
-        ph_dir<L>(A, lane, mu, tau, true);
-        a_soc = RES(R_APR);
-        continue;
-      }
-      first = false;
-      alpha *= o.alpha_red;
-      if (!(alpha > amin)) break;
-    }
-    if (tiny && tiny_count >= 2 && mu <= mu_floor) { status = NMPC_STEP_TOO_SMALL; break; }
-    if (!accepted) { status = NMPC_RESTORATION_NEEDED; break; }
-    // ---- filter augmentation
-    if (!tiny && !(is_ftype(alpha_test) && armijo(alpha_test, phi_t))) {
-      if (lane == 0) {
-        if (nfilt == FILT_CAP) for (int e = 0; e < 2 * (FILT_CAP - 1); ++e) smem[L::FILT0 + e] = smem[L::FILT0 + e + 2];   // drop the oldest
-        const int at = nfilt == FILT_CAP ? FILT_CAP - 1 : nfilt;
-        smem[L::FILT0 + 2 * at] = (1.0 - o.gamma_theta) * theta; smem[L::FILT0 + 2 * at + 1] = phi - o.gamma_phi * theta;
-      }
-      if (nfilt < FILT_CAP) ++nfilt;
+    double alpha = a_pr_max, phi_t = 0.0, th_t = 0.0;
+    bool accepted = false, used_soc = false, moved = false;     // moved: the iterate already sits at the new point (soft restoration step)
+    int n_steps = 0, tag = '?';
+    if (tiny) {
+      trial(alpha, false);
+      if (!isfinite(RES(R_THT)) || !isfinite(barr_of())) { status = NMPC_INVALID_NUMBER; break; }
+      if (a.tiny_last) { a.tiny_flag = true; tag = 'T'; } else tag = 't';
+      a.tiny_last = RES(R_DYMAX) < o.tiny_step_y_tol;
+      accepted = true;
+    } else a.tiny_last = false;
+    // BacktrackingLineSearch::TrySoftRestoStep with the current step (DU, DS)
+    auto try_soft = [&](bool& sat) {
+      sat = false;
+      if (o.soft_resto_red == 0.0) return false;
+      const double al = fmin(a_pr_max, a_du);
+      trial(al, false);
+      th_t = RES(R_THT); phi_t = barr_of();
+      if (!isfinite(th_t) || !isfinite(phi_t)) return false;
+      alpha = al; a_du = al;
+      if (check_accept(0.0, phi_t, th_t)) { sat = true; return true; }
+      const double nvar = (double)(nx_ + mtot + (mode ? 2 * mtot : 0));
+      const double ft = RES(R_FT), lbt = RES(R_LBT), dtt = RES(R_DTT);
+      derivs(dw);                                       // complementarity sums with the current mu
+      const double cur_err = RES(R_DU1) / nvar + RES(R_THETA) / (double)mtot + RES(R_CO1) / (double)max(1, nz);
+      ph_slot<L>(cold, mode ? 2 : 1, true, mode != 0, lane);
+      accept_(al, al, dw, false, false);
+      derivs(dw);
+      const double tr_err = RES(R_DU1) / nvar + RES(R_THETA) / (double)mtot + RES(R_CO1) / (double)max(1, nz);
+      if (lane == 0) { RES(R_FT) = ft; RES(R_LBT) = lbt; RES(R_DTT) = dtt; }
       __syncwarp();
+      if (tr_err <= o.soft_resto_red * cur_err) { moved = true; ++n_soft; return true; }
+      ph_slot<L>(cold, mode ? 2 : 1, false, mode != 0, lane);
+      derivs(dw);
+      return false;
+    };
+    if (!goto_resto && !tiny) {
+      if (a.in_soft) {
+        if (++a.soft_cnt > o.max_soft_resto) accepted = false;
+        else {
+          bool sat = false;
+          accepted = try_soft(sat);
+          if (accepted) { tag = 's'; if (sat) { a.in_soft = false; a.soft_cnt = 0; tag = 'S'; } }
+        }
+      } else {
+        bool skip_first = false;
+        for (;;) {       // DoBacktrackingLineSearch (repeated once when the watchdog is stopped)
+          bool eval_err = false; accepted = false;
+          const double a_max = a_pr_max;
+          double amin = a_max;
+          if (!a.in_wd) {
+            amin = o.gamma_theta;
+            if (gbd < 0.0) {
+              amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gbd));
+              if (theta <= a.theta_min) amin = fmin(amin, o.delta * n_pow(theta, o.s_theta) / n_pow(-gbd, o.s_phi));
+            }
+            amin *= o.alpha_min_frac;
+          }
+          alpha = a_max;
+          double a_test = a.in_wd ? a.wd_alpha_test : alpha;
+          if (skip_first) alpha *= o.alpha_red;
+          while (alpha > amin || n_steps == 0) {
+            trial(alpha, false);
+            th_t = RES(R_THT); phi_t = barr_of();
+            const bool okv = isfinite(th_t) && isfinite(phi_t);
+            if (!a.in_wd) a_test = alpha;
+            if (okv) accepted = check_accept(a_test, phi_t, th_t); else { accepted = false; eval_err = true; }
+            if (accepted || a.in_wd) break;
+            if (okv && alpha == a_max && a.ref_theta <= th_t && o.max_soc > 0) {
+              // second-order correction (FilterLSAcceptor::TrySecondOrderCorrection)
+              int count = 0; double theta_old = 0.0, theta_trial = th_t, a_soc = alpha; bool first = true;
+              while (count < o.max_soc && !accepted && (count == 0 || theta_trial <= o.kappa_soc * theta_old)) {
+                theta_old = theta_trial;
+                if (mode) ph_socrhs<L, true>(A, lane, a_soc, a.mu, dw, first, cold); else ph_socrhs<L, false>(A, lane, a_soc, a.mu, dw, first, cold);
+                first = false;
+                riccati_resolve<L>(T, Q20, ric, a.mu, lane);
+                riccati_forward<L>(T, ric, true, lane, DX0, DUS0);
+                dirs(true, dw);
+                a_soc = RES(R_APR);
+                trial(a_soc, true);
+                th_t = RES(R_THT); phi_t = barr_of();
+                if (!isfinite(th_t) || !isfinite(phi_t)) break;
+                accepted = check_accept(a_test, phi_t, th_t);
+                if (accepted) { alpha = a_soc; used_soc = true; ++n_soc; }
+                else { ++count; theta_trial = th_t; }
+              }
+              if (accepted) break;
+            }
+            alpha *= o.alpha_red; ++n_steps;
+          }
+          if (accepted) {      // UpdateForNextIteration
+            if (!is_ftype(a_test) || !armijo(a_test, phi_t)) { augment(); tag = used_soc ? 'H' : 'h'; } else tag = used_soc ? 'F' : 'f';
+          } else if (a.in_wd) tag = 'w';
+          if (a.in_wd) {
+            if (accepted) { a.in_wd = false; break; }
+            if (eval_err || ++a.wd_trial > o.watchdog_trial_max) { stop_watchdog(); skip_first = true; continue; }
+            accepted = true; break;        // take the step without acceptance test
+          }
+          break;
+        }
+      }
     }
-    if (used_soc) a_du = RES(R_ADU);
+    bool entered_resto = false;
+    if (!accepted) {
+      if (!a.in_soft && !goto_resto) {      // try the current direction as a soft restoration step
+        augment();                           // PrepareRestoPhaseStart
+        bool sat = false;
+        accepted = try_soft(sat);
+        if (accepted) { if (sat) tag = 'S'; else { a.in_soft = true; tag = 's'; } }
+      }
+      if (!accepted) {
+        if (!a.in_soft) augment();
+        if (theta <= 1e-2 * o.tol || !o.resto) {       // "Restoration phase called, but point is almost feasible"
+          status = NMPC_RESTORATION_FAILED;
+          break;
+        }
+        tag = 'R';
+        if (mode) {     // restoration inside the restoration phase: n, p from their closed form, duals unchanged
+          ph_resto_np<L>(A, lane, a.mu, cold);
+          alpha = 0.0; a_du = 0.0; moved = false; used_soc = false;
+          a.in_soft = false; a.soft_cnt = 0; a.wd_short = 0;
+          accepted = true;
+          if (lane <= L::N) { for (int r = 0; r < R; ++r) RW(A_DS, r) = 0.0; for (int i = 0; i < 6; ++i) LV(LV_DU + i) = 0.0; }
+          __syncwarp();
+          trial(0.0, false);
+        } else entered_resto = true;
+      }
+    } else if (!a.in_soft || tiny) {
+      if (used_soc) a_du = RES(R_ADU);
+      if (n_steps == 0) a.wd_short = 0; else ++a.wd_short;
+    }
     if (A.dbg && lane == 0 && iter < A.dbg_rows) {
-      double* Lg = A.dbg + ((size_t)b * A.dbg_rows + iter) * 8;
-      Lg[0] = mu; Lg[1] = f / df; Lg[2] = pr_inf; Lg[3] = du_inf; Lg[4] = dw; Lg[5] = alpha; Lg[6] = a_du; Lg[7] = (double)(n_ls - ls_before);
+      double* Lg = A.dbg + ((size_t)b * A.dbg_rows + iter) * DBG_COLS;
+      Lg[0] = a.mu; Lg[1] = mode ? a.f : a.f / df; Lg[2] = pr_inf; Lg[3] = du_inf; Lg[4] = dw; Lg[5] = alpha; Lg[6] = a_du;
+      Lg[7] = (double)(n_ls - ls_before); Lg[8] = (double)tag; Lg[9] = (double)mode;
     }
-    ph_accept<L>(A, lane, alpha, a_du, mu, dw, used_soc);
-    f = RES(R_FT); LB = RES(R_LBT); DT = RES(R_DTT);
+    if (entered_resto) {
+      // MinC_1NrmRestorationPhase::PerformRestoration: park the original algorithm, start a fresh one on the restoration problem
+      ++n_resto;
+      ph_slot<L>(cold, 1, true, false, lane);
+      a.infpr = RES(R_PR);                 // max-norm of g - s at the current point (latest ph_derivs)
+      ao = a;
+      const double mu_r = fmax(ao.mu, ao.infpr);
+      alg_init(a, mu_r, o.tau_min, o.tol);
+      ph_resto_init<L>(A, lane, mu_r, cold);
+      mode = 1;
+      ph_trial<L, true>(A, lane, 0.0, false, df, a.mu, cold);
+      a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+      ++iter;
+      continue;
+    }
+    // ---- accept (IpoptAlgorithm::AcceptTrialPoint)
+    if (moved) accept_(0.0, 0.0, dw, false, true);         // the soft restoration step already moved the iterate: kappa_Sigma reset only
+    else accept_(alpha, a_du, dw, used_soc, true);
+    a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+    if (mode) ++n_resto_it;
     ++iter;
   }
   ph_output<L>(A, b, lane, df, status, iter);
-  if (lane == 0 && A.stats) { atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); }
+  if (lane == 0 && A.stats) {
+    atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); atomicAdd(&A.stats[3], n_resto);
+    atomicAdd(&A.stats[4], n_resto_it); atomicAdd(&A.stats[5], n_wd); atomicAdd(&A.stats[6], n_soft); atomicAdd(&A.stats[7], n_freset);
+  }
 }
 
 // Longest-first fetch order for the NEXT call on this handle from this call's iteration counts: counting sort,
@@ -902,16 +1389,19 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
   using L = Lay<N_, NOBS_>;
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next call on this handle starts from clean counters
-    *A.counter_next = 0; *A.done_next = 0; A.stats_next[0] = 0; A.stats_next[1] = 0; A.stats_next[2] = 0;
+    *A.counter_next = 0; *A.done_next = 0;
+    for (int i = 0; i < NSTAT; ++i) A.stats_next[i] = 0;
   }
-  double* ric = A.ric + (size_t)(blockIdx.x * L::WPB + (threadIdx.x >> 5)) * A.ric_stride;
+  const size_t slot = (size_t)(blockIdx.x * L::WPB + (threadIdx.x >> 5));
+  double* ric = A.ric + slot * A.ric_stride;
+  double* cold = A.cold + slot * A.cold_stride;
   for (;;) {
     int q = 0;
     if (lane == 0) q = atomicAdd(A.counter, 1);
     q = __shfl_sync(FULL, q, 0);
     if (q >= A.B) break;
     const int b = A.order ? A.order[q] : q;
-    solve_instance<L>(A, ric, b, lane);
+    solve_instance<L>(A, ric, cold, b, lane);
     __syncwarp();
     int fin = 0;
     if (lane == 0) { __threadfence(); fin = atomicAdd(A.done, 1); }      // this instance's outputs are visible before the count
@@ -927,6 +1417,8 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
 #undef SOC
 #undef RES
 #undef PAR
+#undef RG
+#undef UREF
 #undef smem
 
 }  // namespace nmpc

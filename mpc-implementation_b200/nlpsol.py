@@ -309,8 +309,7 @@ class Solver:
     def work_counters(self) -> Dict[str, int]:
         st = _ffi.NmpcStats()
         _ffi.check(_ffi.lib().nmpc_get_stats(self._h, C.byref(st)), "nmpc_get_stats")
-        return dict(kernel_launches=st.kernel_launches, factorizations=st.factorizations, ls_trials=st.ls_trials,
-                    soc_accepted=st.soc_accepted)
+        return {name: int(getattr(st, name)) for name, _ in _ffi.NmpcStats._fields_}
 
     # -- function-level evaluation (nlp_f / nlp_g / nlp_grad_f / nlp_hess_l of the reference's nlpsol) ----
     def evaluate(self, w, p, lam=None, v=None, sigma: float = 1.0, obstacles=None, weights=None, target_traj=None):
