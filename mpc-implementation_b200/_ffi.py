@@ -10,7 +10,7 @@ import subprocess
 from pathlib import Path
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = _CSRC / "libnmpc_b200.so"
+LIB_PATH = Path(__import__("os").environ.get("NMPC_B200_LIB", _CSRC / "libnmpc_b200.so"))     # override: A/B timing of library builds
 
 NMPC_OBS_PER_INSTANCE = 1
 

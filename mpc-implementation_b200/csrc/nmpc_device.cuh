@@ -179,8 +179,8 @@ struct Lay {
   //      restoration phase): restoration row arrays, reference controls, the restoration problem's own filter, and three
   //      slots that hold a saved iterate + step
   static constexpr int RSZ = R * S;
-  static constexpr int CG_ROWS = 0;                     // 8 arrays [R][S]: n, p, z_n, z_p, dn, dp, dn_soc, dp_soc
-  static constexpr int CG_UR = 8 * RSZ;                 // [6][S] reference controls x_R of the restoration problem
+  static constexpr int CG_ROWS = 0;                     // 10 arrays [R][S]: n, p, z_n, z_p, dn, dp, dy, dn_soc, dp_soc, dy_soc
+  static constexpr int CG_UR = 10 * RSZ;                // [6][S] reference controls x_R of the restoration problem
   static constexpr int CG_FILT = CG_UR + 6 * S;         // [FILT_CAP][2]
   static constexpr int CG_SLOT = CG_FILT + 2 * FILT_CAP;
   static constexpr int SLOT_N = 32 * S + 10 * RSZ;      // U ZL ZU (18 S) | DX DU (14 S) | S Y VL VU (4 RS) | IL IU (2 RS) | n p z_n z_p (4 RS)

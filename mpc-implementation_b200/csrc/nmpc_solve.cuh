@@ -138,7 +138,7 @@ __device__ __forceinline__ int align_warps(int g, int working) {
 // restoration row arrays in the cold scratch: (arr * R + r) * S + lane
 #define RG(arr, r) cold[((arr) * L::R + (r)) * L::S + lane]
 #define UREF(i) cold[L::CG_UR + (i) * L::S + lane]
-enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DN2, G_DP2 };
+enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DY, G_DN2, G_DP2, G_DY2 };
 
 // T-scaled non-zeros of the dynamics Jacobian A_k - I of this lane's stage
 struct Dyn { double e03, e13, e23, e04, e14; };
@@ -561,16 +561,17 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
         c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) + RG(G_N, r) - RG(G_P, r) - s;
         const double chat = c + q.rs * rcp(q.D) + q.rp * rcp(q.Dp) - q.rn * rcp(q.Dn);
         const double dyv = q.Om * (gd + chat);
+        // dy first, then ds, dn, dp from their own dual equations: exact dual consistency whatever the rounding of the D's
         const double dn = -(dyv + q.rn) * rcp(q.Dn), dp = (dyv - q.rp) * rcp(q.Dp);
-        ds = gd + dn - dp + c;
-        if (soc) { RG(G_DN2, r) = dn; RG(G_DP2, r) = dp; } else { RG(G_DN, r) = dn; RG(G_DP, r) = dp; }
+        ds = (dyv - q.rs) * rcp(q.D);
+        if (soc) { RG(G_DN2, r) = dn; RG(G_DP2, r) = dp; RG(G_DY2, r) = dyv; } else { RG(G_DN, r) = dn; RG(G_DP, r) = dp; RG(G_DY, r) = dyv; }
         const double in_ = rcp(q.n), ip_ = rcp(q.p);
         tp = fmax(tp, fmax(-dn * in_, -dp * ip_));
         dual_frac(q.zn, (mu - q.zn * dn) * in_ - q.zn);
         dual_frac(q.zp, (mu - q.zp * dp) * ip_ - q.zp);
         gbd += (A.o.resto_rho - mu * in_ + kd * mu) * dn + (A.o.resto_rho - mu * ip_ + kd * mu) * dp;
         nottiny = nottiny || (fabs(dn) > tt * (1.0 + fabs(q.n))) || (fabs(dp) > tt * (1.0 + fabs(q.p)));
-        dymax = fmax(dymax, fabs(q.D * ds + q.rs));
+        dymax = fmax(dymax, fabs(dyv));
       } else {
         c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) - s;
         ds = gd + c;
@@ -749,7 +750,7 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
-      const double dy = (vl * il + vu * iu + dw) * ds + (mu * beta - y);
+      const double dy = RS ? (soc ? RG(G_DY2, r) : RG(G_DY, r)) : (vl * il + vu * iu + dw) * ds + (mu * beta - y);
       RW(A_Y, r) = y + alpha * dy;
       if (hl) vl += a_du * ((mu - vl * ds) * il - vl);
       if (hu) vu += a_du * ((mu + vu * ds) * iu - vu);
@@ -821,7 +822,7 @@ __device__ __noinline__ void ph_resto_np(const SolveArgs& A, int lane, double mu
     for (int r = 0; r < L::R; ++r) {
       const double c = RW(A_G, r) - RW(A_S, r);
       const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h);
-      RG(G_N, r) = nv; RG(G_P, r) = c + nv; RG(G_DN, r) = 0.0; RG(G_DP, r) = 0.0;
+      RG(G_N, r) = nv; RG(G_P, r) = c + nv; RG(G_DN, r) = 0.0; RG(G_DP, r) = 0.0; RG(G_DY, r) = 0.0;
     }
   }
   __syncwarp();

@@ -639,15 +639,28 @@ struct Algo {
     }
     return cholesky(M.data(), nm);
   }
+  // Row quantities of a step whose structural part d.x[0:n0] is known (q = J0 dx).  Restoration problem: dy first,
+  //     dy = Om (q + chat),  chat = c + rs/D + rp/Dp - rn/Dn,   ds = (dy - rs)/D,  dn = -(dy + rn)/Dn,  dp = (dy - rp)/Dp,
+  // so that the dual equations of s, n, p hold exactly whatever the rounding of the (large) D's.
+  void recover_rows(const std::vector<double>& rx, const std::vector<double>& rs, const double* cc, Iter& d) const {
+    for (int r = 0; r < m; ++r) {
+      double q = 0; const double* Jr = &J0[(size_t)r * n0]; for (int i = 0; i < n0; ++i) q += Jr[i] * d.x[i];
+      if (ne) {
+        const double Dn = Dx[n0 + r], Dp = Dx[n0 + m + r], rn = rx[n0 + r], rp = rx[n0 + m + r];
+        const double chat = cc[r] + rs[r] / Ds[r] + rp / Dp - rn / Dn;
+        const double dy = Om[r] * (q + chat);
+        d.y[r] = dy; d.s[r] = (dy - rs[r]) / Ds[r]; d.x[n0 + r] = -(dy + rn) / Dn; d.x[n0 + m + r] = (dy - rp) / Dp;
+      } else { d.s[r] = q + cc[r]; d.y[r] = Ds[r] * d.s[r] + rs[r]; }
+    }
+  }
   void solve_dir(const std::vector<double>& rx, const std::vector<double>& rs, const double* cc, Iter& d) {
     const bool expl = ne && o.resto_explicit;
-    std::vector<double> t(m), tt(m), q(m);
+    std::vector<double> t(m), tt(m);
     for (int r = 0; r < m; ++r) t[r] = Ds[r] * cc[r] + rs[r];
     if (ne && !expl) {
       for (int r = 0; r < m; ++r) {
-        const double Dn = Dx[n0 + r], Dp = Dx[n0 + m + r], det = Dn * Dp + Ds[r] * (Dn + Dp);
-        const double bn = rx[n0 + r] + t[r], bp = rx[n0 + m + r] - t[r];
-        tt[r] = t[r] + Ds[r] * (-Dp * bn + Dn * bp) / det;
+        const double Dn = Dx[n0 + r], Dp = Dx[n0 + m + r];
+        tt[r] = Om[r] * (cc[r] + rs[r] / Ds[r] + rx[n0 + m + r] / Dp - rx[n0 + r] / Dn);
       }
     } else tt = t;
     const int nm = expl ? n : n0;
@@ -656,19 +669,12 @@ struct Algo {
     if (expl) for (int r = 0; r < m; ++r) { rhs[n0 + r] = -(rx[n0 + r] + t[r]); rhs[n0 + m + r] = -(rx[n0 + m + r] - t[r]); }
     chol_solve(M.data(), nm, rhs.data());
     for (int i = 0; i < nm; ++i) d.x[i] = rhs[i];
-    for (int r = 0; r < m; ++r) { double v = 0; const double* Jr = &J0[(size_t)r * n0]; for (int i = 0; i < n0; ++i) v += Jr[i] * d.x[i]; q[r] = v; }
-    if (ne && !expl) {
+    if (expl) {      // validation path: everything from the explicit solve
       for (int r = 0; r < m; ++r) {
-        const double Dn = Dx[n0 + r], Dp = Dx[n0 + m + r], det = Dn * Dp + Ds[r] * (Dn + Dp);
-        const double bn = rx[n0 + r] + t[r], bp = rx[n0 + m + r] - t[r];
-        d.x[n0 + r] = (-(Dp + Ds[r]) * bn - Ds[r] * bp - Ds[r] * Dp * q[r]) / det;
-        d.x[n0 + m + r] = (-Ds[r] * bn - (Dn + Ds[r]) * bp + Ds[r] * Dn * q[r]) / det;
+        double q = 0; const double* Jr = &J0[(size_t)r * n0]; for (int i = 0; i < n0; ++i) q += Jr[i] * d.x[i];
+        d.s[r] = q + d.x[n0 + r] - d.x[n0 + m + r] + cc[r]; d.y[r] = Ds[r] * d.s[r] + rs[r];
       }
-    }
-    for (int r = 0; r < m; ++r) {
-      double jd = q[r]; if (ne) jd += d.x[n0 + r] - d.x[n0 + m + r];
-      d.s[r] = jd + cc[r]; d.y[r] = Ds[r] * d.s[r] + rs[r];
-    }
+    } else recover_rows(rx, rs, cc, d);
   }
   void dual_dirs(Iter& d) const {
     for (int i = 0; i < n; ++i) {
@@ -706,7 +712,28 @@ struct Algo {
     }
     return a;
   }
-  double ftb_dual(const Iter& d) const { return ftb_dual_of(cur, d, tau, *this); }
+  double ftb_dual(const Iter& d) const {
+    if (getenv("ORACLE_DEBUG_DUAL")) {
+      double a = 1.0; int wi = -1, wk = -1;
+      for (int i = 0; i < n; ++i) {
+        if (d.zL[i] < 0 && hasxL(i)) { double t = -tau * cur.zL[i] / d.zL[i]; if (t < a) { a = t; wi = i; wk = 0; } }
+        if (d.zU[i] < 0 && hasxU(i)) { double t = -tau * cur.zU[i] / d.zU[i]; if (t < a) { a = t; wi = i; wk = 1; } }
+      }
+      for (int r = 0; r < m; ++r) {
+        if (d.vL[r] < 0 && hasdL(r)) { double t = -tau * cur.vL[r] / d.vL[r]; if (t < a) { a = t; wi = r; wk = 2; } }
+        if (d.vU[r] < 0 && hasdU(r)) { double t = -tau * cur.vU[r] / d.vU[r]; if (t < a) { a = t; wi = r; wk = 3; } }
+      }
+      if (wk >= 0) {
+        const double z = wk == 0 ? cur.zL[wi] : wk == 1 ? cur.zU[wi] : wk == 2 ? cur.vL[wi] : cur.vU[wi];
+        const double dz = wk == 0 ? d.zL[wi] : wk == 1 ? d.zU[wi] : wk == 2 ? d.vL[wi] : d.vU[wi];
+        const double dp = wk < 2 ? d.x[wi] : d.s[wi];
+        const double sl = wk == 0 ? slxL(cur, wi) : wk == 1 ? slxU(cur, wi) : wk == 2 ? sldL(cur, wi) : sldU(cur, wi);
+        fprintf(stderr, "iter %d resto %d: a_du %g limited by kind %d idx %d (n0 %d m %d): z %g dz %g dprimal %g slack %g raw slack %g\n", iter, (int)is_resto, a, wk, wi, n0, m, z, dz, dp, sl,
+                wk == 0 ? cur.x[wi] - P.xL[wi] : wk == 1 ? P.xU[wi] - cur.x[wi] : wk == 2 ? cur.s[wi] - P.dL[wi] : P.dU[wi] - cur.s[wi]);
+      }
+    }
+    return ftb_dual_of(cur, d, tau, *this);
+  }
   // gradient of the barrier function (with damping) times the step
   double grad_barr_t_delta(const Iter& d) const {
     double gbd = 0;
@@ -730,8 +757,7 @@ struct Algo {
   }
 
   // ---- search direction (with inertia correction) ---------------------------------------------------
-  bool compute_direction() {
-    P.eval_hess(1.0, cur.y.data(), mu, W0.data());
+  void build_sigma_rhs() {      // Sigma's, right-hand sides and residual at the current point (current mu)
     std::vector<double> jty(n); JtY(cur.y.data(), jty.data());
     for (int i = 0; i < n; ++i) {
       double sig = 0, r_ = grad[i] + jty[i]; const bool hl = hasxL(i), hu = hasxU(i);
@@ -750,10 +776,20 @@ struct Algo {
       Sgs[r] = sig; rS[r] = r_;
       cvec[r] = crow(g, cur, r);
     }
+  }
+  void set_perturbation(double dw) {
+    for (int i = 0; i < n; ++i) Dx[i] = Sgx[i] + dw;
+    for (int r = 0; r < m; ++r) {
+      Ds[r] = Sgs[r] + dw;
+      Om[r] = (ne && !o.resto_explicit) ? 1.0 / (1.0 / Ds[r] + 1.0 / Dx[n0 + r] + 1.0 / Dx[n0 + m + r]) : Ds[r];
+    }
+  }
+  bool compute_direction() {
+    P.eval_hess(1.0, cur.y.data(), mu, W0.data());
+    build_sigma_rhs();
     double dw = 0.0; bool ok = false;
     for (;;) {       // PDPerturbationHandler: delta_x = delta_s = dw, delta_c = delta_d = 0
-      for (int i = 0; i < n; ++i) Dx[i] = Sgx[i] + dw;
-      for (int r = 0; r < m; ++r) Ds[r] = Sgs[r] + dw;
+      set_perturbation(dw);
       ok = factor(true, Dx, Ds);
       if (ok) break;
       if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : std::max(o.dw_min, dw_last * o.dw_dec);
@@ -856,17 +892,11 @@ struct Algo {
   void stop_watchdog() {
     in_watchdog = false; cur = wd_iter; del = wd_del; wd_short = 0; dw_cur = wd_dw;
     eval_point();
-    // The primal step (dx, ds) is the stored one; its dual parts are recomputed at the restored point with the CURRENT
-    // barrier parameter (identical to the stored ones unless mu changed while the watchdog was active; the CUDA kernel
-    // never stores dual steps, it derives them from (dx, ds) when it needs them).
-    for (int r = 0; r < m; ++r) {
-      double sig = 0, r_ = -cur.y[r]; const bool hl = hasdL(r), hu = hasdU(r);
-      if (hl) { double sl = sldL(cur, r); sig += cur.vL[r] / sl; r_ -= mu / sl; }
-      if (hu) { double sl = sldU(cur, r); sig += cur.vU[r] / sl; r_ += mu / sl; }
-      if (hl && !hu) r_ += o.kappa_d * mu;
-      if (hu && !hl) r_ -= o.kappa_d * mu;
-      del.y[r] = (sig + wd_dw) * del.s[r] + r_;
-    }
+    // The structural part dx of the step is the stored one; its row and dual parts are recomputed at the restored point
+    // with the CURRENT barrier parameter (identical to the stored ones unless mu changed while the watchdog was active;
+    // the CUDA kernel keeps only (dx, du) of a step and derives the rest when it needs it).
+    build_sigma_rhs(); set_perturbation(wd_dw);
+    recover_rows(rX, rS, cvec.data(), del);
     dual_dirs(del);
     ref_theta = wd_theta; ref_barr = wd_barr; ref_gbd = wd_gbd;
   }

@@ -76,6 +76,15 @@ for k in range(steps):
             if rel(a[0], g[0]) > 1e-6 or rel(a[5], g[5]) > 1e-4 or int(a[7]) != int(g[7]) or (int(a[8]) % 1000) != int(g[8]):
                 first = it; break
         print(f"    first divergence at iteration {first}")
+        fmt = lambda a, mode, tag: "mu %.3e f %.6e pr %.3e du %.3e dw %.2e a %.4e/%.4e ls %2d %s%s" % (a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], 'R' if mode else ' ', chr(int(tag)) if tag > 0 else '?')
+        print("    oracle tail:")
+        for a in seq[-5:]:
+            print("         " + fmt(a, a[8] >= 1000, int(a[8]) % 1000))
+        print("    gpu tail:")
+        for it in range(max(0, int(ig[b]) - 5), min(int(ig[b]) + 1, ROWS)):
+            g = lg[it]
+            if g[0] != 0:
+                print("     %3d " % it + fmt(g, g[9], g[8]))
         lo_i = max(0, (first or 0) - 3)
         for it in range(lo_i, min(n, lo_i + 8)):
             a, g = seq[it], lg[it]
