@@ -51,6 +51,7 @@ constexpr int RIC_L = 54;     // 21: Cholesky factor of Lambda (packed lower) + 
 constexpr int RIC_K2 = 81;    // 6 : kappa of the SOC right-hand side
 constexpr int RIC_N = 88;
 constexpr int FILT_CAP = 24;
+constexpr int ALG_N = 48;     // per-warp algorithm state kept in shared memory
 constexpr int STG_N = 356;    // Riccati staging area (nmpc_riccati.cuh)
 
 // scalar results returned by the phases through shared memory
@@ -83,12 +84,13 @@ static __device__ __noinline__ double n_log(double x) { return log(x); }
 static __device__ __noinline__ double n_pow(double x, double y) { return pow(x, y); }
 static __device__ __noinline__ double2 n_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
-// IPOPT's CalculateSafeSlack: a slack that rounding has pushed to (or below) zero is replaced by a tiny positive value
-// (slack_move = eps^(3/4)).  z = multiplier of that bound at the current iterate, bnd = the bound itself.
-__device__ __forceinline__ double safe_slack(double sl, double z, double bnd, double mu) {
+// IPOPT's CalculateSafeSlack: a slack that rounding has pushed to (or below) eps * min(1, mu) is replaced by a tiny
+// positive value (slack_move = eps^(3/4)) and the bound moved.  Here the accepted VARIABLE is moved instead (ph_accept),
+// by the same amount floored at four ulps of the bound; z = multiplier of that bound at the current iterate.
+static __device__ __noinline__ double safe_value(double sl, double z, double bnd, double mu) {
   const double s_min = 2.220446049250313e-16 * fmin(1.0, mu);
-  if (sl < s_min) sl = fmin(fmax(mu / z, s_min), fmax(sl, 0.0) + 1.8189894035458565e-12 * fmax(1.0, fabs(bnd)));
-  return sl;
+  const double t = fmin(fmax(mu / z, s_min), fmax(sl, 0.0) + 1.8189894035458565e-12 * fmax(1.0, fabs(bnd)));
+  return fmax(t, 4.0 * 2.220446049250313e-16 * fabs(bnd));
 }
 
 // ---- warp collectives ---------------------------------------------------------------------------
@@ -170,8 +172,8 @@ struct Lay {
   static constexpr int STG0 = even_up(SOCX0 + (SOC_N - SOC_LO) * S);
   __host__ __device__ static constexpr int soc(int e) { return e < SOC_LO ? LQ0 + e * S : SOCX0 + (e - SOC_LO) * S; }
   static constexpr int OBS0 = STG0 + STG_N;
-  static constexpr int FILT0 = even_up(OBS0 + 3 * NOBS_ + 1);
-  static constexpr int RES0 = FILT0 + 2 * FILT_CAP;
+  static constexpr int ALG0 = even_up(OBS0 + 3 * NOBS_ + 1);     // algorithm state (nmpc_solve.cuh: AlgF), ALG_N doubles
+  static constexpr int RES0 = ALG0 + ALG_N;
   static constexpr int PAR0 = RES0 + 24;
   static constexpr int TOTAL = even_up(PAR0 + 14);   // p (11), w1, w2 of this instance
   // warps (= concurrent instances) per block: as many slices as fit in the 227 KB a block may use, at most NMPC_WPB_MAX
@@ -181,8 +183,9 @@ struct Lay {
   static constexpr int RSZ = R * S;
   static constexpr int CG_ROWS = 0;                     // 10 arrays [R][S]: n, p, z_n, z_p, dn, dp, dy, dn_soc, dp_soc, dy_soc
   static constexpr int CG_UR = 10 * RSZ;                // [6][S] reference controls x_R of the restoration problem
-  static constexpr int CG_FILT = CG_UR + 6 * S;         // [FILT_CAP][2]
-  static constexpr int CG_SLOT = CG_FILT + 2 * FILT_CAP;
+  static constexpr int CG_FILT = CG_UR + 6 * S;         // [2][FILT_CAP][2]: filter of the original problem, of the restoration problem
+  static constexpr int CG_PARK = CG_FILT + 4 * FILT_CAP;   // [ALG_N] algorithm state of the original problem while the restoration phase runs
+  static constexpr int CG_SLOT = CG_PARK + ALG_N;
   static constexpr int SLOT_N = 32 * S + 10 * RSZ;      // U ZL ZU (18 S) | DX DU (14 S) | S Y VL VU (4 RS) | IL IU (2 RS) | n p z_n z_p (4 RS)
   static constexpr int COLD_TOTAL = even_up(CG_SLOT + 3 * SLOT_N);
   static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);

@@ -202,7 +202,7 @@ __device__ __forceinline__ RestoRow resto_row(const SolveArgs& A, const double* 
                                               double mu, double dw) {
   RestoRow q;
   q.zn = RG(G_ZN, r); q.zp = RG(G_ZP, r);
-  q.n = safe_slack(RG(G_N, r), q.zn, 0.0, mu); q.p = safe_slack(RG(G_P, r), q.zp, 0.0, mu);
+  q.n = (RG(G_N, r)); q.p = (RG(G_P, r));
   const double in_ = rcp(q.n), ip_ = rcp(q.p), kdm = A.o.kappa_d * mu;
   q.D = sig_s + dw; q.Dn = q.zn * in_ + dw; q.Dp = q.zp * ip_ + dw;
   q.rs = mu * beta - y;
@@ -343,7 +343,7 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
 // to the control diagonal and its gradient to the control right-hand side; rows enter with the weight Om(dw) instead
 // of Sigma_s + dw, so this phase is re-run for every inertia-correction value dw.
 template <class L, bool RS>
-__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df, double mu, double dw, double* cold) {
+__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df, double mu, double dw, bool want1, double* cold) {
   const Prob& pr = A.pr; constexpr int N = L::N; const double T = pr.T;
   const bool act = lane <= N, hasu = lane < N;
   double u[6];
@@ -372,7 +372,8 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
   for (int i = 0; i < 8; ++i) { a[i] = 0.0; qa[i] = 0.0; qb[i] = 0.0; qd[i] = 0.0; }
   double du_l = 0.0, pr_l = 0.0, sumy = 0.0, sumz = 0.0, viol = 0.0, pmax = 0.0, pmin = CUDART_INF;
   double du1 = 0.0, pr1 = 0.0, co1 = 0.0, oth = 0.0, oinf = 0.0;
-  auto compl_ = [&](double pz) { pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); co1 += fabs(pz - mu); };
+  // want1: also the 1-norms the soft restoration phase tests (rare; the hot path skips them)
+  auto compl_ = [&](double pz) { pmax = fmax(pmax, pz); pmin = fmin(pmin, pz); if (want1) co1 += fabs(pz - mu); };
   if (act) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) LV(LV_X + i) = st.X[i];
@@ -402,7 +403,8 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
         ya = y + q.Om * chat; w = dc * dc * q.Om; yad = y;
         // n / p parts of the optimality error
         const double gn = A.o.resto_rho + y - q.zn, gp = A.o.resto_rho - y - q.zp;
-        du_l = fmax(du_l, fmax(fabs(gn), fabs(gp))); du1 += fabs(gn) + fabs(gp); sumz += q.zn + q.zp;
+        du_l = fmax(du_l, fmax(fabs(gn), fabs(gp))); if (want1) du1 += fabs(gn) + fabs(gp);
+        sumz += q.zn + q.zp;
         compl_(q.n * q.zn); compl_(q.p * q.zp);
       } else {
         ya = ls ? (vu - vl) : sig * c; w = dc * dc * sig; yad = y;
@@ -427,10 +429,11 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
       }
       // optimality-error ingredients
       const double gs = fabs(-y - vl + vu);
-      du_l = fmax(du_l, gs); du1 += gs; pr_l = fmax(pr_l, fabs(c)); pr1 += fabs(c); sumy += fabs(y); sumz += vl + vu;
+      du_l = fmax(du_l, gs); pr_l = fmax(pr_l, fabs(c)); sumy += fabs(y); sumz += vl + vu;
+      if (want1) { du1 += gs; pr1 += fabs(c); }
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      if (b.hl) compl_(safe_slack(s - b.lo, vl, b.lo, mu) * vl);
-      if (b.hu) compl_(safe_slack(b.hi - s, vu, b.hi, mu) * vu);
+      if (b.hl) compl_((s - b.lo) * vl);
+      if (b.hu) compl_((b.hi - s) * vu);
       const double lo_o = __ldg(A.lbg + lane * L::R + r), hi_o = __ldg(A.ubg + lane * L::R + r);
       if (lo_o > -1e19) viol = fmax(viol, lo_o - gu);
       if (hi_o < 1e19) viol = fmax(viol, gu - hi_o);
@@ -474,7 +477,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
       if (hasu) {
         const Bnd b = ctl_bounds(A, lane, i);
         const double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
-        const double sl = safe_slack(u[i] - b.lo, zl, b.lo, mu), su = safe_slack(b.hi - u[i], zu, b.hi, mu);
+        const double sl = (u[i] - b.lo), su = (b.hi - u[i]);
         double gR = 0.0;
         if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))); gR = eta * d * d * (u[i] - ur); glx[i] += gR; }
         if (ls) rb = zu - zl;
@@ -486,7 +489,8 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
           if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))); sig += eta * d * d; rb += gR / mu; }
         }
         const double gx = fabs(glx[i] - zl + zu);
-        du_l = fmax(du_l, gx); du1 += gx; sumz += zl + zu;
+        du_l = fmax(du_l, gx); if (want1) du1 += gx;
+        sumz += zl + zu;
         if (b.hl) compl_(sl * zl);
         if (b.hu) compl_(su * zu);
       }
@@ -495,12 +499,12 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
   }
   du_l = warp_max(du_l); pr_l = warp_max(pr_l); sumy = warp_sum(sumy); sumz = warp_sum(sumz);
   viol = warp_max(viol); pmax = warp_max(pmax); pmin = warp_min(pmin);
-  du1 = warp_sum(du1); pr1 = warp_sum(pr1); co1 = warp_sum(co1);
+  if (want1) { du1 = warp_sum(du1); pr1 = warp_sum(pr1); co1 = warp_sum(co1); }
   if (RS) { oth = warp_sum(oth); oinf = warp_max(oinf); }
   if (lane == 0) {
     RES(R_F) = fsum; RES(R_DU) = du_l; RES(R_PR) = pr_l; RES(R_SUMY) = sumy; RES(R_SUMZ) = sumz;
     RES(R_VIOL) = viol; RES(R_PMAX) = pmax; RES(R_PMIN) = pmin;
-    RES(R_DU1) = du1; RES(R_THETA) = pr1; RES(R_CO1) = co1;
+    if (want1) { RES(R_DU1) = du1; RES(R_THETA) = pr1; RES(R_CO1) = co1; }
     if (RS) { RES(R_OTH) = oth; RES(R_OINF) = oinf; }
   }
   __syncwarp();
@@ -591,7 +595,7 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
       for (int i = 0; i < 6; ++i) {
         const Bnd b = ctl_bounds(A, lane, i);
         const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
-        const double il = b.hl ? rcp(safe_slack(u - b.lo, zl, b.lo, mu)) : 0.0, iu = b.hu ? rcp(safe_slack(b.hi - u, zu, b.hi, mu)) : 0.0;
+        const double il = b.hl ? rcp((u - b.lo)) : 0.0, iu = b.hu ? rcp((b.hi - u)) : 0.0;
         tp = fmax(tp, fmax(-du * il, du * iu));
         if (b.hl) dual_frac(zl, (mu - zl * du) * il - zl);
         if (b.hu) dual_frac(zu, (mu + zu * du) * iu - zu);
@@ -633,8 +637,8 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     if (hasu) {
       ut[i] = fma(alpha, soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), LV(LV_U + i));   // same expression as ph_accept
       const Bnd b = ctl_bounds(A, lane, i);
-      if (b.hl) prod *= safe_slack(ut[i] - b.lo, LV(LV_ZL + i), b.lo, mu);
-      if (b.hu) prod *= safe_slack(b.hi - ut[i], LV(LV_ZU + i), b.hi, mu);
+      if (b.hl) prod *= (ut[i] - b.lo);
+      if (b.hu) prod *= (b.hi - ut[i]);
       if (b.hl && !b.hu) dt += ut[i] - b.lo;
       if (b.hu && !b.hl) dt += b.hi - ut[i];
       if (i == 2 || i == 5) { lb += n_log(prod); prod = 1.0; }
@@ -656,13 +660,13 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
         const double nt = fma(alpha, soc ? RG(G_DN2, r) : RG(G_DN, r), RG(G_N, r));
         const double pt = fma(alpha, soc ? RG(G_DP2, r) : RG(G_DP, r), RG(G_P, r));
         ct += nt - pt;
-        const double ns = safe_slack(nt, RG(G_ZN, r), 0.0, mu), ps = safe_slack(pt, RG(G_ZP, r), 0.0, mu);
+        const double ns = (nt), ps = (pt);
         prod *= ns * ps; cnt += 2; dt += ns + ps; l += A.o.resto_rho * (nt + pt);
       }
       SOC(SOC_CT + r) = ct; th += fabs(ct);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      if (b.hl) { prod *= safe_slack(sv - b.lo, RW(A_VL, r), b.lo, mu); ++cnt; }
-      if (b.hu) { prod *= safe_slack(b.hi - sv, RW(A_VU, r), b.hi, mu); ++cnt; }
+      if (b.hl) { prod *= (sv - b.lo); ++cnt; }
+      if (b.hu) { prod *= (b.hi - sv); ++cnt; }
       if (b.hl && !b.hu) dt += sv - b.lo;
       if (b.hu && !b.hl) dt += b.hi - sv;
       if (cnt >= 4) { lb += n_log(prod); prod = 1.0; cnt = 0; }
@@ -722,6 +726,7 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
                                        double* cold) {
   const bool act = lane <= L::N, hasu = lane < L::N;
   const double ks = A.o.kappa_sigma, kd = A.o.kappa_d, iks = 1.0 / A.o.kappa_sigma;
+  const double smin = EPSM * fmin(1.0, mu);
   if (hasu) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -729,12 +734,14 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i);
       const double zl0 = LV(LV_ZL + i), zu0 = LV(LV_ZU + i);
       double zl = zl0, zu = zu0;
-      if (b.hl) zl += a_du * ((mu - zl * du) * rcp(safe_slack(u - b.lo, zl0, b.lo, mu)) - zl);
-      if (b.hu) zu += a_du * ((mu + zu * du) * rcp(safe_slack(b.hi - u, zu0, b.hi, mu)) - zu);
-      const double un = fma(alpha, du, u);
+      if (b.hl) zl += a_du * ((mu - zl * du) * rcp((u - b.lo)) - zl);
+      if (b.hu) zu += a_du * ((mu + zu * du) * rcp((b.hi - u)) - zu);
+      double un = fma(alpha, du, u);
+      if (b.hl && un - b.lo < smin) un = b.lo + safe_value(un - b.lo, zl0, b.lo, mu);       // slack safeguard: the variable moves
+      if (b.hu && b.hi - un < smin) un = b.hi - safe_value(b.hi - un, zu0, b.hi, mu);
       if (reset) {
-        if (b.hl) { const double i2 = rcp(safe_slack(un - b.lo, zl0, b.lo, mu)); zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
-        if (b.hu) { const double i2 = rcp(safe_slack(b.hi - un, zu0, b.hi, mu)); zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
+        if (b.hl) { const double i2 = rcp((un - b.lo)); zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
+        if (b.hu) { const double i2 = rcp((b.hi - un)); zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
       }
       LV(LV_U + i) = un; LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu;
     }
@@ -754,20 +761,24 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       RW(A_Y, r) = y + alpha * dy;
       if (hl) vl += a_du * ((mu - vl * ds) * il - vl);
       if (hu) vu += a_du * ((mu + vu * ds) * iu - vu);
-      const double sn = fma(alpha, ds, s);
+      double sn = fma(alpha, ds, s);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
+      if (hl && sn - b.lo < smin) sn = b.lo + safe_value(sn - b.lo, vl0, b.lo, mu);
+      if (hu && b.hi - sn < smin) sn = b.hi - safe_value(b.hi - sn, vu0, b.hi, mu);
       double il2 = 0.0, iu2 = 0.0;
-      if (hl) { il2 = rcp(safe_slack(sn - b.lo, vl0, b.lo, mu)); if (reset) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
-      if (hu) { iu2 = rcp(safe_slack(b.hi - sn, vu0, b.hi, mu)); if (reset) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
+      if (hl) { il2 = rcp((sn - b.lo)); if (reset) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
+      if (hu) { iu2 = rcp((b.hi - sn)); if (reset) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
       RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
       if (RS) {
         const double n0 = RG(G_N, r), p0 = RG(G_P, r), zn0 = RG(G_ZN, r), zp0 = RG(G_ZP, r);
         const double dn = soc ? RG(G_DN2, r) : RG(G_DN, r), dp = soc ? RG(G_DP2, r) : RG(G_DP, r);
-        double zn = zn0 + a_du * ((mu - zn0 * dn) * rcp(safe_slack(n0, zn0, 0.0, mu)) - zn0);
-        double zp = zp0 + a_du * ((mu - zp0 * dp) * rcp(safe_slack(p0, zp0, 0.0, mu)) - zp0);
-        const double nn_ = fma(alpha, dn, n0), pn_ = fma(alpha, dp, p0);
+        double zn = zn0 + a_du * ((mu - zn0 * dn) * rcp((n0)) - zn0);
+        double zp = zp0 + a_du * ((mu - zp0 * dp) * rcp((p0)) - zp0);
+        double nn_ = fma(alpha, dn, n0), pn_ = fma(alpha, dp, p0);
+        if (nn_ < smin) nn_ = safe_value(nn_, zn0, 0.0, mu);
+        if (pn_ < smin) pn_ = safe_value(pn_, zp0, 0.0, mu);
         if (reset) {
-          const double i1 = rcp(safe_slack(nn_, zn0, 0.0, mu)), i2 = rcp(safe_slack(pn_, zp0, 0.0, mu));
+          const double i1 = rcp((nn_)), i2 = rcp((pn_));
           zn = fmax(fmin(zn, ks * mu * i1), mu * i1 * iks); zp = fmax(fmin(zp, ks * mu * i2), mu * i2 * iks);
         }
         RG(G_N, r) = nn_; RG(G_P, r) = pn_; RG(G_ZN, r) = zn; RG(G_ZP, r) = zp;
@@ -846,8 +857,8 @@ __device__ __noinline__ double ph_resto_finish(const SolveArgs& A, int lane, dou
       const Bnd b = ctl_bounds(A, lane, i);
       const double u0 = sl[(LV_U + i) * S + lane], zl0 = sl[(LV_ZL + i) * S + lane], zu0 = sl[(LV_ZU + i) * S + lane], u1 = LV(LV_U + i);
       double zl = 0.0, zu = 0.0;
-      if (b.hl) upd(zl0, safe_slack(u0 - b.lo, zl0, b.lo, mu), safe_slack(u1 - b.lo, zl0, b.lo, mu), zl);
-      if (b.hu) upd(zu0, safe_slack(b.hi - u0, zu0, b.hi, mu), safe_slack(b.hi - u1, zu0, b.hi, mu), zu);
+      if (b.hl) upd(zl0, (u0 - b.lo), (u1 - b.lo), zl);
+      if (b.hu) upd(zu0, (b.hi - u0), (b.hi - u1), zu);
       if (pass == 1) { LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu; }
     }
   }
@@ -859,8 +870,8 @@ __device__ __noinline__ double ph_resto_finish(const SolveArgs& A, int lane, dou
       const double s0 = sl[32 * S + (A_S * L::R + r) * S + lane], vl0 = sl[32 * S + (A_VL * L::R + r) * S + lane], vu0 = sl[32 * S + (A_VU * L::R + r) * S + lane];
       const double s1 = RW(A_S, r);
       double vl = 0.0, vu = 0.0;
-      if (b.hl) upd(vl0, safe_slack(s0 - b.lo, vl0, b.lo, mu), safe_slack(s1 - b.lo, vl0, b.lo, mu), vl);
-      if (b.hu) upd(vu0, safe_slack(b.hi - s0, vu0, b.hi, mu), safe_slack(b.hi - s1, vu0, b.hi, mu), vu);
+      if (b.hl) upd(vl0, (s0 - b.lo), (s1 - b.lo), vl);
+      if (b.hu) upd(vu0, (b.hi - s0), (b.hi - s1), vu);
       if (pass == 1) { RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_Y, r) = 0.0; RW(A_DS, r) = 0.0; }
     }
 #pragma unroll
@@ -946,27 +957,67 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
 }
 
 // ---------------------------------------------------------------------------------------------------
-// State of one run of the algorithm (IpoptAlgorithm + BacktrackingLineSearch + FilterLSAcceptor members).  The
-// restoration phase is a second run of the same algorithm on the restoration problem; the original run's state is
-// parked in `Ao` meanwhile.
-struct Alg {
-  double mu, tau, dw_last, tol;
-  double theta_max, theta_min, ref_theta, ref_barr, ref_gbd;
-  double f, LB, DT;                      // objective and barrier pieces (sum of logs, damping sum) of the current point
-  double wd_theta, wd_barr, wd_gbd, wd_alpha_test, wd_dw;
-  double infpr;                          // max-norm of g - s where the restoration phase was called
-  int nfilt, succ_rej, n_resets, wd_short, wd_trial, soft_cnt;
-  bool last_rej_filter, in_wd, in_soft, tiny_last, tiny_flag, first_iter, mu_started;
+// State of one run of the algorithm (IpoptAlgorithm + BacktrackingLineSearch + FilterLSAcceptor members) lives in the
+// warp's shared-memory slice (Lay::ALG0), as doubles: every lane holds the same value of everything below, so plain
+// stores may be issued by all lanes and read-modify-writes go through al_add().  The restoration phase is a second run of
+// the same algorithm on the restoration problem; the original run's fields [0, F_NALG) are parked in the cold scratch
+// meanwhile.  Keeping this state out of registers keeps the hot loop free of spills across the phase calls, and lets the
+// rare paths (watchdog stop, soft restoration, restoration entry / exit) be separate functions.
+enum AlgF {
+  F_MU = 0, F_TAU, F_DWLAST, F_TOL, F_THMAX, F_THMIN, F_RTH, F_RBARR, F_RGBD,      // barrier parameter, filter reference point
+  F_F, F_LB, F_DT,                                  // objective and barrier pieces (sum of logs, damping sum) of the current point
+  F_WTH, F_WBARR, F_WGBD, F_WAT, F_WDW,             // watchdog reference
+  F_INFPR,                                          // max-norm of g - s where the restoration phase was called
+  F_NFILT, F_SUCC, F_NRES, F_WSHORT, F_WTRIAL, F_SOFTC,
+  F_LASTREJ, F_INWD, F_INSOFT, F_TINYLAST, F_TINYFLAG, F_FIRST, F_MUST,
+  F_NALG,
+  F_MODE = F_NALG,                                  // 0 original problem, 1 restoration problem
+  F_DW, F_APR, F_ADU, F_GBD, F_THETA, F_PHI,        // this iteration: delta_w, step limits, barrier slope, theta, barrier of the current point
+  F_C0,                                             // 8 work counters
+  F_END = F_C0 + NSTAT
 };
-__device__ __forceinline__ void alg_init(Alg& a, double mu, double tau_min, double tol) {
-  a.mu = mu; a.tau = fmax(tau_min, 1.0 - mu); a.dw_last = 0.0; a.tol = tol;
-  a.theta_max = -1.0; a.theta_min = -1.0; a.ref_theta = 0.0; a.ref_barr = 0.0; a.ref_gbd = 0.0;
-  a.f = 0.0; a.LB = 0.0; a.DT = 0.0; a.wd_theta = a.wd_barr = a.wd_gbd = a.wd_alpha_test = a.wd_dw = 0.0; a.infpr = 0.0;
-  a.nfilt = 0; a.succ_rej = 0; a.n_resets = 0; a.wd_short = 0; a.wd_trial = 0; a.soft_cnt = 0;
-  a.last_rej_filter = false; a.in_wd = false; a.in_soft = false; a.tiny_last = false; a.tiny_flag = false; a.first_iter = true; a.mu_started = false;
+static_assert(F_END <= ALG_N, "algorithm state does not fit its shared-memory region");
+#define AL(f) smem[L::ALG0 + (f)]
+
+template <class L>
+__device__ __forceinline__ double al_add(int f, double d) { const double v = AL(f) + d; __syncwarp(); AL(f) = v; return v; }
+template <class L>
+__device__ __forceinline__ void al_count(int c, int lane) { if (lane == 0) AL(F_C0 + c) += 1.0; }
+template <class L>
+__device__ __noinline__ void alg_init(double mu, double tau_min, double tol) {
+  __syncwarp();
+#pragma unroll 1
+  for (int f = 0; f < F_NALG; ++f) AL(f) = 0.0;
+  __syncwarp();
+  AL(F_MU) = mu; AL(F_TAU) = fmax(tau_min, 1.0 - mu); AL(F_TOL) = tol; AL(F_THMAX) = -1.0; AL(F_THMIN) = -1.0; AL(F_FIRST) = 1.0;
+  __syncwarp();
 }
-// filter [FILT_CAP][2] = (barrier, theta) margins; the original problem's lives in shared memory, the restoration
-// problem's in the cold scratch
+
+// mode-dispatched phases
+template <class L>
+__device__ __forceinline__ void do_derivs(const SolveArgs& A, int lane, int mode, double df, double dw, bool want1, double* cold) {
+  if (mode) ph_derivs<L, true>(A, lane, false, df, AL(F_MU), dw, want1, cold); else ph_derivs<L, false>(A, lane, false, df, AL(F_MU), dw, want1, cold);
+}
+template <class L>
+__device__ __forceinline__ void do_dir(const SolveArgs& A, int lane, int mode, bool soc, double dw, double* cold) {
+  if (mode) ph_dir<L, true>(A, lane, AL(F_MU), AL(F_TAU), soc, dw, cold); else ph_dir<L, false>(A, lane, AL(F_MU), AL(F_TAU), soc, dw, cold);
+}
+template <class L>
+__device__ __forceinline__ void do_trial(const SolveArgs& A, int lane, int mode, double alpha, bool soc, double df, double* cold) {
+  if (mode) ph_trial<L, true>(A, lane, alpha, soc, df, AL(F_MU), cold); else ph_trial<L, false>(A, lane, alpha, soc, df, AL(F_MU), cold);
+  al_count<L>(1, lane);
+}
+template <class L>
+__device__ __forceinline__ void do_accept(const SolveArgs& A, int lane, int mode, double alpha, double a_du, double dw, bool soc, bool reset, double* cold) {
+  if (mode) ph_accept<L, true>(A, lane, alpha, a_du, AL(F_MU), dw, soc, reset, cold); else ph_accept<L, false>(A, lane, alpha, a_du, AL(F_MU), dw, soc, reset, cold);
+}
+// objective and barrier pieces of the last trial point become those of the current point
+template <class L>
+__device__ __forceinline__ void take_trial_values() { AL(F_F) = RES(R_FT); AL(F_LB) = RES(R_LBT); AL(F_DT) = RES(R_DTT); }
+template <class L>
+__device__ __forceinline__ double trial_barrier(const SolveArgs& A) { const double mu = AL(F_MU); return RES(R_FT) - mu * RES(R_LBT) + A.o.kappa_d * mu * RES(R_DTT); }
+
+// ---- FilterLSAcceptor.  filter [FILT_CAP][2] = (barrier, theta) margins, in the cold scratch (a handful of loads per trial)
 __device__ __forceinline__ bool filter_ok(const double* filt, int nfilt, double barr, double theta) {
   for (int e = 0; e < nfilt; ++e) {
     const double fb = filt[2 * e], ft = filt[2 * e + 1];
@@ -977,6 +1028,7 @@ __device__ __forceinline__ bool filter_ok(const double* filt, int nfilt, double 
 // add (barr, theta), dropping the entries it dominates (and the oldest one if the filter is full); returns the new length
 static __device__ __noinline__ int filter_add(double* filt, int nfilt, double barr, double theta, int lane) {
   int n = 0;
+  __syncwarp();
   if (lane == 0) {
     for (int e = 0; e < nfilt; ++e) {
       const double fb = filt[2 * e], ft = filt[2 * e + 1];
@@ -989,14 +1041,237 @@ static __device__ __noinline__ int filter_add(double* filt, int nfilt, double ba
   __syncwarp();
   return n;
 }
+template <class L>
+__device__ __forceinline__ double* filter_of(double* cold, int mode) { return cold + L::CG_FILT + (mode ? 2 * FILT_CAP : 0); }
+template <class L>
+__device__ __forceinline__ void augment_filter(const SolveArgs& A, double* cold, int mode, int lane) {
+  const double rb = AL(F_RBARR), rt = AL(F_RTH);
+  const int n = filter_add(filter_of<L>(cold, mode), (int)AL(F_NFILT), rb - A.o.gamma_phi * rt, (1.0 - A.o.gamma_theta) * rt, lane);
+  AL(F_NFILT) = (double)n;
+}
+template <class L>
+__device__ __forceinline__ void acceptor_reset() { AL(F_NFILT) = 0.0; AL(F_LASTREJ) = 0.0; AL(F_SUCC) = 0.0; }
+template <class L>
+__device__ __forceinline__ bool is_ftype(const SolveArgs& A, double at) {
+  const double rt = AL(F_RTH), rg = AL(F_RGBD);
+  if (rt == 0.0 && rg > 0.0 && rg < 100.0 * EPSM) return true;
+  return rg < 0.0 && at * n_pow(-rg, A.o.s_phi) > A.o.delta * n_pow(rt, A.o.s_theta);
+}
+template <class L>
+__device__ __forceinline__ bool armijo(const SolveArgs& A, double at, double tb) { const double rb = AL(F_RBARR); return cmp_le(tb - rb, A.o.eta_phi * at * AL(F_RGBD), rb); }
+__device__ __forceinline__ bool ok_to_current(const Opt& o, double rb, double rt, double tb, double tt, bool from_resto) {
+  if (!from_resto && tb > rb) {
+    const double basval = fabs(rb) > 10.0 ? log10(fabs(rb)) : 1.0;
+    if (log10(tb - rb) > o.obj_max_inc + basval) return false;
+  }
+  return cmp_le(tt, (1.0 - o.gamma_theta) * rt, rt) || cmp_le(tb - rb, -o.gamma_phi * rt, rb);
+}
+// FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
+template <class L>
+__device__ __noinline__ bool check_accept(const SolveArgs& A, double* cold, int mode, double at, double tb, double tt) {
+  const Opt& o = A.o;
+  if (!isfinite(tb) || !isfinite(tt)) return false;
+  const double rt = AL(F_RTH);
+  if (AL(F_THMAX) < 0.0) AL(F_THMAX) = (mode ? o.resto_theta_max_fact : o.theta_max_fact) * fmax(1.0, rt);
+  if (AL(F_THMIN) < 0.0) AL(F_THMIN) = o.theta_min_fact * fmax(1.0, rt);
+  if (AL(F_THMAX) > 0.0 && tt > AL(F_THMAX)) return false;
+  bool acc;
+  if (at > 0.0 && is_ftype<L>(A, at) && rt <= AL(F_THMIN)) acc = armijo<L>(A, at, tb);
+  else acc = ok_to_current(o, AL(F_RBARR), rt, tb, tt, false);
+  if (!acc) { AL(F_LASTREJ) = 0.0; return false; }
+  acc = filter_ok(filter_of<L>(cold, mode), (int)AL(F_NFILT), tb, tt);
+  if (!acc) AL(F_LASTREJ) = 1.0;
+  return acc;
+}
+
+// ---- watchdog (BacktrackingLineSearch::StartWatchDog / StopWatchDog) -------------------------------------------------
+template <class L>
+__device__ __noinline__ void wd_start(const SolveArgs& A, double* cold, int lane) {
+  al_count<L>(5, lane);
+  AL(F_INWD) = 1.0; AL(F_WTRIAL) = 0.0; AL(F_WAT) = AL(F_APR); AL(F_WDW) = AL(F_DW);
+  AL(F_WTH) = AL(F_RTH); AL(F_WBARR) = AL(F_RBARR); AL(F_WGBD) = AL(F_RGBD);
+  ph_slot<L>(cold, 0, true, AL(F_MODE) != 0.0, lane);
+}
+// restore the watchdog's reference iterate and its step; everything that belongs to the current point is recomputed
+template <class L>
+__device__ __noinline__ void wd_stop(const SolveArgs& A, double* cold, int lane, double df) {
+  const int mode = (int)AL(F_MODE);
+  const double dw = AL(F_WDW);
+  AL(F_INWD) = 0.0; AL(F_WSHORT) = 0.0; AL(F_DW) = dw;
+  ph_slot<L>(cold, 0, false, mode != 0, lane);
+  do_derivs<L>(A, lane, mode, df, dw, false, cold);
+  do_dir<L>(A, lane, mode, false, dw, cold);
+  AL(F_APR) = RES(R_APR); AL(F_ADU) = RES(R_ADU); AL(F_GBD) = RES(R_GBD); AL(F_THETA) = RES(R_THETA);
+  do_trial<L>(A, lane, mode, 0.0, false, df, cold);
+  take_trial_values<L>();
+  AL(F_PHI) = trial_barrier<L>(A);
+  AL(F_RTH) = AL(F_WTH); AL(F_RBARR) = AL(F_WBARR); AL(F_RGBD) = AL(F_WGBD);
+  __syncwarp();
+}
+
+// ---- BacktrackingLineSearch::TrySoftRestoStep with the current step (DU, DS): 0 rejected, 1 accepted by the primal-dual
+//      error test (the iterate has already MOVED to the new point, without kappa_Sigma reset), 2 accepted by the original
+//      criterion (not moved).  alpha = min(alpha_primal_max, alpha_dual_max) is returned for both step sizes.
+template <class L>
+__device__ __noinline__ int soft_step(const SolveArgs& A, double* cold, int lane, double df, int nzt, double& alpha) {
+  const Opt& o = A.o;
+  constexpr int mtot = L::R * L::S, nx_ = NU * L::N;
+  const int mode = (int)AL(F_MODE);
+  const double dw = AL(F_DW);
+  if (o.soft_resto_red == 0.0) return 0;
+  const double al = fmin(AL(F_APR), AL(F_ADU));
+  do_trial<L>(A, lane, mode, al, false, df, cold);
+  const double th_t = RES(R_THT), phi_t = trial_barrier<L>(A);
+  if (!isfinite(th_t) || !isfinite(phi_t)) return 0;
+  alpha = al;
+  if (check_accept<L>(A, cold, mode, 0.0, phi_t, th_t)) return 2;
+  const int nz = mode ? nzt + 2 * mtot : nzt;
+  const double nvar = (double)(nx_ + mtot + (mode ? 2 * mtot : 0));
+  const double ft = RES(R_FT), lbt = RES(R_LBT), dtt = RES(R_DTT);
+  do_derivs<L>(A, lane, mode, df, dw, true, cold);                       // 1-norm sums at the current point, current mu
+  const double cur_err = RES(R_DU1) / nvar + RES(R_THETA) / (double)mtot + RES(R_CO1) / (double)max(1, nz);
+  ph_slot<L>(cold, mode ? 2 : 1, true, mode != 0, lane);
+  do_accept<L>(A, lane, mode, al, al, dw, false, false, cold);
+  do_derivs<L>(A, lane, mode, df, dw, true, cold);
+  const double tr_err = RES(R_DU1) / nvar + RES(R_THETA) / (double)mtot + RES(R_CO1) / (double)max(1, nz);
+  __syncwarp();
+  if (lane == 0) { RES(R_FT) = ft; RES(R_LBT) = lbt; RES(R_DTT) = dtt; }
+  __syncwarp();
+  if (tr_err <= o.soft_resto_red * cur_err) { al_count<L>(6, lane); return 1; }
+  ph_slot<L>(cold, mode ? 2 : 1, false, mode != 0, lane);
+  do_derivs<L>(A, lane, mode, df, dw, false, cold);
+  return 0;
+}
+
+// ---- restoration phase --------------------------------------------------------------------------------------------------
+// MinC_1NrmRestorationPhase::PerformRestoration: park the original algorithm, start a fresh one on the restoration problem
+template <class L>
+__device__ __noinline__ void resto_enter(const SolveArgs& A, double* cold, int lane, double df) {
+  const Opt& o = A.o;
+  al_count<L>(3, lane);
+  ph_slot<L>(cold, 1, true, false, lane);
+  const double infpr = RES(R_PR);                 // max-norm of g - s at the current point (latest ph_derivs)
+  AL(F_INFPR) = infpr;
+  __syncwarp();
+  for (int f = lane; f < F_NALG; f += 32) cold[L::CG_PARK + f] = AL(f);
+  const double mu_r = fmax(AL(F_MU), infpr);
+  __syncwarp();
+  alg_init<L>(mu_r, o.tau_min, o.tol);
+  ph_resto_init<L>(A, lane, mu_r, cold);
+  AL(F_MODE) = 1.0;
+  ph_trial<L, true>(A, lane, 0.0, false, df, mu_r, cold);
+  take_trial_values<L>();
+  __syncwarp();
+}
+// RestoFilterConvergenceCheck at the current restoration iterate (E0 etc. of the restoration problem are passed in):
+// -1 continue, -2 acceptable to the original problem's filter, >= 0 failure status
+template <class L>
+__device__ __noinline__ int resto_check(const SolveArgs& A, double* cold, int lane, double df, int iter, double E0, double du_inf, double pr_inf, double pmax) {
+  const Opt& o = A.o;
+  int st = -1;
+  if (iter >= o.max_iter) return NMPC_MAXITER_EXCEEDED;
+  const double* park = cold + L::CG_PARK;
+  const double oth = RES(R_OTH), oinf = RES(R_OINF);
+  double infpr_max = fmax(o.kappa_resto * park[F_INFPR], fmin(o.tol, o.constr_viol_tol));
+  if (o.kappa_resto == 0.0) infpr_max = 0.0;
+  if (AL(F_FIRST) == 0.0 && !(oinf > infpr_max)) {
+    const double omu = park[F_MU];
+    ph_trial<L, false>(A, lane, 0.0, false, df, omu, cold);       // original objective and barrier terms at the restoration iterate
+    const double tb = RES(R_FT) - omu * RES(R_LBT) + o.kappa_d * omu * RES(R_DTT);
+    if (filter_ok(filter_of<L>(cold, 0), (int)park[F_NFILT], tb, oth) && ok_to_current(o, park[F_RBARR], park[F_RTH], tb, oth, true)) st = -2;
+  }
+  if (st == -1) {       // is the restoration problem itself solved?  then the original one is (locally) infeasible
+    const double tol = AL(F_TOL);
+    if (!isfinite(E0)) st = NMPC_INVALID_NUMBER;
+    else if (E0 <= tol && du_inf / df <= o.dual_inf_tol && pr_inf <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
+      if (oinf <= 1e2 * tol) {
+        if (tol > 1e-1 * o.tol) AL(F_TOL) = 1e-2 * tol;       // tighten once: the problem is only very slightly infeasible
+        else st = NMPC_RESTORATION_FAILED;                     // converged to a feasible point the original filter does not accept
+      } else st = NMPC_INFEASIBLE_PROBLEM;
+    }
+  }
+  AL(F_FIRST) = 0.0;
+  return st;
+}
+// back to the original problem: x, s from the restoration phase, new bound multipliers, y = 0
+template <class L>
+__device__ __noinline__ void resto_leave(const SolveArgs& A, double* cold, int lane, double df) {
+  const Opt& o = A.o;
+  __syncwarp();
+  for (int f = lane; f < F_NALG; f += 32) AL(f) = cold[L::CG_PARK + f];
+  AL(F_MODE) = 0.0;
+  __syncwarp();
+  const double mu = AL(F_MU), tau = AL(F_TAU);
+  const double adu = ph_resto_finish<L>(A, lane, mu, tau, 0.0, 0, cold, 1);
+  const double zmax = ph_resto_finish<L>(A, lane, mu, tau, adu, 1, cold, 1);
+  if (zmax > o.bound_mult_reset_threshold) ph_unit_mults<L>(A, lane);
+  ph_accept<L, false>(A, lane, 0.0, 0.0, mu, 0.0, false, true, cold);      // kappa_Sigma reset (AcceptTrialPoint)
+  ph_trial<L, false>(A, lane, 0.0, false, df, mu, cold);
+  take_trial_values<L>();
+  AL(F_INSOFT) = 0.0; AL(F_SOFTC) = 0.0; AL(F_WSHORT) = 0.0;
+  __syncwarp();
+}
+// restoration inside the restoration phase (RestoRestorationPhase): n, p from their closed form, duals unchanged
+template <class L>
+__device__ __noinline__ void resto_inner(const SolveArgs& A, double* cold, int lane, double df) {
+  ph_resto_np<L>(A, lane, AL(F_MU), cold);
+  AL(F_INSOFT) = 0.0; AL(F_SOFTC) = 0.0; AL(F_WSHORT) = 0.0;
+  if (lane <= L::N) {
+    for (int r = 0; r < L::R; ++r) RW(A_DS, r) = 0.0;
+    for (int i = 0; i < 6; ++i) LV(LV_DU + i) = 0.0;
+  }
+  __syncwarp();
+  do_trial<L>(A, lane, 1, 0.0, false, df, cold);
+}
+
+// MonotoneMuUpdate (with fast decrease).  The error ingredients of the current point are passed by reference because the
+// restoration objective depends on mu (eta = sqrt(mu)): they are refreshed when mu changes in restoration mode.
+// Returns false when a tiny step can no longer be answered by a smaller mu (TINY_STEP_DETECTED).
+template <class L>
+__device__ __noinline__ bool update_mu(const SolveArgs& A, double* cold, int lane, double df, int nz, double mu_floor,
+                                       double& du_inf, double& pr_inf, double& pmax, double& pmin, double& sd, double& sc) {
+  const Opt& o = A.o;
+  constexpr int mtot = L::R * L::S;
+  const int mode = (int)AL(F_MODE);
+  bool tf = AL(F_TINYFLAG) != 0.0;
+  AL(F_TINYFLAG) = 0.0;
+  if (mode && AL(F_MUST) == 0.0) { AL(F_MUST) = 1.0; return true; }       // first restoration iteration: mu comes from the initializer
+  AL(F_MUST) = 1.0;
+  double mu = AL(F_MU);
+  auto emu = [&](double m) { return fmax(du_inf / sd, fmax(pr_inf, fmax(pmax - m, m - pmin) / sc)); };
+  double Emu = emu(mu);
+  bool done = false;
+  while ((Emu <= o.kappa_eps * mu || tf) && !done) {
+    const double nm = fmax(mu_floor, fmin(o.kappa_mu * mu, n_pow(mu, o.theta_mu)));
+    const bool changed = nm != mu;
+    if (!changed && tf) return false;
+    if (!changed) break;
+    mu = nm;
+    AL(F_MU) = mu; AL(F_TAU) = fmax(o.tau_min, 1.0 - mu);
+    if (mode) {
+      __syncwarp();
+      do_derivs<L>(A, lane, 1, df, 0.0, false, cold);
+      du_inf = RES(R_DU); pr_inf = RES(R_PR); pmax = RES(R_PMAX); pmin = RES(R_PMIN);
+      const double sumy = RES(R_SUMY), sumz = RES(R_SUMZ);
+      sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nz)) / o.s_max;
+      sc = fmax(o.s_max, sumz / (double)max(1, nz)) / o.s_max;
+      ph_trial<L, true>(A, lane, 0.0, false, df, mu, cold);
+      take_trial_values<L>();
+    }
+    if (tf) { done = true; tf = false; }
+    else { Emu = emu(mu); done = !(Emu <= o.kappa_eps * mu); }
+    AL(F_INSOFT) = 0.0; AL(F_SOFTC) = 0.0; acceptor_reset<L>();        // linesearch->Reset()
+  }
+  return true;
+}
 
 template <class L>
 __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, double* cold, int b, int lane) {
   const Prob& pr = A.pr; const Opt& o = A.o;
   constexpr int S = L::S, R = L::R;
   constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(3 * R), Q20 = L::soc(3 * R + 6);
+  constexpr int mtot = R * S;
   const double T = pr.T;
-  unsigned long long n_fact = 0, n_ls = 0, n_soc = 0, n_resto = 0, n_resto_it = 0, n_wd = 0, n_soft = 0, n_freset = 0;
 
   ph_load<L>(A, b, lane);
   double df = 1.0;
@@ -1007,282 +1282,154 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     __syncwarp();
   }
   const int nzt = ph_start<L>(A, lane);
-  Alg a, ao;                                       // running algorithm; parked original algorithm during restoration
-  alg_init(a, o.mu_init, o.tau_min, o.tol); alg_init(ao, o.mu_init, o.tau_min, o.tol);
-  ph_trial<L, false>(A, lane, 0.0, false, df, a.mu, cold);          // barrier pieces and constraint violation of the start
-  a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
+  alg_init<L>(o.mu_init, o.tau_min, o.tol);
+  for (int f = F_NALG + lane; f < F_END; f += 32) AL(f) = 0.0;
+  __syncwarp();
+  ph_trial<L, false>(A, lane, 0.0, false, df, o.mu_init, cold);      // barrier pieces and constraint violation of the start
+  take_trial_values<L>();
   const double mu_floor = fmin(o.tol, df * o.compl_inf_tol) / (o.kappa_eps + 1.0);
-  int iter = 0, status = NMPC_MAXITER_EXCEEDED, mode = 0; bool ls = true;
-  constexpr int mtot = R * S, nx_ = NU * L::N;
-  double* filt1 = cold + L::CG_FILT;
+  int iter = 0, status = NMPC_MAXITER_EXCEEDED;
 
-  // mode-dispatched phases
-  auto derivs = [&](double dw_) { if (mode) ph_derivs<L, true>(A, lane, false, df, a.mu, dw_, cold); else ph_derivs<L, false>(A, lane, false, df, a.mu, dw_, cold); };
-  auto dirs = [&](bool soc_, double dw_) { if (mode) ph_dir<L, true>(A, lane, a.mu, a.tau, soc_, dw_, cold); else ph_dir<L, false>(A, lane, a.mu, a.tau, soc_, dw_, cold); };
-  auto trial = [&](double al, bool soc_) { if (mode) ph_trial<L, true>(A, lane, al, soc_, df, a.mu, cold); else ph_trial<L, false>(A, lane, al, soc_, df, a.mu, cold); ++n_ls; };
-  auto accept_ = [&](double al, double adu, double dw_, bool soc_, bool reset) {
-    if (mode) ph_accept<L, true>(A, lane, al, adu, a.mu, dw_, soc_, reset, cold); else ph_accept<L, false>(A, lane, al, adu, a.mu, dw_, soc_, reset, cold);
-  };
-  auto filt = [&]() -> double* { return mode ? filt1 : &smem[L::FILT0]; };
-  auto barr_of = [&]() { return RES(R_FT) - a.mu * RES(R_LBT) + o.kappa_d * a.mu * RES(R_DTT); };
-  // FilterLSAcceptor
-  auto is_ftype = [&](double at) {
-    if (a.ref_theta == 0.0 && a.ref_gbd > 0.0 && a.ref_gbd < 100.0 * EPSM) return true;
-    return a.ref_gbd < 0.0 && at * n_pow(-a.ref_gbd, o.s_phi) > o.delta * n_pow(a.ref_theta, o.s_theta);
-  };
-  auto armijo = [&](double at, double tb) { return cmp_le(tb - a.ref_barr, o.eta_phi * at * a.ref_gbd, a.ref_barr); };
-  auto ok_to_current = [&](const Alg& q, double tb, double tt_, bool from_resto) {
-    if (!from_resto && tb > q.ref_barr) {
-      const double basval = fabs(q.ref_barr) > 10.0 ? log10(fabs(q.ref_barr)) : 1.0;
-      if (log10(tb - q.ref_barr) > o.obj_max_inc + basval) return false;
-    }
-    return cmp_le(tt_, (1.0 - o.gamma_theta) * q.ref_theta, q.ref_theta) || cmp_le(tb - q.ref_barr, -o.gamma_phi * q.ref_theta, q.ref_barr);
-  };
-  auto check_accept = [&](double at, double tb, double tt_) {
-    if (!isfinite(tb) || !isfinite(tt_)) return false;
-    if (a.theta_max < 0.0) a.theta_max = (mode ? o.resto_theta_max_fact : o.theta_max_fact) * fmax(1.0, a.ref_theta);
-    if (a.theta_min < 0.0) a.theta_min = o.theta_min_fact * fmax(1.0, a.ref_theta);
-    if (a.theta_max > 0.0 && tt_ > a.theta_max) return false;
-    bool acc;
-    if (at > 0.0 && is_ftype(at) && a.ref_theta <= a.theta_min) acc = armijo(at, tb);
-    else acc = ok_to_current(a, tb, tt_, false);
-    if (!acc) { a.last_rej_filter = false; return false; }
-    acc = filter_ok(filt(), a.nfilt, tb, tt_);
-    if (!acc) a.last_rej_filter = true;
-    return acc;
-  };
-  auto augment = [&]() { a.nfilt = filter_add(filt(), a.nfilt, a.ref_barr - o.gamma_phi * a.ref_theta, (1.0 - o.gamma_theta) * a.ref_theta, lane); };
-  auto acceptor_reset = [&]() { a.nfilt = 0; a.last_rej_filter = false; a.succ_rej = 0; };
-
+  {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
+    align_warps(A.align_group, 1);
+    ph_derivs<L, false>(A, lane, true, df, o.mu_init, 0.0, false, cold);
+    al_count<L>(0, lane);
+    const bool ok = riccati_factor<L>(T, ric, A.ricmap, 1.0, 0.0, lane);
+    if (ok) riccati_forward<L>(T, ric, false, lane, DX0, DU0);
+    ph_lsy<L>(A, lane, ok);
+  }
   for (;;) {
     // Alignment point: the warps of a block start every IPM iteration together, so that they walk through the
     // same ~200 KB of phase code at the same time and share instruction-cache lines (unaligned warps thrash it:
     // `no_instruction` was 56 % of all stall cycles in v3).  Pure scheduling; results cannot depend on it.
     align_warps(A.align_group, 1);
-    if (ls) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
-      ph_derivs<L, false>(A, lane, true, df, a.mu, 0.0, cold);
-      ++n_fact;
-      const bool ok = riccati_factor<L>(T, ric, A.ricmap, 1.0, 0.0, lane);
-      if (ok) riccati_forward<L>(T, ric, false, lane, DX0, DU0);
-      ph_lsy<L>(A, lane, ok);
-      ls = false;
-      continue;
-    }
-    derivs(0.0);
+    int mode = (int)AL(F_MODE);
+    do_derivs<L>(A, lane, mode, df, 0.0, false, cold);
     // ---- optimality error (scaled) and termination
-    double du_inf = RES(R_DU), pr_inf = RES(R_PR), sumy = RES(R_SUMY), sumz = RES(R_SUMZ), viol = RES(R_VIOL);
-    double pmax = RES(R_PMAX), pmin = RES(R_PMIN);
+    double du_inf = RES(R_DU), pr_inf = RES(R_PR), pmax = RES(R_PMAX), pmin = RES(R_PMIN);
     const int nz = mode ? nzt + 2 * mtot : nzt;
-    double sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nz)) / o.s_max;
-    double sc = fmax(o.s_max, sumz / (double)max(1, nz)) / o.s_max;
+    double sd, sc;
+    {
+      const double sumy = RES(R_SUMY), sumz = RES(R_SUMZ);
+      sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nz)) / o.s_max;
+      sc = fmax(o.s_max, sumz / (double)max(1, nz)) / o.s_max;
+    }
     const double E0 = fmax(du_inf / sd, fmax(pr_inf, pmax / sc));
     if (mode == 0) {
-      if (!isfinite(E0) || !isfinite(a.f)) { status = NMPC_INVALID_NUMBER; break; }
-      if (E0 <= o.tol && du_inf / df <= o.dual_inf_tol && viol <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
+      if (!isfinite(E0) || !isfinite(AL(F_F))) { status = NMPC_INVALID_NUMBER; break; }
+      if (E0 <= o.tol && du_inf / df <= o.dual_inf_tol && RES(R_VIOL) <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
         status = NMPC_SOLVE_SUCCEEDED; break;
       }
       if (iter >= o.max_iter) { status = NMPC_MAXITER_EXCEEDED; break; }
     } else {
-      // RestoFilterConvergenceCheck: is the current restoration iterate acceptable to the ORIGINAL problem's filter?
-      int st = -1;                                  // -1 continue, -2 success, >= 0 failure status
-      if (iter >= o.max_iter) st = NMPC_MAXITER_EXCEEDED;
-      else {
-        const double oth = RES(R_OTH), oinf = RES(R_OINF);
-        double infpr_max = fmax(o.kappa_resto * ao.infpr, fmin(o.tol, o.constr_viol_tol));
-        if (o.kappa_resto == 0.0) infpr_max = 0.0;
-        if (!a.first_iter && !(oinf > infpr_max)) {
-          ph_trial<L, false>(A, lane, 0.0, false, df, ao.mu, cold);       // original objective and barrier terms at the restoration iterate
-          const double tb = RES(R_FT) - ao.mu * RES(R_LBT) + o.kappa_d * ao.mu * RES(R_DTT);
-          if (filter_ok(&smem[L::FILT0], ao.nfilt, tb, oth) && ok_to_current(ao, tb, oth, true)) st = -2;
-        }
-        if (st == -1) {       // is the restoration problem itself solved?  then the original one is (locally) infeasible
-          if (!isfinite(E0)) st = NMPC_INVALID_NUMBER;
-          else if (E0 <= a.tol && du_inf / df <= o.dual_inf_tol && pr_inf <= o.constr_viol_tol && pmax / df <= o.compl_inf_tol) {
-            if (oinf <= 1e2 * a.tol) {
-              if (a.tol > 1e-1 * o.tol) a.tol *= 1e-2;       // tighten once: the problem is only very slightly infeasible
-              else st = NMPC_RESTORATION_FAILED;              // converged to a feasible point the original filter does not accept
-            } else st = NMPC_INFEASIBLE_PROBLEM;
-          }
-        }
-        a.first_iter = false;
-      }
-      if (st == -2) {        // back to the original problem: x, s from the restoration phase, new bound multipliers, y = 0
-        a = ao; mode = 0;
-        const double adu = ph_resto_finish<L>(A, lane, a.mu, a.tau, 0.0, 0, cold, 1);
-        const double zmax = ph_resto_finish<L>(A, lane, a.mu, a.tau, adu, 1, cold, 1);
-        if (zmax > o.bound_mult_reset_threshold) ph_unit_mults<L>(A, lane);
-        ph_accept<L, false>(A, lane, 0.0, 0.0, a.mu, 0.0, false, true, cold);      // kappa_Sigma reset (AcceptTrialPoint)
-        ph_trial<L, false>(A, lane, 0.0, false, df, a.mu, cold);
-        a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
-        a.in_soft = false; a.soft_cnt = 0; a.wd_short = 0;
-        continue;
-      }
+      const int st = resto_check<L>(A, cold, lane, df, iter, E0, du_inf, pr_inf, pmax);
+      if (st == -2) { resto_leave<L>(A, cold, lane, df); continue; }
       if (st >= 0) { status = st; break; }
     }
-    // ---- barrier parameter (MonotoneMuUpdate, with fast decrease)
-    {
-      bool tf = a.tiny_flag, tiny_exit = false; a.tiny_flag = false;
-      auto emu = [&](double m) { return fmax(du_inf / sd, fmax(pr_inf, fmax(pmax - m, m - pmin) / sc)); };
-      if (mode && !a.mu_started) a.mu_started = true;        // first restoration iteration: mu comes from the initializer
-      else {
-        a.mu_started = true;
-        double Emu = emu(a.mu);
-        bool done = false;
-        while ((Emu <= o.kappa_eps * a.mu || tf) && !done) {
-          const double nm = fmax(mu_floor, fmin(o.kappa_mu * a.mu, n_pow(a.mu, o.theta_mu)));
-          const bool changed = nm != a.mu;
-          if (!changed && tf) { tiny_exit = true; break; }     // TINY_STEP_DETECTED: solved to best possible accuracy
-          if (!changed) break;
-          a.mu = nm; a.tau = fmax(o.tau_min, 1.0 - a.mu);
-          if (mode) {     // the restoration objective depends on mu (eta = sqrt(mu)): refresh gradient and error ingredients
-            derivs(0.0);
-            du_inf = RES(R_DU); pr_inf = RES(R_PR); sumy = RES(R_SUMY); sumz = RES(R_SUMZ); pmax = RES(R_PMAX); pmin = RES(R_PMIN);
-            sd = fmax(o.s_max, (sumy + sumz) / (double)max(1, mtot + nz)) / o.s_max;
-            sc = fmax(o.s_max, sumz / (double)max(1, nz)) / o.s_max;
-            ph_trial<L, true>(A, lane, 0.0, false, df, a.mu, cold); a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
-          }
-          if (tf) { done = true; tf = false; }
-          else { Emu = emu(a.mu); done = !(Emu <= o.kappa_eps * a.mu); }
-          a.in_soft = false; a.soft_cnt = 0; acceptor_reset();        // linesearch->Reset()
-        }
-      }
-      if (tiny_exit) {
-        if (mode == 0) status = NMPC_STEP_TOO_SMALL;
-        else status = RES(R_OINF) <= 1e2 * o.tol ? NMPC_RESTORATION_FAILED : NMPC_INFEASIBLE_PROBLEM;
-        break;
-      }
+    // ---- barrier parameter
+    if (!update_mu<L>(A, cold, lane, df, nz, mu_floor, du_inf, pr_inf, pmax, pmin, sd, sc)) {
+      if (mode == 0) status = NMPC_STEP_TOO_SMALL;
+      else status = RES(R_OINF) <= 1e2 * o.tol ? NMPC_RESTORATION_FAILED : NMPC_INFEASIBLE_PROBLEM;
+      break;
     }
+    const double mu = AL(F_MU);
     // ---- search direction with inertia correction
-    const unsigned long long ls_before = n_ls;
+    const double ls_before = AL(F_C0 + 1);
     double dw = 0.0; bool ok = false;
-    for (;;) {
-      ++n_fact;
-      ok = riccati_factor<L>(T, ric, A.ricmap, a.mu, dw, lane);
-      if (ok) break;
-      if (dw == 0.0) dw = (a.dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, a.dw_last * o.dw_dec);
-      else dw = (a.dw_last == 0.0 || 1e5 * a.dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
-      if (dw > o.dw_max) break;
-      if (mode) derivs(dw);                 // restoration rows enter with Om(dw)
+    {
+      const double dw_last = AL(F_DWLAST);
+      for (;;) {
+        al_count<L>(0, lane);
+        ok = riccati_factor<L>(T, ric, A.ricmap, mu, dw, lane);
+        if (ok) break;
+        if (dw == 0.0) dw = (dw_last == 0.0) ? o.dw_init : fmax(o.dw_min, dw_last * o.dw_dec);
+        else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
+        if (dw > o.dw_max) break;
+        if (mode) ph_derivs<L, true>(A, lane, false, df, mu, dw, false, cold);       // restoration rows enter with Om(dw)
+      }
     }
     bool goto_resto = !ok;                  // step computation failed: fall back to the restoration phase
     if (ok) {
-      if (dw > 0.0) a.dw_last = dw;
+      if (dw > 0.0) AL(F_DWLAST) = dw;
       riccati_forward<L>(T, ric, false, lane, DX0, DU0);
-      dirs(false, dw);
+      do_dir<L>(A, lane, mode, false, dw, cold);
     }
-    double a_pr_max = RES(R_APR), a_du = RES(R_ADU), gbd = RES(R_GBD), theta = RES(R_THETA);
-    double phi = a.f - a.mu * a.LB + o.kappa_d * a.mu * a.DT;
+    AL(F_DW) = dw; AL(F_APR) = RES(R_APR); AL(F_ADU) = RES(R_ADU); AL(F_GBD) = RES(R_GBD); AL(F_THETA) = RES(R_THETA);
+    AL(F_PHI) = AL(F_F) - mu * AL(F_LB) + o.kappa_d * mu * AL(F_DT);
     // ---- BacktrackingLineSearch::FindAcceptableTrialPoint
     // InitThisLineSearch (+ the filter reset heuristic)
-    if (!a.in_wd) {
-      if (o.max_filter_resets > 0 && a.n_resets < o.max_filter_resets) {
-        if (a.last_rej_filter) { if (++a.succ_rej >= o.filter_reset_trigger) { acceptor_reset(); ++a.n_resets; ++n_freset; } }
-        else a.succ_rej = 0;
+    if (AL(F_INWD) == 0.0) {
+      if (o.max_filter_resets > 0 && AL(F_NRES) < (double)o.max_filter_resets) {
+        if (AL(F_LASTREJ) != 0.0) {
+          if (al_add<L>(F_SUCC, 1.0) >= (double)o.filter_reset_trigger) { acceptor_reset<L>(); al_add<L>(F_NRES, 1.0); al_count<L>(7, lane); }
+        } else AL(F_SUCC) = 0.0;
       }
-      a.last_rej_filter = false;
-      a.ref_theta = theta; a.ref_barr = phi; a.ref_gbd = gbd;
-    } else { a.ref_theta = a.wd_theta; a.ref_barr = a.wd_barr; a.ref_gbd = a.wd_gbd; }
-    bool tiny = !goto_resto && RES(R_TINY) != 0.0 && theta <= 1e-4;
-    // restore the watchdog's reference iterate and its step; everything that belongs to the current point is recomputed
-    auto stop_watchdog = [&]() {
-      a.in_wd = false; a.wd_short = 0; dw = a.wd_dw;
-      ph_slot<L>(cold, 0, false, mode != 0, lane);
-      derivs(dw); dirs(false, dw);
-      a_pr_max = RES(R_APR); a_du = RES(R_ADU); gbd = RES(R_GBD); theta = RES(R_THETA);
-      trial(0.0, false); a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
-      phi = a.f - a.mu * a.LB + o.kappa_d * a.mu * a.DT;
-      a.ref_theta = a.wd_theta; a.ref_barr = a.wd_barr; a.ref_gbd = a.wd_gbd;
-    };
-    if (a.in_wd && (goto_resto || tiny)) { stop_watchdog(); goto_resto = false; tiny = false; }
-    if (o.watchdog_trigger > 0 && !a.in_wd && !goto_resto && !tiny && !a.in_soft && a.wd_short >= o.watchdog_trigger) {
-      ++n_wd;                                  // StartWatchDog
-      a.in_wd = true; a.wd_trial = 0; a.wd_alpha_test = a_pr_max; a.wd_dw = dw;
-      a.wd_theta = a.ref_theta; a.wd_barr = a.ref_barr; a.wd_gbd = a.ref_gbd;
-      ph_slot<L>(cold, 0, true, mode != 0, lane);
-    }
-    double alpha = a_pr_max, phi_t = 0.0, th_t = 0.0;
+      AL(F_LASTREJ) = 0.0;
+      AL(F_RTH) = AL(F_THETA); AL(F_RBARR) = AL(F_PHI); AL(F_RGBD) = AL(F_GBD);
+    } else { AL(F_RTH) = AL(F_WTH); AL(F_RBARR) = AL(F_WBARR); AL(F_RGBD) = AL(F_WGBD); }
+    bool tiny = !goto_resto && RES(R_TINY) != 0.0 && AL(F_THETA) <= 1e-4;
+    if (AL(F_INWD) != 0.0 && (goto_resto || tiny)) { wd_stop<L>(A, cold, lane, df); dw = AL(F_DW); goto_resto = false; tiny = false; }
+    if (o.watchdog_trigger > 0 && AL(F_INWD) == 0.0 && !goto_resto && !tiny && AL(F_INSOFT) == 0.0 && AL(F_WSHORT) >= (double)o.watchdog_trigger)
+      wd_start<L>(A, cold, lane);
+    double alpha = AL(F_APR), a_du = AL(F_ADU), phi_t = 0.0, th_t = 0.0;
     bool accepted = false, used_soc = false, moved = false;     // moved: the iterate already sits at the new point (soft restoration step)
     int n_steps = 0, tag = '?';
     if (tiny) {
-      trial(alpha, false);
-      if (!isfinite(RES(R_THT)) || !isfinite(barr_of())) { status = NMPC_INVALID_NUMBER; break; }
-      if (a.tiny_last) { a.tiny_flag = true; tag = 'T'; } else tag = 't';
-      a.tiny_last = RES(R_DYMAX) < o.tiny_step_y_tol;
+      do_trial<L>(A, lane, mode, alpha, false, df, cold);
+      if (!isfinite(RES(R_THT)) || !isfinite(trial_barrier<L>(A))) { status = NMPC_INVALID_NUMBER; break; }
+      if (AL(F_TINYLAST) != 0.0) { AL(F_TINYFLAG) = 1.0; tag = 'T'; } else tag = 't';
+      AL(F_TINYLAST) = RES(R_DYMAX) < o.tiny_step_y_tol ? 1.0 : 0.0;
       accepted = true;
-    } else a.tiny_last = false;
-    // BacktrackingLineSearch::TrySoftRestoStep with the current step (DU, DS)
-    auto try_soft = [&](bool& sat) {
-      sat = false;
-      if (o.soft_resto_red == 0.0) return false;
-      const double al = fmin(a_pr_max, a_du);
-      trial(al, false);
-      th_t = RES(R_THT); phi_t = barr_of();
-      if (!isfinite(th_t) || !isfinite(phi_t)) return false;
-      alpha = al; a_du = al;
-      if (check_accept(0.0, phi_t, th_t)) { sat = true; return true; }
-      const double nvar = (double)(nx_ + mtot + (mode ? 2 * mtot : 0));
-      const double ft = RES(R_FT), lbt = RES(R_LBT), dtt = RES(R_DTT);
-      derivs(dw);                                       // complementarity sums with the current mu
-      const double cur_err = RES(R_DU1) / nvar + RES(R_THETA) / (double)mtot + RES(R_CO1) / (double)max(1, nz);
-      ph_slot<L>(cold, mode ? 2 : 1, true, mode != 0, lane);
-      accept_(al, al, dw, false, false);
-      derivs(dw);
-      const double tr_err = RES(R_DU1) / nvar + RES(R_THETA) / (double)mtot + RES(R_CO1) / (double)max(1, nz);
-      if (lane == 0) { RES(R_FT) = ft; RES(R_LBT) = lbt; RES(R_DTT) = dtt; }
-      __syncwarp();
-      if (tr_err <= o.soft_resto_red * cur_err) { moved = true; ++n_soft; return true; }
-      ph_slot<L>(cold, mode ? 2 : 1, false, mode != 0, lane);
-      derivs(dw);
-      return false;
-    };
+    } else AL(F_TINYLAST) = 0.0;
     if (!goto_resto && !tiny) {
-      if (a.in_soft) {
-        if (++a.soft_cnt > o.max_soft_resto) accepted = false;
+      if (AL(F_INSOFT) != 0.0) {
+        if (al_add<L>(F_SOFTC, 1.0) > (double)o.max_soft_resto) accepted = false;
         else {
-          bool sat = false;
-          accepted = try_soft(sat);
-          if (accepted) { tag = 's'; if (sat) { a.in_soft = false; a.soft_cnt = 0; tag = 'S'; } }
+          const int r = soft_step<L>(A, cold, lane, df, nzt, alpha);
+          accepted = r != 0; moved = r == 1; a_du = alpha;
+          if (accepted) { tag = 's'; if (r == 2) { AL(F_INSOFT) = 0.0; AL(F_SOFTC) = 0.0; tag = 'S'; } }
         }
       } else {
         bool skip_first = false;
         for (;;) {       // DoBacktrackingLineSearch (repeated once when the watchdog is stopped)
           bool eval_err = false; accepted = false;
-          const double a_max = a_pr_max;
+          const bool in_wd = AL(F_INWD) != 0.0;
+          const double a_max = AL(F_APR), gbd = AL(F_GBD), theta = AL(F_THETA), ref_theta = AL(F_RTH);
           double amin = a_max;
-          if (!a.in_wd) {
+          if (!in_wd) {
             amin = o.gamma_theta;
             if (gbd < 0.0) {
               amin = fmin(o.gamma_theta, o.gamma_phi * theta / (-gbd));
-              if (theta <= a.theta_min) amin = fmin(amin, o.delta * n_pow(theta, o.s_theta) / n_pow(-gbd, o.s_phi));
+              if (theta <= AL(F_THMIN)) amin = fmin(amin, o.delta * n_pow(theta, o.s_theta) / n_pow(-gbd, o.s_phi));
             }
             amin *= o.alpha_min_frac;
           }
-          alpha = a_max;
-          double a_test = a.in_wd ? a.wd_alpha_test : alpha;
+          alpha = a_max; a_du = AL(F_ADU);
+          double a_test = in_wd ? AL(F_WAT) : alpha;
           if (skip_first) alpha *= o.alpha_red;
           while (alpha > amin || n_steps == 0) {
-            trial(alpha, false);
-            th_t = RES(R_THT); phi_t = barr_of();
+            do_trial<L>(A, lane, mode, alpha, false, df, cold);
+            th_t = RES(R_THT); phi_t = trial_barrier<L>(A);
             const bool okv = isfinite(th_t) && isfinite(phi_t);
-            if (!a.in_wd) a_test = alpha;
-            if (okv) accepted = check_accept(a_test, phi_t, th_t); else { accepted = false; eval_err = true; }
-            if (accepted || a.in_wd) break;
-            if (okv && alpha == a_max && a.ref_theta <= th_t && o.max_soc > 0) {
+            if (!in_wd) a_test = alpha;
+            if (okv) accepted = check_accept<L>(A, cold, mode, a_test, phi_t, th_t); else { accepted = false; eval_err = true; }
+            if (accepted || in_wd) break;
+            if (okv && alpha == a_max && ref_theta <= th_t && o.max_soc > 0) {
               // second-order correction (FilterLSAcceptor::TrySecondOrderCorrection)
               int count = 0; double theta_old = 0.0, theta_trial = th_t, a_soc = alpha; bool first = true;
               while (count < o.max_soc && !accepted && (count == 0 || theta_trial <= o.kappa_soc * theta_old)) {
                 theta_old = theta_trial;
-                if (mode) ph_socrhs<L, true>(A, lane, a_soc, a.mu, dw, first, cold); else ph_socrhs<L, false>(A, lane, a_soc, a.mu, dw, first, cold);
+                if (mode) ph_socrhs<L, true>(A, lane, a_soc, mu, dw, first, cold); else ph_socrhs<L, false>(A, lane, a_soc, mu, dw, first, cold);
                 first = false;
-                riccati_resolve<L>(T, Q20, ric, a.mu, lane);
+                riccati_resolve<L>(T, Q20, ric, mu, lane);
                 riccati_forward<L>(T, ric, true, lane, DX0, DUS0);
-                dirs(true, dw);
+                do_dir<L>(A, lane, mode, true, dw, cold);
                 a_soc = RES(R_APR);
-                trial(a_soc, true);
-                th_t = RES(R_THT); phi_t = barr_of();
+                do_trial<L>(A, lane, mode, a_soc, true, df, cold);
+                th_t = RES(R_THT); phi_t = trial_barrier<L>(A);
                 if (!isfinite(th_t) || !isfinite(phi_t)) break;
-                accepted = check_accept(a_test, phi_t, th_t);
-                if (accepted) { alpha = a_soc; used_soc = true; ++n_soc; }
+                accepted = check_accept<L>(A, cold, mode, a_test, phi_t, th_t);
+                if (accepted) { alpha = a_soc; a_du = RES(R_ADU); used_soc = true; al_count<L>(2, lane); }
                 else { ++count; theta_trial = th_t; }
               }
               if (accepted) break;
@@ -1290,11 +1437,12 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
             alpha *= o.alpha_red; ++n_steps;
           }
           if (accepted) {      // UpdateForNextIteration
-            if (!is_ftype(a_test) || !armijo(a_test, phi_t)) { augment(); tag = used_soc ? 'H' : 'h'; } else tag = used_soc ? 'F' : 'f';
-          } else if (a.in_wd) tag = 'w';
-          if (a.in_wd) {
-            if (accepted) { a.in_wd = false; break; }
-            if (eval_err || ++a.wd_trial > o.watchdog_trial_max) { stop_watchdog(); skip_first = true; continue; }
+            if (!is_ftype<L>(A, a_test) || !armijo<L>(A, a_test, phi_t)) { augment_filter<L>(A, cold, mode, lane); tag = used_soc ? 'H' : 'h'; }
+            else tag = used_soc ? 'F' : 'f';
+          } else if (in_wd) tag = 'w';
+          if (in_wd) {
+            if (accepted) { AL(F_INWD) = 0.0; break; }
+            if (eval_err || al_add<L>(F_WTRIAL, 1.0) > (double)o.watchdog_trial_max) { wd_stop<L>(A, cold, lane, df); dw = AL(F_DW); skip_first = true; continue; }
             accepted = true; break;        // take the step without acceptance test
           }
           break;
@@ -1303,64 +1451,39 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     }
     bool entered_resto = false;
     if (!accepted) {
-      if (!a.in_soft && !goto_resto) {      // try the current direction as a soft restoration step
-        augment();                           // PrepareRestoPhaseStart
-        bool sat = false;
-        accepted = try_soft(sat);
-        if (accepted) { if (sat) tag = 'S'; else { a.in_soft = true; tag = 's'; } }
+      if (AL(F_INSOFT) == 0.0 && !goto_resto) {      // try the current direction as a soft restoration step
+        augment_filter<L>(A, cold, mode, lane);       // PrepareRestoPhaseStart
+        const int r = soft_step<L>(A, cold, lane, df, nzt, alpha);
+        accepted = r != 0; moved = r == 1; a_du = alpha; used_soc = false;
+        if (accepted) { if (r == 2) tag = 'S'; else { AL(F_INSOFT) = 1.0; tag = 's'; } }
       }
       if (!accepted) {
-        if (!a.in_soft) augment();
-        if (theta <= 1e-2 * o.tol || !o.resto) {       // "Restoration phase called, but point is almost feasible"
-          status = NMPC_RESTORATION_FAILED;
-          break;
-        }
+        if (AL(F_INSOFT) == 0.0) augment_filter<L>(A, cold, mode, lane);
+        if (AL(F_THETA) <= 1e-2 * o.tol || !o.resto) { status = NMPC_RESTORATION_FAILED; break; }    // "... called, but point is almost feasible"
         tag = 'R';
-        if (mode) {     // restoration inside the restoration phase: n, p from their closed form, duals unchanged
-          ph_resto_np<L>(A, lane, a.mu, cold);
-          alpha = 0.0; a_du = 0.0; moved = false; used_soc = false;
-          a.in_soft = false; a.soft_cnt = 0; a.wd_short = 0;
-          accepted = true;
-          if (lane <= L::N) { for (int r = 0; r < R; ++r) RW(A_DS, r) = 0.0; for (int i = 0; i < 6; ++i) LV(LV_DU + i) = 0.0; }
-          __syncwarp();
-          trial(0.0, false);
-        } else entered_resto = true;
+        if (mode) { resto_inner<L>(A, cold, lane, df); alpha = 0.0; a_du = 0.0; moved = false; used_soc = false; accepted = true; }
+        else entered_resto = true;
       }
-    } else if (!a.in_soft || tiny) {
-      if (used_soc) a_du = RES(R_ADU);
-      if (n_steps == 0) a.wd_short = 0; else ++a.wd_short;
+    } else if (AL(F_INSOFT) == 0.0 || tiny) {
+      if (n_steps == 0) AL(F_WSHORT) = 0.0; else al_add<L>(F_WSHORT, 1.0);
     }
     if (A.dbg && lane == 0 && iter < A.dbg_rows) {
       double* Lg = A.dbg + ((size_t)b * A.dbg_rows + iter) * DBG_COLS;
-      Lg[0] = a.mu; Lg[1] = mode ? a.f : a.f / df; Lg[2] = pr_inf; Lg[3] = du_inf; Lg[4] = dw; Lg[5] = alpha; Lg[6] = a_du;
-      Lg[7] = (double)(n_ls - ls_before); Lg[8] = (double)tag; Lg[9] = (double)mode;
+      Lg[0] = mu; Lg[1] = mode ? AL(F_F) : AL(F_F) / df; Lg[2] = pr_inf; Lg[3] = du_inf; Lg[4] = dw; Lg[5] = alpha; Lg[6] = a_du;
+      Lg[7] = AL(F_C0 + 1) - ls_before; Lg[8] = (double)tag; Lg[9] = (double)mode;
     }
-    if (entered_resto) {
-      // MinC_1NrmRestorationPhase::PerformRestoration: park the original algorithm, start a fresh one on the restoration problem
-      ++n_resto;
-      ph_slot<L>(cold, 1, true, false, lane);
-      a.infpr = RES(R_PR);                 // max-norm of g - s at the current point (latest ph_derivs)
-      ao = a;
-      const double mu_r = fmax(ao.mu, ao.infpr);
-      alg_init(a, mu_r, o.tau_min, o.tol);
-      ph_resto_init<L>(A, lane, mu_r, cold);
-      mode = 1;
-      ph_trial<L, true>(A, lane, 0.0, false, df, a.mu, cold);
-      a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
-      ++iter;
-      continue;
-    }
+    if (entered_resto) { resto_enter<L>(A, cold, lane, df); ++iter; continue; }
     // ---- accept (IpoptAlgorithm::AcceptTrialPoint)
-    if (moved) accept_(0.0, 0.0, dw, false, true);         // the soft restoration step already moved the iterate: kappa_Sigma reset only
-    else accept_(alpha, a_du, dw, used_soc, true);
-    a.f = RES(R_FT); a.LB = RES(R_LBT); a.DT = RES(R_DTT);
-    if (mode) ++n_resto_it;
+    if (moved) do_accept<L>(A, lane, mode, 0.0, 0.0, dw, false, true, cold);     // the soft step already moved the iterate: kappa_Sigma reset only
+    else do_accept<L>(A, lane, mode, alpha, a_du, dw, used_soc, true, cold);
+    take_trial_values<L>();
+    if (mode) al_count<L>(4, lane);
     ++iter;
   }
   ph_output<L>(A, b, lane, df, status, iter);
   if (lane == 0 && A.stats) {
-    atomicAdd(&A.stats[0], n_fact); atomicAdd(&A.stats[1], n_ls); atomicAdd(&A.stats[2], n_soc); atomicAdd(&A.stats[3], n_resto);
-    atomicAdd(&A.stats[4], n_resto_it); atomicAdd(&A.stats[5], n_wd); atomicAdd(&A.stats[6], n_soft); atomicAdd(&A.stats[7], n_freset);
+#pragma unroll
+    for (int c = 0; c < NSTAT; ++c) atomicAdd(&A.stats[c], (unsigned long long)AL(F_C0 + c));
   }
 }
 
@@ -1420,6 +1543,7 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
 #undef PAR
 #undef RG
 #undef UREF
+#undef AL
 #undef smem
 
 }  // namespace nmpc

@@ -539,20 +539,20 @@ struct Algo {
       out[r] = v;
     }
   }
-  // CalculateSafeSlack: a slack that rounding has pushed to (or below) zero is replaced by a tiny positive value
-  double safe_slack(double sl, double z, double bnd, bool* adj = nullptr) const {
+  // CalculateSafeSlack.  IPOPT replaces a slack that rounding has pushed to (or below) eps * min(1, mu) by a tiny positive
+  // value and moves the BOUND accordingly.  Here (and in the CUDA kernel) the accepted VARIABLE is moved by the same tiny
+  // amount instead (accept_trial_point), floored at four ulps of the bound so that the repaired slack is representable;
+  // trial points are evaluated with their plain slacks.  z = multiplier of the bound at the current iterate.
+  double safe_value(double sl, double z, double bnd) const {
     const double s_min = EPS * std::min(1.0, mu);
-    if (sl < s_min) {
-      if (adj) *adj = true;
-      const double t = std::max(mu / z, s_min);
-      return std::min(t, std::max(sl, 0.0) + o.slack_move * std::max(1.0, std::fabs(bnd)));
-    }
-    return sl;
+    const double t = std::min(std::max(mu / z, s_min), std::max(sl, 0.0) + o.slack_move * std::max(1.0, std::fabs(bnd)));
+    return std::max(t, 4.0 * EPS * std::fabs(bnd));
   }
-  double slxL(const Iter& it, int i) const { return safe_slack(it.x[i] - P.xL[i], cur.zL[i], P.xL[i]); }
-  double slxU(const Iter& it, int i) const { return safe_slack(P.xU[i] - it.x[i], cur.zU[i], P.xU[i]); }
-  double sldL(const Iter& it, int r) const { return safe_slack(it.s[r] - P.dL[r], cur.vL[r], P.dL[r]); }
-  double sldU(const Iter& it, int r) const { return safe_slack(P.dU[r] - it.s[r], cur.vU[r], P.dU[r]); }
+  bool unsafe(double sl) const { return sl < EPS * std::min(1.0, mu); }
+  double slxL(const Iter& it, int i) const { return it.x[i] - P.xL[i]; }
+  double slxU(const Iter& it, int i) const { return P.xU[i] - it.x[i]; }
+  double sldL(const Iter& it, int r) const { return it.s[r] - P.dL[r]; }
+  double sldU(const Iter& it, int r) const { return P.dU[r] - it.s[r]; }
 
   double barrier_of(const Iter& it, double fv, double mu_) const {
     double phi = fv;
@@ -1034,21 +1034,16 @@ struct Algo {
 
   // IpoptAlgorithm::AcceptTrialPoint: slack safeguard (bounds move), kappa_sigma correction, new current point
   void accept_trial_point() {
-    // IPOPT moves a bound whose slack had to be safeguarded (AdjustVariableBounds) and then recomputes the slack as
-    // x - x_L, which rounds back to zero and is safeguarded again; here the bound stays and EVERY slack evaluation goes
-    // through safe_slack() instead (same values up to slack_move * |bound| ~ 1e-12; the CUDA kernel does the same).
-    {
-      bool a = false;
-      for (int i = 0; i < n; ++i) {
-        if (hasxL(i)) { a = false; safe_slack(tr.x[i] - P.xL[i], cur.zL[i], P.xL[i], &a); C.n_slack_adj += a; }
-        if (hasxU(i)) { a = false; safe_slack(P.xU[i] - tr.x[i], cur.zU[i], P.xU[i], &a); C.n_slack_adj += a; }
-      }
-      for (int r = 0; r < m; ++r) {
-        if (hasdL(r)) { a = false; safe_slack(tr.s[r] - P.dL[r], cur.vL[r], P.dL[r], &a); C.n_slack_adj += a; }
-        if (hasdU(r)) { a = false; safe_slack(P.dU[r] - tr.s[r], cur.vU[r], P.dU[r], &a); C.n_slack_adj += a; }
-      }
+    const int adj0 = C.n_slack_adj;
+    for (int i = 0; i < n; ++i) {
+      if (hasxL(i) && unsafe(tr.x[i] - P.xL[i])) { tr.x[i] = P.xL[i] + safe_value(tr.x[i] - P.xL[i], cur.zL[i], P.xL[i]); ++C.n_slack_adj; }
+      if (hasxU(i) && unsafe(P.xU[i] - tr.x[i])) { tr.x[i] = P.xU[i] - safe_value(P.xU[i] - tr.x[i], cur.zU[i], P.xU[i]); ++C.n_slack_adj; }
     }
-    // (every slack goes through the safeguard, also after a bound has moved: x - (x - 1e-17) rounds to zero)
+    for (int r = 0; r < m; ++r) {
+      if (hasdL(r) && unsafe(tr.s[r] - P.dL[r])) { tr.s[r] = P.dL[r] + safe_value(tr.s[r] - P.dL[r], cur.vL[r], P.dL[r]); ++C.n_slack_adj; }
+      if (hasdU(r) && unsafe(P.dU[r] - tr.s[r])) { tr.s[r] = P.dU[r] - safe_value(P.dU[r] - tr.s[r], cur.vU[r], P.dU[r]); ++C.n_slack_adj; }
+    }
+    if (C.n_slack_adj != adj0) f_t = P.eval_fg(tr.x.data(), mu, g_t.data());      // a variable moved (by <= 1e-12 |bound|)
     auto reset = [&](double& z, double sl) { z = std::max(std::min(z, o.kappa_sigma * mu / sl), mu / (o.kappa_sigma * sl)); };
     for (int i = 0; i < n; ++i) { if (hasxL(i)) reset(tr.zL[i], slxL(tr, i)); if (hasxU(i)) reset(tr.zU[i], slxU(tr, i)); }
     for (int r = 0; r < m; ++r) { if (hasdL(r)) reset(tr.vL[r], sldL(tr, r)); if (hasdU(r)) reset(tr.vU[r], sldU(tr, r)); }
