@@ -207,6 +207,13 @@ static int fail(const std::string& m) { g_err = m; return 1; }
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+// like CK, but releases the half-built handle first (nmpc_create)
+#define CKH(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) { nmpc_destroy(h); return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
+
 struct nmpc_handle {
   nmpc_spec spec; int device; int sm_count;
   Prob pr; Opt opt;
@@ -235,6 +242,7 @@ const char* nmpc_version(void) { return "nmpc_b200 0.1 (sm_100a)"; }
 int32_t nmpc_n_w(const nmpc_spec* s) { return NU * s->N; }
 int32_t nmpc_n_g(const nmpc_spec* s) { return (5 + s->n_obs) * (s->N + 1); }
 
+extern "C" int nmpc_destroy(nmpc_handle* h);
 int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   if (!spec || !out) return fail("nmpc_create: null argument");
   if (spec->N < 1 || spec->N + 1 > NMPC_MAX_STAGES) return fail("nmpc_create: need 1 <= N <= 31");
@@ -280,31 +288,31 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   h->auto_order = 1;
   if (const char* e = getenv("NMPC_B200_AUTO_ORDER")) h->auto_order = atoi(e) != 0;
   h->ric_stride = RIC_N * h->pr.N;
-  CK(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
-  CK(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->cold_stride * h->max_blocks * h->warps_per_block));   // rare paths: restoration, watchdog
-  CK(cudaMalloc(&h->d_ricmap, sizeof(unsigned) * 32 * 16));
+  CKH(cudaMalloc(&h->d_ric, sizeof(double) * (size_t)h->ric_stride * h->max_blocks * h->warps_per_block));   // L2-resident Riccati scratch
+  CKH(cudaMalloc(&h->d_cold, sizeof(double) * (size_t)h->cold_stride * h->max_blocks * h->warps_per_block));   // rare paths: restoration, watchdog
+  CKH(cudaMalloc(&h->d_ricmap, sizeof(unsigned) * 32 * 16));
   {
     const int rc = h->inst->ricmap(h->d_ricmap, 0);
     if (rc != 0) { nmpc_destroy(h); return fail(std::string("nmpc_create: map kernel failed: ") + cudaGetErrorString((cudaError_t)rc)); }
-    CK(cudaDeviceSynchronize());
+    CKH(cudaDeviceSynchronize());
   }
-  CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));
-  CK(cudaMemset(h->d_counter, 0, 4 * sizeof(int)));
-  CK(cudaMalloc(&h->d_stats, 2 * NSTAT * sizeof(unsigned long long)));
-  CK(cudaMemset(h->d_stats, 0, 2 * NSTAT * sizeof(unsigned long long)));
-  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CKH(cudaMalloc(&h->d_counter, 4 * sizeof(int)));
+  CKH(cudaMemset(h->d_counter, 0, 4 * sizeof(int)));
+  CKH(cudaMalloc(&h->d_stats, 2 * NSTAT * sizeof(unsigned long long)));
+  CKH(cudaMemset(h->d_stats, 0, 2 * NSTAT * sizeof(unsigned long long)));
+  CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   const int mb = spec->max_batch > 0 ? spec->max_batch : 0;
   if (mb > 0) {
     const size_t nw = NU * spec->N, ng = (size_t)h->pr.R * h->pr.S;
-    CK(cudaMalloc(&h->d_p, sizeof(double) * mb * NPAR)); CK(cudaMalloc(&h->d_x0, sizeof(double) * mb * nw));
-    CK(cudaMalloc(&h->d_lbx, sizeof(double) * nw)); CK(cudaMalloc(&h->d_ubx, sizeof(double) * nw));
-    CK(cudaMalloc(&h->d_lbg, sizeof(double) * ng)); CK(cudaMalloc(&h->d_ubg, sizeof(double) * ng));
+    CKH(cudaMalloc(&h->d_p, sizeof(double) * mb * NPAR)); CKH(cudaMalloc(&h->d_x0, sizeof(double) * mb * nw));
+    CKH(cudaMalloc(&h->d_lbx, sizeof(double) * nw)); CKH(cudaMalloc(&h->d_ubx, sizeof(double) * nw));
+    CKH(cudaMalloc(&h->d_lbg, sizeof(double) * ng)); CKH(cudaMalloc(&h->d_ubg, sizeof(double) * ng));
     h->obs_cap = (size_t)mb * 3 * (spec->n_obs > 0 ? spec->n_obs : 1);
-    CK(cudaMalloc(&h->d_obs, sizeof(double) * h->obs_cap));
-    CK(cudaMalloc(&h->d_x, sizeof(double) * mb * nw)); CK(cudaMalloc(&h->d_f, sizeof(double) * mb));
-    CK(cudaMalloc(&h->d_g, sizeof(double) * mb * ng)); CK(cudaMalloc(&h->d_lamx, sizeof(double) * mb * nw));
-    CK(cudaMalloc(&h->d_lamg, sizeof(double) * mb * ng));
-    CK(cudaMalloc(&h->d_status, sizeof(int32_t) * mb)); CK(cudaMalloc(&h->d_iters, sizeof(int32_t) * mb));
+    CKH(cudaMalloc(&h->d_obs, sizeof(double) * h->obs_cap));
+    CKH(cudaMalloc(&h->d_x, sizeof(double) * mb * nw)); CKH(cudaMalloc(&h->d_f, sizeof(double) * mb));
+    CKH(cudaMalloc(&h->d_g, sizeof(double) * mb * ng)); CKH(cudaMalloc(&h->d_lamx, sizeof(double) * mb * nw));
+    CKH(cudaMalloc(&h->d_lamg, sizeof(double) * mb * ng));
+    CKH(cudaMalloc(&h->d_status, sizeof(int32_t) * mb)); CKH(cudaMalloc(&h->d_iters, sizeof(int32_t) * mb));
   }
   *out = h;
   return 0;
@@ -337,11 +345,10 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.p = p; A.x0 = x0; A.lbx = lbx; A.ubx = ubx; A.lbg = lbg; A.ubg = ubg; A.obs = obst;
   A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
   A.x = x; A.f = f; A.g = g; A.lam_x = lam_x; A.lam_g = lam_g; A.status = status; A.iters = iters;
-  const int par = h->parity; h->parity ^= 1;
+  const int par = h->parity;            // flipped only after a successful launch (see below)
   A.counter = h->d_counter + par; A.counter_next = h->d_counter + (par ^ 1);
   A.done = h->d_counter + 2 + par; A.done_next = h->d_counter + 2 + (par ^ 1);
   A.stats = h->d_stats + NSTAT * par; A.stats_next = h->d_stats + NSTAT * (par ^ 1);
-  h->stats_last = h->d_stats + NSTAT * par;
   A.ric = h->d_ric; A.ric_stride = h->ric_stride; A.ricmap = h->d_ricmap;
   A.cold = h->d_cold; A.cold_stride = h->cold_stride;
   A.dbg = h->dbg; A.dbg_rows = h->dbg_rows;
@@ -350,6 +357,8 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
     for (int i = 0; i < 2; ++i) { if (h->d_order[i]) cudaFree(h->d_order[i]); h->d_order[i] = nullptr; }
     if (h->d_keep_iters) cudaFree(h->d_keep_iters);
     h->d_keep_iters = nullptr; h->order_cap = 0; h->prev_B = 0; h->have_order = 0;
+    // (a failure here returns before anything of this call was enqueued: parity and counters are untouched, the
+    //  partially allocated buffers are freed by the next attempt or by nmpc_destroy)
     CK(cudaMalloc(&h->d_order[0], sizeof(int32_t) * B)); CK(cudaMalloc(&h->d_order[1], sizeof(int32_t) * B));
     CK(cudaMalloc(&h->d_keep_iters, sizeof(int32_t) * B));
     h->order_cap = B;
@@ -363,9 +372,6 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.order = h->order_next; h->order_next = nullptr;
   if (!A.order && h->auto_order && h->have_order && h->prev_B == B) A.order = h->d_order[par];
   A.order_out = h->auto_order ? h->d_order[par ^ 1] : nullptr;       // ... and this call prepares the next one's
-  h->have_order = h->auto_order;
-  h->launches = 1;
-  h->prev_B = B;
   // Grid: one block per SM at most; with `fill` > 1 a small batch is packed onto fewer SMs (fill instances per warp,
   // refilled from the queue) so that concurrent solves of other handles find free SMs instead of SMs held by blocks
   // whose eight warps wait for one straggler.
@@ -376,8 +382,22 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   }
   {
     const int rc = h->inst->launch(A, blocks, h->smem_bytes, s);
-    if (rc != 0) return fail(std::string("nmpc_solve: launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    if (rc != 0) {
+      // The kernel that would have reset the NEXT call's queue / done / work counters did not run: keep the parity (the
+      // next call reuses THIS call's buffers) and put them back to their clean state, so that a later call can never
+      // start from a stale queue counter and return without having written its outputs.
+      cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), s);
+      cudaMemsetAsync(h->d_stats, 0, 2 * NSTAT * sizeof(unsigned long long), s);
+      h->have_order = 0; h->prev_B = 0;
+      return fail(std::string("nmpc_solve: launch failed: ") + cudaGetErrorString((cudaError_t)rc));
+    }
   }
+  // the launch is enqueued: it owns buffer set `par` and prepares set `par ^ 1` for the next call
+  h->parity = par ^ 1;
+  h->stats_last = h->d_stats + NSTAT * par;
+  h->have_order = h->auto_order;
+  h->launches = 1;
+  h->prev_B = B;
   h->last_stream = s;
   return 0;
 }

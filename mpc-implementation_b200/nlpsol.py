@@ -111,13 +111,22 @@ class Solver:
         return t
 
     @staticmethod
-    def _host(a, n: int) -> np.ndarray:
+    def _host(a, n: int, what: str = "argument", shared: bool = False) -> np.ndarray:
+        """Host container -> contiguous float64 [rows, n].  Raises ValueError on a wrong length (the C ABI takes plain
+        pointers: a short vector would be read past its end).  shared: a batch-shared vector (bounds), exactly n entries."""
         if torch is not None and isinstance(a, torch.Tensor):
             a = a.detach().cpu().numpy()
         a = np.asarray(a, dtype=np.float64)
         if a.ndim == 2 and a.shape[1] == 1 and a.shape[0] == n:   # CasADi column vector
             a = a.reshape(1, n)
-        a = a.reshape(-1, n) if a.ndim != 2 else a
+        if a.ndim == 2 and a.shape[1] != n:
+            raise ValueError(f"solver: {what} has {a.shape[1]} columns, expected {n}")
+        if a.ndim != 2:
+            if a.size % n != 0 or a.size == 0:
+                raise ValueError(f"solver: {what} has {a.size} entries, expected a multiple of {n}")
+            a = a.reshape(-1, n)
+        if shared and a.shape[0] != 1:
+            raise ValueError(f"solver: {what} must have exactly {n} entries (it is shared by the batch), got {a.size}")
         return np.ascontiguousarray(a)
 
     # -- the call --------------------------------------------------------------------------------
@@ -160,12 +169,19 @@ class Solver:
             self._dev_cache[k] = buf
         return buf[1]
 
+    @staticmethod
+    def _batch_of(p) -> int:
+        """Batch size of a parameter argument in any of the accepted containers (list, numpy, torch; (11,), (11,1), (B,11))."""
+        if _is_cuda_tensor(p):
+            return int(p.numel() // NP)
+        return int(np.asarray(p, dtype=np.float64).size // NP)
+
     def _traj(self, traj, p):
         """Context manager: nmpc_set_target_trajectory for the duration of one call."""
         import contextlib
         if traj is None:
             return contextlib.nullcontext()
-        B = int(p.shape[0]) if (hasattr(p, "shape") and len(p.shape) == 2 and p.shape[1] == NP) else 1
+        B = self._batch_of(p)
         t = torch.as_tensor(traj if _is_cuda_tensor(traj) else np.asarray(traj, dtype=np.float64),
                             dtype=torch.float64, device=f"cuda:{self.device}").reshape(-1, self.N, 2).contiguous()
         if t.shape[0] != B:
@@ -180,8 +196,7 @@ class Solver:
             try:
                 yield
             finally:
-                if _is_cuda_tensor(p):
-                    self._keep_t = t
+                self._keep_t = t            # the solve may still be in flight (device call, or blocking=False): hold the tensor
                 L.nmpc_set_target_trajectory(self._h, None)
         return cm()
 
@@ -190,7 +205,7 @@ class Solver:
         import contextlib
         if weights is None:
             return contextlib.nullcontext()
-        B = int(p.shape[0]) if (hasattr(p, "shape") and len(p.shape) == 2 and p.shape[1] == NP) else 1
+        B = self._batch_of(p)
         w = torch.as_tensor(weights if _is_cuda_tensor(weights) else np.asarray(weights, dtype=np.float64),
                             dtype=torch.float64, device=f"cuda:{self.device}").reshape(-1, 2).contiguous()
         if w.shape[0] != B:
@@ -205,8 +220,7 @@ class Solver:
             try:
                 yield
             finally:
-                if _is_cuda_tensor(p):      # asynchronous call: the kernel reads w later on the stream
-                    self._keep_w = w
+                self._keep_w = w            # asynchronous call (device tensors, or blocking=False): the kernel reads w later
                 L.nmpc_set_weights(self._h, None)
         return cm()
 
@@ -224,13 +238,13 @@ class Solver:
     def _call_host(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, blocking=True):
         L = _ffi.lib()
         single = np.asarray(p).ndim == 1 or (np.asarray(p).ndim == 2 and np.asarray(p).shape[1] == 1)
-        p = self._host(p, NP)
+        p = self._host(p, NP, "p")
         B = p.shape[0]
-        x0 = np.zeros((B, self.n_w)) if x0 is None else self._host(x0, self.n_w)
+        x0 = np.zeros((B, self.n_w)) if x0 is None else self._host(x0, self.n_w, "x0")
         if x0.shape[0] != B:
             raise ValueError("solver: x0 and p disagree on the batch size")
-        lbx, ubx = self._host(lbx, self.n_w), self._host(ubx, self.n_w)
-        lbg, ubg = self._host(lbg, self.n_g), self._host(ubg, self.n_g)
+        lbx, ubx = self._host(lbx, self.n_w, "lbx", True), self._host(ubx, self.n_w, "ubx", True)
+        lbg, ubg = self._host(lbg, self.n_g, "lbg", True), self._host(ubg, self.n_g, "ubg", True)
         obs, flags = self._obst(obstacles, B)
         if B > self._max_batch:
             self._create(max(B, 2 * self._max_batch))

@@ -51,10 +51,7 @@ def test_golden_fixtures(pkg, name):
     st = s.stats()
     ref = {k: G[k] for k in ("x", "f", "g", "status", "iters")}
     stg = st["return_status"]
-    # T = 1 instances finish at the FP64 noise floor of the barrier problem (Sigma_s * ulp(s) ~ 1e-5 on saturated
-    # pitch rows): there the final flag is decided by rounding, the returned point is not.
-    flips = int((G["status"] != stg).sum())
-    assert flips <= (2 if name == "nmpc_tt" else 0), (G["status"], stg)
+    assert np.array_equal(G["status"], stg), (G["status"], stg)            # no status flips on any fixture
     both = (G["status"] == 0) & (stg == 0)
     sel = lambda d: {k: d[k][both] for k in ("x", "f", "g")}
     r2 = sel(ref); r2["status"] = G["status"][both]
@@ -83,11 +80,10 @@ def test_solve_parity_random(pkg, oracle_mod, name, N, B):
     s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
     sol = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
     st = s.stats()
-    # identical algorithm, rounding-level differences only: status flips happen on hard instances (T = 1: noise floor)
-    hard = name == "nmpc_tt"
-    assert (ref["status"] == st["return_status"]).mean() >= (0.75 if hard else 0.95)
+    # identical algorithm, rounding-level differences only
+    assert (ref["status"] == st["return_status"]).mean() >= 0.95
     both = (ref["status"] == 0) & (st["return_status"] == 0)
-    assert both.sum() >= (0.7 if hard else 0.95) * (ref["status"] == 0).sum()
+    assert both.sum() >= 0.95 * (ref["status"] == 0).sum()
     okr = ref["status"] == 0                               # solution parity wherever the oracle converged
     assert (np.abs(sol["f"][okr] - ref["f"][okr]) <= 1e-7 * np.abs(ref["f"][okr])).all()
     sel = lambda d: {k: (v[both] if v is not None else None) for k, v in d.items() if k in ("x", "f", "g", "status")}
@@ -322,8 +318,30 @@ def test_closed_loop_matches_oracle_teacher_forced(pkg, oracle_mod):
     assert abs(float(cl.err_sum[0]) - err) <= 1e-9 * err
 
 
-def test_full_size_properties(pkg):
-    """BASELINE config 2 size (4096 NMPC_TT instances): size-independent properties of every converged solve."""
+def _sampled_parity(oracle_mod, sc, p, x0, sol, st, n_sample, seed, obs=None):
+    """Solve a seeded random sample of a full-size batch with the oracle and compare it with the CUDA path: statuses,
+    and u0* / f* / active set wherever both converged (the north star's tolerances)."""
+    lbx, ubx, lbg, ubg = sc.bounds()
+    idx = np.sort(np.random.default_rng(seed).choice(p.shape[0], size=min(n_sample, p.shape[0]), replace=False))
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    ref = oracle_mod.solve(sp, sc.obstacle_table() if obs is None else obs[idx], p[idx], x0[idx], lbx, ubx, lbg, ubg,
+                           obs_per_instance=obs is not None)
+    tonp = lambda a: a[torch.as_tensor(idx, device=a.device)].cpu().numpy() if torch.is_tensor(a) else a[idx]
+    sg, ig = tonp(st["return_status"]), tonp(st["iter_count"])
+    agree = (ref["status"] == sg).mean()
+    conv_agree = ((ref["status"] == 0) == (sg == 0)).mean()
+    assert agree >= 0.97 and conv_agree >= 0.985, (agree, conv_agree, np.bincount(ref["status"], minlength=7), np.bincount(sg, minlength=7))
+    both = (ref["status"] == 0) & (sg == 0)
+    got = {k: tonp(sol[k])[both] for k in ("x", "f", "g")}
+    r2 = {k: ref[k][both] for k in ("x", "f", "g")}; r2["status"] = ref["status"][both]
+    _compare(r2, got, sg[both], ig[both], (lbx, ubx, lbg, ubg))
+    assert (ref["iters"][both] == ig[both]).mean() >= 0.9
+    return ref, idx
+
+
+def test_full_size_properties(pkg, oracle_mod):
+    """BASELINE config 2 size (4096 NMPC_TT instances): a 2048-instance sample against the oracle, and size-independent
+    properties of every converged solve."""
     sc = pkg.SCENARIOS["nmpc_tt"]
     B = 4096
     lbx, ubx, lbg, ubg = sc.bounds()
@@ -333,7 +351,8 @@ def test_full_size_properties(pkg):
     sol = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
     st = s.stats()
     ok = st["success"]
-    assert ok.mean() > 0.5
+    ref, idx = _sampled_parity(oracle_mod, sc, p, x0, sol, st, 2048, seed=11)
+    assert abs(ok[idx].mean() - (ref["status"] == 0).mean()) <= 0.01             # converged fraction = the oracle's
     assert np.all(st["iter_count"] <= 100) and np.all(st["iter_count"][ok] > 0)
     x, g = sol["x"][ok], sol["g"][ok]
     assert np.all(x >= lbx - 1e-12) and np.all(x <= ubx + 1e-12)                 # honour_original_bounds
@@ -364,8 +383,9 @@ def test_full_size_properties(pkg):
                                               ("plus_trajectory", 15, 65536, 0),
                                               ("10_obstacles", 15, 32768, 3),         # config 4: 262144 / 8 GPUs, 3 real obstacles jittered
                                               ("race_track_2", 30, 131072, 10)])      # config 5: 2x horizon, 1M / 8 GPUs, 10 obstacles jittered
-def test_full_size_other_configs(pkg, name, N, B, jitter):
-    """BASELINE configs 3-5 at the per-GPU batch size, all on the device: size-independent properties."""
+def test_full_size_other_configs(pkg, oracle_mod, name, N, B, jitter):
+    """BASELINE configs 3-5 at the per-GPU batch size, all on the device: a seeded sample against the oracle (2048
+    instances; 512 at the doubled horizon, where a dense oracle solve costs ~0.3 s), and size-independent properties."""
     sc = pkg.SCENARIOS[name]
     if N != sc.N:
         sc = sc.with_horizon(N)
@@ -388,6 +408,9 @@ def test_full_size_other_configs(pkg, name, N, B, jitter):
     sol = s(x0=x0, p=pt, lbx=T(lbx), ubx=T(ubx), lbg=T(lbg), ubg=T(ubg), obstacles=obt)
     st = s.stats()
     ok = st["success"]
+    x0n = np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (B, sc.N))
+    ref, idx = _sampled_parity(oracle_mod, sc, p, x0n, sol, st, 512 if N == 30 else 2048, seed=13, obs=obs)
+    assert abs(float(ok[torch.as_tensor(idx, device=dev)].double().mean()) - (ref["status"] == 0).mean()) <= 0.01
     assert float(ok.double().mean()) > 0.9
     assert int(st["iter_count"].max()) <= 100 and int(st["iter_count"][ok].min()) > 0
     x, g = sol["x"][ok], sol["g"][ok]
@@ -415,6 +438,98 @@ def test_full_size_other_configs(pkg, name, N, B, jitter):
     # IPOPT's unscaled complementarity tolerance compl_inf_tol = 1e-4
     assert float((up * torch.where(fu, ub - g, zero)).amax()) <= 1e-4 and float((lo * torch.where(fl, g - lb, zero)).amax()) <= 1e-4
     assert float(up[:, ~fu].amax() if (~fu).any() else 0.0) <= 1e-8 and float(lo[:, ~fl].amax() if (~fl).any() else 0.0) <= 1e-8
+
+
+@pytest.mark.parametrize("name,N,B,steps", [("nmpc_tt", 15, 96, 40), ("race_track_2", 30, 24, 40)])
+def test_closed_loop_teacher_forced_batch(pkg, oracle_mod, name, N, B, steps):
+    """Teacher-forced closed loop on the scenarios where free-running loops separate (T = 1; the doubled horizon): the
+    GPU loop runs, and at every step the oracle solves the GPU's own (p, warm start).  Per step: the statuses agree
+    on (nearly) every instance, and wherever both converged u0*, f* and the active set agree to the north star's
+    tolerances.  Infeasible NLPs that the loop itself produces are part of the population."""
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    sc = pkg.SCENARIOS[name]
+    if N != sc.N:
+        sc = sc.with_horizon(N)
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p0, vw = pkg.random_instances(sc, B, seed=4242 + N)
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    cl = ClosedLoop(s, sc, p0, target_vw=vw)
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    agree = tot = conv_dis = n_both = 0
+    for k in range(steps):
+        p = cl.p.cpu().numpy().copy(); w0 = cl.u_warm.cpu().numpy().copy()
+        sol = cl.step(want_g=True)
+        st = s.stats(); sg = st["return_status"].cpu().numpy(); ig = st["iter_count"].cpu().numpy()
+        ref = oracle_mod.solve(sp, sc.obstacle_table(), p, w0, lbx, ubx, lbg, ubg, want_lam=False)
+        agree += int((ref["status"] == sg).sum()); tot += B
+        conv_dis += int(((ref["status"] == 0) != (sg == 0)).sum())
+        both = (ref["status"] == 0) & (sg == 0)
+        if k == 0:
+            continue            # cold first step (u0 = 0): most T = 1 instances run into max_iter on both sides
+        n_both += int(both.sum())
+        got = {q: sol[q].cpu().numpy()[both] for q in ("x", "f", "g")}
+        r2 = {q: ref[q][both] for q in ("x", "f", "g")}; r2["status"] = ref["status"][both]
+        _compare(r2, got, sg[both], ig[both], (lbx, ubx, lbg, ubg))
+    assert agree >= 0.97 * tot, (agree, tot)
+    assert conv_dis <= 0.01 * tot, (conv_dis, tot)
+    assert n_both >= 0.8 * B * (steps - 1)
+
+
+def test_bench_population_status_census(pkg, oracle_mod):
+    """The bench workload itself (bench.py config 2: NMPC_TT, randomised states, closed loop): after five warm steps the
+    oracle solves the same (p, warm start) population.  Converged / not-converged agrees on >= 99 % of the instances,
+    the full status on >= 97 %, and the converged solutions agree to tolerance."""
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    sc = pkg.SCENARIOS["nmpc_tt"]
+    B = 2048
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p0, vw = pkg.random_instances(sc, B, seed=2000)
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    cl = ClosedLoop(s, sc, p0, target_vw=vw)
+    for _ in range(5):
+        cl.step()
+    p = cl.p.cpu().numpy().copy(); w0 = cl.u_warm.cpu().numpy().copy()
+    sol = cl.step(want_g=True)
+    st = s.stats(); sg = st["return_status"].cpu().numpy(); ig = st["iter_count"].cpu().numpy()
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    ref = oracle_mod.solve(sp, sc.obstacle_table(), p, w0, lbx, ubx, lbg, ubg, want_lam=False)
+    conf = np.zeros((7, 7), dtype=int)
+    np.add.at(conf, (ref["status"], sg), 1)
+    assert ((ref["status"] == 0) == (sg == 0)).mean() >= 0.99, conf
+    assert np.trace(conf) >= 0.97 * B, conf
+    assert conf[0, 0] >= 0.85 * B, conf
+    both = (ref["status"] == 0) & (sg == 0)
+    got = {q: sol[q].cpu().numpy()[both] for q in ("x", "f", "g")}
+    r2 = {q: ref[q][both] for q in ("x", "f", "g")}; r2["status"] = ref["status"][both]
+    _compare(r2, got, sg[both], ig[both], (lbx, ubx, lbg, ubg))
+    # restoration / watchdog machinery is exercised by this population on both sides
+    wc = s.work_counters()
+    assert wc["resto_calls"] > 0 and ref["stats"][:, 2].sum() > 0
+
+
+def test_restoration_outcomes(pkg, oracle_mod):
+    """NLPs that are infeasible by construction (stage-0 rows violated: the UAV starts inside an obstacle's keep-out
+    disc, or above the altitude ceiling by more than the bound relaxation): IPOPT's answer is the restoration phase
+    and "Infeasible_Problem_Detected" (or Restoration_Failed / max_iter), never success; both sides agree, and the
+    iterate handed back reduces the infeasibility (that is what the reference's loop would apply)."""
+    sc = pkg.SCENARIOS["nmpc_tt"]
+    lbx, ubx, lbg, ubg = sc.bounds()
+    B = 32
+    p, _ = pkg.random_instances(sc, B, seed=99)
+    ob = sc.obstacle_table()
+    p[:16, 0] = ob[1, 0] + 10.0; p[:16, 1] = ob[1, 1] - 5.0          # inside obstacle 2 (r_uav + r_obs = 35)
+    p[16:, 2] = 150.0 + 10.0 ** np.linspace(-5.5, -2, 16)            # above z <= 150 (relaxed: 150 + 1.5e-6)
+    x0 = np.tile(np.array([16.0, 0, 0, 0, 0, 0]), (B, sc.N))
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    ref = oracle_mod.solve(sp, ob, p, x0, lbx, ubx, lbg, ubg)
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=B)
+    sol = s(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    sg = s.stats()["return_status"]
+    assert (ref["status"] != 0).all() and (sg != 0).all()
+    assert np.isin(sg, (1, 2, 6)).all() and (sg == 6).sum() >= B // 2, sg
+    assert (ref["status"] == sg).mean() >= 0.8, (ref["status"], sg)
+    assert s.work_counters()["resto_calls"] >= B // 2
+    assert np.isfinite(sol["x"]).all() and np.all(sol["x"] >= lbx - 1e-12) and np.all(sol["x"] <= ubx + 1e-12)
 
 
 def test_schedule_independence(pkg):
@@ -516,7 +631,7 @@ def test_edge_cases(pkg):
     # UAV exactly above the target: sqrt is not differentiable there -> reported, not hidden
     p = np.array(list(sc.x_init) + [99.0, 150.0, 0.0])
     sol = s(x0=np.zeros(sc.n_w), p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
-    assert int(s.stats()["return_status"][0]) in (0, 1, 2, 3, 4, 5)
+    assert int(s.stats()["return_status"][0]) in (0, 1, 2, 3, 4, 5, 6)
     # growing past max_batch re-creates the handle transparently
     pb, _ = pkg.random_instances(sc, 9, 1)
     out = s(x0=np.zeros((9, sc.n_w)), p=pb, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
