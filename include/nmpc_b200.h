@@ -127,7 +127,8 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
  * parameter block the next solve reads:
  *   p [B][11]: p[0:8] <- x + T f_u(x, u[:,0]);  p[8:11] <- target + T [v cos th, v sin th, om]
  *   u_warm [B][6N] <- x_sol shifted by one stage, last stage repeated (may alias x_sol)
- *   target_vw [B][2] = (v, om) of the target for this step (the scripts' con_t, keyed on mpc_iter)
+ *   target_vw [B][2] = (v, om) of the target for this step (the scripts' con_t, keyed on mpc_iter); nmpc_solve_and_step
+ *   also takes NULL here when a device-side schedule is set (nmpc_set_schedule)
  *   fov_centre [B][2] (may be NULL) = (X_E, Y_E) of the NEW state
  *   err_accum [B] (may be NULL; needs fov_centre) += || FOV centre of the NEW state - target of THIS step ||, the
  *   per-step term of the scripts' final metric (NMPC_TT.py:433-440). */
@@ -143,6 +144,16 @@ int nmpc_solve_and_step(nmpc_handle* h, int32_t B, double* p, double* u_warm,
                         const double* obst, uint32_t flags, const double* target_vw,
                         double* x, double* f, double* fov_centre, double* err_accum,
                         int32_t* status, int32_t* iters, void* cuda_stream);
+
+/* Target schedule on the device.  The reference's shift_timestep reads the target's (v, omega) for this step from an
+ * if-chain keyed on the global step counter (`con_t`, T_Trajectory.py:24-57, Plus Trajectory.py:25-69, Race Track 2.py:28-36).
+ * dev_table [n_rows][len][2] holds (v, omega) per step for n_rows schedules (a step index beyond len - 1 uses the last
+ * entry); instance b follows row dev_row_of_instance[b] (NULL: row 0) starting at step dev_phase[b] (NULL: 0).  After
+ * this call nmpc_solve_and_step accepts target_vw == NULL, looks the pair up in its epilogue with
+ * step = mpc_iter + phase[b], and advances mpc_iter by one per call -- no per-step host work at any batch size.
+ * dev_table == NULL removes the schedule.  All arrays stay owned by the caller and must outlive their use. */
+int nmpc_set_schedule(nmpc_handle* h, const double* dev_table, int32_t n_rows, int32_t len,
+                      const int32_t* dev_row_of_instance, const int32_t* dev_phase, int32_t mpc_iter);
 
 /* statistics of the last nmpc_solve on this handle (device work counters, host copy) */
 typedef struct nmpc_stats {

@@ -35,7 +35,7 @@ class NmpcStats(C.Structure):
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_eval", "nmpc_step",
-           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_set_schedule", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
            "nmpc_last_error", "nmpc_version"]
 
 _lib = None
@@ -72,6 +72,7 @@ def lib():
     L.nmpc_set_order.argtypes = [vp, vp]
     L.nmpc_set_weights.argtypes = [vp, vp]
     L.nmpc_set_target_trajectory.argtypes = [vp, vp]
+    L.nmpc_set_schedule.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32]
     L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
     L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]

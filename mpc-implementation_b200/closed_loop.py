@@ -23,9 +23,12 @@ from .scenarios import NP, Scenario
 
 class ClosedLoop:
     def __init__(self, solver: Solver, scenario: Scenario, p0, target_vw=None, device: Optional[str] = None,
-                 phase=None, predict_target: bool = False, obstacles=None, obstacle_vel=None):
+                 phase=None, predict_target: bool = False, obstacles=None, obstacle_vel=None, schedules=None, schedule_of=None):
         """p0 [B,11] initial [state; target]; target_vw [B,2] constant per-instance target (v, omega) or None to
-        follow scenario.schedule(mpc_iter + phase[b]).  predict_target: hand the solver the target's own Euler
+        follow scenario.schedule(mpc_iter + phase[b]).  schedules: optional list of schedule functions (mpc_iter ->
+        (v, omega)) with schedule_of[b] the one instance b follows (BASELINE config 3 mixes the T and the Plus
+        trajectory in one batch); default: the scenario's own.  The schedule lives on the device as a table
+        (nmpc_set_schedule), so that a step costs no host work whatever the batch size.  predict_target: hand the solver the target's own Euler
         prediction over the horizon (same model as the target step of shift_timestep, NMPC_TT.py:24-27) instead of
         the frozen target the reference uses.  obstacles [B, n_obs, 3] = (cx, cy, r_uav + r_obs) per instance and
         obstacle_vel [B, n_obs, 2]: obstacle fields as data, moved by T * velocity after every step (the moving
@@ -47,23 +50,36 @@ class ClosedLoop:
         self.err_sum = torch.zeros(self.B, dtype=torch.float64, device=dev)
         self.mpc_iter = 0
         self.phase = None if phase is None else np.asarray(phase, dtype=np.int64)
+        self.sched_fns = list(schedules) if schedules is not None else [scenario.schedule]
+        self.sched_of = None if schedule_of is None else np.asarray(schedule_of, dtype=np.int64)
         if target_vw is not None:
             self.vw = to(np.asarray(target_vw, dtype=np.float64)).reshape(self.B, 2).contiguous()
             self._const_vw = True
         else:
             self.vw = torch.zeros((self.B, 2), dtype=torch.float64, device=dev)
             self._const_vw = False
+            # breakpoint schedules as a dense table [n_sched][len][2]: every script's schedule is constant after its
+            # last breakpoint (< scenario.steps), so len = steps + max phase covers any run; later steps use the last entry
+            L = int(scenario.steps + (int(self.phase.max()) if self.phase is not None else 0) + 1)
+            self.sched_table = torch.as_tensor(np.array([[fn(i) for i in range(L)] for fn in self.sched_fns], dtype=np.float64),
+                                               device=dev).contiguous()
+            self._phase_dev = None if self.phase is None else torch.as_tensor(self.phase, device=dev)
+            self._sched_dev = None if self.sched_of is None else torch.as_tensor(self.sched_of, device=dev)
+            solver.set_schedule(self.sched_table, self._sched_dev, self._phase_dev, mpc_iter=0)
         self.last = None
 
     def _schedule_vw(self):
+        """(v, omega) of this step into self.vw -- one gather on the device (only the unfused path and the target
+        prediction read it; the fused step looks the schedule up inside the kernel)."""
         if self._const_vw:
             return
-        if self.phase is None:
-            v, w = self.sc.schedule(self.mpc_iter)
-            self.vw[:, 0] = v; self.vw[:, 1] = w
-        else:
-            vw = np.array([self.sc.schedule(self.mpc_iter + int(ph)) for ph in self.phase], dtype=np.float64)
-            self.vw.copy_(torch.from_numpy(vw))
+        L = self.sched_table.shape[1]
+        at = torch.full((self.B,), self.mpc_iter, dtype=torch.int64, device=self.vw.device)
+        if self._phase_dev is not None:
+            at = at + self._phase_dev
+        at = at.clamp(max=L - 1)
+        rows = self._sched_dev if self._sched_dev is not None else torch.zeros_like(at)
+        self.vw.copy_(self.sched_table[rows, at])
 
     def _move_obstacles(self):
         if self.obstacles is not None and self.obstacle_vel is not None:
@@ -92,9 +108,11 @@ class ClosedLoop:
     def step(self, want_g: bool = False, want_lam: bool = False, want_x: bool = True):
         """One closed-loop batch step; returns the solver output dict (device tensors).  Without g / multipliers
         the solve and the shift are one launch (nmpc_solve_and_step)."""
-        self._schedule_vw()
+        if self._const_vw or self.predict_target or want_g or want_lam:
+            self._schedule_vw()
         if not (want_g or want_lam):
-            sol = self.solver.solve_and_step(self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg, self.vw, self.fov,
+            sol = self.solver.solve_and_step(self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg,
+                                             self.vw if self._const_vw else None, self.fov,
                                              self.err_sum, obstacles=self.obstacles, want_x=want_x,
                                              target_traj=self.target_prediction() if self.predict_target else None)
             self._move_obstacles()
@@ -106,6 +124,8 @@ class ClosedLoop:
                           target_traj=self.target_prediction() if self.predict_target else None)
         # shift + error[i] = || FOVcentre_{i+1} - target_i ||   (NMPC_TT.py:435), one kernel
         self.solver.step(sol["x"], self.p, self.u_warm, self.vw, self.fov, self.err_sum)
+        if not self._const_vw:      # keep the device-side step counter of the fused path in line with this loop's
+            self.solver.set_schedule(self.sched_table, self._sched_dev, self._phase_dev, mpc_iter=self.mpc_iter + 1)
         self._move_obstacles()
         self.mpc_iter += 1
         self.last = sol
@@ -131,7 +151,7 @@ class PipelinedClosedLoop:
 
     def __init__(self, make_solver: Callable[[int], Solver], scenario: Scenario, p0, target_vw=None,
                  pipelines: Optional[int] = None, device: Optional[str] = None, phase=None, predict_target: bool = False,
-                 obstacles=None, obstacle_vel=None):
+                 obstacles=None, obstacle_vel=None, schedules=None, schedule_of=None):
         """make_solver(n) -> Solver for a sub-batch of n instances (give it `fill=2`: a sub-batch then leaves SMs to
         the others).  pipelines: number of sub-batches; None = about 32768 / B, at most 8 (measured best: 8 at
         B = 4096, 2 at B = 16384 on a B200)."""
@@ -151,7 +171,8 @@ class PipelinedClosedLoop:
                 sub = lambda a: None if a is None else (a[torch.as_tensor(idx, device=a.device)] if torch.is_tensor(a) else np.asarray(a)[idx])
                 lp = ClosedLoop(sol, scenario, p0[idx], None if target_vw is None else np.asarray(target_vw)[idx], device=dev,
                                 phase=None if phase is None else np.asarray(phase)[idx], predict_target=predict_target,
-                                obstacles=sub(obstacles), obstacle_vel=sub(obstacle_vel))
+                                obstacles=sub(obstacles), obstacle_vel=sub(obstacle_vel), schedules=schedules,
+                                schedule_of=None if schedule_of is None else np.asarray(schedule_of)[idx])
             self.loops.append(lp); self.streams.append(st)
         self.synchronize()
 

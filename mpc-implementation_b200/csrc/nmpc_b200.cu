@@ -223,6 +223,7 @@ struct nmpc_handle {
   int32_t *d_order[2], *d_keep_iters; int order_cap, prev_B, auto_order, parity, have_order; const int32_t* order_next;
   const double *weights, *tgt;
   double *fuse_p, *fuse_u, *fuse_fov, *fuse_err; const double* fuse_vw;   // set for the duration of nmpc_solve_and_step
+  const double* sched_table; const int32_t *sched_id, *sched_phase; int sched_rows, sched_len, sched_iter;   // nmpc_set_schedule
   int* d_counter;                  // [4]: queue counter x2, done counter x2
   unsigned long long* d_stats;     // [2][NSTAT]
   unsigned long long* stats_last;  // the half written by the last call
@@ -365,6 +366,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   }
   A.iters_keep = h->d_keep_iters;
   A.step_p = h->fuse_p; A.step_u = h->fuse_u; A.step_vw = h->fuse_vw; A.step_fov = h->fuse_fov; A.step_err = h->fuse_err;
+  A.sched_table = h->sched_table; A.sched_id = h->sched_id; A.sched_phase = h->sched_phase; A.sched_len = h->sched_len; A.sched_iter = h->sched_iter;
   A.tgt = h->tgt;
   A.weights = h->weights;
   A.align_group = h->align_group;
@@ -408,12 +410,14 @@ int nmpc_solve_and_step(nmpc_handle* h, int32_t B, double* p, double* u_warm,
                         double* x, double* f, double* fov_centre, double* err_accum,
                         int32_t* status, int32_t* iters, void* cuda_stream) {
   if (!h) return fail("nmpc_solve_and_step: null handle");
-  if (!p || !u_warm || !target_vw) return fail("nmpc_solve_and_step: null required pointer");
+  if (!p || !u_warm) return fail("nmpc_solve_and_step: null required pointer");
+  if (!target_vw && !h->sched_table) return fail("nmpc_solve_and_step: target_vw is NULL and no schedule is set (nmpc_set_schedule)");
   if (err_accum && !fov_centre) return fail("nmpc_solve_and_step: err_accum needs fov_centre");
   if (x == u_warm) return fail("nmpc_solve_and_step: x must not alias u_warm (pass NULL if the solution itself is not needed)");
   h->fuse_p = p; h->fuse_u = u_warm; h->fuse_vw = target_vw; h->fuse_fov = fov_centre; h->fuse_err = err_accum;
   const int rc = nmpc_solve(h, B, p, u_warm, lbx, ubx, lbg, ubg, obst, flags, x, f, nullptr, nullptr, nullptr, status, iters, cuda_stream);
   h->fuse_p = nullptr; h->fuse_u = nullptr; h->fuse_vw = nullptr; h->fuse_fov = nullptr; h->fuse_err = nullptr;
+  if (rc == 0 && !target_vw) ++h->sched_iter;        // the schedule is keyed on the number of closed-loop steps taken (mpc_iter)
   return rc;
 }
 
@@ -525,6 +529,15 @@ int nmpc_set_weights(nmpc_handle* h, const double* dev_weights) {
 int nmpc_set_target_trajectory(nmpc_handle* h, const double* dev_targets) {
   if (!h) return fail("nmpc_set_target_trajectory: null handle");
   h->tgt = dev_targets;
+  return 0;
+}
+
+int nmpc_set_schedule(nmpc_handle* h, const double* dev_table, int32_t n_rows, int32_t len,
+                      const int32_t* dev_row_of_instance, const int32_t* dev_phase, int32_t mpc_iter) {
+  if (!h) return fail("nmpc_set_schedule: null handle");
+  if (dev_table && (n_rows < 1 || len < 1)) return fail("nmpc_set_schedule: need n_rows >= 1 and len >= 1");
+  h->sched_table = dev_table; h->sched_rows = n_rows; h->sched_len = len;
+  h->sched_id = dev_row_of_instance; h->sched_phase = dev_phase; h->sched_iter = mpc_iter;
   return 0;
 }
 

@@ -55,6 +55,9 @@ struct SolveArgs {
   // fused closed-loop shift (nmpc_solve_and_step): when step_p != NULL the warp that solved instance b also applies
   // shift_timestep to it -- p[b] and u_warm[b] in place, FOV centre, error term -- and no nmpc_step launch is needed
   double *step_p, *step_u; const double* step_vw; double *step_fov, *step_err;
+  // target schedule on the device (nmpc_set_schedule): when step_vw == NULL the target's (v, omega) of this step is
+  // sched_table[sched_id[b]][min(sched_iter + sched_phase[b], sched_len - 1)]  -- the scripts' `con_t` keyed on mpc_iter
+  const double* sched_table; const int32_t *sched_id, *sched_phase; int sched_len, sched_iter;
   int32_t* iters_keep;               // handle-owned copy of iters[] (drives the next call's fetch order)
   const int32_t* order;              // optional processing order (longest-first scheduling); NULL = 0..B-1
   int* counter;                      // work queue of THIS call
@@ -949,9 +952,18 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
       if (lane < N - 1) uw[NU * lane + i] = un;                   // drop the first stage ...
       else if (lane == N - 1) uw[NU * lane + i] = u[i];           // ... and repeat the last (:20-23)
     }
-    if (lane == 0)
-      closed_loop_shift(pr.T, pr.hv, pr.hh, A.step_p + (size_t)b * NPAR, u, __ldg(A.step_vw + 2 * (size_t)b), __ldg(A.step_vw + 2 * (size_t)b + 1),
+    if (lane == 0) {
+      double tv, tw;
+      if (A.step_vw) { tv = __ldg(A.step_vw + 2 * (size_t)b); tw = __ldg(A.step_vw + 2 * (size_t)b + 1); }
+      else {
+        const int row = A.sched_id ? __ldg(A.sched_id + b) : 0, ph = A.sched_phase ? __ldg(A.sched_phase + b) : 0;
+        const int at = min(A.sched_iter + ph, A.sched_len - 1);
+        const double* e = A.sched_table + ((size_t)row * A.sched_len + at) * 2;
+        tv = __ldg(e); tw = __ldg(e + 1);
+      }
+      closed_loop_shift(pr.T, pr.hv, pr.hh, A.step_p + (size_t)b * NPAR, u, tv, tw,
                         A.step_fov ? A.step_fov + 2 * (size_t)b : nullptr, A.step_err ? A.step_err + b : nullptr);
+    }
   }
   __syncwarp();
 }

@@ -385,12 +385,38 @@ class Solver:
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         ptr = lambda t: None if t is None else t.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if target_vw is None and getattr(self, "_sched", None) is None:
+            raise ValueError("solver: target_vw is None and no schedule is set (set_schedule)")
         _ffi.check(L.nmpc_solve_and_step(self._h, B, ptr(p), ptr(u_warm), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
                                          ptr(target_vw), ptr(x), ptr(f), ptr(fov_centre), ptr(err_accum), ptr(status), ptr(iters),
                                          stream), "nmpc_solve_and_step")
         self._keep = (obs,)
         self._stats = dict(return_status=status, iter_count=iters)
         return dict(x=x, f=f, g=None, lam_x=None, lam_g=None)
+
+    def set_schedule(self, table, row_of_instance=None, phase=None, mpc_iter: int = 0):
+        """Device-side target schedule (nmpc_set_schedule): table [n_rows, len, 2] of (v, omega) per closed-loop step;
+        instance b follows row row_of_instance[b] starting at step phase[b].  solve_and_step(target_vw=None) then looks
+        the pair up in the kernel's epilogue and advances the step counter.  table=None removes the schedule."""
+        L = _ffi.lib()
+        if table is None:
+            self._sched = None
+            _ffi.check(L.nmpc_set_schedule(self._h, None, 0, 0, None, None, 0), "nmpc_set_schedule")
+            return
+        dev = f"cuda:{self.device}"
+        t = torch.as_tensor(np.asarray(table, dtype=np.float64) if not torch.is_tensor(table) else table, dtype=torch.float64, device=dev).contiguous()
+        if t.dim() != 3 or t.shape[2] != 2:
+            raise ValueError("solver: schedule table must be [n_rows, len, 2]")
+        i32 = lambda a: None if a is None else torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a, device=dev).to(torch.int32).contiguous()
+        rows, ph = i32(row_of_instance), i32(phase)
+        if rows is not None and (int(rows.min()) < 0 or int(rows.max()) >= t.shape[0]):
+            raise ValueError("solver: schedule row index out of range")
+        if ph is not None and int(ph.min()) < 0:
+            raise ValueError("solver: schedule phases must be >= 0")
+        self._sched = (t, rows, ph)          # owned here: the handle keeps raw pointers
+        ptr = lambda a: None if a is None else a.data_ptr()
+        _ffi.check(L.nmpc_set_schedule(self._h, t.data_ptr(), int(t.shape[0]), int(t.shape[1]), ptr(rows), ptr(ph), int(mpc_iter)),
+                   "nmpc_set_schedule")
 
     def step(self, x_sol, p, u_warm, target_vw, fov_centre=None, err_accum=None):
         """In-place closed-loop shift of B instances (torch CUDA float64 tensors): p [B,11], u_warm [B,6N];
