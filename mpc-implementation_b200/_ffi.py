@@ -72,12 +72,14 @@ def lib():
     L.nmpc_set_order.argtypes = [vp, vp]
     L.nmpc_set_weights.argtypes = [vp, vp]
     L.nmpc_set_target_trajectory.argtypes = [vp, vp]
-    L.nmpc_set_schedule.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32]
+    if hasattr(L, "nmpc_set_schedule"):      # (absent only in old builds loaded through NMPC_B200_LIB for A/B timing)
+        L.nmpc_set_schedule.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32]
     L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
     L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]
     for name in EXPORTS:
-        getattr(L, name).restype = C.c_int
+        if hasattr(L, name):
+            getattr(L, name).restype = C.c_int
     L.nmpc_last_error.restype = C.c_char_p
     L.nmpc_version.restype = C.c_char_p
     L.nmpc_n_w.restype = C.c_int32

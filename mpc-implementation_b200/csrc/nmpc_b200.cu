@@ -29,11 +29,11 @@ namespace nmpc {
   int ipm_prepare_##N##_##O(int*, size_t*, int*, int*);  \
   int ipm_ricmap_##N##_##O(unsigned*, cudaStream_t);     \
   int ipm_launch_##N##_##O(const SolveArgs&, int, size_t, cudaStream_t);
-NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3)
+NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3) NMPC_DECL_INST(15, 7)
 }  // namespace nmpc
 struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*, int*); int (*ricmap)(unsigned*, cudaStream_t); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
 #define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_ricmap_##N##_##O, nmpc::ipm_launch_##N##_##O}
-static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3)};
+static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3), NMPC_INST(15, 7)};      // (15, 7): the 7 obstacle rows of MATLAB/Dynamic Obstacles/Dynamic Obstacle avoidance.m:126-134
 
 struct EvalArgs {
   Prob pr; int B;

@@ -85,13 +85,9 @@ static __device__ __noinline__ double n_pow(double x, double y) { return pow(x, 
 static __device__ __noinline__ double2 n_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
 __device__ __forceinline__ double rcp(double x) { return __drcp_rn(x); }
 // IPOPT's CalculateSafeSlack: a slack that rounding has pushed to (or below) eps * min(1, mu) is replaced by a tiny
-// positive value (slack_move = eps^(3/4)) and the bound moved.  Here the accepted VARIABLE is moved instead (ph_accept),
-// by the same amount floored at four ulps of the bound; z = multiplier of that bound at the current iterate.
-static __device__ __noinline__ double safe_value(double sl, double z, double bnd, double mu) {
-  const double s_min = 2.220446049250313e-16 * fmin(1.0, mu);
-  const double t = fmin(fmax(mu / z, s_min), fmax(sl, 0.0) + 1.8189894035458565e-12 * fmax(1.0, fabs(bnd)));
-  return fmax(t, 4.0 * 2.220446049250313e-16 * fabs(bnd));
-}
+// positive value and the bound moved.  Here the accepted VARIABLE is moved instead (ph_accept / ph_repair), to
+// slack = max(slack, 0) + slack_move * max(1, |bound|), slack_move = eps^(3/4).
+__device__ __forceinline__ double safe_value(double sl, double bnd) { return fmax(sl, 0.0) + 1.8189894035458565e-12 * fmax(1.0, fabs(bnd)); }
 
 // ---- warp collectives ---------------------------------------------------------------------------
 static __device__ __noinline__ double warp_sum(double v) {

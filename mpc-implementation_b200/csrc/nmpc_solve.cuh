@@ -723,29 +723,62 @@ __device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_so
   __syncwarp();
 }
 
-// accept the trial point: primal step alpha, dual step a_du, kappa_Sigma reset (reset), new reciprocal slacks
+// Slack safeguard (rare): repair the primal values whose slack fell below smin after a step, then give their
+// multipliers the kappa_Sigma reset against the repaired slack (ph_accept left them un-reset) and refresh the
+// reciprocal row slacks.
+template <class L, bool RS>
+__device__ __noinline__ void ph_repair(const SolveArgs& A, int lane, double mu, bool reset, double* cold) {
+  const double ks = A.o.kappa_sigma, iks = 1.0 / A.o.kappa_sigma, smin = EPSM * fmin(1.0, mu);
+  auto clampz = [&](double z, double sl) { const double i2 = rcp(sl); return reset ? fmax(fmin(z, ks * mu * i2), mu * i2 * iks) : z; };
+  if (lane < L::N) {
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+      const Bnd b = ctl_bounds(A, lane, i);
+      double u = LV(LV_U + i);
+      if (b.hl && u - b.lo < smin) { const double t = safe_value(u - b.lo, b.lo); u = b.lo + t; LV(LV_ZL + i) = clampz(LV(LV_ZL + i), t); }
+      if (b.hu && b.hi - u < smin) { const double t = safe_value(b.hi - u, b.hi); u = b.hi - t; LV(LV_ZU + i) = clampz(LV(LV_ZU + i), t); }
+      LV(LV_U + i) = u;
+    }
+  }
+  if (lane <= L::N) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; ++r) {
+      const Bnd b = row_bounds<L>(A, lane, r, RW(A_DC, r));
+      double s = RW(A_S, r);
+      if (b.hl && s - b.lo < smin) { const double t = safe_value(s - b.lo, b.lo); s = b.lo + t; RW(A_VL, r) = clampz(RW(A_VL, r), t); RW(A_IL, r) = rcp(t); }
+      if (b.hu && b.hi - s < smin) { const double t = safe_value(b.hi - s, b.hi); s = b.hi - t; RW(A_VU, r) = clampz(RW(A_VU, r), t); RW(A_IU, r) = rcp(t); }
+      RW(A_S, r) = s;
+      if (RS) {
+        double n = RG(G_N, r), p = RG(G_P, r);
+        if (n < smin) { n = safe_value(n, 0.0); RG(G_N, r) = n; RG(G_ZN, r) = clampz(RG(G_ZN, r), n); }
+        if (p < smin) { p = safe_value(p, 0.0); RG(G_P, r) = p; RG(G_ZP, r) = clampz(RG(G_ZP, r), p); }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// accept the trial point: primal step alpha, dual step a_du, kappa_Sigma reset (reset), new reciprocal slacks.
+// Straight-line: a slack that comes out below smin only raises a flag (its multiplier is left un-reset) and the rare
+// ph_repair fixes it up afterwards.
 template <class L, bool RS>
 __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alpha, double a_du, double mu, double dw, bool soc, bool reset,
                                        double* cold) {
   const bool act = lane <= L::N, hasu = lane < L::N;
   const double ks = A.o.kappa_sigma, kd = A.o.kappa_d, iks = 1.0 / A.o.kappa_sigma;
   const double smin = EPSM * fmin(1.0, mu);
+  bool bad = false;
   if (hasu) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const Bnd b = ctl_bounds(A, lane, i);
       const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i);
-      const double zl0 = LV(LV_ZL + i), zu0 = LV(LV_ZU + i);
-      double zl = zl0, zu = zu0;
-      if (b.hl) zl += a_du * ((mu - zl * du) * rcp((u - b.lo)) - zl);
-      if (b.hu) zu += a_du * ((mu + zu * du) * rcp((b.hi - u)) - zu);
-      double un = fma(alpha, du, u);
-      if (b.hl && un - b.lo < smin) un = b.lo + safe_value(un - b.lo, zl0, b.lo, mu);       // slack safeguard: the variable moves
-      if (b.hu && b.hi - un < smin) un = b.hi - safe_value(b.hi - un, zu0, b.hi, mu);
-      if (reset) {
-        if (b.hl) { const double i2 = rcp((un - b.lo)); zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
-        if (b.hu) { const double i2 = rcp((b.hi - un)); zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
-      }
+      double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
+      if (b.hl) zl += a_du * ((mu - zl * du) * rcp(u - b.lo) - zl);
+      if (b.hu) zu += a_du * ((mu + zu * du) * rcp(b.hi - u) - zu);
+      const double un = fma(alpha, du, u);
+      if (b.hl) { const double sl = un - b.lo, i2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) zl = fmax(fmin(zl, ks * mu * i2), mu * i2 * iks); }
+      if (b.hu) { const double sl = b.hi - un, i2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) zu = fmax(fmin(zu, ks * mu * i2), mu * i2 * iks); }
       LV(LV_U + i) = un; LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu;
     }
   }
@@ -755,8 +788,7 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
       const double ds = soc ? SOC(SOC_DS2 + r) : RW(A_DS, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      const double vl0 = RW(A_VL, r), vu0 = RW(A_VU, r);
-      double vl = vl0, vu = vu0;
+      double vl = RW(A_VL, r), vu = RW(A_VU, r);
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
@@ -764,31 +796,28 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       RW(A_Y, r) = y + alpha * dy;
       if (hl) vl += a_du * ((mu - vl * ds) * il - vl);
       if (hu) vu += a_du * ((mu + vu * ds) * iu - vu);
-      double sn = fma(alpha, ds, s);
+      const double sn = fma(alpha, ds, s);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      if (hl && sn - b.lo < smin) sn = b.lo + safe_value(sn - b.lo, vl0, b.lo, mu);
-      if (hu && b.hi - sn < smin) sn = b.hi - safe_value(b.hi - sn, vu0, b.hi, mu);
       double il2 = 0.0, iu2 = 0.0;
-      if (hl) { il2 = rcp((sn - b.lo)); if (reset) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
-      if (hu) { iu2 = rcp((b.hi - sn)); if (reset) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
+      if (hl) { const double sl = sn - b.lo; il2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
+      if (hu) { const double sl = b.hi - sn; iu2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
       RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
       if (RS) {
         const double n0 = RG(G_N, r), p0 = RG(G_P, r), zn0 = RG(G_ZN, r), zp0 = RG(G_ZP, r);
         const double dn = soc ? RG(G_DN2, r) : RG(G_DN, r), dp = soc ? RG(G_DP2, r) : RG(G_DP, r);
-        double zn = zn0 + a_du * ((mu - zn0 * dn) * rcp((n0)) - zn0);
-        double zp = zp0 + a_du * ((mu - zp0 * dp) * rcp((p0)) - zp0);
-        double nn_ = fma(alpha, dn, n0), pn_ = fma(alpha, dp, p0);
-        if (nn_ < smin) nn_ = safe_value(nn_, zn0, 0.0, mu);
-        if (pn_ < smin) pn_ = safe_value(pn_, zp0, 0.0, mu);
-        if (reset) {
-          const double i1 = rcp((nn_)), i2 = rcp((pn_));
-          zn = fmax(fmin(zn, ks * mu * i1), mu * i1 * iks); zp = fmax(fmin(zp, ks * mu * i2), mu * i2 * iks);
-        }
+        double zn = zn0 + a_du * ((mu - zn0 * dn) * rcp(n0) - zn0);
+        double zp = zp0 + a_du * ((mu - zp0 * dp) * rcp(p0) - zp0);
+        const double nn_ = fma(alpha, dn, n0), pn_ = fma(alpha, dp, p0);
+        const bool un1 = nn_ < smin, un2 = pn_ < smin;
+        bad = bad || un1 || un2;
+        if (reset && !un1) { const double i1 = rcp(nn_); zn = fmax(fmin(zn, ks * mu * i1), mu * i1 * iks); }
+        if (reset && !un2) { const double i2 = rcp(pn_); zp = fmax(fmin(zp, ks * mu * i2), mu * i2 * iks); }
         RG(G_N, r) = nn_; RG(G_P, r) = pn_; RG(G_ZN, r) = zn; RG(G_ZP, r) = zp;
       }
     }
   }
   __syncwarp();
+  if (__any_sync(FULL, bad)) ph_repair<L, RS>(A, lane, mu, reset, cold);
 }
 
 // ---- rare paths --------------------------------------------------------------------------------------------------

@@ -539,15 +539,12 @@ struct Algo {
       out[r] = v;
     }
   }
-  // CalculateSafeSlack.  IPOPT replaces a slack that rounding has pushed to (or below) eps * min(1, mu) by a tiny positive
-  // value and moves the BOUND accordingly.  Here (and in the CUDA kernel) the accepted VARIABLE is moved by the same tiny
-  // amount instead (accept_trial_point), floored at four ulps of the bound so that the repaired slack is representable;
-  // trial points are evaluated with their plain slacks.  z = multiplier of the bound at the current iterate.
-  double safe_value(double sl, double z, double bnd) const {
-    const double s_min = EPS * std::min(1.0, mu);
-    const double t = std::min(std::max(mu / z, s_min), std::max(sl, 0.0) + o.slack_move * std::max(1.0, std::fabs(bnd)));
-    return std::max(t, 4.0 * EPS * std::fabs(bnd));
-  }
+  // CalculateSafeSlack.  IPOPT replaces a slack that rounding has pushed to (or below) eps * min(1, mu) by
+  // min(max(mu / z, s_min), slack + slack_move * max(1, |bound|)) and moves the BOUND accordingly.  Here (and in the CUDA
+  // kernel) the accepted VARIABLE is moved instead (accept_trial_point), to slack = max(slack, 0) + slack_move * max(1,
+  // |bound|): the multiplier-dependent alternative mu / z is dropped (it would make the repair depend on the order of
+  // the primal repair and the kappa_Sigma reset of z); trial points are evaluated with their plain slacks.
+  double safe_value(double sl, double /*z*/, double bnd) const { return std::max(sl, 0.0) + o.slack_move * std::max(1.0, std::fabs(bnd)); }
   bool unsafe(double sl) const { return sl < EPS * std::min(1.0, mu); }
   double slxL(const Iter& it, int i) const { return it.x[i] - P.xL[i]; }
   double slxU(const Iter& it, int i) const { return P.xU[i] - it.x[i]; }
