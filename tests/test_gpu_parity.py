@@ -61,6 +61,25 @@ def _compare_bulk(ref, got, bounds, frac=0.995):
 
 
 @pytest.mark.parametrize("name", NAMES)
+def test_casadi_records(pkg, name):
+    """PINNING HOOK: real CasADi + IPOPT records (tests/golden/casadi_<name>.npz, made by bench/run_casadi.py where CasADi
+    is installed) take precedence over the oracle's own fixtures: same status, f* 1e-8, u0* 1e-6 against REAL IPOPT."""
+    f = GOLD / f"casadi_{name}.npz"
+    if not f.exists():
+        pytest.skip("no real-reference records in this repository (CasADi unavailable in the build image): parity unpinned")
+    C = np.load(f, allow_pickle=False)
+    sc = pkg.SCENARIOS[name]
+    s = pkg.nlpsol("solver", "ipm", sc, max_batch=len(C["f"]))
+    lbx, ubx, lbg, ubg = sc.bounds()
+    sol = s(x0=C["x0"], p=C["p"], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    stg = s.stats()["return_status"]
+    assert np.array_equal(C["status"], stg), (C["status"], stg)
+    ok = C["status"] == 0
+    assert np.all(np.abs(sol["f"][ok] - C["f"][ok]) <= F_RTOL * np.abs(C["f"][ok]))
+    assert np.all(np.abs(sol["x"][ok, :6] - C["x"][ok, :6]).max(axis=1) <= U0_RTOL * np.abs(C["x"][ok, :6]).max(axis=1))
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_golden_fixtures(pkg, name):
     """Committed oracle solutions (first closed-loop steps of each reference script + seeded instances)."""
     sc = pkg.SCENARIOS[name]
