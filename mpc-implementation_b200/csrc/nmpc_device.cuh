@@ -42,9 +42,9 @@ enum LqEnt {
   LQ_ZERO = 78,    // 1 : 0.0 (lets the Riccati add its stage terms without branches)
   LQ_N = 79
 };
-// second-order-correction scratch (offsets in units of S doubles inside the `soc` region)
-//   DS2 [R], CSOC [R], CT [R], DUS [6], DXS [8], Q2 [8]
-__host__ __device__ inline int soc_entries(int R) { return 3 * R + 22; }
+// second-order-correction scratch in shared memory (offsets in units of S doubles inside the `soc` region):
+//   CT [R] (residual of the last trial point), DUS [6], Q2 [8];  the two arrays only the SOC itself touches (DS2, CSOC)
+//   live in the cold global scratch
 // Riccati factors in the per-warp global (L2-resident) scratch, per stage:
 constexpr int RIC_K = 0;      // 54: rows r=0..5 of [K | kappa], 9 doubles each
 constexpr int RIC_L = 54;     // 21: Cholesky factor of Lambda (packed lower) + 6 inverse diagonal
@@ -158,12 +158,12 @@ struct Lay {
   static constexpr int LV0 = 0;
   static constexpr int RW0 = even_up(LV0 + LV_N * S);
   static constexpr int LQ0 = even_up(RW0 + A_NROW * R * S);
-  // Second-order-correction scratch, 3R + 14 entries: as many as fit live in the LQ entries that are dead after the
+  // Second-order-correction scratch, R + 14 entries: as many as fit live in the LQ entries that are dead after the
   // factorisation ([0, LQ_DEAD)), the rest in an extra region.  The last 14 entries (du_soc, q') are addressed as
-  // blocks by the Riccati sweeps, so they are never split: SOC_LO <= 3R unless everything fits.
-  static constexpr int SOC_N = 3 * R + 14;
+  // blocks by the Riccati sweeps, so they are never split: SOC_LO <= R unless everything fits.
+  static constexpr int SOC_N = R + 14;
   static constexpr bool SOC_ALIAS = SOC_N <= LQ_DEAD;
-  static constexpr int SOC_LO = SOC_ALIAS ? SOC_N : (3 * R < LQ_DEAD ? 3 * R : LQ_DEAD);
+  static constexpr int SOC_LO = SOC_ALIAS ? SOC_N : (R < LQ_DEAD ? R : LQ_DEAD);
   static constexpr int SOCX0 = even_up(LQ0 + LQ_N * S);
   static constexpr int STG0 = even_up(SOCX0 + (SOC_N - SOC_LO) * S);
   __host__ __device__ static constexpr int soc(int e) { return e < SOC_LO ? LQ0 + e * S : SOCX0 + (e - SOC_LO) * S; }
@@ -177,8 +177,8 @@ struct Lay {
   //      restoration phase): restoration row arrays, reference controls, the restoration problem's own filter, and three
   //      slots that hold a saved iterate + step
   static constexpr int RSZ = R * S;
-  static constexpr int CG_ROWS = 0;                     // 10 arrays [R][S]: n, p, z_n, z_p, dn, dp, dy, dn_soc, dp_soc, dy_soc
-  static constexpr int CG_UR = 10 * RSZ;                // [6][S] reference controls x_R of the restoration problem
+  static constexpr int CG_ROWS = 0;                     // 12 arrays [R][S]: n, p, z_n, z_p, dn, dp, dy, dn_soc, dp_soc, dy_soc, ds_soc, c_soc
+  static constexpr int CG_UR = 12 * RSZ;                // [6][S] reference controls x_R of the restoration problem
   static constexpr int CG_FILT = CG_UR + 6 * S;         // [2][FILT_CAP][2]: filter of the original problem, of the restoration problem
   static constexpr int CG_PARK = CG_FILT + 4 * FILT_CAP;   // [ALG_N] algorithm state of the original problem while the restoration phase runs
   static constexpr int CG_SLOT = CG_PARK + ALG_N;

@@ -133,15 +133,13 @@ __device__ __forceinline__ int align_warps(int g, int working) {
 #define SOC(e) smem[L::soc(e) + lane]
 #define RES(i) smem[L::RES0 + (i)]
 #define PAR(i) smem[L::PAR0 + (i)]
-#define SOC_DS2 0
-#define SOC_CSOC (L::R)
-#define SOC_CT (2 * L::R)
-#define SOC_DUS (3 * L::R)
-#define SOC_Q2 (3 * L::R + 6)
+#define SOC_CT 0
+#define SOC_DUS (L::R)
+#define SOC_Q2 (L::R + 6)
 // restoration row arrays in the cold scratch: (arr * R + r) * S + lane
 #define RG(arr, r) cold[((arr) * L::R + (r)) * L::S + lane]
 #define UREF(i) cold[L::CG_UR + (i) * L::S + lane]
-enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DY, G_DN2, G_DP2, G_DY2 };
+enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DY, G_DN2, G_DP2, G_DY2, G_DS2, G_CSOC };     // the last two: SOC step in s, SOC residual
 
 // T-scaled non-zeros of the dynamics Jacobian A_k - I of this lane's stage
 struct Dyn { double e03, e13, e23, e04, e14; };
@@ -565,7 +563,7 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
       if (RS) {
         const double y = RW(A_Y, r);
         const RestoRow q = resto_row<L>(A, cold, lane, r, vl * il + vu * iu, beta, y, mu, dw);
-        c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) + RG(G_N, r) - RG(G_P, r) - s;
+        c = soc ? RG(G_CSOC, r) : RW(A_G, r) + RG(G_N, r) - RG(G_P, r) - s;
         const double chat = c + q.rs * rcp(q.D) + q.rp * rcp(q.Dp) - q.rn * rcp(q.Dn);
         const double dyv = q.Om * (gd + chat);
         // dy first, then ds, dn, dp from their own dual equations: exact dual consistency whatever the rounding of the D's
@@ -580,11 +578,11 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
         nottiny = nottiny || (fabs(dn) > tt * (1.0 + fabs(q.n))) || (fabs(dp) > tt * (1.0 + fabs(q.p)));
         dymax = fmax(dymax, fabs(dyv));
       } else {
-        c = soc ? SOC(SOC_CSOC + r) : RW(A_G, r) - s;
+        c = soc ? RG(G_CSOC, r) : RW(A_G, r) - s;
         ds = gd + c;
         dymax = fmax(dymax, fabs((vl * il + vu * iu + dw) * ds + (mu * beta - RW(A_Y, r))));
       }
-      if (soc) SOC(SOC_DS2 + r) = ds; else RW(A_DS, r) = ds;
+      if (soc) RG(G_DS2, r) = ds; else RW(A_DS, r) = ds;
       tp = fmax(tp, fmax(-ds * il, ds * iu));
       if (hl) dual_frac(vl, (mu - vl * ds) * il - vl);
       if (hu) dual_frac(vu, (mu + vu * ds) * iu - vu);
@@ -657,7 +655,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r);
       const double g = __dmul_rn(dc, gu);
-      const double sv = fma(alpha, soc ? SOC(SOC_DS2 + r) : RW(A_DS, r), RW(A_S, r));
+      const double sv = fma(alpha, soc ? RG(G_DS2, r) : RW(A_DS, r), RW(A_S, r));
       double ct = g - sv;
       if (RS) {
         const double nt = fma(alpha, soc ? RG(G_DN2, r) : RG(G_DN, r), RG(G_N, r));
@@ -701,9 +699,9 @@ __device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_so
       const bool hl = il > 0.0, hu = iu > 0.0;
       double c0 = RW(A_G, r) - RW(A_S, r);
       if (RS) c0 += RG(G_N, r) - RG(G_P, r);
-      const double cprev = first ? c0 : SOC(SOC_CSOC + r);
+      const double cprev = first ? c0 : RG(G_CSOC, r);
       const double cs = a_soc * cprev + SOC(SOC_CT + r);
-      SOC(SOC_CSOC + r) = cs;
+      RG(G_CSOC, r) = cs;
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
@@ -786,7 +784,7 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
 #pragma unroll 1
     for (int r = 0; r < L::R; ++r) {
       const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
-      const double ds = soc ? SOC(SOC_DS2 + r) : RW(A_DS, r);
+      const double ds = soc ? RG(G_DS2, r) : RW(A_DS, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       double vl = RW(A_VL, r), vu = RW(A_VU, r);
       double beta = iu - il;
@@ -1310,7 +1308,7 @@ template <class L>
 __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, double* cold, int b, int lane) {
   const Prob& pr = A.pr; const Opt& o = A.o;
   constexpr int S = L::S, R = L::R;
-  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(3 * R), Q20 = L::soc(3 * R + 6);
+  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(R), Q20 = L::soc(R + 6);
   constexpr int mtot = R * S;
   const double T = pr.T;
 
