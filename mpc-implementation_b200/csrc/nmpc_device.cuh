@@ -23,23 +23,30 @@ constexpr int NX = 8, NU = 6, NPAR = 11;
 // ---- per-lane vectors in shared memory: index e * S + stage ------------------------------------
 enum LvEnt { LV_U = 0, LV_ZL = 6, LV_ZU = 12, LV_X = 18, LV_GL = 26, LV_DX = 32, LV_DU = 40, LV_N = 46 };
 // ---- per-row (constraint) arrays in shared memory: index (arr * R + r) * S + stage --------------
-enum RowArr { A_S = 0, A_Y, A_VL, A_VU, A_G, A_DS, A_DC, A_IL, A_IU, A_NROW };
+// The obstacle rows have no lower bound in this NLP family (lbg = -inf, NMPC_TT.py:280-282), so the two arrays that belong
+// to lower bounds (multiplier v_L and reciprocal slack 1/(s - l)) exist for the five box rows only: they come last and
+// hold NBOX rows instead of R.  A finite lower bound on an obstacle row is refused (NMPC_INVALID_NUMBER).
+enum RowArr { A_S = 0, A_Y, A_VU, A_G, A_DS, A_DC, A_IU, A_NFULL, A_VL = A_NFULL, A_IL, A_NROW };
+constexpr int NBOX = 5;
 // ---- per-stage LQ data (entry-major: e * S + stage).  Entries [0, LQ_DEAD) are dead once the
 //      factorisation has succeeded and are reused by the second-order-correction arrays. ----------
 enum LqEnt {
   LQ_Q = 0,        // 24: 21 = packed lower triangle over (x,y,z,X5,X6,X7), +3 = (theta,theta),(psi,theta),(psi,psi)
-  LQ_NN = 24,      // 3 : sum_j dc_j^2 n_j n_j^T (xx, xy, yy)          -- delta_w part of G^T D_s G
-  LQ_QD = 27,      // 8 : G^T c                                        -- delta_w part of q
-  LQ_QB = 35,      // 8 : G^T beta                                     -- mu part of q
-  LQ_DEAD = 43,
-  LQ_QA = 43,      // 8 : grad l + G^T (Sigma_s c)                     -- q = QA + mu*QB + dw*QD
-  LQ_SV = 51,      // 2 : d2/dv dtheta, d2/dv dpsi (only non-zeros of the control-state block)
-  LQ_RD = 53,      // 6 : diagonal control block Sigma_x (without delta_w)
-  LQ_RB = 59,      // 6 : control gradient per unit mu                 -- r = mu * RB
-  LQ_DD = 65,      // 3 : direction d = (cps*cth, sps*cth, sth)
-  LQ_EE = 68,      // 5 : T*E03, T*E13, T*E23, T*E04, T*E14
-  LQ_DG = 73,      // 5 : dc_r^2 of the five box rows                  -- delta_w part of G^T D_s G
-  LQ_ZERO = 78,    // 1 : 0.0 (lets the Riccati add its stage terms without branches)
+  LQ_DEAD = 24,
+  LQ_QA = 24,      // 8 : grad l + G^T (Sigma_s c)                     -- q = QA + mu*QB + dw*QD
+  LQ_SV = 32,      // 2 : d2/dv dtheta, d2/dv dpsi (only non-zeros of the control-state block)
+  LQ_RD = 34,      // 6 : diagonal control block Sigma_x (without delta_w)
+  LQ_RB = 40,      // 6 : control gradient per unit mu                 -- r = mu * RB
+  LQ_DD = 46,      // 3 : direction d = (cps*cth, sps*cth, sth)
+  LQ_EE = 49,      // 5 : T*E03, T*E13, T*E23, T*E04, T*E14
+  LQ_ZERO = 54,    // 1 : 0.0 (lets the Riccati add its stage terms without branches)
+  LQ_NFOLD = 55,   // ---- the entries below hold the mu / delta_w parts separately, so that an inertia-correction retry
+                   //      re-factors without re-evaluating anything.  Layouts that gain a resident warp by dropping them
+                   //      (Lay::FOLD) fold mu and delta_w into Q / QA in ph_derivs and re-run it on a retry instead.
+  LQ_DG = 55,      // 5 : dc_r^2 of the five box rows                  -- delta_w part of G^T D_s G
+  LQ_NN = 60,      // 3 : sum_j dc_j^2 n_j n_j^T (xx, xy, yy)          -- delta_w part of G^T D_s G
+  LQ_QD = 63,      // 8 : G^T c                                        -- delta_w part of q
+  LQ_QB = 71,      // 8 : G^T beta                                     -- mu part of q
   LQ_N = 79
 };
 // second-order-correction scratch in shared memory (offsets in units of S doubles inside the `soc` region):
@@ -152,19 +159,23 @@ struct Prob {
 #define NMPC_WPB_MAX 8     // 8 warps x 255 registers is the whole register file of an SM
 #endif
 __host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
-template <int N_, int NOBS_>
-struct Lay {
+template <int N_, int NOBS_, bool FOLD_>
+struct LayT {
   static constexpr int N = N_, S = N_ + 1, R = 5 + NOBS_, NOBS = NOBS_;
+  static constexpr bool FOLD = FOLD_;
+  static constexpr int LQ_NE = FOLD_ ? LQ_NFOLD : LQ_N;
   static constexpr int LV0 = 0;
   static constexpr int RW0 = even_up(LV0 + LV_N * S);
-  static constexpr int LQ0 = even_up(RW0 + A_NROW * R * S);
-  // Second-order-correction scratch, R + 14 entries: as many as fit live in the LQ entries that are dead after the
-  // factorisation ([0, LQ_DEAD)), the rest in an extra region.  The last 14 entries (du_soc, q') are addressed as
-  // blocks by the Riccati sweeps, so they are never split: SOC_LO <= R unless everything fits.
-  static constexpr int SOC_N = R + 14;
+  static constexpr int RW_N = (A_NFULL * R + (A_NROW - A_NFULL) * NBOX) * S;
+  __host__ __device__ static constexpr int rw(int arr, int r) { return RW0 + (arr < A_NFULL ? arr * R + r : A_NFULL * R + (arr - A_NFULL) * NBOX + r) * S; }
+  static constexpr int LQ0 = even_up(RW0 + RW_N);
+  // Second-order-correction scratch in shared memory: du_soc [6] and q' [8], in the LQ entries that are dead after
+  // the factorisation (the residual of the last trial point, c_t [R], goes to the cold scratch with the other SOC arrays).
+  static constexpr int SOC_N = 14;
   static constexpr bool SOC_ALIAS = SOC_N <= LQ_DEAD;
-  static constexpr int SOC_LO = SOC_ALIAS ? SOC_N : (R < LQ_DEAD ? R : LQ_DEAD);
-  static constexpr int SOCX0 = even_up(LQ0 + LQ_N * S);
+  static constexpr int SOC_LO = SOC_N;
+  static_assert(SOC_ALIAS, "SOC scratch must fit the dead LQ entries");
+  static constexpr int SOCX0 = even_up(LQ0 + LQ_NE * S);
   static constexpr int STG0 = even_up(SOCX0 + (SOC_N - SOC_LO) * S);
   __host__ __device__ static constexpr int soc(int e) { return e < SOC_LO ? LQ0 + e * S : SOCX0 + (e - SOC_LO) * S; }
   static constexpr int OBS0 = STG0 + STG_N;
@@ -177,16 +188,23 @@ struct Lay {
   //      restoration phase): restoration row arrays, reference controls, the restoration problem's own filter, and three
   //      slots that hold a saved iterate + step
   static constexpr int RSZ = R * S;
-  static constexpr int CG_ROWS = 0;                     // 12 arrays [R][S]: n, p, z_n, z_p, dn, dp, dy, dn_soc, dp_soc, dy_soc, ds_soc, c_soc
-  static constexpr int CG_UR = 12 * RSZ;                // [6][S] reference controls x_R of the restoration problem
+  static constexpr int CG_ROWS = 0;                     // 13 arrays [R][S]: n, p, z_n, z_p, dn, dp, dy, dn_soc, dp_soc, dy_soc, ds_soc, c_soc, c_t
+  static constexpr int CG_UR = 13 * RSZ;                // [6][S] reference controls x_R of the restoration problem
   static constexpr int CG_FILT = CG_UR + 6 * S;         // [2][FILT_CAP][2]: filter of the original problem, of the restoration problem
   static constexpr int CG_PARK = CG_FILT + 4 * FILT_CAP;   // [ALG_N] algorithm state of the original problem while the restoration phase runs
   static constexpr int CG_SLOT = CG_PARK + ALG_N;
-  static constexpr int SLOT_N = 32 * S + 10 * RSZ;      // U ZL ZU (18 S) | DX DU (14 S) | S Y VL VU (4 RS) | IL IU (2 RS) | n p z_n z_p (4 RS)
+  static constexpr int SLOT_N = 32 * S + 8 * RSZ + 2 * NBOX * S;   // U ZL ZU (18 S) | DX DU (14 S) | S Y VU IU (4 RS) | VL IL (2 NBOX S) | n p z_n z_p (4 RS)
   static constexpr int COLD_TOTAL = even_up(CG_SLOT + 3 * SLOT_N);
   static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);
   static constexpr int WPB = WPB_FIT < 1 ? 1 : (WPB_FIT > NMPC_WPB_MAX ? NMPC_WPB_MAX : WPB_FIT);
 };
+
+// FOLD where it buys another resident warp per SM (big layouts), the separate mu / delta_w entries otherwise
+#ifndef NMPC_FOLD_MIN_S
+#define NMPC_FOLD_MIN_S 20     // measured: (30,10) 3 -> 4 warps per SM is +16 % (config 5); (15,10) 6 -> 7 warps is -3 % (config 4), so short horizons keep the separate entries
+#endif
+template <int N_, int NOBS_>
+using Lay = LayT<N_, NOBS_, (N_ + 1 >= NMPC_FOLD_MIN_S) && (LayT<N_, NOBS_, true>::WPB > LayT<N_, NOBS_, false>::WPB)>;
 
 // ---- stage state of one lane -----------------------------------------------------------------------
 struct Stage {

@@ -36,8 +36,10 @@ template <class L>
 __device__ __forceinline__ double q_entry(int k, int i, int j, double dw) {
   const int qi = q_index(i, j);
   double v = qi >= 0 ? smem[L::LQ0 + (LQ_Q + qi) * L::S + k] : 0.0;
-  if (i < 2 && j < 2) v += dw * smem[L::LQ0 + (LQ_NN + i + j) * L::S + k];
-  else if (i == j && i != 4) v += dw * smem[L::LQ0 + (LQ_DG + ((i == 2) ? 0 : (i == 3 ? 1 : i - 3))) * L::S + k];
+  if (!L::FOLD) {
+    if (i < 2 && j < 2) v += dw * smem[L::LQ0 + (LQ_NN + i + j) * L::S + k];
+    else if (i == j && i != 4) v += dw * smem[L::LQ0 + (LQ_DG + ((i == 2) ? 0 : (i == 3 ? 1 : i - 3))) * L::S + k];
+  }
   return v;
 }
 
@@ -77,12 +79,14 @@ __device__ void ric_map_build(int lane, unsigned* __restrict__ out /* [RIC_MAP_W
         else {
           const int i = a - 6, j = b - 6, qi = q_index(i, j);
           if (qi >= 0) p0 = LQ_Q + qi;
-          if (i < 2 && j < 2) p2 = LQ_NN + i + j;
-          else if (i == j && i != 4) p2 = LQ_DG + ((i == 2) ? 0 : (i == 3 ? 1 : i - 3));
+          if (!L::FOLD) {
+            if (i < 2 && j < 2) p2 = LQ_NN + i + j;
+            else if (i == j && i != 4) p2 = LQ_DG + ((i == 2) ? 0 : (i == 3 ? 1 : i - 3));
+          }
         }
       } else {
         if (b < 6) p1 = LQ_RB + b;
-        else { p0 = LQ_QA + (b - 6); p1 = LQ_QB + (b - 6); p2 = LQ_QD + (b - 6); }
+        else { p0 = LQ_QA + (b - 6); if (!L::FOLD) { p1 = LQ_QB + (b - 6); p2 = LQ_QD + (b - 6); } }
       }
       // H[a][b] = z_a^T P+ z_b,  h[b] = z_b^T p+ : the part that is ONE scaled entry of P+ / p+ / Y_special
       const int ca = (a >= 1 && a < 6) ? 1 : 0, cb = (b >= 1 && b < 6) ? 1 : 0;    // powers of T
@@ -156,7 +160,8 @@ __device__ __noinline__ bool riccati_factor(double T, double* __restrict__ ric, 
   for (int o = lane; o < 72; o += 32) {
     const int i = o >> 3, j = o & 7;
     smem[PP + i * 9 + j] = i < 8 ? q_entry<L>(N, i, j, dw)
-                                 : smem[LQ0 + (LQ_QA + j) * S + N] + mu * smem[LQ0 + (LQ_QB + j) * S + N] + dw * smem[LQ0 + (LQ_QD + j) * S + N];
+                                 : (L::FOLD ? smem[LQ0 + (LQ_QA + j) * S + N]
+                                            : smem[LQ0 + (LQ_QA + j) * S + N] + mu * smem[LQ0 + (LQ_QB + j) * S + N] + dw * smem[LQ0 + (LQ_QD + j) * S + N]);
   }
   __syncwarp();
 #pragma unroll 1

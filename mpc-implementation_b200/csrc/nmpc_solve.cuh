@@ -128,18 +128,20 @@ __device__ __forceinline__ int align_warps(int g, int working) {
 }
 
 #define LV(e) smem[L::LV0 + (e) * L::S + lane]
-#define RW(arr, r) smem[L::RW0 + ((arr) * L::R + (r)) * L::S + lane]
+#define RW(arr, r) smem[L::rw(arr, r) + lane]
+// lower-bound arrays exist for the box rows only (nmpc_device.cuh: RowArr)
+#define VL_(r) ((r) < NBOX ? RW(A_VL, r) : 0.0)
+#define IL_(r) ((r) < NBOX ? RW(A_IL, r) : 0.0)
 #define LQ(e) smem[L::LQ0 + (e) * L::S + lane]
 #define SOC(e) smem[L::soc(e) + lane]
 #define RES(i) smem[L::RES0 + (i)]
 #define PAR(i) smem[L::PAR0 + (i)]
-#define SOC_CT 0
-#define SOC_DUS (L::R)
-#define SOC_Q2 (L::R + 6)
+#define SOC_DUS 0
+#define SOC_Q2 6
 // restoration row arrays in the cold scratch: (arr * R + r) * S + lane
 #define RG(arr, r) cold[((arr) * L::R + (r)) * L::S + lane]
 #define UREF(i) cold[L::CG_UR + (i) * L::S + lane]
-enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DY, G_DN2, G_DP2, G_DY2, G_DS2, G_CSOC };     // the last two: SOC step in s, SOC residual
+enum RgArr { G_N = 0, G_P, G_ZN, G_ZP, G_DN, G_DP, G_DY, G_DN2, G_DP2, G_DY2, G_DS2, G_CSOC, G_CT };     // the last three: SOC step in s, SOC residual, residual of the last trial point
 
 // T-scaled non-zeros of the dynamics Jacobian A_k - I of this lane's stage
 struct Dyn { double e03, e13, e23, e04, e14; };
@@ -264,12 +266,12 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
   double c3[3] = {dy.e03, dy.e13, dy.e23}, c4[2] = {dy.e04, dy.e14};
   scan_excl<3>(c3, lane); scan_excl<2>(c4, lane);
   double zmax = 0.0;
-  // scratch in row arrays that are not live yet: A_G = row max, A_IL / A_IU = obstacle normal
+  // scratch in row arrays that are not live yet: A_G = row max, A_S / A_IU = obstacle normal
   if (act) {
 #pragma unroll 1
     for (int jn = 0; jn < L::NOBS; ++jn) {
       double nx, ny, iD; obs_value<L>(st.X, jn, nx, ny, iD);
-      RW(A_G, 5 + jn) = 0.0; RW(A_IL, 5 + jn) = nx; RW(A_IU, 5 + jn) = ny;
+      RW(A_G, 5 + jn) = 0.0; RW(A_S, 5 + jn) = nx; RW(A_IU, 5 + jn) = ny;
     }
   }
 #pragma unroll 1
@@ -284,7 +286,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
       zmax = fmax(zmax, fmax(fabs(pv2), fabs(pt2)));
 #pragma unroll 1
       for (int jn = 0; jn < L::NOBS; ++jn) {
-        const double nx = RW(A_IL, 5 + jn), ny = RW(A_IU, 5 + jn);
+        const double nx = RW(A_S, 5 + jn), ny = RW(A_IU, 5 + jn);
         const double m1 = fabs(nx * pv0 + ny * pv1), m2 = fabs(nx * pt0 + ny * pt1), m3 = fabs(nx * pp0 + ny * pp1);
         RW(A_G, 5 + jn) = fmax(RW(A_G, 5 + jn), fmax(m1, fmax(m2, m3)));
       }
@@ -308,7 +310,7 @@ template <class L>
 __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
   const Prob& pr = A.pr; constexpr int N = L::N;
   const bool act = lane <= N, hasu = lane < N;
-  double u[6]; int nz = 0;
+  double u[6]; int nz = 0; bool bad_lb = false;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     u[i] = act ? LV(LV_U + i) : 0.0;
@@ -327,14 +329,16 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
       const Bnd b = row_bounds<L>(A, lane, r, dc);
       const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
       RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = 0.0;
-      RW(A_VL, r) = b.hl ? 1.0 : 0.0; RW(A_VU, r) = b.hu ? 1.0 : 0.0;
-      RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
+      RW(A_VU, r) = b.hu ? 1.0 : 0.0; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
+      if (box) { RW(A_VL, r) = b.hl ? 1.0 : 0.0; RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; }
+      else if (b.hl) bad_lb = true;                     // a lower bound on an obstacle row: not this NLP family
       nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
     };
     FOR_ROWS(st.X, body);
   }
   __syncwarp();
-  return __reduce_add_sync(FULL, nz);
+  const int total = __reduce_add_sync(FULL, nz);
+  return __any_sync(FULL, bad_lb) ? -1 : total;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -387,7 +391,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r);
       const double g = __dmul_rn(dc, gu);
-      const double s = RW(A_S, r), y = RW(A_Y, r), vl = RW(A_VL, r), vu = RW(A_VU, r), il = RW(A_IL, r), iu = RW(A_IU, r);
+      const double s = RW(A_S, r), y = RW(A_Y, r), vl = box ? RW(A_VL, r) : 0.0, vu = RW(A_VU, r), il = box ? RW(A_IL, r) : 0.0, iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       RW(A_G, r) = g;
       double c = g - s;
@@ -407,23 +411,25 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
         du_l = fmax(du_l, fmax(fabs(gn), fabs(gp))); if (want1) du1 += fabs(gn) + fabs(gp);
         sumz += q.zn + q.zp;
         compl_(q.n * q.zn); compl_(q.p * q.zp);
+      } else if (L::FOLD && !ls) {      // mu and delta_w folded in: Q gets G^T (Sigma_s + dw) G, q gets G^T ((Sigma_s + dw) c + mu beta)
+        ya = (sig + dw) * c + mu * beta; w = dc * dc * (sig + dw); yad = y;
       } else {
         ya = ls ? (vu - vl) : sig * c; w = dc * dc * sig; yad = y;
       }
       if (box) {
         a[si] += dc * yad; qa[si] += dc * ya;
-        if (!RS) { qb[si] += dc * beta; qd[si] += dc * c; }
+        if (!RS && !L::FOLD) { qb[si] += dc * beta; qd[si] += dc * c; }
         if (si == 3) q22 += w; else q66[tri(si < 3 ? si : si - 2, si < 3 ? si : si - 2)] += w;
-        LQ(LQ_DG + r) = RS ? 0.0 : dc * dc;
+        if (!L::FOLD) LQ(LQ_DG + r) = RS ? 0.0 : dc * dc;
       } else {
         const double cur = ls ? 0.0 : -y * dc * iD;        // y * d2h,  d2h = -(I - n n^T)/D
         q66[0] += w * nx * nx + cur * (1.0 - nx * nx);
         q66[1] += w * nx * ny - cur * nx * ny;
         q66[2] += w * ny * ny + cur * (1.0 - ny * ny);
-        if (!RS) { nn[0] += dc * dc * nx * nx; nn[1] += dc * dc * nx * ny; nn[2] += dc * dc * ny * ny; }
+        if (!RS && !L::FOLD) { nn[0] += dc * dc * nx * nx; nn[1] += dc * dc * nx * ny; nn[2] += dc * dc * ny * ny; }
         const double gy = -dc * yad, ga = -dc * ya;
         a[0] += gy * nx; a[1] += gy * ny; qa[0] += ga * nx; qa[1] += ga * ny;
-        if (!RS) {
+        if (!RS && !L::FOLD) {
           const double gb = -dc * beta, gd = -dc * c;
           qb[0] += gb * nx; qb[1] += gb * ny; qd[0] += gd * nx; qd[1] += gd * ny;
         }
@@ -442,10 +448,14 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
     FOR_ROWS(st.X, body);
 #pragma unroll
     for (int e = 0; e < 21; ++e) LQ(LQ_Q + e) = q66[e];
-    LQ(LQ_NN + 0) = nn[0]; LQ(LQ_NN + 1) = nn[1]; LQ(LQ_NN + 2) = nn[2];
     LQ(LQ_ZERO) = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { LQ(LQ_QA + i) = qa[i]; LQ(LQ_QB + i) = ls ? 0.0 : qb[i]; LQ(LQ_QD + i) = ls ? 0.0 : qd[i]; }
+    for (int i = 0; i < 8; ++i) LQ(LQ_QA + i) = qa[i];
+    if (!L::FOLD) {
+      LQ(LQ_NN + 0) = nn[0]; LQ(LQ_NN + 1) = nn[1]; LQ(LQ_NN + 2) = nn[2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { LQ(LQ_QB + i) = ls ? 0.0 : qb[i]; LQ(LQ_QD + i) = ls ? 0.0 : qd[i]; }
+    }
     LQ(LQ_DD + 0) = st.cps * st.cth; LQ(LQ_DD + 1) = st.sps * st.cth; LQ(LQ_DD + 2) = st.sth;
     LQ(LQ_EE + 0) = dy.e03; LQ(LQ_EE + 1) = dy.e13; LQ(LQ_EE + 2) = dy.e23; LQ(LQ_EE + 3) = dy.e04; LQ(LQ_EE + 4) = dy.e14;
     LQ(LQ_Q + 21) = q22;
@@ -523,7 +533,7 @@ __device__ __noinline__ void ph_lsy(const SolveArgs& A, int lane, bool ok) {
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r);
       const double gd = box ? dc * dx[si] : -dc * (nx * dx[0] + ny * dx[1]);
-      const double yv = gd + (RW(A_VU, r) - RW(A_VL, r));
+      const double yv = gd + (RW(A_VU, r) - (box ? RW(A_VL, r) : 0.0));
       RW(A_Y, r) = yv; ymax = fmax(ymax, fabs(yv));
     };
     FOR_ROWS(X, body);
@@ -553,7 +563,7 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
 #pragma unroll
     for (int i = 0; i < 8; ++i) { X[i] = LV(LV_X + i); dx[i] = LV(LV_DX + i); }
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
-      const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), vl = RW(A_VL, r), vu = RW(A_VU, r);
+      const double dc = RW(A_DC, r), s = RW(A_S, r), il = box ? RW(A_IL, r) : 0.0, iu = RW(A_IU, r), vl = box ? RW(A_VL, r) : 0.0, vu = RW(A_VU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       double beta = iu - il;
       if (hl && !hu) beta += kd;
@@ -664,7 +674,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
         const double ns = (nt), ps = (pt);
         prod *= ns * ps; cnt += 2; dt += ns + ps; l += A.o.resto_rho * (nt + pt);
       }
-      SOC(SOC_CT + r) = ct; th += fabs(ct);
+      RG(G_CT, r) = ct; th += fabs(ct);      // (only the second-order correction reads it back)
       const Bnd b = row_bounds<L>(A, lane, r, dc);
       if (b.hl) { prod *= (sv - b.lo); ++cnt; }
       if (b.hu) { prod *= (b.hi - sv); ++cnt; }
@@ -695,17 +705,17 @@ __device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_so
     }
     const double kd = A.o.kappa_d;
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
-      const double dc = RW(A_DC, r), il = RW(A_IL, r), iu = RW(A_IU, r);
+      const double dc = RW(A_DC, r), il = box ? RW(A_IL, r) : 0.0, iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
       double c0 = RW(A_G, r) - RW(A_S, r);
       if (RS) c0 += RG(G_N, r) - RG(G_P, r);
       const double cprev = first ? c0 : RG(G_CSOC, r);
-      const double cs = a_soc * cprev + SOC(SOC_CT + r);
+      const double cs = a_soc * cprev + RG(G_CT, r);
       RG(G_CSOC, r) = cs;
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
-      const double sig = RW(A_VL, r) * il + RW(A_VU, r) * iu;
+      const double sig = (box ? RW(A_VL, r) : 0.0) * il + RW(A_VU, r) * iu;
       double yh;
       if (RS) {
         const double y = RW(A_Y, r);
@@ -743,7 +753,7 @@ __device__ __noinline__ void ph_repair(const SolveArgs& A, int lane, double mu, 
     for (int r = 0; r < L::R; ++r) {
       const Bnd b = row_bounds<L>(A, lane, r, RW(A_DC, r));
       double s = RW(A_S, r);
-      if (b.hl && s - b.lo < smin) { const double t = safe_value(s - b.lo, b.lo); s = b.lo + t; RW(A_VL, r) = clampz(RW(A_VL, r), t); RW(A_IL, r) = rcp(t); }
+      if (r < NBOX && b.hl && s - b.lo < smin) { const double t = safe_value(s - b.lo, b.lo); s = b.lo + t; RW(A_VL, r) = clampz(RW(A_VL, r), t); RW(A_IL, r) = rcp(t); }
       if (b.hu && b.hi - s < smin) { const double t = safe_value(b.hi - s, b.hi); s = b.hi - t; RW(A_VU, r) = clampz(RW(A_VU, r), t); RW(A_IU, r) = rcp(t); }
       RW(A_S, r) = s;
       if (RS) {
@@ -783,10 +793,10 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
   if (act) {
 #pragma unroll 1
     for (int r = 0; r < L::R; ++r) {
-      const double dc = RW(A_DC, r), s = RW(A_S, r), il = RW(A_IL, r), iu = RW(A_IU, r), y = RW(A_Y, r);
+      const double dc = RW(A_DC, r), s = RW(A_S, r), il = IL_(r), iu = RW(A_IU, r), y = RW(A_Y, r);
       const double ds = soc ? RG(G_DS2, r) : RW(A_DS, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      double vl = RW(A_VL, r), vu = RW(A_VU, r);
+      double vl = VL_(r), vu = RW(A_VU, r);
       double beta = iu - il;
       if (hl && !hu) beta += kd;
       if (hu && !hl) beta -= kd;
@@ -799,7 +809,8 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       double il2 = 0.0, iu2 = 0.0;
       if (hl) { const double sl = sn - b.lo; il2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
       if (hu) { const double sl = b.hi - sn; iu2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
-      RW(A_S, r) = sn; RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_IL, r) = il2; RW(A_IU, r) = iu2;
+      RW(A_S, r) = sn; RW(A_VU, r) = vu; RW(A_IU, r) = iu2;
+      if (r < NBOX) { RW(A_VL, r) = vl; RW(A_IL, r) = il2; }
       if (RS) {
         const double n0 = RG(G_N, r), p0 = RG(G_P, r), zn0 = RG(G_ZN, r), zp0 = RG(G_ZP, r);
         const double dn = soc ? RG(G_DN2, r) : RG(G_DN, r), dp = soc ? RG(G_DP2, r) : RG(G_DP, r);
@@ -829,10 +840,12 @@ __device__ __noinline__ void ph_slot(double* cold, int slot, bool save, bool wit
   };
   cp(L::LV0, 0, 18 * S);                                   // U, ZL, ZU
   cp(L::LV0 + LV_DX * S, 18 * S, 14 * S);                  // DX, DU
-  cp(L::RW0, 32 * S, 4 * RSZ);                             // S, Y, VL, VU
-  cp(L::RW0 + A_IL * RSZ, 32 * S + 4 * RSZ, 2 * RSZ);      // IL, IU
+  cp(L::rw(A_S, 0), 32 * S, 3 * RSZ);                      // S, Y, VU
+  cp(L::rw(A_IU, 0), 32 * S + 3 * RSZ, RSZ);               // IU
+  cp(L::rw(A_VL, 0), 32 * S + 4 * RSZ, 2 * NBOX * S);      // VL, IL (box rows)
+  constexpr int R0 = 32 * S + 4 * RSZ + 2 * NBOX * S;
   if (with_resto)
-    for (int i = lane; i < 4 * RSZ; i += 32) { if (save) sl[32 * S + 6 * RSZ + i] = cold[i]; else cold[i] = sl[32 * S + 6 * RSZ + i]; }
+    for (int i = lane; i < 4 * RSZ; i += 32) { if (save) sl[R0 + i] = cold[i]; else cold[i] = sl[R0 + i]; }
   __syncwarp();
 }
 
@@ -847,7 +860,8 @@ __device__ __noinline__ void ph_resto_init(const SolveArgs& A, int lane, double 
       const double c = RW(A_G, r) - RW(A_S, r);
       const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h), pv = c + nv;
       RG(G_N, r) = nv; RG(G_P, r) = pv; RG(G_ZN, r) = mu / nv; RG(G_ZP, r) = mu / pv;
-      RW(A_VL, r) = fmin(rho, RW(A_VL, r)); RW(A_VU, r) = fmin(rho, RW(A_VU, r)); RW(A_Y, r) = 0.0;
+      if (r < NBOX) RW(A_VL, r) = fmin(rho, RW(A_VL, r));
+      RW(A_VU, r) = fmin(rho, RW(A_VU, r)); RW(A_Y, r) = 0.0;
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) { UREF(i) = LV(LV_U + i); LV(LV_ZL + i) = fmin(rho, LV(LV_ZL + i)); LV(LV_ZU + i) = fmin(rho, LV(LV_ZU + i)); }
@@ -897,12 +911,13 @@ __device__ __noinline__ double ph_resto_finish(const SolveArgs& A, int lane, dou
     for (int r = 0; r < L::R; ++r) {
       const double dc = RW(A_DC, r);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      const double s0 = sl[32 * S + (A_S * L::R + r) * S + lane], vl0 = sl[32 * S + (A_VL * L::R + r) * S + lane], vu0 = sl[32 * S + (A_VU * L::R + r) * S + lane];
+      const double s0 = sl[32 * S + (A_S * L::R + r) * S + lane], vu0 = sl[32 * S + (A_VU * L::R + r) * S + lane];
+      const double vl0 = r < NBOX ? sl[32 * S + 4 * L::RSZ + r * S + lane] : 0.0;
       const double s1 = RW(A_S, r);
       double vl = 0.0, vu = 0.0;
-      if (b.hl) upd(vl0, (s0 - b.lo), (s1 - b.lo), vl);
+      if (b.hl && r < NBOX) upd(vl0, (s0 - b.lo), (s1 - b.lo), vl);
       if (b.hu) upd(vu0, (b.hi - s0), (b.hi - s1), vu);
-      if (pass == 1) { RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_Y, r) = 0.0; RW(A_DS, r) = 0.0; }
+      if (pass == 1) { if (r < NBOX) RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_Y, r) = 0.0; RW(A_DS, r) = 0.0; }
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) if (pass == 1) LV(LV_DU + i) = 0.0;
@@ -920,7 +935,7 @@ __device__ __noinline__ void ph_unit_mults(const SolveArgs& A, int lane) {
   }
   if (lane <= L::N) {
 #pragma unroll 1
-    for (int r = 0; r < L::R; ++r) { RW(A_VL, r) = RW(A_IL, r) > 0.0 ? 1.0 : 0.0; RW(A_VU, r) = RW(A_IU, r) > 0.0 ? 1.0 : 0.0; }
+    for (int r = 0; r < L::R; ++r) { if (r < NBOX) RW(A_VL, r) = RW(A_IL, r) > 0.0 ? 1.0 : 0.0; RW(A_VU, r) = RW(A_IU, r) > 0.0 ? 1.0 : 0.0; }
   }
   __syncwarp();
 }
@@ -1308,7 +1323,7 @@ template <class L>
 __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, double* cold, int b, int lane) {
   const Prob& pr = A.pr; const Opt& o = A.o;
   constexpr int S = L::S, R = L::R;
-  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(R), Q20 = L::soc(R + 6);
+  constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(SOC_DUS), Q20 = L::soc(SOC_Q2);
   constexpr int mtot = R * S;
   const double T = pr.T;
 
@@ -1321,6 +1336,10 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     __syncwarp();
   }
   const int nzt = ph_start<L>(A, lane);
+  if (nzt < 0) {       // a finite lower bound on an obstacle row (never the case in the reference's NLPs): refused, reported as data
+    ph_output<L>(A, b, lane, df, NMPC_INVALID_NUMBER, 0);
+    return;
+  }
   alg_init<L>(o.mu_init, o.tau_min, o.tol);
   for (int f = F_NALG + lane; f < F_END; f += 32) AL(f) = 0.0;
   __syncwarp();
@@ -1366,12 +1385,14 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
       if (st >= 0) { status = st; break; }
     }
     // ---- barrier parameter
+    const double mu_before = AL(F_MU);
     if (!update_mu<L>(A, cold, lane, df, nz, mu_floor, du_inf, pr_inf, pmax, pmin, sd, sc)) {
       if (mode == 0) status = NMPC_STEP_TOO_SMALL;
       else status = RES(R_OINF) <= 1e2 * o.tol ? NMPC_RESTORATION_FAILED : NMPC_INFEASIBLE_PROBLEM;
       break;
     }
     const double mu = AL(F_MU);
+    if (L::FOLD && mode == 0 && mu != mu_before) ph_derivs<L, false>(A, lane, false, df, mu, 0.0, false, cold);   // folded layouts: mu is inside q
     // ---- search direction with inertia correction
     const double ls_before = AL(F_C0 + 1);
     double dw = 0.0; bool ok = false;
@@ -1385,6 +1406,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
         else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? o.dw_inc_first * dw : o.dw_inc * dw;
         if (dw > o.dw_max) break;
         if (mode) ph_derivs<L, true>(A, lane, false, df, mu, dw, false, cold);       // restoration rows enter with Om(dw)
+        else if (L::FOLD) ph_derivs<L, false>(A, lane, false, df, mu, dw, false, cold);   // folded layouts: dw is inside Q / q
       }
     }
     bool goto_resto = !ok;                  // step computation failed: fall back to the restoration phase
