@@ -74,7 +74,9 @@ for r in data:
 names = subprocess.run(["c++filt"], input="\n".join(agg), capture_output=True, text=True).stdout.splitlines()
 ti = sum(g["inst"] for g in agg.values()); ts = sum(g["samples"] for g in agg.values())
 print(f"\n## per device function: executed warp instructions ({ti:.3e}) and stall samples ({ts})")
-for (fn, g), nm in sorted(zip(agg.items(), names), key=lambda t: -t[0][1]["samples"])[:18]:
+for (fn, g), nm in sorted(zip(agg.items(), names), key=lambda t: -t[0][1]["samples"])[:40]:
+    if g["samples"] < 0.0002 * ts and not any(k in nm for k in ("ph_load", "ph_output")):
+        continue
     nm = re.sub(r"nmpc::Lay<\d+, \d+>", "L", nm).replace("nmpc::SolveArgs const&", "A"); nm = re.sub(r"_INTERNAL_\w+::", "", nm)
     top = sorted(((c[6:], g[c]) for c in stall_cols), key=lambda t: -t[1])[:3]
     print(f"  {100 * g['inst'] / ti:5.1f}% inst {100 * g['samples'] / ts:5.1f}% samples  {nm[:60]:60s} " + " ".join(f"{c} {100 * x / max(1, g['samples']):.0f}%" for c, x in top))
