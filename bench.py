@@ -34,15 +34,15 @@ UNIT = "solves/s"
 # BASELINE.json configs[1..4] ("config 2..5" in SURVEY.md section 8d), per GPU.  cpu = (instances, consecutive closed-loop
 # steps) of the bounded CPU sample timed beside the GPU number (about 10-30 s of oracle work on 16 threads).
 CONFIGS = {
-    2: dict(scenario="nmpc_tt", N=15, batch=4096, jitter=0, mix=None, cpu=(4096, 4), ref=(512, None),
+    2: dict(scenario="nmpc_tt", N=15, batch=4096, jitter=0, mix=None, cpu=(4096, 12), ref=(1024, None),
             what="Python/NMPC_TT.py batched over randomised UAV states and target speeds (BASELINE.json configs[1])"),
-    3: dict(scenario="t_trajectory", N=15, batch=65536, jitter=0, mix="plus_trajectory", cpu=(8192, 2), ref=(2048, None),
+    3: dict(scenario="t_trajectory", N=15, batch=65536, jitter=0, mix="plus_trajectory", cpu=(16384, 3), ref=(2048, None),
             what="T_Trajectory / Plus Trajectory target paths, half the batch on each schedule, random schedule phase "
                  "(BASELINE.json configs[2])"),
-    4: dict(scenario="10_obstacles", N=15, batch=32768, jitter=3, mix=None, cpu=(4096, 2), ref=(1024, None),
+    4: dict(scenario="10_obstacles", N=15, batch=32768, jitter=3, mix=None, cpu=(8192, 4), ref=(1024, None),
             what="10_obstacles.py (15 g rows per stage), per-instance obstacle layouts, 262144 instances over 8 GPUs "
                  "(BASELINE.json configs[3])"),
-    5: dict(scenario="race_track_2", N=30, batch=131072, jitter=10, mix=None, cpu=(1024, 1), ref=(256, None),
+    5: dict(scenario="race_track_2", N=30, batch=131072, jitter=10, mix=None, cpu=(2048, 3), ref=(256, None),
             what="Race Track 2 at twice the reference horizon (N = 30), per-instance obstacle layouts, 1M instances over "
                  "8 GPUs (BASELINE.json configs[4])"),
 }
