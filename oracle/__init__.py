@@ -50,6 +50,7 @@ def lib():
         _lib.oracle_solve_log.restype = C.c_int
         _lib.oracle_eval_traj.restype = C.c_int
         _lib.oracle_solve_traj.restype = C.c_int
+        _lib.oracle_solve_warm.restype = C.c_int
         _lib.oracle_set_option.restype = C.c_int
         _lib.oracle_set_option.argtypes = [C.c_char_p, C.c_double]
     return _lib
@@ -102,8 +103,10 @@ def evaluate(spec: OracleSpec, obs: np.ndarray, w, p, lam_g=None, sigma=1.0, hes
 
 
 def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=False, scaling=True,
-          max_iter=0, tol=0.0, nthreads=None, want_g=True, want_lam=True, target_traj=None):
-    """Batch solve: p (B,11), x0 (B,6N) -> dict(x,f,g,lam_x,lam_g,status,iters,stats)."""
+          max_iter=0, tol=0.0, nthreads=None, want_g=True, want_lam=True, target_traj=None, lam_x0=None, lam_g0=None):
+    """Batch solve: p (B,11), x0 (B,6N) -> dict(x,f,g,lam_x,lam_g,status,iters,stats).
+    lam_x0 (B,6N), lam_g0 (B,n_g): multiplier guesses of the NON-REFERENCE warm-start mode (Options::ws_* in
+    nmpc_oracle.cpp); a NaN in lam_x0[b, 0] cold-starts instance b."""
     N, n_obs = spec.N, spec.n_obs
     nw, ng = 6 * N, (5 + n_obs) * (N + 1)
     p = _c(p).reshape(-1, 11); B = p.shape[0]
@@ -119,7 +122,10 @@ def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=
     if nthreads is None:
         nthreads = min(B, os.cpu_count() or 1)
     tg = None if target_traj is None else _c(target_traj).reshape(B, N, 2)
-    lib().oracle_solve_traj(C.byref(spec), C.c_int(B), _dp(p), _dp(x0), _dp(tg), _dp(lbx), _dp(ubx), _dp(lbg), _dp(ubg),
+    lx0 = None if lam_x0 is None else _c(lam_x0).reshape(B, nw)
+    lg0 = None if lam_g0 is None else _c(lam_g0).reshape(B, ng)
+    assert (lx0 is None) == (lg0 is None)
+    lib().oracle_solve_warm(C.byref(spec), C.c_int(B), _dp(p), _dp(x0), _dp(tg), _dp(lx0), _dp(lg0), _dp(lbx), _dp(ubx), _dp(lbg), _dp(ubg),
                        _dp(obs), C.c_int(int(obs_per_instance)), C.c_int(int(scaling)), C.c_int(int(max_iter)),
                        C.c_double(float(tol)),
                        _dp(x), _dp(f), _dp(g), _dp(lam_x), _dp(lam_g), _ip(status), _ip(iters), _ip(stats),

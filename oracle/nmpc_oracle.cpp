@@ -400,6 +400,12 @@ struct Options {
   double bound_mult_reset_threshold = 1e3, constr_mult_reset_threshold = 0.0;
   double resto_theta_max_fact = 1e8;
   int resto_explicit = 0;      // 1: factor the restoration KKT system with the n/p variables explicit (validation of the elimination)
+  // NON-REFERENCE fast mode (the scripts pass no lam_x0 / lam_g0 and leave warm_start_init_point = no): IPOPT's
+  // WarmStartIterateInitializer for instances that come with a multiplier guess [3P]
+  double ws_mu_init = 1e-4;                                          // mu_init a warm-started solve begins with
+  double ws_bound_push = 1e-3, ws_bound_frac = 1e-3, ws_slack_push = 1e-3, ws_slack_frac = 1e-3;   // warm_start_(slack_)bound_push / frac
+  double ws_mult_push = 1e-3;                                        // warm_start_mult_bound_push
+  double ws_mult_init_max = 1e6;                                     // warm_start_mult_init_max
 };
 
 struct Counters {
@@ -1235,8 +1241,10 @@ struct Algo {
 struct Result { int32_t status; int32_t iters; double f; Counters c; };
 
 // Original problem: scaling, bounds, starting point (DefaultIterateInitializer), main loop, finalisation.
+// lamx0 / lamg0 (CasADi's lam_x0 / lam_g0, unscaled; NULL or NaN in lamx0[0] = none): warm start of the multipliers, see Options::ws_*
 Result solve_instance(Instance& I, const Options& o, const double* x0, const double* lbx, const double* ubx, const double* lbg,
-                      const double* ubg, double* x_out, double* g_out, double* lamx_out, double* lamg_out, std::vector<IterLog>* log) {
+                      const double* ubg, double* x_out, double* g_out, double* lamx_out, double* lamg_out, std::vector<IterLog>* log,
+                      const double* lamx0 = nullptr, const double* lamg0 = nullptr) {
   Result res{}; Counters C;
   OrigNlp P(I);
   const int n = P.n0, m = P.m;
@@ -1266,8 +1274,9 @@ Result solve_instance(Instance& I, const Options& o, const double* x0, const dou
     P.dL[r] = lbg[r] > -1e19 ? relax_lo(P.dc[r] * lbg[r]) : -INF;
     P.dU[r] = ubg[r] < 1e19 ? relax_hi(P.dc[r] * ubg[r]) : INF;
   }
-  auto push = [&](double& v, double lo, double hi) {
-    const bool hl = lo > -INF, hu = hi < INF; const double k1 = o.bound_push, k2 = o.bound_frac;
+  const bool warm = lamx0 && lamg0 && !std::isnan(lamx0[0]);
+  auto push = [&](double& v, double lo, double hi, double k1, double k2) {
+    const bool hl = lo > -INF, hu = hi < INF;
     if (hl && hu) {
       const double pl = std::min(k1 * std::max(1.0, std::fabs(lo)), k2 * (hi - lo));
       const double pu = std::min(k1 * std::max(1.0, std::fabs(hi)), k2 * (hi - lo));
@@ -1278,14 +1287,27 @@ Result solve_instance(Instance& I, const Options& o, const double* x0, const dou
   Status status = MAXITER_EXCEEDED;
   try {
     // ---- starting point
-    for (int i = 0; i < n; ++i) push(A.cur.x[i], P.xL[i], P.xU[i]);
-    A.mu = o.mu_init; A.tau = std::max(o.tau_min, 1 - A.mu);
+    for (int i = 0; i < n; ++i) push(A.cur.x[i], P.xL[i], P.xU[i], warm ? o.ws_bound_push : o.bound_push, warm ? o.ws_bound_frac : o.bound_frac);
+    A.mu = warm ? o.ws_mu_init : o.mu_init; A.tau = std::max(o.tau_min, 1 - A.mu);
     A.f = P.eval_fg(A.cur.x.data(), A.mu, A.g.data());
-    for (int r = 0; r < m; ++r) { A.cur.s[r] = A.g[r]; push(A.cur.s[r], P.dL[r], P.dU[r]); }
+    for (int r = 0; r < m; ++r) { A.cur.s[r] = A.g[r]; push(A.cur.s[r], P.dL[r], P.dU[r], warm ? o.ws_slack_push : o.bound_push, warm ? o.ws_slack_frac : o.bound_frac); }
+    if (warm) {   // WarmStartIterateInitializer: multipliers from the caller, pushed away from zero; v from y_d = v_U - v_L
+      auto clip = [&](double v) { return std::min(std::max(v, -o.ws_mult_init_max), o.ws_mult_init_max); };
+      for (int i = 0; i < n; ++i) {
+        const double lz = clip(lamx0[i] * P.df);
+        A.cur.zL[i] = A.hasxL(i) ? std::max(-lz, o.ws_mult_push) : 0.0; A.cur.zU[i] = A.hasxU(i) ? std::max(lz, o.ws_mult_push) : 0.0;
+      }
+      for (int r = 0; r < m; ++r) {
+        const double y = clip(lamg0[r] * P.df / P.dc[r]);
+        A.cur.y[r] = y;
+        A.cur.vL[r] = A.hasdL(r) ? std::max(-y, o.ws_mult_push) : 0.0; A.cur.vU[r] = A.hasdU(r) ? std::max(y, o.ws_mult_push) : 0.0;
+      }
+    } else {
     for (int i = 0; i < n; ++i) { A.cur.zL[i] = A.hasxL(i) ? 1.0 : 0.0; A.cur.zU[i] = A.hasxU(i) ? 1.0 : 0.0; }
     for (int r = 0; r < m; ++r) { A.cur.vL[r] = A.hasdL(r) ? 1.0 : 0.0; A.cur.vU[r] = A.hasdU(r) ? 1.0 : 0.0; }
+    }
     P.eval_derivs(A.cur.x.data(), A.mu, A.grad.data(), A.J0.data());
-    {   // least-squares multipliers (LeastSquareMultipliers: W = 0, D_x = D_s = I)
+    if (!warm) {   // least-squares multipliers (LeastSquareMultipliers: W = 0, D_x = D_s = I)
       std::vector<double> one_n(n, 1.0), one_m(m, 1.0), rx(n), rs(m), zero(m, 0.0);
       for (int i = 0; i < n; ++i) rx[i] = A.grad[i] - A.cur.zL[i] + A.cur.zU[i];
       for (int r = 0; r < m; ++r) rs[r] = -A.cur.vL[r] + A.cur.vU[r];
@@ -1335,6 +1357,9 @@ void apply_overrides(Options& o) {
     else if (k == "max_soc") o.max_soc = (int)v; else if (k == "resto_rho") o.resto_rho = v;
     else if (k == "obj_max_inc") o.obj_max_inc = v; else if (k == "mu_init") o.mu_init = v;
     else if (k == "bound_mult_reset_threshold") o.bound_mult_reset_threshold = v;
+    else if (k == "ws_mu_init") o.ws_mu_init = v; else if (k == "ws_bound_push") o.ws_bound_push = v;
+    else if (k == "ws_bound_frac") o.ws_bound_frac = v; else if (k == "ws_slack_push") o.ws_slack_push = v;
+    else if (k == "ws_slack_frac") o.ws_slack_frac = v; else if (k == "ws_mult_push") o.ws_mult_push = v;
   }
 }
 
@@ -1385,6 +1410,12 @@ int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const dou
                       const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
                       double* x, double* f, double* g, double* lam_x, double* lam_g,
                       int32_t* status, int32_t* iters, int32_t* stats, int nthreads);
+int oracle_solve_warm(const oracle_spec* spec, int B, const double* p, const double* x0, const double* tgt,
+                      const double* lam_x0, const double* lam_g0,
+                      const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                      const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
+                      double* x, double* f, double* g, double* lam_x, double* lam_g,
+                      int32_t* status, int32_t* iters, int32_t* stats, int nthreads);
 int oracle_solve(const oracle_spec* spec, int B, const double* p, const double* x0,
                  const double* lbx, const double* ubx, const double* lbg, const double* ubg,
                  const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
@@ -1395,6 +1426,16 @@ int oracle_solve(const oracle_spec* spec, int B, const double* p, const double* 
 }
 // same with per-instance, per-stage target trajectories tgt [B][N][2] (NULL = p[8:10] for every stage)
 int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const double* x0, const double* tgt,
+                      const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                      const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
+                      double* x, double* f, double* g, double* lam_x, double* lam_g,
+                      int32_t* status, int32_t* iters, int32_t* stats, int nthreads) {
+  return oracle_solve_warm(spec, B, p, x0, tgt, nullptr, nullptr, lbx, ubx, lbg, ubg, obs, obs_per_instance, scaling, max_iter, tol,
+                           x, f, g, lam_x, lam_g, status, iters, stats, nthreads);
+}
+// same with multiplier guesses lam_x0 [B][nw], lam_g0 [B][ng] (non-reference warm start; a NaN in lam_x0[b][0] = cold start of b)
+int oracle_solve_warm(const oracle_spec* spec, int B, const double* p, const double* x0, const double* tgt,
+                      const double* lam_x0, const double* lam_g0,
                       const double* lbx, const double* ubx, const double* lbg, const double* ubg,
                       const double* obs, int obs_per_instance, int scaling, int max_iter, double tol,
                       double* x, double* f, double* g, double* lam_x, double* lam_g,
@@ -1413,7 +1454,8 @@ int oracle_solve_traj(const oracle_spec* spec, int B, const double* p, const dou
       std::vector<double> xo(nw);
       Result r = solve_instance(I, o, x0 + (size_t)b * nw, lbx, ubx, lbg, ubg, xo.data(),
                                 g ? g + (size_t)b * ng : nullptr, lam_x ? lam_x + (size_t)b * nw : nullptr,
-                                lam_g ? lam_g + (size_t)b * ng : nullptr, nullptr);
+                                lam_g ? lam_g + (size_t)b * ng : nullptr, nullptr,
+                                lam_x0 ? lam_x0 + (size_t)b * nw : nullptr, lam_g0 ? lam_g0 + (size_t)b * ng : nullptr);
       std::memcpy(x + (size_t)b * nw, xo.data(), sizeof(double) * nw);
       if (f) f[b] = r.f;
       if (status) status[b] = r.status;
