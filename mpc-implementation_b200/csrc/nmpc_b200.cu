@@ -233,7 +233,7 @@ struct nmpc_handle {
   cudaStream_t own_stream, last_stream;
   int64_t launches;
   double* dbg; int dbg_rows;
-  int align_group, fill;
+  int align_group, align_mid, fill;
 };
 
 extern "C" {
@@ -284,6 +284,9 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
     const int g = atoi(e);
     if (g == 0 || (g > 0 && h->warps_per_block % g == 0)) h->align_group = g;
   }
+  h->align_mid = 1;           // point 1 (after the inertia-correction retries) on, point 2 (after the line search) off
+  if (const char* e = getenv("NMPC_B200_ALIGN_MID")) h->align_mid = atoi(e) & 3;      // tuning knob: mid-iteration alignment points
+  if (h->align_group == 0 || 3 * (h->warps_per_block / h->align_group) > 15) h->align_mid = 0;   // 16 named barriers per block
   h->fill = spec->fill > 1 ? spec->fill : 1;
   if (const char* e = getenv("NMPC_B200_FILL")) { const int f = atoi(e); if (f >= 1) h->fill = f; }   // tuning override
   h->auto_order = 1;
@@ -369,7 +372,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.sched_table = h->sched_table; A.sched_id = h->sched_id; A.sched_phase = h->sched_phase; A.sched_len = h->sched_len; A.sched_iter = h->sched_iter;
   A.tgt = h->tgt;
   A.weights = h->weights;
-  A.align_group = h->align_group;
+  A.align_group = h->align_group; A.align_mid = h->align_mid;
   // fetch order: explicit (nmpc_set_order) > the order the previous call on this handle prepared for the same B > natural
   A.order = h->order_next; h->order_next = nullptr;
   if (!A.order && h->auto_order && h->have_order && h->prev_B == B) A.order = h->d_order[par];

@@ -74,6 +74,7 @@ struct SolveArgs {
   const unsigned* ricmap;            // per-lane ownership maps of the factorisation (nmpc_riccati.cuh: ric_map_build)
   double* dbg; int dbg_rows;         // optional per-iteration log [B][dbg_rows][10] (tests only)
   int align_group;                   // warps that start each IPM iteration together (0 = no alignment, else divides WPB)
+  int align_mid;                     // bit mask of the mid-iteration alignment points in use (0 = iteration start only)
 };
 constexpr int NSTAT = 8;
 constexpr int DBG_COLS = 10;
@@ -125,6 +126,27 @@ __device__ __forceinline__ int align_warps(int g, int working) {
   asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
                : "=r"(out) : "r"((unsigned)working), "r"(id), "r"(nt) : "memory");
   return (int)out;
+}
+
+// Mid-iteration alignment points (named barriers 1 + point * groups + group): between two calls of align_warps every
+// warp of the group passes each point in use exactly once, either waiting at it (mid_sync) or -- on a path that skips
+// it -- by announcing itself without waiting (mid_arrive), so nobody waits for a warp that will not come.
+__device__ __forceinline__ void mid_bar(int g, int groups, int point, bool wait) {
+  const unsigned id = 1 + point * groups + (threadIdx.x >> 5) / g, nt = 32 * g;
+  if (wait) asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nt) : "memory");
+  else asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nt) : "memory");
+}
+template <class L>
+__device__ __forceinline__ void mid_sync(const SolveArgs& A, int point, int& done) {
+  if (A.align_mid >> (point - 1) & 1) { mid_bar(A.align_group, L::WPB / A.align_group, point, true); done |= 1 << (point - 1); }
+}
+template <class L>
+__device__ __forceinline__ void mid_flush(const SolveArgs& A, int& done) {     // announce at the points this round did not pass; done < 0: no round open
+  if (done < 0) return;
+#pragma unroll
+  for (int pt = 1; pt <= 2; ++pt)
+    if ((A.align_mid >> (pt - 1) & 1) && !(done >> (pt - 1) & 1)) mid_bar(A.align_group, L::WPB / A.align_group, pt, false);
+  done = -1;
 }
 
 #define LV(e) smem[L::LV0 + (e) * L::S + lane]
@@ -348,8 +370,9 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
 // to the control diagonal and its gradient to the control right-hand side; rows enter with the weight Om(dw) instead
 // of Sigma_s + dw, so this phase is re-run for every inertia-correction value dw.
 template <class L, bool RS>
-__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df, double mu, double dw, bool want1, double* cold) {
+__device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, double df, double mu, double dw, int flags, double* cold) {
   const Prob& pr = A.pr; constexpr int N = L::N; const double T = pr.T;
+  const bool want1 = flags & 1;
   const bool act = lane <= N, hasu = lane < N;
   double u[6];
 #pragma unroll
@@ -1049,8 +1072,8 @@ __device__ __noinline__ void alg_init(double mu, double tau_min, double tol) {
 
 // mode-dispatched phases
 template <class L>
-__device__ __forceinline__ void do_derivs(const SolveArgs& A, int lane, int mode, double df, double dw, bool want1, double* cold) {
-  if (mode) ph_derivs<L, true>(A, lane, false, df, AL(F_MU), dw, want1, cold); else ph_derivs<L, false>(A, lane, false, df, AL(F_MU), dw, want1, cold);
+__device__ __forceinline__ void do_derivs(const SolveArgs& A, int lane, int mode, double df, double dw, int flags, double* cold) {
+  if (mode) ph_derivs<L, true>(A, lane, false, df, AL(F_MU), dw, flags & 1, cold); else ph_derivs<L, false>(A, lane, false, df, AL(F_MU), dw, flags, cold);
 }
 template <class L>
 __device__ __forceinline__ void do_dir(const SolveArgs& A, int lane, int mode, bool soc, double dw, double* cold) {
@@ -1348,8 +1371,10 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
   const double mu_floor = fmin(o.tol, df * o.compl_inf_tol) / (o.kappa_eps + 1.0);
   int iter = 0, status = NMPC_MAXITER_EXCEEDED;
 
+  int mids = -1;
   {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
-    align_warps(A.align_group, 1);
+    align_warps(A.align_group, 1); mids = 0;
+    mid_flush<L>(A, mids);
     ph_derivs<L, false>(A, lane, true, df, o.mu_init, 0.0, false, cold);
     al_count<L>(0, lane);
     const bool ok = riccati_factor<L>(T, ric, A.ricmap, 1.0, 0.0, lane);
@@ -1360,9 +1385,10 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     // Alignment point: the warps of a block start every IPM iteration together, so that they walk through the
     // same ~200 KB of phase code at the same time and share instruction-cache lines (unaligned warps thrash it:
     // `no_instruction` was 56 % of all stall cycles in v3).  Pure scheduling; results cannot depend on it.
-    align_warps(A.align_group, 1);
+    mid_flush<L>(A, mids);
+    align_warps(A.align_group, 1); mids = 0;
     int mode = (int)AL(F_MODE);
-    do_derivs<L>(A, lane, mode, df, 0.0, false, cold);
+    do_derivs<L>(A, lane, mode, df, 0.0, 0, cold);
     // ---- optimality error (scaled) and termination
     double du_inf = RES(R_DU), pr_inf = RES(R_PR), pmax = RES(R_PMAX), pmin = RES(R_PMIN);
     const int nz = mode ? nzt + 2 * mtot : nzt;
@@ -1410,6 +1436,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
       }
     }
     bool goto_resto = !ok;                  // step computation failed: fall back to the restoration phase
+    mid_sync<L>(A, 1, mids);                // re-align after the inertia-correction retries (on by default: -5 % .. -21 % per iteration)
     if (ok) {
       if (dw > 0.0) AL(F_DWLAST) = dw;
       riccati_forward<L>(T, ric, false, lane, DX0, DU0);
@@ -1534,6 +1561,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
       Lg[7] = AL(F_C0 + 1) - ls_before; Lg[8] = (double)tag; Lg[9] = (double)mode;
     }
     if (entered_resto) { resto_enter<L>(A, cold, lane, df); ++iter; continue; }
+    mid_sync<L>(A, 2, mids);                // re-align after the line search (off by default: measured neutral)
     // ---- accept (IpoptAlgorithm::AcceptTrialPoint)
     if (moved) do_accept<L>(A, lane, mode, 0.0, 0.0, dw, false, true, cold);     // the soft step already moved the iterate: kappa_Sigma reset only
     else do_accept<L>(A, lane, mode, alpha, a_du, dw, used_soc, true, cold);
@@ -1541,6 +1569,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     if (mode) al_count<L>(4, lane);
     ++iter;
   }
+  mid_flush<L>(A, mids);
   ph_output<L>(A, b, lane, df, status, iter);
   if (lane == 0 && A.stats) {
 #pragma unroll
@@ -1593,7 +1622,7 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(c
     fin = __shfl_sync(FULL, fin, 0);
     if (fin == A.B - 1 && A.order_out) next_order<L>(A, lane);           // last instance of the call
   }
-  while (align_warps(A.align_group, 0)) {}   // out of work: keep matching the alignment barrier until the group is done
+  while (align_warps(A.align_group, 0)) { int m = 0; mid_flush<L>(A, m); }   // out of work: keep matching the alignment barriers until the group is done
 }
 
 #undef LV
