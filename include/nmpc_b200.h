@@ -67,7 +67,19 @@ typedef struct nmpc_spec {
   int32_t fill;        /* scheduling hint, 0 or 1 = default: a batch smaller than the machine is spread over as many SMs as it
                           has instances; k > 1 packs it onto fewer SMs, k instances per resident warp (refilled from the
                           queue), which leaves SMs to the concurrent solves of other handles (pipelined sub-batches) */
+  int32_t model;       /* NMPC_MODEL_GIMBAL (0, every Python script) or NMPC_MODEL_GIMBAL_LESS (1) */
 } nmpc_spec;
+
+/* Model variants.
+ *   NMPC_MODEL_GIMBAL       8 states [x y z theta psi phi_g shi_g theta_g], 6 controls, p[11], rows [z theta X5 X6 X7 obstacles]
+ *                           per stage, cost = w1 * distance + w2 * FOV ellipse          Python/NMPC_TT.py:105-154, :193-244
+ *   NMPC_MODEL_GIMBAL_LESS  5 states [x y z theta psi], 3 controls [v omega_2 omega_3], p[8] = [state(5); x_t y_t theta_t], rows
+ *                           [z theta obstacles] per stage, cost = distance only (w1, w2, vfov, hfov ignored)
+ *                                                                   MATLAB/Dynamic Obstacles/NMPC_TT.m:25-37, :100-111
+ * Every array below has the model's own sizes: n_w = nmpc_n_w(spec) controls, n_g = nmpc_n_g(spec) rows, nmpc_n_p(spec)
+ * parameters per instance (6N / (5 + n_obs)(N + 1) / 11 for model 0, 3N / (2 + n_obs)(N + 1) / 8 for model 1). */
+#define NMPC_MODEL_GIMBAL 0
+#define NMPC_MODEL_GIMBAL_LESS 1
 
 typedef struct nmpc_handle nmpc_handle;
 
@@ -199,8 +211,9 @@ int nmpc_set_debug_log(nmpc_handle* h, double* dev_buf, int32_t rows);
 int nmpc_measure_fp64_peak(int device, double* tflops);
 
 /* sizes implied by a spec */
-int32_t nmpc_n_w(const nmpc_spec* spec);   /* 6 N */
-int32_t nmpc_n_g(const nmpc_spec* spec);   /* (5 + n_obs)(N + 1) */
+int32_t nmpc_n_w(const nmpc_spec* spec);   /* 6 N                 (model 1: 3 N) */
+int32_t nmpc_n_g(const nmpc_spec* spec);   /* (5 + n_obs)(N + 1)  (model 1: (2 + n_obs)(N + 1)) */
+int32_t nmpc_n_p(const nmpc_spec* spec);   /* 11                  (model 1: 8) */
 
 const char* nmpc_last_error(void);   /* thread-local */
 const char* nmpc_version(void);

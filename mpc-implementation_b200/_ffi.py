@@ -25,7 +25,7 @@ class NmpcSpec(C.Structure):
     _fields_ = [("T", C.c_double), ("N", C.c_int32), ("n_obs", C.c_int32),
                 ("w1", C.c_double), ("w2", C.c_double), ("vfov", C.c_double), ("hfov", C.c_double),
                 ("max_iter", C.c_int32), ("scaling", C.c_int32), ("tol", C.c_double),
-                ("max_batch", C.c_int32), ("fill", C.c_int32)]
+                ("max_batch", C.c_int32), ("fill", C.c_int32), ("model", C.c_int32)]
 
 
 class NmpcStats(C.Structure):
@@ -35,7 +35,7 @@ class NmpcStats(C.Structure):
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_eval", "nmpc_step",
-           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_set_schedule", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g",
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_set_schedule", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g", "nmpc_n_p",
            "nmpc_last_error", "nmpc_version"]
 
 _lib = None
@@ -77,6 +77,7 @@ def lib():
     L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.nmpc_n_w.argtypes = [C.POINTER(NmpcSpec)]
     L.nmpc_n_g.argtypes = [C.POINTER(NmpcSpec)]
+    L.nmpc_n_p.argtypes = [C.POINTER(NmpcSpec)]
     for name in EXPORTS:
         if hasattr(L, name):
             getattr(L, name).restype = C.c_int
@@ -84,6 +85,7 @@ def lib():
     L.nmpc_version.restype = C.c_char_p
     L.nmpc_n_w.restype = C.c_int32
     L.nmpc_n_g.restype = C.c_int32
+    L.nmpc_n_p.restype = C.c_int32
     _lib = L
     return L
 

@@ -40,7 +40,7 @@ class ClosedLoop:
         self.obstacles, self.obstacle_vel = t64(obstacles), t64(obstacle_vel)
         self.solver, self.sc = solver, scenario
         dev = device or f"cuda:{solver.device}"
-        self.p = torch.as_tensor(np.asarray(p0, dtype=np.float64), device=dev).reshape(-1, NP).contiguous().clone()
+        self.p = torch.as_tensor(np.asarray(p0, dtype=np.float64), device=dev).reshape(-1, scenario.n_p).contiguous().clone()
         self.B = self.p.shape[0]
         self.u_warm = torch.zeros((self.B, scenario.n_w), dtype=torch.float64, device=dev)     # u0 = 0  (:329)
         lbx, ubx, lbg, ubg = scenario.bounds()
@@ -89,10 +89,11 @@ class ClosedLoop:
         """[B, N, 2]: x_t, y_t of stages 0..N-1 under theta_{k+1} = theta_k + T w, (x, y)_{k+1} = (x, y)_k + T v (cos, sin)(theta_k)."""
         N, T = self.sc.N, self.sc.T
         k = torch.arange(N, dtype=torch.float64, device=self.p.device)
-        th = self.p[:, 10:11] + T * self.vw[:, 1:2] * k[None, :]                        # theta at stage k
+        nt = self.sc.n_p - 3                                                       # target block of p
+        th = self.p[:, nt + 2:nt + 3] + T * self.vw[:, 1:2] * k[None, :]                        # theta at stage k
         step = T * self.vw[:, 0:1, None] * torch.stack([torch.cos(th), torch.sin(th)], dim=2)
         excl = torch.cat([torch.zeros_like(step[:, :1]), torch.cumsum(step[:, :-1], dim=1)], dim=1)   # exclusive prefix sum
-        pos = self.p[:, None, 8:10] + excl
+        pos = self.p[:, None, nt:nt + 2] + excl
         return pos.contiguous()
 
     def next_order(self):
@@ -155,7 +156,7 @@ class PipelinedClosedLoop:
         """make_solver(n) -> Solver for a sub-batch of n instances (give it `fill=2`: a sub-batch then leaves SMs to
         the others).  pipelines: number of sub-batches; None = about 32768 / B, at most 8 (measured best: 8 at
         B = 4096, 2 at B = 16384 on a B200)."""
-        p0 = np.asarray(p0, dtype=np.float64).reshape(-1, NP)
+        p0 = np.asarray(p0, dtype=np.float64).reshape(-1, scenario.n_p)
         B = p0.shape[0]
         if pipelines is None:
             pipelines = max(1, min(8, 32768 // max(B, 1)))

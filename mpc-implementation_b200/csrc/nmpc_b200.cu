@@ -25,15 +25,18 @@ using namespace nmpc;
 // ------------------------------------------------------------------------------------------------
 // The IPM kernel (nmpc_solve.cuh) is a template on (N, n_obs); its instantiations live in nmpc_inst.cu objects.
 namespace nmpc {
-#define NMPC_DECL_INST(N, O)                      \
-  int ipm_prepare_##N##_##O(int*, size_t*, int*, int*);  \
-  int ipm_ricmap_##N##_##O(unsigned*, cudaStream_t);     \
-  int ipm_launch_##N##_##O(const SolveArgs&, int, size_t, cudaStream_t);
-NMPC_DECL_INST(15, 3) NMPC_DECL_INST(15, 10) NMPC_DECL_INST(30, 10) NMPC_DECL_INST(30, 3) NMPC_DECL_INST(5, 3) NMPC_DECL_INST(15, 7)
+#define NMPC_DECL_INST(N, O, M)                      \
+  int ipm_prepare_##N##_##O##_##M(int*, size_t*, int*, int*);  \
+  int ipm_ricmap_##N##_##O##_##M(unsigned*, cudaStream_t);     \
+  int ipm_launch_##N##_##O##_##M(const SolveArgs&, int, size_t, cudaStream_t);
+NMPC_DECL_INST(15, 3, 0) NMPC_DECL_INST(15, 10, 0) NMPC_DECL_INST(30, 10, 0) NMPC_DECL_INST(30, 3, 0) NMPC_DECL_INST(5, 3, 0) NMPC_DECL_INST(15, 7, 0)
+NMPC_DECL_INST(15, 0, 1)
 }  // namespace nmpc
-struct IpmInst { int N, n_obs; int (*prepare)(int*, size_t*, int*, int*); int (*ricmap)(unsigned*, cudaStream_t); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
-#define NMPC_INST(N, O) {N, O, nmpc::ipm_prepare_##N##_##O, nmpc::ipm_ricmap_##N##_##O, nmpc::ipm_launch_##N##_##O}
-static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3), NMPC_INST(15, 10), NMPC_INST(30, 10), NMPC_INST(30, 3), NMPC_INST(5, 3), NMPC_INST(15, 7)};      // (15, 7): the 7 obstacle rows of MATLAB/Dynamic Obstacles/Dynamic Obstacle avoidance.m:126-134
+struct IpmInst { int N, n_obs, model; int (*prepare)(int*, size_t*, int*, int*); int (*ricmap)(unsigned*, cudaStream_t); int (*launch)(const SolveArgs&, int, size_t, cudaStream_t); };
+#define NMPC_INST(N, O, M) {N, O, M, nmpc::ipm_prepare_##N##_##O##_##M, nmpc::ipm_ricmap_##N##_##O##_##M, nmpc::ipm_launch_##N##_##O##_##M}
+static const IpmInst IPM_INSTS[] = {NMPC_INST(15, 3, 0), NMPC_INST(15, 10, 0), NMPC_INST(30, 10, 0), NMPC_INST(30, 3, 0), NMPC_INST(5, 3, 0),
+                                    NMPC_INST(15, 7, 0),      // the 7 obstacle rows of MATLAB/Dynamic Obstacles/Dynamic Obstacle avoidance.m:126-134
+                                    NMPC_INST(15, 0, 1)};     // the gimbal-less tracker of MATLAB/Dynamic Obstacles/NMPC_TT.m
 
 struct EvalArgs {
   Prob pr; int B;
@@ -48,18 +51,21 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= A.B) return;
-  const int N = pr.N, R = pr.R, S = pr.S, n_obs = pr.n_obs, nw = NU * N, ng = R * S;
+  const int nu = model_nu(pr.model), nb = model_nb(pr.model), npar = model_np(pr.model);      // model 1: see nmpc_device.cuh
+  const int N = pr.N, R = pr.R, S = pr.S, n_obs = pr.n_obs, nw = nu * N, ng = R * S;
   const bool act = lane <= N, hasu = lane < N;
   const double T = pr.T;
-  const double* pp = A.p + (size_t)b * NPAR;
+  const double* pp = A.p + (size_t)b * npar;
   double X0[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) X0[i] = pp[i];
-  const double xt = (A.tgt && hasu) ? A.tgt[((size_t)b * N + lane) * 2] : pp[8];
-  const double yt = (A.tgt && hasu) ? A.tgt[((size_t)b * N + lane) * 2 + 1] : pp[9];
+  for (int i = 0; i < 8; ++i) X0[i] = i < (pr.model ? 5 : 8) ? pp[i] : 0.0;
+  const double xt = (A.tgt && hasu) ? A.tgt[((size_t)b * N + lane) * 2] : pp[npar - 3];
+  const double yt = (A.tgt && hasu) ? A.tgt[((size_t)b * N + lane) * 2 + 1] : pp[npar - 2];
   double u[6], vv[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { u[i] = hasu ? A.w[(size_t)b * nw + NU * lane + i] : 0.0; vv[i] = (hasu && A.v) ? A.v[(size_t)b * nw + NU * lane + i] : 0.0; }
+  for (int i = 0; i < 6; ++i) {
+    u[i] = (hasu && i < nu) ? A.w[(size_t)b * nw + nu * lane + i] : 0.0; vv[i] = (hasu && A.v && i < nu) ? A.v[(size_t)b * nw + nu * lane + i] : 0.0;
+  }
   const double* obs = A.obs + (A.obs_per_instance ? (size_t)b * 3 * n_obs : 0);
   Stage st;
   rollout(pr, X0, u, lane, st);
@@ -77,16 +83,16 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
 #pragma unroll
   for (int i = 0; i < 21; ++i) Hl[i] = 0.0;
   double l = 0.0;
-  if (hasu) l = stage_cost_d2(A.weights ? with_weights(pr, A.weights[2 * (size_t)b], A.weights[2 * (size_t)b + 1]) : pr, st.X, xt, yt, gl, Hl);
+  if (hasu) l = pr.model ? stage_cost_dist_d2(st.X, xt, yt, gl, Hl)
+                         : stage_cost_d2(A.weights ? with_weights(pr, A.weights[2 * (size_t)b], A.weights[2 * (size_t)b + 1]) : pr, st.X, xt, yt, gl, Hl);
   const double fsum = warp_sum(l);
   if (lane == 0 && A.f) A.f[b] = fsum;
   if (act && A.g) {
     double* go = A.g + (size_t)b * ng + lane * R;
-#pragma unroll
-    for (int r = 0; r < 5; ++r) go[r] = st.X[box_state(r)];
+    for (int r = 0; r < nb; ++r) go[r] = st.X[box_state(r)];
     for (int jn = 0; jn < n_obs; ++jn) {
       const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
-      go[5 + jn] = obs[3 * jn + 2] - sqrt(dx_ * dx_ + dy_ * dy_);
+      go[nb + jn] = obs[3 * jn + 2] - sqrt(dx_ * dx_ + dy_ * dy_);
     }
   }
   double a[8], lamn[8], out[6];
@@ -96,17 +102,16 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
 #pragma unroll
     for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
     adjoint(a, lamn); Bt(lamn, out);
-    if (hasu) for (int i = 0; i < 6; ++i) A.grad[(size_t)b * nw + NU * lane + i] = out[i];
+    if (hasu) for (int i = 0; i < nu; ++i) A.grad[(size_t)b * nw + nu * lane + i] = out[i];
   }
   const double* lm = A.lam ? A.lam + (size_t)b * ng + lane * R : nullptr;
   auto gt_lam = [&](double* acc) {   // acc += G_k^T lam_k
     if (act && lm) {
-#pragma unroll
-      for (int r = 0; r < 5; ++r) acc[box_state(r)] += lm[r];
+      for (int r = 0; r < nb; ++r) acc[box_state(r)] += lm[r];
       for (int jn = 0; jn < n_obs; ++jn) {
         const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
         const double iD = 1.0 / sqrt(dx_ * dx_ + dy_ * dy_);
-        acc[0] += -lm[5 + jn] * dx_ * iD; acc[1] += -lm[5 + jn] * dy_ * iD;
+        acc[0] += -lm[nb + jn] * dx_ * iD; acc[1] += -lm[nb + jn] * dy_ * iD;
       }
     }
   };
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
     for (int i = 0; i < 8; ++i) a[i] = 0.0;
     gt_lam(a);
     adjoint(a, lamn); Bt(lamn, out);
-    if (hasu) for (int i = 0; i < 6; ++i) A.jtv[(size_t)b * nw + NU * lane + i] = out[i];
+    if (hasu) for (int i = 0; i < nu; ++i) A.jtv[(size_t)b * nw + nu * lane + i] = out[i];
   }
   if (A.hv) {
     // adjoint of the Lagrangian sigma f + lam^T g
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
       if (lm) for (int jn = 0; jn < n_obs; ++jn) {
         const double dx_ = st.X[0] - obs[3 * jn], dy_ = st.X[1] - obs[3 * jn + 1];
         const double D = sqrt(dx_ * dx_ + dy_ * dy_), iD = 1.0 / D, nx = dx_ * iD, ny = dy_ * iD;
-        const double cur = -lm[5 + jn] * iD;
+        const double cur = -lm[nb + jn] * iD;
         wx[0] += cur * ((1.0 - nx * nx) * dx[0] - nx * ny * dx[1]);
         wx[1] += cur * (-nx * ny * dx[0] + (1.0 - ny * ny) * dx[1]);
       }
@@ -170,29 +175,29 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
     }
     adjoint(wx, lamn); Bt(lamn, out);
     out[0] += wu0;
-    if (hasu) for (int i = 0; i < 6; ++i) A.hv[(size_t)b * nw + NU * lane + i] = out[i];
+    if (hasu) for (int i = 0; i < nu; ++i) A.hv[(size_t)b * nw + nu * lane + i] = out[i];
   }
 }
 
 struct StepArgs {
-  double T, hv, hh; int N, B;
+  double T, hv, hh; int N, B, model;
   const double* x_sol; double *p, *u_warm; const double* vw; double *fov, *err;
 };
 
 __global__ void nmpc_step_kernel(const StepArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= A.B) return;
-  const int nw = NU * A.N;
+  const int nu = model_nu(A.model), nw = nu * A.N;
   const double* xs = A.x_sol + (size_t)b * nw;
-  double u0[NU];
-  for (int i = 0; i < NU; ++i) u0[i] = xs[i];
+  double u0[NU] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < nu; ++i) u0[i] = xs[i];
   // warm start: drop the first stage, repeat the last (NMPC_TT.py:20-23).  x_sol may alias u_warm.
   double* uw = A.u_warm + (size_t)b * nw;
   for (int k = 0; k < A.N - 1; ++k)
-    for (int i = 0; i < NU; ++i) uw[NU * k + i] = xs[NU * (k + 1) + i];
+    for (int i = 0; i < nu; ++i) uw[nu * k + i] = xs[nu * (k + 1) + i];
   if (A.u_warm != A.x_sol)
-    for (int i = 0; i < NU; ++i) uw[NU * (A.N - 1) + i] = xs[NU * (A.N - 1) + i];
-  closed_loop_shift(A.T, A.hv, A.hh, A.p + (size_t)b * NPAR, u0, A.vw[2 * b], A.vw[2 * b + 1],
+    for (int i = 0; i < nu; ++i) uw[nu * (A.N - 1) + i] = xs[nu * (A.N - 1) + i];
+  closed_loop_shift_model(A.model, A.T, A.hv, A.hh, A.p + (size_t)b * model_np(A.model), u0, A.vw[2 * b], A.vw[2 * b + 1],
                     A.fov ? A.fov + 2 * (size_t)b : nullptr, A.err ? A.err + b : nullptr);
 }
 
@@ -240,8 +245,9 @@ extern "C" {
 
 const char* nmpc_last_error(void) { return g_err.c_str(); }
 const char* nmpc_version(void) { return "nmpc_b200 0.1 (sm_100a)"; }
-int32_t nmpc_n_w(const nmpc_spec* s) { return NU * s->N; }
-int32_t nmpc_n_g(const nmpc_spec* s) { return (5 + s->n_obs) * (s->N + 1); }
+int32_t nmpc_n_w(const nmpc_spec* s) { return model_nu(s->model) * s->N; }
+int32_t nmpc_n_g(const nmpc_spec* s) { return (model_nb(s->model) + s->n_obs) * (s->N + 1); }
+int32_t nmpc_n_p(const nmpc_spec* s) { return model_np(s->model); }
 
 extern "C" int nmpc_destroy(nmpc_handle* h);
 int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
@@ -249,6 +255,7 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   if (spec->N < 1 || spec->N + 1 > NMPC_MAX_STAGES) return fail("nmpc_create: need 1 <= N <= 31");
   if (spec->n_obs < 0 || spec->n_obs > NMPC_MAX_OBS) return fail("nmpc_create: need 0 <= n_obs <= 16");
   if (!(spec->T > 0)) return fail("nmpc_create: T must be positive");
+  if (spec->model != NMPC_MODEL_GIMBAL && spec->model != NMPC_MODEL_GIMBAL_LESS) return fail("nmpc_create: model must be NMPC_MODEL_GIMBAL (0) or NMPC_MODEL_GIMBAL_LESS (1)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("nmpc_create: no CUDA device (this library has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail("nmpc_create: bad device index");
@@ -261,17 +268,19 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   memset(h, 0, sizeof *h);
   h->spec = *spec; h->device = device; h->sm_count = prop.multiProcessorCount;
   h->pr.T = spec->T; h->pr.w1 = spec->w1; h->pr.w2 = spec->w2; h->pr.hv = 0.5 * spec->vfov; h->pr.hh = 0.5 * spec->hfov;
-  h->pr.N = spec->N; h->pr.n_obs = spec->n_obs; h->pr.R = 5 + spec->n_obs; h->pr.S = spec->N + 1;
+  h->pr.N = spec->N; h->pr.n_obs = spec->n_obs; h->pr.R = model_nb(spec->model) + spec->n_obs; h->pr.S = spec->N + 1;
+  h->pr.model = spec->model;
+  if (spec->model == NMPC_MODEL_GIMBAL_LESS) { h->pr.w1 = 1.0; h->pr.w2 = 0.0; }     // distance-only cost (NMPC_TT.m:100-104)
   h->opt = Opt();
   h->opt.max_iter = spec->max_iter > 0 ? spec->max_iter : 100;
   h->opt.scaling = spec->scaling; h->opt.tol = spec->tol > 0 ? spec->tol : 1e-8;
   h->inst = nullptr;
-  for (const IpmInst& in : IPM_INSTS) if (in.N == spec->N && in.n_obs == spec->n_obs) h->inst = &in;
+  for (const IpmInst& in : IPM_INSTS) if (in.N == spec->N && in.n_obs == spec->n_obs && in.model == spec->model) h->inst = &in;
   if (!h->inst) {
     std::string have;
-    for (const IpmInst& in : IPM_INSTS) have += " (" + std::to_string(in.N) + "," + std::to_string(in.n_obs) + ")";
+    for (const IpmInst& in : IPM_INSTS) have += " (" + std::to_string(in.N) + "," + std::to_string(in.n_obs) + (in.model ? ",model 1)" : ")");
     delete h;
-    return fail("nmpc_create: no kernel instantiation for this (N, n_obs); built:" + have + " -- add the pair to csrc/Makefile INSTS and the table in nmpc_b200.cu");
+    return fail("nmpc_create: no kernel instantiation for this (N, n_obs, model); built:" + have + " -- add it to csrc/Makefile INSTS and the table in nmpc_b200.cu");
   }
   {
     const int rc = h->inst->prepare(&h->blocks_per_sm, &h->smem_bytes, &h->warps_per_block, &h->cold_stride);
@@ -307,8 +316,8 @@ int nmpc_create(const nmpc_spec* spec, int device, nmpc_handle** out) {
   CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   const int mb = spec->max_batch > 0 ? spec->max_batch : 0;
   if (mb > 0) {
-    const size_t nw = NU * spec->N, ng = (size_t)h->pr.R * h->pr.S;
-    CKH(cudaMalloc(&h->d_p, sizeof(double) * mb * NPAR)); CKH(cudaMalloc(&h->d_x0, sizeof(double) * mb * nw));
+    const size_t nw = (size_t)model_nu(spec->model) * spec->N, ng = (size_t)h->pr.R * h->pr.S;
+    CKH(cudaMalloc(&h->d_p, sizeof(double) * mb * model_np(spec->model))); CKH(cudaMalloc(&h->d_x0, sizeof(double) * mb * nw));
     CKH(cudaMalloc(&h->d_lbx, sizeof(double) * nw)); CKH(cudaMalloc(&h->d_ubx, sizeof(double) * nw));
     CKH(cudaMalloc(&h->d_lbg, sizeof(double) * ng)); CKH(cudaMalloc(&h->d_ubg, sizeof(double) * ng));
     h->obs_cap = (size_t)mb * 3 * (spec->n_obs > 0 ? spec->n_obs : 1);
@@ -459,9 +468,9 @@ int nmpc_solve_host_async(nmpc_handle* h, int32_t B, const double* p, const doub
   if (B > h->spec.max_batch) return fail("nmpc_solve_host: B exceeds spec.max_batch");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = h->own_stream;
-  const size_t nw = NU * h->pr.N, ng = (size_t)h->pr.R * h->pr.S;
+  const size_t nw = (size_t)model_nu(h->pr.model) * h->pr.N, ng = (size_t)h->pr.R * h->pr.S;
   const size_t nobs = (size_t)3 * h->pr.n_obs * ((flags & NMPC_OBS_PER_INSTANCE) ? B : 1);
-  CK(cudaMemcpyAsync(h->d_p, p, sizeof(double) * B * NPAR, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h->d_p, p, sizeof(double) * B * model_np(h->pr.model), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * B * nw, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->d_lbx, lbx, sizeof(double) * nw, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(h->d_ubx, ubx, sizeof(double) * nw, cudaMemcpyHostToDevice, s));
@@ -510,7 +519,7 @@ int nmpc_step(nmpc_handle* h, int32_t B, const double* x_sol, double* p,
   if (!x_sol || !p || !u_warm || !target_vw) return fail("nmpc_step: null required pointer");
   CK(cudaSetDevice(h->device));
   if (err_accum && !fov_centre) return fail("nmpc_step: err_accum needs fov_centre");
-  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, x_sol, p, u_warm, target_vw, fov_centre, err_accum};
+  StepArgs A{h->pr.T, h->pr.hv, h->pr.hh, h->pr.N, B, h->pr.model, x_sol, p, u_warm, target_vw, fov_centre, err_accum};
   nmpc_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(A);
   CK(cudaGetLastError());
   h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;

@@ -19,6 +19,15 @@ namespace nmpc {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NX = 8, NU = 6, NPAR = 11;
+// Model 1 = the gimbal-less tracker of MATLAB/Dynamic Obstacles/NMPC_TT.m:25-35 (states x, y, z, theta, psi; controls v,
+// omega_2, omega_3; p = [state(5); target(3)]; cost = horizontal distance, :100-104; rows [z, theta], :107-111).  Its dynamics
+// are the first five rows of model 0's, so it runs on the same 8-state / 6-control machinery with the camera states held
+// at zero: the three camera controls are ABSENT variables (no bounds, no multipliers, zero gradient; a unit entry on the
+// diagonal of the control block keeps the stage systems decoupled and positive, their step is exactly zero), and only the
+// first NB = 2 box rows exist.  The C ABI sees the model's own sizes (3N controls, 2 (N + 1) rows, p[8]).
+__host__ __device__ constexpr int model_nu(int model) { return model ? 3 : 6; }
+__host__ __device__ constexpr int model_nb(int model) { return model ? 2 : 5; }
+__host__ __device__ constexpr int model_np(int model) { return model ? 8 : 11; }
 
 // ---- per-lane vectors in shared memory: index e * S + stage ------------------------------------
 enum LvEnt { LV_U = 0, LV_ZL = 6, LV_ZU = 12, LV_X = 18, LV_GL = 26, LV_DX = 32, LV_DU = 40, LV_N = 46 };
@@ -27,7 +36,6 @@ enum LvEnt { LV_U = 0, LV_ZL = 6, LV_ZU = 12, LV_X = 18, LV_GL = 26, LV_DX = 32,
 // to lower bounds (multiplier v_L and reciprocal slack 1/(s - l)) exist for the five box rows only: they come last and
 // hold NBOX rows instead of R.  A finite lower bound on an obstacle row is refused (NMPC_INVALID_NUMBER).
 enum RowArr { A_S = 0, A_Y, A_VU, A_G, A_DS, A_DC, A_IU, A_NFULL, A_VL = A_NFULL, A_IL, A_NROW };
-constexpr int NBOX = 5;
 // ---- per-stage LQ data (entry-major: e * S + stage).  Entries [0, LQ_DEAD) are dead once the
 //      factorisation has succeeded and are reused by the second-order-correction arrays. ----------
 enum LqEnt {
@@ -150,7 +158,8 @@ __device__ __forceinline__ double shfl_next(double v, int lane) {   // value of 
 // ---- problem constants passed by value to the kernels ---------------------------------------------
 struct Prob {
   double T, w1, w2, hv, hh;   // hv = VFOV/2, hh = HFOV/2
-  int N, n_obs, R, S;         // R = 5 + n_obs rows per stage, S = N + 1 stages
+  int N, n_obs, R, S;         // R = (5 | 2) + n_obs rows per stage, S = N + 1 stages
+  int model;                  // 0: UAV + gimballed camera (the Python scripts), 1: gimbal-less tracker
 };
 
 // ---- compile-time shared-memory layout of one warp's workspace (offsets from the warp's slice base).
@@ -159,15 +168,16 @@ struct Prob {
 #define NMPC_WPB_MAX 8     // 8 warps x 255 registers is the whole register file of an SM
 #endif
 __host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
-template <int N_, int NOBS_, bool FOLD_>
+template <int N_, int NOBS_, bool FOLD_, int MODEL_ = 0>
 struct LayT {
-  static constexpr int N = N_, S = N_ + 1, R = 5 + NOBS_, NOBS = NOBS_;
+  static constexpr int MODEL = MODEL_, NB = model_nb(MODEL_), NUA = model_nu(MODEL_), NPA = model_np(MODEL_);
+  static constexpr int N = N_, S = N_ + 1, R = NB + NOBS_, NOBS = NOBS_;
   static constexpr bool FOLD = FOLD_;
   static constexpr int LQ_NE = FOLD_ ? LQ_NFOLD : LQ_N;
   static constexpr int LV0 = 0;
   static constexpr int RW0 = even_up(LV0 + LV_N * S);
-  static constexpr int RW_N = (A_NFULL * R + (A_NROW - A_NFULL) * NBOX) * S;
-  __host__ __device__ static constexpr int rw(int arr, int r) { return RW0 + (arr < A_NFULL ? arr * R + r : A_NFULL * R + (arr - A_NFULL) * NBOX + r) * S; }
+  static constexpr int RW_N = (A_NFULL * R + (A_NROW - A_NFULL) * NB) * S;
+  __host__ __device__ static constexpr int rw(int arr, int r) { return RW0 + (arr < A_NFULL ? arr * R + r : A_NFULL * R + (arr - A_NFULL) * NB + r) * S; }
   static constexpr int LQ0 = even_up(RW0 + RW_N);
   // Second-order-correction scratch in shared memory: du_soc [6] and q' [8], in the LQ entries that are dead after
   // the factorisation (the residual of the last trial point, c_t [R], goes to the cold scratch with the other SOC arrays).
@@ -193,7 +203,7 @@ struct LayT {
   static constexpr int CG_FILT = CG_UR + 6 * S;         // [2][FILT_CAP][2]: filter of the original problem, of the restoration problem
   static constexpr int CG_PARK = CG_FILT + 4 * FILT_CAP;   // [ALG_N] algorithm state of the original problem while the restoration phase runs
   static constexpr int CG_SLOT = CG_PARK + ALG_N;
-  static constexpr int SLOT_N = 32 * S + 8 * RSZ + 2 * NBOX * S;   // U ZL ZU (18 S) | DX DU (14 S) | S Y VU IU (4 RS) | VL IL (2 NBOX S) | n p z_n z_p (4 RS)
+  static constexpr int SLOT_N = 32 * S + 8 * RSZ + 2 * NB * S;   // U ZL ZU (18 S) | DX DU (14 S) | S Y VU IU (4 RS) | VL IL (2 NB S) | n p z_n z_p (4 RS)
   static constexpr int COLD_TOTAL = even_up(CG_SLOT + 3 * SLOT_N);
   static constexpr int WPB_FIT = (227 * 1024) / (TOTAL * 8);
   static constexpr int WPB = WPB_FIT < 1 ? 1 : (WPB_FIT > NMPC_WPB_MAX ? NMPC_WPB_MAX : WPB_FIT);
@@ -203,8 +213,8 @@ struct LayT {
 #ifndef NMPC_FOLD_MIN_S
 #define NMPC_FOLD_MIN_S 20     // measured: (30,10) 3 -> 4 warps per SM is +16 % (config 5); (15,10) 6 -> 7 warps is -3 % (config 4), so short horizons keep the separate entries
 #endif
-template <int N_, int NOBS_>
-using Lay = LayT<N_, NOBS_, (N_ + 1 >= NMPC_FOLD_MIN_S) && (LayT<N_, NOBS_, true>::WPB > LayT<N_, NOBS_, false>::WPB)>;
+template <int N_, int NOBS_, int MODEL_ = 0>
+using Lay = LayT<N_, NOBS_, (N_ + 1 >= NMPC_FOLD_MIN_S) && (LayT<N_, NOBS_, true, MODEL_>::WPB > LayT<N_, NOBS_, false, MODEL_>::WPB), MODEL_>;
 
 // ---- stage state of one lane -----------------------------------------------------------------------
 struct Stage {
@@ -336,6 +346,24 @@ __device__ __forceinline__ double stage_cost_d2(const Prob& pr, const double* X,
   return w1 * D + w2 * (U * U + V * V - 1.0);
 }
 
+// model 1: distance-only stage cost (MATLAB/Dynamic Obstacles/NMPC_TT.m:100-104), same output layout
+__device__ __forceinline__ double stage_cost_dist(const double* X, double xt, double yt) {
+  const double ex = X[0] - xt, ey = X[1] - yt;
+  return sqrt(ex * ex + ey * ey);
+}
+__device__ __forceinline__ double stage_cost_dist_d2(const double* X, double xt, double yt, double* gl, double* Hl) {
+#pragma unroll
+  for (int v = 0; v < 6; ++v) gl[v] = 0.0;
+#pragma unroll
+  for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
+  const double ex = X[0] - xt, ey = X[1] - yt;
+  const double D = sqrt(ex * ex + ey * ey), iD = rcp(D);
+  const double nx = ex * iD, ny = ey * iD;
+  gl[0] = nx; gl[1] = ny;
+  Hl[tri(0, 0)] = iD * (1.0 - nx * nx); Hl[tri(1, 0)] = iD * (-nx * ny); Hl[tri(1, 1)] = iD * (1.0 - ny * ny);
+  return D;
+}
+
 // Closed-loop shift of ONE instance (NMPC_TT.py:13-30, :399-402, :435): plant Euler step with the first input u0, target
 // Euler step with (tv, tw), FOV centre of the new state and the tracking-error term.  st = [x(8); x_t, y_t, theta_t] in
 // place.  Used by nmpc_step_kernel (one thread per instance) and by the fused epilogue of the IPM kernel (lane 0).
@@ -363,6 +391,23 @@ __device__ __forceinline__ void closed_loop_shift(double T, double hv, double hh
     fov[0] = xe; fov[1] = ye;
     if (err) *err += sqrt((xe - tx0) * (xe - tx0) + (ye - ty0) * (ye - ty0));     // NMPC_TT.py:435
   }
+}
+
+// the same on the caller's p record of either model: model 1 holds [state(5); target(3)] (MATLAB/Dynamic Obstacles/shift1.m)
+__device__ __forceinline__ void closed_loop_shift_model(int model, double T, double hv, double hh, double* p, const double* u0, double tv, double tw,
+                                                        double* fov, double* err) {
+  if (!model) { closed_loop_shift(T, hv, hh, p, u0, tv, tw, fov, err); return; }
+  double st[NPAR], u6[NU] = {u0[0], u0[1], u0[2], 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 5; ++i) st[i] = p[i];
+  st[5] = 0.0; st[6] = 0.0; st[7] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st[8 + i] = p[5 + i];
+  closed_loop_shift(T, hv, hh, st, u6, tv, tw, fov, err);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) p[i] = st[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p[5 + i] = st[8 + i];
 }
 
 // 6x6 Cholesky on a packed lower triangle (in place).  Returns false when a pivot is not positive.

@@ -100,8 +100,11 @@ struct Bnd { double lo, hi; bool hl, hu; };
 // 1e-10 slack, i.e. a 1e-5 error in a multiplier -- enough to stall the end game (seen with v2).
 __device__ __forceinline__ double relaxed_lo(double lo, double relax) { return lo > -1e19 ? __dsub_rn(lo, __dmul_rn(relax, fmax(1.0, fabs(lo)))) : -CUDART_INF; }
 __device__ __forceinline__ double relaxed_hi(double hi, double relax) { return hi < 1e19 ? __dadd_rn(hi, __dmul_rn(relax, fmax(1.0, fabs(hi)))) : CUDART_INF; }
+template <class L>
 __device__ __forceinline__ Bnd ctl_bounds(const SolveArgs& A, int k, int i) {
-  Bnd b; b.lo = relaxed_lo(__ldg(A.lbx + NU * k + i), A.o.bound_relax); b.hi = relaxed_hi(__ldg(A.ubx + NU * k + i), A.o.bound_relax);
+  Bnd b;
+  if (i >= L::NUA) { b.lo = -CUDART_INF; b.hi = CUDART_INF; b.hl = false; b.hu = false; return b; }     // absent control (model 1)
+  b.lo = relaxed_lo(__ldg(A.lbx + L::NUA * k + i), A.o.bound_relax); b.hi = relaxed_hi(__ldg(A.ubx + L::NUA * k + i), A.o.bound_relax);
   b.hl = b.lo > -CUDART_INF; b.hu = b.hi < CUDART_INF;
   return b;
 }
@@ -152,8 +155,8 @@ __device__ __forceinline__ void mid_flush(const SolveArgs& A, int& done) {     /
 #define LV(e) smem[L::LV0 + (e) * L::S + lane]
 #define RW(arr, r) smem[L::rw(arr, r) + lane]
 // lower-bound arrays exist for the box rows only (nmpc_device.cuh: RowArr)
-#define VL_(r) ((r) < NBOX ? RW(A_VL, r) : 0.0)
-#define IL_(r) ((r) < NBOX ? RW(A_IL, r) : 0.0)
+#define VL_(r) ((r) < L::NB ? RW(A_VL, r) : 0.0)
+#define IL_(r) ((r) < L::NB ? RW(A_IL, r) : 0.0)
 #define LQ(e) smem[L::LQ0 + (e) * L::S + lane]
 #define SOC(e) smem[L::soc(e) + lane]
 #define RES(i) smem[L::RES0 + (i)]
@@ -197,14 +200,14 @@ __device__ __forceinline__ double obs_value(const double* X, int jn, double& nx,
 // rows in a rolled loop.  body(r, box, si, gu, nx, ny, iD) with gu the unscaled row value.
 #define FOR_ROWS(X, body)                                                                           \
   do {                                                                                              \
-    _Pragma("unroll") for (int r_ = 0; r_ < 5; ++r_) {                                              \
+    _Pragma("unroll") for (int r_ = 0; r_ < L::NB; ++r_) {                                          \
       const int si_ = r_ == 0 ? 2 : (r_ == 1 ? 3 : r_ + 3);                                         \
       body(r_, true, si_, (X)[si_], 0.0, 0.0, 0.0);                                                 \
     }                                                                                               \
     _Pragma("unroll 1") for (int jn_ = 0; jn_ < L::NOBS; ++jn_) {                                   \
       double nx_, ny_, iD_;                                                                         \
       const double gu_ = obs_value<L>((X), jn_, nx_, ny_, iD_);                                     \
-      body(5 + jn_, false, 0, gu_, nx_, ny_, iD_);                                                  \
+      body(L::NB + jn_, false, 0, gu_, nx_, ny_, iD_);                                              \
     }                                                                                               \
   } while (0)
 
@@ -215,6 +218,20 @@ __device__ __forceinline__ double2 stage_target(const SolveArgs& A, int lane) {
   if (!A.tgt || lane >= L::N) return make_double2(PAR(8), PAR(9));
   const double* t = A.tgt + ((size_t)PAR(NPAR + 2) * L::N + lane) * 2;
   return make_double2(__ldg(t), __ldg(t + 1));
+}
+
+// stage cost of this lane's stage (value / value + gradient + Hessian over (x, y, z, X5, X6, X7)) for the model of the layout
+template <class L>
+__device__ __forceinline__ double cost_val(const SolveArgs& A, const double* X, int lane) {
+  const double2 t = stage_target<L>(A, lane);
+  if (L::MODEL) return stage_cost_dist(X, t.x, t.y);
+  return stage_cost(with_weights(A.pr, PAR(NPAR), PAR(NPAR + 1)), X, t.x, t.y);
+}
+template <class L>
+__device__ __forceinline__ double cost_d2(const SolveArgs& A, const double* X, int lane, double* gl, double* Hl) {
+  const double2 t = stage_target<L>(A, lane);
+  if (L::MODEL) return stage_cost_dist_d2(X, t.x, t.y, gl, Hl);
+  return stage_cost_d2(with_weights(A.pr, PAR(NPAR), PAR(NPAR + 1)), X, t.x, t.y, gl, Hl);
 }
 
 // Row quantities of the restoration problem's condensed Newton system (AugRestoSystemSolver).  With the slack s and the
@@ -241,16 +258,18 @@ __device__ __forceinline__ RestoRow resto_row(const SolveArgs& A, const double* 
 // load one instance: p -> PAR, warm start -> LV_U, obstacle table, unit scaling
 template <class L>
 __device__ __noinline__ void ph_load(const SolveArgs& A, int b, int lane) {
-  if (lane < NPAR) PAR(lane) = A.p[(size_t)b * NPAR + lane];
+  if (L::MODEL) {      // p = [state(5); target(3)]: the camera states are zero
+    if (lane < NPAR) PAR(lane) = lane < 5 ? A.p[(size_t)b * L::NPA + lane] : (lane < 8 ? 0.0 : A.p[(size_t)b * L::NPA + lane - 3]);
+  } else if (lane < NPAR) PAR(lane) = A.p[(size_t)b * NPAR + lane];
   if (lane == NPAR) PAR(NPAR) = A.weights ? A.weights[2 * (size_t)b] : A.pr.w1;
   if (lane == NPAR + 1) PAR(NPAR + 1) = A.weights ? A.weights[2 * (size_t)b + 1] : A.pr.w2;
   if (lane == NPAR + 2) PAR(NPAR + 2) = (double)b;      // instance index, for the per-stage target lookup
   const double* ob = A.obs + (A.obs_per_instance ? (size_t)b * 3 * L::NOBS : 0);
   for (int i = lane; i < 3 * L::NOBS; i += 32) smem[L::OBS0 + i] = ob[i];
   if (lane <= L::N) {
-    const double* xx = A.x0 + (size_t)b * (NU * L::N) + NU * lane;
+    const double* xx = A.x0 + (size_t)b * (L::NUA * L::N) + L::NUA * lane;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { LV(LV_U + i) = lane < L::N ? xx[i] : 0.0; LV(LV_DU + i) = 0.0; }
+    for (int i = 0; i < 6; ++i) { LV(LV_U + i) = (lane < L::N && i < L::NUA) ? xx[i] : 0.0; LV(LV_DU + i) = 0.0; }
 #pragma unroll 1
     for (int r = 0; r < L::R; ++r) { RW(A_DC, r) = 1.0; RW(A_DS, r) = 0.0; }
   }
@@ -271,7 +290,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = 0.0;
   if (hasu && lane >= 1) {
-    stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y, gl, Hl);
+    cost_d2<L>(A, st.X, lane, gl, Hl);
 #pragma unroll
     for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
   }
@@ -293,7 +312,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 #pragma unroll 1
     for (int jn = 0; jn < L::NOBS; ++jn) {
       double nx, ny, iD; obs_value<L>(st.X, jn, nx, ny, iD);
-      RW(A_G, 5 + jn) = 0.0; RW(A_S, 5 + jn) = nx; RW(A_IU, 5 + jn) = ny;
+      RW(A_G, L::NB + jn) = 0.0; RW(A_S, L::NB + jn) = nx; RW(A_IU, L::NB + jn) = ny;
     }
   }
 #pragma unroll 1
@@ -308,9 +327,9 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
       zmax = fmax(zmax, fmax(fabs(pv2), fabs(pt2)));
 #pragma unroll 1
       for (int jn = 0; jn < L::NOBS; ++jn) {
-        const double nx = RW(A_S, 5 + jn), ny = RW(A_IU, 5 + jn);
+        const double nx = RW(A_S, L::NB + jn), ny = RW(A_IU, L::NB + jn);
         const double m1 = fabs(nx * pv0 + ny * pv1), m2 = fabs(nx * pt0 + ny * pt1), m3 = fabs(nx * pp0 + ny * pp1);
-        RW(A_G, 5 + jn) = fmax(RW(A_G, 5 + jn), fmax(m1, fmax(m2, m3)));
+        RW(A_G, L::NB + jn) = fmax(RW(A_G, L::NB + jn), fmax(m1, fmax(m2, m3)));
       }
     }
   }
@@ -319,9 +338,9 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
     RW(A_DC, 0) = zmax > mg ? fmax(smin, mg / zmax) : 1.0;
     const double lin = lane >= 1 ? T : 0.0, sl = lin > mg ? fmax(smin, mg / lin) : 1.0;
 #pragma unroll
-    for (int r = 1; r < 5; ++r) RW(A_DC, r) = sl;
+    for (int r = 1; r < L::NB; ++r) RW(A_DC, r) = sl;
 #pragma unroll 1
-    for (int jn = 0; jn < L::NOBS; ++jn) { const double m = RW(A_G, 5 + jn); RW(A_DC, 5 + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
+    for (int jn = 0; jn < L::NOBS; ++jn) { const double m = RW(A_G, L::NB + jn); RW(A_DC, L::NB + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
   }
   __syncwarp();
   return gmax > A.o.max_grad ? fmax(A.o.scal_min, A.o.max_grad / gmax) : 1.0;
@@ -337,7 +356,7 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
   for (int i = 0; i < 6; ++i) {
     u[i] = act ? LV(LV_U + i) : 0.0;
     if (hasu) {
-      const Bnd b = ctl_bounds(A, lane, i);
+      const Bnd b = ctl_bounds<L>(A, lane, i);
       u[i] = push_in(u[i], b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
       LV(LV_U + i) = u[i]; LV(LV_ZL + i) = b.hl ? 1.0 : 0.0; LV(LV_ZU + i) = b.hu ? 1.0 : 0.0;
       nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
@@ -386,7 +405,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
   for (int e = 0; e < 21; ++e) Hl[e] = 0.0;
   double l = 0.0;
   if (!RS) {
-    if (hasu) l = stage_cost_d2(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y, gl, Hl);
+    if (hasu) l = cost_d2<L>(A, st.X, lane, gl, Hl);
     if (lane == 0) {   // stage 0 is constant in w
 #pragma unroll
       for (int v = 0; v < 6; ++v) gl[v] = 0.0;
@@ -479,6 +498,10 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
 #pragma unroll
       for (int i = 0; i < 8; ++i) { LQ(LQ_QB + i) = ls ? 0.0 : qb[i]; LQ(LQ_QD + i) = ls ? 0.0 : qd[i]; }
     }
+    if (!L::FOLD && L::NB < 5) {      // rows that do not exist in this model
+#pragma unroll
+      for (int r = L::NB; r < 5; ++r) LQ(LQ_DG + r) = 0.0;
+    }
     LQ(LQ_DD + 0) = st.cps * st.cth; LQ(LQ_DD + 1) = st.sps * st.cth; LQ(LQ_DD + 2) = st.sth;
     LQ(LQ_EE + 0) = dy.e03; LQ(LQ_EE + 1) = dy.e13; LQ(LQ_EE + 2) = dy.e23; LQ(LQ_EE + 3) = dy.e04; LQ(LQ_EE + 4) = dy.e14;
     LQ(LQ_Q + 21) = q22;
@@ -507,9 +530,9 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
     const double eta = RS ? A.o.resto_eta_factor * sqrt(mu) : 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      double sig = 1.0, rb = 0.0;
-      if (hasu) {
-        const Bnd b = ctl_bounds(A, lane, i);
+      double sig = 1.0, rb = 0.0;       // absent controls (model 1) keep the unit diagonal and a zero right-hand side
+      if (hasu && i < L::NUA) {
+        const Bnd b = ctl_bounds<L>(A, lane, i);
         const double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
         const double sl = (u[i] - b.lo), su = (b.hi - u[i]);
         double gR = 0.0;
@@ -627,7 +650,7 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
       const double eta = RS ? A.o.resto_eta_factor * sqrt(mu) : 0.0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        const Bnd b = ctl_bounds(A, lane, i);
+        const Bnd b = ctl_bounds<L>(A, lane, i);
         const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
         const double il = b.hl ? rcp((u - b.lo)) : 0.0, iu = b.hu ? rcp((b.hi - u)) : 0.0;
         tp = fmax(tp, fmax(-du * il, du * iu));
@@ -670,7 +693,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
     ut[i] = 0.0;
     if (hasu) {
       ut[i] = fma(alpha, soc ? SOC(SOC_DUS + i) : LV(LV_DU + i), LV(LV_U + i));   // same expression as ph_accept
-      const Bnd b = ctl_bounds(A, lane, i);
+      const Bnd b = ctl_bounds<L>(A, lane, i);
       if (b.hl) prod *= (ut[i] - b.lo);
       if (b.hu) prod *= (b.hi - ut[i]);
       if (b.hl && !b.hu) dt += ut[i] - b.lo;
@@ -681,7 +704,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
   }
   Stage st; rollout(pr, &PAR(0), ut, lane, st);
   double l = 0.0;
-  if (!RS) l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y) : 0.0;
+  if (!RS) l = hasu ? cost_val<L>(A, st.X, lane) : 0.0;
   else l = 0.5 * A.o.resto_eta_factor * sqrt(mu) * fr;
   double th = 0.0;
   if (act) {
@@ -764,7 +787,7 @@ __device__ __noinline__ void ph_repair(const SolveArgs& A, int lane, double mu, 
   if (lane < L::N) {
 #pragma unroll 1
     for (int i = 0; i < 6; ++i) {
-      const Bnd b = ctl_bounds(A, lane, i);
+      const Bnd b = ctl_bounds<L>(A, lane, i);
       double u = LV(LV_U + i);
       if (b.hl && u - b.lo < smin) { const double t = safe_value(u - b.lo, b.lo); u = b.lo + t; LV(LV_ZL + i) = clampz(LV(LV_ZL + i), t); }
       if (b.hu && b.hi - u < smin) { const double t = safe_value(b.hi - u, b.hi); u = b.hi - t; LV(LV_ZU + i) = clampz(LV(LV_ZU + i), t); }
@@ -776,7 +799,7 @@ __device__ __noinline__ void ph_repair(const SolveArgs& A, int lane, double mu, 
     for (int r = 0; r < L::R; ++r) {
       const Bnd b = row_bounds<L>(A, lane, r, RW(A_DC, r));
       double s = RW(A_S, r);
-      if (r < NBOX && b.hl && s - b.lo < smin) { const double t = safe_value(s - b.lo, b.lo); s = b.lo + t; RW(A_VL, r) = clampz(RW(A_VL, r), t); RW(A_IL, r) = rcp(t); }
+      if (r < L::NB && b.hl && s - b.lo < smin) { const double t = safe_value(s - b.lo, b.lo); s = b.lo + t; RW(A_VL, r) = clampz(RW(A_VL, r), t); RW(A_IL, r) = rcp(t); }
       if (b.hu && b.hi - s < smin) { const double t = safe_value(b.hi - s, b.hi); s = b.hi - t; RW(A_VU, r) = clampz(RW(A_VU, r), t); RW(A_IU, r) = rcp(t); }
       RW(A_S, r) = s;
       if (RS) {
@@ -802,7 +825,7 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
   if (hasu) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const Bnd b = ctl_bounds(A, lane, i);
+      const Bnd b = ctl_bounds<L>(A, lane, i);
       const double u = LV(LV_U + i), du = soc ? SOC(SOC_DUS + i) : LV(LV_DU + i);
       double zl = LV(LV_ZL + i), zu = LV(LV_ZU + i);
       if (b.hl) zl += a_du * ((mu - zl * du) * rcp(u - b.lo) - zl);
@@ -833,7 +856,7 @@ __device__ __noinline__ void ph_accept(const SolveArgs& A, int lane, double alph
       if (hl) { const double sl = sn - b.lo; il2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) vl = fmax(fmin(vl, ks * mu * il2), mu * il2 * iks); }
       if (hu) { const double sl = b.hi - sn; iu2 = rcp(sl); const bool un_ = sl < smin; bad = bad || un_; if (reset && !un_) vu = fmax(fmin(vu, ks * mu * iu2), mu * iu2 * iks); }
       RW(A_S, r) = sn; RW(A_VU, r) = vu; RW(A_IU, r) = iu2;
-      if (r < NBOX) { RW(A_VL, r) = vl; RW(A_IL, r) = il2; }
+      if (r < L::NB) { RW(A_VL, r) = vl; RW(A_IL, r) = il2; }
       if (RS) {
         const double n0 = RG(G_N, r), p0 = RG(G_P, r), zn0 = RG(G_ZN, r), zp0 = RG(G_ZP, r);
         const double dn = soc ? RG(G_DN2, r) : RG(G_DN, r), dp = soc ? RG(G_DP2, r) : RG(G_DP, r);
@@ -865,8 +888,8 @@ __device__ __noinline__ void ph_slot(double* cold, int slot, bool save, bool wit
   cp(L::LV0 + LV_DX * S, 18 * S, 14 * S);                  // DX, DU
   cp(L::rw(A_S, 0), 32 * S, 3 * RSZ);                      // S, Y, VU
   cp(L::rw(A_IU, 0), 32 * S + 3 * RSZ, RSZ);               // IU
-  cp(L::rw(A_VL, 0), 32 * S + 4 * RSZ, 2 * NBOX * S);      // VL, IL (box rows)
-  constexpr int R0 = 32 * S + 4 * RSZ + 2 * NBOX * S;
+  cp(L::rw(A_VL, 0), 32 * S + 4 * RSZ, 2 * L::NB * S);      // VL, IL (box rows)
+  constexpr int R0 = 32 * S + 4 * RSZ + 2 * L::NB * S;
   if (with_resto)
     for (int i = lane; i < 4 * RSZ; i += 32) { if (save) sl[R0 + i] = cold[i]; else cold[i] = sl[R0 + i]; }
   __syncwarp();
@@ -883,7 +906,7 @@ __device__ __noinline__ void ph_resto_init(const SolveArgs& A, int lane, double 
       const double c = RW(A_G, r) - RW(A_S, r);
       const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h), pv = c + nv;
       RG(G_N, r) = nv; RG(G_P, r) = pv; RG(G_ZN, r) = mu / nv; RG(G_ZP, r) = mu / pv;
-      if (r < NBOX) RW(A_VL, r) = fmin(rho, RW(A_VL, r));
+      if (r < L::NB) RW(A_VL, r) = fmin(rho, RW(A_VL, r));
       RW(A_VU, r) = fmin(rho, RW(A_VU, r)); RW(A_Y, r) = 0.0;
     }
 #pragma unroll
@@ -921,7 +944,7 @@ __device__ __noinline__ double ph_resto_finish(const SolveArgs& A, int lane, dou
   if (lane < L::N) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const Bnd b = ctl_bounds(A, lane, i);
+      const Bnd b = ctl_bounds<L>(A, lane, i);
       const double u0 = sl[(LV_U + i) * S + lane], zl0 = sl[(LV_ZL + i) * S + lane], zu0 = sl[(LV_ZU + i) * S + lane], u1 = LV(LV_U + i);
       double zl = 0.0, zu = 0.0;
       if (b.hl) upd(zl0, (u0 - b.lo), (u1 - b.lo), zl);
@@ -935,12 +958,12 @@ __device__ __noinline__ double ph_resto_finish(const SolveArgs& A, int lane, dou
       const double dc = RW(A_DC, r);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
       const double s0 = sl[32 * S + (A_S * L::R + r) * S + lane], vu0 = sl[32 * S + (A_VU * L::R + r) * S + lane];
-      const double vl0 = r < NBOX ? sl[32 * S + 4 * L::RSZ + r * S + lane] : 0.0;
+      const double vl0 = r < L::NB ? sl[32 * S + 4 * L::RSZ + r * S + lane] : 0.0;
       const double s1 = RW(A_S, r);
       double vl = 0.0, vu = 0.0;
-      if (b.hl && r < NBOX) upd(vl0, (s0 - b.lo), (s1 - b.lo), vl);
+      if (b.hl && r < L::NB) upd(vl0, (s0 - b.lo), (s1 - b.lo), vl);
       if (b.hu) upd(vu0, (b.hi - s0), (b.hi - s1), vu);
-      if (pass == 1) { if (r < NBOX) RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_Y, r) = 0.0; RW(A_DS, r) = 0.0; }
+      if (pass == 1) { if (r < L::NB) RW(A_VL, r) = vl; RW(A_VU, r) = vu; RW(A_Y, r) = 0.0; RW(A_DS, r) = 0.0; }
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) if (pass == 1) LV(LV_DU + i) = 0.0;
@@ -954,11 +977,11 @@ template <class L>
 __device__ __noinline__ void ph_unit_mults(const SolveArgs& A, int lane) {
   if (lane < L::N) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { const Bnd b = ctl_bounds(A, lane, i); LV(LV_ZL + i) = b.hl ? 1.0 : 0.0; LV(LV_ZU + i) = b.hu ? 1.0 : 0.0; }
+    for (int i = 0; i < 6; ++i) { const Bnd b = ctl_bounds<L>(A, lane, i); LV(LV_ZL + i) = b.hl ? 1.0 : 0.0; LV(LV_ZU + i) = b.hu ? 1.0 : 0.0; }
   }
   if (lane <= L::N) {
 #pragma unroll 1
-    for (int r = 0; r < L::R; ++r) { if (r < NBOX) RW(A_VL, r) = RW(A_IL, r) > 0.0 ? 1.0 : 0.0; RW(A_VU, r) = RW(A_IU, r) > 0.0 ? 1.0 : 0.0; }
+    for (int r = 0; r < L::R; ++r) { if (r < L::NB) RW(A_VL, r) = RW(A_IL, r) > 0.0 ? 1.0 : 0.0; RW(A_VU, r) = RW(A_IU, r) > 0.0 ? 1.0 : 0.0; }
   }
   __syncwarp();
 }
@@ -968,27 +991,27 @@ template <class L>
 __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, double df, int status, int iter) {
   const Prob& pr = A.pr; constexpr int N = L::N, R = L::R, S = L::S;
   const bool act = lane <= N, hasu = lane < N;
-  constexpr int nw = NU * N, ng = R * S;
+  constexpr int nw = L::NUA * N, ng = R * S;
   double u[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = 0.0;
   if (hasu) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) u[i] = fmin(fmax(LV(LV_U + i), __ldg(A.lbx + NU * lane + i)), __ldg(A.ubx + NU * lane + i));
+    for (int i = 0; i < L::NUA; ++i) u[i] = fmin(fmax(LV(LV_U + i), __ldg(A.lbx + L::NUA * lane + i)), __ldg(A.ubx + L::NUA * lane + i));
     if (A.x) {
-      double* xo = A.x + (size_t)b * nw + NU * lane;
+      double* xo = A.x + (size_t)b * nw + L::NUA * lane;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) xo[i] = u[i];
+      for (int i = 0; i < L::NUA; ++i) xo[i] = u[i];
     }
     if (A.lam_x) {
-      double* lo = A.lam_x + (size_t)b * nw + NU * lane;
+      double* lo = A.lam_x + (size_t)b * nw + L::NUA * lane;
       const double idf = 1.0 / df;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) lo[i] = (LV(LV_ZU + i) - LV(LV_ZL + i)) * idf;
+      for (int i = 0; i < L::NUA; ++i) lo[i] = (LV(LV_ZU + i) - LV(LV_ZL + i)) * idf;
     }
   }
   Stage st; rollout(pr, &PAR(0), u, lane, st);
-  const double l = hasu ? stage_cost(with_weights(pr, PAR(NPAR), PAR(NPAR + 1)), st.X, stage_target<L>(A, lane).x, stage_target<L>(A, lane).y) : 0.0;
+  const double l = hasu ? cost_val<L>(A, st.X, lane) : 0.0;
   const double fu = warp_sum(l);
   if (lane == 0) {
     if (A.f) A.f[b] = fu;
@@ -1012,10 +1035,10 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
   if (A.step_p) {     // fused closed-loop shift of this instance (NMPC_TT.py:13-30): warm start, plant, target, FOV error
     double* uw = A.step_u + (size_t)b * nw;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < L::NUA; ++i) {
       const double un = __shfl_down_sync(FULL, u[i], 1);          // control of the next stage
-      if (lane < N - 1) uw[NU * lane + i] = un;                   // drop the first stage ...
-      else if (lane == N - 1) uw[NU * lane + i] = u[i];           // ... and repeat the last (:20-23)
+      if (lane < N - 1) uw[L::NUA * lane + i] = un;               // drop the first stage ...
+      else if (lane == N - 1) uw[L::NUA * lane + i] = u[i];       // ... and repeat the last (:20-23)
     }
     if (lane == 0) {
       double tv, tw;
@@ -1026,7 +1049,7 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
         const double* e = A.sched_table + ((size_t)row * A.sched_len + at) * 2;
         tv = __ldg(e); tw = __ldg(e + 1);
       }
-      closed_loop_shift(pr.T, pr.hv, pr.hh, A.step_p + (size_t)b * NPAR, u, tv, tw,
+      closed_loop_shift_model(L::MODEL, pr.T, pr.hv, pr.hh, A.step_p + (size_t)b * L::NPA, u, tv, tw,
                         A.step_fov ? A.step_fov + 2 * (size_t)b : nullptr, A.step_err ? A.step_err + b : nullptr);
     }
   }
@@ -1192,7 +1215,7 @@ __device__ __noinline__ void wd_stop(const SolveArgs& A, double* cold, int lane,
 template <class L>
 __device__ __noinline__ int soft_step(const SolveArgs& A, double* cold, int lane, double df, int nzt, double& alpha) {
   const Opt& o = A.o;
-  constexpr int mtot = L::R * L::S, nx_ = NU * L::N;
+  constexpr int mtot = L::R * L::S, nx_ = L::NUA * L::N;
   const int mode = (int)AL(F_MODE);
   const double dw = AL(F_DW);
   if (o.soft_resto_red == 0.0) return 0;
@@ -1598,9 +1621,9 @@ __device__ __noinline__ void next_order(const SolveArgs& A, int lane) {
 
 // persistent kernel: Lay::WPB warps per block (one block per SM), one instance per warp at a time, instances from
 // an atomic work queue (optionally in a caller-given order)
-template <int N_, int NOBS_>
-__global__ void __launch_bounds__(32 * Lay<N_, NOBS_>::WPB, 1) nmpc_ipm_kernel(const SolveArgs A) {
-  using L = Lay<N_, NOBS_>;
+template <int N_, int NOBS_, int MODEL_>
+__global__ void __launch_bounds__(32 * Lay<N_, NOBS_, MODEL_>::WPB, 1) nmpc_ipm_kernel(const SolveArgs A) {
+  using L = Lay<N_, NOBS_, MODEL_>;
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next call on this handle starts from clean counters
     *A.counter_next = 0; *A.done_next = 0;

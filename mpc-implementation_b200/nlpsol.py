@@ -37,7 +37,7 @@ def _is_cuda_tensor(a) -> bool:
 def _spec_from(problem, opts: Optional[dict]) -> Dict[str, Any]:
     if isinstance(problem, Scenario):
         d = dict(T=problem.T, N=problem.N, obstacles=problem.obstacle_table(), w1=problem.w1, w2=problem.w2,
-                 vfov=problem.vfov, hfov=problem.hfov)
+                 vfov=problem.vfov, hfov=problem.hfov, model=problem.model)
     else:
         d = dict(problem)
         if "obstacles" in d:
@@ -63,7 +63,9 @@ class Solver:
         self.T, self.N = float(d["T"]), int(d["N"])
         self.obstacles = np.ascontiguousarray(d["obstacles"], dtype=np.float64)
         self.n_obs = self.obstacles.shape[0]
-        self.n_w, self.n_g = NU * self.N, (5 + self.n_obs) * (self.N + 1)
+        self.model = int(d.get("model", 0))     # 0: the scripts' 8-state UAV + camera; 1: the gimbal-less 5-state tracker (nmpc_b200.h)
+        self.n_p = 8 if self.model else NP
+        self.n_w, self.n_g = (3 if self.model else NU) * self.N, ((2 if self.model else 5) + self.n_obs) * (self.N + 1)
         self.device = device
         self._d = d
         self._h = C.c_void_p()
@@ -81,7 +83,7 @@ class Solver:
         d = self._d
         spec = _ffi.NmpcSpec(self.T, self.N, self.n_obs, float(d.get("w1", 1.0)), float(d.get("w2", 2.0)),
                              float(d.get("vfov", 1.0)), float(d.get("hfov", 1.0)),
-                             d["max_iter"], d["scaling"], d["tol"], int(max_batch), self.fill)
+                             d["max_iter"], d["scaling"], d["tol"], int(max_batch), self.fill, self.model)
         _ffi.check(L.nmpc_create(C.byref(spec), self.device, C.byref(self._h)), "nmpc_create")
         self._max_batch = max_batch
         self.spec = spec
@@ -169,12 +171,11 @@ class Solver:
             self._dev_cache[k] = buf
         return buf[1]
 
-    @staticmethod
-    def _batch_of(p) -> int:
+    def _batch_of(self, p) -> int:
         """Batch size of a parameter argument in any of the accepted containers (list, numpy, torch; (11,), (11,1), (B,11))."""
         if _is_cuda_tensor(p):
-            return int(p.numel() // NP)
-        return int(np.asarray(p, dtype=np.float64).size // NP)
+            return int(p.numel() // self.n_p)
+        return int(np.asarray(p, dtype=np.float64).size // self.n_p)
 
     def _traj(self, traj, p):
         """Context manager: nmpc_set_target_trajectory for the duration of one call."""
@@ -238,7 +239,7 @@ class Solver:
     def _call_host(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, blocking=True):
         L = _ffi.lib()
         single = np.asarray(p).ndim == 1 or (np.asarray(p).ndim == 2 and np.asarray(p).shape[1] == 1)
-        p = self._host(p, NP, "p")
+        p = self._host(p, self.n_p, "p")
         B = p.shape[0]
         x0 = np.zeros((B, self.n_w)) if x0 is None else self._host(x0, self.n_w, "x0")
         if x0.shape[0] != B:
@@ -271,7 +272,7 @@ class Solver:
         L = _ffi.lib()
         dev = p.device
         single = p.dim() == 1
-        p = p.to(torch.float64).reshape(-1, NP).contiguous()
+        p = p.to(torch.float64).reshape(-1, self.n_p).contiguous()
         B = p.shape[0]
         x0 = torch.zeros((B, self.n_w), dtype=torch.float64, device=dev) if x0 is None else x0.to(torch.float64).reshape(B, self.n_w).contiguous()
         lbx, ubx = self._dev_const("lbx", lbx), self._dev_const("ubx", ubx)
@@ -335,7 +336,7 @@ class Solver:
         dev = f"cuda:{self.device}"
         to = lambda a, n: torch.as_tensor(np.asarray(a, dtype=np.float64) if not _is_cuda_tensor(a) else a,
                                           dtype=torch.float64, device=dev).reshape(-1, n).contiguous()
-        w, p = to(w, self.n_w), to(p, NP)
+        w, p = to(w, self.n_w), to(p, self.n_p)
         B = w.shape[0]
         lam_t = to(lam, self.n_g) if lam is not None else None
         v_t = to(v, self.n_w) if v is not None else None

@@ -7,6 +7,8 @@ Each reference script is the same NLP with different module-level constants (SUR
     Python/Race Trajectory 1.py  T=.2  3 dummy obstacles  target v=14, race schedule  1595 steps
     Python/Race Track 2.py       T=.2  10 obstacles r=50  target v=12, oval           2000 steps
     Python/10_obstacles.py       T=.2  3 real r=100 + 7 dummies, target v=13          1595 steps
+and the gimbal-less model variant (model = 1: 5 states, 3 controls, p[8], rows [z, theta], distance-only cost):
+    MATLAB/Dynamic Obstacles/NMPC_TT.m  T=.2  no obstacles  target (15, 0.12)          100 steps
 """
 from __future__ import annotations
 
@@ -66,18 +68,31 @@ class Scenario:
     w2: float = 2.0
     vfov: float = 1.0
     hfov: float = 1.0
+    model: int = 0        # 0: UAV + gimballed camera (every Python script); 1: gimbal-less tracker (MATLAB/Dynamic Obstacles/NMPC_TT.m)
 
     @property
     def n_obs(self) -> int:
         return len(self.obstacles)
 
     @property
+    def nu(self) -> int:
+        return 3 if self.model else NU
+
+    @property
+    def n_box(self) -> int:
+        return 2 if self.model else 5
+
+    @property
+    def n_p(self) -> int:
+        return 8 if self.model else NP
+
+    @property
     def n_w(self) -> int:
-        return NU * self.N
+        return self.nu * self.N
 
     @property
     def n_g(self) -> int:
-        return (5 + self.n_obs) * (self.N + 1)
+        return (self.n_box + self.n_obs) * (self.N + 1)
 
     def obstacle_table(self) -> np.ndarray:
         """[n_obs][3] = cx, cy, UAV_r + obs_r  (the constants of NMPC_TT.py:241-243)."""
@@ -86,14 +101,15 @@ class Scenario:
         return o
 
     def bounds(self):
-        """lbx, ubx, lbg, ubg exactly as NMPC_TT.py:62-89, :269-306 (Race Track 2.py:289-341)."""
+        """lbx, ubx, lbg, ubg exactly as NMPC_TT.py:62-89, :269-306 (Race Track 2.py:289-341); model 1: the first three
+        controls and the first two rows of the same tables (MATLAB/Dynamic Obstacles/NMPC_TT.m:14-22, :127-133)."""
         N = self.N
-        lo = [14.0, -PI / 30, -PI / 21, -PI / 30, -PI / 30, -PI / 30]
-        hi = [30.0, PI / 30, PI / 21, PI / 30, PI / 30, PI / 30]
+        lo = [14.0, -PI / 30, -PI / 21, -PI / 30, -PI / 30, -PI / 30][:self.nu]
+        hi = [30.0, PI / 30, PI / 21, PI / 30, PI / 30, PI / 30][:self.nu]
         lbx = np.tile(np.array(lo), N)
         ubx = np.tile(np.array(hi), N)
-        glo = [75.0, -0.2618, -PI / 6, -PI / 6, -PI / 2] + [-np.inf] * self.n_obs
-        ghi = [150.0, 0.2618, PI / 6, PI / 6, PI / 2] + [0.0] * self.n_obs
+        glo = [75.0, -0.2618, -PI / 6, -PI / 6, -PI / 2][:self.n_box] + [-np.inf] * self.n_obs
+        ghi = [150.0, 0.2618, PI / 6, PI / 6, PI / 2][:self.n_box] + [0.0] * self.n_obs
         lbg = np.tile(np.array(glo), N + 1)
         ubg = np.tile(np.array(ghi), N + 1)
         return lbx, ubx, lbg, ubg
@@ -124,6 +140,9 @@ SCENARIOS = {
     "10_obstacles": Scenario("10_obstacles", "Python/10_obstacles.py", 0.2, 15,
                              ((500.0, 20.0, 100.0), (1700.0, 197.0, 100.0), (130.0, 830.0, 100.0)) + ((10000.0, 10000.0, 100.0),) * 7,
                              _X99, _TGT, _piecewise(13.0, _RACE1_TABLE), 1595),
+    # model variant: x0 / xs NMPC_TT.m:138-139, constant target input shift1.m:9, sim_time / T = 100 steps :144
+    "gimbal_less": Scenario("gimbal_less", "MATLAB/Dynamic Obstacles/NMPC_TT.m", 0.2, 15, (), (90.0, 150.0, 80.0, 0.0, 0.0),
+                            _TGT, lambda i: (15.0, 0.12), 100, w1=1.0, w2=0.0, model=1),
 }
 
 
@@ -136,7 +155,7 @@ def get(name: str) -> Scenario:
 # every stage-0 row of g strictly feasible and break the mirror symmetry of the scripts' first solve
 # ------------------------------------------------------------------------------------------------
 def random_instances(sc: Scenario, B: int, seed: int):
-    """Returns p [B,11], target (v, omega) [B,2] as float64 numpy arrays."""
+    """Returns p [B,11] (model 1: [B,8], the same draws without the camera states), target (v, omega) [B,2] as float64 numpy arrays."""
     rng = np.random.default_rng(seed)
     x = np.empty((B, NX))
     cx, cy = sc.x_init[0], sc.x_init[1]
@@ -155,4 +174,4 @@ def random_instances(sc: Scenario, B: int, seed: int):
     vw = np.empty((B, 2))
     vw[:, 0] = rng.uniform(8, 20, B)
     vw[:, 1] = rng.uniform(-0.05, 0.05, B)
-    return np.concatenate([x, tgt], axis=1), vw
+    return np.concatenate([x[:, :5] if sc.model else x, tgt], axis=1), vw

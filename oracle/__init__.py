@@ -29,7 +29,18 @@ STAT_COLUMNS = ("factorizations", "soc_accepted", "resto_calls", "resto_iters", 
 
 class OracleSpec(C.Structure):
     _fields_ = [("T", C.c_double), ("N", C.c_int32), ("n_obs", C.c_int32),
-                ("w1", C.c_double), ("w2", C.c_double), ("vfov", C.c_double), ("hfov", C.c_double)]
+                ("w1", C.c_double), ("w2", C.c_double), ("vfov", C.c_double), ("hfov", C.c_double), ("model", C.c_int32)]
+
+    # model 0: 8 states / 6 controls / p[11] / rows [z, theta, X5, X6, X7, obstacles]  (the Python scripts)
+    # model 1: 5 states / 3 controls / p[8]  / rows [z, theta, obstacles]              (MATLAB/Dynamic Obstacles/NMPC_TT.m)
+    @property
+    def nu(self): return 3 if self.model else 6
+    @property
+    def npar(self): return 8 if self.model else 11
+    @property
+    def nw(self): return self.nu * self.N
+    @property
+    def ng(self): return ((2 if self.model else 5) + self.n_obs) * (self.N + 1)
 
 
 def build(force: bool = False) -> Path:
@@ -77,8 +88,8 @@ def _c(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def make_spec(T, N, n_obs, w1=1.0, w2=2.0, vfov=1.0, hfov=1.0) -> OracleSpec:
-    return OracleSpec(float(T), int(N), int(n_obs), float(w1), float(w2), float(vfov), float(hfov))
+def make_spec(T, N, n_obs, w1=1.0, w2=2.0, vfov=1.0, hfov=1.0, model=0) -> OracleSpec:
+    return OracleSpec(float(T), int(N), int(n_obs), float(w1), float(w2), float(vfov), float(hfov), int(model))
 
 
 def obstacle_table(obstacles, uav_r=5.0) -> np.ndarray:
@@ -90,7 +101,7 @@ def obstacle_table(obstacles, uav_r=5.0) -> np.ndarray:
 
 def evaluate(spec: OracleSpec, obs: np.ndarray, w, p, lam_g=None, sigma=1.0, hessian=False, target_traj=None):
     N, n_obs = spec.N, spec.n_obs
-    nw, ng = 6 * N, (5 + n_obs) * (N + 1)
+    nw, ng = spec.nw, spec.ng
     w, p, obs = _c(w), _c(p), _c(obs)
     f = C.c_double()
     g = np.zeros(ng); grad = np.zeros(nw); J = np.zeros((ng, nw)); X = np.zeros((N + 1, 8))
@@ -108,8 +119,8 @@ def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=
     lam_x0 (B,6N), lam_g0 (B,n_g): multiplier guesses of the NON-REFERENCE warm-start mode (Options::ws_* in
     nmpc_oracle.cpp); a NaN in lam_x0[b, 0] cold-starts instance b."""
     N, n_obs = spec.N, spec.n_obs
-    nw, ng = 6 * N, (5 + n_obs) * (N + 1)
-    p = _c(p).reshape(-1, 11); B = p.shape[0]
+    nw, ng = spec.nw, spec.ng
+    p = _c(p).reshape(-1, spec.npar); B = p.shape[0]
     x0 = _c(x0).reshape(B, nw)
     lbx, ubx, lbg, ubg, obs = _c(lbx), _c(ubx), _c(lbg), _c(ubg), _c(obs)
     assert lbx.size == nw and ubx.size == nw and lbg.size == ng and ubg.size == ng
@@ -134,7 +145,7 @@ def solve(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, *, obs_per_instance=
 
 
 def solve_log(spec: OracleSpec, obs, p, x0, lbx, ubx, lbg, ubg, scaling=True, max_log=128):
-    N = spec.N; nw = 6 * N
+    N = spec.N; nw = spec.nw
     x = np.zeros(nw); f = C.c_double(); st = C.c_int32(); it = C.c_int32()
     log = np.zeros((max_log, 9))
     n = lib().oracle_solve_log(C.byref(spec), _dp(_c(p)), _dp(_c(x0)), _dp(_c(lbx)), _dp(_c(ubx)), _dp(_c(lbg)),

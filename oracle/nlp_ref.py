@@ -176,3 +176,89 @@ def fov_centre(x0: np.ndarray, vfov: float = 1.0, hfov: float = 1.0):
     b_p = (x0[2] * math.tan(x0[5] + hfov / 2) - x0[2] * math.tan(x0[5] - hfov / 2)) / 2
     return (x0[0] + a_p + x0[2] * math.tan(x0[6] - vfov / 2),
             x0[1] + b_p + x0[2] * math.tan(x0[5] - hfov / 2))
+
+
+# ----------------------------------------------------------------------------------------------
+# The gimbal-less tracker of MATLAB/Dynamic Obstacles/NMPC_TT.m (model 1): 5 states, 3 controls, p = [state(5); target(3)],
+# distance-only cost, rows [z, theta] per stage.  Literal restatement, independent of the 8-state code above.
+# ----------------------------------------------------------------------------------------------
+NX5, NU5, NP5 = 5, 3, 8     # NMPC_TT.m:25-35, :37
+
+
+@dataclass
+class RefSpec5:
+    T: float = 0.2          # NMPC_TT.m:9
+    N: int = 15             # NMPC_TT.m:10
+
+    @property
+    def n_w(self) -> int:
+        return NU5 * self.N
+
+    @property
+    def n_g(self) -> int:
+        return 2 * (self.N + 1)
+
+
+def rollout5(spec: RefSpec5, w: torch.Tensor, p: torch.Tensor) -> List[torch.Tensor]:
+    """X(:,1) = P(1:5); X(:,k+1) = X(:,k) + T*f_u(X(:,k), U(:,k))   NMPC_TT.m:45-51, rhs :33-34"""
+    X = [p[0:5]]
+    for k in range(spec.N):
+        st = X[k]
+        v_u, om2, om3 = w[NU5 * k: NU5 * (k + 1)]
+        th, ps = st[3], st[4]
+        rhs = torch.stack([v_u * torch.cos(ps) * torch.cos(th), v_u * torch.sin(ps) * torch.cos(th), v_u * torch.sin(th), om2, om3])
+        X.append(st + spec.T * rhs)
+    return X
+
+
+def objective5(spec: RefSpec5, w: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """obj = sum_{k=1..N} sqrt((X(1,k)-P(6))^2 + (X(2,k)-P(7))^2)   NMPC_TT.m:100-104 (1-based: stages 0..N-1)"""
+    X = rollout5(spec, w, p)
+    obj = torch.zeros((), dtype=w.dtype)
+    for k in range(spec.N):
+        obj = obj + torch.sqrt((X[k][0] - p[5]) ** 2 + (X[k][1] - p[6]) ** 2)
+    return obj
+
+
+def constraints5(spec: RefSpec5, w: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """g = [X(3,k); X(4,k)] for k = 1..N+1   NMPC_TT.m:107-111"""
+    X = rollout5(spec, w, p)
+    rows = []
+    for k in range(spec.N + 1):
+        rows += [X[k][2], X[k][3]]
+    return torch.stack(rows)
+
+
+def bounds5(spec: RefSpec5):
+    """NMPC_TT.m:14-22, :127-133"""
+    N = spec.N
+    lbx = np.tile(np.array([14.0, -PI / 30, -PI / 21]), N)
+    ubx = np.tile(np.array([30.0, PI / 30, PI / 21]), N)
+    lbg = np.tile(np.array([75.0, -0.2618]), N + 1)
+    ubg = np.tile(np.array([150.0, 0.2618]), N + 1)
+    return lbx, ubx, lbg, ubg
+
+
+def eval_all5(spec: RefSpec5, w: np.ndarray, p: np.ndarray, lam_g: np.ndarray | None = None, sigma: float = 1.0):
+    wt = torch.tensor(np.asarray(w, dtype=np.float64), requires_grad=True)
+    pt = torch.tensor(np.asarray(p, dtype=np.float64))
+    f = objective5(spec, wt, pt)
+    g = constraints5(spec, wt, pt)
+    grad = torch.autograd.grad(f, wt, retain_graph=True)[0]
+    J = torch.autograd.functional.jacobian(lambda ww: constraints5(spec, ww, pt), wt)
+    out = dict(f=float(f.detach()), g=g.detach().numpy(), grad=grad.numpy(), J=J.numpy())
+    if lam_g is not None:
+        lt = torch.tensor(np.asarray(lam_g, dtype=np.float64))
+        H = torch.autograd.functional.hessian(lambda ww: sigma * objective5(spec, ww, pt) + (lt * constraints5(spec, ww, pt)).sum(), wt)
+        out["H"] = H.numpy()
+    return out
+
+
+def shift1(T: float, x0: np.ndarray, u: np.ndarray, xs: np.ndarray, con_t: Tuple[float, float] = (15.0, 0.12)):
+    """MATLAB/Dynamic Obstacles/shift1.m: u is (N,3) (rows = stages).  Returns x0+, u0+ (drop first row, repeat last), xs+."""
+    v, om2, om3 = u[0]
+    th, ps = x0[3], x0[4]
+    x0n = x0 + T * np.array([v * math.cos(ps) * math.cos(th), v * math.sin(ps) * math.cos(th), v * math.sin(th), om2, om3])
+    xsn = xs + T * np.array([con_t[0] * math.cos(xs[2]), con_t[0] * math.sin(xs[2]), con_t[1]])
+    u0 = np.concatenate([u[1:], u[-1:]], axis=0)
+    return x0n, u0, xsn

@@ -108,10 +108,18 @@ template <int NV> Jet<NV> jtan(const Jet<NV>& a) { double t = std::tan(a.v); dou
 // ------------------------------------------------------------------------------------------
 // problem description
 // ------------------------------------------------------------------------------------------
+// model 0: the scripts' UAV with a gimballed camera, 8 states / 6 controls, p = [state(8); x_t; y_t; theta_t]   NMPC_TT.py:105-154
+// model 1: the gimbal-less tracker of MATLAB/Dynamic Obstacles/NMPC_TT.m:25-35 -- states (x,y,z,theta,psi), controls
+//          (v, omega_2, omega_3), p = [state(5); x_t; y_t; theta_t], cost = horizontal distance only (:100-104), rows
+//          [z, theta] per stage (:107-111).  Its dynamics are the first five rows of model 0's, so the rollout and the
+//          sensitivities below run on the 8-state arrays with the camera states held at zero.
 struct Spec {
-  double T; int N; int n_obs; double w1, w2, vfov, hfov;
-  int rows() const { return 5 + n_obs; }
-  int nw() const { return NU * N; }
+  double T; int N; int n_obs; double w1, w2, vfov, hfov; int model = 0;
+  int nu() const { return model ? 3 : NU; }
+  int nlin() const { return model ? 2 : 5; }
+  int npar() const { return model ? 8 : NPAR; }
+  int rows() const { return nlin() + n_obs; }
+  int nw() const { return nu() * N; }
   int ng() const { return rows() * (N + 1); }
 };
 
@@ -157,9 +165,9 @@ J6 j6cos(const J6& a) { return jcos(a); } J6 j6sqrt(const J6& a) { return jsqrt(
 // ------------------------------------------------------------------------------------------
 struct Instance {
   Spec sp;
-  const double* p;      // 11
+  const double* p;      // 11 (model 1: 8)
   const double* obs;    // n_obs x 3 : cx, cy, r_uav + r_obs
-  int nw, ng, rows;
+  int nw, ng, rows, nu, nlin, pt;
   // work (valid after eval_point)
   std::vector<double> X;        // (N+1) x 8
   std::vector<double> Sx;       // (N+1) x 8 x nw  sensitivities dX_k/dw
@@ -169,18 +177,26 @@ struct Instance {
 
   // optional per-stage predicted target [N][2] (the reference keeps (x_t, y_t) = p[8:10] over the horizon)
   const double* tgt = nullptr;
-  double xt(int k) const { return tgt ? tgt[2 * k] : p[8]; }
-  double yt(int k) const { return tgt ? tgt[2 * k + 1] : p[9]; }
+  double xt(int k) const { return tgt ? tgt[2 * k] : p[pt]; }
+  double yt(int k) const { return tgt ? tgt[2 * k + 1] : p[pt + 1]; }
 
   Instance(const Spec& s, const double* p_, const double* obs_) : sp(s), p(p_), obs(obs_) {
-    nw = sp.nw(); ng = sp.ng(); rows = sp.rows();
+    nw = sp.nw(); ng = sp.ng(); rows = sp.rows(); nu = sp.nu(); nlin = sp.nlin(); pt = sp.model ? 5 : 8;
     X.resize((sp.N + 1) * NX);
+  }
+  // stage cost: model 0 = NMPC_TT.py:209-220, model 1 = MATLAB/Dynamic Obstacles/NMPC_TT.m:100-104 (distance only, no weights)
+  template <class S>
+  S cost_at(const S& x, const S& y, const S& z, const S& X5, const S& X6, const S& X7, int k,
+            S (*Tan)(const S&), S (*Sin)(const S&), S (*Cos)(const S&), S (*Sqrt)(const S&), S (*Sq)(const S&)) const {
+    if (sp.model) return Sqrt(Sq(x - xt(k)) + Sq(y - yt(k)));
+    return stage_cost_literal<S>(sp, x, y, z, X5, X6, X7, xt(k), yt(k), Tan, Sin, Cos, Sqrt, Sq);
   }
 
   void rollout(const double* w) {
-    for (int i = 0; i < NX; ++i) X[i] = p[i];
+    for (int i = 0; i < NX; ++i) X[i] = i < (sp.model ? 5 : NX) ? p[i] : 0.0;
     for (int k = 0; k < sp.N; ++k) {
-      const double* st = &X[k * NX]; const double* u = w + NU * k; double* nx = &X[(k + 1) * NX];
+      const double* st = &X[k * NX]; double u[NU] = {0, 0, 0, 0, 0, 0}; double* nx = &X[(k + 1) * NX];
+      for (int i = 0; i < nu; ++i) u[i] = w[nu * k + i];
       double th = st[3], ps = st[4], v = u[0];
       nx[0] = st[0] + sp.T * (v * std::cos(ps) * std::cos(th));
       nx[1] = st[1] + sp.T * (v * std::sin(ps) * std::cos(th));
@@ -198,14 +214,15 @@ struct Instance {
     double f = 0;
     for (int k = 0; k < sp.N; ++k) {
       const double* st = &X[k * NX];
-      f += stage_cost_literal<D>(sp, st[0], st[1], st[2], st[5], st[6], st[7], xt(k), yt(k), dtan, dsin, dcos, dsqrt, dsq).v;
+      f += cost_at<D>(st[0], st[1], st[2], st[5], st[6], st[7], k, dtan, dsin, dcos, dsqrt, dsq).v;
     }
     for (int k = 0; k <= sp.N; ++k) {
       const double* st = &X[k * NX]; double* gk = g + k * rows;
-      gk[0] = st[2]; gk[1] = st[3]; gk[2] = st[5]; gk[3] = st[6]; gk[4] = st[7];
+      static const int LIN[5] = {2, 3, 5, 6, 7};
+      for (int i = 0; i < nlin; ++i) gk[i] = st[LIN[i]];
       for (int j = 0; j < sp.n_obs; ++j) {
         double dx = st[0] - obs[3 * j], dy = st[1] - obs[3 * j + 1];
-        gk[5 + j] = -std::sqrt(dx * dx + dy * dy) + obs[3 * j + 2];
+        gk[nlin + j] = -std::sqrt(dx * dx + dy * dy) + obs[3 * j + 2];
       }
     }
     return f;
@@ -219,8 +236,8 @@ struct Instance {
       const double* st = &X[k * NX];
       J6 v[6];
       for (int i = 0; i < 6; ++i) v[i] = J6::var(st[COST_IDX[i]], i);
-      cost[k] = stage_cost_literal<J6>(sp, v[0], v[1], v[2], v[3], v[4], v[5], xt(k), yt(k), j6tan, j6sin, j6cos, j6sqrt, j6sq);
-      Jet<3> th = Jet<3>::var(st[3], 0), ps = Jet<3>::var(st[4], 1), vv = Jet<3>::var(w[NU * k], 2);
+      cost[k] = cost_at<J6>(v[0], v[1], v[2], v[3], v[4], v[5], k, j6tan, j6sin, j6cos, j6sqrt, j6sq);
+      Jet<3> th = Jet<3>::var(st[3], 0), ps = Jet<3>::var(st[4], 1), vv = Jet<3>::var(w[nu * k], 2);
       dyn[k * 3 + 0] = sp.T * (vv * jcos(ps) * jcos(th));
       dyn[k * 3 + 1] = sp.T * (vv * jsin(ps) * jcos(th));
       dyn[k * 3 + 2] = sp.T * (vv * jsin(th));
@@ -236,14 +253,14 @@ struct Instance {
     Sx.assign((size_t)(N + 1) * NX * nw, 0.0);
     for (int k = 0; k < N; ++k) {
       const double* S0 = &Sx[(size_t)k * NX * nw]; double* S1 = &Sx[(size_t)(k + 1) * NX * nw];
-      for (int c = 0; c < NU * k; ++c) {   // only columns of earlier stages are non-zero
+      for (int c = 0; c < nu * k; ++c) {   // only columns of earlier stages are non-zero
         for (int r = 0; r < NX; ++r) S1[r * nw + c] = S0[r * nw + c];
         for (int r = 0; r < 3; ++r)
           S1[r * nw + c] += dyn[k * 3 + r].g[0] * S0[3 * nw + c] + dyn[k * 3 + r].g[1] * S0[4 * nw + c];
       }
-      int c0 = NU * k;
+      int c0 = nu * k;
       for (int r = 0; r < 3; ++r) S1[r * nw + c0] = dyn[k * 3 + r].g[2];
-      for (int i = 1; i < NU; ++i) S1[(2 + i) * nw + c0 + i] = sp.T;   // rows 3..7 <- controls 1..5
+      for (int i = 1; i < nu; ++i) S1[(2 + i) * nw + c0 + i] = sp.T;   // rows 3..7 <- controls 1..5
     }
   }
   void grad_f(double* grad) const {
@@ -252,7 +269,7 @@ struct Instance {
       const double* S = &Sx[(size_t)k * NX * nw];
       for (int i = 0; i < 6; ++i) {
         double gi = cost[k].g[i]; const double* row = S + COST_IDX[i] * nw;
-        for (int c = 0; c < NU * k; ++c) grad[c] += gi * row[c];
+        for (int c = 0; c < nu * k; ++c) grad[c] += gi * row[c];
       }
     }
   }
@@ -262,13 +279,13 @@ struct Instance {
     static const int LIN[5] = {2, 3, 5, 6, 7};
     for (int k = 1; k <= sp.N; ++k) {
       const double* S = &Sx[(size_t)k * NX * nw];
-      for (int i = 0; i < 5; ++i) {
+      for (int i = 0; i < nlin; ++i) {
         double* Jr = J + (size_t)(k * rows + i) * nw; const double* row = S + LIN[i] * nw;
-        for (int c = 0; c < NU * k; ++c) Jr[c] = row[c];
+        for (int c = 0; c < nu * k; ++c) Jr[c] = row[c];
       }
       for (int j = 0; j < sp.n_obs; ++j) {
-        double* Jr = J + (size_t)(k * rows + 5 + j) * nw; const Jet<2>& o = obsj[k * sp.n_obs + j];
-        for (int c = 0; c < NU * k; ++c) Jr[c] = o.g[0] * S[c] + o.g[1] * S[nw + c];
+        double* Jr = J + (size_t)(k * rows + nlin + j) * nw; const Jet<2>& o = obsj[k * sp.n_obs + j];
+        for (int c = 0; c < nu * k; ++c) Jr[c] = o.g[0] * S[c] + o.g[1] * S[nw + c];
       }
     }
   }
@@ -282,10 +299,10 @@ struct Instance {
     for (int k = N; k >= 1; --k) {
       double* l = &lamx[k * NX];
       if (k < N) for (int i = 0; i < 6; ++i) l[COST_IDX[i]] += sigma * cost[k].g[i];
-      for (int i = 0; i < 5; ++i) l[LIN[i]] += lam[k * rows + i];
+      for (int i = 0; i < nlin; ++i) l[LIN[i]] += lam[k * rows + i];
       for (int j = 0; j < sp.n_obs; ++j) {
-        l[0] += lam[k * rows + 5 + j] * obsj[k * sp.n_obs + j].g[0];
-        l[1] += lam[k * rows + 5 + j] * obsj[k * sp.n_obs + j].g[1];
+        l[0] += lam[k * rows + nlin + j] * obsj[k * sp.n_obs + j].g[0];
+        l[1] += lam[k * rows + nlin + j] * obsj[k * sp.n_obs + j].g[1];
       }
       if (k < N) {   // + A_k^T lamx_{k+1}
         const double* ln = &lamx[(k + 1) * NX];
@@ -301,7 +318,7 @@ struct Instance {
         for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) H[COST_IDX[i]][COST_IDX[j]] += sigma * cost[k].h[i][j];
       if (k >= 1)
         for (int j = 0; j < sp.n_obs; ++j) {
-          const Jet<2>& o = obsj[k * sp.n_obs + j]; double l = lam[k * rows + 5 + j];
+          const Jet<2>& o = obsj[k * sp.n_obs + j]; double l = lam[k * rows + nlin + j];
           for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) H[a][b] += l * o.h[a][b];
         }
       if (k < N) {   // dynamics curvature weighted by the next-stage adjoint; vars (theta=3, psi=4, v=8)
@@ -310,11 +327,11 @@ struct Instance {
         for (int r = 0; r < 3; ++r)
           for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[DI[a]][DI[b]] += ln[r] * dyn[k * 3 + r].h[a][b];
       }
-      int ncol = std::min(nw, NU * (k + 1));   // Z's non-zero columns: controls of stages <= k
+      int ncol = std::min(nw, nu * (k + 1));   // Z's non-zero columns: controls of stages <= k
       std::fill(Z.begin(), Z.end(), 0.0);
       const double* S = &Sx[(size_t)k * NX * nw];
-      for (int r = 0; r < NX; ++r) for (int c = 0; c < NU * k; ++c) Z[(size_t)r * nw + c] = S[(size_t)r * nw + c];
-      if (k < N) for (int i = 0; i < NU; ++i) Z[(size_t)(NX + i) * nw + NU * k + i] = 1.0;
+      for (int r = 0; r < NX; ++r) for (int c = 0; c < nu * k; ++c) Z[(size_t)r * nw + c] = S[(size_t)r * nw + c];
+      if (k < N) for (int i = 0; i < nu; ++i) Z[(size_t)(NX + i) * nw + nu * k + i] = 1.0;
       for (int r = 0; r < 14; ++r) {
         double* hz = &HZ[(size_t)r * nw]; std::fill(hz, hz + ncol, 0.0);
         for (int q = 0; q < 14; ++q) { double h = H[r][q]; if (h == 0.0) continue; const double* zq = &Z[(size_t)q * nw];
@@ -1369,9 +1386,9 @@ void apply_overrides(Options& o) {
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
-struct oracle_spec { double T; int32_t N; int32_t n_obs; double w1, w2, vfov, hfov; };
+struct oracle_spec { double T; int32_t N; int32_t n_obs; double w1, w2, vfov, hfov; int32_t model; };
 
-static Spec to_spec(const oracle_spec* s) { return Spec{s->T, s->N, s->n_obs, s->w1, s->w2, s->vfov, s->hfov}; }
+static Spec to_spec(const oracle_spec* s) { return Spec{s->T, s->N, s->n_obs, s->w1, s->w2, s->vfov, s->hfov, s->model}; }
 
 // function-level evaluation at (w, p): any output pointer may be NULL
 int oracle_eval_traj(const oracle_spec* spec, const double* obs, const double* w, const double* p, const double* tgt,
@@ -1447,7 +1464,7 @@ int oracle_solve_warm(const oracle_spec* spec, int B, const double* p, const dou
     for (;;) {
       int b = next.fetch_add(1); if (b >= B) break;
       const double* ob = obs + (obs_per_instance ? (size_t)b * sp.n_obs * 3 : 0);
-      Instance I(sp, p + (size_t)b * NPAR, ob);
+      Instance I(sp, p + (size_t)b * sp.npar(), ob);
       if (tgt) I.tgt = tgt + (size_t)b * 2 * sp.N;
       Options o; o.scaling = scaling; if (max_iter > 0) o.max_iter = max_iter; if (tol > 0) o.tol = tol;
       apply_overrides(o);
