@@ -201,6 +201,23 @@ int nmpc_set_weights(nmpc_handle* h, const double* dev_weights);
  * nmpc_solve_host / nmpc_eval on this handle (must stay allocated, at least B rows); NULL restores p[8:10]. */
 int nmpc_set_target_trajectory(nmpc_handle* h, const double* dev_targets);
 
+/* NON-REFERENCE fast mode: warm start of the multipliers -- CasADi's lam_x0 / lam_g0 inputs with
+ * ipopt.warm_start_init_point = "yes".  No reference script uses it (they pass neither, NMPC_TT.py:358-365), and it changes
+ * the iterates, so it is OFF unless this call enables it.  dev_lam_x0 [B][n_w], dev_lam_g0 [B][n_g] (sign convention of the
+ * lam_x / lam_g outputs) are read by every subsequent nmpc_solve on this handle; nmpc_solve_and_step additionally
+ * OVERWRITES them with the multipliers of its own solve shifted by one stage (the dual counterpart of the primal warm
+ * start, NMPC_TT.py:20-23).  A NaN in dev_lam_x0[b][0] cold-starts instance b (IPOPT's default multiplier start, mu_init
+ * 0.1); the fused shift stores that marker after a solve that did not converge.  NULL, NULL restores the cold start.
+ * opts NULL or fields <= 0: IPOPT's defaults (1e-3 pushes) and mu_init 1e-4.
+ * Measured (tests/probes/warm_start_probe.py): a re-solve from (x*, lam*) drops from 19 to 6..9 iterations; in the closed
+ * loop the shifted guesses do NOT reduce the iteration count (the active set of the shifted problem differs). */
+typedef struct nmpc_warm_opts {
+  double mu_init;             /* barrier parameter a warm-started solve begins with */
+  double bound_push, bound_frac, slack_bound_push, slack_bound_frac;   /* warm_start_(slack_)bound_push / _frac */
+  double mult_bound_push;     /* warm_start_mult_bound_push */
+} nmpc_warm_opts;
+int nmpc_set_warm_start(nmpc_handle* h, double* dev_lam_x0, double* dev_lam_g0, const nmpc_warm_opts* opts);
+
 /* Test hook: per-iteration log of every instance of subsequent nmpc_solve calls,
  * dev_buf [B][rows][10] = {mu, f, inf_pr, inf_du, delta_w, alpha_pr, alpha_du, ls_trials, step tag (IPOPT's alpha_primal_char),
  * 1 inside the restoration phase}; NULL disables. */

@@ -28,6 +28,12 @@ class NmpcSpec(C.Structure):
                 ("max_batch", C.c_int32), ("fill", C.c_int32), ("model", C.c_int32)]
 
 
+class NmpcWarmOpts(C.Structure):
+    """struct nmpc_warm_opts"""
+    _fields_ = [("mu_init", C.c_double), ("bound_push", C.c_double), ("bound_frac", C.c_double),
+                ("slack_bound_push", C.c_double), ("slack_bound_frac", C.c_double), ("mult_bound_push", C.c_double)]
+
+
 class NmpcStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("factorizations", C.c_int64),
                 ("ls_trials", C.c_int64), ("soc_accepted", C.c_int64), ("resto_calls", C.c_int64), ("resto_iters", C.c_int64),
@@ -35,7 +41,7 @@ class NmpcStats(C.Structure):
 
 
 EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_eval", "nmpc_step",
-           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_set_schedule", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g", "nmpc_n_p",
+           "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_set_schedule", "nmpc_set_warm_start", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g", "nmpc_n_p",
            "nmpc_last_error", "nmpc_version"]
 
 _lib = None
@@ -72,6 +78,8 @@ def lib():
     L.nmpc_set_order.argtypes = [vp, vp]
     L.nmpc_set_weights.argtypes = [vp, vp]
     L.nmpc_set_target_trajectory.argtypes = [vp, vp]
+    if hasattr(L, "nmpc_set_warm_start"):
+        L.nmpc_set_warm_start.argtypes = [vp, vp, vp, C.POINTER(NmpcWarmOpts)]
     if hasattr(L, "nmpc_set_schedule"):      # (absent only in old builds loaded through NMPC_B200_LIB for A/B timing)
         L.nmpc_set_schedule.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_int32]
     L.nmpc_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

@@ -23,8 +23,11 @@ from .scenarios import NP, Scenario
 
 class ClosedLoop:
     def __init__(self, solver: Solver, scenario: Scenario, p0, target_vw=None, device: Optional[str] = None,
-                 phase=None, predict_target: bool = False, obstacles=None, obstacle_vel=None, schedules=None, schedule_of=None):
-        """p0 [B,11] initial [state; target]; target_vw [B,2] constant per-instance target (v, omega) or None to
+                 phase=None, predict_target: bool = False, obstacles=None, obstacle_vel=None, schedules=None, schedule_of=None,
+                 warm_duals: bool = False):
+        """warm_duals (NON-REFERENCE mode, off by default; needs a solver built with ipopt.warm_start_init_point = 'yes'): the
+        multipliers of every solve, shifted by one stage in the fused epilogue, start the next one (nmpc_set_warm_start).
+        p0 [B,11] initial [state; target]; target_vw [B,2] constant per-instance target (v, omega) or None to
         follow scenario.schedule(mpc_iter + phase[b]).  schedules: optional list of schedule functions (mpc_iter ->
         (v, omega)) with schedule_of[b] the one instance b follows (BASELINE config 3 mixes the T and the Plus
         trajectory in one batch); default: the scenario's own.  The schedule lives on the device as a table
@@ -67,6 +70,12 @@ class ClosedLoop:
             self._sched_dev = None if self.sched_of is None else torch.as_tensor(self.sched_of, device=dev)
             solver.set_schedule(self.sched_table, self._sched_dev, self._phase_dev, mpc_iter=0)
         self.last = None
+        self.warm_duals = bool(warm_duals)
+        if self.warm_duals:
+            self.lam_x0 = torch.zeros((self.B, scenario.n_w), dtype=torch.float64, device=dev)
+            self.lam_g0 = torch.zeros((self.B, scenario.n_g), dtype=torch.float64, device=dev)
+            self.lam_x0[:, 0] = float("nan")             # no guess yet: the first solve is a cold start
+            solver.set_warm_start(self.lam_x0, self.lam_g0)
 
     def _schedule_vw(self):
         """(v, omega) of this step into self.vw -- one gather on the device (only the unfused path and the target
@@ -111,6 +120,8 @@ class ClosedLoop:
         the solve and the shift are one launch (nmpc_solve_and_step)."""
         if self._const_vw or self.predict_target or want_g or want_lam:
             self._schedule_vw()
+        if self.warm_duals and (want_g or want_lam):
+            raise ValueError("ClosedLoop: warm_duals needs the fused step (want_g = want_lam = False)")
         if not (want_g or want_lam):
             sol = self.solver.solve_and_step(self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg,
                                              self.vw if self._const_vw else None, self.fov,

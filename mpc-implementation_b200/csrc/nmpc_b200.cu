@@ -227,6 +227,7 @@ struct nmpc_handle {
   // per-call bookkeeping, double-buffered by call parity: the launch of call n resets / produces the buffers of call n+1
   int32_t *d_order[2], *d_keep_iters; int order_cap, prev_B, auto_order, parity, have_order; const int32_t* order_next;
   const double *weights, *tgt;
+  double *ws_lamx, *ws_lamg;       // nmpc_set_warm_start
   double *fuse_p, *fuse_u, *fuse_fov, *fuse_err; const double* fuse_vw;   // set for the duration of nmpc_solve_and_step
   const double* sched_table; const int32_t *sched_id, *sched_phase; int sched_rows, sched_len, sched_iter;   // nmpc_set_schedule
   int* d_counter;                  // [4]: queue counter x2, done counter x2
@@ -380,6 +381,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.step_p = h->fuse_p; A.step_u = h->fuse_u; A.step_vw = h->fuse_vw; A.step_fov = h->fuse_fov; A.step_err = h->fuse_err;
   A.sched_table = h->sched_table; A.sched_id = h->sched_id; A.sched_phase = h->sched_phase; A.sched_len = h->sched_len; A.sched_iter = h->sched_iter;
   A.tgt = h->tgt;
+  A.lam_x0 = h->ws_lamx; A.lam_g0 = h->ws_lamg; A.ws_shift = (h->ws_lamx && h->fuse_p) ? 1 : 0;
   A.weights = h->weights;
   A.align_group = h->align_group; A.align_mid = h->align_mid;
   // fetch order: explicit (nmpc_set_order) > the order the previous call on this handle prepared for the same B > natural
@@ -541,6 +543,21 @@ int nmpc_set_weights(nmpc_handle* h, const double* dev_weights) {
 int nmpc_set_target_trajectory(nmpc_handle* h, const double* dev_targets) {
   if (!h) return fail("nmpc_set_target_trajectory: null handle");
   h->tgt = dev_targets;
+  return 0;
+}
+
+int nmpc_set_warm_start(nmpc_handle* h, double* dev_lam_x0, double* dev_lam_g0, const nmpc_warm_opts* opts) {
+  if (!h) return fail("nmpc_set_warm_start: null handle");
+  if ((dev_lam_x0 == nullptr) != (dev_lam_g0 == nullptr)) return fail("nmpc_set_warm_start: give both multiplier guesses or neither");
+  h->ws_lamx = dev_lam_x0; h->ws_lamg = dev_lam_g0;
+  if (opts) {
+    const Opt d = Opt();
+    auto pick = [](double v, double dflt) { return v > 0.0 ? v : dflt; };
+    h->opt.ws_mu_init = pick(opts->mu_init, d.ws_mu_init);
+    h->opt.ws_bound_push = pick(opts->bound_push, d.ws_bound_push); h->opt.ws_bound_frac = pick(opts->bound_frac, d.ws_bound_frac);
+    h->opt.ws_slack_push = pick(opts->slack_bound_push, d.ws_slack_push); h->opt.ws_slack_frac = pick(opts->slack_bound_frac, d.ws_slack_frac);
+    h->opt.ws_mult_push = pick(opts->mult_bound_push, d.ws_mult_push);
+  }
   return 0;
 }
 

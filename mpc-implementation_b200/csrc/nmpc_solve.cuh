@@ -41,6 +41,9 @@ struct Opt {
   double resto_rho = 1000.0, resto_eta_factor = 1.0, kappa_resto = 0.9;
   double bound_mult_reset_threshold = 1e3;
   double resto_theta_max_fact = 1e8;
+  // NON-REFERENCE warm start of the multipliers (nmpc_set_warm_start; IPOPT's WarmStartIterateInitializer [3P])
+  double ws_mu_init = 1e-4, ws_bound_push = 1e-3, ws_bound_frac = 1e-3, ws_slack_push = 1e-3, ws_slack_frac = 1e-3;
+  double ws_mult_push = 1e-3, ws_mult_init_max = 1e6;
 };
 
 struct SolveArgs {
@@ -55,6 +58,10 @@ struct SolveArgs {
   // fused closed-loop shift (nmpc_solve_and_step): when step_p != NULL the warp that solved instance b also applies
   // shift_timestep to it -- p[b] and u_warm[b] in place, FOV centre, error term -- and no nmpc_step launch is needed
   double *step_p, *step_u; const double* step_vw; double *step_fov, *step_err;
+  // multiplier guesses lam_x0 [B][n_w], lam_g0 [B][n_g] (NULL = IPOPT's cold multiplier start, as every reference script;
+  // a NaN in lam_x0[b][0] cold-starts instance b); with ws_shift the fused closed-loop epilogue overwrites them with
+  // this solve's multipliers shifted by one stage (NaN marker after a failed solve)
+  double *lam_x0, *lam_g0; int ws_shift;
   // target schedule on the device (nmpc_set_schedule): when step_vw == NULL the target's (v, omega) of this step is
   // sched_table[sched_id[b]][min(sched_iter + sched_phase[b], sched_len - 1)]  -- the scripts' `con_t` keyed on mpc_iter
   const double* sched_table; const int32_t *sched_id, *sched_phase; int sched_len, sched_iter;
@@ -347,18 +354,28 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 }
 
 // starting point: push controls and slacks inside their bounds, unit bound multipliers; returns #finite bounds
+// warm (non-reference mode): multipliers from the caller's guesses (unscaled, CasADi's sign convention lam = upper - lower),
+// pushed away from zero, smaller pushes of the primal point (WarmStartIterateInitializer)
 template <class L>
-__device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
+__device__ __noinline__ int ph_start(const SolveArgs& A, int lane, int b_, double df, bool warm) {
   const Prob& pr = A.pr; constexpr int N = L::N;
   const bool act = lane <= N, hasu = lane < N;
+  const double kb1 = warm ? A.o.ws_bound_push : A.o.bound_push, kb2 = warm ? A.o.ws_bound_frac : A.o.bound_frac;
+  const double ks1 = warm ? A.o.ws_slack_push : A.o.bound_push, ks2 = warm ? A.o.ws_slack_frac : A.o.bound_frac;
+  const double zmin = A.o.ws_mult_push, zcap = A.o.ws_mult_init_max;
   double u[6]; int nz = 0; bool bad_lb = false;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     u[i] = act ? LV(LV_U + i) : 0.0;
     if (hasu) {
       const Bnd b = ctl_bounds<L>(A, lane, i);
-      u[i] = push_in(u[i], b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
-      LV(LV_U + i) = u[i]; LV(LV_ZL + i) = b.hl ? 1.0 : 0.0; LV(LV_ZU + i) = b.hu ? 1.0 : 0.0;
+      u[i] = push_in(u[i], b.lo, b.hi, b.hl, b.hu, kb1, kb2);
+      double zl = b.hl ? 1.0 : 0.0, zu = b.hu ? 1.0 : 0.0;
+      if (warm && i < L::NUA) {
+        const double lz = fmin(fmax(A.lam_x0[(size_t)b_ * (L::NUA * N) + L::NUA * lane + i] * df, -zcap), zcap);
+        zl = b.hl ? fmax(-lz, zmin) : 0.0; zu = b.hu ? fmax(lz, zmin) : 0.0;
+      }
+      LV(LV_U + i) = u[i]; LV(LV_ZL + i) = zl; LV(LV_ZU + i) = zu;
       nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
     } else if (act) { LV(LV_ZL + i) = 0.0; LV(LV_ZU + i) = 0.0; }
   }
@@ -368,10 +385,15 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane) {
       const double dc = RW(A_DC, r);
       const double g = __dmul_rn(dc, gu);
       const Bnd b = row_bounds<L>(A, lane, r, dc);
-      const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, A.o.bound_push, A.o.bound_frac);
-      RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = 0.0;
-      RW(A_VU, r) = b.hu ? 1.0 : 0.0; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
-      if (box) { RW(A_VL, r) = b.hl ? 1.0 : 0.0; RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; }
+      const double s = push_in(g, b.lo, b.hi, b.hl, b.hu, ks1, ks2);
+      double y = 0.0, vl = b.hl ? 1.0 : 0.0, vu = b.hu ? 1.0 : 0.0;
+      if (warm) {      // y_d from the caller; v from y_d = v_U - v_L
+        y = fmin(fmax(A.lam_g0[(size_t)b_ * (L::R * L::S) + lane * L::R + r] * df / dc, -zcap), zcap);
+        vl = b.hl ? fmax(-y, zmin) : 0.0; vu = b.hu ? fmax(y, zmin) : 0.0;
+      }
+      RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = y;
+      RW(A_VU, r) = vu; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
+      if (box) { RW(A_VL, r) = vl; RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; }
       else if (b.hl) bad_lb = true;                     // a lower bound on an obstacle row: not this NLP family
       nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
     };
@@ -1040,6 +1062,22 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
       if (lane < N - 1) uw[L::NUA * lane + i] = un;               // drop the first stage ...
       else if (lane == N - 1) uw[L::NUA * lane + i] = u[i];       // ... and repeat the last (:20-23)
     }
+    if (A.ws_shift && A.lam_x0) {     // next step's multiplier guesses: this solve's, one stage on (NaN marker after a failed solve)
+      const double idf = 1.0 / df;
+      double* lx = A.lam_x0 + (size_t)b * nw; double* lg = A.lam_g0 + (size_t)b * ng;
+#pragma unroll
+      for (int i = 0; i < L::NUA; ++i) {
+        const double v = (LV(LV_ZU + i) - LV(LV_ZL + i)) * idf, vn = __shfl_down_sync(FULL, v, 1);
+        if (lane < N - 1) lx[L::NUA * lane + i] = vn; else if (lane == N - 1) lx[L::NUA * lane + i] = v;
+      }
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        const double v = act ? RW(A_Y, r) * RW(A_DC, r) * idf : 0.0, vn = __shfl_down_sync(FULL, v, 1);
+        if (lane < N) lg[lane * R + r] = vn; else if (lane == N) lg[lane * R + r] = v;
+      }
+      __syncwarp();
+      if (lane == 0 && status != NMPC_SOLVE_SUCCEEDED) lx[0] = CUDART_NAN;
+    }
     if (lane == 0) {
       double tv, tw;
       if (A.step_vw) { tv = __ldg(A.step_vw + 2 * (size_t)b); tw = __ldg(A.step_vw + 2 * (size_t)b + 1); }
@@ -1381,21 +1419,24 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     if (o.scaling == 2 && lane <= L::N) { for (int r = 0; r < R; ++r) RW(A_DC, r) = 1.0; }   // debug: objective only
     __syncwarp();
   }
-  const int nzt = ph_start<L>(A, lane);
+  // multiplier guesses for this instance?  (same address for every lane: uniform)
+  const bool warm = A.lam_x0 != nullptr && !isnan(A.lam_x0[(size_t)b * (L::NUA * L::N)]);
+  const double mu0 = warm ? o.ws_mu_init : o.mu_init;
+  const int nzt = ph_start<L>(A, lane, b, df, warm);
   if (nzt < 0) {       // a finite lower bound on an obstacle row (never the case in the reference's NLPs): refused, reported as data
     ph_output<L>(A, b, lane, df, NMPC_INVALID_NUMBER, 0);
     return;
   }
-  alg_init<L>(o.mu_init, o.tau_min, o.tol);
+  alg_init<L>(mu0, o.tau_min, o.tol);
   for (int f = F_NALG + lane; f < F_END; f += 32) AL(f) = 0.0;
   __syncwarp();
-  ph_trial<L, false>(A, lane, 0.0, false, df, o.mu_init, cold);      // barrier pieces and constraint violation of the start
+  ph_trial<L, false>(A, lane, 0.0, false, df, mu0, cold);      // barrier pieces and constraint violation of the start
   take_trial_values<L>();
   const double mu_floor = fmin(o.tol, df * o.compl_inf_tol) / (o.kappa_eps + 1.0);
   int iter = 0, status = NMPC_MAXITER_EXCEEDED;
 
   int mids = -1;
-  {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
+  if (!warm) {   // least-squares multiplier start: (I + J^T J) t = -(grad_x L) - J^T (grad_s L),  y = J t + grad_s L
     align_warps(A.align_group, 1); mids = 0;
     mid_flush<L>(A, mids);
     ph_derivs<L, false>(A, lane, true, df, o.mu_init, 0.0, false, cold);

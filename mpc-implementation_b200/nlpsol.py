@@ -50,6 +50,11 @@ def _spec_from(problem, opts: Optional[dict]) -> Dict[str, Any]:
     d["max_iter"] = int(ip.get("max_iter", 100))          # NMPC_TT.py:259
     d["tol"] = float(ip.get("tol", 1e-8))
     d["scaling"] = 0 if ip.get("nlp_scaling_method", "gradient-based") == "none" else int(ip.get("_scaling_debug_mode", 1))
+    # NON-REFERENCE mode (no script sets it): IPOPT's warm_start_init_point and its pushes; lam_x0 / lam_g0 are ignored without it
+    d["warm"] = str(ip.get("warm_start_init_point", "no")).lower() == "yes"
+    d["warm_opts"] = (float(ip.get("mu_init", 0.0)) if d["warm"] else 0.0, float(ip.get("warm_start_bound_push", 0.0)),
+                      float(ip.get("warm_start_bound_frac", 0.0)), float(ip.get("warm_start_slack_bound_push", 0.0)),
+                      float(ip.get("warm_start_slack_bound_frac", 0.0)), float(ip.get("warm_start_mult_bound_push", 0.0)))
     return d
 
 
@@ -72,6 +77,7 @@ class Solver:
         self._max_batch = 0
         self._dev_cache: Dict[str, Any] = {}
         self._stats: Dict[str, Any] = {}
+        self._warm = None
         self._create(max_batch)
 
     # -- handle management ---------------------------------------------------------------------
@@ -134,8 +140,11 @@ class Solver:
     # -- the call --------------------------------------------------------------------------------
     def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, obstacles=None,
                  want_g: bool = True, want_lam: bool = True, order=None, weights=None, target_traj=None,
-                 blocking: bool = True):
-        """weights: optional [B, 2] per-instance cost weights (w1, w2) for this call (numpy or CUDA tensor); the
+                 blocking: bool = True, lam_x0=None, lam_g0=None):
+        """lam_x0 [B, n_w], lam_g0 [B, n_g]: CasADi's multiplier guesses.  Like IPOPT they are ignored unless the solver was
+        built with opts = {'ipopt': {'warm_start_init_point': 'yes', ...}} (no reference script does: non-reference fast mode,
+        nmpc_set_warm_start); a NaN in lam_x0[b, 0] cold-starts instance b.
+        weights: optional [B, 2] per-instance cost weights (w1, w2) for this call (numpy or CUDA tensor); the
         reference edits them in source (NMPC_TT.py:204-205) and its MATLAB outer loop sweeps them (MPC.m:90).
         target_traj: optional [B, N, 2] predicted target positions per stage (default: p[8:10] for every stage, as
         in the reference).
@@ -146,6 +155,24 @@ class Solver:
             raise ValueError("solver: p is required")
         if any(v is None for v in (lbx, ubx, lbg, ubg)):
             raise ValueError("solver: lbx, ubx, lbg, ubg are required (the reference passes all four)")
+        if self._d["warm"] and lam_x0 is not None and lam_g0 is not None:
+            if not _is_cuda_tensor(p):       # the multiplier guesses live on the device: take the device path, hand numpy back
+                dev = f"cuda:{self.device}"
+                t = lambda a, n: None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev).reshape(-1, n)
+                B = self._batch_of(p)
+                out = self(x0=t(x0, self.n_w), p=t(p, self.n_p), lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, obstacles=obstacles, want_g=want_g,
+                           want_lam=want_lam, order=order, weights=weights, target_traj=target_traj, lam_x0=lam_x0, lam_g0=lam_g0)
+                torch.cuda.synchronize()
+                self._stats = {k: v.cpu().numpy() for k, v in self._stats.items()}
+                return {k: (None if v is None else v.cpu().numpy()) for k, v in out.items()}
+            B = self._batch_of(p)
+            self.set_warm_start(torch.as_tensor(lam_x0, dtype=torch.float64, device=p.device).reshape(B, self.n_w),
+                                torch.as_tensor(lam_g0, dtype=torch.float64, device=p.device).reshape(B, self.n_g))
+            try:
+                return self(x0=x0, p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, obstacles=obstacles, want_g=want_g, want_lam=want_lam,
+                            order=order, weights=weights, target_traj=target_traj)
+            finally:
+                self.set_warm_start(None, None)
         with self._weights(weights, p), self._traj(target_traj, p):
             if _is_cuda_tensor(p):
                 return self._call_device(x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order)
@@ -394,6 +421,24 @@ class Solver:
         self._keep = (obs,)
         self._stats = dict(return_status=status, iter_count=iters)
         return dict(x=x, f=f, g=None, lam_x=None, lam_g=None)
+
+    def set_warm_start(self, lam_x0, lam_g0):
+        """nmpc_set_warm_start: CUDA float64 tensors lam_x0 [B, n_w], lam_g0 [B, n_g] read by the following solves (and
+        overwritten with the shifted multipliers by solve_and_step); None, None restores IPOPT's cold multiplier start.
+        NON-REFERENCE mode; the pushes / mu_init come from the solver's 'ipopt' options."""
+        L = _ffi.lib()
+        if lam_x0 is None:
+            self._warm = None
+            _ffi.check(L.nmpc_set_warm_start(self._h, None, None, None), "nmpc_set_warm_start")
+            return
+        if not (_is_cuda_tensor(lam_x0) and _is_cuda_tensor(lam_g0)) or lam_x0.dtype != torch.float64 or lam_g0.dtype != torch.float64:
+            raise ValueError("solver: lam_x0 / lam_g0 must be CUDA float64 tensors")
+        lam_x0, lam_g0 = lam_x0.contiguous(), lam_g0.contiguous()
+        if lam_x0.numel() % self.n_w or lam_g0.numel() % self.n_g or lam_x0.numel() // self.n_w != lam_g0.numel() // self.n_g:
+            raise ValueError("solver: lam_x0 must be [B, n_w] and lam_g0 [B, n_g]")
+        self._warm = (lam_x0, lam_g0)        # owned here: the handle keeps raw pointers
+        o = _ffi.NmpcWarmOpts(*self._d["warm_opts"])
+        _ffi.check(L.nmpc_set_warm_start(self._h, lam_x0.data_ptr(), lam_g0.data_ptr(), C.byref(o)), "nmpc_set_warm_start")
 
     def set_schedule(self, table, row_of_instance=None, phase=None, mpc_iter: int = 0):
         """Device-side target schedule (nmpc_set_schedule): table [n_rows, len, 2] of (v, omega) per closed-loop step;

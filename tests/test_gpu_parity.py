@@ -693,3 +693,91 @@ def test_edge_cases(pkg):
     pb, _ = pkg.random_instances(sc, 9, 1)
     out = s(x0=np.zeros((9, sc.n_w)), p=pb, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
     assert out["x"].shape == (9, sc.n_w)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# NON-REFERENCE fast mode: multiplier / mu warm start.  Off by default; parity against the oracle's restatement of
+# IPOPT's WarmStartIterateInitializer.
+# ------------------------------------------------------------------------------------------------------------------
+WARM_OPTS = {"ipopt": {"max_iter": 100, "warm_start_init_point": "yes", "mu_init": 1e-4}}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["t_trajectory", "race_track_2", "gimbal_less"])
+def test_warm_start_parity(pkg, oracle_mod, name):
+    """Re-solve from the primal-dual solution: the kernel follows the oracle's warm-started iterates (same statuses and iteration
+    counts, same solutions), takes far fewer iterations than the cold start, and a NaN marker cold-starts an instance bit for
+    bit like a call without guesses.  Without warm_start_init_point the guesses are ignored, as in IPOPT."""
+    sc = pkg.SCENARIOS[name]
+    B = 96
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, _ = pkg.random_instances(sc, B, seed=31)
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov, sc.model)
+    obs = sc.obstacle_table()
+    r0 = oracle_mod.solve(sp, obs, p, np.zeros((B, sc.n_w)), lbx, ubx, lbg, ubg)
+    lx = r0["lam_x"].copy(); lx[::4, 0] = np.nan
+    oracle_mod.set_option("ws_mu_init", 1e-4)
+    try:
+        ref = oracle_mod.solve(sp, obs, p, r0["x"], lbx, ubx, lbg, ubg, lam_x0=lx, lam_g0=r0["lam_g"])
+    finally:
+        oracle_mod.clear_options()
+    s = pkg.nlpsol("w", "ipm", sc, WARM_OPTS, max_batch=B)
+    sol = s(x0=r0["x"], p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, lam_x0=lx, lam_g0=r0["lam_g"])
+    st = s.stats()
+    assert (st["return_status"] == ref["status"]).mean() >= 0.97
+    both = (st["return_status"] == 0) & (ref["status"] == 0)
+    assert both.mean() > 0.85
+    assert (st["iter_count"][both] == ref["iters"][both]).mean() >= 0.95
+    rf = np.abs(sol["f"].ravel() - ref["f"])[both] / np.maximum(1.0, np.abs(ref["f"][both]))
+    assert rf.max() <= F_RTOL
+    ru = np.abs(sol["x"][both, :sc.nu] - ref["x"][both, :sc.nu]).max(axis=1) / np.abs(ref["x"][both, :sc.nu]).max(axis=1)
+    assert np.mean(ru <= U0_RTOL) >= 0.97 and ru.max() <= 1e-3
+    # cold reference on the same starts
+    c = pkg.nlpsol("c", "ipm", sc, max_batch=B)
+    cold = c(x0=r0["x"], p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg, lam_x0=lx, lam_g0=r0["lam_g"])      # guesses ignored: not enabled
+    cst = c.stats()
+    cold2 = c(x0=r0["x"], p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    assert np.array_equal(cold["x"], cold2["x"]) and np.array_equal(cst["iter_count"], c.stats()["iter_count"])
+    assert np.array_equal(sol["x"][::4], cold["x"][::4]) and np.array_equal(st["iter_count"][::4], cst["iter_count"][::4])
+    w = both.copy(); w[::4] = False
+    assert st["iter_count"][w].mean() < 0.7 * cst["iter_count"][w].mean()
+
+
+@pytest.mark.gpu
+def test_warm_duals_closed_loop(pkg, oracle_mod):
+    """The fused epilogue's dual shift: ClosedLoop(warm_duals=True) against the oracle driven with the same shift on the host."""
+    import torch
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    sc = pkg.SCENARIOS["t_trajectory"]
+    B, K = 64, 6
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p0, vw = pkg.random_instances(sc, B, seed=41)
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    obs = sc.obstacle_table()
+    cl = ClosedLoop(pkg.nlpsol("w", "ipm", sc, WARM_OPTS, max_batch=B), sc, p0, target_vw=vw, warm_duals=True)
+    R = 5 + sc.n_obs
+    p = p0.copy(); u = np.zeros((B, sc.n_w)); lx = np.zeros((B, sc.n_w)); lg = np.zeros((B, sc.n_g)); lx[:, 0] = np.nan
+    oracle_mod.set_option("ws_mu_init", 1e-4)
+    try:
+        for k in range(K):
+            cl.step()
+            stg = cl.solver.stats()
+            r = oracle_mod.solve(sp, obs, p, u, lbx, ubx, lbg, ubg, lam_x0=lx, lam_g0=lg)
+            gs, gi = stg["return_status"].cpu().numpy(), stg["iter_count"].cpu().numpy()
+            assert (gs == r["status"]).mean() >= 0.95, k
+            same = (gs == 0) & (r["status"] == 0)
+            assert (gi[same] == r["iters"][same]).mean() >= 0.9, k
+            # teacher forcing: the oracle continues from the GPU's iterate so that single flips do not compound
+            x = cl.last["x"].cpu().numpy()
+            assert np.abs(x[same] - r["x"][same]).max() <= 1e-4
+            ok = gs == 0
+            lx = cl.lam_x0.cpu().numpy().copy(); lg = cl.lam_g0.cpu().numpy().copy()
+            assert np.array_equal(np.isnan(lx[:, 0]), ~ok)                     # marker after a failed solve
+            # the shifted multipliers are this solve's own (compare with the oracle's where both converged)
+            ex = np.concatenate([r["lam_x"].reshape(B, sc.N, 6)[:, 1:], r["lam_x"].reshape(B, sc.N, 6)[:, -1:]], 1).reshape(B, -1)
+            eg = np.concatenate([r["lam_g"].reshape(B, sc.N + 1, R)[:, 1:], r["lam_g"].reshape(B, sc.N + 1, R)[:, -1:]], 1).reshape(B, -1)
+            assert np.abs(lx[same][:, 1:] - ex[same][:, 1:]).max() <= 1e-5 * max(1.0, np.abs(ex[same]).max())
+            assert np.abs(lg[same] - eg[same]).max() <= 1e-5 * max(1.0, np.abs(eg[same]).max())
+            p = cl.p.cpu().numpy().copy(); u = cl.u_warm.cpu().numpy().copy()
+    finally:
+        oracle_mod.clear_options()

@@ -39,7 +39,7 @@ def test_scenario_constants(pkg):
     assert np.allclose(S["10_obstacles"].obstacle_table()[0], [500, 20, 105])
     for name, sc in S.items():
         rs = nlp_ref.RefSpec(T=sc.T, N=sc.N, obstacles=sc.obstacles)
-        for a, b in zip(sc.bounds(), nlp_ref.bounds(rs)):
+        for a, b in zip(sc.bounds(), nlp_ref.bounds5(nlp_ref.RefSpec5(sc.T, sc.N)) if sc.model else nlp_ref.bounds(rs)):
             assert np.array_equal(a, b), name
 
 
@@ -65,8 +65,8 @@ def test_no_cpu_fallback(pkg):
 def test_spec_struct_layout_matches_header(pkg):
     """ctypes mirror of struct nmpc_spec has the field order / size the C header implies."""
     f = [n for n, _ in pkg._ffi.NmpcSpec._fields_]
-    assert f == ["T", "N", "n_obs", "w1", "w2", "vfov", "hfov", "max_iter", "scaling", "tol", "max_batch", "fill"]
-    assert ctypes.sizeof(pkg._ffi.NmpcSpec) == 72
+    assert f == ["T", "N", "n_obs", "w1", "w2", "vfov", "hfov", "max_iter", "scaling", "tol", "max_batch", "fill", "model"]
+    assert ctypes.sizeof(pkg._ffi.NmpcSpec) == 80
 
 
 def test_random_instances_are_seeded_and_feasible(pkg):
