@@ -157,6 +157,23 @@ int nmpc_solve_and_step(nmpc_handle* h, int32_t B, double* p, double* u_warm,
                         double* x, double* f, double* fov_centre, double* err_accum,
                         int32_t* status, int32_t* iters, void* cuda_stream);
 
+/* The scripts' main loop `while mpc_iter < sim_time / T` (NMPC_TT.py:346-402) on the device: every one of the B instances
+ * advances `steps` closed-loop steps (solve :358-365 + shift_timestep :382 + FOV centre / error :399-402, :435) in ONE launch.
+ * The closed loops are independent, so there is no batch-wide barrier between the steps: the warp that has finished step k of
+ * an instance goes straight on with its step k + 1 (the epilogue has written p and the warm start in place), and the SMs never
+ * wait for the slowest solve of a step.  Per instance the arithmetic is exactly that of `steps` consecutive
+ * nmpc_solve_and_step calls -- results are bit-identical (tests) -- only the schedule differs.
+ *   p [B][n_p], u_warm [B][n_w] in/out;  target_vw [B][2] constant per instance, or NULL with nmpc_set_schedule (the table is read
+ *   at mpc_iter, mpc_iter + 1, ...; the step counter advances by `steps`)
+ *   x [B][n_w], f [B]: solution of the LAST step (may be NULL);  fov_centre [B][2], err_accum [B] (+=) as in nmpc_step
+ *   status_log, iters_log [steps][B]: outcome of every solve (may be NULL);  converged [B]: += number of converged solves (may be NULL)
+ * Not available with a per-step target prediction (nmpc_set_target_trajectory), which the host recomputes every step. */
+int nmpc_run_closed_loop(nmpc_handle* h, int32_t B, int32_t steps, double* p, double* u_warm,
+                         const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                         const double* obst, uint32_t flags, const double* target_vw,
+                         double* x, double* f, double* fov_centre, double* err_accum,
+                         int32_t* status_log, int32_t* iters_log, int32_t* converged, void* cuda_stream);
+
 /* Target schedule on the device.  The reference's shift_timestep reads the target's (v, omega) for this step from an
  * if-chain keyed on the global step counter (`con_t`, T_Trajectory.py:24-57, Plus Trajectory.py:25-69, Race Track 2.py:28-36).
  * dev_table [n_rows][len][2] holds (v, omega) per step for n_rows schedules (a step index beyond len - 1 uses the last

@@ -143,6 +143,18 @@ class ClosedLoop:
         self.last = sol
         return sol
 
+    def run_free(self, steps: int, log: bool = True, want_x: bool = False):
+        """`steps` closed-loop steps of every instance in one launch with no batch-wide barrier between the steps
+        (Solver.run_closed_loop): the fast way through a Monte-Carlo study; per instance bit-identical to step() x steps."""
+        if self.predict_target or self.obstacle_vel is not None:
+            raise ValueError("ClosedLoop.run_free: target predictions / moving obstacles are recomputed on the host every step; use step()")
+        out = self.solver.run_closed_loop(steps, self.p, self.u_warm, self.lbx, self.ubx, self.lbg, self.ubg,
+                                          self.vw if self._const_vw else None, self.fov, self.err_sum, obstacles=self.obstacles,
+                                          want_x=want_x, log=log)
+        self.mpc_iter += steps
+        self.last = out
+        return out
+
     def run(self, steps: int):
         conv = 0
         for _ in range(steps):

@@ -228,6 +228,7 @@ struct nmpc_handle {
   int32_t *d_order[2], *d_keep_iters; int order_cap, prev_B, auto_order, parity, have_order; const int32_t* order_next;
   const double *weights, *tgt;
   double *ws_lamx, *ws_lamg;       // nmpc_set_warm_start
+  int run_steps; int32_t *run_status_log, *run_iters_log, *run_conv;   // set for the duration of nmpc_run_closed_loop
   double *fuse_p, *fuse_u, *fuse_fov, *fuse_err; const double* fuse_vw;   // set for the duration of nmpc_solve_and_step
   const double* sched_table; const int32_t *sched_id, *sched_phase; int sched_rows, sched_len, sched_iter;   // nmpc_set_schedule
   int* d_counter;                  // [4]: queue counter x2, done counter x2
@@ -382,6 +383,7 @@ int nmpc_solve(nmpc_handle* h, int32_t B, const double* p, const double* x0,
   A.sched_table = h->sched_table; A.sched_id = h->sched_id; A.sched_phase = h->sched_phase; A.sched_len = h->sched_len; A.sched_iter = h->sched_iter;
   A.tgt = h->tgt;
   A.lam_x0 = h->ws_lamx; A.lam_g0 = h->ws_lamg; A.ws_shift = (h->ws_lamx && h->fuse_p) ? 1 : 0;
+  A.run_steps = h->run_steps > 1 ? h->run_steps : 1; A.status_log = h->run_status_log; A.iters_log = h->run_iters_log; A.conv_count = h->run_conv;
   A.weights = h->weights;
   A.align_group = h->align_group; A.align_mid = h->align_mid;
   // fetch order: explicit (nmpc_set_order) > the order the previous call on this handle prepared for the same B > natural
@@ -432,6 +434,23 @@ int nmpc_solve_and_step(nmpc_handle* h, int32_t B, double* p, double* u_warm,
   const int rc = nmpc_solve(h, B, p, u_warm, lbx, ubx, lbg, ubg, obst, flags, x, f, nullptr, nullptr, nullptr, status, iters, cuda_stream);
   h->fuse_p = nullptr; h->fuse_u = nullptr; h->fuse_vw = nullptr; h->fuse_fov = nullptr; h->fuse_err = nullptr;
   if (rc == 0 && !target_vw) ++h->sched_iter;        // the schedule is keyed on the number of closed-loop steps taken (mpc_iter)
+  return rc;
+}
+
+int nmpc_run_closed_loop(nmpc_handle* h, int32_t B, int32_t steps, double* p, double* u_warm,
+                         const double* lbx, const double* ubx, const double* lbg, const double* ubg,
+                         const double* obst, uint32_t flags, const double* target_vw,
+                         double* x, double* f, double* fov_centre, double* err_accum,
+                         int32_t* status_log, int32_t* iters_log, int32_t* converged, void* cuda_stream) {
+  if (!h) return fail("nmpc_run_closed_loop: null handle");
+  if (steps < 1) return fail("nmpc_run_closed_loop: steps must be >= 1");
+  if (h->tgt) return fail("nmpc_run_closed_loop: a per-step target prediction (nmpc_set_target_trajectory) needs the step-by-step calls");
+  h->run_steps = steps; h->run_status_log = status_log; h->run_iters_log = iters_log; h->run_conv = converged;
+  const int sched0 = h->sched_iter;
+  const int rc = nmpc_solve_and_step(h, B, p, u_warm, lbx, ubx, lbg, ubg, obst, flags, target_vw, x, f, fov_centre, err_accum,
+                                     nullptr, nullptr, cuda_stream);
+  h->run_steps = 0; h->run_status_log = nullptr; h->run_iters_log = nullptr; h->run_conv = nullptr;
+  if (rc == 0 && !target_vw) h->sched_iter = sched0 + steps;
   return rc;
 }
 

@@ -62,6 +62,9 @@ struct SolveArgs {
   // a NaN in lam_x0[b][0] cold-starts instance b); with ws_shift the fused closed-loop epilogue overwrites them with
   // this solve's multipliers shifted by one stage (NaN marker after a failed solve)
   double *lam_x0, *lam_g0; int ws_shift;
+  // free-running closed loop (nmpc_run_closed_loop): every instance advances run_steps closed-loop steps back to back in the
+  // warp that fetched it; optional per-step logs [run_steps][B], per-instance count of converged solves
+  int run_steps; int32_t *status_log, *iters_log, *conv_count;
   // target schedule on the device (nmpc_set_schedule): when step_vw == NULL the target's (v, omega) of this step is
   // sched_table[sched_id[b]][min(sched_iter + sched_phase[b], sched_len - 1)]  -- the scripts' `con_t` keyed on mpc_iter
   const double* sched_table; const int32_t *sched_id, *sched_phase; int sched_len, sched_iter;
@@ -266,8 +269,8 @@ __device__ __forceinline__ RestoRow resto_row(const SolveArgs& A, const double* 
 template <class L>
 __device__ __noinline__ void ph_load(const SolveArgs& A, int b, int lane) {
   if (L::MODEL) {      // p = [state(5); target(3)]: the camera states are zero
-    if (lane < NPAR) PAR(lane) = lane < 5 ? A.p[(size_t)b * L::NPA + lane] : (lane < 8 ? 0.0 : A.p[(size_t)b * L::NPA + lane - 3]);
-  } else if (lane < NPAR) PAR(lane) = A.p[(size_t)b * NPAR + lane];
+    if (lane < NPAR) PAR(lane) = lane < 5 ? __ldcg(A.p + (size_t)b * L::NPA + lane) : (lane < 8 ? 0.0 : __ldcg(A.p + (size_t)b * L::NPA + lane - 3));
+  } else if (lane < NPAR) PAR(lane) = __ldcg(A.p + (size_t)b * NPAR + lane);      // (L2 path: a free-running call re-reads what its own epilogue wrote)
   if (lane == NPAR) PAR(NPAR) = A.weights ? A.weights[2 * (size_t)b] : A.pr.w1;
   if (lane == NPAR + 1) PAR(NPAR + 1) = A.weights ? A.weights[2 * (size_t)b + 1] : A.pr.w2;
   if (lane == NPAR + 2) PAR(NPAR + 2) = (double)b;      // instance index, for the per-stage target lookup
@@ -1010,7 +1013,7 @@ __device__ __noinline__ void ph_unit_mults(const SolveArgs& A, int lane) {
 
 // outputs: honour the original bounds, unscale multipliers, f and g at the returned point
 template <class L>
-__device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, double df, int status, int iter) {
+__device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, double df, int status, int iter, int step) {
   const Prob& pr = A.pr; constexpr int N = L::N, R = L::R, S = L::S;
   const bool act = lane <= N, hasu = lane < N;
   constexpr int nw = L::NUA * N, ng = R * S;
@@ -1039,7 +1042,13 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
     if (A.f) A.f[b] = fu;
     if (A.status) A.status[b] = status;
     if (A.iters) A.iters[b] = iter;
-    if (A.iters_keep) A.iters_keep[b] = iter;
+    if (A.iters_keep) {      // drives the next call's longest-first order: the mean over the steps of a free-running call
+      const int acc = (step == 0 ? 0 : A.iters_keep[b]) + iter;
+      A.iters_keep[b] = (A.run_steps > 1 && step == A.run_steps - 1) ? acc / A.run_steps : acc;
+    }
+    if (A.status_log) A.status_log[(size_t)step * A.B + b] = status;
+    if (A.iters_log) A.iters_log[(size_t)step * A.B + b] = iter;
+    if (A.conv_count && status == NMPC_SOLVE_SUCCEEDED) A.conv_count[b] += 1;
   }
   if (act) {
     if (A.g) {
@@ -1083,7 +1092,7 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
       if (A.step_vw) { tv = __ldg(A.step_vw + 2 * (size_t)b); tw = __ldg(A.step_vw + 2 * (size_t)b + 1); }
       else {
         const int row = A.sched_id ? __ldg(A.sched_id + b) : 0, ph = A.sched_phase ? __ldg(A.sched_phase + b) : 0;
-        const int at = min(A.sched_iter + ph, A.sched_len - 1);
+        const int at = min(A.sched_iter + step + ph, A.sched_len - 1);
         const double* e = A.sched_table + ((size_t)row * A.sched_len + at) * 2;
         tv = __ldg(e); tw = __ldg(e + 1);
       }
@@ -1404,7 +1413,7 @@ __device__ __noinline__ bool update_mu(const SolveArgs& A, double* cold, int lan
 }
 
 template <class L>
-__device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, double* cold, int b, int lane) {
+__device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, double* cold, int b, int lane, int step) {
   const Prob& pr = A.pr; const Opt& o = A.o;
   constexpr int S = L::S, R = L::R;
   constexpr int DX0 = L::LV0 + LV_DX * S, DU0 = L::LV0 + LV_DU * S, DUS0 = L::soc(SOC_DUS), Q20 = L::soc(SOC_Q2);
@@ -1424,7 +1433,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
   const double mu0 = warm ? o.ws_mu_init : o.mu_init;
   const int nzt = ph_start<L>(A, lane, b, df, warm);
   if (nzt < 0) {       // a finite lower bound on an obstacle row (never the case in the reference's NLPs): refused, reported as data
-    ph_output<L>(A, b, lane, df, NMPC_INVALID_NUMBER, 0);
+    ph_output<L>(A, b, lane, df, NMPC_INVALID_NUMBER, 0, step);
     return;
   }
   alg_init<L>(mu0, o.tau_min, o.tol);
@@ -1634,7 +1643,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
     ++iter;
   }
   mid_flush<L>(A, mids);
-  ph_output<L>(A, b, lane, df, status, iter);
+  ph_output<L>(A, b, lane, df, status, iter, step);
   if (lane == 0 && A.stats) {
 #pragma unroll
     for (int c = 0; c < NSTAT; ++c) atomicAdd(&A.stats[c], (unsigned long long)AL(F_C0 + c));
@@ -1679,7 +1688,9 @@ __global__ void __launch_bounds__(32 * Lay<N_, NOBS_, MODEL_>::WPB, 1) nmpc_ipm_
     q = __shfl_sync(FULL, q, 0);
     if (q >= A.B) break;
     const int b = A.order ? A.order[q] : q;
-    solve_instance<L>(A, ric, cold, b, lane);
+    // free-running closed loop: the steps of one instance follow each other here (the epilogue of step k has written p and the
+    // warm start of step k + 1 in place), with no batch-wide barrier between the steps
+    for (int step = 0; step < A.run_steps; ++step) { solve_instance<L>(A, ric, cold, b, lane, step); __syncwarp(); }
     __syncwarp();
     int fin = 0;
     if (lane == 0) { __threadfence(); fin = atomicAdd(A.done, 1); }      // this instance's outputs are visible before the count

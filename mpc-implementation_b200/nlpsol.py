@@ -422,6 +422,39 @@ class Solver:
         self._stats = dict(return_status=status, iter_count=iters)
         return dict(x=x, f=f, g=None, lam_x=None, lam_g=None)
 
+    def run_closed_loop(self, steps: int, p, u_warm, lbx, ubx, lbg, ubg, target_vw, fov_centre=None, err_accum=None,
+                        obstacles=None, want_x: bool = False, log: bool = True):
+        """`steps` closed-loop steps of every instance in ONE launch, without a batch-wide barrier between the steps
+        (nmpc_run_closed_loop; the scripts' `while mpc_iter < sim_time / T` loop, NMPC_TT.py:346-402).  p / u_warm are advanced in
+        place.  Returns dict(x, f of the last step, status_log / iters_log [steps, B] when log, converged [B] = number of
+        converged solves per instance); stats() reports the last step.  Bit-identical to `steps` solve_and_step calls."""
+        L = _ffi.lib()
+        dev = p.device
+        B = p.shape[0]
+        lbx, ubx = self._dev_const("lbx", lbx), self._dev_const("ubx", ubx)
+        lbg, ubg = self._dev_const("lbg", lbg), self._dev_const("ubg", ubg)
+        flags = 0
+        if obstacles is None:
+            obs = self._dev_const("obs", self.obstacles)
+        else:
+            obs = obstacles.to(torch.float64).contiguous()
+            flags = _ffi.NMPC_OBS_PER_INSTANCE if obs.numel() == 3 * self.n_obs * B and B > 1 else 0
+        if target_vw is None and getattr(self, "_sched", None) is None:
+            raise ValueError("solver: target_vw is None and no schedule is set (set_schedule)")
+        x = torch.empty((B, self.n_w), dtype=torch.float64, device=dev) if want_x else None
+        f = torch.empty(B, dtype=torch.float64, device=dev)
+        slog = torch.empty((steps, B), dtype=torch.int32, device=dev) if log else None
+        ilog = torch.empty((steps, B), dtype=torch.int32, device=dev) if log else None
+        conv = torch.zeros(B, dtype=torch.int32, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _ffi.check(L.nmpc_run_closed_loop(self._h, B, int(steps), ptr(p), ptr(u_warm), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
+                                          ptr(target_vw), ptr(x), ptr(f), ptr(fov_centre), ptr(err_accum), ptr(slog), ptr(ilog), ptr(conv),
+                                          stream), "nmpc_run_closed_loop")
+        self._keep = (obs,)
+        self._stats = dict(return_status=slog[-1], iter_count=ilog[-1]) if log else {}
+        return dict(x=x, f=f, status_log=slog, iters_log=ilog, converged=conv)
+
     def set_warm_start(self, lam_x0, lam_g0):
         """nmpc_set_warm_start: CUDA float64 tensors lam_x0 [B, n_w], lam_g0 [B, n_g] read by the following solves (and
         overwritten with the shifted multipliers by solve_and_step); None, None restores IPOPT's cold multiplier start.

@@ -781,3 +781,35 @@ def test_warm_duals_closed_loop(pkg, oracle_mod):
             p = cl.p.cpu().numpy().copy(); u = cl.u_warm.cpu().numpy().copy()
     finally:
         oracle_mod.clear_options()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# free-running closed loop (nmpc_run_closed_loop): K steps of every instance in one launch, no batch-wide barrier between steps
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,N,B,K,phases", [("nmpc_tt", 15, 300, 7, False), ("t_trajectory", 15, 257, 9, True), ("race_track_2", 30, 96, 4, False),
+                                               ("10_obstacles", 15, 64, 5, False), ("gimbal_less", 15, 200, 6, False)])
+def test_free_running_loop_is_the_same_loop(pkg, name, N, B, K, phases):
+    """Bit-identical to K consecutive nmpc_solve_and_step calls: states, warm starts, error sums, and the status / iteration count
+    of every solve -- with a constant per-instance target input and with the device schedule (+ per-instance phases)."""
+    import torch
+    from mpc_implementation_b200.closed_loop import ClosedLoop
+    sc = pkg.SCENARIOS[name]
+    if N != sc.N:
+        sc = sc.with_horizon(N)
+    p0, vw = pkg.random_instances(sc, B, seed=17)
+    kw = dict(phase=np.random.default_rng(3).integers(0, 400, B)) if phases else dict(target_vw=vw)
+    a = ClosedLoop(pkg.nlpsol("a", "ipm", sc, max_batch=B), sc, p0, **kw)
+    b = ClosedLoop(pkg.nlpsol("b", "ipm", sc, max_batch=B), sc, p0, **kw)
+    st, it = [], []
+    for k in range(K):
+        a.step(); s = a.solver.stats()
+        st.append(s["return_status"].clone()); it.append(s["iter_count"].clone())
+    out = b.run_free(K)
+    torch.cuda.synchronize()
+    assert torch.equal(a.p, b.p) and torch.equal(a.u_warm, b.u_warm) and torch.equal(a.err_sum, b.err_sum) and torch.equal(a.fov, b.fov)
+    assert torch.equal(torch.stack(st), out["status_log"]) and torch.equal(torch.stack(it), out["iters_log"])
+    assert torch.equal(out["converged"], (torch.stack(st) == 0).sum(dim=0).to(torch.int32))
+    # and the two loops stay interchangeable afterwards (schedule counter, fetch order)
+    a.step(); b.step(); torch.cuda.synchronize()
+    assert torch.equal(a.p, b.p) and torch.equal(a.u_warm, b.u_warm)
