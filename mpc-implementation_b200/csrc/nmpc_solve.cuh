@@ -1672,7 +1672,7 @@ __device__ __noinline__ void next_order(const SolveArgs& A, int lane) {
 // persistent kernel: Lay::WPB warps per block (one block per SM), one instance per warp at a time, instances from
 // an atomic work queue (optionally in a caller-given order)
 template <int N_, int NOBS_, int MODEL_>
-__global__ void __launch_bounds__(32 * Lay<N_, NOBS_, MODEL_>::WPB, 1) nmpc_ipm_kernel(const SolveArgs A) {
+__global__ void __launch_bounds__(32 * Lay<N_, NOBS_, MODEL_>::WPB, 1) nmpc_ipm_kernel(const __grid_constant__ SolveArgs A) {
   using L = Lay<N_, NOBS_, MODEL_>;
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {      // the next call on this handle starts from clean counters
