@@ -135,6 +135,14 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
               double sigma, const double* lam, const double* v,
               double* f, double* g, double* grad_f, double* jtv, double* hv, void* cuda_stream);
 
+/* sol['lam_p'] of CasADi's result dict (NMPC_TT.py:358-365 returns it with x, f, g, lam_x, lam_g; no script reads it): the
+ * multipliers of the parameters, lam_p = -(d/dp)(f + lam_g^T g) at the returned point [3P: CasADi's sign convention, the one
+ * that makes grad_x (f + lam_g^T g) + lam_x = 0 for lam_x].  x_sol [B][n_w], p [B][n_p], lam_g [B][n_g] as returned by
+ * nmpc_solve; lam_p [B][n_p].  With a per-stage target prediction (nmpc_set_target_trajectory) the target entries of p do not
+ * enter the NLP and their multipliers are 0. */
+int nmpc_lam_p(nmpc_handle* h, int32_t B, const double* x_sol, const double* p, const double* obst, uint32_t flags,
+               const double* lam_g, double* lam_p, void* cuda_stream);
+
 /* shift_timestep (NMPC_TT.py:13-30) + FOV centre (:399-402) for B instances, in place on the
  * parameter block the next solve reads:
  *   p [B][11]: p[0:8] <- x + T f_u(x, u[:,0]);  p[8:11] <- target + T [v cos th, v sin th, om]

@@ -40,7 +40,7 @@ class NmpcStats(C.Structure):
                 ("watchdog_starts", C.c_int64), ("soft_resto_steps", C.c_int64), ("filter_resets", C.c_int64)]
 
 
-EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_run_closed_loop", "nmpc_eval", "nmpc_step",
+EXPORTS = ["nmpc_create", "nmpc_destroy", "nmpc_solve", "nmpc_solve_host", "nmpc_solve_host_async", "nmpc_synchronize", "nmpc_query", "nmpc_solve_and_step", "nmpc_run_closed_loop", "nmpc_eval", "nmpc_lam_p", "nmpc_step",
            "nmpc_get_stats", "nmpc_set_debug_log", "nmpc_set_order", "nmpc_set_weights", "nmpc_set_target_trajectory", "nmpc_set_schedule", "nmpc_set_warm_start", "nmpc_measure_fp64_peak", "nmpc_n_w", "nmpc_n_g", "nmpc_n_p",
            "nmpc_last_error", "nmpc_version"]
 
@@ -75,6 +75,8 @@ def lib():
         L.nmpc_run_closed_loop.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 7 + [C.c_uint32] + [vp] * 8 + [vp]
     L.nmpc_eval.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_uint32, C.c_double, vp, vp] + [vp] * 5 + [vp]
     L.nmpc_step.argtypes = [vp, C.c_int32] + [vp] * 6 + [vp]
+    if hasattr(L, "nmpc_lam_p"):
+        L.nmpc_lam_p.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_uint32, vp, vp, vp]
     L.nmpc_get_stats.argtypes = [vp, C.POINTER(NmpcStats)]
     L.nmpc_set_debug_log.argtypes = [vp, vp, C.c_int32]
     L.nmpc_set_order.argtypes = [vp, vp]

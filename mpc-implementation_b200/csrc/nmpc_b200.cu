@@ -44,6 +44,7 @@ struct EvalArgs {
   const double *weights, *tgt;
   double sigma; const double *lam, *v;
   double *f, *g, *grad, *jtv, *hv;
+  double* lamp;      // nmpc_lam_p: -(d/dp)(sigma f + lam^T g), [B][n_p]
 };
 
 __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
@@ -121,6 +122,30 @@ __global__ void __launch_bounds__(128) nmpc_eval_kernel(const EvalArgs A) {
     gt_lam(a);
     adjoint(a, lamn); Bt(lamn, out);
     if (hasu) for (int i = 0; i < nu; ++i) A.jtv[(size_t)b * nw + nu * lane + i] = out[i];
+  }
+  if (A.lamp) {
+    // lam_p of CasADi's result dict (NMPC_TT.py:358-365 returns it, nobody reads it): minus the gradient of the Lagrangian with
+    // respect to p = [X_0; x_t; y_t; theta_t].  d/dX_0 is the adjoint at stage 0 (the stage-0 cost and rows count here, unlike in
+    // the gradient with respect to w); the stage costs depend on the target only through (x - x_t, y - y_t), so d/d(x_t, y_t) =
+    // -sum_k dl_k/d(x, y); theta_t does not enter.  With a per-stage target prediction the target entries of p are unused: 0.
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) a[cost_state(v)] = A.sigma * gl[v];
+    gt_lam(a);
+    adjoint(a, lamn);
+    const double sx = warp_sum(hasu ? A.sigma * gl[0] : 0.0), sy = warp_sum(hasu ? A.sigma * gl[1] : 0.0);
+    if (lane == 0) {
+      double l0[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) l0[i] = a[i] + lamn[i];
+      l0[3] += e03 * lamn[0] + e13 * lamn[1] + e23 * lamn[2];
+      l0[4] += e04 * lamn[0] + e14 * lamn[1];
+      double* lp = A.lamp + (size_t)b * npar;
+      const int ns = pr.model ? 5 : 8;
+      for (int i = 0; i < ns; ++i) lp[i] = -l0[i];
+      lp[ns] = A.tgt ? 0.0 : sx; lp[ns + 1] = A.tgt ? 0.0 : sy; lp[ns + 2] = 0.0;
+    }
   }
   if (A.hv) {
     // adjoint of the Lagrangian sigma f + lam^T g
@@ -525,7 +550,25 @@ int nmpc_eval(nmpc_handle* h, int32_t B, const double* w, const double* p, const
   EvalArgs A;
   A.pr = h->pr; A.B = B; A.w = w; A.p = p; A.obs = obst; A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
   A.weights = h->weights; A.tgt = h->tgt;
-  A.sigma = sigma; A.lam = lam; A.v = v; A.f = f; A.g = g; A.grad = grad_f; A.jtv = jtv; A.hv = hv;
+  A.sigma = sigma; A.lam = lam; A.v = v; A.f = f; A.g = g; A.grad = grad_f; A.jtv = jtv; A.hv = hv; A.lamp = nullptr;
+  const int warps = 4;
+  nmpc_eval_kernel<<<(B + warps - 1) / warps, warps * 32, 0, (cudaStream_t)cuda_stream>>>(A);
+  CK(cudaGetLastError());
+  h->last_stream = (cudaStream_t)cuda_stream; h->launches = 1;
+  return 0;
+}
+
+int nmpc_lam_p(nmpc_handle* h, int32_t B, const double* x_sol, const double* p, const double* obst, uint32_t flags,
+               const double* lam_g, double* lam_p, void* cuda_stream) {
+  if (!h) return fail("nmpc_lam_p: null handle");
+  if (B <= 0) return 0;
+  if (!x_sol || !p || !lam_g || !lam_p) return fail("nmpc_lam_p: null required pointer");
+  if (h->pr.n_obs > 0 && !obst) return fail("nmpc_lam_p: obstacle table required");
+  CK(cudaSetDevice(h->device));
+  EvalArgs A;
+  A.pr = h->pr; A.B = B; A.w = x_sol; A.p = p; A.obs = obst; A.obs_per_instance = (flags & NMPC_OBS_PER_INSTANCE) ? 1 : 0;
+  A.weights = h->weights; A.tgt = h->tgt;
+  A.sigma = 1.0; A.lam = lam_g; A.v = nullptr; A.f = nullptr; A.g = nullptr; A.grad = nullptr; A.jtv = nullptr; A.hv = nullptr; A.lamp = lam_p;
   const int warps = 4;
   nmpc_eval_kernel<<<(B + warps - 1) / warps, warps * 32, 0, (cudaStream_t)cuda_stream>>>(A);
   CK(cudaGetLastError());

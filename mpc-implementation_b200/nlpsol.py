@@ -290,7 +290,16 @@ class Solver:
                       ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters)),
                    "nmpc_solve_host")
         self._stats = dict(return_status=status, iter_count=iters)      # success is derived in stats(): valid after wait()
-        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
+        lam_p = None
+        if want_lam and blocking:      # CasADi's result dict also carries lam_p (nobody in the reference reads it)
+            dev = f"cuda:{self.device}"
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            xd, pd, ld, od = up(x), up(p), up(lam_g), up(obs)
+            lp = torch.empty((B, self.n_p), dtype=torch.float64, device=dev)
+            _ffi.check(L.nmpc_lam_p(self._h, B, xd.data_ptr(), pd.data_ptr(), od.data_ptr() if od.numel() else None, flags, ld.data_ptr(),
+                                    lp.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "nmpc_lam_p")
+            lam_p = lp.cpu().numpy()
+        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g, lam_p=lam_p)
         if single:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
         return out
@@ -333,9 +342,13 @@ class Solver:
         _ffi.check(L.nmpc_solve(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
                                 ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters), stream),
                    "nmpc_solve")
+        lam_p = None
+        if want_lam:      # CasADi's result dict also carries lam_p (one small extra launch; nobody in the reference reads it)
+            lam_p = torch.empty((B, self.n_p), dtype=torch.float64, device=dev)
+            _ffi.check(L.nmpc_lam_p(self._h, B, ptr(x), ptr(p), ptr(obs), flags, ptr(lam_g), ptr(lam_p), stream), "nmpc_lam_p")
         self._keep = (p, x0, obs, order)   # keep inputs alive until the stream has consumed them
         self._stats = dict(return_status=status, iter_count=iters)      # success is derived lazily in stats()
-        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
+        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g, lam_p=lam_p)
         if single:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
         return out

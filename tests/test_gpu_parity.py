@@ -813,3 +813,31 @@ def test_free_running_loop_is_the_same_loop(pkg, name, N, B, K, phases):
     # and the two loops stay interchangeable afterwards (schedule counter, fetch order)
     a.step(); b.step(); torch.cuda.synchronize()
     assert torch.equal(a.p, b.p) and torch.equal(a.u_warm, b.u_warm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["nmpc_tt", "race_track_2", "gimbal_less"])
+def test_lam_p(pkg, name):
+    """sol['lam_p'] (CasADi returns it next to lam_x / lam_g, NMPC_TT.py:358-365): minus the gradient of f + lam_g^T g with respect
+    to p at the returned point, against autograd of the literal NLP -- and the same sign convention as lam_x."""
+    from oracle import nlp_ref
+    sc = pkg.SCENARIOS[name]
+    B = 6
+    lbx, ubx, lbg, ubg = sc.bounds()
+    p, _ = pkg.random_instances(sc, B, seed=9)
+    s = pkg.nlpsol("s", "ipm", sc, max_batch=B)
+    sol = s(x0=np.zeros((B, sc.n_w)), p=p, lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+    assert sol["lam_p"].shape == (B, sc.n_p)
+    for b in range(B):
+        pt = torch.tensor(p[b], requires_grad=True); wt = torch.tensor(sol["x"][b], requires_grad=True); lt = torch.tensor(sol["lam_g"][b])
+        if sc.model:
+            rs = nlp_ref.RefSpec5(sc.T, sc.N)
+            Lg = nlp_ref.objective5(rs, wt, pt) + (lt * nlp_ref.constraints5(rs, wt, pt)).sum()
+        else:
+            rs = nlp_ref.RefSpec(T=sc.T, N=sc.N, obstacles=sc.obstacles, uav_r=sc.uav_r, w1=sc.w1, w2=sc.w2)
+            Lg = nlp_ref.objective(rs, wt, pt) + (lt * nlp_ref.constraints(rs, wt, pt)).sum()
+        gp, gw = torch.autograd.grad(Lg, [pt, wt])
+        scale = max(1.0, float(gp.abs().max()))
+        assert np.abs(sol["lam_p"][b] + gp.numpy()).max() <= 1e-9 * scale, (sol["lam_p"][b], gp)
+        if s.stats()["return_status"][b] == 0:      # same convention as lam_x: grad_x L + lam_x = 0 at a solution
+            assert np.abs(sol["lam_x"][b] + gw.numpy()).max() <= 1e-5 * max(1.0, float(gw.abs().max()))
