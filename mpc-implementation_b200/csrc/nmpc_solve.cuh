@@ -1117,6 +1117,7 @@ enum AlgF {
   F_INFPR,                                          // max-norm of g - s where the restoration phase was called
   F_NFILT, F_SUCC, F_NRES, F_WSHORT, F_WTRIAL, F_SOFTC,
   F_LASTREJ, F_INWD, F_INSOFT, F_TINYLAST, F_TINYFLAG, F_FIRST, F_MUST,
+  F_PWPHI, F_PWTH,                                  // (-F_RGBD)^s_phi and delta * F_RTH^s_theta of the switching condition, computed once per reference point (< 0: not yet)
   F_NALG,
   F_MODE = F_NALG,                                  // 0 original problem, 1 restoration problem
   F_DW, F_APR, F_ADU, F_GBD, F_THETA, F_PHI,        // this iteration: delta_w, step limits, barrier slope, theta, barrier of the current point
@@ -1137,6 +1138,7 @@ __device__ __noinline__ void alg_init(double mu, double tau_min, double tol) {
   for (int f = 0; f < F_NALG; ++f) AL(f) = 0.0;
   __syncwarp();
   AL(F_MU) = mu; AL(F_TAU) = fmax(tau_min, 1.0 - mu); AL(F_TOL) = tol; AL(F_THMAX) = -1.0; AL(F_THMIN) = -1.0; AL(F_FIRST) = 1.0;
+  AL(F_PWPHI) = -1.0;
   __syncwarp();
 }
 
@@ -1202,7 +1204,14 @@ template <class L>
 __device__ __forceinline__ bool is_ftype(const SolveArgs& A, double at) {
   const double rt = AL(F_RTH), rg = AL(F_RGBD);
   if (rt == 0.0 && rg > 0.0 && rg < 100.0 * EPSM) return true;
-  return rg < 0.0 && at * n_pow(-rg, A.o.s_phi) > A.o.delta * n_pow(rt, A.o.s_theta);
+  if (!(rg < 0.0)) return false;
+  if (AL(F_PWPHI) < 0.0) {      // every lane computes and stores the same two values (the reference point changes once per line search)
+    const double a = n_pow(-rg, A.o.s_phi), b = A.o.delta * n_pow(rt, A.o.s_theta);
+    __syncwarp();
+    AL(F_PWPHI) = a; AL(F_PWTH) = b;
+    __syncwarp();
+  }
+  return at * AL(F_PWPHI) > AL(F_PWTH);
 }
 template <class L>
 __device__ __forceinline__ bool armijo(const SolveArgs& A, double at, double tb) { const double rb = AL(F_RBARR); return cmp_le(tb - rb, A.o.eta_phi * at * AL(F_RGBD), rb); }
@@ -1252,7 +1261,7 @@ __device__ __noinline__ void wd_stop(const SolveArgs& A, double* cold, int lane,
   do_trial<L>(A, lane, mode, 0.0, false, df, cold);
   take_trial_values<L>();
   AL(F_PHI) = trial_barrier<L>(A);
-  AL(F_RTH) = AL(F_WTH); AL(F_RBARR) = AL(F_WBARR); AL(F_RGBD) = AL(F_WGBD);
+  AL(F_RTH) = AL(F_WTH); AL(F_RBARR) = AL(F_WBARR); AL(F_RGBD) = AL(F_WGBD); AL(F_PWPHI) = -1.0;
   __syncwarp();
 }
 
@@ -1528,6 +1537,7 @@ __device__ __noinline__ void solve_instance(const SolveArgs& A, double* ric, dou
       AL(F_LASTREJ) = 0.0;
       AL(F_RTH) = AL(F_THETA); AL(F_RBARR) = AL(F_PHI); AL(F_RGBD) = AL(F_GBD);
     } else { AL(F_RTH) = AL(F_WTH); AL(F_RBARR) = AL(F_WBARR); AL(F_RGBD) = AL(F_WGBD); }
+    AL(F_PWPHI) = -1.0;
     bool tiny = !goto_resto && RES(R_TINY) != 0.0 && AL(F_THETA) <= 1e-4;
     if (AL(F_INWD) != 0.0 && (goto_resto || tiny)) { wd_stop<L>(A, cold, lane, df); dw = AL(F_DW); goto_resto = false; tiny = false; }
     if (o.watchdog_trigger > 0 && AL(F_INWD) == 0.0 && !goto_resto && !tiny && AL(F_INSOFT) == 0.0 && AL(F_WSHORT) >= (double)o.watchdog_trigger)
