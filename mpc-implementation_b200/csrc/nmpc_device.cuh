@@ -120,11 +120,12 @@ static __device__ __noinline__ double warp_min(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
-// exclusive prefix sums of NV independent values (interleaved for ILP)
-template <int NV>
+// exclusive prefix sums of NV independent values (interleaved for ILP).  W (a power of two >= the number of stages): lanes >= W
+// hold zeros and are not needed, so the steps with offsets >= W are dropped (they would add exact zeros: same results).
+template <int NV, int W = 32>
 __device__ __forceinline__ void scan_excl(double* v, int lane) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
+  for (int o = 1; o < W; o <<= 1) {
     double t[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) t[c] = __shfl_up_sync(FULL, v[c], o);
@@ -136,11 +137,11 @@ __device__ __forceinline__ void scan_excl(double* v, int lane) {
 #pragma unroll
   for (int c = 0; c < NV; ++c) { const double e = __shfl_up_sync(FULL, v[c], 1); v[c] = lane == 0 ? 0.0 : e; }
 }
-// inclusive suffix sums of NV independent values
-template <int NV>
+// inclusive suffix sums of NV independent values (W as above)
+template <int NV, int W = 32>
 __device__ __forceinline__ void rscan_incl(double* v, int lane) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
+  for (int o = 1; o < W; o <<= 1) {
     double t[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) t[c] = __shfl_down_sync(FULL, v[c], o);
@@ -172,6 +173,7 @@ template <int N_, int NOBS_, bool FOLD_, int MODEL_ = 0>
 struct LayT {
   static constexpr int MODEL = MODEL_, NB = model_nb(MODEL_), NUA = model_nu(MODEL_), NPA = model_np(MODEL_);
   static constexpr int N = N_, S = N_ + 1, R = NB + NOBS_, NOBS = NOBS_;
+  static constexpr int SW = S <= 8 ? 8 : (S <= 16 ? 16 : 32);      // width of the warp scans over the stages
   static constexpr bool FOLD = FOLD_;
   static constexpr int LQ_NE = FOLD_ ? LQ_NFOLD : LQ_N;
   static constexpr int LV0 = 0;
@@ -223,20 +225,21 @@ struct Stage {
 };
 
 // Rollout by prefix sums.  u is this lane's control (ignored for lanes >= N).  NMPC_TT.py:139-148,160-167
+template <int W = 32>
 __device__ __forceinline__ void rollout(const Prob& pr, const double* __restrict__ X0, const double* u, int lane, Stage& st) {
   const bool has_u = lane < pr.N;
   const double T = pr.T;
   double a[5];
 #pragma unroll
   for (int c = 0; c < 5; ++c) a[c] = has_u ? T * u[c + 1] : 0.0;
-  scan_excl<5>(a, lane);
+  scan_excl<5, W>(a, lane);
 #pragma unroll
   for (int c = 0; c < 5; ++c) st.X[3 + c] = X0[3 + c] + a[c];
   const double2 sct = n_sincos(st.X[3]), scp = n_sincos(st.X[4]);
   st.sth = sct.x; st.cth = sct.y; st.sps = scp.x; st.cps = scp.y;
   const double tv = has_u ? T * u[0] : 0.0;
   double inc[3] = {tv * st.cps * st.cth, tv * st.sps * st.cth, tv * st.sth};
-  scan_excl<3>(inc, lane);
+  scan_excl<3, W>(inc, lane);
   st.X[0] = X0[0] + inc[0]; st.X[1] = X0[1] + inc[1]; st.X[2] = X0[2] + inc[2];
 }
 

@@ -186,14 +186,15 @@ __device__ __forceinline__ Dyn dyn_entries(const Stage& s, double tv) {
   return d;
 }
 // adjoint recursion lam_k = a_k + A_k^T lam_{k+1} by suffix scans; returns lam_{k+1} in lamn
+template <int W = 32>
 __device__ __forceinline__ void adjoint(const double* a, const Dyn& d, bool act, int lane, double* lamn) {
   double v[6] = {act ? a[0] : 0.0, act ? a[1] : 0.0, act ? a[2] : 0.0, act ? a[5] : 0.0, act ? a[6] : 0.0, act ? a[7] : 0.0};
-  rscan_incl<6>(v, lane);
+  rscan_incl<6, W>(v, lane);
   lamn[0] = shfl_next(v[0], lane); lamn[1] = shfl_next(v[1], lane); lamn[2] = shfl_next(v[2], lane);
   lamn[5] = shfl_next(v[3], lane); lamn[6] = shfl_next(v[4], lane); lamn[7] = shfl_next(v[5], lane);
   double w[2] = {(act ? a[3] : 0.0) + d.e03 * lamn[0] + d.e13 * lamn[1] + d.e23 * lamn[2],
                  (act ? a[4] : 0.0) + d.e04 * lamn[0] + d.e14 * lamn[1]};
-  rscan_incl<2>(w, lane);
+  rscan_incl<2, W>(w, lane);
   lamn[3] = shfl_next(w[0], lane); lamn[4] = shfl_next(w[1], lane);
 }
 
@@ -294,7 +295,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
   double u[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = act ? LV(LV_U + i) : 0.0;
-  Stage st; rollout(pr, &PAR(0), u, lane, st);
+  Stage st; rollout<L::SW>(pr, &PAR(0), u, lane, st);
   const Dyn dy = dyn_entries(st, hasu ? T * u[0] : 0.0);
   double gl[6], Hl[21], a[8], lamn[8];
 #pragma unroll
@@ -304,7 +305,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 #pragma unroll
     for (int v = 0; v < 6; ++v) a[cost_state(v)] = gl[v];
   }
-  adjoint(a, dy, act, lane, lamn);
+  adjoint<L::SW>(a, dy, act, lane, lamn);
   double gmax = 0.0;
   if (hasu) {
     gmax = fabs(T * (st.cps * st.cth * lamn[0] + st.sps * st.cth * lamn[1] + st.sth * lamn[2]));
@@ -315,7 +316,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
   // row maxima of the Jacobian: |d g_{k,i} / d u_j| for j < k
   const double d0 = st.cps * st.cth, d1 = st.sps * st.cth, d2 = st.sth;
   double c3[3] = {dy.e03, dy.e13, dy.e23}, c4[2] = {dy.e04, dy.e14};
-  scan_excl<3>(c3, lane); scan_excl<2>(c4, lane);
+  scan_excl<3, L::SW>(c3, lane); scan_excl<2, L::SW>(c4, lane);
   double zmax = 0.0;
   // scratch in row arrays that are not live yet: A_G = row max, A_S / A_IU = obstacle normal
   if (act) {
@@ -382,7 +383,7 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane, int b_, doubl
       nz += (b.hl ? 1 : 0) + (b.hu ? 1 : 0);
     } else if (act) { LV(LV_ZL + i) = 0.0; LV(LV_ZU + i) = 0.0; }
   }
-  Stage st; rollout(pr, &PAR(0), u, lane, st);
+  Stage st; rollout<L::SW>(pr, &PAR(0), u, lane, st);
   if (act) {
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r);
@@ -421,7 +422,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
   double u[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) u[i] = act ? LV(LV_U + i) : 0.0;
-  Stage st; rollout(pr, &PAR(0), u, lane, st);
+  Stage st; rollout<L::SW>(pr, &PAR(0), u, lane, st);
   const Dyn dy = dyn_entries(st, hasu ? T * u[0] : 0.0);
   double gl[6], Hl[21];
 #pragma unroll
@@ -532,7 +533,7 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
     LQ(LQ_Q + 21) = q22;
   }
   double lamn[8];
-  adjoint(a, dy, act, lane, lamn);
+  adjoint<L::SW>(a, dy, act, lane, lamn);
   if (act) {
     double svt = 0.0, svp = 0.0, q33 = 0.0, q34 = 0.0, q44 = 0.0;
     if (hasu && !ls) {
@@ -727,7 +728,7 @@ __device__ __noinline__ void ph_trial(const SolveArgs& A, int lane, double alpha
       if (RS) { const double ur = UREF(i), d = rcp(fmax(1.0, fabs(ur))), e = d * (ut[i] - ur); fr += e * e; }
     }
   }
-  Stage st; rollout(pr, &PAR(0), ut, lane, st);
+  Stage st; rollout<L::SW>(pr, &PAR(0), ut, lane, st);
   double l = 0.0;
   if (!RS) l = hasu ? cost_val<L>(A, st.X, lane) : 0.0;
   else l = 0.5 * A.o.resto_eta_factor * sqrt(mu) * fr;
@@ -1035,7 +1036,7 @@ __device__ __noinline__ void ph_output(const SolveArgs& A, int b, int lane, doub
       for (int i = 0; i < L::NUA; ++i) lo[i] = (LV(LV_ZU + i) - LV(LV_ZL + i)) * idf;
     }
   }
-  Stage st; rollout(pr, &PAR(0), u, lane, st);
+  Stage st; rollout<L::SW>(pr, &PAR(0), u, lane, st);
   const double l = hasu ? cost_val<L>(A, st.X, lane) : 0.0;
   const double fu = warp_sum(l);
   if (lane == 0) {
