@@ -58,6 +58,32 @@ def _spec_from(problem, opts: Optional[dict]) -> Dict[str, Any]:
     return d
 
 
+class _Sol(dict):
+    """Result dict of a solve.  sol['lam_p'] -- the sixth key of CasADi's result dict, which no reference script reads -- is
+    computed on first access (one small launch, nmpc_lam_p) instead of on every call."""
+
+    def __init__(self, items, lam_p_fn=None):
+        super().__init__(items)
+        self._lam_p_fn = lam_p_fn
+        if lam_p_fn is not None:
+            super().__setitem__("lam_p", None)
+
+    def __getitem__(self, k):
+        if k == "lam_p" and self._lam_p_fn is not None:
+            super().__setitem__("lam_p", self._lam_p_fn())
+            self._lam_p_fn = None
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
 class Solver:
     """Callable returned by nlpsol(); owns one nmpc_handle."""
 
@@ -290,19 +316,19 @@ class Solver:
                       ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters)),
                    "nmpc_solve_host")
         self._stats = dict(return_status=status, iter_count=iters)      # success is derived in stats(): valid after wait()
-        lam_p = None
-        if want_lam and blocking:      # CasADi's result dict also carries lam_p (nobody in the reference reads it)
+        def lam_p_host():      # CasADi's result dict also carries lam_p (nobody in the reference reads it): on first access
             dev = f"cuda:{self.device}"
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
             xd, pd, ld, od = up(x), up(p), up(lam_g), up(obs)
             lp = torch.empty((B, self.n_p), dtype=torch.float64, device=dev)
             _ffi.check(L.nmpc_lam_p(self._h, B, xd.data_ptr(), pd.data_ptr(), od.data_ptr() if od.numel() else None, flags, ld.data_ptr(),
                                     lp.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "nmpc_lam_p")
-            lam_p = lp.cpu().numpy()
-        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g, lam_p=lam_p)
+            r = lp.cpu().numpy()
+            return r[0] if single else r
+        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
         if single:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
-        return out
+        return _Sol(out, lam_p_host if (want_lam and blocking) else None)
 
     def _call_device(self, x0, p, lbx, ubx, lbg, ubg, obstacles, want_g, want_lam, order=None):
         L = _ffi.lib()
@@ -342,16 +368,18 @@ class Solver:
         _ffi.check(L.nmpc_solve(self._h, B, ptr(p), ptr(x0), ptr(lbx), ptr(ubx), ptr(lbg), ptr(ubg), ptr(obs), flags,
                                 ptr(x), ptr(f), ptr(g), ptr(lam_x), ptr(lam_g), ptr(status), ptr(iters), stream),
                    "nmpc_solve")
-        lam_p = None
-        if want_lam:      # CasADi's result dict also carries lam_p (one small extra launch; nobody in the reference reads it)
-            lam_p = torch.empty((B, self.n_p), dtype=torch.float64, device=dev)
-            _ffi.check(L.nmpc_lam_p(self._h, B, ptr(x), ptr(p), ptr(obs), flags, ptr(lam_g), ptr(lam_p), stream), "nmpc_lam_p")
+        def lam_p_dev():      # CasADi's result dict also carries lam_p (nobody in the reference reads it): on first access
+            lp = torch.empty((B, self.n_p), dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                _ffi.check(L.nmpc_lam_p(self._h, B, ptr(x), ptr(p), ptr(obs), flags, ptr(lam_g), ptr(lp),
+                                        torch.cuda.current_stream(dev).cuda_stream), "nmpc_lam_p")
+            return lp[0] if single else lp
         self._keep = (p, x0, obs, order)   # keep inputs alive until the stream has consumed them
         self._stats = dict(return_status=status, iter_count=iters)      # success is derived lazily in stats()
-        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g, lam_p=lam_p)
+        out = dict(x=x, f=f, g=g, lam_x=lam_x, lam_g=lam_g)
         if single:
             out = {k: (v[0] if v is not None else None) for k, v in out.items()}
-        return out
+        return _Sol(out, lam_p_dev if want_lam else None)
 
     def stats(self) -> Dict[str, Any]:
         """Per-instance outcome of the last call (CasADi: solver.stats()); after a blocking=False call, valid once
