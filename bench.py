@@ -404,6 +404,32 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier(); dist.destroy_process_group()
         return
 
+    # ---- the same closed loop advanced by nmpc_run_closed_loop (the scripts' whole `while mpc_iter < sim_time / T` loop on the
+    #      device: a warp goes on with step k + 1 of its instance without waiting for the batch; bit-identical per instance,
+    #      tests/test_gpu_parity.py::test_free_running_loop_is_the_same_loop).  Reported beside the headline, not as it: a
+    #      "step" of the metric is one pass over the batch, which this mode deliberately does not have.
+    free = None
+    if not args.no_free_running:
+        from mpc_implementation_b200.closed_loop import ClosedLoop
+        scf, pf, vwf, obsf, schedf = make_workload(b200nmpc, cfg, B, seed=2000 + rank)
+        clf = ClosedLoop(b200nmpc.nlpsol("free", "ipm", scf, {"ipopt": {"max_iter": 100}}, device=local_rank, max_batch=B), scf, pf,
+                         target_vw=vwf, obstacles=obsf,
+                         **({} if schedf is None else dict(schedules=schedf["schedules"], schedule_of=schedf["schedule_of"], phase=schedf["phase"])))
+        clf.run_free(args.warmup, log=False)
+        chunk = max(1, K // 4); nl = max(1, K // chunk)
+        conv_f = torch.zeros((), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(nl):
+            conv_f += clf.run_free(chunk, log=False)["converged"].sum()
+        f1.record(); torch.cuda.synchronize()
+        ms_f = f0.elapsed_time(f1)
+        free = {"value": float(conv_f.item()) / (ms_f * 1e-3), "unit": UNIT, "steps": nl * chunk, "steps_per_launch": chunk, "gpu_launches": nl,
+                "ms_per_step": ms_f / (nl * chunk), "converged_fraction": float(conv_f.item()) / (B * nl * chunk), "n_gpus": 1,
+                "note": "nmpc_run_closed_loop on rank 0's GPU: one handle, no sub-batch pipelining, no batch-wide barrier between steps, no L2 flush between steps (there is no step boundary to flush at)"}
+        del clf
+
     # ---- one extra untimed step on rank 0: work counters for the flop numerator, and the census of THIS population
     #      (status histogram; how many of the non-converged NLPs are provably infeasible from p alone)
     p_now = cl.p.cpu().numpy(); obs_now = obs
@@ -496,6 +522,7 @@ def run_b200(args, rank, world, local_rank):
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=[,obstacles=], blocking=False) with pinned numpy buffers -> nmpc_solve_host_async / nmpc_query / nmpc_synchronize, one solver per sub-batch, serviced in completion order"},
         "gpu_launches": K * S,     # nmpc_ipm_kernel (solve + shift + schedule lookup + next call's fetch order), one per sub-batch step
         "gathered": gathered,
+        "free_running": free,
         "roofline": {"bound": "hbm", "achieved": agg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": agg_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_step": bps * B, "bytes_per_solve": bps,
                      "kernel": "nmpc_ipm_kernel", "launches_per_step": S, "step_ms": k_ms, "per_launch_event_ms": launch_ms, "peak_source": which,
@@ -548,6 +575,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-free-running", action="store_true", help="skip the extra nmpc_run_closed_loop measurement on rank 0")
     ap.add_argument("--pipelines", type=int, default=0, help="independently pipelined sub-batches per GPU (0 = choose from the batch size, 1 = one batch on one stream)")
     ap.add_argument("--no-lpt", action="store_true", help="disable the library's longest-first scheduling (NMPC_B200_AUTO_ORDER=0)")
     ap.add_argument("--count-work", action="store_true", help="read device work counters every timed step (adds a sync)")
