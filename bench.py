@@ -260,8 +260,9 @@ def run_b200(args, rank, world, local_rank):
     B = args.batch or cfg["batch"]
     if args.no_lpt:
         os.environ["NMPC_B200_AUTO_ORDER"] = "0"
-    # sub-batches: measured best 8 at B = 4096, 2 at B = 16384 (tools/pipeline_probe.py): about 32768 / B, at most 8
-    S = max(1, min(args.pipelines, B)) if args.pipelines > 0 else max(1, min(8, 32768 // max(B, 1)))     # PipelinedClosedLoop default
+    # sub-batches: measured best 8 at B = 4096, 2 at B = 16384 (tools/pipeline_probe.py), and still 2 for the big batches (tools/
+    # pack_sweep_big.sh: configs 3 / 4 +6.5 % / +10 % over one batch): about 32768 / B, at least 2, at most 8
+    S = max(1, min(args.pipelines, B)) if args.pipelines > 0 else max(1, min(B, max(2, min(8, 32768 // max(B, 1)))))     # PipelinedClosedLoop default
     sc, p, vw, obs, sched = make_workload(b200nmpc, cfg, B, seed=2000 + rank)
     per_obs = obs is not None
     # fill = 2: a sub-batch occupies half as many SMs as it has warps' worth of instances, leaving SMs to the other sub-batches
@@ -348,8 +349,12 @@ def run_b200(args, rank, world, local_rank):
     Ke = min(K, args.e2e_steps) if args.e2e_steps > 0 else K
     lbx, ubx, lbg, ubg = sc.bounds()
     pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    # sub-batches of the host arm: the device arm's when it has several; a big single batch is split in four so that the copies
+    # and the (single-threaded numpy) shift of one quarter overlap the solves of the others -- what a host-side caller would do
+    S_e = S if B < 16384 else max(S, 4)
+    index_e = cl.index if S_e == S else np.array_split(np.arange(B), S_e)
     hs = []
-    for idx in cl.index:
+    for idx in index_e:
         ph = pin((len(idx), 11)); ph[:] = p[idx]
         uh = pin((len(idx), sc.n_w)); uh[:] = 0.0
         oh = None
@@ -396,7 +401,7 @@ def run_b200(args, rank, world, local_rank):
     t_e_max = sharding.max_over_ranks(t_e, dev)
     conv_e_all = float(sharding.sum_counters([conv_e], dev)[0])
     e2e_val = conv_e_all / t_e_max if t_e_max > 0 else None
-    h2d = B * (11 + sc.n_w + (3 * sc.n_obs if per_obs else 0)) * 8 + S * (2 * sc.n_w + 2 * sc.n_g + (0 if per_obs else 3 * sc.n_obs)) * 8
+    h2d = B * (11 + sc.n_w + (3 * sc.n_obs if per_obs else 0)) * 8 + S_e * (2 * sc.n_w + 2 * sc.n_g + (0 if per_obs else 3 * sc.n_obs)) * 8
     d2h = B * (sc.n_w + 1) * 8 + B * 8
 
     if rank != 0:
@@ -518,7 +523,7 @@ def run_b200(args, rank, world, local_rank):
                         "batch_step_ms_first_quarter": float(np.mean(batch_step_ms[:q])), "batch_step_ms_last_quarter": float(np.mean(batch_step_ms[-q:]))},
         "cold_first_step": cold, "wall_s": wall,
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "step_ms": e2e_ms[:64],
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke, "sub_batches": S_e, "step_ms": e2e_ms[:64],
                 "api": "b200nmpc.nlpsol(...)(x0=,p=,lbx=,ubx=,lbg=,ubg=[,obstacles=], blocking=False) with pinned numpy buffers -> nmpc_solve_host_async / nmpc_query / nmpc_synchronize, one solver per sub-batch, serviced in completion order"},
         "gpu_launches": K * S,     # nmpc_ipm_kernel (solve + shift + schedule lookup + next call's fetch order), one per sub-batch step
         "gathered": gathered,

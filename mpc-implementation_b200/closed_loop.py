@@ -177,12 +177,12 @@ class PipelinedClosedLoop:
                  pipelines: Optional[int] = None, device: Optional[str] = None, phase=None, predict_target: bool = False,
                  obstacles=None, obstacle_vel=None, schedules=None, schedule_of=None):
         """make_solver(n) -> Solver for a sub-batch of n instances (give it `fill=2`: a sub-batch then leaves SMs to
-        the others).  pipelines: number of sub-batches; None = about 32768 / B, at most 8 (measured best: 8 at
-        B = 4096, 2 at B = 16384 on a B200)."""
+        the others).  pipelines: number of sub-batches; None = about 32768 / B, at least 2, at most 8 (measured best: 8 at
+        B = 4096, 2 at B = 16384 ... 131072 on a B200)."""
         p0 = np.asarray(p0, dtype=np.float64).reshape(-1, scenario.n_p)
         B = p0.shape[0]
         if pipelines is None:
-            pipelines = max(1, min(8, 32768 // max(B, 1)))
+            pipelines = max(2, min(8, 32768 // max(B, 1)))
         S = max(1, min(int(pipelines), B))
         self.index = np.array_split(np.arange(B), S)
         self.B, self.sc = B, scenario
