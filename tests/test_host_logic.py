@@ -88,3 +88,16 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_result_dict_computes_lam_p_on_first_access():
+    """sol['lam_p'] (CasADi's sixth result key, never read by the reference) costs nothing unless somebody reads it."""
+    from mpc_implementation_b200.nlpsol import _Sol
+    calls = []
+    s = _Sol(dict(x=1, f=2), lambda: calls.append(1) or "LP")
+    assert "lam_p" in s and set(s.keys()) == {"x", "f", "lam_p"} and not calls
+    assert s["x"] == 1 and not calls
+    assert s["lam_p"] == "LP" and s["lam_p"] == "LP" and len(calls) == 1
+    assert dict(s.items())["lam_p"] == "LP" and s.get("lam_p") == "LP" and s.get("nope", 7) == 7
+    t = _Sol(dict(x=1), None)
+    assert "lam_p" not in t
