@@ -35,7 +35,9 @@ enum LvEnt { LV_U = 0, LV_ZL = 6, LV_ZU = 12, LV_X = 18, LV_GL = 26, LV_DX = 32,
 // The obstacle rows have no lower bound in this NLP family (lbg = -inf, NMPC_TT.py:280-282), so the two arrays that belong
 // to lower bounds (multiplier v_L and reciprocal slack 1/(s - l)) exist for the five box rows only: they come last and
 // hold NBOX rows instead of R.  A finite lower bound on an obstacle row is refused (NMPC_INVALID_NUMBER).
-enum RowArr { A_S = 0, A_Y, A_VU, A_G, A_DS, A_DC, A_IU, A_NFULL, A_VL = A_NFULL, A_IL, A_NROW };
+// (the scaled row values g themselves are not kept: every reader visits the rows with the cached states X at hand and
+// recomputes g = dc * row(X), bit for bit what ph_derivs had)
+enum RowArr { A_S = 0, A_Y, A_VU, A_DS, A_DC, A_IU, A_NFULL, A_VL = A_NFULL, A_IL, A_NROW };
 // ---- per-stage LQ data (entry-major: e * S + stage).  Entries [0, LQ_DEAD) are dead once the
 //      factorisation has succeeded and are reused by the second-order-correction arrays. ----------
 enum LqEnt {

@@ -318,12 +318,12 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
   double c3[3] = {dy.e03, dy.e13, dy.e23}, c4[2] = {dy.e04, dy.e14};
   scan_excl<3, L::SW>(c3, lane); scan_excl<2, L::SW>(c4, lane);
   double zmax = 0.0;
-  // scratch in row arrays that are not live yet: A_G = row max, A_S / A_IU = obstacle normal
+  // scratch in row arrays that are not live yet (ph_start initialises them): A_Y = row max, A_S / A_IU = obstacle normal
   if (act) {
 #pragma unroll 1
     for (int jn = 0; jn < L::NOBS; ++jn) {
       double nx, ny, iD; obs_value<L>(st.X, jn, nx, ny, iD);
-      RW(A_G, L::NB + jn) = 0.0; RW(A_S, L::NB + jn) = nx; RW(A_IU, L::NB + jn) = ny;
+      RW(A_Y, L::NB + jn) = 0.0; RW(A_S, L::NB + jn) = nx; RW(A_IU, L::NB + jn) = ny;
     }
   }
 #pragma unroll 1
@@ -340,7 +340,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
       for (int jn = 0; jn < L::NOBS; ++jn) {
         const double nx = RW(A_S, L::NB + jn), ny = RW(A_IU, L::NB + jn);
         const double m1 = fabs(nx * pv0 + ny * pv1), m2 = fabs(nx * pt0 + ny * pt1), m3 = fabs(nx * pp0 + ny * pp1);
-        RW(A_G, L::NB + jn) = fmax(RW(A_G, L::NB + jn), fmax(m1, fmax(m2, m3)));
+        RW(A_Y, L::NB + jn) = fmax(RW(A_Y, L::NB + jn), fmax(m1, fmax(m2, m3)));
       }
     }
   }
@@ -351,7 +351,7 @@ __device__ __noinline__ double ph_scaling(const SolveArgs& A, int lane) {
 #pragma unroll
     for (int r = 1; r < L::NB; ++r) RW(A_DC, r) = sl;
 #pragma unroll 1
-    for (int jn = 0; jn < L::NOBS; ++jn) { const double m = RW(A_G, L::NB + jn); RW(A_DC, L::NB + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
+    for (int jn = 0; jn < L::NOBS; ++jn) { const double m = RW(A_Y, L::NB + jn); RW(A_DC, L::NB + jn) = m > mg ? fmax(smin, mg / m) : 1.0; }
   }
   __syncwarp();
   return gmax > A.o.max_grad ? fmax(A.o.scal_min, A.o.max_grad / gmax) : 1.0;
@@ -395,7 +395,7 @@ __device__ __noinline__ int ph_start(const SolveArgs& A, int lane, int b_, doubl
         y = fmin(fmax(A.lam_g0[(size_t)b_ * (L::R * L::S) + lane * L::R + r] * df / dc, -zcap), zcap);
         vl = b.hl ? fmax(-y, zmin) : 0.0; vu = b.hu ? fmax(y, zmin) : 0.0;
       }
-      RW(A_G, r) = g; RW(A_S, r) = s; RW(A_Y, r) = y;
+      RW(A_S, r) = s; RW(A_Y, r) = y;
       RW(A_VU, r) = vu; RW(A_IU, r) = b.hu ? rcp(b.hi - s) : 0.0;
       if (box) { RW(A_VL, r) = vl; RW(A_IL, r) = b.hl ? rcp(s - b.lo) : 0.0; }
       else if (b.hl) bad_lb = true;                     // a lower bound on an obstacle row: not this NLP family
@@ -461,7 +461,6 @@ __device__ __noinline__ void ph_derivs(const SolveArgs& A, int lane, bool ls, do
       const double g = __dmul_rn(dc, gu);
       const double s = RW(A_S, r), y = RW(A_Y, r), vl = box ? RW(A_VL, r) : 0.0, vu = RW(A_VU, r), il = box ? RW(A_IL, r) : 0.0, iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      RW(A_G, r) = g;
       double c = g - s;
       const double sig = ls ? 1.0 : vl * il + vu * iu;
       double beta = iu - il;                              // barrier gradient per unit mu (with damping)
@@ -645,7 +644,7 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
       if (RS) {
         const double y = RW(A_Y, r);
         const RestoRow q = resto_row<L>(A, cold, lane, r, vl * il + vu * iu, beta, y, mu, dw);
-        c = soc ? RG(G_CSOC, r) : RW(A_G, r) + RG(G_N, r) - RG(G_P, r) - s;
+        c = soc ? RG(G_CSOC, r) : __dmul_rn(dc, gu) + RG(G_N, r) - RG(G_P, r) - s;
         const double chat = c + q.rs * rcp(q.D) + q.rp * rcp(q.Dp) - q.rn * rcp(q.Dn);
         const double dyv = q.Om * (gd + chat);
         // dy first, then ds, dn, dp from their own dual equations: exact dual consistency whatever the rounding of the D's
@@ -660,7 +659,7 @@ __device__ __noinline__ void ph_dir(const SolveArgs& A, int lane, double mu, dou
         nottiny = nottiny || (fabs(dn) > tt * (1.0 + fabs(q.n))) || (fabs(dp) > tt * (1.0 + fabs(q.p)));
         dymax = fmax(dymax, fabs(dyv));
       } else {
-        c = soc ? RG(G_CSOC, r) : RW(A_G, r) - s;
+        c = soc ? RG(G_CSOC, r) : __dmul_rn(dc, gu) - s;
         ds = gd + c;
         dymax = fmax(dymax, fabs((vl * il + vu * iu + dw) * ds + (mu * beta - RW(A_Y, r))));
       }
@@ -779,7 +778,7 @@ __device__ __noinline__ void ph_socrhs(const SolveArgs& A, int lane, double a_so
     auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
       const double dc = RW(A_DC, r), il = box ? RW(A_IL, r) : 0.0, iu = RW(A_IU, r);
       const bool hl = il > 0.0, hu = iu > 0.0;
-      double c0 = RW(A_G, r) - RW(A_S, r);
+      double c0 = __dmul_rn(dc, gu) - RW(A_S, r);
       if (RS) c0 += RG(G_N, r) - RG(G_P, r);
       const double cprev = first ? c0 : RG(G_CSOC, r);
       const double cs = a_soc * cprev + RG(G_CT, r);
@@ -922,19 +921,22 @@ __device__ __noinline__ void ph_slot(double* cold, int slot, bool save, bool wit
 }
 
 // RestoIterateInitializer: elastic variables from the closed-form minimiser, their multipliers mu / value, bound
-// multipliers min(rho, .), y = 0, reference point x_R = current controls.  A_G holds g of the current point.
+// multipliers min(rho, .), y = 0, reference point x_R = current controls.  LV_X holds the states of the current point.
 template <class L>
 __device__ __noinline__ void ph_resto_init(const SolveArgs& A, int lane, double mu, double* cold) {
   const double rho = A.o.resto_rho, h = mu / (2.0 * rho);
   if (lane <= L::N) {
-#pragma unroll 1
-    for (int r = 0; r < L::R; ++r) {
-      const double c = RW(A_G, r) - RW(A_S, r);
+    double X[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) X[i] = LV(LV_X + i);
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
+      const double c = __dmul_rn(RW(A_DC, r), gu) - RW(A_S, r);
       const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h), pv = c + nv;
       RG(G_N, r) = nv; RG(G_P, r) = pv; RG(G_ZN, r) = mu / nv; RG(G_ZP, r) = mu / pv;
-      if (r < L::NB) RW(A_VL, r) = fmin(rho, RW(A_VL, r));
+      if (box) RW(A_VL, r) = fmin(rho, RW(A_VL, r));
       RW(A_VU, r) = fmin(rho, RW(A_VU, r)); RW(A_Y, r) = 0.0;
-    }
+    };
+    FOR_ROWS(X, body);
 #pragma unroll
     for (int i = 0; i < 6; ++i) { UREF(i) = LV(LV_U + i); LV(LV_ZL + i) = fmin(rho, LV(LV_ZL + i)); LV(LV_ZU + i) = fmin(rho, LV(LV_ZU + i)); }
   }
@@ -945,12 +947,15 @@ template <class L>
 __device__ __noinline__ void ph_resto_np(const SolveArgs& A, int lane, double mu, double* cold) {
   const double rho = A.o.resto_rho, h = mu / (2.0 * rho);
   if (lane <= L::N) {
-#pragma unroll 1
-    for (int r = 0; r < L::R; ++r) {
-      const double c = RW(A_G, r) - RW(A_S, r);
+    double X[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) X[i] = LV(LV_X + i);
+    auto body = [&](const int r, const bool box, const int si, const double gu, double nx, double ny, double iD) {
+      const double c = __dmul_rn(RW(A_DC, r), gu) - RW(A_S, r);
       const double a = h - 0.5 * c, nv = a + sqrt(a * a + c * h);
       RG(G_N, r) = nv; RG(G_P, r) = c + nv; RG(G_DN, r) = 0.0; RG(G_DP, r) = 0.0; RG(G_DY, r) = 0.0;
-    }
+    };
+    FOR_ROWS(X, body);
   }
   __syncwarp();
 }
