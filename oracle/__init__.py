@@ -3,7 +3,9 @@
 PARITY UNPINNED (see nmpc_oracle.cpp / nlp_ref.py headers): the reference has no golden
 vectors and CasADi/IPOPT is not available, so the oracle is pinned only against
   * torch.autograd derivatives of the literal formulas (oracle/nlp_ref.py), and
-  * KKT certificates evaluated independently in tests/.
+  * KKT certificates evaluated independently in tests/, and
+  * oracle/ipm_fullspace.py, a structurally independent restatement of the main loop (full-space KKT system, inertia
+    counted from an LDL^T factorisation, autograd derivatives) that must reproduce the C++ oracle's iteration logs.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.
 """

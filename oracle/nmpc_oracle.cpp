@@ -26,8 +26,18 @@
 //       Linear algebra: the augmented system is reduced by eliminating slacks and multipliers
 //       and solved by a dense Cholesky of the n_w x n_w condensed matrix (inertia of the
 //       augmented matrix is correct  <=>  that matrix is positive definite).
-//   Not restated: IPOPT's restoration phase and watchdog (an instance that would enter
-//   restoration is returned with status RESTORATION_NEEDED and counted as not converged).
+//       Round 2 added what IPOPT does when that line search does not simply succeed, restated
+//       from memory of IPOPT 3.12's sources [3P]: filter details (Compare_le slack, dominated
+//       entries, obj_max_inc, filter resets), tiny-step handling, the watchdog, the soft
+//       restoration phase, the restoration phase proper (MinC_1NrmRestorationPhase with n, p
+//       eliminated; RestoFilterConvergenceCheck; multipliers after restoration) and the slack
+//       safeguard -- with IPOPT's own exits (Maximum_Iterations_Exceeded, Restoration_Failed,
+//       Infeasible_Problem_Detected, Search_Direction_Becomes_Too_Small).
+//   Not restated: iterative refinement / residual-ratio heuristics of PDFullSpaceSolver, the
+//   degeneracy heuristics of PDPerturbationHandler, expect_infeasible_problem, adaptive mu.
+//   Independent check of the main loop: oracle/ipm_fullspace.py (full-space KKT system with a
+//   symmetric-indefinite factorisation and inertia count, derivatives by torch.autograd of the
+//   literal formulas) must reproduce this file's iterates (tests/test_oracle_solve.py).
 //
 // Build:  g++ -O3 -march=native -shared -fPIC -o oracle/_build/libnmpc_oracle.so oracle/nmpc_oracle.cpp -lpthread
 #include <algorithm>
