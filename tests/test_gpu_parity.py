@@ -587,6 +587,23 @@ def test_restoration_outcomes(pkg, oracle_mod):
     assert (ref["status"] == sg).mean() >= 0.8, (ref["status"], sg)
     assert s.work_counters()["resto_calls"] >= B // 2
     assert np.isfinite(sol["x"]).all() and np.all(sol["x"] >= lbx - 1e-12) and np.all(sol["x"] <= ubx + 1e-12)
+    # independent certificate of "Infeasible_Problem_Detected" (as tests/test_oracle_solve.py::
+    # test_infeasible_exit_is_a_local_minimiser_of_the_violation): an LP on the linearised rows around the point the
+    # KERNEL returned finds no direction that decreases the l1 violation
+    from scipy.optimize import linprog
+    n, m = sc.n_w, sc.n_g
+    fu, fl = np.isfinite(ubg), np.isfinite(lbg)
+    for i in np.flatnonzero(sg == 6)[:12]:
+        g = sol["g"][i]
+        J = oracle_mod.evaluate(sp, ob, sol["x"][i], p[i])["J"]
+        theta = np.maximum(lbg - g, 0).sum() + np.maximum(g - ubg, 0).sum()
+        assert theta > 1e-6, (i, theta)
+        A = np.hstack([J, np.eye(m), -np.eye(m)])
+        res = linprog(np.concatenate([np.zeros(n), np.ones(2 * m)]),
+                      A_ub=np.vstack([A[fu], -A[fl]]), b_ub=np.concatenate([(ubg - g)[fu], (g - lbg)[fl]]),
+                      bounds=[(max(lbx[k] - sol["x"][i][k], -1e-2), min(ubx[k] - sol["x"][i][k], 1e-2)) for k in range(n)] + [(0, None)] * (2 * m),
+                      method="highs")
+        assert res.status == 0 and theta - res.fun <= 1e-5 * theta + 1e-8, (i, theta, res.fun)
 
 
 def test_schedule_independence(pkg):
