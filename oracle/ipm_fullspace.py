@@ -40,26 +40,30 @@ EPS = np.finfo(np.float64).eps
 class Problem:
     """The reference NLP of one instance: literal formulas + autograd (nlp_ref), numpy in / numpy out."""
 
-    def __init__(self, spec: nlp_ref.RefSpec, p):
+    def __init__(self, spec, p):
+        """spec: nlp_ref.RefSpec (the Python scripts' NLP) or nlp_ref.RefSpec5 (MATLAB/Dynamic Obstacles/NMPC_TT.m)."""
         self.spec = spec
         self.p = torch.tensor(np.asarray(p, dtype=np.float64))
         self.n, self.m = spec.n_w, spec.n_g
+        five = isinstance(spec, nlp_ref.RefSpec5)
+        self._f = nlp_ref.objective5 if five else nlp_ref.objective
+        self._g = nlp_ref.constraints5 if five else nlp_ref.constraints
 
     def fg(self, x):
         with torch.no_grad():
             w = torch.tensor(x)
-            return float(nlp_ref.objective(self.spec, w, self.p)), nlp_ref.constraints(self.spec, w, self.p).numpy()
+            return float(self._f(self.spec, w, self.p)), self._g(self.spec, w, self.p).numpy()
 
     def derivs(self, x):
         w = torch.tensor(x, requires_grad=True)
-        grad = torch.autograd.grad(nlp_ref.objective(self.spec, w, self.p), w)[0].numpy()
-        J = torch.func.jacrev(lambda ww: nlp_ref.constraints(self.spec, ww, self.p))(torch.tensor(x)).numpy()
+        grad = torch.autograd.grad(self._f(self.spec, w, self.p), w)[0].numpy()
+        J = torch.func.jacrev(lambda ww: self._g(self.spec, ww, self.p))(torch.tensor(x)).numpy()
         return grad, J
 
     def hess(self, x, sigma, lam):
         lt = torch.tensor(lam)
         H = torch.autograd.functional.hessian(
-            lambda ww: sigma * nlp_ref.objective(self.spec, ww, self.p) + (lt * nlp_ref.constraints(self.spec, ww, self.p)).sum(),
+            lambda ww: sigma * self._f(self.spec, ww, self.p) + (lt * self._g(self.spec, ww, self.p)).sum(),
             torch.tensor(x), vectorize=True)
         return H.numpy()
 

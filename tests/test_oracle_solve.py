@@ -296,7 +296,8 @@ FULLSPACE_CASES = [("t_trajectory", 0),      # the T = 0.2 scripts' own cold fir
                    ("nmpc_tt", 4),           # warm-started T = 1 solve
                    ("nmpc_tt", 10),          # 68 iterations, one accepted second-order correction
                    ("race_track_2", 1),      # ten obstacle rows: 240 rows, 570 x 570 full-space system
-                   ("10_obstacles", 2)]
+                   ("10_obstacles", 2),
+                   ("gimbal_less", 0)]       # the other NLP (MATLAB/Dynamic Obstacles/NMPC_TT.m): 45 variables, 32 rows, its script's first solve
 
 
 def _fullspace_case(args):
@@ -311,13 +312,15 @@ def _fullspace_case(args):
     import oracle
     from oracle import ipm_fullspace
     sc = b200nmpc.SCENARIOS[name]
-    sp = oracle.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
-    obs = sc.obstacle_table(); lbx, ubx, lbg, ubg = sc.bounds()
+    five = getattr(sc, "model", 0) == 1
+    sp = oracle.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov, model=1 if five else 0)
+    obs = np.zeros((0, 3)) if five else sc.obstacle_table()
+    lbx, ubx, lbg, ubg = sc.bounds()
     G = np.load(GOLD / f"solves_{name}.npz")
     p, x0 = G["p"][idx], G["x0"][idx]
     lg = oracle.solve_log(sp, obs, p, x0, lbx, ubx, lbg, ubg)
     full = oracle.solve(sp, obs, p[None], x0[None], lbx, ubx, lbg, ubg)
-    rs = nlp_ref.RefSpec(T=sc.T, N=sc.N, obstacles=sc.obstacles, uav_r=sc.uav_r, w1=sc.w1, w2=sc.w2)
+    rs = nlp_ref.RefSpec5(sc.T, sc.N) if five else nlp_ref.RefSpec(T=sc.T, N=sc.N, obstacles=sc.obstacles, uav_r=sc.uav_r, w1=sc.w1, w2=sc.w2)
     log = []
     q = ipm_fullspace.solve(ipm_fullspace.Problem(rs, p), x0, lbx, ubx, lbg, ubg, log=log)
     return dict(name=name, idx=idx, o_status=int(lg["status"]), o_iters=int(lg["iters"]), o_log=lg["log"], o_x=lg["x"], o_f=lg["f"],
@@ -339,7 +342,7 @@ def test_fullspace_ipm_reproduces_oracle_iterates(pkg, oracle_mod):
     import concurrent.futures as cf
     import multiprocessing as mp
     from oracle import STATUS_NAMES
-    with cf.ProcessPoolExecutor(max_workers=min(6, mp.cpu_count()), mp_context=mp.get_context("spawn")) as ex:
+    with cf.ProcessPoolExecutor(max_workers=min(len(FULLSPACE_CASES), mp.cpu_count()), mp_context=mp.get_context("spawn")) as ex:
         results = list(ex.map(_fullspace_case, FULLSPACE_CASES))
     for r in results:
         tag = (r["name"], r["idx"])
