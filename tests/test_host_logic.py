@@ -101,3 +101,82 @@ def test_result_dict_computes_lam_p_on_first_access():
     assert dict(s.items())["lam_p"] == "LP" and s.get("lam_p") == "LP" and s.get("nope", 7) == 7
     t = _Sol(dict(x=1), None)
     assert "lam_p" not in t
+
+
+def test_casadi_recorder_mechanics(pkg, oracle_mod, tmp_path, monkeypatch):
+    """bench/run_casadi.py (the pinning hook) end to end WITHOUT CasADi: a stand-in `casadi` module whose nlpsol is backed
+    by the CPU oracle, and a miniature script with the reference's call shape (NMPC_TT.py:267, :358-365 -- kwargs of
+    DM columns, result dict of DMs, solver.stats()).  Checks what can be checked here: the wrapper records every call and
+    unwraps itself, plotting imports are stubbed, --max-steps stops the script's loop, and the file it writes has the
+    layout tests/test_oracle_solve.py::test_oracle_against_casadi_records and tests/test_gpu_parity.py::test_casadi_records
+    load (so those two become live the day real records exist).  It does NOT pin anything: the numbers are the oracle's."""
+    import importlib.util
+    import sys
+    import types
+    sc = pkg.SCENARIOS["nmpc_tt"]
+    sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov)
+    lbx, ubx, lbg, ubg = sc.bounds()
+
+    class DM:                                                         # the sliver of casadi.DM the recorder and the script use
+        def __init__(self, v):
+            self.a = np.asarray(v.a if isinstance(v, DM) else v, dtype=np.float64).reshape(-1, 1)
+
+        def full(self):
+            return self.a
+
+        def __float__(self):
+            return float(self.a.reshape(-1)[0])
+
+    calls = []
+
+    def nlpsol(name, plugin, prob, opts):
+        assert (name, plugin) == ("solver", "ipopt")
+
+        class Fn:
+            def __call__(self, *, x0, lbx, ubx, lbg, ubg, p):
+                v = lambda d: DM(d).full().reshape(-1)
+                r = oracle_mod.solve(sp, sc.obstacle_table(), v(p)[None], v(x0)[None], v(lbx), v(ubx), v(lbg), v(ubg))
+                self._st = dict(return_status=oracle_mod.STATUS_NAMES[int(r["status"][0])], iter_count=int(r["iters"][0]), success=bool(r["status"][0] == 0))
+                calls.append(1)
+                return {k: DM(r[k][0]) for k in ("x", "f", "g", "lam_x", "lam_g")}
+
+            def stats(self):
+                return self._st
+        return Fn()
+
+    fake = types.ModuleType("casadi")
+    fake.DM, fake.nlpsol, fake.__version__ = DM, nlpsol, "stand-in"
+    monkeypatch.setitem(sys.modules, "casadi", fake)
+    script = tmp_path / "Python" / "NMPC_TT.py"
+    script.parent.mkdir()
+    p0 = list(sc.x_init) + list(sc.target_init)
+    script.write_text(
+        "import casadi as ca\nimport numpy as np\nimport matplotlib.pyplot as plt\nfrom mayavi import mlab\n"
+        "import sys; sys.path.insert(0, %r)\nimport b200nmpc\nsc = b200nmpc.SCENARIOS['nmpc_tt']\n"
+        "lbx, ubx, lbg, ubg = sc.bounds()\nsolver = ca.nlpsol('solver', 'ipopt', {}, {})\n"
+        "p = np.array(%r); u0 = np.zeros(sc.n_w)\n"
+        "if __name__ == '__main__':\n"
+        "    for mpc_iter in range(50):\n"
+        "        sol = solver(x0=ca.DM(u0), lbx=ca.DM(lbx), ubx=ca.DM(ubx), lbg=ca.DM(lbg), ubg=ca.DM(ubg), p=ca.DM(p))\n"
+        "        u0 = np.roll(sol['x'].full().reshape(-1), -6)\n"
+        "    plt.plot([0], [0]); mlab.show()\n" % (str(ROOT), p0))
+    spec = importlib.util.spec_from_file_location("run_casadi", ROOT / "bench" / "run_casadi.py")
+    rc = importlib.util.module_from_spec(spec); spec.loader.exec_module(rc)
+    monkeypatch.setattr(sys, "argv", ["run_casadi.py", "--reference-root", str(tmp_path), "--scripts", "NMPC_TT.py", "--max-steps", "3",
+                                      "--out", str(tmp_path / "golden")])
+    before = set(sys.modules)
+    try:
+        assert rc.main() == 0
+    finally:
+        for k in set(sys.modules) - before:            # the recorder's inert plotting stubs must not outlive this test
+            if isinstance(sys.modules[k], rc._Stub):
+                del sys.modules[k]
+    assert len(calls) == 3 and fake.nlpsol is nlpsol                     # stopped after --max-steps; casadi.nlpsol restored
+    C = np.load(tmp_path / "golden" / "casadi_nmpc_tt.npz", allow_pickle=False)
+    assert C["p"].shape == (3, 11) and C["x0"].shape == (3, sc.n_w) and C["x"].shape == (3, sc.n_w) and C["g"].shape == (3, sc.n_g)
+    assert C["lam_x"].shape == (3, sc.n_w) and C["lam_g"].shape == (3, sc.n_g) and C["f"].shape == (3,)
+    assert C["status"].dtype == np.int32 and C["iters"].dtype == np.int32 and str(C["casadi_version"]) == "stand-in"
+    assert np.array_equal(C["p"][0], np.array(p0)) and not C["x0"][0].any() and np.array_equal(C["x0"][1], np.roll(C["x"][0], -6))
+    # ... and the loader side: the recorded file drives the same comparison the pinning tests run
+    r = oracle_mod.solve(sp, sc.obstacle_table(), C["p"], C["x0"], lbx, ubx, lbg, ubg)
+    assert np.array_equal(r["status"], C["status"]) and np.array_equal(r["iters"], C["iters"]) and np.allclose(r["f"], C["f"], rtol=1e-12)
