@@ -180,3 +180,23 @@ def test_casadi_recorder_mechanics(pkg, oracle_mod, tmp_path, monkeypatch):
     # ... and the loader side: the recorded file drives the same comparison the pinning tests run
     r = oracle_mod.solve(sp, sc.obstacle_table(), C["p"], C["x0"], lbx, ubx, lbg, ubg)
     assert np.array_equal(r["status"], C["status"]) and np.array_equal(r["iters"], C["iters"]) and np.allclose(r["f"], C["f"], rtol=1e-12)
+
+
+def test_plain_c_caller_builds_against_the_header(pkg, tmp_path):
+    """include/nmpc_b200.h is a C header (not only C++) and examples/c_abi_demo.c -- a plain-C closed loop over
+    nmpc_solve_host, no Python / torch / CUDA headers -- compiles and links against libnmpc_b200.so.  Without a GPU the
+    program must fail LOUDLY in nmpc_create (no CPU fallback); with one it prints the known answer of T_Trajectory.py's
+    first solve (its B200 output is committed as profiles/r2/c_abi_demo.log)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "c_abi_demo"
+    libdir = pkg._ffi.LIB_PATH.parent
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-std=c11", "-I", str(ROOT / "include"), "-o", str(exe), str(ROOT / "examples" / "c_abi_demo.c"),
+                           "-L", str(libdir), "-lnmpc_b200", f"-Wl,-rpath,{libdir}", "-lm"])
+    r = subprocess.run([str(exe), "1"], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "f = 248.10109322" in r.stdout, (r.stdout, r.stderr)
+    else:
+        assert r.returncode == 2 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
