@@ -18,11 +18,12 @@ definite") and hand-written or jet derivatives.  Here instead
   * the algorithm state is a handful of numpy vectors; nothing is shared with nmpc_oracle.cpp.
 
 Restated: gradient-based scaling, bound relaxation, DefaultIterateInitializer with least-squares multipliers, monotone
-barrier update, fraction to the boundary, inertia correction, the filter line search with second-order corrections,
-the kappa_sigma multiplier safeguard, the scaled-error convergence test.  NOT restated: watchdog, soft restoration,
-restoration phase, tiny steps -- a solve that needs one of them stops with status "needs_globalisation", and the test
-(tests/test_oracle_solve.py::test_fullspace_ipm_reproduces_oracle_iterates) uses instances on which the C++ oracle's
-own counters say that none of them ran.  Only tests/ may import this module.
+barrier update, fraction to the boundary, inertia correction, the filter line search with second-order corrections and
+the filter-reset heuristic, the watchdog, the soft restoration phase, tiny-step handling, the kappa_sigma multiplier
+safeguard, the scaled-error convergence test.  NOT restated: the restoration phase proper (a solve that needs it stops
+with status "needs_restoration" -- the test checks that this happens at the iteration where the C++ oracle enters it) and
+the slack safeguard ("needs_slack_safeguard").  tests/test_oracle_solve.py::test_fullspace_ipm_reproduces_oracle_iterates
+compares iteration logs with the C++ oracle.  Only tests/ may import this module.
 """
 from __future__ import annotations
 
@@ -88,9 +89,10 @@ def _inertia(K):
     return pos, neg, zero
 
 
-def solve(prob: Problem, x0, lbx, ubx, lbg, ubg, *, max_iter=100, tol=1e-8, log=None):
+def solve(prob: Problem, x0, lbx, ubx, lbg, ubg, *, max_iter=100, tol=1e-8, log=None, events=None):
     """One cold-started solve.  Returns dict(status, iters, x, f, lam_x, lam_g); log (a list) receives one tuple
-    (mu, f, inf_pr, inf_du, dw, alpha_pr, alpha_du, trial points) per iteration, as IPOPT's iteration output would."""
+    (mu, f, inf_pr, inf_du, dw, alpha_pr, alpha_du, trial points) per iteration, as IPOPT's iteration output would;
+    events (a list) receives (iteration, what) whenever a globalisation heuristic acts."""
     n, m = prob.n, prob.m
     # options (IPOPT 3.12 defaults unless the scripts set them)
     dual_inf_tol, constr_viol_tol, compl_inf_tol = 1.0, 1e-4, 1e-4
@@ -184,26 +186,61 @@ def solve(prob: Problem, x0, lbx, ubx, lbg, ubg, *, max_iter=100, tol=1e-8, log=
         viol = max(np.where(np.abs(lbg) < 1e19, lbg - gu, -np.inf).max(), np.where(np.abs(ubg) < 1e19, gu - ubg, -np.inf).max(), 0.0)
         return E <= tol and du / df <= dual_inf_tol and viol <= constr_viol_tol and co / df <= compl_inf_tol
 
+    # ---------------------------------------------------------------------------------------------------------------
+    # algorithm state.  P = the current iterate with everything evaluated at it.
+    P = dict(x=x, s=s, y=y, zl=zl, zu=zu, f=f, g=g, grad=grad, J=J)
     filt: list[tuple[float, float]] = []
     theta_max = theta_min = None
     dw_last = 0.0
     tau = max(tau_min, 1.0 - mu)
+    last_rej_filter, succ_filter_rej, n_filter_resets = False, 0, 0            # filter reset heuristic
+    in_watchdog, wd_short, wd_trial, wd = False, 0, 0, None                      # watchdog
+    in_soft, soft_cnt = False, 0                                                 # soft restoration phase
+    tiny_last, tiny_flag = False, False                                          # tiny-step handling
+    counters = dict(watchdog_starts=0, soft_resto_steps=0, filter_resets=0, tiny_steps=0)
     it = 0
-    status = None
-    while status is None:
-        if converged():
+
+    def ftb(vals, steps, mask, tau_):
+        neg = mask & (steps < 0)
+        return min(1.0, (-tau_ * vals[neg] / steps[neg]).min(initial=1.0))
+
+    def err_at(Q, mu_):
+        return errors(Q["x"], Q["s"], Q["y"], Q["zl"], Q["zu"], Q["g"], Q["grad"], Q["J"], mu_)
+
+    def pd_error(Q, mu_):
+        """IpoptCalculatedQuantities::*_primal_dual_system_error: averaged 1-norms (soft restoration test)"""
+        a_, c_ = slacks(Q["x"], Q["s"])
+        du = np.abs(Q["grad"] + Q["J"].T @ Q["y"] - Q["zl"][:n] + Q["zu"][:n]).sum() + np.abs(-Q["y"] - Q["zl"][n:] + Q["zu"][n:]).sum()
+        pr = np.abs(Q["g"] - Q["s"]).sum()
+        co = np.abs(a_ * Q["zl"] - mu_)[LO].sum() + np.abs(c_ * Q["zu"] - mu_)[UP].sum()
+        nb = int(LO.sum() + UP.sum())
+        return du / (n + m) + pr / m + co / nb
+
+    while True:
+        # ---- OptimalityErrorConvergenceCheck
+        du0, pr0, co0, E0 = err_at(P, 0.0)
+        gu = P["g"] / dc
+        viol = max(np.where(np.abs(lbg) < 1e19, lbg - gu, -np.inf).max(), np.where(np.abs(ubg) < 1e19, gu - ubg, -np.inf).max(), 0.0)
+        if E0 <= tol and du0 / df <= dual_inf_tol and viol <= constr_viol_tol and co0 / df <= compl_inf_tol:
             status = "Solve_Succeeded"; break
         if it >= max_iter:
             status = "Maximum_Iterations_Exceeded"; break
-        # ---- monotone barrier update (MonotoneMuUpdate, mu_allow_fast_monotone_decrease)
+        # ---- MonotoneMuUpdate (mu_allow_fast_monotone_decrease); a second tiny step in a row forces mu down
         mu_floor = min(tol, df * compl_inf_tol) / (kappa_eps + 1.0)
-        while errors(x, s, y, zl, zu, g, grad, J, mu)[3] <= kappa_eps * mu:
+        tf, tiny_flag, done = tiny_flag, False, False
+        while (err_at(P, mu)[3] <= kappa_eps * mu or tf) and not done:
             new = max(mu_floor, min(kappa_mu * mu, mu ** theta_mu))
             if new == mu:
+                if tf:
+                    return dict(status="Search_Direction_Becomes_Too_Small", iters=it, counters=counters)
                 break
-            mu = new; tau = max(tau_min, 1.0 - mu); filt = []
-        du0, pr0, _, _ = errors(x, s, y, zl, zu, g, grad, J, 0.0)
-        # ---- search direction from the full-space system, inertia from the spectrum
+            mu = new; tau = max(tau_min, 1.0 - mu)
+            if tf:
+                done, tf = True, False
+            in_soft, soft_cnt = False, 0                                         # BacktrackingLineSearch::Reset
+            filt, last_rej_filter, succ_filter_rej = [], False, 0                # FilterLSAcceptor::Reset
+        # ---- search direction from the full-space system, inertia counted from the LDL^T pivots
+        x, s, y, zl, zu, f, g, grad, J = (P[k] for k in ("x", "s", "y", "zl", "zu", "f", "g", "grad", "J"))
         a, c = slacks(x, s)
         sig = np.where(LO, zl / a, 0.0) + np.where(UP, zu / c, 0.0)
         gphi = np.concatenate([grad, np.zeros(m)]) - np.where(LO, mu / a, 0.0) + np.where(UP, mu / c, 0.0) \
@@ -225,108 +262,228 @@ def solve(prob: Problem, x0, lbx, ubx, lbg, ubg, *, max_iter=100, tol=1e-8, log=
             else:
                 dw = (k_first if (dw_last == 0.0 or 1e5 * dw_last < dw) else k_inc) * dw
             if dw > dw_max:
-                return dict(status="needs_globalisation", iters=it, why="inertia")
+                return dict(status="needs_restoration", iters=it, why="inertia", counters=counters)
         if dw > 0:
             dw_last = dw
 
-        def direction(cres):
-            sol = np.linalg.solve(K, -np.concatenate([rhs1, cres]))
-            dv, dy_ = sol[:n + m], sol[n + m:]
-            dzl = np.where(LO, (mu - zl * dv) / a - zl, 0.0)
-            dzu = np.where(UP, (mu + zu * dv) / c - zu, 0.0)
-            return dv, dy_, dzl, dzu
-
-        def ftb(vals, steps, mask):
-            neg = mask & (steps < 0)
-            return min(1.0, (-tau * vals[neg] / steps[neg]).min(initial=1.0))
+        def direction(cres_, K=K, rhs1=rhs1, a=a, c=c, zl=zl, zu=zu, mu=mu):
+            sol = np.linalg.solve(K, -np.concatenate([rhs1, cres_]))
+            dv_, dy_ = sol[:n + m], sol[n + m:]
+            return dict(v=dv_, y=dy_, zl=np.where(LO, (mu - zl * dv_) / a - zl, 0.0), zu=np.where(UP, (mu + zu * dv_) / c - zu, 0.0))
 
         cres = g - s
-        dv, dy, dzl, dzu = direction(cres)
-        a_max = min(ftb(a, dv, LO), ftb(c, -dv, UP))
-        # ---- filter line search (BacktrackingLineSearch + FilterLSAcceptor)
-        theta = np.abs(cres).sum()
-        phi = barrier(x, s, f, mu)
-        gbd = float(gphi @ dv)
+        step = direction(cres)
+
+        def a_max_of(stp, Q=None):
+            Q = P if Q is None else Q                                            # (P is looked up at call time: the watchdog may restore it)
+            a_, c_ = slacks(Q["x"], Q["s"])
+            return min(ftb(a_, stp["v"], LO, tau), ftb(c_, -stp["v"], UP, tau))
+
+        def a_dual_of(stp, Q=None):
+            Q = P if Q is None else Q
+            return min(ftb(Q["zl"], stp["zl"], LO, tau), ftb(Q["zu"], stp["zu"], UP, tau))
+
+        # ---- BacktrackingLineSearch::FindAcceptableTrialPoint ---------------------------------------------------------
+        cur_theta = np.abs(cres).sum()
+        if not in_watchdog:                                                      # InitThisLineSearch
+            if n_filter_resets < 5:                                              # filter reset heuristic (max_filter_resets = 5)
+                if last_rej_filter:
+                    succ_filter_rej += 1
+                    if succ_filter_rej >= 5:                                     # filter_reset_trigger
+                        filt, last_rej_filter, succ_filter_rej = [], False, 0
+                        n_filter_resets += 1; counters["filter_resets"] += 1
+                        if events is not None:
+                            events.append((it, "filter_reset"))
+                else:
+                    succ_filter_rej = 0
+            last_rej_filter = False
+            ref = dict(theta=cur_theta, phi=barrier(x, s, f, mu), gbd=float(gphi @ step["v"]))
+        else:
+            ref = wd["ref"]
         if theta_max is None:
-            theta_max = 1e4 * max(1.0, theta); theta_min = 1e-4 * max(1.0, theta)
+            theta_max = 1e4 * max(1.0, ref["theta"]); theta_min = 1e-4 * max(1.0, ref["theta"])
 
         def ftype(al):
-            if theta == 0.0 and 0.0 < gbd < 100.0 * EPS:
+            if ref["theta"] == 0.0 and 0.0 < ref["gbd"] < 100.0 * EPS:
                 return True
-            return gbd < 0 and al * (-gbd) ** s_phi > delta * theta ** s_theta
+            return ref["gbd"] < 0 and al * (-ref["gbd"]) ** s_phi > delta * ref["theta"] ** s_theta
 
         def armijo(al, phi_t):
-            return _cmp_le(phi_t - phi, eta_phi * al * gbd, phi)
+            return _cmp_le(phi_t - ref["phi"], eta_phi * al * ref["gbd"], ref["phi"])
 
         def acceptable(al, phi_t, th_t):
+            nonlocal last_rej_filter
             if not (math.isfinite(phi_t) and math.isfinite(th_t)) or th_t > theta_max:
                 return False
-            if ftype(al) and theta <= theta_min:
+            if al > 0.0 and ftype(al) and ref["theta"] <= theta_min:
                 ok = armijo(al, phi_t)
             else:
-                if phi_t > phi:
-                    bas = math.log10(abs(phi)) if abs(phi) > 10.0 else 1.0
-                    if math.log10(phi_t - phi) > obj_max_inc + bas:
-                        return False
-                ok = _cmp_le(th_t, (1 - g_theta) * theta, theta) or _cmp_le(phi_t - phi, -g_phi * theta, phi)
-            return ok and all(_cmp_le(phi_t, fb, fb) or _cmp_le(th_t, ft, ft) for fb, ft in filt)
+                ok = True
+                if phi_t > ref["phi"]:
+                    bas = math.log10(abs(ref["phi"])) if abs(ref["phi"]) > 10.0 else 1.0
+                    ok = not (math.log10(phi_t - ref["phi"]) > obj_max_inc + bas)
+                ok = ok and (_cmp_le(th_t, (1 - g_theta) * ref["theta"], ref["theta"]) or _cmp_le(phi_t - ref["phi"], -g_phi * ref["theta"], ref["phi"]))
+            if not ok:
+                last_rej_filter = False
+                return False
+            ok = all(_cmp_le(phi_t, fb, fb) or _cmp_le(th_t, ft, ft) for fb, ft in filt)
+            if not ok:
+                last_rej_filter = True
+            return ok
 
-        a_min = g_theta
-        if gbd < 0:
-            a_min = min(g_theta, g_phi * theta / (-gbd))
-            if theta <= theta_min:
-                a_min = min(a_min, delta * theta ** s_theta / (-gbd) ** s_phi)
-        a_min *= a_min_frac
-
-        def trial(al, step):
-            xt = x + al * step[:n]; st_ = s + al * step[n:]
-            ft, gt = fg(xt)
-            return xt, st_, ft, gt, np.abs(gt - st_).sum(), barrier(xt, st_, ft, mu)
-
-        alpha, n_trials, shortened, accepted = a_max, 0, 0, None
-        step = (dv, dy, dzl, dzu)
-        while alpha > a_min or shortened == 0:
-            xt, st_, ft, gt, th_t, phi_t = trial(alpha, step[0]); n_trials += 1
-            if acceptable(alpha, phi_t, th_t):
-                accepted = (alpha, xt, st_, ft, gt, phi_t); break
-            if alpha == a_max and theta <= th_t and math.isfinite(phi_t):
-                # second-order correction: same matrix, constraint residual alpha * c + c(trial), accumulated
-                csoc, a_soc, th_old, cnt = cres.copy(), alpha, 0.0, 0
-                th_soc, g_soc, s_soc = th_t, gt, st_
-                while cnt < max_soc and accepted is None and (cnt == 0 or th_soc <= kappa_soc * th_old):
-                    th_old = th_soc
-                    csoc = a_soc * csoc + (g_soc - s_soc)
-                    stp = direction(csoc)
-                    a_soc = min(ftb(a, stp[0], LO), ftb(c, -stp[0], UP))
-                    xt, st_, ft, gt, th_t2, phi_t2 = trial(a_soc, stp[0]); n_trials += 1
-                    if not math.isfinite(phi_t2):
-                        break
-                    if acceptable(alpha, phi_t2, th_t2):
-                        accepted = (a_soc, xt, st_, ft, gt, phi_t2); step = stp
-                    else:
-                        cnt += 1; th_soc, g_soc, s_soc = th_t2, gt, st_
-                if accepted is not None:
-                    break
-            alpha *= 0.5; shortened += 1
-        if accepted is None:
-            return dict(status="needs_globalisation", iters=it, why="line search")
-        a_pr, xt, st_, ft, gt, phi_t = accepted
-        f_before = f
-        if not (ftype(alpha) and armijo(alpha, phi_t)):       # not an Armijo-accepted f-type step: augment the filter
-            ne = (phi - g_phi * theta, (1 - g_theta) * theta)
+        def augment_filter():
+            nonlocal filt
+            ne = (ref["phi"] - g_phi * ref["theta"], (1 - g_theta) * ref["theta"])
             filt = [e for e in filt if not (e[0] >= ne[0] and e[1] >= ne[1])] + [ne]
-        dv, dy, dzl, dzu = step
-        a_du = min(ftb(zl, dzl, LO), ftb(zu, dzu, UP))
-        y = y + a_pr * dy
-        zl = zl + a_du * dzl; zu = zu + a_du * dzu
-        x, s, f, g = xt, st_, ft, gt
-        # kappa_sigma safeguard (IpoptAlgorithm::correct_bound_multiplier)
-        a, c = slacks(x, s)
-        zl = np.where(LO, np.maximum(np.minimum(zl, kappa_sigma * mu / a), mu / (kappa_sigma * a)), 0.0)
-        zu = np.where(UP, np.maximum(np.minimum(zu, kappa_sigma * mu / c), mu / (kappa_sigma * c)), 0.0)
-        grad, J = derivs(x)
+
+        def trial(al, stp, Q=None):
+            Q = P if Q is None else Q
+            xt = Q["x"] + al * stp["v"][:n]; st_ = Q["s"] + al * stp["v"][n:]
+            ft, gt = fg(xt)
+            return dict(x=xt, s=st_, f=ft, g=gt, theta=np.abs(gt - st_).sum(), phi=barrier(xt, st_, ft, mu))
+
+        n_trials = 0
+
+        def backtrack(stp, Q, skip_first):
+            """DoBacktrackingLineSearch from iterate Q along stp.  Returns (trial point or None, alpha_primal, step used, shortened)."""
+            nonlocal n_trials
+            a_max = a_max_of(stp, Q)
+            if in_watchdog:
+                a_min, a_test = a_max, wd["alpha_test"]
+            else:
+                a_min = g_theta
+                if ref["gbd"] < 0:
+                    a_min = min(g_theta, g_phi * ref["theta"] / (-ref["gbd"]))
+                    if ref["theta"] <= theta_min:
+                        a_min = min(a_min, delta * ref["theta"] ** s_theta / (-ref["gbd"]) ** s_phi)
+                a_min *= a_min_frac
+                a_test = a_max
+            alpha, shortened, got, used = a_max, 0, None, stp
+            if skip_first:
+                alpha *= 0.5
+            while alpha > a_min or shortened == 0:
+                t = trial(alpha, stp, Q); n_trials += 1
+                if not in_watchdog:
+                    a_test = alpha
+                if acceptable(a_test, t["phi"], t["theta"]):
+                    got = t; break
+                if in_watchdog:
+                    break
+                if alpha == a_max and ref["theta"] <= t["theta"] and math.isfinite(t["phi"]):
+                    # second-order correction: same matrix, constraint residual alpha * c + c(trial), accumulated
+                    csoc, a_soc, th_old, cnt, ts = cres.copy(), alpha, 0.0, 0, t
+                    while cnt < max_soc and got is None and (cnt == 0 or ts["theta"] <= kappa_soc * th_old):
+                        th_old = ts["theta"]
+                        csoc = a_soc * csoc + (ts["g"] - ts["s"])
+                        sstep = direction(csoc)
+                        a_soc = a_max_of(sstep, Q)
+                        ts = trial(a_soc, sstep, Q); n_trials += 1
+                        if not math.isfinite(ts["phi"]):
+                            break
+                        if acceptable(a_test, ts["phi"], ts["theta"]):
+                            got, used, alpha = ts, sstep, a_soc
+                        else:
+                            cnt += 1
+                    if got is not None:
+                        break
+                alpha *= 0.5; shortened += 1
+            if got is not None and not (ftype(a_test) and armijo(a_test, got["phi"])):
+                augment_filter()                                                 # not an Armijo-accepted f-type step
+            return got, alpha, used, shortened
+
+        def soft_step(stp):
+            """TrySoftRestoStep: equal primal and dual step lengths; accepted if the original criterion holds at alpha_test = 0
+            or the averaged primal-dual error shrinks by soft_resto_pderror_reduction_factor."""
+            al = min(a_max_of(stp), a_dual_of(stp))
+            t = trial(al, stp)
+            if not (math.isfinite(t["phi"]) and math.isfinite(t["theta"])):
+                return None, al, False
+            t.update(y=y + al * stp["y"], zl=zl + al * stp["zl"], zu=zu + al * stp["zu"])
+            if acceptable(0.0, t["phi"], t["theta"]):
+                return t, al, True
+            t["grad"], t["J"] = derivs(t["x"])
+            if pd_error(t, mu) <= (1.0 - 1e-4) * pd_error(P, mu):
+                counters["soft_resto_steps"] += 1
+                return t, al, False
+            return None, al, False
+
+        dvm = step["v"]
+        vcur = np.concatenate([x, s])
+        tiny = bool((np.abs(dvm) / (1.0 + np.abs(vcur)) <= 10.0 * EPS).all() and cur_theta <= 1e-4)
+        if in_watchdog and tiny:       # StopWatchDog here would re-enter the line search at the stored point WITH second-order
+            # corrections, i.e. with a fresh factorisation there: rare (never seen), not restated
+            return dict(status="needs_globalisation", iters=it, why="tiny step inside the watchdog", counters=counters)
+        if not in_watchdog and not tiny and not in_soft and wd_short >= 10:     # StartWatchDog (watchdog_shortened_iter_trigger)
+            in_watchdog, wd_trial = True, 0
+            wd = dict(P=P, step=step, dw=dw, ref=ref, alpha_test=a_max_of(step))
+            counters["watchdog_starts"] += 1
+            if events is not None:
+                events.append((it, "watchdog_start"))
+        got, a_pr, used, shortened, dual_done = None, 0.0, step, 0, False
+        if tiny:
+            counters["tiny_steps"] += 1
+            a_pr = a_max_of(step)
+            got = trial(a_pr, step); n_trials += 1
+            if tiny_last:
+                tiny_flag = True
+            tiny_last = bool(np.abs(step["y"]).max() < 1e-2)                     # tiny_step_y_tol
+        else:
+            tiny_last = False
+            if in_soft:
+                soft_cnt += 1
+                if soft_cnt <= 10:                                               # max_soft_resto_iters
+                    got, a_pr, sat = soft_step(step)
+                    dual_done = got is not None
+                    if got is not None and sat:
+                        in_soft, soft_cnt, dual_done, a_pr = False, 0, False, 0.0     # IPOPT then repeats the dual step with alpha_primal = 0
+            else:
+                skip_first = False
+                while True:
+                    got, a_pr, used, shortened = backtrack(step, P, skip_first)
+                    if not in_watchdog:
+                        break
+                    if got is not None:
+                        in_watchdog = False; break
+                    wd_trial += 1
+                    if wd_trial > 3:                                             # watchdog_trial_iter_max: back to the stored point
+                        P, step, dw, in_watchdog, wd_short = wd["P"], wd["step"], wd["dw"], False, 0
+                        x, s, y, zl, zu, f, g, grad, J = (P[k] for k in ("x", "s", "y", "zl", "zu", "f", "g", "grad", "J"))
+                        cres = g - s
+                        ref = wd["ref"]
+                        skip_first = True
+                        continue
+                    got = trial(a_pr, step)                                     # accept the full step without test
+                    break
+        if got is None:
+            if not in_soft:                                                      # the current direction as a soft restoration step
+                augment_filter()
+                got, a_pr, sat = soft_step(step)
+                if got is not None:
+                    dual_done = True
+                    if sat:
+                        dual_done, a_pr = False, 0.0
+                    else:
+                        in_soft = True
+            if got is None:
+                return dict(status="needs_restoration", iters=it, why="line search", counters=counters)
+        f_before = P["f"]
+        if not dual_done:
+            a_du = a_dual_of(used)
+            got.update(y=y + a_pr * used["y"], zl=zl + a_du * used["zl"], zu=zu + a_du * used["zu"])
+            wd_short = 0 if shortened == 0 else wd_short + 1
+        else:
+            a_du = a_pr
+        # ---- AcceptTrialPoint: kappa_sigma safeguard (the slack safeguard is not restated: stop if it would act)
+        a, c = slacks(got["x"], got["s"])
+        if (a[LO] < EPS * min(1.0, mu)).any() or (c[UP] < EPS * min(1.0, mu)).any():
+            return dict(status="needs_slack_safeguard", iters=it, counters=counters)
+        got["zl"] = np.where(LO, np.maximum(np.minimum(got["zl"], kappa_sigma * mu / a), mu / (kappa_sigma * a)), 0.0)
+        got["zu"] = np.where(UP, np.maximum(np.minimum(got["zu"], kappa_sigma * mu / c), mu / (kappa_sigma * c)), 0.0)
+        got["grad"], got["J"] = derivs(got["x"])
+        P = {k: got[k] for k in ("x", "s", "y", "zl", "zu", "f", "g", "grad", "J")}
         if log is not None:
             log.append((mu, f_before / df, pr0, du0, dw, a_pr, a_du, n_trials))
         it += 1
-    xo = np.minimum(np.maximum(x, lbx), ubx)                     # honor_original_bounds
-    return dict(status=status, iters=it, x=xo, f=prob.fg(xo)[0], lam_x=(zu[:n] - zl[:n]) / df, lam_g=y * dc / df)
+    xo = np.minimum(np.maximum(P["x"], lbx), ubx)                # honor_original_bounds
+    return dict(status=status, iters=it, x=xo, f=prob.fg(xo)[0], lam_x=(P["zu"][:n] - P["zl"][:n]) / df, lam_g=P["y"] * dc / df,
+                counters=counters)
