@@ -79,6 +79,33 @@ def test_casadi_records(pkg, name):
     assert np.all(np.abs(sol["x"][ok, :6] - C["x"][ok, :6]).max(axis=1) <= U0_RTOL * np.abs(C["x"][ok, :6]).max(axis=1))
 
 
+def test_fullspace_fixtures(pkg):
+    """The kernel against solutions computed by the INDEPENDENT full-space restatement of IPOPT's algorithm
+    (oracle/ipm_fullspace.py -- full-space KKT system, LDL^T inertia count, autograd derivatives; fixture
+    tests/golden/fullspace_solves.npz made by tests/golden/make_fullspace_golden.py), i.e. against an implementation that
+    shares no code with the C++ oracle the other tests use: same return status, f* rel 1e-8, u0* rel 1e-6, multipliers."""
+    F = np.load(GOLD / "fullspace_solves.npz")
+    same_iters = 0
+    for k, (name, idx) in enumerate(zip(F["names"], F["idx"])):
+        name = str(name)
+        sc = pkg.SCENARIOS[name]
+        G = np.load(GOLD / f"solves_{name}.npz")
+        s = pkg.nlpsol("solver", "ipm", sc, max_batch=1)
+        lbx, ubx, lbg, ubg = sc.bounds()
+        sol = s(x0=G["x0"][idx][None], p=G["p"][idx][None], lbx=lbx, ubx=ubx, lbg=lbg, ubg=ubg)
+        st = s.stats()
+        assert int(st["return_status"][0]) == int(F["status"][k]), (name, idx, st["return_status"], F["status"][k])
+        same_iters += int(st["iter_count"][0]) == int(F["iters"][k])
+        if F["status"][k] == 0:
+            x = F[f"x_{k}"]
+            assert abs(sol["f"][0] - F["f"][k]) <= F_RTOL * abs(F["f"][k]), (name, idx)
+            nu = sc.nu
+            assert np.abs(sol["x"][0][:nu] - x[:nu]).max() <= U0_RTOL * np.abs(x[:nu]).max(), (name, idx)
+            lg = F[f"lam_g_{k}"]
+            assert np.abs(sol["lam_g"][0] - lg).max() <= 1e-3 * max(1.0, np.abs(lg).max()), (name, idx)
+    assert same_iters >= len(F["idx"]) - 2, same_iters
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_golden_fixtures(pkg, name):
     """Committed oracle solutions (first closed-loop steps of each reference script + seeded instances)."""

@@ -402,3 +402,24 @@ def test_fullspace_ipm_reproduces_oracle_iterates(pkg, oracle_mod):
     assert any(r["o_status"] == 1 for r in results) and any(r["o_log"][:, 4].max() > 0 for r in results)   # max_iter run; inertia corrections
     assert sum(r["q_counters"]["watchdog_starts"] for r in results) >= 10                          # watchdog phases ...
     assert any(r["q_counters"]["filter_resets"] for r in results) and any(r["q_counters"]["soft_resto_steps"] for r in results)
+
+
+def test_fullspace_fixture_matches_oracle(pkg, oracle_mod):
+    """tests/golden/fullspace_solves.npz holds solutions computed by the independent full-space restatement
+    (tests/golden/make_fullspace_golden.py); the C++ oracle returns the same status, iteration count, f*, x* and multipliers on
+    those instances (the GPU suite compares the kernel with the same file)."""
+    F = np.load(GOLD / "fullspace_solves.npz")
+    for k, (name, idx) in enumerate(zip(F["names"], F["idx"])):
+        name = str(name)
+        sc = pkg.SCENARIOS[name]
+        sp = oracle_mod.make_spec(sc.T, sc.N, sc.n_obs, sc.w1, sc.w2, sc.vfov, sc.hfov, model=sc.model)
+        obs = np.zeros((0, 3)) if sc.model == 1 else sc.obstacle_table()
+        G = np.load(GOLD / f"solves_{name}.npz")
+        r = oracle_mod.solve(sp, obs, G["p"][idx][None], G["x0"][idx][None], *sc.bounds())
+        assert r["status"][0] == F["status"][k] and r["iters"][0] == F["iters"][k], (name, idx)
+        conv = F["status"][k] == 0
+        assert abs(r["f"][0] - F["f"][k]) <= (1e-11 if conv else 1e-7) * abs(F["f"][k]), (name, idx)
+        assert np.abs(r["x"][0] - F[f"x_{k}"]).max() <= (1e-8 if conv else 1e-4), (name, idx)
+        if conv:
+            assert np.abs(r["lam_g"][0] - F[f"lam_g_{k}"]).max() <= 1e-7 * max(1.0, np.abs(F[f"lam_g_{k}"]).max()), (name, idx)
+            assert np.abs(r["lam_x"][0] - F[f"lam_x_{k}"]).max() <= 1e-7 * max(1.0, np.abs(F[f"lam_x_{k}"]).max()), (name, idx)
