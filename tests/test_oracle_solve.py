@@ -36,6 +36,8 @@ def test_oracle_against_casadi_records(pkg, oracle_mod, name):
     r = oracle_mod.solve(sp, obs, C["p"], C["x0"], lbx, ubx, lbg, ubg)
     assert np.array_equal(r["status"], C["status"]), (r["status"], C["status"])
     ok = C["status"] == 0
+    # (a uniform f* mismatch of 1 ... 2e-8 would point at the evaluation point of sol['f'] -- projected vs unprojected final
+    #  iterate, DESIGN.md section 5 "known candidate deviation" -- not at the iterates)
     assert np.all(np.abs(r["f"][ok] - C["f"][ok]) <= 1e-8 * np.abs(C["f"][ok]))
     assert np.all(np.abs(r["x"][ok, :6] - C["x"][ok, :6]).max(axis=1) <= 1e-6 * np.abs(C["x"][ok, :6]).max(axis=1))
     assert (np.abs(r["iters"][ok] - C["iters"][ok]) <= 2).mean() >= 0.9
